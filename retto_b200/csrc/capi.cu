@@ -1,0 +1,108 @@
+// capi.cu — context lifetime, memory helpers and configuration defaults of the C ABI
+// (include/retto_b200.h).  Stage entry points live next to their kernels.
+#include "common.cuh"
+
+extern "C" int32_t retto_b200_abi_version(void) { return RETTO_B200_ABI_VERSION; }
+
+extern "C" void retto_b200_config_default(retto_b200_config* c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->max_side_len = 2000;                 // session.rs:33
+    c->min_side_len = 30;                   // session.rs:34
+    c->det_limit_side_len = 736;            // det_processor.rs:78
+    c->det_limit_type = 0;                  // LimitType::Min
+    for (int i = 0; i < 3; ++i) { c->det_mean[i] = 0.5f; c->det_std[i] = 0.5f; }
+    c->det_scale = 1.0f / 255.0f;           // 1f32 / 255.0
+    c->det_thresh = 0.3f;
+    c->det_box_thresh = 0.5f;
+    c->det_max_candidates = 1000;
+    c->det_unclip_ratio = 1.6f;
+    c->det_use_dilation = 1;
+    c->det_score_mode = 1;                  // ScoreMode::Fast
+    c->det_min_mini_box_size = 3;
+    c->det_dilation_2x2 = 1;
+    c->cls_image_shape[0] = 3; c->cls_image_shape[1] = 48; c->cls_image_shape[2] = 192;  // cls_processor.rs:30
+    c->cls_batch_num = 6;
+    c->cls_thresh = 0.9f;
+    c->cls_label[0] = 0; c->cls_label[1] = 180;
+    c->rec_image_shape[0] = 3; c->rec_image_shape[1] = 48; c->rec_image_shape[2] = 320;  // rec_processor.rs:132
+    c->rec_batch_num = 6;
+    c->max_components_per_page = 16384;
+    c->max_det_side = 4096;
+}
+
+extern "C" retto_b200_status retto_b200_create(int32_t device_id, const retto_b200_config* cfg, retto_b200_ctx** out) {
+    if (!out) return RETTO_B200_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n) return RETTO_B200_ERR_CUDA;
+    if (cudaSetDevice(device_id) != cudaSuccess) return RETTO_B200_ERR_CUDA;
+    retto_b200_ctx* c = new retto_b200_ctx();
+    c->device = device_id;
+    if (cfg) c->cfg = *cfg; else retto_b200_config_default(&c->cfg);
+    if (c->cfg.max_components_per_page <= 0) c->cfg.max_components_per_page = 16384;
+    if (c->cfg.max_det_side <= 0) c->cfg.max_det_side = 4096;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RETTO_B200_ERR_CUDA; }
+    *out = c;
+    return RETTO_B200_OK;
+}
+
+extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStream_t s = c->stream;
+    delete c;  // DevBuf / HostBuf members free their memory
+    cudaStreamDestroy(s);
+}
+
+extern "C" const char* retto_b200_last_error(const retto_b200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" void* retto_b200_stream(retto_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" uint64_t retto_b200_launch_count(const retto_b200_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" retto_b200_status retto_b200_sync(retto_b200_ctx* c) {
+    if (!c) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return RETTO_B200_OK;
+}
+
+extern "C" retto_b200_status retto_b200_dev_alloc(retto_b200_ctx* c, size_t bytes, void** d_out) {
+    if (!c || !d_out) return RETTO_B200_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { c->set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return RETTO_B200_ERR_OOM; }
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_dev_free(retto_b200_ctx* c, void* p) {
+    if (!c) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    RT_CUDA_OK(c, cudaFree(p));
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_host_alloc(retto_b200_ctx* c, size_t bytes, void** h_out) {
+    if (!c || !h_out) return RETTO_B200_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostAlloc(h_out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { c->set_error(std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return RETTO_B200_ERR_OOM; }
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_host_free(retto_b200_ctx* c, void* p) {
+    if (!c) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaFreeHost(p));
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_h2d(retto_b200_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
+    if (!c) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_d2h(retto_b200_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+    if (!c) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return RETTO_B200_OK;
+}
+
+retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {
+    RT_CUDA_OK(ctx, dst.ensure(bytes ? bytes : 16, ctx->stream));
+    if (bytes) RT_CUDA_OK(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return RETTO_B200_OK;
+}

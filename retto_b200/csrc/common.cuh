@@ -1,0 +1,191 @@
+// common.cuh — context, buffers and launch helpers shared by the kernels of libretto_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/retto_b200.h"
+
+#define RT_CUDA_OK(ctx, expr)                                                                    \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+            return RETTO_B200_ERR_CUDA;                                                          \
+        }                                                                                        \
+    } while (0)
+
+#define RT_TRY(expr)                                   \
+    do {                                               \
+        retto_b200_status _s = (expr);                 \
+        if (_s != RETTO_B200_OK) return _s;            \
+    } while (0)
+
+// growable device buffer (never shrinks; growth synchronises the stream)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t ensure(size_t bytes, cudaStream_t s) {
+        if (bytes <= cap) return cudaSuccess;
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    HostBuf() = default;
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    ~HostBuf() { release(); }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ---- device-side descriptors ------------------------------------------------------------------
+struct DetPostPage {       // one page of a det_postprocess batch
+    const float* prob;
+    int h, w, ori_h, ori_w;
+    int strips, rowblocks;   // tile grid: 128 px x 16 rows
+    int tile_base;           // first tile index of this page in the flat tile list
+    long long px_base;       // first pixel of this page in the flat bitmap / label arrays
+    int comp_base;           // first slot of this page in the component tables
+    int box_base;            // first slot in the candidate box table
+};
+
+struct PageCounters {      // per page, zeroed before each det_postprocess
+    int n_roots;
+    int euler;               // #components - #holes of the dilated bitmap
+    int n_boxes;
+    int status;
+    int row_total;           // rows allocated in the row-extreme table
+    int pad[3];
+};
+
+struct CompRec {           // per connected component (dense id)
+    int root;                // min linear index (page-local)
+    int ymax, xmin, xmax;
+    int row_off;             // offset into the row-extreme table (page-relative)
+    int pad[3];
+};
+
+struct CropDev {
+    const uint8_t* page; int page_h, page_w;
+    float box[8];
+    float t[9]; int cls;     // inverse projection (crop -> page) and its class
+    int w, h;                // final crop dims (after rotate270)
+    int rot;
+    int status;
+    unsigned long long offset;
+};
+
+struct LineDev {
+    int crop, img_w, resized_w, pad;
+    unsigned long long dst_offset;
+};
+
+struct LogitsRow {         // one (line) entry of a CTC batch
+    const float* logits; int t; int out_base;  // out_base: first (line, t) slot in idx/prob arrays
+};
+
+struct retto_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    retto_b200_config cfg;
+    std::string err;
+    uint64_t launches = 0;
+
+    void set_error(const std::string& e) { err = e; }
+
+    // descriptor staging (device side; host side is pageable and snapshotted by cudaMemcpyAsync)
+    DevBuf d_stage, d_stage2, d_stage3;
+
+    // dictionary (rec_processor.rs:29-46)
+    std::vector<std::string> dict;
+    DevBuf d_dict_bytes, d_dict_offs;
+    int dict_max_len = 0;
+
+    // ctc scratch
+    DevBuf d_ctc_rows, d_ctc_idx, d_ctc_prob, d_ctc_tok, d_ctc_cnt, d_ctc_score, d_ctc_text, d_ctc_tlen, d_ctc_flag;
+    HostBuf h_ctc;
+
+    // det post state (kept for the fetch_* taps and for crop jobs)
+    std::vector<DetPostPage> dp_pages;
+    DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out;
+    HostBuf h_dp;
+
+    // crops
+    std::vector<CropDev> crops;
+    DevBuf d_crop_descs, d_crop_pix, d_crop_flip;
+    HostBuf h_crops;
+
+    // batches
+    DevBuf d_lines, d_batch;
+    DevBuf d_cls_idx, d_cls_out;
+    HostBuf h_cls;
+
+    // session scratch
+    DevBuf d_pages_raw, d_pages_rs, d_det_in;
+    std::vector<retto_b200_page_result> r_pages;
+    std::vector<retto_b200_box> r_boxes;
+    std::vector<retto_b200_cls_result> r_cls;
+    std::vector<uint32_t> r_text_offs;
+    std::vector<char> r_text;
+    std::vector<float> r_scores;
+};
+
+#define RT_LAUNCH_CHECK(ctx)                                                                      \
+    do {                                                                                          \
+        (ctx)->launches++;                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            (ctx)->set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));            \
+            return RETTO_B200_ERR_CUDA;                                                           \
+        }                                                                                         \
+    } while (0)
+
+// copy a host descriptor array to the device (async on the stream; the source is pageable host
+// memory, which cudaMemcpyAsync snapshots before returning, so callers may reuse it immediately)
+retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes);
+
+// binary search: largest p with prefix[p] <= v   (prefix has n+1 entries, prefix[0] = 0)
+__device__ __forceinline__ int rt_find_segment(const int* __restrict__ prefix, int n, int v) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+

@@ -1,0 +1,309 @@
+// ctc_decode.cu — K10: rec postprocess (argmax + max over the class axis) and CTC greedy decode.
+// Replaces RecProcessor::postprocess (rec_processor.rs:190-208: two full scalar passes, argmax and
+// max) and RecCharacter::decode (rec_processor.rs:48-97).
+//
+// Roofline: HBM.  Algorithmic bytes = 4 * rows * C (each logit read once).  One warp per (line, t)
+// row: 128-bit streaming loads (row starts are only 4-byte aligned: 26500 B rows for C = 6625, so
+// up to 3 head elements are peeled), per-lane running (value, index) with the reference's
+// first-maximum rule, warp-shuffle reduction "greater value wins, lower index on ties".
+#include <math_constants.h>
+
+#include "common.cuh"
+
+struct CtcTensor {
+    const float* logits;  // [n, t, C]
+    int n, t;
+    int line_base;        // first line index of this tensor
+    int pad;
+};
+
+__device__ __forceinline__ void amax_upd(float v, int i, float& bv, int& bi, int& nan) {
+    nan |= (v != v);
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+}
+
+// rows_prefix[k] = number of rows before tensor k.  idx/prob are laid out [line][max_t].
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) ctc_argmax_kernel(const CtcTensor* __restrict__ tensors, const int* __restrict__ rows_prefix,
+                                                                 int n_tensors, int total_rows, int C, int max_t,
+                                                                 int* __restrict__ idx_out, float* __restrict__ prob_out,
+                                                                 int* __restrict__ line_nan) {
+    const int lane = threadIdx.x & 31;
+    const int row_g = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row_g >= total_rows) return;
+    const int k = rt_find_segment(rows_prefix, n_tensors, row_g);
+    const CtcTensor tn = tensors[k];
+    const int r = row_g - rows_prefix[k];
+    const float* __restrict__ row = tn.logits + (size_t)r * (size_t)C;
+
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    int nan = 0;
+
+    int head = (int)(((16u - (unsigned)((uintptr_t)row & 15u)) & 15u) >> 2);
+    if (head > C) head = C;
+    if (lane < head) amax_upd(__ldcs(row + lane), lane, bv, bi, nan);
+    const float4* __restrict__ body = reinterpret_cast<const float4*>(row + head);
+    const int nvec = (C - head) >> 2;
+    int i = lane;
+    // 4 independent 128-bit loads in flight per lane
+    for (; i + 96 < nvec; i += 128) {
+        const float4 a = __ldcs(body + i);
+        const float4 b = __ldcs(body + i + 32);
+        const float4 c = __ldcs(body + i + 64);
+        const float4 d = __ldcs(body + i + 96);
+        int base = head + 4 * i;
+        amax_upd(a.x, base, bv, bi, nan); amax_upd(a.y, base + 1, bv, bi, nan); amax_upd(a.z, base + 2, bv, bi, nan); amax_upd(a.w, base + 3, bv, bi, nan);
+        base += 128;
+        amax_upd(b.x, base, bv, bi, nan); amax_upd(b.y, base + 1, bv, bi, nan); amax_upd(b.z, base + 2, bv, bi, nan); amax_upd(b.w, base + 3, bv, bi, nan);
+        base += 128;
+        amax_upd(c.x, base, bv, bi, nan); amax_upd(c.y, base + 1, bv, bi, nan); amax_upd(c.z, base + 2, bv, bi, nan); amax_upd(c.w, base + 3, bv, bi, nan);
+        base += 128;
+        amax_upd(d.x, base, bv, bi, nan); amax_upd(d.y, base + 1, bv, bi, nan); amax_upd(d.z, base + 2, bv, bi, nan); amax_upd(d.w, base + 3, bv, bi, nan);
+    }
+    for (; i < nvec; i += 32) {
+        const float4 a = __ldcs(body + i);
+        const int base = head + 4 * i;
+        amax_upd(a.x, base, bv, bi, nan); amax_upd(a.y, base + 1, bv, bi, nan); amax_upd(a.z, base + 2, bv, bi, nan); amax_upd(a.w, base + 3, bv, bi, nan);
+    }
+    for (int j = head + 4 * nvec + lane; j < C; j += 32) amax_upd(__ldcs(row + j), j, bv, bi, nan);
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        nan |= __shfl_xor_sync(0xffffffffu, nan, off);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+        const int line = tn.line_base + r / tn.t;
+        const int t = r - (r / tn.t) * tn.t;
+        idx_out[(size_t)line * max_t + t] = bi;
+        prob_out[(size_t)line * max_t + t] = bv;
+        if (nan) line_nan[line] = 1;
+    }
+}
+
+// one thread per line: CTC collapse (rec_processor.rs:57-95): keep t iff idx != 0 && (t == 0 || idx[t]
+// != idx[t-1]) && idx not in ignored_tokens ([0]); score = sum(p) / count, sequential f32 (NaN when
+// count == 0).  Text = concatenation of dict[idx] written at a fixed per-line stride.
+__global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ prob, const int* __restrict__ line_t,
+                                    int n_lines, int max_t, const unsigned* __restrict__ dict_offs,
+                                    const unsigned char* __restrict__ dict_bytes, int n_dict, int text_stride, int* __restrict__ tokens,
+                                    int* __restrict__ counts, float* __restrict__ scores, unsigned char* __restrict__ text,
+                                    int* __restrict__ text_len) {
+    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= n_lines) return;
+    const int T = line_t[line];
+    const int* li = idx + (size_t)line * max_t;
+    const float* lp = prob + (size_t)line * max_t;
+    int* tk = tokens + (size_t)line * max_t;
+    unsigned char* tx = text + (size_t)line * text_stride;
+    float acc = 0.0f;
+    int cnt = 0, tl = 0, prev = -1;
+    for (int t = 0; t < T; ++t) {
+        const int c = li[t];
+        const bool sel = (c != 0) && (t == 0 || c != prev);
+        prev = c;
+        if (sel) {
+            tk[cnt++] = c;
+            acc = __fadd_rn(acc, lp[t]);
+            if (c < n_dict) {
+                const unsigned b = dict_offs[c], e = dict_offs[c + 1];
+                for (unsigned q = b; q < e; ++q) tx[tl++] = dict_bytes[q];
+            }
+        }
+    }
+    for (int t = cnt; t < max_t; ++t) tk[t] = -1;
+    counts[line] = cnt;
+    scores[line] = __fdiv_rn(acc, (float)cnt);  // 0/0 -> NaN like the reference (rec_processor.rs:94)
+    text_len[line] = tl;
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static retto_b200_status ctc_prepare(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int n_descs, int C,
+                                     std::vector<CtcTensor>& tensors, std::vector<int>& prefix, std::vector<int>& line_t, int* max_t) {
+    if (!h_descs || n_descs < 0 || C <= 0) { ctx->set_error("ctc: bad arguments"); return RETTO_B200_ERR_INVALID_ARG; }
+    tensors.resize(n_descs);
+    prefix.assign(n_descs + 1, 0);
+    line_t.clear();
+    int mt = 1;
+    long long rows = 0;
+    for (int k = 0; k < n_descs; ++k) {
+        if (h_descs[k].n < 0 || h_descs[k].t <= 0) { ctx->set_error("ctc: bad tensor dims"); return RETTO_B200_ERR_INVALID_ARG; }
+        tensors[k] = CtcTensor{h_descs[k].d_logits, h_descs[k].n, h_descs[k].t, (int)line_t.size(), 0};
+        prefix[k] = (int)rows;
+        rows += (long long)h_descs[k].n * h_descs[k].t;
+        if (rows > 0x7fffffffLL) { ctx->set_error("ctc: too many rows"); return RETTO_B200_ERR_CAPACITY; }
+        for (int i = 0; i < h_descs[k].n; ++i) line_t.push_back(h_descs[k].t);
+        if (h_descs[k].n > 0) mt = std::max(mt, h_descs[k].t);
+    }
+    prefix[n_descs] = (int)rows;
+    *max_t = mt;
+    return RETTO_B200_OK;
+}
+
+static retto_b200_status ctc_run_argmax(retto_b200_ctx* ctx, const std::vector<CtcTensor>& tensors, const std::vector<int>& prefix, int C,
+                                        int max_t, int n_lines, int* d_idx, float* d_prob, int* d_line_nan) {
+    const int total_rows = prefix.back();
+    if (total_rows == 0) return RETTO_B200_OK;
+    std::vector<char> blob(tensors.size() * sizeof(CtcTensor) + prefix.size() * sizeof(int));
+    memcpy(blob.data(), tensors.data(), tensors.size() * sizeof(CtcTensor));
+    memcpy(blob.data() + tensors.size() * sizeof(CtcTensor), prefix.data(), prefix.size() * sizeof(int));
+    RT_TRY(rt_upload(ctx, ctx->d_ctc_rows, blob.data(), blob.size()));
+    const CtcTensor* d_t = ctx->d_ctc_rows.as<CtcTensor>();
+    const int* d_pre = reinterpret_cast<const int*>(ctx->d_ctc_rows.as<char>() + tensors.size() * sizeof(CtcTensor));
+    RT_CUDA_OK(ctx, cudaMemsetAsync(d_line_nan, 0, sizeof(int) * (size_t)n_lines, ctx->stream));
+    constexpr int WARPS = 8;
+    const int grid = (total_rows + WARPS - 1) / WARPS;
+    ctc_argmax_kernel<WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(d_t, d_pre, (int)tensors.size(), total_rows, C, max_t, d_idx, d_prob, d_line_nan);
+    RT_LAUNCH_CHECK(ctx);
+    return RETTO_B200_OK;
+}
+
+extern "C" retto_b200_status retto_b200_ctc_argmax(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs,
+                                                   int32_t num_classes, int32_t* d_idx, float* d_prob) {
+    if (!ctx) return RETTO_B200_ERR_INVALID_ARG;
+    std::vector<CtcTensor> tensors;
+    std::vector<int> prefix, line_t;
+    int max_t = 1;
+    RT_TRY(ctc_prepare(ctx, h_descs, n_descs, num_classes, tensors, prefix, line_t, &max_t));
+    // this tap writes [line][t] densely only when every tensor has the same t; otherwise stride = max_t
+    const int n_lines = (int)line_t.size();
+    RT_CUDA_OK(ctx, ctx->d_ctc_flag.ensure(sizeof(int) * (size_t)std::max(n_lines, 1), ctx->stream));
+    return ctc_run_argmax(ctx, tensors, prefix, num_classes, max_t, n_lines, d_idx, d_prob, ctx->d_ctc_flag.as<int>());
+}
+
+extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs,
+                                                   int32_t num_classes, uint32_t* h_text_offsets, char* h_text, size_t text_capacity,
+                                                   float* h_scores, int32_t* h_tokens, int32_t* h_token_counts, int32_t max_t_out) {
+    if (!ctx) return RETTO_B200_ERR_INVALID_ARG;
+    if (ctx->dict.empty()) { ctx->set_error("ctc_decode: no dictionary loaded"); return RETTO_B200_ERR_NO_DICT; }
+    if ((int)ctx->dict.size() != num_classes) {
+        ctx->set_error("ctc_decode: num_classes " + std::to_string(num_classes) + " != dictionary size " + std::to_string(ctx->dict.size()));
+        return RETTO_B200_ERR_INVALID_ARG;
+    }
+    std::vector<CtcTensor> tensors;
+    std::vector<int> prefix, line_t;
+    int max_t = 1;
+    RT_TRY(ctc_prepare(ctx, h_descs, n_descs, num_classes, tensors, prefix, line_t, &max_t));
+    const int n_lines = (int)line_t.size();
+    h_text_offsets[0] = 0;
+    if (n_lines == 0) return RETTO_B200_OK;
+    if (h_tokens && max_t_out < max_t) { ctx->set_error("ctc_decode: max_t too small for token output"); return RETTO_B200_ERR_INVALID_ARG; }
+    const int text_stride = max_t * std::max(ctx->dict_max_len, 1);
+    const size_t nl = (size_t)n_lines;
+    RT_CUDA_OK(ctx, ctx->d_ctc_idx.ensure(sizeof(int) * nl * max_t, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_ctc_prob.ensure(sizeof(float) * nl * max_t, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_ctc_tok.ensure(sizeof(int) * nl * max_t, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_ctc_cnt.ensure(sizeof(int) * nl * 4, ctx->stream));  // counts | text_len | line_t | nan flags
+    RT_CUDA_OK(ctx, ctx->d_ctc_score.ensure(sizeof(float) * nl, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_ctc_text.ensure(nl * text_stride, ctx->stream));
+    int* d_cnt = ctx->d_ctc_cnt.as<int>();
+    int* d_tlen = d_cnt + nl;
+    int* d_linet = d_cnt + 2 * nl;
+    int* d_nan = d_cnt + 3 * nl;
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(d_linet, line_t.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, ctx->stream));
+    RT_TRY(ctc_run_argmax(ctx, tensors, prefix, num_classes, max_t, n_lines, ctx->d_ctc_idx.as<int>(), ctx->d_ctc_prob.as<float>(), d_nan));
+    ctc_collapse_kernel<<<(n_lines + 127) / 128, 128, 0, ctx->stream>>>(
+        ctx->d_ctc_idx.as<int>(), ctx->d_ctc_prob.as<float>(), d_linet, n_lines, max_t, ctx->d_dict_offs.as<unsigned>(),
+        ctx->d_dict_bytes.as<unsigned char>(), (int)ctx->dict.size(), text_stride, ctx->d_ctc_tok.as<int>(), d_cnt,
+        ctx->d_ctc_score.as<float>(), ctx->d_ctc_text.as<unsigned char>(), d_tlen);
+    RT_LAUNCH_CHECK(ctx);
+    // results -> host
+    const size_t hbytes = sizeof(int) * nl * 4 + sizeof(float) * nl + nl * text_stride + (h_tokens ? sizeof(int) * nl * max_t : 0);
+    RT_CUDA_OK(ctx, ctx->h_ctc.ensure(hbytes));
+    char* hb = ctx->h_ctc.as<char>();
+    int* hc = reinterpret_cast<int*>(hb);
+    float* hs = reinterpret_cast<float*>(hb + sizeof(int) * nl * 4);
+    unsigned char* ht = reinterpret_cast<unsigned char*>(hb + sizeof(int) * nl * 4 + sizeof(float) * nl);
+    int* htok = reinterpret_cast<int*>(hb + sizeof(int) * nl * 4 + sizeof(float) * nl + nl * text_stride);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(hc, d_cnt, sizeof(int) * nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(hs, ctx->d_ctc_score.p, sizeof(float) * nl, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(ht, ctx->d_ctc_text.p, nl * text_stride, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_tokens) RT_CUDA_OK(ctx, cudaMemcpyAsync(htok, ctx->d_ctc_tok.p, sizeof(int) * nl * max_t, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    const int* h_cnt = hc;
+    const int* h_tlen = hc + nl;
+    const int* h_nan = hc + 3 * nl;
+    size_t off = 0;
+    retto_b200_status st = RETTO_B200_OK;
+    for (int i = 0; i < n_lines; ++i) {
+        if (h_nan[i]) { ctx->set_error("ctc_decode: NaN logits in line " + std::to_string(i)); st = RETTO_B200_ERR_NAN_LOGITS; }
+        const size_t len = (size_t)h_tlen[i];
+        if (off + len > text_capacity) { ctx->set_error("ctc_decode: text buffer too small"); return RETTO_B200_ERR_CAPACITY; }
+        memcpy(h_text + off, ht + (size_t)i * text_stride, len);
+        off += len;
+        h_text_offsets[i + 1] = (uint32_t)off;
+        h_scores[i] = hs[i];
+        if (h_token_counts) h_token_counts[i] = h_cnt[i];
+        if (h_tokens) {
+            for (int t = 0; t < max_t_out; ++t) h_tokens[(size_t)i * max_t_out + t] = t < max_t ? htok[(size_t)i * max_t + t] : -1;
+        }
+    }
+    return st;
+}
+
+extern "C" retto_b200_status retto_b200_dict_load(retto_b200_ctx* ctx, const char* utf8, size_t len) {
+    if (!ctx || (!utf8 && len)) return RETTO_B200_ERR_INVALID_ARG;
+    // RecCharacter::new (rec_processor.rs:29-46): content.lines().map(str::trim) ; insert(0,"blank") ; push(" ")
+    std::vector<std::string> d;
+    d.push_back("blank");
+    size_t i = 0;
+    auto is_ws = [](const std::string& s, size_t pos, size_t* adv) -> bool {
+        // Rust char::is_whitespace (White_Space property) for the UTF-8 sequence at pos
+        const unsigned char c = (unsigned char)s[pos];
+        if (c == ' ' || (c >= 0x09 && c <= 0x0d)) { *adv = 1; return true; }
+        if (c == 0xC2 && pos + 1 < s.size()) {
+            const unsigned char c1 = (unsigned char)s[pos + 1];
+            if (c1 == 0x85 || c1 == 0xA0) { *adv = 2; return true; }
+        }
+        if (c == 0xE1 && pos + 2 < s.size() && (unsigned char)s[pos + 1] == 0x9A && (unsigned char)s[pos + 2] == 0x80) { *adv = 3; return true; }
+        if (c == 0xE2 && pos + 2 < s.size()) {
+            const unsigned char c1 = (unsigned char)s[pos + 1], c2 = (unsigned char)s[pos + 2];
+            if (c1 == 0x80 && ((c2 >= 0x80 && c2 <= 0x8A) || c2 == 0xA8 || c2 == 0xA9 || c2 == 0xAF)) { *adv = 3; return true; }
+            if (c1 == 0x81 && c2 == 0x9F) { *adv = 3; return true; }
+        }
+        if (c == 0xE3 && pos + 2 < s.size() && (unsigned char)s[pos + 1] == 0x80 && (unsigned char)s[pos + 2] == 0x80) { *adv = 3; return true; }
+        return false;
+    };
+    while (i < len) {
+        size_t j = i;
+        while (j < len && utf8[j] != '\n') ++j;
+        size_t e = j;
+        if (e > i && utf8[e - 1] == '\r') --e;  // str::lines strips "\r\n"
+        std::string line(utf8 + i, e - i);
+        // trim both ends
+        size_t b = 0, adv = 0;
+        while (b < line.size() && is_ws(line, b, &adv)) b += adv;
+        size_t en = line.size();
+        for (;;) {
+            bool cut = false;
+            for (size_t back = 1; back <= 3 && back <= en - b; ++back) {
+                size_t a2 = 0;
+                if (en - back >= b && is_ws(line, en - back, &a2) && a2 == back) { en -= back; cut = true; break; }
+            }
+            if (!cut) break;
+        }
+        d.push_back(line.substr(b, en - b));
+        i = j + 1;
+    }
+    d.push_back(" ");
+    std::vector<unsigned> offs(d.size() + 1, 0);
+    std::string bytes;
+    int mx = 1;
+    for (size_t k = 0; k < d.size(); ++k) {
+        offs[k] = (unsigned)bytes.size();
+        bytes += d[k];
+        if (k >= 1) mx = std::max(mx, (int)d[k].size());
+    }
+    offs[d.size()] = (unsigned)bytes.size();
+    RT_TRY(rt_upload(ctx, ctx->d_dict_offs, offs.data(), offs.size() * sizeof(unsigned)));
+    if (bytes.empty()) bytes.push_back('\0');
+    RT_TRY(rt_upload(ctx, ctx->d_dict_bytes, bytes.data(), bytes.size()));
+    ctx->dict = std::move(d);
+    ctx->dict_max_len = mx;
+    return RETTO_B200_OK;
+}
+
+extern "C" int32_t retto_b200_dict_size(const retto_b200_ctx* ctx) { return ctx ? (int32_t)ctx->dict.size() : 0; }
