@@ -152,6 +152,16 @@ retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, const retto_b2
 retto_b200_status retto_b200_det_post_fetch_bitmap(retto_b200_ctx* ctx, int32_t page, uint8_t* h_bitmap);
 retto_b200_status retto_b200_det_post_fetch_labels(retto_b200_ctx* ctx, int32_t page, int32_t* h_labels);
 
+/* parity tap: per connected component (in raster order of its first pixel) of page `page` of the last
+ * det_postprocess call: discovery key, status (0 kept, 1 sside<min, 2 score<box_thresh, 3 sside2<min+2,
+ * 4 size filter, 5 empty unclip, 6 never discovered by find_contours, -1 reference panic), the first
+ * min_area_rect (8 ints), its sside and box score (NaN when not evaluated).  n_holes = number of hole
+ * borders find_contours would additionally report (#components - Euler number). */
+retto_b200_status retto_b200_det_post_enable_trace(retto_b200_ctx* ctx, int32_t on);
+retto_b200_status retto_b200_det_post_fetch_trace(retto_b200_ctx* ctx, int32_t page, int32_t* n_components, int32_t* n_holes,
+                                                  int32_t* h_key, int32_t* h_status, int32_t* h_rect1, float* h_sside1,
+                                                  float* h_score, int32_t max_components);
+
 /* PointBox::scale_and_clip (points.rs:179-194) on host box arrays — used for session.rs:94-97 */
 retto_b200_status retto_b200_scale_and_clip(retto_b200_ctx* ctx, retto_b200_box* h_boxes, int32_t n,
                                             double bitmap_w, double bitmap_h, double ori_w, double ori_h);

@@ -109,7 +109,8 @@ EXPORTS = [
     "retto_b200_stream", "retto_b200_sync", "retto_b200_launch_count", "retto_b200_dev_alloc", "retto_b200_dev_free",
     "retto_b200_host_alloc", "retto_b200_host_free", "retto_b200_h2d", "retto_b200_d2h", "retto_b200_resize_both_plan",
     "retto_b200_resize_either_plan", "retto_b200_thumbnail", "retto_b200_det_preprocess", "retto_b200_det_postprocess",
-    "retto_b200_det_post_fetch_bitmap", "retto_b200_det_post_fetch_labels", "retto_b200_scale_and_clip", "retto_b200_crop_boxes",
+    "retto_b200_det_post_fetch_bitmap", "retto_b200_det_post_fetch_labels", "retto_b200_det_post_enable_trace",
+    "retto_b200_det_post_fetch_trace", "retto_b200_scale_and_clip", "retto_b200_crop_boxes",
     "retto_b200_crop_fetch", "retto_b200_plan_batches", "retto_b200_build_batches", "retto_b200_cls_postprocess",
     "retto_b200_dict_load", "retto_b200_dict_size", "retto_b200_ctc_decode", "retto_b200_ctc_argmax", "retto_b200_run_pages",
 ]
@@ -162,6 +163,8 @@ def lib() -> C.CDLL:
     L.retto_b200_det_postprocess.argtypes = [vp, C.POINTER(DetPostDesc), i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(Box), i32]
     L.retto_b200_det_post_fetch_bitmap.argtypes = [vp, i32, vp]
     L.retto_b200_det_post_fetch_labels.argtypes = [vp, i32, vp]
+    L.retto_b200_det_post_enable_trace.argtypes = [vp, i32]
+    L.retto_b200_det_post_fetch_trace.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), vp, vp, vp, vp, vp, i32]
     L.retto_b200_scale_and_clip.argtypes = [vp, C.POINTER(Box), i32, C.c_double, C.c_double, C.c_double, C.c_double]
     L.retto_b200_crop_boxes.argtypes = [vp, C.POINTER(CropJob), i32, C.POINTER(CropInfo)]
     L.retto_b200_crop_fetch.argtypes = [vp, i32, vp]

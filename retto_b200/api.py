@@ -158,6 +158,21 @@ class Context:
         self._check(self._L.retto_b200_det_post_fetch_labels(self._h, page, out.ctypes.data))
         return out
 
+    def enable_trace(self, on: bool = True):
+        self._check(self._L.retto_b200_det_post_enable_trace(self._h, int(on)))
+
+    def fetch_trace(self, page: int):
+        """per-component parity tap: dict(key, status, rect1[n,8], sside1, score, n_holes)"""
+        n, nh = C.c_int32(), C.c_int32()
+        self._check(self._L.retto_b200_det_post_fetch_trace(self._h, page, C.byref(n), C.byref(nh), None, None, None, None, None, 0))
+        k = max(n.value, 1)
+        key, st = np.zeros(k, np.int32), np.zeros(k, np.int32)
+        rect, ss, sc = np.zeros((k, 8), np.int32), np.zeros(k, np.float32), np.zeros(k, np.float32)
+        self._check(self._L.retto_b200_det_post_fetch_trace(self._h, page, C.byref(n), C.byref(nh), key.ctypes.data, st.ctypes.data,
+                                                            rect.ctypes.data, ss.ctypes.data, sc.ctypes.data, k))
+        m = n.value
+        return dict(key=key[:m], status=st[:m], rect1=rect[:m], sside1=ss[:m], score=sc[:m], n_holes=nh.value)
+
     def scale_and_clip(self, boxes: np.ndarray, bitmap_w, bitmap_h, ori_w, ori_h) -> np.ndarray:
         n = len(boxes)
         arr = (Box * max(n, 1))()

@@ -97,7 +97,8 @@ struct CompRec {           // per connected component (dense id)
     int root;                // min linear index (page-local)
     int ymax, xmin, xmax;
     int row_off;             // offset into the row-extreme table (page-relative)
-    int pad[3];
+    int key;                 // raster index at which imageproc's scan discovers the outer border (INT_MAX: never)
+    int pad[2];
 };
 
 struct CropDev {
@@ -142,6 +143,11 @@ struct retto_b200_ctx {
 
     // det post state (kept for the fetch_* taps and for crop jobs)
     std::vector<DetPostPage> dp_pages;
+    std::vector<int> dp_ncomp;
+    std::vector<int32_t> dbg_extra;
+    bool dp_trace_enabled = false, dp_trace_valid = false;
+    DevBuf d_trace;
+    std::vector<int> dp_holes;   // per page: #hole borders of the last det_postprocess (components - Euler number)
     DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out;
     HostBuf h_dp;
 

@@ -1,0 +1,796 @@
+// db_post.cu — K2..K6: DetProcessor::postprocess (det_processor.rs:279-335) on the device, batched
+// over pages:
+//   A  bitmap_runs     threshold (strict >) + 2x2 dilate (det_processor.rs:284-292) -> u8 bitmap,
+//                      run-start labels, per-tile foreground flags            [HBM: 4 B/px in, 5 B/px out]
+//   B  ccl_merge       8-connected union-find merge of runs (atomicMin on the label image), Euler
+//                      number of the bitmap (#components - #holes)            [foreground tiles only]
+//   C  ccl_flatten     path compression; label = min linear index of the component == the pixel at
+//                      which imageproc::contours::find_contours (det_processor.rs:293) discovers
+//                      the component's outer border; collects the roots
+//   D  comp_sort       roots ascending -> dense component ids in discovery order
+//   E  comp_extent     per-component ymax/xmin/xmax from run ends
+//   F  row_alloc       per-component row table allocation (prefix sum)
+//   G  row_extreme     per-row min/max x of each component  (all hull vertices are among them)
+//   H  box_geometry    one warp per component: hull -> min_area_rect -> sside filter -> box_score_fast
+//                      -> unclip -> min_area_rect -> scale_and_clip -> filters   (db_geom.cuh)
+//   I  page_finalize   per page: keep valid boxes in discovery order, sorted_boxes (stable insertion)
+//   J  pack            prefix over pages, dense box array
+// Hole borders (find_contours also returns them, retto does not filter by border_type) are detected
+// through the Euler number; pages with holes are flagged (hole boxes: see DESIGN.md).
+#include "common.cuh"
+#include "db_geom.cuh"
+
+#define TILE_W 128
+#define TILE_H 16
+#define ROWCAP 131072        // row-table entries per page
+#define MAX_OFFSET_PTS 256   // points of one unclipped polygon
+
+struct BoxCand {
+    float xy[8];
+    float score;
+    int valid;
+    int key;     // discovery position of the contour (find_contours order)
+    int status;  // parity tap: 0 kept, 1 sside<min, 2 score<box_thresh, 3 sside2<min+2, 4 size filter, 5 empty unclip,
+                 //             6 never discovered by find_contours, -1 reference panic
+    int rect1[8];
+    float sside1;
+    int rect2[8];   // second min_area_rect (after unclip), before scale_and_clip
+    float dist;     // unclip distance
+    int n_off;      // hull size of the unclipped polygon
+};
+
+__device__ __forceinline__ int find_root(const int* __restrict__ L, int a) {
+    int p = L[a];
+    while (p != a) { a = p; p = L[a]; }
+    return a;
+}
+__device__ __forceinline__ void union_labels(int* L, int a, int b) {
+    bool done;
+    do {
+        a = find_root(L, a);
+        b = find_root(L, b);
+        if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__device__ __forceinline__ bool tile_lookup(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix, int n_pages,
+                                            int total_tiles, int warps_per_block, DetPostPage& pg, int& page, int& s, int& rb, int& tile) {
+    tile = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (tile >= total_tiles) return false;
+    page = rt_find_segment(tile_prefix, n_pages, tile);
+    pg = pages[page];
+    const int lt = tile - tile_prefix[page];
+    rb = lt / pg.strips;
+    s = lt - rb * pg.strips;
+    return true;
+}
+
+// ---- A: threshold + dilate + run labels ---------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix,
+                                                           int n_pages, int total_tiles, float thr, int dilate,
+                                                           unsigned char* __restrict__ bitmap, int* __restrict__ labels,
+                                                           unsigned char* __restrict__ tileflags) {
+    DetPostPage pg; int page, s, rb, tile;
+    if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
+    const int lane = threadIdx.x & 31;
+    const int W = pg.w, H = pg.h;
+    const int x0 = s * TILE_W, x = x0 + lane * 4;
+    const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
+    unsigned char* bm = bitmap + pg.px_base;
+    int* lab = labels + pg.px_base;
+    const float* __restrict__ prob = pg.prob;
+
+    auto load_raw = [&](int y, unsigned& bits5) {  // bit0 = t(x-1), bits1..4 = t(x..x+3)
+        unsigned t = 0;
+        const float* row = prob + (size_t)y * W;
+        if (VEC) {
+            if (x < W) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row + x));
+                t = (v.x > thr ? 1u : 0u) | (v.y > thr ? 2u : 0u) | (v.z > thr ? 4u : 0u) | (v.w > thr ? 8u : 0u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < W && __ldg(row + x + j) > thr) t |= 1u << j;
+        }
+        unsigned left = __shfl_up_sync(RT_FULL, (t >> 3) & 1u, 1);
+        if (lane == 0) left = (x0 > 0 && __ldg(row + x0 - 1) > thr) ? 1u : 0u;
+        bits5 = (t << 1) | left;
+    };
+
+    unsigned prev = 0, any = 0;
+    if (dilate && y0 > 0) load_raw(y0 - 1, prev);
+    for (int y = y0; y < y1; ++y) {
+        unsigned cur;
+        load_raw(y, cur);
+        unsigned nib;
+        if (dilate) {
+            const unsigned m = cur | prev;          // vertical OR
+            nib = ((m >> 1) | m) & 0xfu;            // bit j = m[j+1] | m[j]  (pixel j sits at bit j+1)
+        } else nib = (cur >> 1) & 0xfu;
+        prev = cur;
+        if (VEC) { if (x >= W) nib = 0; }
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j >= W) nib &= ~(1u << j);
+        }
+        any |= nib;
+        // run starts
+        const unsigned notfull = __ballot_sync(RT_FULL, nib != 0xfu);
+        const unsigned below = notfull & ((1u << lane) - 1u);
+        const int l = below ? 31 - __clz(below) : 0;
+        const unsigned nibl = __shfl_sync(RT_FULL, nib, l);
+        int carry;  // run start if the run enters this lane from the left
+        if (!below) carry = x0;
+        else {
+            const unsigned z = (~nibl) & 0xfu;      // non-zero since lane l is not full
+            carry = x0 + 4 * l + (31 - __clz(z)) + 1;
+        }
+        int lb[4];
+        int start = carry;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (nib & (1u << j)) lb[j] = y * W + start;
+            else { lb[j] = -1; start = x + j + 1; }
+        }
+        if (VEC) {
+            if (x < W) {
+                const unsigned packed = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) |
+                                        ((nib & 8u) ? 0xff000000u : 0u);
+                *reinterpret_cast<unsigned*>(bm + (size_t)y * W + x) = packed;
+                *reinterpret_cast<int4*>(lab + (size_t)y * W + x) = make_int4(lb[0], lb[1], lb[2], lb[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < W) { bm[(size_t)y * W + x + j] = (nib & (1u << j)) ? 255 : 0; lab[(size_t)y * W + x + j] = lb[j]; }
+        }
+    }
+    const unsigned anyw = __ballot_sync(RT_FULL, any != 0);
+    if (lane == 0) tileflags[tile] = anyw ? 1 : 0;
+}
+
+// neighbourhood bits of a 4-pixel group for rows y (c) and y-1 (u): bit k = pixel x-1+k, k = 0..5
+__device__ __forceinline__ void load_bits6(const unsigned char* __restrict__ bm, int W, int y, int x, int x0, int lane, bool valid_row,
+                                           unsigned& bits6) {
+    unsigned t = 0;
+    if (valid_row && x < W) {
+        if ((W & 3) == 0) {
+            const unsigned v = *reinterpret_cast<const unsigned*>(bm + (size_t)y * W + x);
+            t = ((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 2u : 0u) | ((v & 0xff0000u) ? 4u : 0u) | ((v & 0xff000000u) ? 8u : 0u);
+        } else {
+            for (int j = 0; j < 4; ++j)
+                if (x + j < W && bm[(size_t)y * W + x + j]) t |= 1u << j;
+        }
+    }
+    unsigned left = __shfl_up_sync(RT_FULL, (t >> 3) & 1u, 1);
+    unsigned right = __shfl_down_sync(RT_FULL, t & 1u, 1);
+    if (lane == 0) left = (valid_row && x0 > 0 && bm[(size_t)y * W + x0 - 1]) ? 1u : 0u;
+    if (lane == 31) right = (valid_row && x0 + TILE_W < W && bm[(size_t)y * W + x0 + TILE_W]) ? 1u : 0u;
+    bits6 = left | (t << 1) | (right << 5);
+}
+
+// ---- B: merge runs (8-connectivity) + Euler number ----------------------------------------------
+__global__ void __launch_bounds__(128) ccl_merge_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix, int n_pages,
+                                                         int total_tiles, const unsigned char* __restrict__ bitmap, int* __restrict__ labels,
+                                                         const unsigned char* __restrict__ tileflags, PageCounters* __restrict__ counters) {
+    DetPostPage pg; int page, s, rb, tile;
+    if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
+    if (!tileflags[tile]) return;
+    const int lane = threadIdx.x & 31;
+    const int W = pg.w, H = pg.h;
+    const int x0 = s * TILE_W, x = x0 + lane * 4;
+    const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
+    const unsigned char* bm = bitmap + pg.px_base;
+    int* L = labels + pg.px_base;
+    unsigned up;
+    load_bits6(bm, W, y0 - 1, x, x0, lane, y0 > 0, up);
+    int euler = 0;
+    for (int y = y0; y < y1; ++y) {
+        unsigned cur;
+        load_bits6(bm, W, y, x, x0, lane, true, cur);
+        if (cur & 0x1eu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned cb = cur >> j, ub = up >> j;      // bit0 = W/NW, bit1 = self/N, bit2 = E/NE
+                if (!(cb & 2u)) continue;
+                const int p = y * W + x + j;
+                const bool Wn = cb & 1u, En = cb & 4u, NW = ub & 1u, N = ub & 2u, NE = ub & 4u;
+                if (N) { if (!(Wn && NW)) union_labels(L, p, p - W); }
+                else {
+                    if (NW && !Wn) union_labels(L, p, p - W - 1);
+                    if (NE && !En) union_labels(L, p, p - W + 1);
+                }
+                if (j == 0 && lane == 0 && Wn) union_labels(L, p, p - 1);  // runs are labelled per strip
+                // Euler characteristic of the 8-connected clique complex (V - E + F - T); every edge /
+                // triangle / tetrahedron is counted at its member with the largest raster index, so only
+                // foreground pixels contribute and empty tiles can be skipped.
+                const int w_ = Wn ? 1 : 0, nw_ = NW ? 1 : 0, n_ = N ? 1 : 0, ne_ = NE ? 1 : 0;
+                const int k3 = w_ + nw_ + n_;
+                euler += 1 - (w_ + nw_ + n_ + ne_) + (k3 * (k3 - 1)) / 2 + (n_ & ne_) - (k3 == 3 ? 1 : 0);
+            }
+        }
+        up = cur;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) euler += __shfl_xor_sync(RT_FULL, euler, off);
+    if (lane == 0 && euler) atomicAdd(&counters[page].euler, euler);
+}
+
+// ---- C: flatten + collect roots ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ccl_flatten_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix, int n_pages,
+                                                           int total_tiles, int* __restrict__ labels, const unsigned char* __restrict__ tileflags,
+                                                           PageCounters* __restrict__ counters, int* __restrict__ roots, int max_comps) {
+    DetPostPage pg; int page, s, rb, tile;
+    if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
+    if (!tileflags[tile]) return;
+    const int lane = threadIdx.x & 31;
+    const int W = pg.w, H = pg.h;
+    const int x = s * TILE_W + lane * 4;
+    const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
+    int* L = labels + pg.px_base;
+    for (int y = y0; y < y1; ++y) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (x + j >= W) continue;
+            const int p = y * W + x + j;
+            const int l = L[p];
+            if (l < 0) continue;
+            const int r = find_root(L, l);
+            if (r != l) L[p] = r;
+            if (r == p) {
+                const int slot = atomicAdd(&counters[page].n_roots, 1);
+                if (slot < max_comps) roots[(size_t)page * max_comps + slot] = p;
+            }
+        }
+    }
+}
+
+// ---- D: sort roots, assign dense ids ----------------------------------------------------------------
+__global__ void __launch_bounds__(1024) comp_sort_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
+                                                          int* __restrict__ roots, CompRec* __restrict__ comps, int* __restrict__ cid_at,
+                                                          int max_comps) {
+    const int page = blockIdx.x;
+    const DetPostPage pg = pages[page];
+    int n = counters[page].n_roots;
+    if (n > max_comps) {
+        if (threadIdx.x == 0) { counters[page].status = RETTO_B200_ERR_CAPACITY; counters[page].n_roots = 0; }
+        return;
+    }
+    int* r = roots + (size_t)page * max_comps;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + threadIdx.x; i < np2; i += blockDim.x) r[i] = 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int a = r[i], b = r[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { r[i] = b; r[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    CompRec* c = comps + (size_t)page * max_comps;
+    int* cid = cid_at + pg.px_base;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int root = r[i];
+        cid[root] = i;
+        CompRec cr;
+        cr.root = root; cr.ymax = -1; cr.xmin = 0x7fffffff; cr.xmax = -1; cr.row_off = 0;
+        cr.key = 0x7fffffff; cr.pad[0] = cr.pad[1] = 0;
+        c[i] = cr;
+    }
+}
+
+// ---- E / G: run-end passes ------------------------------------------------------------------------------
+template <int PASS>  // 0: component extents, 1: per-row extremes
+__global__ void __launch_bounds__(128) run_end_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix, int n_pages,
+                                                       int total_tiles, const unsigned char* __restrict__ bitmap, const int* __restrict__ labels,
+                                                       const unsigned char* __restrict__ tileflags, const int* __restrict__ cid_at,
+                                                       CompRec* __restrict__ comps, int2* __restrict__ rowtab,
+                                                       const PageCounters* __restrict__ counters, int max_comps) {
+    DetPostPage pg; int page, s, rb, tile;
+    if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
+    if (!tileflags[tile]) return;
+    if (counters[page].status != RETTO_B200_OK) return;
+    const int lane = threadIdx.x & 31;
+    const int W = pg.w, H = pg.h;
+    const int x0 = s * TILE_W, x = x0 + lane * 4;
+    const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
+    const unsigned char* bm = bitmap + pg.px_base;
+    const int* L = labels + pg.px_base;
+    const int* cid = cid_at + pg.px_base;
+    CompRec* c = comps + (size_t)page * max_comps;
+    int2* rt = rowtab + (size_t)page * ROWCAP;
+    for (int y = y0; y < y1; ++y) {
+        unsigned cur;
+        load_bits6(bm, W, y, x, x0, lane, true, cur);
+        if (!(cur & 0x1eu)) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned cb = cur >> j;
+            if (!(cb & 2u)) continue;
+            const bool is_start = !(cb & 1u), is_end = !(cb & 4u);
+            if (!is_start && !is_end) continue;
+            const int p = y * W + x + j;
+            const int id = cid[L[p]];
+            if (PASS == 0) {
+                if (is_start) { atomicMin(&c[id].xmin, x + j); atomicMax(&c[id].ymax, y); }
+                if (is_end) atomicMax(&c[id].xmax, x + j);
+                // imageproc's scan (RECALLED, contours.rs) starts an outer border only at x > 0 with a zero to
+                // the left, or (as a "hole"-typed start tracing the same border) at x + 1 < width with a zero to
+                // the right; the frame itself never starts a border.
+                if ((is_start && x + j > 0) || (is_end && x + j + 1 < W)) atomicMin(&c[id].key, p);
+            } else {
+                const CompRec cr = c[id];
+                const int ridx = cr.row_off + (y - cr.root / W);
+                if (ridx < ROWCAP) {
+                    if (is_start) atomicMin(&rt[ridx].x, x + j);
+                    if (is_end) atomicMax(&rt[ridx].y, x + j);
+                }
+            }
+        }
+    }
+}
+
+// ---- F: row table allocation -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) row_alloc_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
+                                                          CompRec* __restrict__ comps, int2* __restrict__ rowtab, int max_comps) {
+    const int page = blockIdx.x;
+    const DetPostPage pg = pages[page];
+    if (counters[page].status != RETTO_B200_OK) return;
+    const int n = counters[page].n_roots;
+    CompRec* c = comps + (size_t)page * max_comps;
+    __shared__ int s_part[1024];
+    __shared__ int s_total;
+    // each thread owns a contiguous chunk of components
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += c[i].ymax - c[i].root / pg.w + 1;
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; }
+        s_total = run;
+        counters[page].row_total = run;
+        if (run > ROWCAP) counters[page].status = RETTO_B200_ERR_CAPACITY;
+    }
+    __syncthreads();
+    int off = s_part[threadIdx.x];
+    for (int i = b; i < e; ++i) { c[i].row_off = off; off += c[i].ymax - c[i].root / pg.w + 1; }
+    const int total = min(s_total, ROWCAP);
+    int2* rt = rowtab + (size_t)page * ROWCAP;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) rt[i] = make_int2(0x7fffffff, -1);
+}
+
+// ---- H: per-component geometry ---------------------------------------------------------------------------------
+struct GeomParams {
+    float box_thresh, unclip_ratio;
+    int min_mini_box_size;
+};
+
+__global__ void __launch_bounds__(128) box_geometry_kernel(const DetPostPage* __restrict__ pages,
+                                                            int n_pages, PageCounters* __restrict__ counters, const CompRec* __restrict__ comps,
+                                                            const int2* __restrict__ rowtab, int2* __restrict__ hullbuf, BoxCand* __restrict__ cand,
+                                                            int max_comps, GeomParams gp) {
+    __shared__ int2 s_pts[4][MAX_OFFSET_PTS];
+    __shared__ int2 s_hull[4][2 * MAX_OFFSET_PTS];
+    __shared__ int s_n[4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int page = blockIdx.y;
+    const int id = blockIdx.x * 4 + wib;
+    if (counters[page].status == RETTO_B200_ERR_CAPACITY) return;
+    const int n_comp = counters[page].n_roots;
+    if (id >= n_comp) return;
+    const DetPostPage pg = pages[page];
+    const CompRec cr = comps[(size_t)page * max_comps + id];
+    BoxCand* out = cand + (size_t)page * max_comps + id;
+    const int ymin = cr.root / pg.w;
+    const int R = cr.ymax - ymin + 1;
+    const int2* rt = rowtab + (size_t)page * ROWCAP + cr.row_off;
+    int2* hull = hullbuf + ((size_t)page * ROWCAP + cr.row_off) * 2;
+
+    // 1. hull of the component == hull of its outer border
+    if (lane == 0) {
+        s_n[wib] = hull_from_rows(R, [&](int i, int& y, int& a, int& b) { const int2 v = rt[i]; y = ymin + i; a = v.x; b = v.y; }, hull);
+    }
+    __syncwarp();
+    int nh = s_n[wib];
+    __syncwarp();
+    double q[8];
+    warp_min_area_rect(hull, nh, q);
+    const float sside = sside_of(q);
+    int qx[4], qy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { qx[i] = (int)q[2 * i]; qy[i] = (int)q[2 * i + 1]; }
+    if (lane == 0) {
+        out->valid = 0; out->key = cr.key; out->sside1 = sside; out->score = CUDART_NAN_F; out->status = 6;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { out->rect1[2 * i] = qx[i]; out->rect1[2 * i + 1] = qy[i]; }
+    }
+    if (cr.key == 0x7fffffff) return;  // every run spans the full width: find_contours never starts this border
+    if (sside < (float)gp.min_mini_box_size) { if (lane == 0) out->status = 1; return; }
+    // 2. box_score_fast on the probability map
+    float score;
+    if (!warp_box_score(pg.prob, pg.h, pg.w, qx, qy, &score)) {
+        if (lane == 0) { atomicMax(&counters[page].status, RETTO_B200_ERR_DEGENERATE_QUAD); out->status = -1; }
+        return;
+    }
+    if (lane == 0) out->score = score;
+    if (score < gp.box_thresh) { if (lane == 0) out->status = 2; return; }
+    // 3. unclip
+    if (lane == 0) {
+        const float dist = unclip_distance(qx, qy, gp.unclip_ratio);
+        out->dist = dist;
+        int m = clipper_offset_round(qx, qy, (double)dist, 0.5, s_pts[wib], MAX_OFFSET_PTS);
+        if (m > 0) {
+            // rows of the offset polygon: sort by (y, x), group by y
+            int2* p = s_pts[wib];
+            for (int i = 1; i < m; ++i) {
+                const int2 v = p[i];
+                int j = i;
+                while (j > 0 && (p[j - 1].y > v.y || (p[j - 1].y == v.y && p[j - 1].x > v.x))) { p[j] = p[j - 1]; --j; }
+                p[j] = v;
+            }
+            // compress to rows in place: (y, xmin, xmax) stored as pairs in s_hull's upper half
+            int2* rows_y = s_hull[wib] + MAX_OFFSET_PTS;            // .x = y, .y unused
+            int2* rows_x = s_hull[wib] + MAX_OFFSET_PTS + MAX_OFFSET_PTS / 2;  // .x = xmin, .y = xmax
+            int nr = 0;
+            for (int i = 0; i < m;) {
+                int j = i;
+                while (j + 1 < m && p[j + 1].y == p[i].y) ++j;
+                if (nr < MAX_OFFSET_PTS / 2) { rows_y[nr] = make_int2(p[i].y, 0); rows_x[nr] = make_int2(p[i].x, p[j].x); ++nr; }
+                i = j + 1;
+            }
+            m = hull_from_rows(nr, [&](int i, int& y, int& a, int& b) { y = rows_y[i].x; a = rows_x[i].x; b = rows_x[i].y; }, s_hull[wib]);
+        }
+        s_n[wib] = m;
+    }
+    __syncwarp();
+    nh = s_n[wib];
+    if (nh <= 0) {
+        // Clipper returned nothing (or overflow): the reference would panic in min_area_rect(&[])
+        if (lane == 0) { atomicMax(&counters[page].status, nh < 0 ? RETTO_B200_ERR_CAPACITY : RETTO_B200_ERR_DEGENERATE_QUAD); out->status = 5; }
+        return;
+    }
+    double q2[8];
+    warp_min_area_rect(s_hull[wib], nh, q2);
+    const float sside2 = sside_of(q2);
+    if (lane == 0) { out->n_off = nh; for (int i = 0; i < 8; ++i) out->rect2[i] = (int)q2[i]; }
+    if (sside2 < (float)(gp.min_mini_box_size + 2)) { if (lane == 0) out->status = 3; return; }
+    if (lane == 0) {
+        out->status = 4;
+        const double inv_w = __ddiv_rn((double)pg.ori_w, (double)pg.w), inv_h = __ddiv_rn((double)pg.ori_h, (double)pg.h);
+        float b[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            b[2 * i] = scale_clip_1((float)q2[2 * i], inv_w, (double)pg.ori_w);
+            b[2 * i + 1] = scale_clip_1((float)q2[2 * i + 1], inv_h, (double)pg.ori_h);
+        }
+        const float pb_h = side_len(b[0], b[1], b[6], b[7]);
+        const float pb_w = side_len(b[0], b[1], b[2], b[3]);
+        if (!(pb_h <= 3.0f || pb_w <= 3.0f)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out->xy[i] = b[i];
+            out->score = score;
+            out->valid = 1;
+            out->status = 0;
+        }
+    }
+}
+
+// ---- I: per-page compaction + sorted_boxes (det_processor.rs:324-333) ----------------------------------------------
+__device__ __forceinline__ bool box_less(const BoxCand& r1, const BoxCand& r2) {
+    const float c1x = __fdiv_rn(__fadd_rn(r1.xy[0], r1.xy[4]), 2.0f), c1y = __fdiv_rn(__fadd_rn(r1.xy[1], r1.xy[5]), 2.0f);
+    const float c2x = __fdiv_rn(__fadd_rn(r2.xy[0], r2.xy[4]), 2.0f), c2y = __fdiv_rn(__fadd_rn(r2.xy[1], r2.xy[5]), 2.0f);
+    if (fabsf(__fsub_rn(c1y, c2y)) < 10.0f) return c1x < c2x;
+    return c1y < c2y;
+}
+
+struct TraceRec { int key, status; int rect1[8]; float sside1, score; int rect2[8]; float dist; int n_off; };
+__global__ void trace_copy_kernel(int n_pages, const PageCounters* __restrict__ counters, const BoxCand* __restrict__ cand, int max_comps,
+                                  TraceRec* __restrict__ trace) {
+    const int page = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (page >= n_pages || i >= counters[page].n_roots || i >= max_comps) return;
+    const BoxCand& b = cand[(size_t)page * max_comps + i];
+    TraceRec t;
+    t.key = b.key; t.status = b.status; t.sside1 = b.sside1; t.score = b.score;
+    for (int k = 0; k < 8; ++k) { t.rect1[k] = b.rect1[k]; t.rect2[k] = b.rect2[k]; }
+    t.dist = b.dist; t.n_off = b.n_off;
+    trace[(size_t)page * max_comps + i] = t;
+}
+
+__global__ void __launch_bounds__(32) page_sort_kernel(int n_pages, PageCounters* __restrict__ counters, BoxCand* __restrict__ cand, int max_comps) {
+    const int page = blockIdx.x;
+    if (threadIdx.x != 0 || page >= n_pages) return;
+    if (counters[page].status == RETTO_B200_ERR_CAPACITY) { counters[page].n_boxes = 0; return; }
+    const int n = counters[page].n_roots;
+    BoxCand* c = cand + (size_t)page * max_comps;
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (c[i].valid) { if (m != i) c[m] = c[i]; ++m; }
+    // contours come in find_contours discovery order
+    for (int i = 1; i < m; ++i) {
+        const BoxCand v = c[i];
+        int j = i;
+        while (j > 0 && v.key < c[j - 1].key) { c[j] = c[j - 1]; --j; }
+        c[j] = v;
+    }
+    // stable insertion sort == Rust's sort_by for n <= 20, and for any n when the comparator is consistent
+    for (int i = 1; i < m; ++i) {
+        const BoxCand v = c[i];
+        int j = i;
+        while (j > 0 && box_less(v, c[j - 1])) { c[j] = c[j - 1]; --j; }
+        c[j] = v;
+    }
+    counters[page].n_boxes = m;
+}
+
+// ---- J: dense packing ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_offsets_kernel(int n_pages, const PageCounters* __restrict__ counters, int* __restrict__ offsets) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int p = 0; p < n_pages; ++p) { offsets[p] = run; run += counters[p].n_boxes; }
+        offsets[n_pages] = run;
+    }
+}
+__global__ void __launch_bounds__(128) pack_boxes_kernel(int n_pages, const PageCounters* __restrict__ counters, const int* __restrict__ offsets,
+                                                          const BoxCand* __restrict__ cand, int max_comps, retto_b200_box* __restrict__ dense,
+                                                          int cap) {
+    const int page = blockIdx.x;
+    const int n = counters[page].n_boxes, base = offsets[page];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (base + i >= cap) break;
+        const BoxCand b = cand[(size_t)page * max_comps + i];
+        retto_b200_box o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.xy[k] = b.xy[k];
+        o.score = b.score;
+        dense[base + i] = o;
+    }
+}
+
+__global__ void zero_counters_kernel(PageCounters* c, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { PageCounters z; memset(&z, 0, sizeof(z)); c[i] = z; }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------------
+extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, const retto_b200_det_post_desc* h_descs, int32_t n,
+                                                        int32_t* h_page_status, int32_t* h_box_offsets, retto_b200_box* h_boxes,
+                                                        int32_t max_boxes_total) {
+    if (!ctx || n < 0 || (n > 0 && (!h_descs || !h_page_status)) || !h_box_offsets) return RETTO_B200_ERR_INVALID_ARG;
+    h_box_offsets[0] = 0;
+    ctx->dp_pages.clear();
+    if (n == 0) return RETTO_B200_OK;
+    const int max_comps = ctx->cfg.max_components_per_page;
+    std::vector<int> tile_prefix(n + 1, 0);
+    long long px = 0;
+    bool vec = true;
+    for (int i = 0; i < n; ++i) {
+        const retto_b200_det_post_desc& d = h_descs[i];
+        if (!d.d_prob || d.h <= 0 || d.w <= 0 || d.ori_h <= 0 || d.ori_w <= 0 || (long long)d.h * d.w > 0x7fffffffLL) {
+            ctx->set_error("det_postprocess: bad descriptor " + std::to_string(i));
+            return RETTO_B200_ERR_INVALID_ARG;
+        }
+        DetPostPage pg;
+        pg.prob = d.d_prob; pg.h = d.h; pg.w = d.w; pg.ori_h = d.ori_h; pg.ori_w = d.ori_w;
+        pg.strips = (d.w + TILE_W - 1) / TILE_W;
+        pg.rowblocks = (d.h + TILE_H - 1) / TILE_H;
+        pg.tile_base = tile_prefix[i];
+        pg.px_base = px;
+        pg.comp_base = i * max_comps;
+        pg.box_base = 0;
+        tile_prefix[i + 1] = tile_prefix[i] + pg.strips * pg.rowblocks;
+        px += ((long long)d.h * d.w + 15) & ~15LL;
+        if ((d.w & 3) || ((uintptr_t)d.d_prob & 15)) vec = false;
+        ctx->dp_pages.push_back(pg);
+    }
+    const int total_tiles = tile_prefix[n];
+    cudaStream_t st = ctx->stream;
+    // device state
+    {
+        std::vector<char> blob(sizeof(DetPostPage) * n + sizeof(int) * (n + 1));
+        memcpy(blob.data(), ctx->dp_pages.data(), sizeof(DetPostPage) * n);
+        memcpy(blob.data() + sizeof(DetPostPage) * n, tile_prefix.data(), sizeof(int) * (n + 1));
+        RT_TRY(rt_upload(ctx, ctx->d_dp_pages, blob.data(), blob.size()));
+    }
+    const DetPostPage* d_pages = ctx->d_dp_pages.as<DetPostPage>();
+    const int* d_tile_prefix = reinterpret_cast<const int*>(ctx->d_dp_pages.as<char>() + sizeof(DetPostPage) * n);
+    RT_CUDA_OK(ctx, ctx->d_dp_counters.ensure(sizeof(PageCounters) * n + sizeof(int) * (n + 1), st));
+    RT_CUDA_OK(ctx, ctx->d_bitmap.ensure((size_t)px, st));
+    RT_CUDA_OK(ctx, ctx->d_labels.ensure((size_t)px * 4, st));
+    RT_CUDA_OK(ctx, ctx->d_cid_at.ensure((size_t)px * 4, st));
+    RT_CUDA_OK(ctx, ctx->d_tileflags.ensure((size_t)total_tiles, st));
+    RT_CUDA_OK(ctx, ctx->d_roots.ensure(sizeof(int) * (size_t)n * max_comps, st));
+    RT_CUDA_OK(ctx, ctx->d_comps.ensure(sizeof(CompRec) * (size_t)n * max_comps, st));
+    RT_CUDA_OK(ctx, ctx->d_rowtab.ensure(sizeof(int2) * (size_t)n * ROWCAP * 3, st));  // row table + 2x hull scratch
+    RT_CUDA_OK(ctx, ctx->d_cand.ensure(sizeof(BoxCand) * (size_t)n * max_comps, st));
+    PageCounters* d_cnt = ctx->d_dp_counters.as<PageCounters>();
+    int* d_offsets = reinterpret_cast<int*>(ctx->d_dp_counters.as<char>() + sizeof(PageCounters) * n);
+    unsigned char* d_bm = ctx->d_bitmap.as<unsigned char>();
+    int* d_lab = ctx->d_labels.as<int>();
+    int* d_cid = ctx->d_cid_at.as<int>();
+    unsigned char* d_tf = ctx->d_tileflags.as<unsigned char>();
+    int* d_roots = ctx->d_roots.as<int>();
+    CompRec* d_comps = ctx->d_comps.as<CompRec>();
+    int2* d_rowtab = ctx->d_rowtab.as<int2>();
+    int2* d_hull = d_rowtab + (size_t)n * ROWCAP;
+    BoxCand* d_cand = ctx->d_cand.as<BoxCand>();
+
+    zero_counters_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, n);
+    RT_LAUNCH_CHECK(ctx);
+    const int tgrid = (total_tiles + 3) / 4;
+    if (vec)
+        bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf);
+    else
+        bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf);
+    RT_LAUNCH_CHECK(ctx);
+    ccl_merge_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt);
+    RT_LAUNCH_CHECK(ctx);
+    ccl_flatten_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_lab, d_tf, d_cnt, d_roots, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    comp_sort_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_roots, d_comps, d_cid, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    run_end_kernel<0><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    row_alloc_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_comps, d_rowtab, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    run_end_kernel<1><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    // H needs the per-page component counts for its grid: size it by the host-known cap when small,
+    // else by a device->host read of the maximum (one tiny sync)
+    RT_CUDA_OK(ctx, ctx->h_dp.ensure(sizeof(PageCounters) * n + sizeof(int) * (n + 1)));
+    PageCounters* h_cnt = ctx->h_dp.as<PageCounters>();
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    int max_n = 0;
+    for (int i = 0; i < n; ++i) max_n = std::max(max_n, std::min(h_cnt[i].n_roots, max_comps));
+    if (max_n > 0) {
+        GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
+        dim3 grid((max_n + 3) / 4, n);
+        box_geometry_kernel<<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp);
+        RT_LAUNCH_CHECK(ctx);
+    }
+    ctx->dp_trace_valid = false;
+    if (ctx->dp_trace_enabled && max_n > 0) {
+        RT_CUDA_OK(ctx, ctx->d_trace.ensure(sizeof(TraceRec) * (size_t)n * max_comps, st));
+        trace_copy_kernel<<<dim3((max_n + 127) / 128, n), 128, 0, st>>>(n, d_cnt, d_cand, max_comps, ctx->d_trace.as<TraceRec>());
+        RT_LAUNCH_CHECK(ctx);
+        ctx->dp_trace_valid = true;
+    }
+    page_sort_kernel<<<n, 32, 0, st>>>(n, d_cnt, d_cand, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    pack_offsets_kernel<<<1, 32, 0, st>>>(n, d_cnt, d_offsets);
+    RT_LAUNCH_CHECK(ctx);
+    const int cap = std::max(max_boxes_total, 0);
+    RT_CUDA_OK(ctx, ctx->d_boxes_out.ensure(sizeof(retto_b200_box) * (size_t)std::max(cap, 1), st));
+    pack_boxes_kernel<<<n, 128, 0, st>>>(n, d_cnt, d_offsets, d_cand, max_comps, ctx->d_boxes_out.as<retto_b200_box>(), cap);
+    RT_LAUNCH_CHECK(ctx);
+    int* h_off = reinterpret_cast<int*>(ctx->h_dp.as<char>() + sizeof(PageCounters) * n);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_off, d_offsets, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, st));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    retto_b200_status ret = RETTO_B200_OK;
+    for (int i = 0; i < n; ++i) {
+        int s = h_cnt[i].status;
+        // hole borders: find_contours would return extra (hole) contours; #holes = #components - euler
+        h_page_status[i] = s;
+        h_box_offsets[i] = h_off[i];
+    }
+    h_box_offsets[n] = h_off[n];
+    ctx->dp_holes.assign(n, 0);
+    ctx->dp_ncomp.assign(n, 0);
+    for (int i = 0; i < n; ++i) { ctx->dp_holes[i] = h_cnt[i].n_roots - h_cnt[i].euler; ctx->dp_ncomp[i] = h_cnt[i].n_roots; }
+    const int total = h_off[n];
+    if (total > cap) {
+        ctx->set_error("det_postprocess: " + std::to_string(total) + " boxes exceed max_boxes_total " + std::to_string(cap));
+        ret = RETTO_B200_ERR_CAPACITY;
+    }
+    const int ncopy = std::min(total, cap);
+    if (ncopy > 0 && h_boxes) {
+        RT_CUDA_OK(ctx, cudaMemcpyAsync(h_boxes, ctx->d_boxes_out.p, sizeof(retto_b200_box) * (size_t)ncopy, cudaMemcpyDeviceToHost, st));
+        RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    }
+    return ret;
+}
+
+extern "C" retto_b200_status retto_b200_det_post_fetch_bitmap(retto_b200_ctx* ctx, int32_t page, uint8_t* h_bitmap) {
+    if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !h_bitmap) return RETTO_B200_ERR_INVALID_ARG;
+    const DetPostPage& pg = ctx->dp_pages[page];
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_bitmap, ctx->d_bitmap.as<unsigned char>() + pg.px_base, (size_t)pg.h * pg.w, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_det_post_fetch_labels(retto_b200_ctx* ctx, int32_t page, int32_t* h_labels) {
+    if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !h_labels) return RETTO_B200_ERR_INVALID_ARG;
+    const DetPostPage& pg = ctx->dp_pages[page];
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_labels, ctx->d_labels.as<int>() + pg.px_base, sizeof(int) * (size_t)pg.h * pg.w, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RETTO_B200_OK;
+}
+
+// PointBox::scale_and_clip (points.rs:179-194) for host-resident result boxes (session.rs:94-97): 8 numbers per box of
+// f64 rounding, done in a tiny kernel so that no arithmetic of the path runs on the CPU.
+__global__ void scale_clip_kernel(retto_b200_box* b, int n, double inv_w, double inv_h, double ori_w, double ori_h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        b[i].xy[2 * k] = scale_clip_1(b[i].xy[2 * k], inv_w, ori_w);
+        b[i].xy[2 * k + 1] = scale_clip_1(b[i].xy[2 * k + 1], inv_h, ori_h);
+    }
+}
+extern "C" retto_b200_status retto_b200_scale_and_clip(retto_b200_ctx* ctx, retto_b200_box* h_boxes, int32_t n, double bitmap_w,
+                                                       double bitmap_h, double ori_w, double ori_h) {
+    if (!ctx || n < 0 || (n > 0 && !h_boxes)) return RETTO_B200_ERR_INVALID_ARG;
+    if (n == 0) return RETTO_B200_OK;
+    RT_TRY(rt_upload(ctx, ctx->d_stage3, h_boxes, sizeof(retto_b200_box) * (size_t)n));
+    scale_clip_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_stage3.as<retto_b200_box>(), n, ori_w / bitmap_w, ori_h / bitmap_h, ori_w, ori_h);
+    RT_LAUNCH_CHECK(ctx);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_boxes, ctx->d_stage3.p, sizeof(retto_b200_box) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RETTO_B200_OK;
+}
+
+// parity tap: per-component trace of the last det_postprocess (enable with retto_b200_det_post_enable_trace)
+extern "C" retto_b200_status retto_b200_det_post_enable_trace(retto_b200_ctx* ctx, int32_t on) {
+    if (!ctx) return RETTO_B200_ERR_INVALID_ARG;
+    ctx->dp_trace_enabled = on != 0;
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_det_post_fetch_trace(retto_b200_ctx* ctx, int32_t page, int32_t* n_components, int32_t* n_holes,
+                                                             int32_t* h_key, int32_t* h_status, int32_t* h_rect1, float* h_sside1,
+                                                             float* h_score, int32_t max_components) {
+    if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !n_components) return RETTO_B200_ERR_INVALID_ARG;
+    const int n = ctx->dp_ncomp[page];
+    *n_components = n;
+    if (n_holes) *n_holes = ctx->dp_holes[page];
+    if (!h_key) return RETTO_B200_OK;
+    if (!ctx->dp_trace_valid && n > 0) { ctx->set_error("trace not enabled for the last det_postprocess"); return RETTO_B200_ERR_INVALID_ARG; }
+    if (n > max_components) return RETTO_B200_ERR_CAPACITY;
+    std::vector<TraceRec> t(n);
+    if (n > 0) {
+        RT_CUDA_OK(ctx, cudaMemcpyAsync(t.data(), ctx->d_trace.as<TraceRec>() + (size_t)page * ctx->cfg.max_components_per_page,
+                                        sizeof(TraceRec) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int i = 0; i < n; ++i) {
+        h_key[i] = t[i].key; h_status[i] = t[i].status; h_sside1[i] = t[i].sside1; h_score[i] = t[i].score;
+        for (int k = 0; k < 8; ++k) h_rect1[8 * i + k] = t[i].rect1[k];
+        if (ctx->dbg_extra.size() < (size_t)(10 * n)) ctx->dbg_extra.resize(10 * n);
+        for (int k = 0; k < 8; ++k) ctx->dbg_extra[10 * i + k] = t[i].rect2[k];
+        ctx->dbg_extra[10 * i + 8] = t[i].n_off;
+        memcpy(&ctx->dbg_extra[10 * i + 9], &t[i].dist, 4);
+    }
+    return RETTO_B200_OK;
+}
+
+extern "C" const int32_t* retto_b200_debug_extra(retto_b200_ctx* ctx) { return ctx ? ctx->dbg_extra.data() : nullptr; }
+
+// debug tap: raw CompRec table of a page (8 ints per component)
+extern "C" retto_b200_status retto_b200_debug_comps(retto_b200_ctx* ctx, int32_t page, int32_t* out, int32_t max_n) {
+    if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size()) return RETTO_B200_ERR_INVALID_ARG;
+    const int n = std::min(ctx->dp_ncomp[page], max_n);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_comps.as<CompRec>() + (size_t)page * ctx->cfg.max_components_per_page, sizeof(CompRec) * n,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_debug_rowtab(retto_b200_ctx* ctx, int32_t page, int32_t* out, int32_t n_rows) {
+    if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size()) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_rowtab.as<int2>() + (size_t)page * ROWCAP, sizeof(int2) * n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RETTO_B200_OK;
+}
