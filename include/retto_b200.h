@@ -198,17 +198,18 @@ typedef struct retto_b200_batch {
     float   max_wh_ratio;  /* rec only: running maximum after this batch */
     uint64_t offset;       /* float offset of the tensor inside the batch arena */
 } retto_b200_batch;
-/* crops: per-crop (w,h) of ONE page in detection order.  kind 0 = cls, 1 = rec.
- * h_order[n_crops] receives the crop index of each planned line; h_batches[ceil(n/batch_num)]. */
-retto_b200_status retto_b200_plan_batches(const retto_b200_config* cfg, int32_t kind, const retto_b200_crop_info* h_crops,
-                                          int32_t n_crops, int32_t* h_order, retto_b200_batch* h_batches, int32_t* n_batches,
-                                          uint64_t* total_floats);
 typedef struct retto_b200_line_job {
     int32_t crop;          /* index into the current crop set */
     int32_t img_w;         /* padded width of the destination tensor */
     int32_t resized_w;     /* min(img_w, ceil(img_h * w / h)) */
     uint64_t dst_offset;   /* float offset of this line's [3,img_h,img_w] block in the batch arena */
 } retto_b200_line_job;
+/* crops: per-crop (w,h) of ONE page in detection order.  kind 0 = cls, 1 = rec.
+ * h_lines[n_crops] receives the planned lines in batch order (crop = index into `crops`, offsets
+ * relative to this page's first tensor); h_batches[ceil(n/batch_num)]. */
+retto_b200_status retto_b200_plan_batches(const retto_b200_config* cfg, int32_t kind, const retto_b200_crop_info* h_crops,
+                                          int32_t n_crops, retto_b200_line_job* h_lines, retto_b200_batch* h_batches,
+                                          int32_t* n_batches, uint64_t* total_floats);
 /* kind 0 = cls (ignores flip flags), 1 = rec (reads crops through their flip flags).
  * The batch arena is context-owned; *d_base receives its device address. */
 retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32_t kind, const retto_b200_line_job* h_lines, int32_t n_lines,

@@ -168,7 +168,7 @@ def lib() -> C.CDLL:
     L.retto_b200_scale_and_clip.argtypes = [vp, C.POINTER(Box), i32, C.c_double, C.c_double, C.c_double, C.c_double]
     L.retto_b200_crop_boxes.argtypes = [vp, C.POINTER(CropJob), i32, C.POINTER(CropInfo)]
     L.retto_b200_crop_fetch.argtypes = [vp, i32, vp]
-    L.retto_b200_plan_batches.argtypes = [C.POINTER(Config), i32, C.POINTER(CropInfo), i32, C.POINTER(i32), C.POINTER(Batch), C.POINTER(i32), C.POINTER(u64)]
+    L.retto_b200_plan_batches.argtypes = [C.POINTER(Config), i32, C.POINTER(CropInfo), i32, C.POINTER(LineJob), C.POINTER(Batch), C.POINTER(i32), C.POINTER(u64)]
     L.retto_b200_build_batches.argtypes = [vp, i32, C.POINTER(LineJob), i32, u64, C.POINTER(vp)]
     L.retto_b200_cls_postprocess.argtypes = [vp, vp, i32, C.POINTER(i32), C.POINTER(ClsResult)]
     L.retto_b200_dict_load.argtypes = [vp, C.c_char_p, C.c_size_t]

@@ -202,16 +202,16 @@ class Context:
 
     # ---- batches --------------------------------------------------------------------------------
     def plan_batches(self, kind: int, infos: Sequence[CropInfo]):
+        """ordering/batching rules of Cls/RecProcessor::process for ONE page -> (lines, batches, total_floats)"""
         n = len(infos)
         arr = (CropInfo * max(n, 1))(*infos)
-        order = (C.c_int32 * max(n, 1))()
-        nb_max = (n + 5) // 1 + 1
-        batches = (Batch * nb_max)()
+        lines = (LineJob * max(n, 1))()
+        batches = (Batch * (n + 1))()
         nb = C.c_int32()
         tot = C.c_uint64()
-        st = self._L.retto_b200_plan_batches(C.byref(self.cfg), kind, arr, n, order, batches, C.byref(nb), C.byref(tot))
+        st = self._L.retto_b200_plan_batches(C.byref(self.cfg), kind, arr, n, lines, batches, C.byref(nb), C.byref(tot))
         self._check(st)
-        return [order[i] for i in range(n)], [batches[i] for i in range(nb.value)], int(tot.value)
+        return [lines[i] for i in range(n)], [batches[i] for i in range(nb.value)], int(tot.value)
 
     def build_batches(self, kind: int, lines: Sequence[LineJob], total_floats: int) -> int:
         n = len(lines)

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -157,7 +159,7 @@ struct retto_b200_ctx {
     HostBuf h_crops;
 
     // batches
-    DevBuf d_lines, d_batch;
+    DevBuf d_lines, d_batch_cls, d_batch_rec;
     DevBuf d_cls_idx, d_cls_out;
     HostBuf h_cls;
 

@@ -1,0 +1,243 @@
+// crop.cu — K7: ImageHelper::get_crop_img (image_helper.rs:223-249): perspective rotate-crop of each text
+// box with imageproc's bicubic warp (white border), then rotate270 when h/w >= 1.5.
+//   setup kernel : 1 thread per crop — 8x8 DLT system in f64 (Gaussian elimination with partial pivoting,
+//                  same operation order as the oracle), cast to f32, cofactor inverse, class detection
+//   warp kernel  : 1 thread per output pixel — inverse map, 4x4 Catmull-Rom taps with the u8 truncation
+//                  between the horizontal and the vertical pass, gather through the read-only path
+// Roofline: HBM/L2 gather; algorithmic bytes = sum over boxes of 6*w*h (3 B read + 3 B written per pixel).
+#include "common.cuh"
+#include "db_geom.cuh"  // side_len
+
+static __device__ bool solve8(double A[8][9]) {
+    for (int col = 0; col < 8; ++col) {
+        int piv = col;
+        double best = fabs(A[col][col]);
+        for (int r = col + 1; r < 8; ++r) { const double v = fabs(A[r][col]); if (v > best) { best = v; piv = r; } }
+        if (best == 0.0) return false;
+        if (piv != col) for (int c = 0; c < 9; ++c) { const double t = A[piv][c]; A[piv][c] = A[col][c]; A[col][c] = t; }
+        for (int r = col + 1; r < 8; ++r) {
+            const double f = __ddiv_rn(A[r][col], A[col][col]);
+            if (f == 0.0) continue;
+            for (int c = col; c < 9; ++c) A[r][c] = __dsub_rn(A[r][c], __dmul_rn(f, A[col][c]));
+        }
+    }
+    for (int r = 7; r >= 0; --r) {
+        double s = A[r][8];
+        for (int c = r + 1; c < 8; ++c) s = __dsub_rn(s, __dmul_rn(A[r][c], A[c][8]));
+        A[r][8] = __ddiv_rn(s, A[r][r]);
+    }
+    return true;
+}
+
+__global__ void crop_setup_kernel(CropDev* __restrict__ crops, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CropDev c = crops[i];
+    const float* box = c.box;
+    // widths / heights (points.rs:125-169), W = max(width_brc, width_tlc), H = max(height_brc, height_tlc)
+    const float w_brc = side_len(box[6], box[7], box[4], box[5]);
+    const float w_tlc = side_len(box[0], box[1], box[2], box[3]);
+    const float h_brc = side_len(box[2], box[3], box[4], box[5]);
+    const float h_tlc = side_len(box[0], box[1], box[6], box[7]);
+    const float W = fmaxf(w_brc, w_tlc), H = fmaxf(h_brc, h_tlc);
+    const double fx[4] = {box[0], box[2], box[4], box[6]}, fy[4] = {box[1], box[3], box[5], box[7]};
+    const double tx[4] = {0.0, (double)W, (double)W, 0.0}, ty[4] = {0.0, 0.0, (double)H, (double)H};
+    double A[8][9];
+    for (int k = 0; k < 4; ++k) {
+        double* r0 = A[2 * k];
+        double* r1 = A[2 * k + 1];
+        r0[0] = 0; r0[1] = 0; r0[2] = 0; r0[3] = -fx[k]; r0[4] = -fy[k]; r0[5] = -1.0;
+        r0[6] = __dmul_rn(ty[k], fx[k]); r0[7] = __dmul_rn(ty[k], fy[k]); r0[8] = -ty[k];
+        r1[0] = fx[k]; r1[1] = fy[k]; r1[2] = 1.0; r1[3] = 0; r1[4] = 0; r1[5] = 0;
+        r1[6] = __dmul_rn(-tx[k], fx[k]); r1[7] = __dmul_rn(-tx[k], fy[k]); r1[8] = tx[k];
+    }
+    int status = RETTO_B200_OK;
+    float inv[9];
+    int cls = 2;
+    if (!solve8(A)) status = RETTO_B200_ERR_DEGENERATE_QUAD;
+    else {
+        float t[9];
+        for (int k = 0; k < 8; ++k) t[k] = (float)A[k][8];
+        t[8] = 1.0f;
+        if (fabsf(t[6]) < 1e-10f && fabsf(t[7]) < 1e-10f && fabsf(__fsub_rn(t[8], 1.0f)) < 1e-10f) {
+            if (fabsf(__fsub_rn(t[0], 1.0f)) < 1e-10f && fabsf(t[1]) < 1e-10f && fabsf(t[3]) < 1e-10f && fabsf(__fsub_rn(t[4], 1.0f)) < 1e-10f) cls = 0;
+            else cls = 1;
+        }
+        const float t00 = t[0], t01 = t[1], t02 = t[2], t10 = t[3], t11 = t[4], t12 = t[5], t20 = t[6], t21 = t[7], t22 = t[8];
+#define M2(a, b, c, d) __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d))
+        const float m00 = M2(t11, t22, t12, t21);
+        const float m01 = M2(t10, t22, t12, t20);
+        const float m02 = M2(t10, t21, t11, t20);
+        const float det = __fadd_rn(__fsub_rn(__fmul_rn(t00, m00), __fmul_rn(t01, m01)), __fmul_rn(t02, m02));
+        if (fabsf(det) < 1e-10f) status = RETTO_B200_ERR_DEGENERATE_QUAD;
+        else {
+            const float m10 = M2(t01, t22, t02, t21);
+            const float m11 = M2(t00, t22, t02, t20);
+            const float m12 = M2(t00, t21, t01, t20);
+            const float m20 = M2(t01, t12, t02, t11);
+            const float m21 = M2(t00, t12, t02, t10);
+            const float m22 = M2(t00, t11, t01, t10);
+#undef M2
+            const float iv[9] = {__fdiv_rn(m00, det), __fdiv_rn(-m10, det), __fdiv_rn(m20, det), __fdiv_rn(-m01, det), __fdiv_rn(m11, det),
+                                 __fdiv_rn(-m21, det), __fdiv_rn(m02, det), __fdiv_rn(-m12, det), __fdiv_rn(m22, det)};
+            for (int k = 0; k < 8; ++k) inv[k] = __fdiv_rn(iv[k], iv[8]);
+            inv[8] = 1.0f;
+        }
+    }
+    if (status == RETTO_B200_OK) { for (int k = 0; k < 9; ++k) crops[i].t[k] = inv[k]; }
+    crops[i].cls = cls;
+    crops[i].status = status;
+}
+
+__device__ __forceinline__ unsigned char clamp_u8_trunc(float x) { return x < 255.0f ? (x > 0.0f ? (unsigned char)x : 0) : 255; }
+__device__ __forceinline__ float cubic(float p0, float p1, float p2, float p3, float x) {
+    // p1 + 0.5 * x * (p2 - p0 + x * (2.0 * p0 - 5.0 * p1 + 4.0 * p2 - p3 + x * (3.0 * (p1 - p2) + p3 - p0)))
+    const float a = __fsub_rn(__fadd_rn(__fmul_rn(3.0f, __fsub_rn(p1, p2)), p3), p0);
+    const float b = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(2.0f, p0), __fmul_rn(5.0f, p1)), __fmul_rn(4.0f, p2)), p3), __fmul_rn(x, a));
+    const float c = __fadd_rn(__fsub_rn(p2, p0), __fmul_rn(x, b));
+    return __fadd_rn(p1, __fmul_rn(__fmul_rn(0.5f, x), c));
+}
+
+__global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restrict__ crops, const int* __restrict__ unit_prefix, int n_crops,
+                                                         int total_units, unsigned char* __restrict__ pix) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total_units) return;
+    const int ci = rt_find_segment(unit_prefix, n_crops, u);
+    const CropDev& c = crops[ci];
+    if (c.status != RETTO_B200_OK) return;
+    const int lu = u - unit_prefix[ci];
+    const int w = c.rot ? c.h : c.w, h = c.rot ? c.w : c.h;  // un-rotated warp size
+    const int y = lu / w, x = lu - y * w;
+    const float xf = (float)x, yf = (float)y;
+    float px, py;
+    if (c.cls == 2) {
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(c.t[6], xf), __fmul_rn(c.t[7], yf)), c.t[8]);
+        px = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.t[0], xf), __fmul_rn(c.t[1], yf)), c.t[2]), d);
+        py = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.t[3], xf), __fmul_rn(c.t[4], yf)), c.t[5]), d);
+    } else if (c.cls == 1) {
+        px = __fadd_rn(__fadd_rn(__fmul_rn(c.t[0], xf), __fmul_rn(c.t[1], yf)), c.t[2]);
+        py = __fadd_rn(__fadd_rn(__fmul_rn(c.t[3], xf), __fmul_rn(c.t[4], yf)), c.t[5]);
+    } else {
+        px = __fadd_rn(xf, c.t[2]);
+        py = __fadd_rn(yf, c.t[5]);
+    }
+    unsigned char rgb[3] = {255, 255, 255};
+    const float left = __fsub_rn(floorf(px), 1.0f), right = __fadd_rn(left, 4.0f);
+    const float top = __fsub_rn(floorf(py), 1.0f), bottom = __fadd_rn(top, 4.0f);
+    if (!(left < 0.0f || right >= (float)c.page_w || top < 0.0f || bottom >= (float)c.page_h) && isfinite(px) && isfinite(py)) {
+        const float xw = __fsub_rn(px, __fadd_rn(left, 1.0f)), yw = __fsub_rn(py, __fadd_rn(top, 1.0f));
+        const unsigned l = (unsigned)left, tp = (unsigned)top;
+        float col[3][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const unsigned char* row = c.page + ((size_t)(tp + r) * c.page_w + l) * 3;
+            unsigned char v[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) v[k] = __ldg(row + k);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                col[ch][r] = (float)clamp_u8_trunc(cubic((float)v[ch], (float)v[3 + ch], (float)v[6 + ch], (float)v[9 + ch], xw));
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) rgb[ch] = clamp_u8_trunc(cubic(col[ch][0], col[ch][1], col[ch][2], col[ch][3], yw));
+    }
+    size_t o;
+    if (c.rot) o = ((size_t)(w - 1 - x) * h + y) * 3;  // rotate270: out(y, w-1-x) = in(x, y), out is h wide
+    else o = ((size_t)y * w + x) * 3;
+    unsigned char* dst = pix + c.offset + o;
+    dst[0] = rgb[0]; dst[1] = rgb[1]; dst[2] = rgb[2];
+}
+
+// host: crop dims (same IEEE operations as the setup kernel; size planning only)
+static inline float side_len_h(float ax, float ay, float bx, float by) {
+    const double dx = (double)(ax - bx), dy = (double)(ay - by);
+    return (float)std::sqrt(dx * dx + dy * dy);
+}
+void rt_crop_dims(const float box[8], int* cw, int* ch, int* rot) {
+    const float w_brc = side_len_h(box[6], box[7], box[4], box[5]);
+    const float w_tlc = side_len_h(box[0], box[1], box[2], box[3]);
+    const float h_brc = side_len_h(box[2], box[3], box[4], box[5]);
+    const float h_tlc = side_len_h(box[0], box[1], box[6], box[7]);
+    const float W = std::max(w_brc, w_tlc), H = std::max(h_brc, h_tlc);
+    const uint32_t w = (uint32_t)W, h = (uint32_t)H;
+    const int r = (w > 0) && ((float)h / (float)w >= 1.5f);
+    *rot = r;
+    *cw = r ? (int)h : (int)w;
+    *ch = r ? (int)w : (int)h;
+}
+
+extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int32_t n,
+                                                   retto_b200_crop_info* h_infos) {
+    if (!ctx || n < 0 || (n > 0 && (!h_jobs || !h_infos))) return RETTO_B200_ERR_INVALID_ARG;
+    ctx->crops.clear();
+    if (n == 0) return RETTO_B200_OK;
+    std::vector<int> prefix(n + 1, 0);
+    unsigned long long off = 0;
+    for (int i = 0; i < n; ++i) {
+        const retto_b200_crop_job& j = h_jobs[i];
+        if (!j.d_page || j.page_h <= 0 || j.page_w <= 0) { ctx->set_error("crop_boxes: bad job " + std::to_string(i)); return RETTO_B200_ERR_INVALID_ARG; }
+        CropDev c;
+        memset(&c, 0, sizeof(c));
+        c.page = j.d_page; c.page_h = j.page_h; c.page_w = j.page_w;
+        memcpy(c.box, j.box.xy, sizeof(float) * 8);
+        rt_crop_dims(c.box, &c.w, &c.h, &c.rot);
+        c.offset = off;
+        const long long px = (long long)c.w * c.h;
+        if (px <= 0 || prefix[i] + px > 0x7fffffffLL) { c.status = RETTO_B200_ERR_DEGENERATE_QUAD; c.w = c.h = 0; prefix[i + 1] = prefix[i]; }
+        else { prefix[i + 1] = prefix[i] + (int)px; off += ((unsigned long long)px * 3 + 15) & ~15ULL; }
+        ctx->crops.push_back(c);
+    }
+    cudaStream_t st = ctx->stream;
+    RT_CUDA_OK(ctx, ctx->d_crop_pix.ensure((size_t)std::max<unsigned long long>(off, 16), st));
+    RT_CUDA_OK(ctx, ctx->d_crop_flip.ensure(sizeof(int) * (size_t)n, st));
+    RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_crop_flip.p, 0, sizeof(int) * (size_t)n, st));
+    {
+        std::vector<char> blob(sizeof(CropDev) * n + sizeof(int) * (n + 1));
+        memcpy(blob.data(), ctx->crops.data(), sizeof(CropDev) * n);
+        memcpy(blob.data() + sizeof(CropDev) * n, prefix.data(), sizeof(int) * (n + 1));
+        RT_TRY(rt_upload(ctx, ctx->d_crop_descs, blob.data(), blob.size()));
+    }
+    CropDev* d_crops = ctx->d_crop_descs.as<CropDev>();
+    const int* d_prefix = reinterpret_cast<const int*>(ctx->d_crop_descs.as<char>() + sizeof(CropDev) * n);
+    crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n);
+    RT_LAUNCH_CHECK(ctx);
+    const int total = prefix[n];
+    if (total > 0) {
+        crop_warp_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_crops, d_prefix, n, total, ctx->d_crop_pix.as<unsigned char>());
+        RT_LAUNCH_CHECK(ctx);
+    }
+    // statuses back (projection degeneracy is only known on the device)
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->crops.data(), d_crops, sizeof(CropDev) * n, cudaMemcpyDeviceToHost, st));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    retto_b200_status ret = RETTO_B200_OK;
+    for (int i = 0; i < n; ++i) {
+        const CropDev& c = ctx->crops[i];
+        h_infos[i].w = c.w; h_infos[i].h = c.h; h_infos[i].rotated270 = c.rot; h_infos[i].status = c.status; h_infos[i].offset = c.offset;
+        if (c.status != RETTO_B200_OK) { ctx->set_error("crop_boxes: degenerate quad " + std::to_string(i) + " (reference: from_control_points().unwrap() panics)"); ret = RETTO_B200_ERR_DEGENERATE_QUAD; }
+    }
+    return ret;
+}
+
+__global__ void crop_flip_copy_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int n_px, int flip) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const int s = flip ? n_px - 1 - i : i;
+    dst[3 * i] = src[3 * s]; dst[3 * i + 1] = src[3 * s + 1]; dst[3 * i + 2] = src[3 * s + 2];
+}
+
+extern "C" retto_b200_status retto_b200_crop_fetch(retto_b200_ctx* ctx, int32_t i, uint8_t* h_out) {
+    if (!ctx || i < 0 || i >= (int)ctx->crops.size() || !h_out) return RETTO_B200_ERR_INVALID_ARG;
+    const CropDev& c = ctx->crops[i];
+    const int n_px = c.w * c.h;
+    if (n_px == 0) return RETTO_B200_OK;
+    int flip = 0;
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(&flip, ctx->d_crop_flip.as<int>() + i, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_stage3.ensure((size_t)n_px * 3, ctx->stream));
+    // rotate_180_in_place (image_helper.rs:268-286) is applied lazily: materialise it here
+    crop_flip_copy_kernel<<<(n_px + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_crop_pix.as<unsigned char>() + c.offset, ctx->d_stage3.as<unsigned char>(), n_px, flip);
+    RT_LAUNCH_CHECK(ctx);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_stage3.p, (size_t)n_px * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RETTO_B200_OK;
+}

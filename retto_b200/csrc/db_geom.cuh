@@ -20,7 +20,7 @@
 // top to the right, down the right side, back up the left side; collinear points dropped.
 // Serial (call from one lane).  `out` needs room for 2*n points.  Returns the hull size.
 template <class RowFn>
-__device__ int hull_from_rows(int n, RowFn row, int2* out) {
+static __device__ int hull_from_rows(int n, RowFn row, int2* out) {
     auto turn_ok = [](int2 p, int2 q, int2 r) -> bool {  // strictly "CounterClockwise" in imageproc's sense
         const long long v = (long long)(q.y - p.y) * (long long)(r.x - q.x) - (long long)(q.x - p.x) * (long long)(r.y - q.y);
         return v < 0;
@@ -66,7 +66,7 @@ __device__ int hull_from_rows(int n, RowFn row, int2* out) {
 // Rotating calipers over hull.windows(2) (closing edge not visited), whole warp cooperates: lane l
 // evaluates edges l, l+32, ...; the winner is the first edge with the strictly smallest area.
 // q[8] = tl.x tl.y tr.x tr.y br.x br.y bl.x bl.y as doubles holding integers (floor/ceil applied).
-__device__ void warp_min_area_rect(const int2* hull, int n, double q[8]) {
+static __device__ void warp_min_area_rect(const int2* hull, int n, double q[8]) {
     const int lane = threadIdx.x & 31;
     if (n == 1) {
 #pragma unroll
@@ -167,7 +167,7 @@ __device__ __forceinline__ void cover_add(RowCover& rc, int a, int b, int bw) {
     rc.a[rc.n] = a; rc.b[rc.n] = b; rc.n++;
 }
 
-__device__ void polygon_row_cover(const int px[4], const int py[4], int bw, int bh, int y, RowCover& rc) {
+static __device__ void polygon_row_cover(const int px[4], const int py[4], int bw, int bh, int y, RowCover& rc) {
     rc.n = 0;
     // scan-fill intersections
     int inter[8];
@@ -249,7 +249,7 @@ __device__ void polygon_row_cover(const int px[4], const int py[4], int bw, int 
 // accumulated in the reference's order (raster order, sequential f32) — the warp loads 32 pixels
 // coalesced and every lane replays the same 32-step add chain through shuffles, so the result is
 // bit-identical to the scalar fold.  Returns false where the reference panics (poly[0] == poly[3]).
-__device__ bool warp_box_score(const float* __restrict__ pred, int h, int w, const int qx[4], const int qy[4], float* score) {
+static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int w, const int qx[4], const int qy[4], float* score) {
     const int lane = threadIdx.x & 31;
     if (qx[0] == qx[3] && qy[0] == qy[3]) return false;
     int x_min = min(min(qx[0], qx[1]), min(qx[2], qx[3])), x_max = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
@@ -283,7 +283,7 @@ __device__ bool warp_box_score(const float* __restrict__ pred, int h, int w, con
 // ---- unclip (det_processor.rs:223-252) ---------------------------------------------------------------
 // geo 0.30 unsigned_area (f32 shoelace, shifted by the first vertex) and Euclidean length (f32 sum of
 // hypotf, restated as (float)sqrt((double)dx*dx + (double)dy*dy)); distance = area * ratio / perimeter.
-__device__ float unclip_distance(const int qx[4], const int qy[4], float ratio) {
+static __device__ float unclip_distance(const int qx[4], const int qy[4], float ratio) {
     float bx[4], by[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { bx[i] = (float)qx[i]; by[i] = (float)qy[i]; }
@@ -309,7 +309,7 @@ __device__ __forceinline__ long long clipper_round(double v) { return v < 0 ? (l
 
 // Clipper 6.4.2 ClipperOffset (jtRound, etClosedPolygon) for one quad; serial.  Writes up to max_out
 // points; returns the count, 0 when Clipper drops the path (< 3 distinct vertices), -1 on overflow.
-__device__ int clipper_offset_round(const int qx[4], const int qy[4], double delta, double arc_tol, int2* out, int max_out) {
+static __device__ int clipper_offset_round(const int qx[4], const int qy[4], double delta, double arc_tol, int2* out, int max_out) {
     long long X[4], Y[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { X[i] = qx[(i + 1) & 3]; Y[i] = qy[(i + 1) & 3]; }  // geo-clipper: ring minus its first point

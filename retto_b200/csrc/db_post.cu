@@ -794,3 +794,29 @@ extern "C" retto_b200_status retto_b200_debug_rowtab(retto_b200_ctx* ctx, int32_
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return RETTO_B200_OK;
 }
+
+// batched variant used by the session: per-box (inv_w, inv_h, ori_w, ori_h), one launch, one sync
+__global__ void scale_clip_multi_kernel(retto_b200_box* b, const double4* __restrict__ prm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 p = prm[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        b[i].xy[2 * k] = scale_clip_1(b[i].xy[2 * k], p.x, p.z);
+        b[i].xy[2 * k + 1] = scale_clip_1(b[i].xy[2 * k + 1], p.y, p.w);
+    }
+}
+retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h_boxes, const double* h_params4, int n) {
+    if (n == 0) return RETTO_B200_OK;
+    const size_t bb = (sizeof(retto_b200_box) * (size_t)n + 31) & ~size_t(31);
+    std::vector<char> blob(bb + sizeof(double) * 4 * (size_t)n);
+    memcpy(blob.data(), h_boxes, sizeof(retto_b200_box) * (size_t)n);
+    memcpy(blob.data() + bb, h_params4, sizeof(double) * 4 * (size_t)n);
+    RT_TRY(rt_upload(ctx, ctx->d_stage3, blob.data(), blob.size()));
+    scale_clip_multi_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_stage3.as<retto_b200_box>(),
+                                                                      reinterpret_cast<const double4*>(ctx->d_stage3.as<char>() + bb), n);
+    RT_LAUNCH_CHECK(ctx);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_boxes, ctx->d_stage3.p, sizeof(retto_b200_box) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RETTO_B200_OK;
+}

@@ -1,0 +1,194 @@
+// rec_batch.cu — K8 / K9: cls + rec batch building and the cls postprocess / 180-degree flip.
+//   plan_batches  (host) : ordering + batching rules of ClsProcessor::process / RecProcessor::process
+//                          (cls_processor.rs:135-140, rec_processor.rs:223-238) — sizes only, no pixels
+//   build_batches (K8)   : ImageHelper::resize_norm_image + concatenate (image_helper.rs:176-209):
+//                          thumbnail to 48 x resized_w, px/255, (v-.5)/.5, RGB planes, zero pad to img_w,
+//                          written straight into the [n,3,48,img_w] batch tensor; rec reads the crop through
+//                          its flip flag (rotate_180_in_place as an index transform: zero bytes moved)
+//   cls_postprocess (K9) : first-max argmax over [n,2], label/score, flip flag when label==180 && score>=thresh
+// Roofline: HBM; algorithmic bytes per line = 3*w*h (crop read) + 12*48*img_w (tensor write).
+#include "common.cuh"
+#include "thumbnail.cuh"
+
+struct FlipReader {
+    const unsigned char* __restrict__ src;
+    unsigned w, h;
+    int flip;
+    __device__ __forceinline__ uchar3 operator()(unsigned x, unsigned y) const {
+        if (flip) { x = w - 1 - x; y = h - 1 - y; }
+        const unsigned char* p = src + ((size_t)y * w + x) * 3;
+        return make_uchar3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+    }
+};
+
+// one thread per output pixel (x < img_w, y < img_h) of one line; 3 planes written
+__global__ void __launch_bounds__(256) build_batches_kernel(const LineDev* __restrict__ lines, const int* __restrict__ unit_prefix, int n_lines,
+                                                             int total_units, const CropDev* __restrict__ crops,
+                                                             const unsigned char* __restrict__ crop_pix, const int* __restrict__ flip_flags,
+                                                             int use_flip, int img_h, float* __restrict__ out) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total_units) return;
+    const int li = rt_find_segment(unit_prefix, n_lines, u);
+    const LineDev ln = lines[li];
+    const int lu = u - unit_prefix[li];
+    const int y = lu / ln.img_w, x = lu - y * ln.img_w;
+    const size_t plane = (size_t)img_h * ln.img_w;
+    float* dst = out + ln.dst_offset + (size_t)y * ln.img_w + x;
+    if (x >= ln.resized_w) {
+        dst[0] = 0.0f; dst[plane] = 0.0f; dst[2 * plane] = 0.0f;
+        return;
+    }
+    const CropDev& c = crops[ln.crop];
+    const unsigned cw = (unsigned)c.w, chh = (unsigned)c.h;
+    const FlipReader rd{crop_pix + c.offset, cw, chh, use_flip ? flip_flags[ln.crop] : 0};
+    const float xr = __fdiv_rn((float)cw, (float)ln.resized_w), yr = __fdiv_rn((float)chh, (float)img_h);
+    unsigned char px[3];
+    thumbnail_pixel(rd, cw, chh, thumb_axis(x, xr, cw), thumb_axis(y, yr, chh), px);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float v = __fdiv_rn((float)px[ch], 255.0f);
+        dst[ch * plane] = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+    }
+}
+
+// ---- K9 ------------------------------------------------------------------------------------------------
+struct ClsLine { const float* logits; int crop; int pad; };
+__global__ void cls_post_kernel(const ClsLine* __restrict__ lines, int n, int ncls, int label0, int label1, float thresh,
+                                int* __restrict__ flip_flags, int* __restrict__ out_label, float* __restrict__ out_score,
+                                int* __restrict__ nan_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = lines[i].logits;
+    int best = 0;
+    float bv = r[0];
+    bool nan = bv != bv;
+    for (int k = 1; k < ncls; ++k) {
+        const float v = r[k];
+        nan |= (v != v);
+        if (v > bv) { bv = v; best = k; }
+    }
+    if (nan) { *nan_flag = 1; }
+    const int label = best == 0 ? label0 : label1;
+    out_label[i] = label;
+    out_score[i] = bv;
+    // cls_processor.rs:164-166
+    if (label == 180 && bv >= thresh) flip_flags[lines[i].crop] ^= 1;
+}
+
+// ---- host ------------------------------------------------------------------------------------------------
+extern "C" retto_b200_status retto_b200_plan_batches(const retto_b200_config* cfg, int32_t kind, const retto_b200_crop_info* crops,
+                                                     int32_t n, retto_b200_line_job* h_lines, retto_b200_batch* h_batches,
+                                                     int32_t* n_batches, uint64_t* total_floats) {
+    if (!cfg || n < 0 || (n > 0 && (!crops || !h_lines || !h_batches)) || !n_batches || !total_floats) return RETTO_B200_ERR_INVALID_ARG;
+    const int* shape = kind == 0 ? cfg->cls_image_shape : cfg->rec_image_shape;
+    const int img_h = shape[1], img_w_cfg = shape[2];
+    const int batch_num = std::max(1, kind == 0 ? cfg->cls_batch_num : cfg->rec_batch_num);
+    // stable sort by Reverse(OrderedFloat(ori_ratio)), ori_ratio = h as f64 / w as f64 (image_helper.rs:79-82)
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        const double ra = (double)crops[a].h / (double)crops[a].w, rb = (double)crops[b].h / (double)crops[b].w;
+        return ra > rb;  // descending; OrderedFloat total order (NaN greatest) is unreachable for w,h > 0
+    });
+    float max_wh_ratio = (float)img_w_cfg / (float)img_h;  // rec_processor.rs:226-227, carried across batches
+    uint64_t off = 0;
+    int nb = 0;
+    for (int b0 = 0; b0 < n; b0 += batch_num) {
+        const int nl = std::min(batch_num, n - b0);
+        int img_w = img_w_cfg;
+        if (kind == 1) {
+            for (int k = 0; k < nl; ++k) {
+                const retto_b200_crop_info& c = crops[idx[b0 + k]];
+                const float wh = (float)c.w / (float)c.h;  // rec_processor.rs:234-236 (current dims == crop dims)
+                if (wh > max_wh_ratio) max_wh_ratio = wh;
+            }
+            img_w = (int)(size_t)((float)img_h * max_wh_ratio);  // image_helper.rs:179
+        }
+        retto_b200_batch& bt = h_batches[nb++];
+        bt.first_line = b0; bt.n = nl; bt.img_w = img_w; bt.max_wh_ratio = max_wh_ratio; bt.offset = off;
+        for (int k = 0; k < nl; ++k) {
+            const retto_b200_crop_info& c = crops[idx[b0 + k]];
+            const double rw = std::ceil((double)img_h * (double)c.w / (double)c.h);  // image_helper.rs:183
+            retto_b200_line_job& l = h_lines[b0 + k];
+            l.crop = idx[b0 + k];
+            l.img_w = img_w;
+            l.resized_w = (int)std::min<size_t>((size_t)img_w, (size_t)rw);
+            l.dst_offset = off + (uint64_t)k * 3 * img_h * img_w;
+        }
+        off += (uint64_t)nl * 3 * img_h * img_w;
+    }
+    *n_batches = nb;
+    *total_floats = off;
+    return RETTO_B200_OK;
+}
+
+extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32_t kind, const retto_b200_line_job* h_lines, int32_t n_lines,
+                                                      uint64_t total_floats, float** d_base) {
+    if (!ctx || n_lines < 0 || (n_lines > 0 && !h_lines) || !d_base) return RETTO_B200_ERR_INVALID_ARG;
+    DevBuf& buf = kind == 0 ? ctx->d_batch_cls : ctx->d_batch_rec;
+    RT_CUDA_OK(ctx, buf.ensure(std::max<size_t>((size_t)total_floats * 4, 16), ctx->stream));
+    *d_base = buf.as<float>();
+    if (n_lines == 0) return RETTO_B200_OK;
+    const int img_h = kind == 0 ? ctx->cfg.cls_image_shape[1] : ctx->cfg.rec_image_shape[1];
+    std::vector<LineDev> lines(n_lines);
+    std::vector<int> prefix(n_lines + 1, 0);
+    for (int i = 0; i < n_lines; ++i) {
+        const retto_b200_line_job& l = h_lines[i];
+        if (l.crop < 0 || l.crop >= (int)ctx->crops.size() || l.img_w <= 0 || l.resized_w < 0 || l.resized_w > l.img_w ||
+            l.dst_offset + (uint64_t)3 * img_h * l.img_w > total_floats || ctx->crops[l.crop].status != RETTO_B200_OK) {
+            ctx->set_error("build_batches: bad line " + std::to_string(i));
+            return RETTO_B200_ERR_INVALID_ARG;
+        }
+        lines[i] = LineDev{l.crop, l.img_w, l.resized_w, 0, l.dst_offset};
+        const long long u = (long long)prefix[i] + (long long)img_h * l.img_w;
+        if (u > 0x7fffffffLL) { ctx->set_error("build_batches: too many pixels"); return RETTO_B200_ERR_CAPACITY; }
+        prefix[i + 1] = (int)u;
+    }
+    std::vector<char> blob(sizeof(LineDev) * n_lines + sizeof(int) * (n_lines + 1));
+    memcpy(blob.data(), lines.data(), sizeof(LineDev) * n_lines);
+    memcpy(blob.data() + sizeof(LineDev) * n_lines, prefix.data(), sizeof(int) * (n_lines + 1));
+    RT_TRY(rt_upload(ctx, ctx->d_lines, blob.data(), blob.size()));
+    const LineDev* d_lines = ctx->d_lines.as<LineDev>();
+    const int* d_prefix = reinterpret_cast<const int*>(ctx->d_lines.as<char>() + sizeof(LineDev) * n_lines);
+    const int total = prefix[n_lines];
+    build_batches_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(d_lines, d_prefix, n_lines, total, ctx->d_crop_descs.as<CropDev>(),
+                                                                       ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
+                                                                       kind == 1 ? 1 : 0, img_h, buf.as<float>());
+    RT_LAUNCH_CHECK(ctx);
+    return RETTO_B200_OK;
+}
+
+retto_b200_status rt_cls_postprocess_ptrs(retto_b200_ctx* ctx, const std::vector<const float*>& logits, const int32_t* crop_index, int n,
+                                          retto_b200_cls_result* h_results) {
+    if (n == 0) return RETTO_B200_OK;
+    std::vector<ClsLine> lines(n);
+    for (int i = 0; i < n; ++i) {
+        if (crop_index[i] < 0 || crop_index[i] >= (int)ctx->crops.size()) { ctx->set_error("cls_postprocess: bad crop index"); return RETTO_B200_ERR_INVALID_ARG; }
+        lines[i] = ClsLine{logits[i], crop_index[i], 0};
+    }
+    RT_TRY(rt_upload(ctx, ctx->d_cls_idx, lines.data(), sizeof(ClsLine) * n));
+    RT_CUDA_OK(ctx, ctx->d_cls_out.ensure(sizeof(int) * (2 * (size_t)n + 1), ctx->stream));
+    int* d_label = ctx->d_cls_out.as<int>();
+    float* d_score = reinterpret_cast<float*>(d_label + n);
+    int* d_nan = d_label + 2 * n;
+    RT_CUDA_OK(ctx, cudaMemsetAsync(d_nan, 0, sizeof(int), ctx->stream));
+    cls_post_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_cls_idx.as<ClsLine>(), n, 2, ctx->cfg.cls_label[0], ctx->cfg.cls_label[1],
+                                                              ctx->cfg.cls_thresh, ctx->d_crop_flip.as<int>(), d_label, d_score, d_nan);
+    RT_LAUNCH_CHECK(ctx);
+    RT_CUDA_OK(ctx, ctx->h_cls.ensure(sizeof(int) * (2 * (size_t)n + 1)));
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_cls.p, d_label, sizeof(int) * (2 * (size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    const int* hl = ctx->h_cls.as<int>();
+    const float* hs = reinterpret_cast<const float*>(hl + n);
+    for (int i = 0; i < n; ++i) { h_results[i].label = hl[i]; h_results[i].score = hs[i]; }
+    if (hl[2 * n]) { ctx->set_error("cls_postprocess: NaN logits (reference: argmax().unwrap() panics, cls_processor.rs:113)"); return RETTO_B200_ERR_NAN_LOGITS; }
+    return RETTO_B200_OK;
+}
+
+extern "C" retto_b200_status retto_b200_cls_postprocess(retto_b200_ctx* ctx, const float* d_logits, int32_t n, const int32_t* h_crop_index,
+                                                        retto_b200_cls_result* h_results) {
+    if (!ctx || n < 0 || (n > 0 && (!d_logits || !h_crop_index || !h_results))) return RETTO_B200_ERR_INVALID_ARG;
+    std::vector<const float*> ptrs(n);
+    for (int i = 0; i < n; ++i) ptrs[i] = d_logits + 2 * (size_t)i;
+    return rt_cls_postprocess_ptrs(ctx, ptrs, h_crop_index, n, h_results);
+}

@@ -1,0 +1,250 @@
+"""GPU parity: rotate-crop (K7), cls/rec batch build (K8), cls postprocess + flip (K9) and the whole
+RettoSession::process_pipeline against the CPU oracle pipeline — boxes, labels, strings bit-exact."""
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+class NpWorker:
+    """deterministic stand-in for RettoInnerWorker used on BOTH sides (oracle gets numpy, the CUDA session
+    gets the same functions through CallableWorker)."""
+
+    def __init__(self, probmap, n_classes=6625):
+        self.probmap = probmap
+        self.C = n_classes
+
+    def det(self, x):
+        assert x.shape[0] == 1 and x.shape[1] == 3
+        assert x.shape[2:] == self.probmap.shape, (x.shape, self.probmap.shape)
+        return self.probmap[None, None]
+
+    def cls(self, x):
+        n = x.shape[0]
+        out = np.zeros((n, 2), np.float32)
+        for i in range(n):
+            left, right = float(x[i, :, :, :96].sum()), float(x[i, :, :, 96:].sum())
+            s = np.float32(0.95 if (int(abs(left) * 7) % 3 == 0) else 0.6)
+            out[i] = (1 - s, s) if left > right else (s, 1 - s)
+        return out
+
+    def rec(self, x):
+        n, _, _, W = x.shape
+        T = W // 8
+        out = np.zeros((n, T, self.C), np.float32)
+        for i in range(n):
+            rng = np.random.default_rng(zlib.crc32(np.ascontiguousarray(x[i]).tobytes()))
+            out[i] = rng.random((T, self.C), dtype=np.float32) * np.float32(1e-3)
+            cls = rng.integers(0, self.C, T)
+            cls[rng.random(T) < 0.4] = 0
+            out[i, np.arange(T), cls] = 0.5 + 0.5 * rng.random(T, dtype=np.float32)
+        return out
+
+
+def test_crop_parity(ctx):
+    import torch
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    page = rng.integers(0, 256, (700, 900, 3), dtype=np.uint8)
+    boxes = []
+    # axis-aligned (translation class), rotated rectangles (projection class), tall (rotate270), near the border (white fill)
+    boxes.append([[50, 60], [350, 60], [350, 100], [50, 100]])
+    boxes.append([[100, 200], [500, 230], [497, 270], [97, 240]])
+    boxes.append([[600, 100], [640, 100], [640, 400], [600, 400]])
+    boxes.append([[0, 0], [200, 0], [200, 30], [0, 30]])
+    boxes.append([[700, 650], [899, 655], [898, 699], [699, 694]])
+    boxes.append([[300, 400], [420, 520], [390, 550], [270, 430]])
+    for _ in range(10):
+        cx, cy = rng.uniform(150, 750), rng.uniform(100, 600)
+        w, h, a = rng.uniform(30, 280), rng.uniform(10, 60), rng.uniform(-0.5, 0.5)
+        c, s = np.cos(a), np.sin(a)
+        pts = [(-w / 2, -h / 2), (w / 2, -h / 2), (w / 2, h / 2), (-w / 2, h / 2)]
+        boxes.append([[round(cx + x * c - y * s), round(cy + x * s + y * c)] for x, y in pts])
+    boxes = np.array(boxes, np.float32)
+    g = _t(page)
+    torch.cuda.synchronize()
+    infos = ctx.crop_boxes([g], [0] * len(boxes), boxes)
+    for i, b in enumerate(boxes):
+        ref = O.get_crop_img(page, b)
+        cw, ch, rot = O.crop_dims(b)
+        assert (infos[i].w, infos[i].h, infos[i].rotated270) == (cw, ch, rot)
+        got = ctx.crop_fetch(i, infos[i])
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), f"crop {i}: {np.abs(got.astype(int) - ref.astype(int)).max()} max diff"
+
+
+def test_batches_and_cls_flip_parity(ctx):
+    import torch
+    from oracle import oracle as O
+    from oracle.pipeline import stable_order_desc_ratio
+    from retto_b200._lib import CropInfo, LineJob
+    rng = np.random.default_rng(1)
+    page = rng.integers(0, 256, (600, 1200, 3), dtype=np.uint8)
+    boxes = []
+    for k in range(15):
+        x0, y0 = int(rng.integers(5, 300)), 10 + 38 * k
+        w, h = int(rng.integers(40, 850)), int(rng.integers(12, 34))
+        boxes.append([[x0, y0], [x0 + w, y0 + 1], [x0 + w, y0 + h], [x0, y0 + h - 1]])
+    boxes.append([[1000, 100], [1030, 100], [1030, 300], [1000, 300]])  # tall -> rotate270
+    boxes = np.array(boxes, np.float32)
+    g = _t(page)
+    torch.cuda.synchronize()
+    infos = ctx.crop_boxes([g], [0] * len(boxes), boxes)
+    crops = [O.get_crop_img(page, b) for b in boxes]
+    dims = [c.shape[:2] for c in crops]
+    order = stable_order_desc_ratio(dims)
+    # cls batches
+    lines, batches, total = ctx.plan_batches(0, infos)
+    assert [l.crop for l in lines] == order
+    base = ctx.build_batches(0, lines, total)
+    host = np.zeros(total, np.float32)
+    ctx._check(ctx._L.retto_b200_d2h(ctx._h, host.ctypes.data, base, total * 4))
+    ctx.sync()
+    for l in lines:
+        ref = O.resize_norm_image(crops[l.crop], (3, 48, 192), None)
+        got = host[l.dst_offset:l.dst_offset + 3 * 48 * 192].reshape(3, 48, 192)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"cls line crop {l.crop}"
+    # cls postprocess: flip crops 0, 3, 7 (label 180 & score >= .9), not 5 (score < .9), not 2 (label 0)
+    n = len(lines)
+    logits = np.tile(np.array([[0.8, 0.2]], np.float32), (n, 1))
+    pos = {l.crop: k for k, l in enumerate(lines)}
+    for c in (0, 3, 7):
+        logits[pos[c]] = (0.05, 0.95)
+    logits[pos[5]] = (0.2, 0.8)
+    logits[pos[2]] = (0.97, 0.03)
+    logits[pos[9]] = (0.5, 0.5)   # tie -> first max -> label 0
+    gl = _t(logits)
+    torch.cuda.synchronize()
+    res = ctx.cls_postprocess(gl, [l.crop for l in lines])
+    st, am, sc = O.cls_postprocess(logits)
+    for k in range(n):
+        assert res[k][0] == (0, 180)[am[k]] and np.float32(res[k][1]) == sc[k]
+    flipped = {c: (c in (0, 3, 7)) for c in range(len(crops))}
+    for c in (0, 2, 3):
+        got = ctx.crop_fetch(c, infos[c])
+        ref = crops[c][::-1, ::-1] if flipped[c] else crops[c]
+        assert np.array_equal(got, ref)
+    # rec batches (running max_wh_ratio, flips applied as an index transform)
+    lines, batches, total = ctx.plan_batches(1, infos)
+    assert [l.crop for l in lines] == order
+    base = ctx.build_batches(1, lines, total)
+    host = np.zeros(total, np.float32)
+    ctx._check(ctx._L.retto_b200_d2h(ctx._h, host.ctypes.data, base, total * 4))
+    ctx.sync()
+    mx = np.float32(320) / np.float32(48)
+    for b in batches:
+        for k in range(b.n):
+            i = lines[b.first_line + k].crop
+            wh = np.float32(dims[i][1]) / np.float32(dims[i][0])
+            mx = max(mx, wh)
+        assert np.float32(b.max_wh_ratio) == mx
+        for k in range(b.n):
+            l = lines[b.first_line + k]
+            ref = O.resize_norm_image(crops[l.crop], (3, 48, 320), float(mx), flip180=flipped[l.crop])
+            assert ref.shape[2] == b.img_w == l.img_w
+            got = host[l.dst_offset:l.dst_offset + 3 * 48 * b.img_w].reshape(3, 48, b.img_w)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"rec line crop {l.crop}"
+    assert len({b.img_w for b in batches}) > 1
+
+
+def _session(ctx, worker, synth_dict):
+    from retto_b200.session import CallableWorker, RettoSession
+    ctx.dict_load(synth_dict)
+    return RettoSession(worker=CallableWorker(worker.det, worker.cls, worker.rec), ctx=ctx)
+
+
+@pytest.mark.parametrize("seed,hw", [(4, (1280, 1280)), (5, (960, 960)), (6, (736, 1000))])
+def test_session_matches_oracle_pipeline(ctx, synth_dict, seed, hw):
+    from oracle import oracle as O
+    from oracle.pipeline import run_page
+    from tools.synth import gen_page, probmap_from_rects
+    O.set_libm(1)
+    h, w = hw
+    img, rects = gen_page(seed, h, w)
+    dh, dw = O.resize_either_plan(h, w)
+    sx, sy = dw / w, dh / h
+    prob = probmap_from_rects(seed, [(r[0] * sx, r[1] * sy, r[2] * sx, r[3] * sy, r[4]) for r in rects], dh, dw)
+    wk = NpWorker(prob)
+    taps = {}
+    ref = run_page(img, wk, synth_dict, taps=taps)
+    assert not taps["det"].comparator_inconsistent
+    sess = _session(ctx, wk, synth_dict)
+    got = sess.run(img)
+    O.set_libm(0)
+    assert got.status == 0
+    assert len(got.det_result) == len(ref["boxes"]) > 5
+    for i in range(len(ref["boxes"])):
+        assert np.array_equal(got.det_result[i].boxes, ref["boxes"][i])
+        assert np.float32(got.det_result[i].score) == ref["scores"][i]
+        assert (got.cls_result[i].label, np.float32(got.cls_result[i].score)) == (ref["cls"][i][0], np.float32(ref["cls"][i][1]))
+        assert got.rec_result[i].text == ref["rec"][i][0]
+        a, b = np.float32(got.rec_result[i].score), np.float32(ref["rec"][i][1])
+        assert a == b or (np.isnan(a) and np.isnan(b))
+    # the worker saw bit-identical tensors on both sides
+    seen = sess.worker.seen
+    assert np.array_equal(seen[0][0].view(np.uint32), taps["det_in"].view(np.uint32))
+    assert len(seen[1]) == len(taps["cls_batches"]) and len(seen[2]) == len(taps["rec_batches"])
+    for a, b in zip(seen[1] + seen[2], taps["cls_batches"] + taps["rec_batches"]):
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert any(taps["flipped"])
+
+
+def test_session_batch_of_pages_with_resizes(ctx, synth_dict):
+    """several pages in one call, including resize_both (>2000 px) and resize_either up-scaling (<736 px)"""
+    from oracle import oracle as O
+    from oracle.pipeline import run_page
+    from tools.synth import gen_page, probmap_from_rects
+    O.set_libm(1)
+    specs = [(11, 900, 1400), (12, 2300, 1700), (13, 500, 640), (14, 1280, 1280)]
+    imgs, refs, workers = [], [], []
+    for seed, h, w in specs:
+        img, rects = gen_page(seed, h, w, n_lines=(6, 14))
+        page = O.resize_both(img)
+        ah, aw = page.shape[:2]
+        dh, dw = O.resize_either_plan(ah, aw)
+        sx, sy = dw / w, dh / h
+        prob = probmap_from_rects(seed, [(r[0] * sx, r[1] * sy, r[2] * sx, r[3] * sy, r[4]) for r in rects], dh, dw)
+        wk = NpWorker(prob)
+        imgs.append(img)
+        workers.append(wk)
+        refs.append(run_page(img, wk, synth_dict))
+
+    class Multi:
+        def __init__(self):
+            self.k = 0
+
+        def det(self, x):
+            w = workers[self.k]
+            self.k += 1
+            return w.det(x)
+
+        def cls(self, x):
+            return workers[0].cls(x)
+
+        def rec(self, x):
+            return workers[0].rec(x)
+
+    sess = _session(ctx, Multi(), synth_dict)
+    got = sess.run_pages(imgs)
+    O.set_libm(0)
+    for g, r in zip(got, refs):
+        assert g.status == 0 and len(g.det_result) == len(r["boxes"]) > 0
+        for i in range(len(r["boxes"])):
+            assert np.array_equal(g.det_result[i].boxes, r["boxes"][i])
+            assert g.cls_result[i].label == r["cls"][i][0]
+            assert g.rec_result[i].text == r["rec"][i][0]
+
+
+def test_session_empty_page(ctx, synth_dict):
+    """no detections -> cls/rec run zero batches and return empty vectors (chunks of an empty slice)"""
+    wk = NpWorker(np.zeros((736, 736), np.float32))
+    sess = _session(ctx, wk, synth_dict)
+    r = sess.run(np.full((736, 736, 3), 255, np.uint8))
+    assert r.status == 0 and r.det_result == [] and r.cls_result == [] and r.rec_result == []

@@ -85,3 +85,57 @@ def gen_probmap(seed: int, h: int = 960, w: int = 960, k_range=(20, 60), wide_an
     bg = (rng.random((h, w)) * 0.2).astype(np.float32)
     prob = np.where(mask > 0, bg + (inside - bg) * ramp, bg).astype(np.float32)
     return np.ascontiguousarray(prob)
+
+
+def gen_page(seed: int, h: int = 1280, w: int = 1280, n_lines=(20, 45), invert_p: float = 0.25):
+    """Synthetic rendered-text page (Pillow default font) + the text-line rectangles that were drawn.
+    returns (rgb uint8 [h,w,3], rects [(x0,y0,x1,y1,rot180)])"""
+    from PIL import Image, ImageDraw, ImageFont
+    rng = np.random.default_rng(seed)
+    inv = rng.random() < invert_p
+    bg, fg = (0, 255) if inv else (255, 0)
+    img = Image.new("RGB", (w, h), (bg, bg, bg))
+    drw = ImageDraw.Draw(img)
+    rects = []
+    y = int(rng.integers(10, 40))
+    target = int(rng.integers(n_lines[0], n_lines[1] + 1))
+    words = ["retto", "B200", "kernel", "ocr", "page", "line", "text", "probability", "contour", "0123456789", "HBM3e", "roofline"]
+    while y < h - 60 and len(rects) < target:
+        size = int(rng.integers(14, 41))
+        try:
+            font = ImageFont.load_default(size=size)
+        except TypeError:
+            font = ImageFont.load_default()
+        x = int(rng.integers(10, max(11, w // 4)))
+        s = " ".join(rng.choice(words) for _ in range(int(rng.integers(2, 9))))
+        box = drw.textbbox((x, y), s, font=font)
+        if box[2] >= w - 5:
+            s = s[: max(3, int(len(s) * (w - 10 - x) / max(1, box[2] - x)) - 1)]
+            box = drw.textbbox((x, y), s, font=font)
+        rot = rng.random() < 0.3
+        if rot:
+            tmp = Image.new("RGB", (box[2] - box[0] + 4, box[3] - box[1] + 4), (bg, bg, bg))
+            ImageDraw.Draw(tmp).text((2 - (box[0] - x), 2 - (box[1] - y)), s, font=font, fill=(fg, fg, fg))
+            img.paste(tmp.rotate(180), (box[0] - 2, box[1] - 2))
+        else:
+            drw.text((x, y), s, font=font, fill=(fg, fg, fg))
+        rects.append((box[0], box[1], box[2], box[3], bool(rot)))
+        y = box[3] + int(rng.integers(14, 40))
+    return np.asarray(img, dtype=np.uint8).copy(), rects
+
+
+def probmap_from_rects(seed: int, rects, h: int, w: int, shrink: float = 0.3) -> np.ndarray:
+    """A DBNet-like probability map for a rendered page: shrunk text-line kernels at ~.85, 2-px ramp,
+    background U[0,.2) (what the det model would emit for that page, without running a model)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    mask = np.zeros((h, w), np.uint8)
+    for (x0, y0, x1, y1, _r) in rects:
+        bh = y1 - y0
+        d = int(bh * shrink * 0.5)
+        cv2.rectangle(mask, (int(x0) + d, int(y0) + d), (int(x1) - d, int(y1) - d), 255, -1)
+    dist = cv2.distanceTransform(mask, cv2.DIST_L2, 3)
+    ramp = np.clip(dist / 2.0, 0.0, 1.0).astype(np.float32)
+    inside = np.clip(rng.normal(0.85, 0.05, (h, w)), 0.55, 1.0).astype(np.float32)
+    bg = (rng.random((h, w)) * 0.2).astype(np.float32)
+    return np.ascontiguousarray(np.where(mask > 0, bg + (inside - bg) * ramp, bg).astype(np.float32))
