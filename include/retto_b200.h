@@ -92,6 +92,12 @@ retto_b200_status retto_b200_sync(retto_b200_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 uint64_t retto_b200_launch_count(const retto_b200_ctx* ctx);
 
+/* measurement taps: when enabled every kernel launch is bracketed by CUDA events on the context's stream;
+ * retto_b200_kernel_times returns "name\tcount\ttotal_ms\n" lines accumulated since the last reset */
+retto_b200_status retto_b200_enable_kernel_timing(retto_b200_ctx* ctx, int32_t on);
+retto_b200_status retto_b200_reset_kernel_times(retto_b200_ctx* ctx);
+retto_b200_status retto_b200_kernel_times(retto_b200_ctx* ctx, char* buf, size_t cap);
+
 /* memory helpers so a host-language binding needs no CUDA runtime of its own */
 retto_b200_status retto_b200_dev_alloc(retto_b200_ctx* ctx, size_t bytes, void** d_out);
 retto_b200_status retto_b200_dev_free(retto_b200_ctx* ctx, void* d_ptr);

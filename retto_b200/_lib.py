@@ -106,7 +106,8 @@ FORWARD_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(
 # every symbol include/retto_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
     "retto_b200_config_default", "retto_b200_abi_version", "retto_b200_create", "retto_b200_destroy", "retto_b200_last_error",
-    "retto_b200_stream", "retto_b200_sync", "retto_b200_launch_count", "retto_b200_dev_alloc", "retto_b200_dev_free",
+    "retto_b200_stream", "retto_b200_sync", "retto_b200_launch_count", "retto_b200_enable_kernel_timing",
+    "retto_b200_reset_kernel_times", "retto_b200_kernel_times", "retto_b200_dev_alloc", "retto_b200_dev_free",
     "retto_b200_host_alloc", "retto_b200_host_free", "retto_b200_h2d", "retto_b200_d2h", "retto_b200_resize_both_plan",
     "retto_b200_resize_either_plan", "retto_b200_thumbnail", "retto_b200_det_preprocess", "retto_b200_det_postprocess",
     "retto_b200_det_post_fetch_bitmap", "retto_b200_det_post_fetch_labels", "retto_b200_det_post_enable_trace",
@@ -150,6 +151,9 @@ def lib() -> C.CDLL:
     L.retto_b200_sync.argtypes = [vp]
     L.retto_b200_launch_count.argtypes = [vp]
     L.retto_b200_launch_count.restype = u64
+    L.retto_b200_enable_kernel_timing.argtypes = [vp, i32]
+    L.retto_b200_reset_kernel_times.argtypes = [vp]
+    L.retto_b200_kernel_times.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.retto_b200_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.retto_b200_dev_free.argtypes = [vp, vp]
     L.retto_b200_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]

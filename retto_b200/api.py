@@ -101,6 +101,22 @@ class Context:
     def launch_count(self) -> int:
         return int(self._L.retto_b200_launch_count(self._h))
 
+    def enable_kernel_timing(self, on: bool = True):
+        self._check(self._L.retto_b200_enable_kernel_timing(self._h, int(on)))
+
+    def reset_kernel_times(self):
+        self._check(self._L.retto_b200_reset_kernel_times(self._h))
+
+    def kernel_times(self):
+        """{kernel name: (launch count, total ms)} measured with CUDA events on the context's stream"""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._L.retto_b200_kernel_times(self._h, buf, len(buf)))
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            name, cnt, ms = ln.split("\t")
+            out[name] = (int(cnt), float(ms))
+        return out
+
     # ---- resizes ------------------------------------------------------------------------------
     def thumbnail(self, srcs: Sequence, out_dims: Sequence):
         """image::imageops::thumbnail on a batch of HWC u8 CUDA tensors."""

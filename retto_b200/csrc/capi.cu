@@ -101,6 +101,38 @@ extern "C" retto_b200_status retto_b200_d2h(retto_b200_ctx* c, void* h_dst, cons
     return RETTO_B200_OK;
 }
 
+// ---- per-kernel timing taps (bench.py roofline) ---------------------------------------------------------
+extern "C" retto_b200_status retto_b200_enable_kernel_timing(retto_b200_ctx* c, int32_t on) {
+    if (!c) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->timer_collect();
+    c->timing_enabled = on != 0;
+    return RETTO_B200_OK;
+}
+extern "C" retto_b200_status retto_b200_reset_kernel_times(retto_b200_ctx* c) {
+    if (!c) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->timer_collect();
+    for (auto& v : c->timer_total_ms) v = 0;
+    for (auto& v : c->timer_count) v = 0;
+    return RETTO_B200_OK;
+}
+// writes "name\tcount\ttotal_ms\n" lines into buf (NUL terminated); returns ERR_CAPACITY if it does not fit
+extern "C" retto_b200_status retto_b200_kernel_times(retto_b200_ctx* c, char* buf, size_t cap) {
+    if (!c || !buf || cap == 0) return RETTO_B200_ERR_INVALID_ARG;
+    RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->timer_collect();
+    std::string s;
+    for (size_t i = 0; i < c->timer_names.size(); ++i) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", c->timer_names[i].c_str(), (unsigned long long)c->timer_count[i], c->timer_total_ms[i]);
+        s += line;
+    }
+    if (s.size() + 1 > cap) return RETTO_B200_ERR_CAPACITY;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return RETTO_B200_OK;
+}
+
 retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {
     RT_CUDA_OK(ctx, dst.ensure(bytes ? bytes : 16, ctx->stream));
     if (bytes) RT_CUDA_OK(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -131,6 +131,42 @@ struct retto_b200_ctx {
 
     void set_error(const std::string& e) { err = e; }
 
+    // optional per-kernel CUDA-event timing (bench.py roofline): events on the launching stream
+    struct TimedLaunch { int name_id; cudaEvent_t a, b; };
+    bool timing_enabled = false;
+    std::vector<std::string> timer_names;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    int timer_pending = -1;
+    std::vector<double> timer_total_ms;
+    std::vector<uint64_t> timer_count;
+    cudaEvent_t get_event() {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void timer_begin(const char* name) {
+        int id = -1;
+        for (size_t i = 0; i < timer_names.size(); ++i) if (timer_names[i] == name) { id = (int)i; break; }
+        if (id < 0) { id = (int)timer_names.size(); timer_names.push_back(name); timer_total_ms.push_back(0); timer_count.push_back(0); }
+        TimedLaunch t{id, get_event(), get_event()};
+        cudaEventRecord(t.a, stream);
+        timed.push_back(t);
+        timer_pending = (int)timed.size() - 1;
+    }
+    void timer_end() {
+        if (timer_pending < 0) return;
+        cudaEventRecord(timed[timer_pending].b, stream);
+        timer_pending = -1;
+    }
+    void timer_collect() {  // caller synchronises the stream first
+        for (auto& t : timed) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { timer_total_ms[t.name_id] += ms; timer_count[t.name_id]++; }
+            event_pool.push_back(t.a); event_pool.push_back(t.b);
+        }
+        timed.clear();
+    }
+
     // descriptor staging (device side; host side is pageable and snapshotted by cudaMemcpyAsync)
     DevBuf d_stage, d_stage2, d_stage3;
 
@@ -173,9 +209,15 @@ struct retto_b200_ctx {
     std::vector<float> r_scores;
 };
 
+#define RT_LAUNCH_BEGIN(ctx, name)                                                                \
+    do {                                                                                          \
+        if ((ctx)->timing_enabled) (ctx)->timer_begin(name);                                      \
+    } while (0)
+
 #define RT_LAUNCH_CHECK(ctx)                                                                      \
     do {                                                                                          \
         (ctx)->launches++;                                                                        \
+        if ((ctx)->timing_enabled) (ctx)->timer_end();                                            \
         cudaError_t _e = cudaGetLastError();                                                      \
         if (_e != cudaSuccess) {                                                                  \
             (ctx)->set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));            \

@@ -199,10 +199,12 @@ extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const re
     }
     CropDev* d_crops = ctx->d_crop_descs.as<CropDev>();
     const int* d_prefix = reinterpret_cast<const int*>(ctx->d_crop_descs.as<char>() + sizeof(CropDev) * n);
+    RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
     crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n);
     RT_LAUNCH_CHECK(ctx);
     const int total = prefix[n];
     if (total > 0) {
+        RT_LAUNCH_BEGIN(ctx, "crop_warp_kernel");
         crop_warp_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_crops, d_prefix, n, total, ctx->d_crop_pix.as<unsigned char>());
         RT_LAUNCH_CHECK(ctx);
     }
@@ -235,6 +237,7 @@ extern "C" retto_b200_status retto_b200_crop_fetch(retto_b200_ctx* ctx, int32_t 
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     RT_CUDA_OK(ctx, ctx->d_stage3.ensure((size_t)n_px * 3, ctx->stream));
     // rotate_180_in_place (image_helper.rs:268-286) is applied lazily: materialise it here
+    RT_LAUNCH_BEGIN(ctx, "crop_flip_copy_kernel");
     crop_flip_copy_kernel<<<(n_px + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_crop_pix.as<unsigned char>() + c.offset, ctx->d_stage3.as<unsigned char>(), n_px, flip);
     RT_LAUNCH_CHECK(ctx);
     RT_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_stage3.p, (size_t)n_px * 3, cudaMemcpyDeviceToHost, ctx->stream));

@@ -156,6 +156,7 @@ static retto_b200_status ctc_run_argmax(retto_b200_ctx* ctx, const std::vector<C
     RT_CUDA_OK(ctx, cudaMemsetAsync(d_line_nan, 0, sizeof(int) * (size_t)n_lines, ctx->stream));
     constexpr int WARPS = 8;
     const int grid = (total_rows + WARPS - 1) / WARPS;
+    RT_LAUNCH_BEGIN(ctx, "ctc_argmax_kernel<WARPS>");
     ctc_argmax_kernel<WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(d_t, d_pre, (int)tensors.size(), total_rows, C, max_t, d_idx, d_prob, d_line_nan);
     RT_LAUNCH_CHECK(ctx);
     return RETTO_B200_OK;
@@ -205,6 +206,7 @@ extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const re
     int* d_nan = d_cnt + 3 * nl;
     RT_CUDA_OK(ctx, cudaMemcpyAsync(d_linet, line_t.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, ctx->stream));
     RT_TRY(ctc_run_argmax(ctx, tensors, prefix, num_classes, max_t, n_lines, ctx->d_ctc_idx.as<int>(), ctx->d_ctc_prob.as<float>(), d_nan));
+    RT_LAUNCH_BEGIN(ctx, "ctc_collapse_kernel");
     ctc_collapse_kernel<<<(n_lines + 127) / 128, 128, 0, ctx->stream>>>(
         ctx->d_ctc_idx.as<int>(), ctx->d_ctc_prob.as<float>(), d_linet, n_lines, max_t, ctx->d_dict_offs.as<unsigned>(),
         ctx->d_dict_bytes.as<unsigned char>(), (int)ctx->dict.size(), text_stride, ctx->d_ctc_tok.as<int>(), d_cnt,

@@ -629,24 +629,32 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     int2* d_hull = d_rowtab + (size_t)n * ROWCAP;
     BoxCand* d_cand = ctx->d_cand.as<BoxCand>();
 
+    RT_LAUNCH_BEGIN(ctx, "zero_counters_kernel");
     zero_counters_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, n);
     RT_LAUNCH_CHECK(ctx);
     const int tgrid = (total_tiles + 3) / 4;
+    RT_LAUNCH_BEGIN(ctx, "bitmap_runs_kernel");
     if (vec)
         bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf);
     else
         bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf);
     RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "ccl_merge_kernel");
     ccl_merge_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt);
     RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "ccl_flatten_kernel");
     ccl_flatten_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_lab, d_tf, d_cnt, d_roots, max_comps);
     RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "comp_sort_kernel");
     comp_sort_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_roots, d_comps, d_cid, max_comps);
     RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "run_end_kernel<0>");
     run_end_kernel<0><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
     RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "row_alloc_kernel");
     row_alloc_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_comps, d_rowtab, max_comps);
     RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "run_end_kernel<1>");
     run_end_kernel<1><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
     RT_LAUNCH_CHECK(ctx);
     // H needs the per-page component counts for its grid: size it by the host-known cap when small,
@@ -660,22 +668,27 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     if (max_n > 0) {
         GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
         dim3 grid((max_n + 3) / 4, n);
+        RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel");
         box_geometry_kernel<<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp);
         RT_LAUNCH_CHECK(ctx);
     }
     ctx->dp_trace_valid = false;
     if (ctx->dp_trace_enabled && max_n > 0) {
         RT_CUDA_OK(ctx, ctx->d_trace.ensure(sizeof(TraceRec) * (size_t)n * max_comps, st));
+        RT_LAUNCH_BEGIN(ctx, "trace_copy_kernel");
         trace_copy_kernel<<<dim3((max_n + 127) / 128, n), 128, 0, st>>>(n, d_cnt, d_cand, max_comps, ctx->d_trace.as<TraceRec>());
         RT_LAUNCH_CHECK(ctx);
         ctx->dp_trace_valid = true;
     }
+    RT_LAUNCH_BEGIN(ctx, "page_sort_kernel");
     page_sort_kernel<<<n, 32, 0, st>>>(n, d_cnt, d_cand, max_comps);
     RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "pack_offsets_kernel");
     pack_offsets_kernel<<<1, 32, 0, st>>>(n, d_cnt, d_offsets);
     RT_LAUNCH_CHECK(ctx);
     const int cap = std::max(max_boxes_total, 0);
     RT_CUDA_OK(ctx, ctx->d_boxes_out.ensure(sizeof(retto_b200_box) * (size_t)std::max(cap, 1), st));
+    RT_LAUNCH_BEGIN(ctx, "pack_boxes_kernel");
     pack_boxes_kernel<<<n, 128, 0, st>>>(n, d_cnt, d_offsets, d_cand, max_comps, ctx->d_boxes_out.as<retto_b200_box>(), cap);
     RT_LAUNCH_CHECK(ctx);
     int* h_off = reinterpret_cast<int*>(ctx->h_dp.as<char>() + sizeof(PageCounters) * n);
@@ -737,6 +750,7 @@ extern "C" retto_b200_status retto_b200_scale_and_clip(retto_b200_ctx* ctx, rett
     if (!ctx || n < 0 || (n > 0 && !h_boxes)) return RETTO_B200_ERR_INVALID_ARG;
     if (n == 0) return RETTO_B200_OK;
     RT_TRY(rt_upload(ctx, ctx->d_stage3, h_boxes, sizeof(retto_b200_box) * (size_t)n));
+    RT_LAUNCH_BEGIN(ctx, "scale_clip_kernel");
     scale_clip_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_stage3.as<retto_b200_box>(), n, ori_w / bitmap_w, ori_h / bitmap_h, ori_w, ori_h);
     RT_LAUNCH_CHECK(ctx);
     RT_CUDA_OK(ctx, cudaMemcpyAsync(h_boxes, ctx->d_stage3.p, sizeof(retto_b200_box) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -813,6 +827,7 @@ retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h
     memcpy(blob.data(), h_boxes, sizeof(retto_b200_box) * (size_t)n);
     memcpy(blob.data() + bb, h_params4, sizeof(double) * 4 * (size_t)n);
     RT_TRY(rt_upload(ctx, ctx->d_stage3, blob.data(), blob.size()));
+    RT_LAUNCH_BEGIN(ctx, "scale_clip_multi_kernel");
     scale_clip_multi_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_stage3.as<retto_b200_box>(),
                                                                       reinterpret_cast<const double4*>(ctx->d_stage3.as<char>() + bb), n);
     RT_LAUNCH_CHECK(ctx);

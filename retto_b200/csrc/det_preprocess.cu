@@ -198,6 +198,7 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
             rs.push_back(dv);
             rs_pre.push_back(rs_pre.back() + (int)(px / 4));
         } else {
+            RT_LAUNCH_BEGIN(ctx, "det_pre_scalar_kernel");
             det_pre_scalar_kernel<<<(unsigned)((px + 255) / 256), 256, 0, ctx->stream>>>(dv, np);
             RT_LAUNCH_CHECK(ctx);
         }
@@ -206,6 +207,7 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
         const DetPreDev* dv; const int* dp;
         RT_TRY(upload_with_prefix(ctx, ctx->d_stage, ident, ident_pre, &dv, &dp));
         const int total = ident_pre.back();
+        RT_LAUNCH_BEGIN(ctx, "det_pre_identity_kernel");
         det_pre_identity_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dv, dp, (int)ident.size(), total, np);
         RT_LAUNCH_CHECK(ctx);
     }
@@ -213,6 +215,7 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
         const DetPreDev* dv; const int* dp;
         RT_TRY(upload_with_prefix(ctx, ctx->d_stage2, rs, rs_pre, &dv, &dp));
         const int total = rs_pre.back();
+        RT_LAUNCH_BEGIN(ctx, "det_pre_resize_kernel");
         det_pre_resize_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dv, dp, (int)rs.size(), total, np);
         RT_LAUNCH_CHECK(ctx);
     }
@@ -236,6 +239,7 @@ extern "C" retto_b200_status retto_b200_thumbnail(retto_b200_ctx* ctx, const ret
     const ResizeDev* dv; const int* dp;
     RT_TRY(upload_with_prefix(ctx, ctx->d_stage3, jobs, pre, &dv, &dp));
     const int total = pre.back();
+    RT_LAUNCH_BEGIN(ctx, "thumbnail_kernel");
     thumbnail_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dv, dp, n, total);
     RT_LAUNCH_CHECK(ctx);
     return RETTO_B200_OK;

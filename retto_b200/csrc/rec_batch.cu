@@ -151,6 +151,7 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
     const LineDev* d_lines = ctx->d_lines.as<LineDev>();
     const int* d_prefix = reinterpret_cast<const int*>(ctx->d_lines.as<char>() + sizeof(LineDev) * n_lines);
     const int total = prefix[n_lines];
+    RT_LAUNCH_BEGIN(ctx, "build_batches_kernel");
     build_batches_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(d_lines, d_prefix, n_lines, total, ctx->d_crop_descs.as<CropDev>(),
                                                                        ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
                                                                        kind == 1 ? 1 : 0, img_h, buf.as<float>());
@@ -172,6 +173,7 @@ retto_b200_status rt_cls_postprocess_ptrs(retto_b200_ctx* ctx, const std::vector
     float* d_score = reinterpret_cast<float*>(d_label + n);
     int* d_nan = d_label + 2 * n;
     RT_CUDA_OK(ctx, cudaMemsetAsync(d_nan, 0, sizeof(int), ctx->stream));
+    RT_LAUNCH_BEGIN(ctx, "cls_post_kernel");
     cls_post_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_cls_idx.as<ClsLine>(), n, 2, ctx->cfg.cls_label[0], ctx->cfg.cls_label[1],
                                                               ctx->cfg.cls_thresh, ctx->d_crop_flip.as<int>(), d_label, d_score, d_nan);
     RT_LAUNCH_CHECK(ctx);

@@ -1,0 +1,107 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/retto_b200.h declares; host-side
+planning entry points (no GPU needed) agree with the oracle's restatement of the reference rules."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from oracle import oracle as O
+from oracle.pipeline import stable_order_desc_ratio
+from retto_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "retto_b200.h")).read()
+    declared = set(re.findall(r"\b(retto_b200_[a-z0-9_]+)\s*\(", hdr)) - {"retto_b200_forward_fn", "retto_b200_status"}
+    L = _lib.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert L.retto_b200_abi_version() == 1
+
+
+def test_config_defaults_match_reference():
+    c = _lib.Config()
+    _lib.lib().retto_b200_config_default(C.byref(c))
+    assert (c.max_side_len, c.min_side_len) == (2000, 30)                                   # session.rs:33-34
+    assert (c.det_limit_side_len, c.det_limit_type, c.det_min_mini_box_size) == (736, 0, 3)  # det_processor.rs:75-93
+    assert np.float32(c.det_scale) == np.float32(1) / np.float32(255)
+    assert (np.float32(c.det_thresh), np.float32(c.det_box_thresh), np.float32(c.det_unclip_ratio)) == (np.float32(.3), np.float32(.5), np.float32(1.6))
+    assert list(c.cls_image_shape) == [3, 48, 192] and c.cls_batch_num == 6 and np.float32(c.cls_thresh) == np.float32(.9) and list(c.cls_label) == [0, 180]
+    assert list(c.rec_image_shape) == [3, 48, 320] and c.rec_batch_num == 6
+    assert c.det_dilation_2x2 == 1
+
+
+def test_no_cuda_device_fails_loudly():
+    """the product has no CPU fallback: creating a context without a GPU is an error, not a silent CPU path"""
+    import torch
+    if torch.cuda.is_available():
+        return
+    h = C.c_void_p()
+    assert _lib.lib().retto_b200_create(0, None, C.byref(h)) == _lib.ERR_CUDA
+
+
+def test_resize_plans_match_oracle():
+    from retto_b200.api import resize_both_plan, resize_either_plan
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        h, w = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
+        assert resize_both_plan(h, w) == O.resize_both_plan(h, w)
+        assert resize_either_plan(h, w) == O.resize_either_plan(h, w)
+        assert resize_either_plan(h, w, 1, 960) == O.resize_either_plan(h, w, 1, 960)
+
+
+def _plan(kind, dims):
+    L = _lib.lib()
+    cfg = _lib.Config()
+    L.retto_b200_config_default(C.byref(cfg))
+    n = len(dims)
+    infos = (_lib.CropInfo * max(n, 1))(*[_lib.CropInfo(w, h, 0, 0, 0) for (h, w) in dims])
+    lines = (_lib.LineJob * max(n, 1))()
+    batches = (_lib.Batch * (n + 1))()
+    nb, tot = C.c_int32(), C.c_uint64()
+    assert L.retto_b200_plan_batches(C.byref(cfg), kind, infos, n, lines, batches, C.byref(nb), C.byref(tot)) == 0
+    return [lines[i] for i in range(n)], [batches[i] for i in range(nb.value)], tot.value
+
+
+def test_plan_batches_follows_cls_and_rec_rules():
+    rng = np.random.default_rng(1)
+    for trial in range(50):
+        n = int(rng.integers(0, 40))
+        dims = [(int(rng.integers(8, 60)), int(rng.integers(8, 900))) for _ in range(n)]
+        if n > 4:
+            dims[3] = dims[1]                       # equal ratios: stable order keeps detection order
+        order = stable_order_desc_ratio(dims)
+        for kind in (0, 1):
+            lines, batches, tot = _plan(kind, dims)
+            assert [l.crop for l in lines] == order
+            assert len(batches) == (n + 5) // 6
+            mx = np.float32(320) / np.float32(48)   # carried across batches, never reset (rec_processor.rs:227)
+            off = 0
+            for b in batches:
+                idxs = order[b.first_line:b.first_line + b.n]
+                if kind == 1:
+                    for i in idxs:
+                        mx = max(mx, np.float32(dims[i][1]) / np.float32(dims[i][0]))
+                    assert np.float32(b.max_wh_ratio) == mx
+                for k, i in enumerate(idxs):
+                    iw, rw = O.resize_norm_plan(dims[i][0], dims[i][1], 48, 192 if kind == 0 else 320, float(mx) if kind == 1 else None)
+                    l = lines[b.first_line + k]
+                    assert (l.img_w, l.resized_w, b.img_w) == (iw, rw, iw)
+                    assert l.dst_offset == off + k * 3 * 48 * iw
+                assert b.offset == off
+                off += b.n * 3 * 48 * b.img_w
+            assert tot == off
+
+
+def test_shard_indices_lpt():
+    from retto_b200.shard import shard_indices
+    sizes = [100, 1, 50, 50, 7, 7, 30, 2]
+    parts = shard_indices(sizes, 3)
+    assert sorted(sum(parts, [])) == list(range(8))
+    loads = [sum(sizes[i] for i in p) for p in parts]
+    assert max(loads) == 100 and all(p == sorted(p) for p in parts)
+    assert shard_indices([5, 5, 5, 5], 2) == [[0, 2], [1, 3]]
