@@ -100,14 +100,36 @@ __device__ __forceinline__ float cubic(float p0, float p1, float p2, float p3, f
 
 __global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restrict__ crops, const int* __restrict__ unit_prefix, int n_crops,
                                                          int total_units, unsigned char* __restrict__ pix) {
+    // one binary search per block (its first unit), then a short linear walk per thread
+    __shared__ int s_ci;
+    if (threadIdx.x == 0) s_ci = rt_find_segment(unit_prefix, n_crops, min(blockIdx.x * blockDim.x, total_units - 1));
+    __syncthreads();
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= total_units) return;
-    const int ci = rt_find_segment(unit_prefix, n_crops, u);
+    int ci = s_ci;
+    while (ci + 1 < n_crops && u >= unit_prefix[ci + 1]) ++ci;
     const CropDev& c = crops[ci];
     if (c.status != RETTO_B200_OK) return;
     const int lu = u - unit_prefix[ci];
     const int w = c.rot ? c.h : c.w, h = c.rot ? c.w : c.h;  // un-rotated warp size
     const int y = lu / w, x = lu - y * w;
+    size_t o;
+    if (c.rot) o = ((size_t)(w - 1 - x) * h + y) * 3;  // rotate270: out(y, w-1-x) = in(x, y), out is h wide
+    else o = ((size_t)y * w + x) * 3;
+    unsigned char* dst = pix + c.offset + o;
+    // Translation class with an integral offset (axis-aligned boxes: the common case for text lines): the sample
+    // position is an exact pixel centre, both cubic weights are 0 and cubic(p0,p1,p2,p3,0) == p1, so the warp
+    // degenerates to a guarded copy (same white-border rule).
+    if (c.cls == 0 && c.t[2] == floorf(c.t[2]) && c.t[5] == floorf(c.t[5])) {
+        const int ix = x + (int)c.t[2], iy = y + (int)c.t[5];
+        unsigned char r0 = 255, r1 = 255, r2 = 255;
+        if (!(ix - 1 < 0 || ix + 3 >= c.page_w || iy - 1 < 0 || iy + 3 >= c.page_h)) {
+            const unsigned char* sp = c.page + ((size_t)iy * c.page_w + ix) * 3;
+            r0 = __ldg(sp); r1 = __ldg(sp + 1); r2 = __ldg(sp + 2);
+        }
+        dst[0] = r0; dst[1] = r1; dst[2] = r2;
+        return;
+    }
     const float xf = (float)x, yf = (float)y;
     float px, py;
     if (c.cls == 2) {
@@ -141,10 +163,6 @@ __global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restric
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) rgb[ch] = clamp_u8_trunc(cubic(col[ch][0], col[ch][1], col[ch][2], col[ch][3], yw));
     }
-    size_t o;
-    if (c.rot) o = ((size_t)(w - 1 - x) * h + y) * 3;  // rotate270: out(y, w-1-x) = in(x, y), out is h wide
-    else o = ((size_t)y * w + x) * 3;
-    unsigned char* dst = pix + c.offset + o;
     dst[0] = rgb[0]; dst[1] = rgb[1]; dst[2] = rgb[2];
 }
 

@@ -272,7 +272,15 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
                 const int xi = x + lane;
                 const float v = (xi <= rc.b[s]) ? __ldg(row + xi) : 0.0f;
                 const int lim = min(32, rc.b[s] - x + 1);
-                for (int k = 0; k < lim; ++k) acc = __fadd_rn(acc, __shfl_sync(RT_FULL, v, k));
+                if (lim == 32) {   // full chunk: 32 independent shuffles first, then the dependent add chain
+                    float t[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) t[k] = __shfl_sync(RT_FULL, v, k);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, t[k]);
+                } else {
+                    for (int k = 0; k < lim; ++k) acc = __fadd_rn(acc, __shfl_sync(RT_FULL, v, k));
+                }
             }
         }
     }

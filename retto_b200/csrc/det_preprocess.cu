@@ -26,6 +26,14 @@ __device__ __forceinline__ float norm1(unsigned char v, float scale, float mean,
 // work unit = 16 consecutive pixels of one row.  unit_prefix[p] = units before page p.
 __global__ void __launch_bounds__(256) det_pre_identity_kernel(const DetPreDev* __restrict__ pages, const int* __restrict__ unit_prefix,
                                                                 int n_pages, int total_units, NormParams np) {
+    // 256-entry normalisation tables per tensor channel, built with the reference's three separately rounded
+    // f32 operations (bit-identical to computing them per pixel, without 48 divisions per thread)
+    __shared__ float s_lut[3][256];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        s_lut[c][v] = norm1((unsigned char)v, np.scale, np.mean[c], np.stdv[c]);
+    }
+    __syncthreads();
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= total_units) return;
     const int p = rt_find_segment(unit_prefix, n_pages, u);
@@ -44,9 +52,9 @@ __global__ void __launch_bounds__(256) det_pre_identity_kernel(const DetPreDev* 
         const unsigned char vr = (wds[o0 >> 2] >> ((o0 & 3) * 8)) & 0xff;
         const unsigned char vg = (wds[o1 >> 2] >> ((o1 & 3) * 8)) & 0xff;
         const unsigned char vb = (wds[o2 >> 2] >> ((o2 & 3) * 8)) & 0xff;
-        bl[i] = norm1(vb, np.scale, np.mean[0], np.stdv[0]);
-        g[i] = norm1(vg, np.scale, np.mean[1], np.stdv[1]);
-        r[i] = norm1(vr, np.scale, np.mean[2], np.stdv[2]);
+        bl[i] = s_lut[0][vb];
+        g[i] = s_lut[1][vg];
+        r[i] = s_lut[2][vr];
     }
     float4* d0 = reinterpret_cast<float4*>(pg.dst + pix);
     float4* d1 = reinterpret_cast<float4*>(pg.dst + plane + pix);

@@ -21,33 +21,48 @@ struct FlipReader {
     }
 };
 
-// one thread per output pixel (x < img_w, y < img_h) of one line; 3 planes written
-__global__ void __launch_bounds__(256) build_batches_kernel(const LineDev* __restrict__ lines, const int* __restrict__ unit_prefix, int n_lines,
-                                                             int total_units, const CropDev* __restrict__ crops,
-                                                             const unsigned char* __restrict__ crop_pix, const int* __restrict__ flip_flags,
-                                                             int use_flip, int img_h, float* __restrict__ out) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= total_units) return;
-    const int li = rt_find_segment(unit_prefix, n_lines, u);
-    const LineDev ln = lines[li];
-    const int lu = u - unit_prefix[li];
-    const int y = lu / ln.img_w, x = lu - y * ln.img_w;
-    const size_t plane = (size_t)img_h * ln.img_w;
-    float* dst = out + ln.dst_offset + (size_t)y * ln.img_w + x;
-    if (x >= ln.resized_w) {
-        dst[0] = 0.0f; dst[plane] = 0.0f; dst[2 * plane] = 0.0f;
-        return;
-    }
+// One block = one (line, 128-column chunk); one thread = one output column over all img_h rows.
+// The x-axis window is computed once per thread, the y-axis windows once per block (shared memory), the
+// normalisation `(px as f32 / 255 - .5) / .5` (image_helper.rs:200-203) comes from a 256-entry table built
+// with the same three correctly-rounded operations (bit-identical, no per-pixel divisions).
+#define BB_COLS 128
+#define BB_MAX_H 64
+struct ChunkDev { int line, x0; };
+__global__ void __launch_bounds__(BB_COLS) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
+                                                                 const CropDev* __restrict__ crops, const unsigned char* __restrict__ crop_pix,
+                                                                 const int* __restrict__ flip_flags, int use_flip, int img_h,
+                                                                 float* __restrict__ out) {
+    __shared__ float s_lut[256];
+    __shared__ ThumbAxis s_ay[BB_MAX_H];
+    const ChunkDev ck = chunks[blockIdx.x];
+    const LineDev ln = lines[ck.line];
     const CropDev& c = crops[ln.crop];
     const unsigned cw = (unsigned)c.w, chh = (unsigned)c.h;
+    for (int v = threadIdx.x; v < 256; v += BB_COLS) s_lut[v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), 0.5f), 0.5f);
+    const float yr = __fdiv_rn((float)chh, (float)img_h);
+    for (int y = threadIdx.x; y < img_h; y += BB_COLS) s_ay[y] = thumb_axis(y, yr, chh);
+    __syncthreads();
+    const int x = ck.x0 + threadIdx.x;
+    if (x >= ln.img_w) return;
+    const size_t plane = (size_t)img_h * ln.img_w;
+    float* dst = out + ln.dst_offset + x;
+    if (x >= ln.resized_w) {
+        for (int y = 0; y < img_h; ++y) {
+            float* d = dst + (size_t)y * ln.img_w;
+            d[0] = 0.0f; d[plane] = 0.0f; d[2 * plane] = 0.0f;
+        }
+        return;
+    }
     const FlipReader rd{crop_pix + c.offset, cw, chh, use_flip ? flip_flags[ln.crop] : 0};
-    const float xr = __fdiv_rn((float)cw, (float)ln.resized_w), yr = __fdiv_rn((float)chh, (float)img_h);
-    unsigned char px[3];
-    thumbnail_pixel(rd, cw, chh, thumb_axis(x, xr, cw), thumb_axis(y, yr, chh), px);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float v = __fdiv_rn((float)px[ch], 255.0f);
-        dst[ch * plane] = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+    const float xr = __fdiv_rn((float)cw, (float)ln.resized_w);
+    const ThumbAxis ax = thumb_axis(x, xr, cw);
+    for (int y = 0; y < img_h; ++y) {
+        unsigned char px[3];
+        thumbnail_pixel(rd, cw, chh, ax, s_ay[y], px);
+        float* d = dst + (size_t)y * ln.img_w;
+        d[0] = s_lut[px[0]];
+        d[plane] = s_lut[px[1]];
+        d[2 * plane] = s_lut[px[2]];
     }
 }
 
@@ -130,8 +145,10 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
     *d_base = buf.as<float>();
     if (n_lines == 0) return RETTO_B200_OK;
     const int img_h = kind == 0 ? ctx->cfg.cls_image_shape[1] : ctx->cfg.rec_image_shape[1];
+    if (img_h > BB_MAX_H) { ctx->set_error("build_batches: image_shape height > 64 is not supported"); return RETTO_B200_ERR_UNSUPPORTED; }
     std::vector<LineDev> lines(n_lines);
-    std::vector<int> prefix(n_lines + 1, 0);
+    std::vector<ChunkDev> chunks;
+    chunks.reserve((size_t)n_lines * 6);
     for (int i = 0; i < n_lines; ++i) {
         const retto_b200_line_job& l = h_lines[i];
         if (l.crop < 0 || l.crop >= (int)ctx->crops.size() || l.img_w <= 0 || l.resized_w < 0 || l.resized_w > l.img_w ||
@@ -140,21 +157,19 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
             return RETTO_B200_ERR_INVALID_ARG;
         }
         lines[i] = LineDev{l.crop, l.img_w, l.resized_w, 0, l.dst_offset};
-        const long long u = (long long)prefix[i] + (long long)img_h * l.img_w;
-        if (u > 0x7fffffffLL) { ctx->set_error("build_batches: too many pixels"); return RETTO_B200_ERR_CAPACITY; }
-        prefix[i + 1] = (int)u;
+        for (int x0 = 0; x0 < l.img_w; x0 += BB_COLS) chunks.push_back(ChunkDev{i, x0});
     }
-    std::vector<char> blob(sizeof(LineDev) * n_lines + sizeof(int) * (n_lines + 1));
+    const size_t lb = (sizeof(LineDev) * n_lines + 15) & ~size_t(15);
+    std::vector<char> blob(lb + sizeof(ChunkDev) * chunks.size());
     memcpy(blob.data(), lines.data(), sizeof(LineDev) * n_lines);
-    memcpy(blob.data() + sizeof(LineDev) * n_lines, prefix.data(), sizeof(int) * (n_lines + 1));
+    memcpy(blob.data() + lb, chunks.data(), sizeof(ChunkDev) * chunks.size());
     RT_TRY(rt_upload(ctx, ctx->d_lines, blob.data(), blob.size()));
     const LineDev* d_lines = ctx->d_lines.as<LineDev>();
-    const int* d_prefix = reinterpret_cast<const int*>(ctx->d_lines.as<char>() + sizeof(LineDev) * n_lines);
-    const int total = prefix[n_lines];
+    const ChunkDev* d_chunks = reinterpret_cast<const ChunkDev*>(ctx->d_lines.as<char>() + lb);
     RT_LAUNCH_BEGIN(ctx, "build_batches_kernel");
-    build_batches_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(d_lines, d_prefix, n_lines, total, ctx->d_crop_descs.as<CropDev>(),
-                                                                       ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
-                                                                       kind == 1 ? 1 : 0, img_h, buf.as<float>());
+    build_batches_kernel<<<(unsigned)chunks.size(), BB_COLS, 0, ctx->stream>>>(d_lines, d_chunks, ctx->d_crop_descs.as<CropDev>(),
+                                                                             ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
+                                                                             kind == 1 ? 1 : 0, img_h, buf.as<float>());
     RT_LAUNCH_CHECK(ctx);
     return RETTO_B200_OK;
 }
