@@ -92,15 +92,17 @@ struct PageCounters {      // per page, zeroed before each det_postprocess
     int n_boxes;
     int status;
     int row_total;           // rows allocated in the row-extreme table
-    int pad[3];
+    int n_holes;             // hole borders (background components not connected to the frame)
+    int pad[2];
 };
 
 struct CompRec {           // per connected component (dense id)
     int root;                // min linear index (page-local)
     int ymax, xmin, xmax;
     int row_off;             // offset into the row-extreme table (page-relative)
-    int key;                 // raster index at which imageproc's scan discovers the outer border (INT_MAX: never)
-    int pad[2];
+    int key;                 // raster index at which imageproc's scan discovers the border (INT_MAX: never)
+    int ymin;                // first row of the contour's point set
+    int pad;
 };
 
 struct CropDev {
@@ -186,7 +188,7 @@ struct retto_b200_ctx {
     bool dp_trace_enabled = false, dp_trace_valid = false;
     DevBuf d_trace;
     std::vector<int> dp_holes;   // per page: #hole borders of the last det_postprocess (components - Euler number)
-    DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out;
+    DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out, d_holes, d_hole_pages;
     HostBuf h_dp;
 
     // crops

@@ -250,18 +250,8 @@ __global__ void __launch_bounds__(128) ccl_flatten_kernel(const DetPostPage* __r
     }
 }
 
-// ---- D: sort roots, assign dense ids ----------------------------------------------------------------
-__global__ void __launch_bounds__(1024) comp_sort_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
-                                                          int* __restrict__ roots, CompRec* __restrict__ comps, int* __restrict__ cid_at,
-                                                          int max_comps) {
-    const int page = blockIdx.x;
-    const DetPostPage pg = pages[page];
-    int n = counters[page].n_roots;
-    if (n > max_comps) {
-        if (threadIdx.x == 0) { counters[page].status = RETTO_B200_ERR_CAPACITY; counters[page].n_roots = 0; }
-        return;
-    }
-    int* r = roots + (size_t)page * max_comps;
+// ascending bitonic sort of r[0..n) by the whole block (r must have room for the next power of two)
+__device__ void block_sort_ints(int* r, int n) {
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     for (int i = n + threadIdx.x; i < np2; i += blockDim.x) r[i] = 0x7fffffff;
@@ -278,6 +268,21 @@ __global__ void __launch_bounds__(1024) comp_sort_kernel(const DetPostPage* __re
             }
             __syncthreads();
         }
+}
+
+// ---- D: sort roots, assign dense ids ----------------------------------------------------------------
+__global__ void __launch_bounds__(1024) comp_sort_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
+                                                          int* __restrict__ roots, CompRec* __restrict__ comps, int* __restrict__ cid_at,
+                                                          int max_comps) {
+    const int page = blockIdx.x;
+    const DetPostPage pg = pages[page];
+    int n = counters[page].n_roots;
+    if (n > max_comps) {
+        if (threadIdx.x == 0) { counters[page].status = RETTO_B200_ERR_CAPACITY; counters[page].n_roots = 0; }
+        return;
+    }
+    int* r = roots + (size_t)page * max_comps;
+    block_sort_ints(r, n);
     CompRec* c = comps + (size_t)page * max_comps;
     int* cid = cid_at + pg.px_base;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(1024) comp_sort_kernel(const DetPostPage* __re
         cid[root] = i;
         CompRec cr;
         cr.root = root; cr.ymax = -1; cr.xmin = 0x7fffffff; cr.xmax = -1; cr.row_off = 0;
-        cr.key = 0x7fffffff; cr.pad[0] = cr.pad[1] = 0;
+        cr.key = 0x7fffffff; cr.ymin = root / pg.w; cr.pad = 0;
         c[i] = cr;
     }
 }
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(128) run_end_kernel(const DetPostPage* __restr
                 if ((is_start && x + j > 0) || (is_end && x + j + 1 < W)) atomicMin(&c[id].key, p);
             } else {
                 const CompRec cr = c[id];
-                const int ridx = cr.row_off + (y - cr.root / W);
+                const int ridx = cr.row_off + (y - cr.ymin);
                 if (ridx < ROWCAP) {
                     if (is_start) atomicMin(&rt[ridx].x, x + j);
                     if (is_end) atomicMax(&rt[ridx].y, x + j);
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(1024) row_alloc_kernel(const DetPostPage* __re
     const int per = (n + blockDim.x - 1) / blockDim.x;
     const int b = threadIdx.x * per, e = min(n, b + per);
     int sum = 0;
-    for (int i = b; i < e; ++i) sum += c[i].ymax - c[i].root / pg.w + 1;
+    for (int i = b; i < e; ++i) sum += c[i].ymax - c[i].ymin + 1;
     s_part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(1024) row_alloc_kernel(const DetPostPage* __re
     }
     __syncthreads();
     int off = s_part[threadIdx.x];
-    for (int i = b; i < e; ++i) { c[i].row_off = off; off += c[i].ymax - c[i].root / pg.w + 1; }
+    for (int i = b; i < e; ++i) { c[i].row_off = off; off += c[i].ymax - c[i].ymin + 1; }
     const int total = min(s_total, ROWCAP);
     int2* rt = rowtab + (size_t)page * ROWCAP;
     for (int i = threadIdx.x; i < total; i += blockDim.x) rt[i] = make_int2(0x7fffffff, -1);
@@ -382,20 +387,22 @@ struct GeomParams {
 __global__ void __launch_bounds__(128) box_geometry_kernel(const DetPostPage* __restrict__ pages,
                                                             int n_pages, PageCounters* __restrict__ counters, const CompRec* __restrict__ comps,
                                                             const int2* __restrict__ rowtab, int2* __restrict__ hullbuf, BoxCand* __restrict__ cand,
-                                                            int max_comps, GeomParams gp) {
+                                                            int max_comps, GeomParams gp, const int* __restrict__ hole_pages) {
     __shared__ int2 s_pts[4][MAX_OFFSET_PTS];
     __shared__ int2 s_hull[4][2 * MAX_OFFSET_PTS];
     __shared__ int s_n[4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int page = blockIdx.y;
-    const int id = blockIdx.x * 4 + wib;
+    // hole_pages == nullptr: ids [0, n_roots) of every page (outer borders); else ids [n_roots, n_roots + n_holes)
+    // of the listed pages (hole borders)
+    const int page = hole_pages ? hole_pages[blockIdx.y] : blockIdx.y;
     if (counters[page].status == RETTO_B200_ERR_CAPACITY) return;
-    const int n_comp = counters[page].n_roots;
+    const int id = (hole_pages ? counters[page].n_roots : 0) + blockIdx.x * 4 + wib;
+    const int n_comp = counters[page].n_roots + (hole_pages ? counters[page].n_holes : 0);
     if (id >= n_comp) return;
     const DetPostPage pg = pages[page];
     const CompRec cr = comps[(size_t)page * max_comps + id];
     BoxCand* out = cand + (size_t)page * max_comps + id;
-    const int ymin = cr.root / pg.w;
+    const int ymin = cr.ymin;
     const int R = cr.ymax - ymin + 1;
     const int2* rt = rowtab + (size_t)page * ROWCAP + cr.row_off;
     int2* hull = hullbuf + ((size_t)page * ROWCAP + cr.row_off) * 2;
@@ -489,6 +496,137 @@ __global__ void __launch_bounds__(128) box_geometry_kernel(const DetPostPage* __
     }
 }
 
+
+// ---- hole borders ---------------------------------------------------------------------------------------------
+// find_contours (det_processor.rs:293) also returns hole borders and retto does not filter by border_type, so every
+// background region enclosed by text pixels yields one more contour: the foreground pixels 4-adjacent to it.
+// Pages whose Euler number says holes exist (rare after the 2x2 dilation) take this extra path: 4-connected CCL of
+// the background (labels reuse the cid_at array, which is free by now), regions not connected to the frame are
+// holes; each becomes one more CompRec (discovery key = the pixel left of the hole's first pixel) with per-row
+// extremes of its border pixels, and goes through the same box_geometry kernel.
+#define MAX_HOLES 4096
+struct HoleArgs {
+    const DetPostPage* pages; const int* flag_pages; const int* flag_prefix; int nf; int total;
+};
+__device__ __forceinline__ bool hole_px(const HoleArgs& h, int& page, DetPostPage& pg, int& p) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= h.total) return false;
+    const int k = rt_find_segment(h.flag_prefix, h.nf, u);
+    page = h.flag_pages[k];
+    pg = h.pages[page];
+    p = u - h.flag_prefix[k];
+    return true;
+}
+__global__ void bg_init_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, int* __restrict__ bgl) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    bgl[pg.px_base + p] = bitmap[pg.px_base + p] ? -1 : p;
+}
+__global__ void bg_merge_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, int* __restrict__ bgl) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    const unsigned char* bm = bitmap + pg.px_base;
+    if (bm[p]) return;
+    int* L = bgl + pg.px_base;
+    const int y = p / pg.w, x = p - y * pg.w;
+    if (x > 0 && !bm[p - 1]) union_labels(L, p, p - 1);
+    if (y > 0 && !bm[p - pg.w]) union_labels(L, p, p - pg.w);
+}
+__global__ void bg_flatten_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, int* __restrict__ bgl, int* __restrict__ labels) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    if (bitmap[pg.px_base + p]) return;
+    int* L = bgl + pg.px_base;
+    const int r = find_root(L, p);
+    L[p] = r;
+    const int y = p / pg.w, x = p - y * pg.w;
+    if (x == 0 || y == 0 || x == pg.w - 1 || y == pg.h - 1) labels[pg.px_base + r] = -2;  // connected to the frame: outer background
+}
+__global__ void hole_collect_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, const int* __restrict__ bgl,
+                                    const int* __restrict__ labels, PageCounters* __restrict__ counters, int* __restrict__ holes) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    if (bitmap[pg.px_base + p] || bgl[pg.px_base + p] != p || labels[pg.px_base + p] == -2) return;
+    const int slot = atomicAdd(&counters[page].n_holes, 1);
+    if (slot < MAX_HOLES) holes[(size_t)page * MAX_HOLES + slot] = p;
+}
+__global__ void __launch_bounds__(1024) hole_sort_kernel(HoleArgs h, PageCounters* __restrict__ counters, int* __restrict__ holes,
+                                                          int* __restrict__ labels, CompRec* __restrict__ comps, int max_comps) {
+    const int page = h.flag_pages[blockIdx.x];
+    const DetPostPage pg = h.pages[page];
+    const int n = counters[page].n_holes, nr = counters[page].n_roots;
+    if (n > MAX_HOLES || nr + n > max_comps) {
+        if (threadIdx.x == 0) { counters[page].status = RETTO_B200_ERR_CAPACITY; counters[page].n_holes = 0; }
+        return;
+    }
+    int* r = holes + (size_t)page * MAX_HOLES;
+    block_sort_ints(r, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int root = r[i];
+        labels[pg.px_base + root] = -(3 + i);       // root -> hole id (restored to -1 by hole_restore_kernel)
+        CompRec cr;
+        cr.root = root; cr.ymax = -1; cr.xmin = 0; cr.xmax = 0; cr.row_off = 0;
+        cr.key = root - 1;                           // discovered at the foreground pixel left of the hole's first pixel
+        cr.ymin = root / pg.w; cr.pad = 0;
+        comps[(size_t)page * max_comps + nr + i] = cr;
+    }
+}
+__global__ void hole_extent_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, const int* __restrict__ bgl,
+                                   const int* __restrict__ labels, const PageCounters* __restrict__ counters, CompRec* __restrict__ comps,
+                                   int max_comps) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    if (bitmap[pg.px_base + p] || counters[page].status != RETTO_B200_OK) return;
+    const int v = labels[pg.px_base + bgl[pg.px_base + p]];
+    if (v > -3) return;
+    atomicMax(&comps[(size_t)page * max_comps + counters[page].n_roots + (-v - 3)].ymax, p / pg.w);
+}
+__global__ void __launch_bounds__(256) hole_row_alloc_kernel(HoleArgs h, PageCounters* __restrict__ counters, CompRec* __restrict__ comps,
+                                                              int2* __restrict__ rowtab, int max_comps) {
+    const int page = h.flag_pages[blockIdx.x];
+    if (counters[page].status != RETTO_B200_OK) return;
+    __shared__ int s_first, s_total;
+    const int n = counters[page].n_holes, nr = counters[page].n_roots;
+    CompRec* c = comps + (size_t)page * max_comps + nr;
+    if (threadIdx.x == 0) {
+        int off = counters[page].row_total;
+        s_first = off;
+        for (int i = 0; i < n; ++i) {   // border rows span [ymin - 1, ymax + 1]
+            c[i].ymin -= 1; c[i].ymax += 1;
+            c[i].row_off = off;
+            off += c[i].ymax - c[i].ymin + 1;
+        }
+        s_total = off;
+        counters[page].row_total = off;
+        if (off > ROWCAP) counters[page].status = RETTO_B200_ERR_CAPACITY;
+    }
+    __syncthreads();
+    int2* rt = rowtab + (size_t)page * ROWCAP;
+    for (int i = s_first + threadIdx.x; i < min(s_total, ROWCAP); i += blockDim.x) rt[i] = make_int2(0x7fffffff, -1);
+}
+__global__ void hole_rows_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, const int* __restrict__ bgl,
+                                 const int* __restrict__ labels, const PageCounters* __restrict__ counters, const CompRec* __restrict__ comps,
+                                 int2* __restrict__ rowtab, int max_comps) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    const unsigned char* bm = bitmap + pg.px_base;
+    if (bm[p] || counters[page].status != RETTO_B200_OK) return;
+    const int v = labels[pg.px_base + bgl[pg.px_base + p]];
+    if (v > -3) return;
+    const CompRec cr = comps[(size_t)page * max_comps + counters[page].n_roots + (-v - 3)];
+    int2* rt = rowtab + (size_t)page * ROWCAP + cr.row_off;
+    const int y = p / pg.w, x = p - y * pg.w;   // a hole never touches the frame: all 4 neighbours are inside the page
+    if (bm[p - 1]) { atomicMin(&rt[y - cr.ymin].x, x - 1); atomicMax(&rt[y - cr.ymin].y, x - 1); }
+    if (bm[p + 1]) { atomicMin(&rt[y - cr.ymin].x, x + 1); atomicMax(&rt[y - cr.ymin].y, x + 1); }
+    if (bm[p - pg.w]) { atomicMin(&rt[y - 1 - cr.ymin].x, x); atomicMax(&rt[y - 1 - cr.ymin].y, x); }
+    if (bm[p + pg.w]) { atomicMin(&rt[y + 1 - cr.ymin].x, x); atomicMax(&rt[y + 1 - cr.ymin].y, x); }
+}
+__global__ void hole_restore_kernel(HoleArgs h, int* __restrict__ labels) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    if (labels[pg.px_base + p] < -1) labels[pg.px_base + p] = -1;
+}
+
 // ---- I: per-page compaction + sorted_boxes (det_processor.rs:324-333) ----------------------------------------------
 __device__ __forceinline__ bool box_less(const BoxCand& r1, const BoxCand& r2) {
     const float c1x = __fdiv_rn(__fadd_rn(r1.xy[0], r1.xy[4]), 2.0f), c1y = __fdiv_rn(__fadd_rn(r1.xy[1], r1.xy[5]), 2.0f);
@@ -502,7 +640,7 @@ __global__ void trace_copy_kernel(int n_pages, const PageCounters* __restrict__ 
                                   TraceRec* __restrict__ trace) {
     const int page = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (page >= n_pages || i >= counters[page].n_roots || i >= max_comps) return;
+    if (page >= n_pages || i >= counters[page].n_roots + counters[page].n_holes || i >= max_comps) return;
     const BoxCand& b = cand[(size_t)page * max_comps + i];
     TraceRec t;
     t.key = b.key; t.status = b.status; t.sside1 = b.sside1; t.score = b.score;
@@ -515,7 +653,7 @@ __global__ void __launch_bounds__(32) page_sort_kernel(int n_pages, PageCounters
     const int page = blockIdx.x;
     if (threadIdx.x != 0 || page >= n_pages) return;
     if (counters[page].status == RETTO_B200_ERR_CAPACITY) { counters[page].n_boxes = 0; return; }
-    const int n = counters[page].n_roots;
+    const int n = counters[page].n_roots + counters[page].n_holes;
     BoxCand* c = cand + (size_t)page * max_comps;
     int m = 0;
     for (int i = 0; i < n; ++i)
@@ -669,8 +807,61 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
         GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
         dim3 grid((max_n + 3) / 4, n);
         RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel");
-        box_geometry_kernel<<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp);
+        box_geometry_kernel<<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
         RT_LAUNCH_CHECK(ctx);
+    }
+    // hole borders: pages with #components - Euler number > 0
+    {
+        std::vector<int> fp, fpre{0};
+        for (int i = 0; i < n; ++i)
+            if (h_cnt[i].status == RETTO_B200_OK && h_cnt[i].n_roots <= max_comps && h_cnt[i].n_roots - h_cnt[i].euler > 0) {
+                fp.push_back(i);
+                fpre.push_back(fpre.back() + ctx->dp_pages[i].h * ctx->dp_pages[i].w);
+            }
+        if (!fp.empty()) {
+            const int nf = (int)fp.size(), total = fpre.back();
+            std::vector<int> blob(fp);
+            blob.insert(blob.end(), fpre.begin(), fpre.end());
+            RT_TRY(rt_upload(ctx, ctx->d_hole_pages, blob.data(), blob.size() * sizeof(int)));
+            RT_CUDA_OK(ctx, ctx->d_holes.ensure(sizeof(int) * (size_t)n * MAX_HOLES, st));
+            HoleArgs ha{d_pages, ctx->d_hole_pages.as<int>(), ctx->d_hole_pages.as<int>() + nf, nf, total};
+            int* d_holes = ctx->d_holes.as<int>();
+            const int g = (total + 255) / 256;
+            RT_LAUNCH_BEGIN(ctx, "bg_init_kernel");
+            bg_init_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "bg_merge_kernel");
+            bg_merge_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "bg_flatten_kernel");
+            bg_flatten_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "hole_collect_kernel");
+            hole_collect_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab, d_cnt, d_holes);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "hole_sort_kernel");
+            hole_sort_kernel<<<nf, 1024, 0, st>>>(ha, d_cnt, d_holes, d_lab, d_comps, max_comps);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "hole_extent_kernel");
+            hole_extent_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab, d_cnt, d_comps, max_comps);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "hole_row_alloc_kernel");
+            hole_row_alloc_kernel<<<nf, 256, 0, st>>>(ha, d_cnt, d_comps, d_rowtab, max_comps);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "hole_rows_kernel");
+            hole_rows_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab, d_cnt, d_comps, d_rowtab, max_comps);
+            RT_LAUNCH_CHECK(ctx);
+            int max_h = 0;
+            for (int i : fp) max_h = std::max(max_h, std::min(h_cnt[i].n_roots - h_cnt[i].euler, MAX_HOLES));
+            GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
+            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
+            box_geometry_kernel<<<dim3((max_h + 3) / 4, nf), 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "hole_restore_kernel");
+            hole_restore_kernel<<<g, 256, 0, st>>>(ha, d_lab);
+            RT_LAUNCH_CHECK(ctx);
+            max_n = std::max(max_n, std::min(max_n + max_h, max_comps));
+        }
     }
     ctx->dp_trace_valid = false;
     if (ctx->dp_trace_enabled && max_n > 0) {
@@ -705,7 +896,7 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     h_box_offsets[n] = h_off[n];
     ctx->dp_holes.assign(n, 0);
     ctx->dp_ncomp.assign(n, 0);
-    for (int i = 0; i < n; ++i) { ctx->dp_holes[i] = h_cnt[i].n_roots - h_cnt[i].euler; ctx->dp_ncomp[i] = h_cnt[i].n_roots; }
+    for (int i = 0; i < n; ++i) { ctx->dp_holes[i] = h_cnt[i].n_holes; ctx->dp_ncomp[i] = h_cnt[i].n_roots + h_cnt[i].n_holes; }
     const int total = h_off[n];
     if (total > cap) {
         ctx->set_error("det_postprocess: " + std::to_string(total) + " boxes exceed max_boxes_total " + std::to_string(cap));

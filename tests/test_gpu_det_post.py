@@ -37,7 +37,7 @@ def _consistent_maps(seed0, n, h, w, **kw):
     return out
 
 
-def _check_pages(ctx, probs, ori_hw=None, libm=1):
+def _check_pages(ctx, probs, ori_hw=None, libm=1, allow_inconsistent=False):
     import torch
     from oracle import oracle as O
     O.set_libm(libm)
@@ -52,7 +52,9 @@ def _check_pages(ctx, probs, ori_hw=None, libm=1):
         lab = ctx.fetch_labels(i, *p.shape)
         assert np.array_equal(lab, _labels_ref(ref.bitmap)), f"label mismatch page {i}"
         boxes, scores = out.page(i)
-        assert not ref.comparator_inconsistent
+        # (an inconsistent sorted_boxes comparator makes the REFERENCE's order depend on Rust's sort internals; the
+        #  oracle and the CUDA path both use the n <= 20 insertion sort, so they still agree with each other)
+        assert allow_inconsistent or not ref.comparator_inconsistent
         assert ref.status >= 0 and out.page_status[i] == 0
         assert boxes.shape == ref.boxes.shape, f"page {i}: {len(boxes)} vs {len(ref.boxes)} boxes"
         assert np.array_equal(boxes, ref.boxes), f"box mismatch page {i}"
@@ -109,3 +111,38 @@ def test_noise_speckles(ctx):
     p = (rng.random((200, 300)) < 0.02).astype(np.float32) * 0.9
     p[50:90, 40:200] = 0.8
     _check_pages(ctx, [p])
+
+
+def test_hole_borders(ctx):
+    """find_contours also returns hole borders (no border_type filter in retto): rings, tiny holes whose border
+    box survives, nested shapes, holes next to the frame"""
+    import cv2
+    maps = []
+    a = np.full((128, 192), 0.05, np.float32)
+    a[10:60, 10:180] = 0.9
+    a[25:45, 30:160] = 0.05            # big hole: hole contour fails the score filter
+    a[80:110, 20:80] = 0.9
+    a[93:96, 40:43] = 0.1              # 3x3 raw hole -> 2x2 after dilation: its border box survives
+    a[93:96, 60:64] = 0.1
+    maps.append(a)
+    b = np.full((96, 96), 0.02, np.float32)
+    b[2:94, 2:94] = 0.95               # frame-filling blob with several holes, one containing an island
+    b[10:40, 10:40] = 0.0
+    b[20:30, 20:30] = 0.9              # island inside the hole (its own outer border)
+    b[50:54, 50:90] = 0.0
+    b[70:73, 10:13] = 0.0
+    maps.append(b)
+    rng = np.random.default_rng(11)
+    for _ in range(4):                 # random blobs: many irregular holes
+        m = (rng.random((80, 120)) < 0.62).astype(np.uint8) * 255
+        m = cv2.morphologyEx(m, cv2.MORPH_OPEN, np.ones((3, 3), np.uint8))
+        maps.append(np.where(m > 0, 0.9, 0.05).astype(np.float32))
+    ctx.enable_trace(True)
+    out = _check_pages(ctx, maps, allow_inconsistent=True)
+    from oracle import oracle as O
+    for i, p in enumerate(maps):
+        # true holes (textbook Suzuki-Abe typing; with the frame quirk some OUTER borders are merely typed "hole")
+        n_holes_ref = sum(h for _, h in O.find_contours(O.threshold_dilate(p), quirk_x0=0))
+        assert ctx.fetch_trace(i)["n_holes"] == n_holes_ref
+    ctx.enable_trace(False)
+    assert ctx.fetch_trace(0)["n_holes"] == 3 and len(out.page(0)[0]) == 3   # 2 outer boxes + 1 surviving hole-border box

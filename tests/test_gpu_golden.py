@@ -34,14 +34,13 @@ def test_det_postprocess_golden(ctx):
     out = ctx.det_postprocess(probs, [(96, 128)] * n)
     for k in range(n):
         tr = ctx.fetch_trace(k)
-        if tr["n_holes"] == 0:   # pages with hole borders: the hole contour has no CUDA counterpart yet
-            boxes, scores = out.page(k)
-            assert np.array_equal(boxes, G[f"det_boxes_{k}"])
-            assert np.array_equal(scores.view(np.uint32), G[f"det_scores_{k}"].view(np.uint32))
-            keep = tr["status"] != 6
-            order = np.argsort(tr["key"][keep], kind="stable")
-            assert np.array_equal(tr["rect1"][keep][order], G[f"det_rect1_{k}"])
-            assert np.array_equal(tr["status"][keep][order], G[f"det_status_{k}"])
+        boxes, scores = out.page(k)
+        assert np.array_equal(boxes, G[f"det_boxes_{k}"])
+        assert np.array_equal(scores.view(np.uint32), G[f"det_scores_{k}"].view(np.uint32))
+        keep = tr["status"] != 6
+        order = np.argsort(tr["key"][keep], kind="stable")
+        assert np.array_equal(tr["rect1"][keep][order], G[f"det_rect1_{k}"])
+        assert np.array_equal(tr["status"][keep][order], G[f"det_status_{k}"])
     ctx.enable_trace(False)
     ring = n - 2
     assert ctx.fetch_trace(ring)["n_holes"] == 1 and int(G[f"det_ncontours_{ring}"]) == 2
