@@ -268,18 +268,28 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
         const float* row = pred + (size_t)(y + y_min) * w + x_min;
         for (int s = 0; s < rc.n; ++s) {
             count += (unsigned long long)(rc.b[s] - rc.a[s] + 1);
-            for (int x = rc.a[s]; x <= rc.b[s]; x += 32) {
-                const int xi = x + lane;
-                const float v = (xi <= rc.b[s]) ? __ldg(row + xi) : 0.0f;
-                const int lim = min(32, rc.b[s] - x + 1);
-                if (lim == 32) {   // full chunk: 32 independent shuffles first, then the dependent add chain
-                    float t[32];
+            // 128 pixels per step: four independent coalesced loads in flight, then the reference's sequential add
+            // chain replayed by every lane through shuffles (bit-identical to the scalar fold)
+            for (int x = rc.a[s]; x <= rc.b[s]; x += 128) {
+                float v[4];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) t[k] = __shfl_sync(RT_FULL, v, k);
+                for (int q = 0; q < 4; ++q) {
+                    const int xi = x + 32 * q + lane;
+                    v[q] = (xi <= rc.b[s]) ? __ldg(row + xi) : 0.0f;
+                }
+                const int n = min(128, rc.b[s] - x + 1);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, t[k]);
-                } else {
-                    for (int k = 0; k < lim; ++k) acc = __fadd_rn(acc, __shfl_sync(RT_FULL, v, k));
+                for (int q = 0; q < 4; ++q) {
+                    const int lim = n - 32 * q;
+                    if (lim >= 32) {
+                        float t[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) t[k] = __shfl_sync(RT_FULL, v[q], k);
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, t[k]);
+                    } else {
+                        for (int k = 0; k < lim; ++k) acc = __fadd_rn(acc, __shfl_sync(RT_FULL, v[q], k));
+                    }
                 }
             }
         }

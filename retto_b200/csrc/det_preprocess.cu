@@ -23,47 +23,45 @@ __device__ __forceinline__ float norm1(unsigned char v, float scale, float mean,
     return __fdiv_rn(__fsub_rn(__fmul_rn((float)v, scale), mean), stdv);
 }
 
-// work unit = 16 consecutive pixels of one row.  unit_prefix[p] = units before page p.
+// work unit = 512 consecutive pixels (identity resize: pixel index == output index), one warp per unit:
+//   3 x LDG.128 per lane, fully coalesced (1536 contiguous bytes per warp) -> shared memory,
+//   then per plane 4 x STG.128 per lane, each store instruction writing 512 contiguous bytes.
+// unit_prefix[p] = units before page p.  Normalisation comes from 256-entry tables built with the
+// reference's three separately rounded f32 operations (bit-identical to per-pixel evaluation).
 __global__ void __launch_bounds__(256) det_pre_identity_kernel(const DetPreDev* __restrict__ pages, const int* __restrict__ unit_prefix,
                                                                 int n_pages, int total_units, NormParams np) {
-    // 256-entry normalisation tables per tensor channel, built with the reference's three separately rounded
-    // f32 operations (bit-identical to computing them per pixel, without 48 divisions per thread)
     __shared__ float s_lut[3][256];
+    __shared__ __align__(16) unsigned s_px[8][384];   // 8 warps x 1536 bytes
     for (int i = threadIdx.x; i < 768; i += blockDim.x) {
         const int c = i >> 8, v = i & 255;
         s_lut[c][v] = norm1((unsigned char)v, np.scale, np.mean[c], np.stdv[c]);
     }
     __syncthreads();
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int u = blockIdx.x * 8 + wib;
     if (u >= total_units) return;
     const int p = rt_find_segment(unit_prefix, n_pages, u);
     const DetPreDev pg = pages[p];
-    const int lu = u - unit_prefix[p];
-    const size_t pix = (size_t)lu * 16;          // first pixel (row-major) of this unit; rows are multiples of 16 px
+    const size_t pix0 = (size_t)(u - unit_prefix[p]) * 512;
     const size_t plane = (size_t)pg.oh * pg.ow;
-    const uint4* s = reinterpret_cast<const uint4*>(pg.src + pix * 3);
-    const uint4 a = __ldcs(s), b = __ldcs(s + 1), c = __ldcs(s + 2);
-    const unsigned wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-    float r[16], g[16], bl[16];
+    const uint4* src = reinterpret_cast<const uint4*>(pg.src + pix0 * 3);
+    uint4* sw = reinterpret_cast<uint4*>(s_px[wib]);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        // byte 3*i + ch of the 48-byte group
-        const int o0 = 3 * i, o1 = 3 * i + 1, o2 = 3 * i + 2;
-        const unsigned char vr = (wds[o0 >> 2] >> ((o0 & 3) * 8)) & 0xff;
-        const unsigned char vg = (wds[o1 >> 2] >> ((o1 & 3) * 8)) & 0xff;
-        const unsigned char vb = (wds[o2 >> 2] >> ((o2 & 3) * 8)) & 0xff;
-        bl[i] = s_lut[0][vb];
-        g[i] = s_lut[1][vg];
-        r[i] = s_lut[2][vr];
-    }
-    float4* d0 = reinterpret_cast<float4*>(pg.dst + pix);
-    float4* d1 = reinterpret_cast<float4*>(pg.dst + plane + pix);
-    float4* d2 = reinterpret_cast<float4*>(pg.dst + 2 * plane + pix);
+    for (int k = 0; k < 3; ++k) sw[k * 32 + lane] = __ldcs(src + k * 32 + lane);
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        __stcs(d0 + q, make_float4(bl[4 * q], bl[4 * q + 1], bl[4 * q + 2], bl[4 * q + 3]));
-        __stcs(d1 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
-        __stcs(d2 + q, make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]));
+        // pixels q*128 + lane*4 .. +3 = 12 bytes = words 3*(q*32+lane) .. +2 (bank = 3*lane mod 32: conflict-free)
+        const unsigned* w3 = s_px[wib] + 3 * (q * 32 + lane);
+        const unsigned w0 = w3[0], w1 = w3[1], w2 = w3[2];
+        // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        const unsigned char r0 = w0 & 0xff, g0 = (w0 >> 8) & 0xff, b0 = (w0 >> 16) & 0xff, r1 = w0 >> 24;
+        const unsigned char g1 = w1 & 0xff, b1 = (w1 >> 8) & 0xff, r2 = (w1 >> 16) & 0xff, g2 = w1 >> 24;
+        const unsigned char b2 = w2 & 0xff, r3 = (w2 >> 8) & 0xff, g3 = (w2 >> 16) & 0xff, b3 = w2 >> 24;
+        const size_t o = pix0 + q * 128 + lane * 4;
+        __stcs(reinterpret_cast<float4*>(pg.dst + o), make_float4(s_lut[0][b0], s_lut[0][b1], s_lut[0][b2], s_lut[0][b3]));
+        __stcs(reinterpret_cast<float4*>(pg.dst + plane + o), make_float4(s_lut[1][g0], s_lut[1][g1], s_lut[1][g2], s_lut[1][g3]));
+        __stcs(reinterpret_cast<float4*>(pg.dst + 2 * plane + o), make_float4(s_lut[2][r0], s_lut[2][r1], s_lut[2][r2], s_lut[2][r3]));
     }
 }
 
@@ -199,9 +197,9 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
         const DetPreDev dv{d.d_rgb, d.h, d.w, d.d_out, d.out_h, d.out_w};
         const long long px = (long long)d.out_h * d.out_w;
         const bool aligned = ((uintptr_t)d.d_rgb % 16 == 0) && ((uintptr_t)d.d_out % 16 == 0);
-        if (d.out_h == d.h && d.out_w == d.w && (d.w % 16 == 0) && aligned) {
+        if (d.out_h == d.h && d.out_w == d.w && (px % 512 == 0) && aligned) {
             ident.push_back(dv);
-            ident_pre.push_back(ident_pre.back() + (int)(px / 16));
+            ident_pre.push_back(ident_pre.back() + (int)(px / 512));
         } else if (d.out_w % 4 == 0 && ((uintptr_t)d.d_out % 16 == 0)) {
             rs.push_back(dv);
             rs_pre.push_back(rs_pre.back() + (int)(px / 4));
@@ -216,7 +214,7 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
         RT_TRY(upload_with_prefix(ctx, ctx->d_stage, ident, ident_pre, &dv, &dp));
         const int total = ident_pre.back();
         RT_LAUNCH_BEGIN(ctx, "det_pre_identity_kernel");
-        det_pre_identity_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dv, dp, (int)ident.size(), total, np);
+        det_pre_identity_kernel<<<(total + 7) / 8, 256, 0, ctx->stream>>>(dv, dp, (int)ident.size(), total, np);
         RT_LAUNCH_CHECK(ctx);
     }
     if (!rs.empty()) {
