@@ -98,7 +98,32 @@ __device__ __forceinline__ float cubic(float p0, float p1, float p2, float p3, f
     return __fadd_rn(p1, __fmul_rn(__fmul_rn(0.5f, x), c));
 }
 
-__global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restrict__ crops, const int* __restrict__ unit_prefix, int n_crops,
+// Translation-class crops with an integral offset (axis-aligned boxes — the common case for text lines): the sample
+// position is an exact pixel centre, both cubic weights are 0 and cubic(p0,p1,p2,p3,0) == p1, so the warp is a guarded
+// row copy (same white-border rule: any tap of the 4x4 window outside the page -> white).  One warp per crop row,
+// byte lanes fully coalesced on both sides.
+__global__ void __launch_bounds__(256) crop_copy_rows_kernel(const CropDev* __restrict__ crops, const int* __restrict__ fast_idx,
+                                                              const int* __restrict__ row_prefix, int n_fast, int total_rows,
+                                                              unsigned char* __restrict__ pix) {
+    const int lane = threadIdx.x & 31;
+    const int ru = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (ru >= total_rows) return;
+    const int k = rt_find_segment(row_prefix, n_fast, ru);
+    const CropDev& c = crops[fast_idx[k]];
+    const int y = ru - row_prefix[k];
+    const int tx = (int)c.t[2], ty = (int)c.t[5];
+    const int iy = y + ty;
+    const bool row_ok = !(iy - 1 < 0 || iy + 3 >= c.page_h);
+    const int xlo = max(0, 1 - tx), xhi = min(c.w - 1, c.page_w - 4 - tx);   // columns whose 4x4 window is inside the page
+    unsigned char* dst = pix + c.offset + (size_t)y * c.w * 3;
+    const unsigned char* src = c.page + ((size_t)iy * c.page_w + tx) * 3;
+    const int nb = 3 * c.w, blo = 3 * xlo, bhi = 3 * xhi + 2;
+    for (int i = lane; i < nb; i += 32) dst[i] = (row_ok && i >= blo && i <= bhi) ? __ldg(src + i) : (unsigned char)255;
+}
+
+// general path (affine / projective, or rotate270): idx lists the crops it handles, unit_prefix their pixel prefix
+__global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restrict__ crops, const int* __restrict__ idx,
+                                                         const int* __restrict__ unit_prefix, int n_crops,
                                                          int total_units, unsigned char* __restrict__ pix) {
     // one binary search per block (its first unit), then a short linear walk per thread
     __shared__ int s_ci;
@@ -108,7 +133,7 @@ __global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restric
     if (u >= total_units) return;
     int ci = s_ci;
     while (ci + 1 < n_crops && u >= unit_prefix[ci + 1]) ++ci;
-    const CropDev& c = crops[ci];
+    const CropDev& c = crops[idx[ci]];
     if (c.status != RETTO_B200_OK) return;
     const int lu = u - unit_prefix[ci];
     const int w = c.rot ? c.h : c.w, h = c.rot ? c.w : c.h;  // un-rotated warp size
@@ -220,15 +245,41 @@ extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const re
     RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
     crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n);
     RT_LAUNCH_CHECK(ctx);
-    const int total = prefix[n];
-    if (total > 0) {
-        RT_LAUNCH_BEGIN(ctx, "crop_warp_kernel");
-        crop_warp_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_crops, d_prefix, n, total, ctx->d_crop_pix.as<unsigned char>());
-        RT_LAUNCH_CHECK(ctx);
-    }
-    // statuses back (projection degeneracy is only known on the device)
+    // projection class / degeneracy are only known on the device: fetch the descriptors, then split the crops into the
+    // row-copy fast path and the general bicubic path
     RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->crops.data(), d_crops, sizeof(CropDev) * n, cudaMemcpyDeviceToHost, st));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    std::vector<int> fast, gen, fast_pre{0}, gen_pre{0};
+    for (int i = 0; i < n; ++i) {
+        const CropDev& c = ctx->crops[i];
+        if (c.status != RETTO_B200_OK || c.w <= 0 || c.h <= 0) continue;
+        if (c.cls == 0 && !c.rot && c.t[2] == floorf(c.t[2]) && c.t[5] == floorf(c.t[5]) && fabsf(c.t[2]) < 1e6f && fabsf(c.t[5]) < 1e6f) {
+            fast.push_back(i); fast_pre.push_back(fast_pre.back() + c.h);
+        } else {
+            gen.push_back(i); gen_pre.push_back(gen_pre.back() + c.w * c.h);
+        }
+    }
+    (void)d_prefix;
+    if (!fast.empty()) {
+        std::vector<int> blob(fast);
+        blob.insert(blob.end(), fast_pre.begin(), fast_pre.end());
+        RT_TRY(rt_upload(ctx, ctx->d_stage, blob.data(), blob.size() * sizeof(int)));
+        const int rows = fast_pre.back();
+        RT_LAUNCH_BEGIN(ctx, "crop_copy_rows_kernel");
+        crop_copy_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_crops, ctx->d_stage.as<int>(), ctx->d_stage.as<int>() + fast.size(), (int)fast.size(), rows,
+                                                              ctx->d_crop_pix.as<unsigned char>());
+        RT_LAUNCH_CHECK(ctx);
+    }
+    if (!gen.empty()) {
+        std::vector<int> blob(gen);
+        blob.insert(blob.end(), gen_pre.begin(), gen_pre.end());
+        RT_TRY(rt_upload(ctx, ctx->d_stage2, blob.data(), blob.size() * sizeof(int)));
+        const int total = gen_pre.back();
+        RT_LAUNCH_BEGIN(ctx, "crop_warp_kernel");
+        crop_warp_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_crops, ctx->d_stage2.as<int>(), ctx->d_stage2.as<int>() + gen.size(), (int)gen.size(), total,
+                                                              ctx->d_crop_pix.as<unsigned char>());
+        RT_LAUNCH_CHECK(ctx);
+    }
     retto_b200_status ret = RETTO_B200_OK;
     for (int i = 0; i < n; ++i) {
         const CropDev& c = ctx->crops[i];

@@ -20,9 +20,11 @@
 
 #if defined(__CUDACC__)
 #define RT_HD __host__ __device__ __forceinline__
+#define RT_HD_BIG static __host__ __device__ __noinline__   // big bodies: one copy per TU keeps kernels small (I-cache, registers)
 #define RT_NOUNROLL _Pragma("unroll 1")
 #else
 #define RT_HD inline
+#define RT_HD_BIG static inline
 #define RT_NOUNROLL
 #endif
 
@@ -104,7 +106,7 @@ RT_HD double dd_round(dd a) { return a.hi + a.lo; }
 
 // sin and cos of a double-double argument, |a| small multiples of pi (no huge-argument reduction:
 // the path only produces |a| <= 2*pi).
-RT_HD void sincos_dd(dd a, dd* s_out, dd* c_out) {
+RT_HD_BIG void sincos_dd(dd a, dd* s_out, dd* c_out) {
     // quadrant reduction: a = k*(pi/2) + r, |r| <= pi/4
     double kf = floor(a.hi * 0.6366197723675814 + 0.5);
     dd r = a;
@@ -176,7 +178,7 @@ RT_HD double rt_cos(double a) {
 }
 
 // atan2 of double-double (y, x); returns dd.  (x, y) != (0, 0).
-RT_HD dd atan2_dd(dd y, dd x) {
+RT_HD_BIG dd atan2_dd(dd y, dd x) {
     double ax = fabs(x.hi), ay = fabs(y.hi);
     // crude double guess (max error ~1e-5 rad)
     double mn = ax < ay ? ax : ay, mx = ax < ay ? ay : ax;
@@ -213,7 +215,7 @@ RT_HD double rt_atan2(double y, double x) {
 }
 
 // acos(v), |v| <= 1
-RT_HD double rt_acos(double v) {
+RT_HD_BIG double rt_acos(double v) {
     if (v >= 1.0) return 0.0;
     if (v <= -1.0) return RT_PI_D;
     dd om = two_sum(1.0, -v);
