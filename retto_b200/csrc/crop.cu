@@ -98,63 +98,8 @@ __device__ __forceinline__ float cubic(float p0, float p1, float p2, float p3, f
     return __fadd_rn(p1, __fmul_rn(__fmul_rn(0.5f, x), c));
 }
 
-// Translation-class crops with an integral offset (axis-aligned boxes — the common case for text lines): the sample
-// position is an exact pixel centre, both cubic weights are 0 and cubic(p0,p1,p2,p3,0) == p1, so the warp is a guarded
-// row copy (same white-border rule: any tap of the 4x4 window outside the page -> white).  One warp per crop row,
-// byte lanes fully coalesced on both sides.
-__global__ void __launch_bounds__(256) crop_copy_rows_kernel(const CropDev* __restrict__ crops, const int* __restrict__ fast_idx,
-                                                              const int* __restrict__ row_prefix, int n_fast, int total_rows,
-                                                              unsigned char* __restrict__ pix) {
-    const int lane = threadIdx.x & 31;
-    const int ru = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (ru >= total_rows) return;
-    const int k = rt_find_segment(row_prefix, n_fast, ru);
-    const CropDev& c = crops[fast_idx[k]];
-    const int y = ru - row_prefix[k];
-    const int tx = (int)c.t[2], ty = (int)c.t[5];
-    const int iy = y + ty;
-    const bool row_ok = !(iy - 1 < 0 || iy + 3 >= c.page_h);
-    const int xlo = max(0, 1 - tx), xhi = min(c.w - 1, c.page_w - 4 - tx);   // columns whose 4x4 window is inside the page
-    unsigned char* dst = pix + c.offset + (size_t)y * c.w * 3;
-    const unsigned char* src = c.page + ((size_t)iy * c.page_w + tx) * 3;
-    const int nb = 3 * c.w, blo = 3 * xlo, bhi = 3 * xhi + 2;
-    for (int i = lane; i < nb; i += 32) dst[i] = (row_ok && i >= blo && i <= bhi) ? __ldg(src + i) : (unsigned char)255;
-}
-
-// general path (affine / projective, or rotate270): idx lists the crops it handles, unit_prefix their pixel prefix
-__global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restrict__ crops, const int* __restrict__ idx,
-                                                         const int* __restrict__ unit_prefix, int n_crops,
-                                                         int total_units, unsigned char* __restrict__ pix) {
-    // one binary search per block (its first unit), then a short linear walk per thread
-    __shared__ int s_ci;
-    if (threadIdx.x == 0) s_ci = rt_find_segment(unit_prefix, n_crops, min(blockIdx.x * blockDim.x, total_units - 1));
-    __syncthreads();
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= total_units) return;
-    int ci = s_ci;
-    while (ci + 1 < n_crops && u >= unit_prefix[ci + 1]) ++ci;
-    const CropDev& c = crops[idx[ci]];
-    if (c.status != RETTO_B200_OK) return;
-    const int lu = u - unit_prefix[ci];
-    const int w = c.rot ? c.h : c.w, h = c.rot ? c.w : c.h;  // un-rotated warp size
-    const int y = lu / w, x = lu - y * w;
-    size_t o;
-    if (c.rot) o = ((size_t)(w - 1 - x) * h + y) * 3;  // rotate270: out(y, w-1-x) = in(x, y), out is h wide
-    else o = ((size_t)y * w + x) * 3;
-    unsigned char* dst = pix + c.offset + o;
-    // Translation class with an integral offset (axis-aligned boxes: the common case for text lines): the sample
-    // position is an exact pixel centre, both cubic weights are 0 and cubic(p0,p1,p2,p3,0) == p1, so the warp
-    // degenerates to a guarded copy (same white-border rule).
-    if (c.cls == 0 && c.t[2] == floorf(c.t[2]) && c.t[5] == floorf(c.t[5])) {
-        const int ix = x + (int)c.t[2], iy = y + (int)c.t[5];
-        unsigned char r0 = 255, r1 = 255, r2 = 255;
-        if (!(ix - 1 < 0 || ix + 3 >= c.page_w || iy - 1 < 0 || iy + 3 >= c.page_h)) {
-            const unsigned char* sp = c.page + ((size_t)iy * c.page_w + ix) * 3;
-            r0 = __ldg(sp); r1 = __ldg(sp + 1); r2 = __ldg(sp + 2);
-        }
-        dst[0] = r0; dst[1] = r1; dst[2] = r2;
-        return;
-    }
+// bicubic sample of one output pixel (x, y) of the un-rotated warp (imageproc warp_into + interpolate_bicubic)
+__device__ __forceinline__ void crop_pixel(const CropDev& c, int x, int y, unsigned char rgb[3]) {
     const float xf = (float)x, yf = (float)y;
     float px, py;
     if (c.cls == 2) {
@@ -168,7 +113,7 @@ __global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restric
         px = __fadd_rn(xf, c.t[2]);
         py = __fadd_rn(yf, c.t[5]);
     }
-    unsigned char rgb[3] = {255, 255, 255};
+    rgb[0] = rgb[1] = rgb[2] = 255;
     const float left = __fsub_rn(floorf(px), 1.0f), right = __fadd_rn(left, 4.0f);
     const float top = __fsub_rn(floorf(py), 1.0f), bottom = __fadd_rn(top, 4.0f);
     if (!(left < 0.0f || right >= (float)c.page_w || top < 0.0f || bottom >= (float)c.page_h) && isfinite(px) && isfinite(py)) {
@@ -188,7 +133,45 @@ __global__ void __launch_bounds__(256) crop_warp_kernel(const CropDev* __restric
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) rgb[ch] = clamp_u8_trunc(cubic(col[ch][0], col[ch][1], col[ch][2], col[ch][3], yw));
     }
-    dst[0] = rgb[0]; dst[1] = rgb[1]; dst[2] = rgb[2];
+}
+
+// One warp per row of the un-rotated warp of one crop (row_prefix over all crops, built on the host from the crop
+// dims).  Translation-class crops with an integral offset (axis-aligned boxes — the common case for text lines)
+// sample exact pixel centres: both cubic weights are 0 and cubic(p0,p1,p2,p3,0) == p1, so the row is a guarded byte
+// copy, fully coalesced on both sides (same white-border rule: any tap of the 4x4 window outside the page -> white).
+// Everything else (affine / projective / rotate270) takes the bicubic path, lanes striding the row.
+__global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restrict__ crops, const int* __restrict__ row_prefix, int n_crops,
+                                                         int total_rows, unsigned char* __restrict__ pix) {
+    const int lane = threadIdx.x & 31;
+    const int ru = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (ru >= total_rows) return;
+    const int k = rt_find_segment(row_prefix, n_crops, ru);
+    const CropDev& c = crops[k];
+    if (c.status != RETTO_B200_OK) return;
+    const int y = ru - row_prefix[k];
+    const int w = c.rot ? c.h : c.w, h = c.rot ? c.w : c.h;  // un-rotated warp size
+    if (c.cls == 0 && !c.rot && c.t[2] == floorf(c.t[2]) && c.t[5] == floorf(c.t[5]) && fabsf(c.t[2]) < 1e6f && fabsf(c.t[5]) < 1e6f) {
+        const int tx = (int)c.t[2], ty = (int)c.t[5];
+        const int iy = y + ty;
+        const bool row_ok = !(iy - 1 < 0 || iy + 3 >= c.page_h);
+        const int xlo = max(0, 1 - tx), xhi = min(w - 1, c.page_w - 4 - tx);   // columns whose 4x4 window is inside the page
+        uchar4* dst = reinterpret_cast<uchar4*>(pix + c.offset) + (size_t)y * w;
+        const unsigned char* src = c.page + ((size_t)iy * c.page_w + tx) * 3;
+        for (int x = lane; x < w; x += 32) {
+            uchar4 o = make_uchar4(255, 255, 255, 255);
+            if (row_ok && x >= xlo && x <= xhi) { const unsigned char* sp = src + 3 * x; o.x = __ldg(sp); o.y = __ldg(sp + 1); o.z = __ldg(sp + 2); }
+            dst[x] = o;
+        }
+        return;
+    }
+    for (int x = lane; x < w; x += 32) {
+        unsigned char rgb[3];
+        crop_pixel(c, x, y, rgb);
+        size_t o;
+        if (c.rot) o = (size_t)(w - 1 - x) * h + y;  // rotate270: out(y, w-1-x) = in(x, y), out is h wide
+        else o = (size_t)y * w + x;
+        reinterpret_cast<uchar4*>(pix + c.offset)[o] = make_uchar4(rgb[0], rgb[1], rgb[2], 255);
+    }
 }
 
 // host: crop dims (same IEEE operations as the setup kernel; size planning only)
@@ -209,9 +192,8 @@ void rt_crop_dims(const float box[8], int* cw, int* ch, int* rot) {
     *ch = r ? (int)w : (int)h;
 }
 
-extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int32_t n,
-                                                   retto_b200_crop_info* h_infos) {
-    if (!ctx || n < 0 || (n > 0 && (!h_jobs || !h_infos))) return RETTO_B200_ERR_INVALID_ARG;
+// async part: descriptors up, projection setup + row kernel enqueued, descriptor read-back enqueued (no sync)
+retto_b200_status rt_crop_launch(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int n, retto_b200_crop_info* h_infos) {
     ctx->crops.clear();
     if (n == 0) return RETTO_B200_OK;
     std::vector<int> prefix(n + 1, 0);
@@ -226,9 +208,11 @@ extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const re
         rt_crop_dims(c.box, &c.w, &c.h, &c.rot);
         c.offset = off;
         const long long px = (long long)c.w * c.h;
-        if (px <= 0 || prefix[i] + px > 0x7fffffffLL) { c.status = RETTO_B200_ERR_DEGENERATE_QUAD; c.w = c.h = 0; prefix[i + 1] = prefix[i]; }
-        else { prefix[i + 1] = prefix[i] + (int)px; off += ((unsigned long long)px * 3 + 15) & ~15ULL; }
+        const int rows = c.rot ? c.w : c.h;
+        if (px <= 0 || px > 0x3fffffffLL || prefix[i] + (long long)rows > 0x7fffffffLL) { c.status = RETTO_B200_ERR_DEGENERATE_QUAD; c.w = c.h = 0; prefix[i + 1] = prefix[i]; }
+        else { prefix[i + 1] = prefix[i] + rows; off += ((unsigned long long)px * 4 + 15) & ~15ULL; }   // crops are stored RGBX (4 B/px): one aligned word per pixel
         ctx->crops.push_back(c);
+        h_infos[i].w = c.w; h_infos[i].h = c.h; h_infos[i].rotated270 = c.rot; h_infos[i].status = c.status; h_infos[i].offset = c.offset;
     }
     cudaStream_t st = ctx->stream;
     RT_CUDA_OK(ctx, ctx->d_crop_pix.ensure((size_t)std::max<unsigned long long>(off, 16), st));
@@ -245,55 +229,44 @@ extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const re
     RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
     crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n);
     RT_LAUNCH_CHECK(ctx);
-    // projection class / degeneracy are only known on the device: fetch the descriptors, then split the crops into the
-    // row-copy fast path and the general bicubic path
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->crops.data(), d_crops, sizeof(CropDev) * n, cudaMemcpyDeviceToHost, st));
-    RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    std::vector<int> fast, gen, fast_pre{0}, gen_pre{0};
-    for (int i = 0; i < n; ++i) {
-        const CropDev& c = ctx->crops[i];
-        if (c.status != RETTO_B200_OK || c.w <= 0 || c.h <= 0) continue;
-        if (c.cls == 0 && !c.rot && c.t[2] == floorf(c.t[2]) && c.t[5] == floorf(c.t[5]) && fabsf(c.t[2]) < 1e6f && fabsf(c.t[5]) < 1e6f) {
-            fast.push_back(i); fast_pre.push_back(fast_pre.back() + c.h);
-        } else {
-            gen.push_back(i); gen_pre.push_back(gen_pre.back() + c.w * c.h);
-        }
-    }
-    (void)d_prefix;
-    if (!fast.empty()) {
-        std::vector<int> blob(fast);
-        blob.insert(blob.end(), fast_pre.begin(), fast_pre.end());
-        RT_TRY(rt_upload(ctx, ctx->d_stage, blob.data(), blob.size() * sizeof(int)));
-        const int rows = fast_pre.back();
-        RT_LAUNCH_BEGIN(ctx, "crop_copy_rows_kernel");
-        crop_copy_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_crops, ctx->d_stage.as<int>(), ctx->d_stage.as<int>() + fast.size(), (int)fast.size(), rows,
-                                                              ctx->d_crop_pix.as<unsigned char>());
+    const int rows = prefix[n];
+    if (rows > 0) {
+        RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
+        crop_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>());
         RT_LAUNCH_CHECK(ctx);
     }
-    if (!gen.empty()) {
-        std::vector<int> blob(gen);
-        blob.insert(blob.end(), gen_pre.begin(), gen_pre.end());
-        RT_TRY(rt_upload(ctx, ctx->d_stage2, blob.data(), blob.size() * sizeof(int)));
-        const int total = gen_pre.back();
-        RT_LAUNCH_BEGIN(ctx, "crop_warp_kernel");
-        crop_warp_kernel<<<(total + 255) / 256, 256, 0, st>>>(d_crops, ctx->d_stage2.as<int>(), ctx->d_stage2.as<int>() + gen.size(), (int)gen.size(), total,
-                                                              ctx->d_crop_pix.as<unsigned char>());
-        RT_LAUNCH_CHECK(ctx);
-    }
+    // projection degeneracy is only known on the device: statuses (strided gather of one int per crop) come back async
+    RT_CUDA_OK(ctx, ctx->h_crops.ensure(sizeof(int) * (size_t)n));
+    RT_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_crops.p, sizeof(int), &d_crops[0].status, sizeof(CropDev), sizeof(int), n, cudaMemcpyDeviceToHost, st));
+    return RETTO_B200_OK;
+}
+// sync + statuses
+retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos) {
+    const int n = (int)ctx->crops.size();
+    if (n == 0) return RETTO_B200_OK;
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    const int* hs = ctx->h_crops.as<int>();
     retto_b200_status ret = RETTO_B200_OK;
     for (int i = 0; i < n; ++i) {
-        const CropDev& c = ctx->crops[i];
-        h_infos[i].w = c.w; h_infos[i].h = c.h; h_infos[i].rotated270 = c.rot; h_infos[i].status = c.status; h_infos[i].offset = c.offset;
-        if (c.status != RETTO_B200_OK) { ctx->set_error("crop_boxes: degenerate quad " + std::to_string(i) + " (reference: from_control_points().unwrap() panics)"); ret = RETTO_B200_ERR_DEGENERATE_QUAD; }
+        ctx->crops[i].status = hs[i];
+        h_infos[i].status = hs[i];
+        if (hs[i] != RETTO_B200_OK) { ctx->set_error("crop_boxes: degenerate quad " + std::to_string(i) + " (reference: from_control_points().unwrap() panics)"); ret = RETTO_B200_ERR_DEGENERATE_QUAD; }
     }
     return ret;
+}
+
+extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int32_t n,
+                                                   retto_b200_crop_info* h_infos) {
+    if (!ctx || n < 0 || (n > 0 && (!h_jobs || !h_infos))) return RETTO_B200_ERR_INVALID_ARG;
+    RT_TRY(rt_crop_launch(ctx, h_jobs, n, h_infos));
+    return rt_crop_finish(ctx, h_infos);
 }
 
 __global__ void crop_flip_copy_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int n_px, int flip) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_px) return;
     const int s = flip ? n_px - 1 - i : i;
-    dst[3 * i] = src[3 * s]; dst[3 * i + 1] = src[3 * s + 1]; dst[3 * i + 2] = src[3 * s + 2];
+    dst[3 * i] = src[4 * s]; dst[3 * i + 1] = src[4 * s + 1]; dst[3 * i + 2] = src[4 * s + 2];   // RGBX -> RGB
 }
 
 extern "C" retto_b200_status retto_b200_crop_fetch(retto_b200_ctx* ctx, int32_t i, uint8_t* h_out) {

@@ -268,16 +268,23 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
         const float* row = pred + (size_t)(y + y_min) * w + x_min;
         for (int s = 0; s < rc.n; ++s) {
             count += (unsigned long long)(rc.b[s] - rc.a[s] + 1);
-            // 128 pixels per step: four independent coalesced loads in flight, then the reference's sequential add
-            // chain replayed by every lane through shuffles (bit-identical to the scalar fold)
-            for (int x = rc.a[s]; x <= rc.b[s]; x += 128) {
-                float v[4];
+            // 128 pixels per step, double buffered: the four coalesced loads of step i+1 are in flight while the
+            // reference's sequential add chain of step i is replayed by every lane through shuffles
+            // (bit-identical to the scalar fold)
+            const int xb = rc.b[s];
+            float v[4], nv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int xi = rc.a[s] + 32 * q + lane;
+                v[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;
+            }
+            for (int x = rc.a[s]; x <= xb; x += 128) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int xi = x + 32 * q + lane;
-                    v[q] = (xi <= rc.b[s]) ? __ldg(row + xi) : 0.0f;
+                    const int xi = x + 128 + 32 * q + lane;
+                    nv[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;
                 }
-                const int n = min(128, rc.b[s] - x + 1);
+                const int n = min(128, xb - x + 1);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int lim = n - 32 * q;
@@ -291,6 +298,8 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
                         for (int k = 0; k < lim; ++k) acc = __fadd_rn(acc, __shfl_sync(RT_FULL, v[q], k));
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = nv[q];
             }
         }
     }

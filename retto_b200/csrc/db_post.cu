@@ -384,7 +384,7 @@ struct GeomParams {
     int min_mini_box_size;
 };
 
-__global__ void __launch_bounds__(128) box_geometry_kernel(const DetPostPage* __restrict__ pages,
+__global__ void __launch_bounds__(128, 4) box_geometry_kernel(const DetPostPage* __restrict__ pages,
                                                             int n_pages, PageCounters* __restrict__ counters, const CompRec* __restrict__ comps,
                                                             const int2* __restrict__ rowtab, int2* __restrict__ hullbuf, BoxCand* __restrict__ cand,
                                                             int max_comps, GeomParams gp, const int* __restrict__ hole_pages) {

@@ -10,37 +10,65 @@
 #include "common.cuh"
 #include "thumbnail.cuh"
 
-struct FlipReader {
-    const unsigned char* __restrict__ src;
+struct FlipReader {   // crops are stored RGBX, one aligned word per pixel
+    const uchar4* __restrict__ src;
     unsigned w, h;
     int flip;
     __device__ __forceinline__ uchar3 operator()(unsigned x, unsigned y) const {
         if (flip) { x = w - 1 - x; y = h - 1 - y; }
-        const unsigned char* p = src + ((size_t)y * w + x) * 3;
-        return make_uchar3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+        const uchar4 p = __ldg(src + (size_t)y * w + x);
+        return make_uchar3(p.x, p.y, p.z);
     }
 };
 
 // One block = one (line, 128-column chunk); one thread = one output column over all img_h rows.
-// The x-axis window is computed once per thread, the y-axis windows once per block (shared memory), the
-// normalisation `(px as f32 / 255 - .5) / .5` (image_helper.rs:200-203) comes from a 256-entry table built
-// with the same three correctly-rounded operations (bit-identical, no per-pixel divisions).
+// Everything that depends only on x is computed once per thread, everything that depends only on y once per block
+// (shared memory); the normalisation `(px as f32 / 255 - .5) / .5` (image_helper.rs:200-203) comes from a 256-entry
+// table built with the same three correctly-rounded operations.  Text crops are 20-60 px tall, so both thumbnail
+// windows are at most 2 px wide almost always: that case runs a branch-light path on the 2x2 source pixels
+// (i0|i1) x (j0|j1) that evaluates exactly the expression of the matching imageops::thumbnail branch; larger
+// windows fall back to the generic thumbnail_pixel.
 #define BB_COLS 128
 #define BB_MAX_H 64
 struct ChunkDev { int line, x0; };
+struct AxisS {
+    int i0, i1;      // the two source indices the window touches (i1 == i0 for a 1-px block)
+    int n;           // block length (0 => fractional case between i0 and i1)
+    float fract;
+};
+__device__ __forceinline__ AxisS axis_small(const ThumbAxis a, unsigned size) {
+    AxisS r;
+    if (a.lo != a.hi) { r.n = (int)(a.hi - a.lo); r.i0 = (int)a.lo; r.i1 = (int)a.hi - 1; r.fract = 0.0f; }
+    else { r.n = 0; r.i0 = (int)a.hi - 1; r.i1 = (int)((a.hi > size - 1) ? size - 1 : a.hi); r.fract = a.fract; }
+    return r;
+}
+struct RowS { int o0, o1; int n; float fract, omf, ft1, fb1, ft2, fb2; };   // per output row (pixel offsets of rows j0/j1)
+
 __global__ void __launch_bounds__(BB_COLS) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
                                                                  const CropDev* __restrict__ crops, const unsigned char* __restrict__ crop_pix,
                                                                  const int* __restrict__ flip_flags, int use_flip, int img_h,
                                                                  float* __restrict__ out) {
     __shared__ float s_lut[256];
     __shared__ ThumbAxis s_ay[BB_MAX_H];
+    __shared__ RowS s_row[BB_MAX_H];
     const ChunkDev ck = chunks[blockIdx.x];
     const LineDev ln = lines[ck.line];
     const CropDev& c = crops[ln.crop];
     const unsigned cw = (unsigned)c.w, chh = (unsigned)c.h;
+    const int flip = use_flip ? flip_flags[ln.crop] : 0;
     for (int v = threadIdx.x; v < 256; v += BB_COLS) s_lut[v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), 0.5f), 0.5f);
     const float yr = __fdiv_rn((float)chh, (float)img_h);
-    for (int y = threadIdx.x; y < img_h; y += BB_COLS) s_ay[y] = thumb_axis(y, yr, chh);
+    for (int y = threadIdx.x; y < img_h; y += BB_COLS) {
+        const ThumbAxis ay = thumb_axis(y, yr, chh);
+        s_ay[y] = ay;
+        const AxisS a = axis_small(ay, chh);
+        RowS r;
+        const int j0 = flip ? (int)chh - 1 - a.i0 : a.i0, j1 = flip ? (int)chh - 1 - a.i1 : a.i1;
+        r.o0 = j0 * (int)cw; r.o1 = j1 * (int)cw; r.n = a.n; r.fract = a.fract; r.omf = __fsub_rn(1.0f, a.fract);
+        r.ft1 = a.fract; r.fb1 = r.omf;                                   // fract / 1, (1 - fract) / 1
+        r.ft2 = __fdiv_rn(a.fract, 2.0f); r.fb2 = __fdiv_rn(r.omf, 2.0f);
+        s_row[y] = r;
+    }
     __syncthreads();
     const int x = ck.x0 + threadIdx.x;
     if (x >= ln.img_w) return;
@@ -53,12 +81,48 @@ __global__ void __launch_bounds__(BB_COLS) build_batches_kernel(const LineDev* _
         }
         return;
     }
-    const FlipReader rd{crop_pix + c.offset, cw, chh, use_flip ? flip_flags[ln.crop] : 0};
+    const uchar4* __restrict__ src = reinterpret_cast<const uchar4*>(crop_pix + c.offset);
+    const FlipReader rd{src, cw, chh, flip};
     const float xr = __fdiv_rn((float)cw, (float)ln.resized_w);
     const ThumbAxis ax = thumb_axis(x, xr, cw);
+    const AxisS xs = axis_small(ax, cw);
+    const int c0 = flip ? (int)cw - 1 - xs.i0 : xs.i0, c1 = flip ? (int)cw - 1 - xs.i1 : xs.i1;
+    const float fh = xs.fract, omfh = __fsub_rn(1.0f, fh);
+    const float fr1 = fh, fl1 = omfh, fr2 = __fdiv_rn(fh, 2.0f), fl2 = __fdiv_rn(omfh, 2.0f);
     for (int y = 0; y < img_h; ++y) {
+        const RowS r = s_row[y];
         unsigned char px[3];
-        thumbnail_pixel(rd, cw, chh, ax, s_ay[y], px);
+        if (xs.n > 2 || r.n > 2) {
+            thumbnail_pixel(rd, cw, chh, ax, s_ay[y], px);
+        } else {
+            const uchar4 p00 = __ldg(src + r.o0 + c0), p10 = __ldg(src + r.o0 + c1);
+            const uchar4 p01 = __ldg(src + r.o1 + c0), p11 = __ldg(src + r.o1 + c1);
+            if (xs.n > 0 && r.n > 0) {          // block mean over (1|2) x (1|2) pixels: (sum + n/2) / n
+                const unsigned n = (unsigned)(xs.n * r.n), h2 = n >> 1;
+                const unsigned w10 = xs.n > 1, w01 = r.n > 1, w11 = w10 & w01;
+                px[0] = (unsigned char)((p00.x + w10 * p10.x + w01 * p01.x + w11 * p11.x + h2) / n);
+                px[1] = (unsigned char)((p00.y + w10 * p10.y + w01 * p01.y + w11 * p11.y + h2) / n);
+                px[2] = (unsigned char)((p00.z + w10 * p10.z + w01 * p01.z + w11 * p11.z + h2) / n);
+            } else if (xs.n == 0 && r.n > 0) {  // horizontal fraction between columns i0,i1 summed over r.n rows
+                const float fl = r.n > 1 ? fl2 : fl1, fr = r.n > 1 ? fr2 : fr1;
+                const unsigned w01 = r.n > 1;
+#define RT_HF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fl, (float)(p00.ch + w01 * p01.ch)), __fmul_rn(fr, (float)(p10.ch + w01 * p11.ch))))
+                px[0] = RT_HF(x); px[1] = RT_HF(y); px[2] = RT_HF(z);
+#undef RT_HF
+            } else if (xs.n > 0 && r.n == 0) {  // vertical fraction between rows j0,j1 summed over xs.n columns
+                const float fb = xs.n > 1 ? r.fb2 : r.fb1, ft = xs.n > 1 ? r.ft2 : r.ft1;
+                const unsigned w10 = xs.n > 1;
+#define RT_VF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fb, (float)(p00.ch + w10 * p10.ch)), __fmul_rn(ft, (float)(p01.ch + w10 * p11.ch))))
+                px[0] = RT_VF(x); px[1] = RT_VF(y); px[2] = RT_VF(z);
+#undef RT_VF
+            } else {                             // both fractional: bilinear on the 2x2
+                const float fv = r.fract;
+                const float f_tr = __fmul_rn(fv, fh), f_tl = __fmul_rn(fv, omfh), f_br = __fmul_rn(r.omf, fh), f_bl = __fmul_rn(r.omf, omfh);
+#define RT_BL(ch) f32_to_u8_numcast(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, (float)p10.ch), __fmul_rn(f_tr, (float)p11.ch)), __fmul_rn(f_bl, (float)p00.ch)), __fmul_rn(f_tl, (float)p01.ch)))
+                px[0] = RT_BL(x); px[1] = RT_BL(y); px[2] = RT_BL(z);
+#undef RT_BL
+            }
+        }
         float* d = dst + (size_t)y * ln.img_w;
         d[0] = s_lut[px[0]];
         d[plane] = s_lut[px[1]];
@@ -89,6 +153,8 @@ __global__ void cls_post_kernel(const ClsLine* __restrict__ lines, int n, int nc
     // cls_processor.rs:164-166
     if (label == 180 && bv >= thresh) flip_flags[lines[i].crop] ^= 1;
 }
+
+retto_b200_status rt_cls_collect(retto_b200_ctx* ctx, int n, retto_b200_cls_result* h_results);
 
 // ---- host ------------------------------------------------------------------------------------------------
 extern "C" retto_b200_status retto_b200_plan_batches(const retto_b200_config* cfg, int32_t kind, const retto_b200_crop_info* crops,
@@ -174,8 +240,9 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
     return RETTO_B200_OK;
 }
 
+// enqueue K9 + the result read-back; with defer == true the caller collects after its next stream sync
 retto_b200_status rt_cls_postprocess_ptrs(retto_b200_ctx* ctx, const std::vector<const float*>& logits, const int32_t* crop_index, int n,
-                                          retto_b200_cls_result* h_results) {
+                                          retto_b200_cls_result* h_results, bool defer) {
     if (n == 0) return RETTO_B200_OK;
     std::vector<ClsLine> lines(n);
     for (int i = 0; i < n; ++i) {
@@ -194,7 +261,13 @@ retto_b200_status rt_cls_postprocess_ptrs(retto_b200_ctx* ctx, const std::vector
     RT_LAUNCH_CHECK(ctx);
     RT_CUDA_OK(ctx, ctx->h_cls.ensure(sizeof(int) * (2 * (size_t)n + 1)));
     RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_cls.p, d_label, sizeof(int) * (2 * (size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (defer) return RETTO_B200_OK;
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rt_cls_collect(ctx, n, h_results);
+}
+// after a stream sync: results of the last rt_cls_postprocess_ptrs
+retto_b200_status rt_cls_collect(retto_b200_ctx* ctx, int n, retto_b200_cls_result* h_results) {
+    if (n == 0) return RETTO_B200_OK;
     const int* hl = ctx->h_cls.as<int>();
     const float* hs = reinterpret_cast<const float*>(hl + n);
     for (int i = 0; i < n; ++i) { h_results[i].label = hl[i]; h_results[i].score = hs[i]; }
@@ -207,5 +280,5 @@ extern "C" retto_b200_status retto_b200_cls_postprocess(retto_b200_ctx* ctx, con
     if (!ctx || n < 0 || (n > 0 && (!d_logits || !h_crop_index || !h_results))) return RETTO_B200_ERR_INVALID_ARG;
     std::vector<const float*> ptrs(n);
     for (int i = 0; i < n; ++i) ptrs[i] = d_logits + 2 * (size_t)i;
-    return rt_cls_postprocess_ptrs(ctx, ptrs, h_crop_index, n, h_results);
+    return rt_cls_postprocess_ptrs(ctx, ptrs, h_crop_index, n, h_results, false);
 }

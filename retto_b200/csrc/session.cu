@@ -8,9 +8,30 @@
 
 retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h_boxes, const double* h_params4, int n);
 retto_b200_status rt_cls_postprocess_ptrs(retto_b200_ctx* ctx, const std::vector<const float*>& logits, const int32_t* crop_index, int n,
-                                          retto_b200_cls_result* h_results);
+                                          retto_b200_cls_result* h_results, bool defer);
+retto_b200_status rt_cls_collect(retto_b200_ctx* ctx, int n, retto_b200_cls_result* h_results);
+retto_b200_status rt_crop_launch(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int n, retto_b200_crop_info* h_infos);
+retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos);
 
+#include <chrono>
 namespace {
+struct HostTrace {   // RETTO_B200_HOST_TRACE=1: wall-clock per stage of run_pages on stderr (host + waits)
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    std::string line;
+    HostTrace() : on(getenv("RETTO_B200_HOST_TRACE") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+    void mark(const char* name) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s=%.3f", name, std::chrono::duration<double, std::milli>(now - last).count());
+        line += buf;
+        last = now;
+    }
+    ~HostTrace() {
+        if (on) fprintf(stderr, "[run_pages ms]%s total=%.3f\n", line.c_str(), std::chrono::duration<double, std::milli>(last - t0).count());
+    }
+};
 struct PageState {
     int ori_h, ori_w;     // decoded image
     int h, w;             // after resize_both
@@ -25,6 +46,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
                                                   retto_b200_forward_fn forward, void* user, retto_b200_results* out) {
     if (!ctx || n_pages < 0 || (n_pages > 0 && !h_pages) || !forward || !out) return RETTO_B200_ERR_INVALID_ARG;
     cudaStream_t st = ctx->stream;
+    HostTrace tr;
     const retto_b200_config& cfg = ctx->cfg;
     ctx->r_pages.assign(n_pages, retto_b200_page_result{0, 0, 0});
     ctx->r_boxes.clear(); ctx->r_cls.clear(); ctx->r_text_offs.assign(1, 0); ctx->r_text.clear(); ctx->r_scores.clear();
@@ -89,6 +111,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
         if (!step2.empty()) RT_TRY(retto_b200_thumbnail(ctx, step2.data(), (int)step2.size()));
     }
 
+    tr.mark("upload+resize");
     // ---- 2. det preprocess (det_processor.rs:256-274) --------------------------------------------------------
     std::vector<retto_b200_tensor> det_in(n_pages), det_out(n_pages);
     {
@@ -105,8 +128,10 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
         }
         RT_TRY(retto_b200_det_preprocess(ctx, descs.data(), n_pages));
     }
+    tr.mark("det_pre");
     // ---- 3. worker.det (session.rs:86) ------------------------------------------------------------------------
     if (forward(user, 0, n_pages, det_in.data(), det_out.data(), (void*)st) != 0) { ctx->set_error("run_pages: det forward failed"); return RETTO_B200_ERR_WORKER; }
+    tr.mark("det_fwd");
     // ---- 4. det postprocess (det_processor.rs:279-335) ----------------------------------------------------------
     std::vector<int32_t> page_status(n_pages, 0), box_off(n_pages + 1, 0);
     {
@@ -129,6 +154,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
             break;
         }
     }
+    tr.mark("det_post");
     const int n_lines = box_off[n_pages];
     ctx->r_boxes.resize(n_lines);
     retto_b200_status ret = RETTO_B200_OK;
@@ -158,24 +184,8 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
                 jobs[k].d_page = ps[i].d_img; jobs[k].page_h = ps[i].h; jobs[k].page_w = ps[i].w;
                 jobs[k].box = ctx->r_boxes[k];
             }
-        RT_TRY(retto_b200_crop_boxes(ctx, jobs.data(), n_lines, infos.data()));
+        RT_TRY(rt_crop_launch(ctx, jobs.data(), n_lines, infos.data()));   // async: the host plans the batches meanwhile
     }
-    // ---- 6. boxes back to original-image coordinates (session.rs:94-97) ----------------------------------------------
-    {
-        bool any = false;
-        std::vector<double> prm((size_t)n_lines * 4);
-        for (int i = 0; i < n_pages; ++i) {
-            if (ps[i].h != ps[i].ori_h || ps[i].w != ps[i].ori_w) any = true;  // identity otherwise: round(x * 1) clamped == x
-            for (int k = box_off[i]; k < box_off[i + 1]; ++k) {
-                prm[4 * (size_t)k] = (double)ps[i].ori_w / (double)ps[i].w;
-                prm[4 * (size_t)k + 1] = (double)ps[i].ori_h / (double)ps[i].h;
-                prm[4 * (size_t)k + 2] = (double)ps[i].ori_w;
-                prm[4 * (size_t)k + 3] = (double)ps[i].ori_h;
-            }
-        }
-        if (any) RT_TRY(rt_scale_and_clip_multi(ctx, ctx->r_boxes.data(), prm.data(), n_lines));
-    }
-
     // ---- 7. cls (cls_processor.rs:127-172) ------------------------------------------------------------------------------
     auto plan_all = [&](int kind, std::vector<retto_b200_line_job>& lines, std::vector<retto_b200_batch>& batches, std::vector<int>& batch_page,
                         uint64_t* total) -> retto_b200_status {
@@ -196,13 +206,35 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
         *total = off;
         return RETTO_B200_OK;
     };
-    std::vector<retto_b200_line_job> lines;
-    std::vector<retto_b200_batch> batches;
-    std::vector<int> batch_page;
-    uint64_t total = 0;
+    std::vector<retto_b200_line_job> lines, rec_lines;
+    std::vector<retto_b200_batch> batches, rec_batches;
+    std::vector<int> batch_page, rec_batch_page;
+    uint64_t total = 0, rec_total = 0;
+    // both plans depend only on the crop dims (known on the host), so they overlap with the crop kernels
     RT_TRY(plan_all(0, lines, batches, batch_page, &total));
+    RT_TRY(plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total));
+    RT_TRY(rt_crop_finish(ctx, infos.data()));
+    tr.mark("crops+plans");
+    // ---- 6. boxes back to original-image coordinates (session.rs:94-97) ----------------------------------------------
+    {
+        bool any = false;
+        std::vector<double> prm((size_t)n_lines * 4);
+        for (int i = 0; i < n_pages; ++i) {
+            if (ps[i].h != ps[i].ori_h || ps[i].w != ps[i].ori_w) any = true;  // identity otherwise: round(x * 1) clamped == x
+            for (int k = box_off[i]; k < box_off[i + 1]; ++k) {
+                prm[4 * (size_t)k] = (double)ps[i].ori_w / (double)ps[i].w;
+                prm[4 * (size_t)k + 1] = (double)ps[i].ori_h / (double)ps[i].h;
+                prm[4 * (size_t)k + 2] = (double)ps[i].ori_w;
+                prm[4 * (size_t)k + 3] = (double)ps[i].ori_h;
+            }
+        }
+        if (any) RT_TRY(rt_scale_and_clip_multi(ctx, ctx->r_boxes.data(), prm.data(), n_lines));
+    }
+
+    tr.mark("scale");
     float* d_base = nullptr;
     RT_TRY(retto_b200_build_batches(ctx, 0, lines.data(), n_lines, total, &d_base));
+    std::vector<int32_t> cls_crop_idx;
     std::vector<retto_b200_tensor> tin(batches.size()), tout(batches.size());
     auto fill_inputs = [&](int img_h) {
         for (size_t b = 0; b < batches.size(); ++b) {
@@ -212,6 +244,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
             memset(&tout[b], 0, sizeof(retto_b200_tensor));
         }
     };
+    tr.mark("cls_build");
     fill_inputs(cfg.cls_image_shape[1]);
     if (forward(user, 1, (int)batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: cls forward failed"); return RETTO_B200_ERR_WORKER; }
     {
@@ -229,15 +262,17 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
                 crop_idx[batches[b].first_line + k] = lines[batches[b].first_line + k].crop;
             }
         }
-        RT_TRY(rt_cls_postprocess_ptrs(ctx, ptrs, crop_idx.data(), n_lines, res.data()));
-        for (int k = 0; k < n_lines; ++k) ctx->r_cls[crop_idx[k]] = res[k];  // final_res[idx].label = label (cls_processor.rs:167)
+        RT_TRY(rt_cls_postprocess_ptrs(ctx, ptrs, crop_idx.data(), n_lines, nullptr, true));   // results collected after the final sync
+        cls_crop_idx = crop_idx;
     }
 
+    tr.mark("cls_fwd+post");
     // ---- 8. rec (rec_processor.rs:214-270) ---------------------------------------------------------------------------------
-    RT_TRY(plan_all(1, lines, batches, batch_page, &total));
+    lines.swap(rec_lines); batches.swap(rec_batches); total = rec_total;
     RT_TRY(retto_b200_build_batches(ctx, 1, lines.data(), n_lines, total, &d_base));
     tin.assign(batches.size(), retto_b200_tensor{});
     tout.assign(batches.size(), retto_b200_tensor{});
+    tr.mark("rec_build");
     fill_inputs(cfg.rec_image_shape[1]);
     if (forward(user, 2, (int)batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: rec forward failed"); return RETTO_B200_ERR_WORKER; }
     {
@@ -258,6 +293,11 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
         retto_b200_status s = retto_b200_ctc_decode(ctx, descs.data(), (int)descs.size(), (int)ctx->dict.size(), toff.data(), text.data(), text.size(),
                                                     sc.data(), nullptr, nullptr, 0);
         if (s != RETTO_B200_OK) return s;
+        {   // the CTC call synchronised the stream: the deferred cls results are on the host now
+            std::vector<retto_b200_cls_result> res(n_lines);
+            RT_TRY(rt_cls_collect(ctx, n_lines, res.data()));
+            for (int k = 0; k < n_lines; ++k) ctx->r_cls[cls_crop_idx[k]] = res[k];  // final_res[idx].label = label (cls_processor.rs:167)
+        }
         // scatter from plan order back to detection order (rec_processor.rs:259-264)
         std::vector<uint32_t> len(n_lines, 0);
         for (int k = 0; k < n_lines; ++k) len[lines[k].crop] = toff[k + 1] - toff[k];
@@ -269,6 +309,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
             ctx->r_scores[dst] = sc[k];
         }
     }
+    tr.mark("rec_fwd+ctc");
     out->text = ctx->r_text.data();
     out->text_offsets = ctx->r_text_offs.data();
     return ret;
