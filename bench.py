@@ -242,19 +242,19 @@ def cpu_oracle_pages_per_s(pages, probs, n_sample, dict_text, threads, repeats=1
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(name, info):
+def algorithmic_bytes(name, info, launch_idx=0):
     """SURVEY.md §8(d) / DESIGN.md per-unit figures x the units one launch processes"""
-    P, HW = info["pages"], info["det_px"]
+    HW = info["det_px"]
     if name.startswith("ctc_argmax"):
         return 4.0 * info["rec_rows"] * C_CLASSES
     if name.startswith("det_pre_identity"):
         return 15.0 * HW                      # 3 B in + 12 B out per pixel
     if name.startswith("bitmap_runs"):
         return 9.0 * HW                       # prob read 4 + bitmap write 1 + label write 4
-    if name.startswith("crop_warp"):
-        return 6.0 * info["crop_px"]
-    if name.startswith("build_batches"):
-        return None                           # two launches (cls, rec) with different sizes: reported as time only
+    if name.startswith("crop_rows"):
+        return 6.0 * info["crop_px"]          # 3 B read + 3 B written per crop pixel
+    if name.startswith("build_batches"):      # two launches per step (cls + rec): sum of both, per launch = half the time
+        return (2 * 3.0 * info["crop_px"] + 4.0 * (info["cls_floats"] + info["rec_floats"])) / 2.0
     return None
 
 
@@ -390,7 +390,10 @@ def main():
     value = total_pages / (ms_dev / 1000.0)
     e2e_value = total_pages / (ms_e2e / 1000.0)
     peak, peak_src = peaks()
-    info = {"pages": P, "det_px": float(P) * S * S, "rec_rows": worker.rec_rows, "crop_px": float(crop_px)}
+    st8 = (C.c_uint64 * 8)()
+    ctx._check(L.retto_b200_last_run_stats(H, st8))
+    info = {"pages": P, "det_px": float(st8[2]), "crop_px": float(st8[3]), "cls_floats": float(st8[4]), "rec_floats": float(st8[5]), "rec_rows": float(st8[6])}
+    crop_px = info["crop_px"]
     kernels = {}
     for name, (cnt, ms) in ktimes.items():
         if cnt == 0:
@@ -411,7 +414,8 @@ def main():
     # the DB-postprocess unit (K2..K6) as SURVEY §8(d) defines it: 9*H*W bytes over the sum of its kernels
     db_names = ["zero_counters", "bitmap_runs", "ccl_merge", "ccl_flatten", "comp_sort", "run_end", "row_alloc", "box_geometry", "page_sort", "pack_"]
     db_ms = sum(v["ms_per_step"] for k, v in kernels.items() if any(k.startswith(n) for n in db_names))
-    path_bytes = 15.0 * info["det_px"] + 9.0 * info["det_px"] + 6.0 * crop_px + 4.0 * worker.rec_rows * C_CLASSES
+    path_bytes = (15.0 * info["det_px"] + 9.0 * info["det_px"] + 6.0 * crop_px + 2 * 3.0 * crop_px + 4.0 * (info["cls_floats"] + info["rec_floats"])
+                  + 4.0 * info["rec_rows"] * C_CLASSES)
     summary = {"db_postprocess_unit": {"ms_per_step": db_ms, "algorithmic_bytes": 9.0 * info["det_px"],
                                        "gbs": 9.0 * info["det_px"] / (db_ms * 1e-3) / 1e9 if db_ms else None},
                "whole_path": {"algorithmic_bytes_per_step": path_bytes, "gbs_at_value": path_bytes * (value / world / P) / 1e9,

@@ -295,6 +295,10 @@ typedef struct retto_b200_results {
 retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
                                        retto_b200_forward_fn forward, void* user, retto_b200_results* out);
 
+/* sizes of the last retto_b200_run_pages call: out8 = {pages, lines, det tensor pixels, crop pixels, cls batch floats,
+ * rec batch floats, rec logit rows (sum n*img_w/8), 0} — used by bench.py for algorithmic byte counts */
+retto_b200_status retto_b200_last_run_stats(const retto_b200_ctx* ctx, uint64_t* out8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -201,6 +201,8 @@ struct retto_b200_ctx {
     DevBuf d_cls_idx, d_cls_out;
     HostBuf h_cls;
 
+    // sizes of the last run_pages call (bench.py algorithmic bytes): pages, lines, det px, crop px, cls floats, rec floats, rec rows
+    uint64_t run_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // session scratch
     DevBuf d_pages_raw, d_pages_rs, d_det_in;
     std::vector<retto_b200_page_result> r_pages;

@@ -44,7 +44,7 @@ __device__ __forceinline__ AxisS axis_small(const ThumbAxis a, unsigned size) {
 }
 struct RowS { int o0, o1; int n; float fract, omf, ft1, fb1, ft2, fb2; };   // per output row (pixel offsets of rows j0/j1)
 
-__global__ void __launch_bounds__(BB_COLS) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
+__global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
                                                                  const CropDev* __restrict__ crops, const unsigned char* __restrict__ crop_pix,
                                                                  const int* __restrict__ flip_flags, int use_flip, int img_h,
                                                                  float* __restrict__ out) {
@@ -89,44 +89,59 @@ __global__ void __launch_bounds__(BB_COLS) build_batches_kernel(const LineDev* _
     const int c0 = flip ? (int)cw - 1 - xs.i0 : xs.i0, c1 = flip ? (int)cw - 1 - xs.i1 : xs.i1;
     const float fh = xs.fract, omfh = __fsub_rn(1.0f, fh);
     const float fr1 = fh, fl1 = omfh, fr2 = __fdiv_rn(fh, 2.0f), fl2 = __fdiv_rn(omfh, 2.0f);
-    for (int y = 0; y < img_h; ++y) {
-        const RowS r = s_row[y];
+    const float fhu = xs.n ? 0.0f : fh, omfhu = xs.n ? 1.0f : omfh;   // (1, 0) weights for a 1-px block column
+    // software pipeline: the four source pixels of row y+1 are in flight while row y is mixed and stored
+    float* d = dst;
+    const int stride = ln.img_w;
+    RowS r = s_row[0];
+    uchar4 p00 = __ldg(src + r.o0 + c0), p10 = __ldg(src + r.o0 + c1), p01 = __ldg(src + r.o1 + c0), p11 = __ldg(src + r.o1 + c1);
+    for (int y = 0; y < img_h; ++y, d += stride) {
+        const RowS rn = s_row[(y + 1 < img_h) ? y + 1 : y];
+        const uchar4 n00 = __ldg(src + rn.o0 + c0), n10 = __ldg(src + rn.o0 + c1), n01 = __ldg(src + rn.o1 + c0), n11 = __ldg(src + rn.o1 + c1);
         unsigned char px[3];
-        if (xs.n > 2 || r.n > 2) {
-            thumbnail_pixel(rd, cw, chh, ax, s_ay[y], px);
-        } else {
-            const uchar4 p00 = __ldg(src + r.o0 + c0), p10 = __ldg(src + r.o0 + c1);
-            const uchar4 p01 = __ldg(src + r.o1 + c0), p11 = __ldg(src + r.o1 + c1);
-            if (xs.n > 0 && r.n > 0) {          // block mean over (1|2) x (1|2) pixels: (sum + n/2) / n
-                const unsigned n = (unsigned)(xs.n * r.n), h2 = n >> 1;
-                const unsigned w10 = xs.n > 1, w01 = r.n > 1, w11 = w10 & w01;
-                px[0] = (unsigned char)((p00.x + w10 * p10.x + w01 * p01.x + w11 * p11.x + h2) / n);
-                px[1] = (unsigned char)((p00.y + w10 * p10.y + w01 * p01.y + w11 * p11.y + h2) / n);
-                px[2] = (unsigned char)((p00.z + w10 * p10.z + w01 * p01.z + w11 * p11.z + h2) / n);
-            } else if (xs.n == 0 && r.n > 0) {  // horizontal fraction between columns i0,i1 summed over r.n rows
-                const float fl = r.n > 1 ? fl2 : fl1, fr = r.n > 1 ? fr2 : fr1;
-                const unsigned w01 = r.n > 1;
-#define RT_HF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fl, (float)(p00.ch + w01 * p01.ch)), __fmul_rn(fr, (float)(p10.ch + w01 * p11.ch))))
-                px[0] = RT_HF(x); px[1] = RT_HF(y); px[2] = RT_HF(z);
-#undef RT_HF
-            } else if (xs.n > 0 && r.n == 0) {  // vertical fraction between rows j0,j1 summed over xs.n columns
-                const float fb = xs.n > 1 ? r.fb2 : r.fb1, ft = xs.n > 1 ? r.ft2 : r.ft1;
-                const unsigned w10 = xs.n > 1;
-#define RT_VF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fb, (float)(p00.ch + w10 * p10.ch)), __fmul_rn(ft, (float)(p01.ch + w10 * p11.ch))))
-                px[0] = RT_VF(x); px[1] = RT_VF(y); px[2] = RT_VF(z);
-#undef RT_VF
-            } else {                             // both fractional: bilinear on the 2x2
-                const float fv = r.fract;
-                const float f_tr = __fmul_rn(fv, fh), f_tl = __fmul_rn(fv, omfh), f_br = __fmul_rn(r.omf, fh), f_bl = __fmul_rn(r.omf, omfh);
-#define RT_BL(ch) f32_to_u8_numcast(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, (float)p10.ch), __fmul_rn(f_tr, (float)p11.ch)), __fmul_rn(f_bl, (float)p00.ch)), __fmul_rn(f_tl, (float)p01.ch)))
-                px[0] = RT_BL(x); px[1] = RT_BL(y); px[2] = RT_BL(z);
+        if (xs.n <= 1 && r.n <= 1) {
+            // Up-scaling regime (the common one: crops are shorter than 48 px): every window is a single pixel or a
+            // fractional pair, and all four imageops::thumbnail branches collapse into the bilinear expression when a
+            // 1-px block axis is given the weights (1, 0):  x*1 = x, x*0 = 0, 0 + a = a are exact, so
+            //   block/block -> p00;  h-fraction -> fl*p00 + fr*p10;  v-fraction -> fb*p00 + ft*p01   bit for bit.
+            // One divergence-free path for the whole warp.
+            const float fv = r.n ? 0.0f : r.fract, omv = r.n ? 1.0f : r.omf;
+            const float f_tr = __fmul_rn(fv, fhu), f_tl = __fmul_rn(fv, omfhu), f_br = __fmul_rn(omv, fhu), f_bl = __fmul_rn(omv, omfhu);
+#define RT_BL(ch) (unsigned char)__float2uint_rz(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, (float)p10.ch), __fmul_rn(f_tr, (float)p11.ch)), __fmul_rn(f_bl, (float)p00.ch)), __fmul_rn(f_tl, (float)p01.ch)))
+            px[0] = RT_BL(x); px[1] = RT_BL(y); px[2] = RT_BL(z);
 #undef RT_BL
-            }
+        } else if (xs.n > 2 || r.n > 2) {
+            thumbnail_pixel(rd, cw, chh, ax, s_ay[y], px);
+        } else if (xs.n > 0 && r.n > 0) {          // block mean over (1|2) x (1|2) pixels: (sum + n/2) / n
+            const unsigned n = (unsigned)(xs.n * r.n), h2 = n >> 1;
+            const unsigned w10 = xs.n > 1, w01 = r.n > 1, w11 = w10 & w01;
+            const unsigned sh = (n == 4) ? 2 : (n == 2) ? 1 : 0;   // n is 1, 2 or 4 here: the division is a shift
+            px[0] = (unsigned char)((p00.x + w10 * p10.x + w01 * p01.x + w11 * p11.x + h2) >> sh);
+            px[1] = (unsigned char)((p00.y + w10 * p10.y + w01 * p01.y + w11 * p11.y + h2) >> sh);
+            px[2] = (unsigned char)((p00.z + w10 * p10.z + w01 * p01.z + w11 * p11.z + h2) >> sh);
+        } else if (xs.n == 0 && r.n > 0) {  // horizontal fraction between columns i0,i1 summed over r.n rows
+            const float fl = r.n > 1 ? fl2 : fl1, fr = r.n > 1 ? fr2 : fr1;
+            const unsigned w01 = r.n > 1;
+#define RT_HF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fl, (float)(p00.ch + w01 * p01.ch)), __fmul_rn(fr, (float)(p10.ch + w01 * p11.ch))))
+            px[0] = RT_HF(x); px[1] = RT_HF(y); px[2] = RT_HF(z);
+#undef RT_HF
+        } else if (xs.n > 0 && r.n == 0) {  // vertical fraction between rows j0,j1 summed over xs.n columns
+            const float fb = xs.n > 1 ? r.fb2 : r.fb1, ft = xs.n > 1 ? r.ft2 : r.ft1;
+            const unsigned w10 = xs.n > 1;
+#define RT_VF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fb, (float)(p00.ch + w10 * p10.ch)), __fmul_rn(ft, (float)(p01.ch + w10 * p11.ch))))
+            px[0] = RT_VF(x); px[1] = RT_VF(y); px[2] = RT_VF(z);
+#undef RT_VF
+        } else {                             // both fractional: bilinear on the 2x2
+            const float fv = r.fract;
+            const float f_tr = __fmul_rn(fv, fh), f_tl = __fmul_rn(fv, omfh), f_br = __fmul_rn(r.omf, fh), f_bl = __fmul_rn(r.omf, omfh);
+#define RT_BL(ch) f32_to_u8_numcast(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, (float)p10.ch), __fmul_rn(f_tr, (float)p11.ch)), __fmul_rn(f_bl, (float)p00.ch)), __fmul_rn(f_tl, (float)p01.ch)))
+            px[0] = RT_BL(x); px[1] = RT_BL(y); px[2] = RT_BL(z);
+#undef RT_BL
         }
-        float* d = dst + (size_t)y * ln.img_w;
         d[0] = s_lut[px[0]];
         d[plane] = s_lut[px[1]];
         d[2 * plane] = s_lut[px[2]];
+        r = rn; p00 = n00; p10 = n10; p01 = n01; p11 = n11;
     }
 }
 

@@ -214,6 +214,14 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     RT_TRY(plan_all(0, lines, batches, batch_page, &total));
     RT_TRY(plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total));
     RT_TRY(rt_crop_finish(ctx, infos.data()));
+    {
+        uint64_t det_px = 0, crop_px = 0, rec_rows = 0;
+        for (int i = 0; i < n_pages; ++i) det_px += (uint64_t)ps[i].det_h * ps[i].det_w;
+        for (int k = 0; k < n_lines; ++k) crop_px += (uint64_t)infos[k].w * infos[k].h;
+        for (const auto& b : rec_batches) rec_rows += (uint64_t)b.n * (b.img_w / 8);
+        const uint64_t st8[8] = {(uint64_t)n_pages, (uint64_t)n_lines, det_px, crop_px, total, rec_total, rec_rows, 0};
+        memcpy(ctx->run_stats, st8, sizeof(st8));
+    }
     tr.mark("crops+plans");
     // ---- 6. boxes back to original-image coordinates (session.rs:94-97) ----------------------------------------------
     {
@@ -313,4 +321,10 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     out->text = ctx->r_text.data();
     out->text_offsets = ctx->r_text_offs.data();
     return ret;
+}
+
+extern "C" retto_b200_status retto_b200_last_run_stats(const retto_b200_ctx* ctx, uint64_t* out8) {
+    if (!ctx || !out8) return RETTO_B200_ERR_INVALID_ARG;
+    memcpy(out8, ctx->run_stats, sizeof(ctx->run_stats));
+    return RETTO_B200_OK;
 }
