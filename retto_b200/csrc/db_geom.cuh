@@ -246,10 +246,13 @@ static __device__ void polygon_row_cover(const int px[4], const int py[4], int b
 }
 
 // box_score_fast (det_processor.rs:188-221): mean of the probability map over the polygon mask,
-// accumulated in the reference's order (raster order, sequential f32) — the warp loads 32 pixels
-// coalesced and every lane replays the same 32-step add chain through shuffles, so the result is
-// bit-identical to the scalar fold.  Returns false where the reference panics (poly[0] == poly[3]).
-static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int w, const int qx[4], const int qy[4], float* score) {
+// accumulated in the reference's order (raster order, sequential f32).  The warp loads 128 pixels coalesced
+// (double buffered), parks them in a warp-private shared-memory line, and every lane replays the same sequential
+// add chain from broadcast LDS.128 reads (8 per 32 pixels; a shuffle per pixel would be bound by the 1/clk/SM
+// shuffle pipe), so the result is bit-identical to the scalar fold.  sbuf: 128 floats private to the warp.
+// Returns false where the reference panics (poly[0] == poly[3]).
+static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int w, const int qx[4], const int qy[4], float* score,
+                                      float* sbuf) {
     const int lane = threadIdx.x & 31;
     if (qx[0] == qx[3] && qy[0] == qy[3]) return false;
     int x_min = min(min(qx[0], qx[1]), min(qx[2], qx[3])), x_max = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
@@ -262,15 +265,13 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
     for (int i = 0; i < 4; ++i) { px[i] = qx[i] - x_min; py[i] = qy[i] - y_min; }
     float acc = 0.0f;
     unsigned long long count = 0;
+    const float4* sb4 = reinterpret_cast<const float4*>(sbuf);
     for (int y = 0; y < bh; ++y) {
         RowCover rc;
         polygon_row_cover(px, py, bw, bh, y, rc);
         const float* row = pred + (size_t)(y + y_min) * w + x_min;
         for (int s = 0; s < rc.n; ++s) {
             count += (unsigned long long)(rc.b[s] - rc.a[s] + 1);
-            // 128 pixels per step, double buffered: the four coalesced loads of step i+1 are in flight while the
-            // reference's sequential add chain of step i is replayed by every lane through shuffles
-            // (bit-identical to the scalar fold)
             const int xb = rc.b[s];
             float v[4], nv[4];
 #pragma unroll
@@ -281,23 +282,22 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
             for (int x = rc.a[s]; x <= xb; x += 128) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    sbuf[32 * q + lane] = v[q];
                     const int xi = x + 128 + 32 * q + lane;
-                    nv[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;
+                    nv[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;   // next step's loads fly during this step's chain
                 }
+                __syncwarp();
                 const int n = min(128, xb - x + 1);
+                if (n == 128) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int lim = n - 32 * q;
-                    if (lim >= 32) {
-                        float t[32];
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) t[k] = __shfl_sync(RT_FULL, v[q], k);
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, t[k]);
-                    } else {
-                        for (int k = 0; k < lim; ++k) acc = __fadd_rn(acc, __shfl_sync(RT_FULL, v[q], k));
+                    for (int k = 0; k < 32; ++k) {
+                        const float4 t = sb4[k];
+                        acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
                     }
+                } else {
+                    for (int k = 0; k < n; ++k) acc = __fadd_rn(acc, sbuf[k]);
                 }
+                __syncwarp();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[q] = nv[q];
             }

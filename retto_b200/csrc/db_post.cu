@@ -384,13 +384,18 @@ struct GeomParams {
     int min_mini_box_size;
 };
 
-__global__ void __launch_bounds__(128, 4) box_geometry_kernel(const DetPostPage* __restrict__ pages,
+// Three phases, one warp per contour each (same grid mapping), communicating through BoxCand:
+//   PHASE 0  hull -> first min_area_rect -> sside filter                     (f64 trig: register heavy)
+//   PHASE 1  box_score_fast                                                  (long sequential chain: light kernel, so
+//                                                                             every box of an SM is resident at once)
+//   PHASE 2  unclip -> second min_area_rect -> scale_and_clip -> filters     (f64 trig: register heavy)
+#define ST_NEED_SCORE 7
+#define ST_NEED_UNCLIP 8
+template <int PHASE>
+__global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(const DetPostPage* __restrict__ pages,
                                                             int n_pages, PageCounters* __restrict__ counters, const CompRec* __restrict__ comps,
                                                             const int2* __restrict__ rowtab, int2* __restrict__ hullbuf, BoxCand* __restrict__ cand,
                                                             int max_comps, GeomParams gp, const int* __restrict__ hole_pages) {
-    __shared__ int2 s_pts[4][MAX_OFFSET_PTS];
-    __shared__ int2 s_hull[4][2 * MAX_OFFSET_PTS];
-    __shared__ int s_n[4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // hole_pages == nullptr: ids [0, n_roots) of every page (outer borders); else ids [n_roots, n_roots + n_holes)
     // of the listed pages (hole borders)
@@ -400,102 +405,120 @@ __global__ void __launch_bounds__(128, 4) box_geometry_kernel(const DetPostPage*
     const int n_comp = counters[page].n_roots + (hole_pages ? counters[page].n_holes : 0);
     if (id >= n_comp) return;
     const DetPostPage pg = pages[page];
-    const CompRec cr = comps[(size_t)page * max_comps + id];
     BoxCand* out = cand + (size_t)page * max_comps + id;
-    const int ymin = cr.ymin;
-    const int R = cr.ymax - ymin + 1;
-    const int2* rt = rowtab + (size_t)page * ROWCAP + cr.row_off;
-    int2* hull = hullbuf + ((size_t)page * ROWCAP + cr.row_off) * 2;
 
-    // 1. hull of the component == hull of its outer border
-    if (lane == 0) {
-        s_n[wib] = hull_from_rows(R, [&](int i, int& y, int& a, int& b) { const int2 v = rt[i]; y = ymin + i; a = v.x; b = v.y; }, hull);
-    }
-    __syncwarp();
-    int nh = s_n[wib];
-    __syncwarp();
-    double q[8];
-    warp_min_area_rect(hull, nh, q);
-    const float sside = sside_of(q);
-    int qx[4], qy[4];
+    if (PHASE == 0) {
+        __shared__ int s_n0[4];
+        const CompRec cr = comps[(size_t)page * max_comps + id];
+        const int ymin = cr.ymin;
+        const int R = cr.ymax - ymin + 1;
+        const int2* rt = rowtab + (size_t)page * ROWCAP + cr.row_off;
+        int2* hull = hullbuf + ((size_t)page * ROWCAP + cr.row_off) * 2;
+        // hull of the component == hull of its border
+        if (lane == 0) {
+            s_n0[wib] = hull_from_rows(R, [&](int i, int& y, int& a, int& b) { const int2 v = rt[i]; y = ymin + i; a = v.x; b = v.y; }, hull);
+        }
+        __syncwarp();
+        const int nh = s_n0[wib];
+        double q[8];
+        warp_min_area_rect(hull, nh, q);
+        const float sside = sside_of(q);
+        if (lane == 0) {
+            out->valid = 0; out->key = cr.key; out->sside1 = sside; out->score = CUDART_NAN_F;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { qx[i] = (int)q[2 * i]; qy[i] = (int)q[2 * i + 1]; }
-    if (lane == 0) {
-        out->valid = 0; out->key = cr.key; out->sside1 = sside; out->score = CUDART_NAN_F; out->status = 6;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { out->rect1[2 * i] = qx[i]; out->rect1[2 * i + 1] = qy[i]; }
-    }
-    if (cr.key == 0x7fffffff) return;  // every run spans the full width: find_contours never starts this border
-    if (sside < (float)gp.min_mini_box_size) { if (lane == 0) out->status = 1; return; }
-    // 2. box_score_fast on the probability map
-    float score;
-    if (!warp_box_score(pg.prob, pg.h, pg.w, qx, qy, &score)) {
-        if (lane == 0) { atomicMax(&counters[page].status, RETTO_B200_ERR_DEGENERATE_QUAD); out->status = -1; }
+            for (int i = 0; i < 8; ++i) out->rect1[i] = (int)q[i];
+            int st = ST_NEED_SCORE;
+            if (cr.key == 0x7fffffff) st = 6;                          // every run spans the full width: never discovered
+            else if (sside < (float)gp.min_mini_box_size) st = 1;
+            out->status = st;
+        }
         return;
     }
-    if (lane == 0) out->score = score;
-    if (score < gp.box_thresh) { if (lane == 0) out->status = 2; return; }
-    // 3. unclip
-    if (lane == 0) {
-        const float dist = unclip_distance(qx, qy, gp.unclip_ratio);
-        out->dist = dist;
-        int m = clipper_offset_round(qx, qy, (double)dist, 0.5, s_pts[wib], MAX_OFFSET_PTS);
-        if (m > 0) {
-            // rows of the offset polygon: sort by (y, x), group by y
-            int2* p = s_pts[wib];
-            for (int i = 1; i < m; ++i) {
-                const int2 v = p[i];
-                int j = i;
-                while (j > 0 && (p[j - 1].y > v.y || (p[j - 1].y == v.y && p[j - 1].x > v.x))) { p[j] = p[j - 1]; --j; }
-                p[j] = v;
-            }
-            // compress to rows in place: (y, xmin, xmax) stored as pairs in s_hull's upper half
-            int2* rows_y = s_hull[wib] + MAX_OFFSET_PTS;            // .x = y, .y unused
-            int2* rows_x = s_hull[wib] + MAX_OFFSET_PTS + MAX_OFFSET_PTS / 2;  // .x = xmin, .y = xmax
-            int nr = 0;
-            for (int i = 0; i < m;) {
-                int j = i;
-                while (j + 1 < m && p[j + 1].y == p[i].y) ++j;
-                if (nr < MAX_OFFSET_PTS / 2) { rows_y[nr] = make_int2(p[i].y, 0); rows_x[nr] = make_int2(p[i].x, p[j].x); ++nr; }
-                i = j + 1;
-            }
-            m = hull_from_rows(nr, [&](int i, int& y, int& a, int& b) { y = rows_y[i].x; a = rows_x[i].x; b = rows_x[i].y; }, s_hull[wib]);
+    if (PHASE == 1) {
+        if (out->status != ST_NEED_SCORE) return;
+        int qx[4], qy[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qx[i] = out->rect1[2 * i]; qy[i] = out->rect1[2 * i + 1]; }
+        __syncwarp();
+        __shared__ __align__(16) float s_buf[4][128];
+        float score;
+        if (!warp_box_score(pg.prob, pg.h, pg.w, qx, qy, &score, s_buf[wib])) {
+            if (lane == 0) { atomicMax(&counters[page].status, RETTO_B200_ERR_DEGENERATE_QUAD); out->status = -1; }
+            return;
         }
-        s_n[wib] = m;
-    }
-    __syncwarp();
-    nh = s_n[wib];
-    if (nh <= 0) {
-        // Clipper returned nothing (or overflow): the reference would panic in min_area_rect(&[])
-        if (lane == 0) { atomicMax(&counters[page].status, nh < 0 ? RETTO_B200_ERR_CAPACITY : RETTO_B200_ERR_DEGENERATE_QUAD); out->status = 5; }
+        if (lane == 0) { out->score = score; out->status = (score < gp.box_thresh) ? 2 : ST_NEED_UNCLIP; }
         return;
     }
-    double q2[8];
-    warp_min_area_rect(s_hull[wib], nh, q2);
-    const float sside2 = sside_of(q2);
-    if (lane == 0) { out->n_off = nh; for (int i = 0; i < 8; ++i) out->rect2[i] = (int)q2[i]; }
-    if (sside2 < (float)(gp.min_mini_box_size + 2)) { if (lane == 0) out->status = 3; return; }
-    if (lane == 0) {
-        out->status = 4;
-        const double inv_w = __ddiv_rn((double)pg.ori_w, (double)pg.w), inv_h = __ddiv_rn((double)pg.ori_h, (double)pg.h);
-        float b[8];
+    if (PHASE == 2) {
+        __shared__ int2 s_pts[4][MAX_OFFSET_PTS];
+        __shared__ int2 s_hull[4][2 * MAX_OFFSET_PTS];
+        __shared__ int s_n[4];
+        if (out->status != ST_NEED_UNCLIP) return;
+        int qx[4], qy[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            b[2 * i] = scale_clip_1((float)q2[2 * i], inv_w, (double)pg.ori_w);
-            b[2 * i + 1] = scale_clip_1((float)q2[2 * i + 1], inv_h, (double)pg.ori_h);
+        for (int i = 0; i < 4; ++i) { qx[i] = out->rect1[2 * i]; qy[i] = out->rect1[2 * i + 1]; }
+        const float score = out->score;
+        __syncwarp();
+        if (lane == 0) {
+            const float dist = unclip_distance(qx, qy, gp.unclip_ratio);
+            out->dist = dist;
+            int m = clipper_offset_round(qx, qy, (double)dist, 0.5, s_pts[wib], MAX_OFFSET_PTS);
+            if (m > 0) {
+                // rows of the offset polygon: sort by (y, x), group by y
+                int2* p = s_pts[wib];
+                for (int i = 1; i < m; ++i) {
+                    const int2 v = p[i];
+                    int j = i;
+                    while (j > 0 && (p[j - 1].y > v.y || (p[j - 1].y == v.y && p[j - 1].x > v.x))) { p[j] = p[j - 1]; --j; }
+                    p[j] = v;
+                }
+                // compress to rows in place: (y, xmin, xmax) stored as pairs in s_hull's upper half
+                int2* rows_y = s_hull[wib] + MAX_OFFSET_PTS;            // .x = y, .y unused
+                int2* rows_x = s_hull[wib] + MAX_OFFSET_PTS + MAX_OFFSET_PTS / 2;  // .x = xmin, .y = xmax
+                int nr = 0;
+                for (int i = 0; i < m;) {
+                    int j = i;
+                    while (j + 1 < m && p[j + 1].y == p[i].y) ++j;
+                    if (nr < MAX_OFFSET_PTS / 2) { rows_y[nr] = make_int2(p[i].y, 0); rows_x[nr] = make_int2(p[i].x, p[j].x); ++nr; }
+                    i = j + 1;
+                }
+                m = hull_from_rows(nr, [&](int i, int& y, int& a, int& b) { y = rows_y[i].x; a = rows_x[i].x; b = rows_x[i].y; }, s_hull[wib]);
+            }
+            s_n[wib] = m;
         }
-        const float pb_h = side_len(b[0], b[1], b[6], b[7]);
-        const float pb_w = side_len(b[0], b[1], b[2], b[3]);
-        if (!(pb_h <= 3.0f || pb_w <= 3.0f)) {
+        __syncwarp();
+        const int nh = s_n[wib];
+        if (nh <= 0) {
+            // Clipper returned nothing (or overflow): the reference would panic in min_area_rect(&[])
+            if (lane == 0) { atomicMax(&counters[page].status, nh < 0 ? RETTO_B200_ERR_CAPACITY : RETTO_B200_ERR_DEGENERATE_QUAD); out->status = 5; }
+            return;
+        }
+        double q2[8];
+        warp_min_area_rect(s_hull[wib], nh, q2);
+        const float sside2 = sside_of(q2);
+        if (lane == 0) { out->n_off = nh; for (int i = 0; i < 8; ++i) out->rect2[i] = (int)q2[i]; }
+        if (sside2 < (float)(gp.min_mini_box_size + 2)) { if (lane == 0) out->status = 3; return; }
+        if (lane == 0) {
+            out->status = 4;
+            const double inv_w = __ddiv_rn((double)pg.ori_w, (double)pg.w), inv_h = __ddiv_rn((double)pg.ori_h, (double)pg.h);
+            float b[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) out->xy[i] = b[i];
-            out->score = score;
-            out->valid = 1;
-            out->status = 0;
+            for (int i = 0; i < 4; ++i) {
+                b[2 * i] = scale_clip_1((float)q2[2 * i], inv_w, (double)pg.ori_w);
+                b[2 * i + 1] = scale_clip_1((float)q2[2 * i + 1], inv_h, (double)pg.ori_h);
+            }
+            const float pb_h = side_len(b[0], b[1], b[6], b[7]);
+            const float pb_w = side_len(b[0], b[1], b[2], b[3]);
+            if (!(pb_h <= 3.0f || pb_w <= 3.0f)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) out->xy[i] = b[i];
+                out->score = score;
+                out->valid = 1;
+                out->status = 0;
+            }
         }
     }
 }
-
 
 // ---- hole borders ---------------------------------------------------------------------------------------------
 // find_contours (det_processor.rs:293) also returns hole borders and retto does not filter by border_type, so every
@@ -806,8 +829,14 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     if (max_n > 0) {
         GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
         dim3 grid((max_n + 3) / 4, n);
-        RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel");
-        box_geometry_kernel<<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+        RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<0:rect1>");
+        box_geometry_kernel<0><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+        RT_LAUNCH_CHECK(ctx);
+        RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
+        box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+        RT_LAUNCH_CHECK(ctx);
+        RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<2:unclip>");
+        box_geometry_kernel<2><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
         RT_LAUNCH_CHECK(ctx);
     }
     // hole borders: pages with #components - Euler number > 0
@@ -854,8 +883,15 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
             int max_h = 0;
             for (int i : fp) max_h = std::max(max_h, std::min(h_cnt[i].n_roots - h_cnt[i].euler, MAX_HOLES));
             GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
+            const dim3 hg((max_h + 3) / 4, nf);
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
-            box_geometry_kernel<<<dim3((max_h + 3) / 4, nf), 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
+            box_geometry_kernel<0><<<hg, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
+            box_geometry_kernel<1><<<hg, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
+            box_geometry_kernel<2><<<hg, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
             RT_LAUNCH_CHECK(ctx);
             RT_LAUNCH_BEGIN(ctx, "hole_restore_kernel");
             hole_restore_kernel<<<g, 256, 0, st>>>(ha, d_lab);

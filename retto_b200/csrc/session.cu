@@ -210,18 +210,10 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     std::vector<retto_b200_batch> batches, rec_batches;
     std::vector<int> batch_page, rec_batch_page;
     uint64_t total = 0, rec_total = 0;
-    // both plans depend only on the crop dims (known on the host), so they overlap with the crop kernels
+    // the plans depend only on the crop dims (known on the host): the cls plan overlaps with the crop kernels, the rec
+    // plan with the cls batch build
     RT_TRY(plan_all(0, lines, batches, batch_page, &total));
-    RT_TRY(plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total));
     RT_TRY(rt_crop_finish(ctx, infos.data()));
-    {
-        uint64_t det_px = 0, crop_px = 0, rec_rows = 0;
-        for (int i = 0; i < n_pages; ++i) det_px += (uint64_t)ps[i].det_h * ps[i].det_w;
-        for (int k = 0; k < n_lines; ++k) crop_px += (uint64_t)infos[k].w * infos[k].h;
-        for (const auto& b : rec_batches) rec_rows += (uint64_t)b.n * (b.img_w / 8);
-        const uint64_t st8[8] = {(uint64_t)n_pages, (uint64_t)n_lines, det_px, crop_px, total, rec_total, rec_rows, 0};
-        memcpy(ctx->run_stats, st8, sizeof(st8));
-    }
     tr.mark("crops+plans");
     // ---- 6. boxes back to original-image coordinates (session.rs:94-97) ----------------------------------------------
     {
@@ -242,6 +234,15 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     tr.mark("scale");
     float* d_base = nullptr;
     RT_TRY(retto_b200_build_batches(ctx, 0, lines.data(), n_lines, total, &d_base));
+    RT_TRY(plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total));   // host work while the GPU builds the cls batches
+    {
+        uint64_t det_px = 0, crop_px = 0, rec_rows = 0;
+        for (int i = 0; i < n_pages; ++i) det_px += (uint64_t)ps[i].det_h * ps[i].det_w;
+        for (int k = 0; k < n_lines; ++k) crop_px += (uint64_t)infos[k].w * infos[k].h;
+        for (const auto& b : rec_batches) rec_rows += (uint64_t)b.n * (b.img_w / 8);
+        const uint64_t st8[8] = {(uint64_t)n_pages, (uint64_t)n_lines, det_px, crop_px, total, rec_total, rec_rows, 0};
+        memcpy(ctx->run_stats, st8, sizeof(st8));
+    }
     std::vector<int32_t> cls_crop_idx;
     std::vector<retto_b200_tensor> tin(batches.size()), tout(batches.size());
     auto fill_inputs = [&](int img_h) {
