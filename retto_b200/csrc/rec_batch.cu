@@ -44,7 +44,7 @@ __device__ __forceinline__ AxisS axis_small(const ThumbAxis a, unsigned size) {
 }
 struct RowS { int o0, o1; int n; float fract, omf, ft1, fb1, ft2, fb2; };   // per output row (pixel offsets of rows j0/j1)
 
-__global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
+__global__ void __launch_bounds__(BB_COLS, 6) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
                                                                  const CropDev* __restrict__ crops, const unsigned char* __restrict__ crop_pix,
                                                                  const int* __restrict__ flip_flags, int use_flip, int img_h,
                                                                  float* __restrict__ out) {
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
     const int stride = ln.img_w;
     RowS r = s_row[0];
     uchar4 p00 = __ldg(src + r.o0 + c0), p10 = __ldg(src + r.o0 + c1), p01 = __ldg(src + r.o1 + c0), p11 = __ldg(src + r.o1 + c1);
+#pragma unroll 2
     for (int y = 0; y < img_h; ++y, d += stride) {
         const RowS rn = s_row[(y + 1 < img_h) ? y + 1 : y];
         const uchar4 n00 = __ldg(src + rn.o0 + c0), n10 = __ldg(src + rn.o0 + c1), n01 = __ldg(src + rn.o1 + c0), n11 = __ldg(src + rn.o1 + c1);

@@ -1,0 +1,89 @@
+"""BASELINE.json full-size configurations, checked through size-independent properties plus oracle spot checks.
+  config 2: DB postprocess on 1024 synthetic 960x960 probability maps in ONE batched call
+  config 3: CTC decode of 16384 lines of 40 x 6625 logits (17.4 GB) in ONE call
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_dbpost_1024_maps_960(ctx):
+    import torch
+    from oracle import oracle as O
+    from tools.synth import gen_probmap
+    O.set_libm(1)
+    uniq = []
+    seed = 2000
+    while len(uniq) < 32:
+        p = gen_probmap(seed, 960, 960)
+        seed += 1
+        if not O.det_postprocess(p, 960, 960).comparator_inconsistent:
+            uniq.append(p)
+    refs = [O.det_postprocess(p, 960, 960) for p in uniq]
+    O.set_libm(0)
+    dev = [torch.from_numpy(p).cuda() for p in uniq]
+    maps = [dev[i % 32].clone() for i in range(1024)]          # 1024 distinct buffers (3.8 GB)
+    torch.cuda.synchronize()
+    out = ctx.det_postprocess(maps, [(960, 960)] * 1024, max_boxes_total=1024 * 80)
+    assert (out.page_status == 0).all()
+    total = 0
+    for i in range(1024):
+        boxes, scores = out.page(i)
+        r = refs[i % 32]
+        assert np.array_equal(boxes, r.boxes), f"map {i}"
+        assert np.array_equal(scores.view(np.uint32), r.scores.view(np.uint32)), f"map {i}"
+        total += len(boxes)
+    assert total == 32 * sum(len(r.boxes) for r in refs) and total > 1024 * 15
+    # bitmap / labels of a few pages, incl. the last one of the batch
+    for i in (0, 517, 1023):
+        bm = ctx.fetch_bitmap(i, 960, 960)
+        assert np.array_equal(bm, O.threshold_dilate(uniq[i % 32]))
+        lab = ctx.fetch_labels(i, 960, 960)
+        fg = lab >= 0
+        assert np.array_equal(fg, bm > 0)
+        ys, xs = np.nonzero(fg)
+        assert (lab[fg] <= ys * 960 + xs).all()                # label = min raster index of the component
+
+
+def test_config3_ctc_16k_lines(ctx, synth_dict):
+    import torch
+    from oracle import oracle as O
+    ctx.dict_load(synth_dict)
+    N, T, C = 16384, 40, 6625
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    x = torch.rand((N, T, C), device="cuda", generator=g) * 1e-3           # 17.4 GB
+    win = torch.randint(1, C, (N, T), device="cuda", generator=g)
+    win[torch.rand((N, T), device="cuda", generator=g) < 0.45] = 0
+    rep = torch.rand((N, T), device="cuda", generator=g) < 0.2
+    win[:, 1:][rep[:, 1:]] = win[:, :-1][rep[:, 1:]]
+    val = 0.5 + 0.5 * torch.rand((N, T), device="cuda", generator=g)
+    x.scatter_(2, win.unsqueeze(-1), val.unsqueeze(-1))
+    tie = torch.rand((N, T), device="cuda", generator=g) < 0.01            # exact ties: first maximum must win
+    other = torch.randint(0, C, (N, T), device="cuda", generator=g)
+    x.scatter_(2, other.unsqueeze(-1), torch.where(tie, val, x.gather(2, other.unsqueeze(-1)).squeeze(-1)).unsqueeze(-1))
+    x[::200, :, :] = 0
+    x[::200, :, 0] = 1.0                                                    # all-blank lines -> NaN score
+    torch.cuda.synchronize()
+    texts, scores, tokens, counts = ctx.ctc_decode([x], want_tokens=True)
+    idx, prob = ctx.ctc_argmax(x)
+    torch.cuda.synchronize()
+    ctx.sync()
+    # properties at full size: prob == row max; idx is the FIRST index attaining it
+    mx = x.amax(dim=2)
+    assert torch.equal(prob, mx)
+    first = (x == mx.unsqueeze(-1)).int().argmax(dim=2).int()
+    assert torch.equal(idx, first)
+    ih = idx.cpu().numpy()
+    keep = (ih != 0) & np.concatenate([np.ones((N, 1), bool), ih[:, 1:] != ih[:, :-1]], 1)
+    assert np.array_equal(counts, keep.sum(1))
+    assert np.isnan(scores[::200]).all() and (counts[::200] == 0).all()
+    assert sum(len(t) for t in texts) == int(counts.sum())                  # one code point per kept class in the synthetic dictionary
+    # oracle spot check on 256 lines spread over the tensor
+    sel = np.linspace(0, N - 1, 256).astype(int)
+    sub = x[torch.from_numpy(sel).cuda()].cpu().numpy()
+    st, oi, op, ot, oc, osc = O.ctc_decode(sub)
+    chars = O.rec_character(synth_dict)
+    assert np.array_equal(tokens[sel][:, :T], ot) and np.array_equal(scores[sel], osc, equal_nan=True)
+    assert [texts[i] for i in sel] == [O.tokens_to_text(ot[k], oc[k], chars) for k in range(256)]
