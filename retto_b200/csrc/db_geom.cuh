@@ -204,30 +204,30 @@ static __device__ void polygon_row_cover(const int px[4], const int py[4], int b
         const bool steep = abs(y1 - y0) > abs(x1 - x0);
         if (steep) { int t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
         if (x0 > x1) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
-        const long long dx = x1 - x0, dy = abs(y1 - y0);
+        const int dx = x1 - x0, dy = abs(y1 - y0);   // |coordinates| <= a few thousand: all products below fit in int32
         const int ystep = y0 < y1 ? 1 : -1;
         // n_k = number of minor-axis steps before emitting major-axis step k:
         //   n_k = 0 if 2k*dy - dx <= 0 else ceil((2k*dy - dx) / (2dx))
         if (steep) {
             // major axis = canvas y; one pixel on row y if x0 <= y <= x1
             if (y < x0 || y > x1) continue;
-            const long long k = y - x0, A = 2 * k * dy - dx;
-            const long long nk = (A <= 0 || dx == 0) ? 0 : (A + 2 * dx - 1) / (2 * dx);
-            const int xx = y0 + ystep * (int)nk;
+            const int k = y - x0, A = 2 * k * dy - dx;
+            const int nk = (A <= 0 || dx == 0) ? 0 : (int)((unsigned)(A + 2 * dx - 1) / (unsigned)(2 * dx));
+            const int xx = y0 + ystep * nk;
             cover_add(rc, xx, xx, bw);
         } else {
             // major axis = canvas x; row y is hit for k with n_k == t
             const int t = (y - y0) * ystep;
             if (t < 0 || t > dy) continue;
-            long long klo, khi;
+            int klo, khi;
             if (dy == 0) { klo = 0; khi = dx; }
             else {
-                klo = (t == 0) ? 0 : (dx * (2LL * t - 1)) / (2 * dy) + 1;
-                khi = (dx * (2LL * t + 1)) / (2 * dy);   // k_lo(t+1) - 1
+                klo = (t == 0) ? 0 : (int)((unsigned)(dx * (2 * t - 1)) / (unsigned)(2 * dy)) + 1;
+                khi = (int)((unsigned)(dx * (2 * t + 1)) / (unsigned)(2 * dy));   // k_lo(t+1) - 1
                 if (khi > dx) khi = dx;
             }
             if (klo > khi) continue;
-            cover_add(rc, x0 + (int)klo, x0 + (int)khi, bw);
+            cover_add(rc, x0 + klo, x0 + khi, bw);
         }
     }
     // sort by a, merge overlaps (adjacent intervals may stay separate: order is what matters)
@@ -249,10 +249,11 @@ static __device__ void polygon_row_cover(const int px[4], const int py[4], int b
 // accumulated in the reference's order (raster order, sequential f32).  The warp loads 128 pixels coalesced
 // (double buffered), parks them in a warp-private shared-memory line, and every lane replays the same sequential
 // add chain from broadcast LDS.128 reads (8 per 32 pixels; a shuffle per pixel would be bound by the 1/clk/SM
-// shuffle pipe), so the result is bit-identical to the scalar fold.  sbuf: 128 floats private to the warp.
+// shuffle pipe), so the result is bit-identical to the scalar fold.  sbuf: 128 floats, cov: 32*17 ints, both private
+// to the warp.
 // Returns false where the reference panics (poly[0] == poly[3]).
 static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int w, const int qx[4], const int qy[4], float* score,
-                                      float* sbuf) {
+                                      float* sbuf, int* cov) {
     const int lane = threadIdx.x & 31;
     if (qx[0] == qx[3] && qy[0] == qy[3]) return false;
     int x_min = min(min(qx[0], qx[1]), min(qx[2], qx[3])), x_max = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
@@ -266,42 +267,59 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
     float acc = 0.0f;
     unsigned long long count = 0;
     const float4* sb4 = reinterpret_cast<const float4*>(sbuf);
-    for (int y = 0; y < bh; ++y) {
-        RowCover rc;
-        polygon_row_cover(px, py, bw, bh, y, rc);
-        const float* row = pred + (size_t)(y + y_min) * w + x_min;
-        for (int s = 0; s < rc.n; ++s) {
-            count += (unsigned long long)(rc.b[s] - rc.a[s] + 1);
-            const int xb = rc.b[s];
-            float v[4], nv[4];
+    // row covers of 32 consecutive rows are computed in parallel (one row per lane) into shared memory, then the
+    // rows are consumed in raster order
+    int* cov_n = cov;                 // [32]
+    int* cov_ab = cov + 32;           // [32][16]: a[8] then b[8]
+    for (int y_base = 0; y_base < bh; y_base += 32) {
+        {
+            RowCover rc;
+            rc.n = 0;
+            if (y_base + lane < bh) polygon_row_cover(px, py, bw, bh, y_base + lane, rc);
+            cov_n[lane] = rc.n;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int xi = rc.a[s] + 32 * q + lane;
-                v[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;
-            }
-            for (int x = rc.a[s]; x <= xb; x += 128) {
+            for (int k = 0; k < 8; ++k) { if (k < rc.n) { cov_ab[lane * 16 + k] = rc.a[k]; cov_ab[lane * 16 + 8 + k] = rc.b[k]; } }
+        }
+        __syncwarp();
+        const int nrows = min(32, bh - y_base);
+        for (int r = 0; r < nrows; ++r) {
+            const int y = y_base + r;
+            const int nseg = cov_n[r];
+            const float* row = pred + (size_t)(y + y_min) * w + x_min;
+            for (int s = 0; s < nseg; ++s) {
+                const int xa = cov_ab[r * 16 + s], xb = cov_ab[r * 16 + 8 + s];
+                count += (unsigned long long)(xb - xa + 1);
+                float v[4], nv[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    sbuf[32 * q + lane] = v[q];
-                    const int xi = x + 128 + 32 * q + lane;
-                    nv[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;   // next step's loads fly during this step's chain
+                    const int xi = xa + 32 * q + lane;
+                    v[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;
                 }
-                __syncwarp();
-                const int n = min(128, xb - x + 1);
-                if (n == 128) {
+                for (int x = xa; x <= xb; x += 128) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const float4 t = sb4[k];
-                        acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
+                    for (int q = 0; q < 4; ++q) {
+                        sbuf[32 * q + lane] = v[q];
+                        const int xi = x + 128 + 32 * q + lane;
+                        nv[q] = (xi <= xb) ? __ldg(row + xi) : 0.0f;   // next step's loads fly during this step's chain
                     }
-                } else {
-                    for (int k = 0; k < n; ++k) acc = __fadd_rn(acc, sbuf[k]);
-                }
-                __syncwarp();
+                    __syncwarp();
+                    const int n = min(128, xb - x + 1);
+                    if (n == 128) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = nv[q];
+                        for (int k = 0; k < 32; ++k) {
+                            const float4 t = sb4[k];
+                            acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
+                        }
+                    } else {
+                        for (int k = 0; k < n; ++k) acc = __fadd_rn(acc, sbuf[k]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = nv[q];
+                }
             }
         }
+        __syncwarp();
     }
     *score = count > 0 ? __fdiv_rn(acc, (float)count) : 0.0f;
     return true;

@@ -441,8 +441,9 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
         for (int i = 0; i < 4; ++i) { qx[i] = out->rect1[2 * i]; qy[i] = out->rect1[2 * i + 1]; }
         __syncwarp();
         __shared__ __align__(16) float s_buf[4][128];
+        __shared__ int s_cov[4][32 * 17];
         float score;
-        if (!warp_box_score(pg.prob, pg.h, pg.w, qx, qy, &score, s_buf[wib])) {
+        if (!warp_box_score(pg.prob, pg.h, pg.w, qx, qy, &score, s_buf[wib], s_cov[wib])) {
             if (lane == 0) { atomicMax(&counters[page].status, RETTO_B200_ERR_DEGENERATE_QUAD); out->status = -1; }
             return;
         }

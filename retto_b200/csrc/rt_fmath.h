@@ -120,18 +120,27 @@ RT_HD_BIG void sincos_dd(dd a, dd* s_out, dd* c_out) {
     dd x = dd_scale2(r, 0.0625);
     dd x2 = dd_mul(x, x);
     // Taylor: sin x = x - x^3/3! + ... (to x^17);  cos x - 1 = -x^2/2! + x^4/4! - ... (to x^16)
+    // term ratios 1/((2i)(2i+1)) and 1/((2i-1)(2i)) as double-double constants (a dd multiply instead of a dd divide)
+    const double SR_HI[8] = {0.16666666666666666, 0.05, 0.023809523809523808, 0.013888888888888888, 0.00909090909090909,
+                             0.00641025641025641, 0.004761904761904762, 0.003676470588235294};
+    const double SR_LO[8] = {9.25185853854297e-18, -2.7755575615628915e-18, 1.32169407693471e-18, 7.709882115452476e-19,
+                             4.415659757031872e-19, 2.2240044563805217e-19, -4.295505750037808e-19, 5.102127870520021e-20};
+    const double CR_HI[7] = {0.08333333333333333, 0.03333333333333333, 0.017857142857142856, 0.011111111111111112,
+                             0.007575757575757576, 0.005494505494505495, 0.004166666666666667};
+    const double CR_LO[7] = {4.625929269271485e-18, 4.625929269271486e-19, 9.912705577010326e-19, -4.2404351634988616e-19,
+                             -2.1026951223961299e-19, -4.2891514515910067e-19, 5.782411586589357e-20};
     dd term = x;   // x^(2i+1)/(2i+1)!
     dd s = x;
     RT_NOUNROLL
     for (int i = 1; i <= 8; ++i) {
-        term = dd_div_d(dd_mul(term, x2), (double)((2 * i) * (2 * i + 1)));
+        term = dd_mul(dd_mul(term, x2), dd{SR_HI[i - 1], SR_LO[i - 1]});
         s = (i & 1) ? dd_sub(s, term) : dd_add(s, term);
     }
     dd cterm = dd_scale2(x2, 0.5);  // x^2/2!
     dd cm1 = dd_neg(cterm);
     RT_NOUNROLL
     for (int i = 2; i <= 8; ++i) {
-        cterm = dd_div_d(dd_mul(cterm, x2), (double)((2 * i - 1) * (2 * i)));
+        cterm = dd_mul(dd_mul(cterm, x2), dd{CR_HI[i - 2], CR_LO[i - 2]});
         cm1 = (i & 1) ? dd_sub(cm1, cterm) : dd_add(cm1, cterm);
     }
     // double-angle x4:  sin 2x = 2 s (1 + cm1);  cos 2x - 1 = -2 s^2
@@ -196,10 +205,12 @@ RT_HD_BIG dd atan2_dd(dd y, dd x) {
     dd d = dd_div(num, den);
     dd d2 = dd_mul(d, d);
     // atan(d) = d (1 - d^2/3 + d^4/5 - d^6/7 + d^8/9 - d^10/11),  |d| <= ~1e-3 (d^13/13 negligible)
-    dd poly = dd_sub(dd_div_d(dd_from(1.0), 9.0), dd_div_d(d2, 11.0));   // 1/9 - d2/11
-    poly = dd_sub(dd_div_d(dd_from(1.0), 7.0), dd_mul(d2, poly));        // 1/7 - d2 (...)
-    poly = dd_sub(dd_div_d(dd_from(1.0), 5.0), dd_mul(d2, poly));        // 1/5 - d2 (...)
-    poly = dd_sub(dd_div_d(dd_from(1.0), 3.0), dd_mul(d2, poly));        // 1/3 - d2 (...)
+    const dd R3{0.3333333333333333, 1.850371707708594e-17}, R5{0.2, -1.1102230246251566e-17}, R7{0.14285714285714285, 7.93016446160826e-18},
+        R9{0.1111111111111111, 6.1679056923619804e-18}, R11{0.09090909090909091, -2.523234146875356e-18};
+    dd poly = dd_sub(R9, dd_mul(d2, R11));                               // 1/9 - d2/11
+    poly = dd_sub(R7, dd_mul(d2, poly));                                 // 1/7 - d2 (...)
+    poly = dd_sub(R5, dd_mul(d2, poly));                                 // 1/5 - d2 (...)
+    poly = dd_sub(R3, dd_mul(d2, poly));                                 // 1/3 - d2 (...)
     poly = dd_sub(dd_from(1.0), dd_mul(d2, poly));                       // 1 - d2 (...)
     dd corr = dd_mul(d, poly);
     return dd_add(dd_from(th), corr);
