@@ -188,7 +188,7 @@ struct retto_b200_ctx {
     bool dp_trace_enabled = false, dp_trace_valid = false;
     DevBuf d_trace;
     std::vector<int> dp_holes;   // per page: #hole borders of the last det_postprocess (components - Euler number)
-    DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out, d_holes, d_hole_pages;
+    DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out, d_holes, d_hole_pages, d_key_at;
     HostBuf h_dp;
 
     // crops

@@ -72,7 +72,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix,
                                                            int n_pages, int total_tiles, float thr, int dilate,
                                                            unsigned char* __restrict__ bitmap, int* __restrict__ labels,
-                                                           unsigned char* __restrict__ tileflags) {
+                                                           unsigned char* __restrict__ tileflags, int* __restrict__ cid_at,
+                                                           int* __restrict__ key_at) {
     DetPostPage pg; int page, s, rb, tile;
     if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
     const int lane = threadIdx.x & 31;
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
     const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
     unsigned char* bm = bitmap + pg.px_base;
     int* lab = labels + pg.px_base;
+    int* ymax_at = cid_at + pg.px_base;   // root-indexed slots, initialised at every run start (a root is always one)
+    int* keyp = key_at + pg.px_base;
     const float* __restrict__ prob = pg.prob;
 
     auto load_raw = [&](int y, unsigned& bits5) {  // bit0 = t(x-1), bits1..4 = t(x..x+3)
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
         for (int j = 0; j < 4; ++j) {
             if (nib & (1u << j)) lb[j] = y * W + start;
             else { lb[j] = -1; start = x + j + 1; }
+            if (lb[j] == y * W + x + j) { ymax_at[lb[j]] = -1; keyp[lb[j]] = 0x7fffffff; }   // run start
         }
         if (VEC) {
             if (x < W) {
@@ -223,29 +227,44 @@ __global__ void __launch_bounds__(128) ccl_merge_kernel(const DetPostPage* __res
 
 // ---- C: flatten + collect roots ---------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ccl_flatten_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix, int n_pages,
-                                                           int total_tiles, int* __restrict__ labels, const unsigned char* __restrict__ tileflags,
-                                                           PageCounters* __restrict__ counters, int* __restrict__ roots, int max_comps) {
+                                                           int total_tiles, const unsigned char* __restrict__ bitmap, int* __restrict__ labels,
+                                                           const unsigned char* __restrict__ tileflags, PageCounters* __restrict__ counters,
+                                                           int* __restrict__ roots, int max_comps, int* __restrict__ cid_at,
+                                                           int* __restrict__ key_at) {
     DetPostPage pg; int page, s, rb, tile;
     if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
     if (!tileflags[tile]) return;
     const int lane = threadIdx.x & 31;
     const int W = pg.w, H = pg.h;
-    const int x = s * TILE_W + lane * 4;
+    const int x0 = s * TILE_W, x = x0 + lane * 4;
     const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
+    const unsigned char* bm = bitmap + pg.px_base;
     int* L = labels + pg.px_base;
+    int* ymax_at = cid_at + pg.px_base;
+    int* keyp = key_at + pg.px_base;
     for (int y = y0; y < y1; ++y) {
+        unsigned cur;
+        load_bits6(bm, W, y, x, x0, lane, true, cur);
+        if (!(cur & 0x1eu)) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (x + j >= W) continue;
+            const unsigned cb = cur >> j;
+            if (!(cb & 2u)) continue;
             const int p = y * W + x + j;
             const int l = L[p];
-            if (l < 0) continue;
             const int r = find_root(L, l);
             if (r != l) L[p] = r;
             if (r == p) {
                 const int slot = atomicAdd(&counters[page].n_roots, 1);
                 if (slot < max_comps) roots[(size_t)page * max_comps + slot] = p;
             }
+            // component extents from run ends only (root-indexed slots initialised by bitmap_runs_kernel):
+            //   last row, and the position at which imageproc's scan (RECALLED, contours.rs) discovers the border: an
+            //   outer border starts only at x > 0 with a zero to the left, or (as a "hole"-typed start tracing the same
+            //   border) at x + 1 < width with a zero to the right; the frame itself never starts a border.
+            const bool is_start = !(cb & 1u), is_end = !(cb & 4u);
+            if (is_start) atomicMax(&ymax_at[r], y);
+            if ((is_start && x + j > 0) || (is_end && x + j + 1 < W)) atomicMin(&keyp[r], p);
         }
     }
 }
@@ -273,7 +292,7 @@ __device__ void block_sort_ints(int* r, int n) {
 // ---- D: sort roots, assign dense ids ----------------------------------------------------------------
 __global__ void __launch_bounds__(1024) comp_sort_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
                                                           int* __restrict__ roots, CompRec* __restrict__ comps, int* __restrict__ cid_at,
-                                                          int max_comps) {
+                                                          const int* __restrict__ key_at, int2* __restrict__ rowtab, int max_comps) {
     const int page = blockIdx.x;
     const DetPostPage pg = pages[page];
     int n = counters[page].n_roots;
@@ -285,14 +304,38 @@ __global__ void __launch_bounds__(1024) comp_sort_kernel(const DetPostPage* __re
     block_sort_ints(r, n);
     CompRec* c = comps + (size_t)page * max_comps;
     int* cid = cid_at + pg.px_base;
+    const int* keyp = key_at + pg.px_base;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int root = r[i];
-        cid[root] = i;
         CompRec cr;
-        cr.root = root; cr.ymax = -1; cr.xmin = 0x7fffffff; cr.xmax = -1; cr.row_off = 0;
-        cr.key = 0x7fffffff; cr.ymin = root / pg.w; cr.pad = 0;
+        cr.root = root; cr.ymax = cid[root]; cr.xmin = 0; cr.xmax = 0; cr.row_off = 0;
+        cr.key = keyp[root]; cr.ymin = root / pg.w; cr.pad = 0;
         c[i] = cr;
+        cid[root] = i;   // the slot now holds the dense component id (discovery order of the first pixel)
     }
+    __syncthreads();
+    // row-table allocation (one row per component row), exclusive prefix over the components
+    __shared__ int s_part[1024];
+    __shared__ int s_total;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += c[i].ymax - c[i].ymin + 1;
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { const int v = s_part[i]; s_part[i] = run; run += v; }
+        s_total = run;
+        counters[page].row_total = run;
+        if (run > ROWCAP) counters[page].status = RETTO_B200_ERR_CAPACITY;
+    }
+    __syncthreads();
+    int off = s_part[threadIdx.x];
+    for (int i = b; i < e; ++i) { c[i].row_off = off; off += c[i].ymax - c[i].ymin + 1; }
+    const int total = min(s_total, ROWCAP);
+    int2* rt = rowtab + (size_t)page * ROWCAP;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) rt[i] = make_int2(0x7fffffff, -1);
 }
 
 // ---- E / G: run-end passes ------------------------------------------------------------------------------
@@ -774,6 +817,7 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     RT_CUDA_OK(ctx, ctx->d_bitmap.ensure((size_t)px, st));
     RT_CUDA_OK(ctx, ctx->d_labels.ensure((size_t)px * 4, st));
     RT_CUDA_OK(ctx, ctx->d_cid_at.ensure((size_t)px * 4, st));
+    RT_CUDA_OK(ctx, ctx->d_key_at.ensure((size_t)px * 4, st));
     RT_CUDA_OK(ctx, ctx->d_tileflags.ensure((size_t)total_tiles, st));
     RT_CUDA_OK(ctx, ctx->d_roots.ensure(sizeof(int) * (size_t)n * max_comps, st));
     RT_CUDA_OK(ctx, ctx->d_comps.ensure(sizeof(CompRec) * (size_t)n * max_comps, st));
@@ -784,6 +828,7 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     unsigned char* d_bm = ctx->d_bitmap.as<unsigned char>();
     int* d_lab = ctx->d_labels.as<int>();
     int* d_cid = ctx->d_cid_at.as<int>();
+    int* d_key = ctx->d_key_at.as<int>();
     unsigned char* d_tf = ctx->d_tileflags.as<unsigned char>();
     int* d_roots = ctx->d_roots.as<int>();
     CompRec* d_comps = ctx->d_comps.as<CompRec>();
@@ -797,24 +842,18 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     const int tgrid = (total_tiles + 3) / 4;
     RT_LAUNCH_BEGIN(ctx, "bitmap_runs_kernel");
     if (vec)
-        bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf);
+        bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
     else
-        bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf);
+        bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
     RT_LAUNCH_CHECK(ctx);
     RT_LAUNCH_BEGIN(ctx, "ccl_merge_kernel");
     ccl_merge_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt);
     RT_LAUNCH_CHECK(ctx);
     RT_LAUNCH_BEGIN(ctx, "ccl_flatten_kernel");
-    ccl_flatten_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_lab, d_tf, d_cnt, d_roots, max_comps);
+    ccl_flatten_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt, d_roots, max_comps, d_cid, d_key);
     RT_LAUNCH_CHECK(ctx);
     RT_LAUNCH_BEGIN(ctx, "comp_sort_kernel");
-    comp_sort_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_roots, d_comps, d_cid, max_comps);
-    RT_LAUNCH_CHECK(ctx);
-    RT_LAUNCH_BEGIN(ctx, "run_end_kernel<0>");
-    run_end_kernel<0><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
-    RT_LAUNCH_CHECK(ctx);
-    RT_LAUNCH_BEGIN(ctx, "row_alloc_kernel");
-    row_alloc_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_comps, d_rowtab, max_comps);
+    comp_sort_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_roots, d_comps, d_cid, d_key, d_rowtab, max_comps);
     RT_LAUNCH_CHECK(ctx);
     RT_LAUNCH_BEGIN(ctx, "run_end_kernel<1>");
     run_end_kernel<1><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
