@@ -135,19 +135,28 @@ class ReplayWorker:
         self.gen.manual_seed(seed)
         self.cb = FORWARD_FN(self._call)
         self.err = None
-        self.rec_bytes = 0
-        self.rec_rows = 0
+        self.begin_step()
+
+    def begin_step(self):
+        """run_pages may split a host-resident batch into chunks: each (stage, call index) has its own tensor list"""
+        self.seq = {0: 0, 1: 0, 2: 0}
+        self.page_cursor = 0
 
     def _call(self, user, stage, n, inputs, outputs, stream):
         try:
-            if stage in self.cache and self.cache[stage][0] == n:
-                C.memmove(outputs, self.cache[stage][1], C.sizeof(self.Tensor) * n)
+            key = (stage, self.seq[stage])
+            self.seq[stage] += 1
+            page0 = self.page_cursor
+            if stage == 0:
+                self.page_cursor += n
+            if key in self.cache and self.cache[key][0] == n:
+                C.memmove(outputs, self.cache[key][1], C.sizeof(self.Tensor) * n)
                 return 0
             torch = self.torch
             arr = (self.Tensor * max(n, 1))()
             if stage == 0:
                 for i in range(n):
-                    p = self.probs[i]
+                    p = self.probs[page0 + i]
                     arr[i].d_data, arr[i].ndim = p.data_ptr(), 4
                     arr[i].shape[0], arr[i].shape[1], arr[i].shape[2], arr[i].shape[3] = 1, 1, p.shape[-2], p.shape[-1]
             elif stage == 1:
@@ -156,7 +165,7 @@ class ReplayWorker:
                 s = torch.where(torch.rand(max(tot, 1), device=self.device, generator=self.gen) < 0.3, 0.95, 0.55)
                 is180 = u < 0.3
                 buf = torch.stack([torch.where(is180, 1 - s, s), torch.where(is180, s, 1 - s)], 1).contiguous().float()
-                self.keep[1] = buf
+                self.keep[key] = buf
                 o = 0
                 for i in range(n):
                     k = int(inputs[i].shape[0])
@@ -173,8 +182,7 @@ class ReplayWorker:
                 rep = torch.rand(v.shape[0], device=self.device, generator=self.gen) < 0.2
                 win[1:][rep[1:]] = win[:-1][rep[1:]]
                 v[torch.arange(v.shape[0], device=self.device), win] = 0.5 + 0.5 * torch.rand(v.shape[0], device=self.device, generator=self.gen)
-                self.keep[2] = pool
-                self.rec_bytes, self.rec_rows = tot_rows * C_CLASSES * 4, tot_rows
+                self.keep[key] = pool
                 o = 0
                 for i in range(n):
                     k, T = int(inputs[i].shape[0]), int(inputs[i].shape[3]) // 8
@@ -183,7 +191,7 @@ class ReplayWorker:
                     o += k * T
             torch.cuda.synchronize()
             C.memmove(outputs, arr, C.sizeof(self.Tensor) * n)
-            self.cache[stage] = (n, arr)
+            self.cache[key] = (n, arr)
             return 0
         except Exception as e:  # noqa
             self.err = e
@@ -339,6 +347,7 @@ def main():
     torch.cuda.synchronize()
 
     def step(pg):
+        worker.begin_step()
         st = L.retto_b200_run_pages(H, pg, P, worker.cb, None, C.byref(res))
         if worker.err is not None:
             raise worker.err

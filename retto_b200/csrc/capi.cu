@@ -52,6 +52,10 @@ extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStream_t s = c->stream;
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+    for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     delete c;  // DevBuf / HostBuf members free their memory
     cudaStreamDestroy(s);
 }

@@ -204,7 +204,9 @@ struct retto_b200_ctx {
     // sizes of the last run_pages call (bench.py algorithmic bytes): pages, lines, det px, crop px, cls floats, rec floats, rec rows
     uint64_t run_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // session scratch
-    DevBuf d_pages_raw, d_pages_rs, d_det_in;
+    DevBuf d_pages_raw, d_pages_rs, d_det_in, d_pages_up;
+    cudaStream_t copy_stream = nullptr;          // H2D of later chunks overlaps the kernels of earlier ones (run_pages)
+    std::vector<cudaEvent_t> copy_events;
     std::vector<retto_b200_page_result> r_pages;
     std::vector<retto_b200_box> r_boxes;
     std::vector<retto_b200_cls_result> r_cls;

@@ -14,6 +14,13 @@ retto_b200_status rt_crop_launch(retto_b200_ctx* ctx, const retto_b200_crop_job*
 retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos);
 
 #include <chrono>
+#define RUN_CHUNK_PAGES_MAX 64
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
 namespace {
 struct HostTrace {   // RETTO_B200_HOST_TRACE=1: wall-clock per stage of run_pages on stderr (host + waits)
     bool on;
@@ -42,8 +49,8 @@ struct PageState {
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 }  // namespace
 
-extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
-                                                  retto_b200_forward_fn forward, void* user, retto_b200_results* out) {
+static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
+                                        retto_b200_forward_fn forward, void* user, retto_b200_results* out) {
     if (!ctx || n_pages < 0 || (n_pages > 0 && !h_pages) || !forward || !out) return RETTO_B200_ERR_INVALID_ARG;
     cudaStream_t st = ctx->stream;
     HostTrace tr;
@@ -321,6 +328,139 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     tr.mark("rec_fwd+ctc");
     out->text = ctx->r_text.data();
     out->text_offsets = ctx->r_text_offs.data();
+    return ret;
+}
+
+// Page upload by the SMs: pinned host memory is device-accessible under UVA, so a copy kernel on the copy stream can
+// pull the pages over PCIe without occupying the DMA engine — the many small descriptor uploads of the compute stream
+// would otherwise queue behind megabytes of page copies in the same H2D engine FIFO and serialise the pipeline.
+struct PullArgs { const uint4* src[RUN_CHUNK_PAGES_MAX]; uint4* dst[RUN_CHUNK_PAGES_MAX]; unsigned n16[RUN_CHUNK_PAGES_MAX]; int n; };
+// A SMALL grid on purpose (PULL_BLOCKS blocks of 512 threads, 8 x 16 B in flight per thread = 64 KB per block): PCIe needs
+// only ~0.2 MB in flight to saturate, and a grid that filled the SMs with threads waiting on PCIe would starve the
+// compute stream's kernels of block slots — the overlap this pipeline exists for.
+__global__ void __launch_bounds__(512) pull_pages_kernel(PullArgs a) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (int p = 0; p < a.n; ++p) {
+        const uint4* __restrict__ s = a.src[p];
+        uint4* __restrict__ d = a.dst[p];
+        const unsigned n = a.n16[p];
+        unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 7 * stride < n; i += 8 * stride) {
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldcs(s + i + k * stride);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) d[i + k * stride] = v[k];
+        }
+        for (; i < n; i += stride) d[i] = __ldcs(s + i);
+    }
+}
+
+// Host-resident batches larger than one chunk are pipelined: every page is uploaded on a separate copy stream up front
+// (one event per chunk), and chunk k is processed on the compute stream as soon as its pages have landed, so the PCIe
+// transfer of the later chunks overlaps with the kernels of the earlier ones.  Results are concatenated in page order.
+extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
+                                                  retto_b200_forward_fn forward, void* user, retto_b200_results* out) {
+    if (!ctx || n_pages < 0 || (n_pages > 0 && !h_pages) || !forward || !out) return RETTO_B200_ERR_INVALID_ARG;
+    // pages per chunk / blocks of the pull kernel: tunables for experiments, defaults measured on B200
+    static const int RUN_CHUNK_PAGES = env_int("RETTO_B200_CHUNK_PAGES", 32, 1, RUN_CHUNK_PAGES_MAX);
+    static const int PULL_BLOCKS = env_int("RETTO_B200_PULL_BLOCKS", 16, 1, 1024);
+    static const int USE_DMA = env_int("RETTO_B200_PULL_DMA", 0, 0, 1);
+    bool all_host = n_pages > RUN_CHUNK_PAGES;
+    for (int i = 0; i < n_pages && all_host; ++i) if (h_pages[i].on_device || !h_pages[i].rgb || h_pages[i].h <= 0 || h_pages[i].w <= 0) all_host = false;
+    if (!all_host) return run_pages_once(ctx, h_pages, n_pages, forward, user, out);
+
+    if (!ctx->copy_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        RT_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi));   // page pulls first: they are the critical path
+    }
+    const int n_chunks = (n_pages + RUN_CHUNK_PAGES - 1) / RUN_CHUNK_PAGES;
+    while ((int)ctx->copy_events.size() < n_chunks) {
+        cudaEvent_t e;
+        RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_events.push_back(e);
+    }
+    size_t raw_bytes = 0;
+    for (int i = 0; i < n_pages; ++i) raw_bytes += align256((size_t)h_pages[i].h * h_pages[i].w * 3);
+    RT_CUDA_OK(ctx, ctx->d_pages_up.ensure(std::max<size_t>(raw_bytes, 256), ctx->stream));
+    std::vector<retto_b200_page> dev_pages(n_pages);
+    {
+        size_t off = 0;
+        PullArgs pa;
+        pa.n = 0;
+        bool pull_ok = true;
+        for (int i = 0; i < n_pages; ++i) {
+            uint8_t* d = ctx->d_pages_up.as<uint8_t>() + off;
+            const size_t bytes = (size_t)h_pages[i].h * h_pages[i].w * 3;
+            off += align256(bytes);
+            dev_pages[i] = retto_b200_page{d, h_pages[i].h, h_pages[i].w, 1};
+            cudaPointerAttributes at;
+            const bool pinned = cudaPointerGetAttributes(&at, h_pages[i].rgb) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr &&
+                                ((uintptr_t)at.devicePointer % 16 == 0);
+            cudaGetLastError();
+            if (pinned && pull_ok && !USE_DMA) {
+                pa.src[pa.n] = reinterpret_cast<const uint4*>(at.devicePointer);
+                pa.dst[pa.n] = reinterpret_cast<uint4*>(d);
+                pa.n16[pa.n] = (unsigned)(bytes / 16);
+                ++pa.n;
+                if (bytes % 16) RT_CUDA_OK(ctx, cudaMemcpyAsync(d + (bytes & ~size_t(15)), h_pages[i].rgb + (bytes & ~size_t(15)), bytes % 16, cudaMemcpyHostToDevice, ctx->copy_stream));
+            } else {
+                pull_ok = false;   // pageable memory: plain DMA copy (no overlap guarantee)
+                RT_CUDA_OK(ctx, cudaMemcpyAsync(d, h_pages[i].rgb, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+            if ((i + 1) % RUN_CHUNK_PAGES == 0 || i + 1 == n_pages) {
+                if (pa.n > 0) {
+                    pull_pages_kernel<<<PULL_BLOCKS, 512, 0, ctx->copy_stream>>>(pa);
+                    ctx->launches++;
+                    pa.n = 0;
+                }
+                RT_CUDA_OK(ctx, cudaEventRecord(ctx->copy_events[i / RUN_CHUNK_PAGES], ctx->copy_stream));
+            }
+        }
+    }
+    std::vector<retto_b200_page_result> a_pages;
+    std::vector<retto_b200_box> a_boxes;
+    std::vector<retto_b200_cls_result> a_cls;
+    std::vector<uint32_t> a_toffs(1, 0);
+    std::vector<char> a_text;
+    std::vector<float> a_scores;
+    uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    retto_b200_status ret = RETTO_B200_OK;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int p0 = c * RUN_CHUNK_PAGES, np = std::min(RUN_CHUNK_PAGES, n_pages - p0);
+        RT_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[c], 0));
+        retto_b200_results r;
+        retto_b200_status s = run_pages_once(ctx, dev_pages.data() + p0, np, forward, user, &r);
+        if (s != RETTO_B200_OK && s != RETTO_B200_ERR_DEGENERATE_QUAD && s != RETTO_B200_ERR_CAPACITY) { cudaStreamSynchronize(ctx->copy_stream); return s; }
+        if (s != RETTO_B200_OK) ret = s;
+        const int line0 = (int)a_boxes.size();
+        for (int i = 0; i < r.n_pages; ++i) {
+            retto_b200_page_result pr = r.pages[i];
+            pr.first_line += line0;
+            a_pages.push_back(pr);
+        }
+        a_boxes.insert(a_boxes.end(), r.boxes, r.boxes + r.n_lines);
+        a_cls.insert(a_cls.end(), r.cls, r.cls + r.n_lines);
+        a_scores.insert(a_scores.end(), r.rec_scores, r.rec_scores + r.n_lines);
+        const uint32_t t0 = a_toffs.back();
+        for (int k = 0; k < r.n_lines; ++k) a_toffs.push_back(t0 + r.text_offsets[k + 1]);
+        if (r.n_lines) a_text.insert(a_text.end(), r.text, r.text + r.text_offsets[r.n_lines]);
+        for (int k = 0; k < 8; ++k) stats[k] += ctx->run_stats[k];
+    }
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    memcpy(ctx->run_stats, stats, sizeof(stats));
+    a_text.push_back(0);
+    ctx->r_pages.swap(a_pages); ctx->r_boxes.swap(a_boxes); ctx->r_cls.swap(a_cls);
+    ctx->r_text_offs.swap(a_toffs); ctx->r_text.swap(a_text); ctx->r_scores.swap(a_scores);
+    out->n_pages = n_pages;
+    out->pages = ctx->r_pages.data();
+    out->n_lines = (int)ctx->r_boxes.size();
+    out->boxes = ctx->r_boxes.data();
+    out->cls = ctx->r_cls.data();
+    out->text_offsets = ctx->r_text_offs.data();
+    out->text = ctx->r_text.data();
+    out->rec_scores = ctx->r_scores.data();
     return ret;
 }
 

@@ -248,3 +248,48 @@ def test_session_empty_page(ctx, synth_dict):
     sess = _session(ctx, wk, synth_dict)
     r = sess.run(np.full((736, 736, 3), 255, np.uint8))
     assert r.status == 0 and r.det_result == [] and r.cls_result == [] and r.rec_result == []
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_session_chunked_pipeline_equals_unchunked(ctx, synth_dict, pinned):
+    """more host pages than one chunk take the chunked H2D/compute pipeline (csrc/session.cu): results must equal
+    page-by-page runs.  pinned pages are pulled by pull_pages_kernel, pageable ones by cudaMemcpyAsync."""
+    rng = np.random.default_rng(8)
+    imgs = []
+    for i in range(70):
+        im = np.full((160 + 8 * (i % 5), 240 + 16 * (i % 3), 3), 255, np.uint8)
+        for k in range(int(rng.integers(1, 4))):
+            y0, x0 = 20 + 40 * k, int(rng.integers(10, 60))
+            im[y0:y0 + int(rng.integers(10, 22)), x0:x0 + int(rng.integers(60, 150))] = int(rng.integers(0, 60))
+        if pinned:
+            import torch
+            im = torch.from_numpy(im).pin_memory().numpy()
+        imgs.append(im)
+
+    class W:   # stateless stand-ins: every output is a function of the input tensor only
+        def det(self, x):
+            g = (x[0].mean(axis=0) + 1.0) / 2.0
+            return np.clip(1.0 - g, 0.0, 1.0).astype(np.float32)[None, None]
+
+        def cls(self, x):
+            s = x.reshape(x.shape[0], -1).mean(axis=1)
+            return np.stack([np.where(s > s.mean(), 0.95, 0.05), np.where(s > s.mean(), 0.05, 0.95)], 1).astype(np.float32)
+
+        def rec(self, x):
+            n, T = x.shape[0], x.shape[3] // 8
+            out = np.zeros((n, T, 6625), np.float32)
+            for i in range(n):
+                rng2 = np.random.default_rng(zlib.crc32(np.ascontiguousarray(x[i]).tobytes()))
+                out[i, np.arange(T), rng2.integers(0, 6625, T)] = 0.5 + 0.5 * rng2.random(T, dtype=np.float32)
+            return out
+
+    sess = _session(ctx, W(), synth_dict)
+    batch = sess.run_pages(imgs)
+    assert len(batch) == 70 and sum(len(r.det_result) for r in batch) > 70
+    for i in (0, 1, 63, 64, 65, 69):
+        one = sess.run(imgs[i])
+        assert len(one.det_result) == len(batch[i].det_result)
+        for a, b in zip(one.det_result, batch[i].det_result):
+            assert np.array_equal(a.boxes, b.boxes) and a.score == b.score
+        assert [c.label for c in one.cls_result] == [c.label for c in batch[i].cls_result]
+        assert [r.text for r in one.rec_result] == [r.text for r in batch[i].rec_result]
