@@ -116,7 +116,7 @@ struct CropDev {
 };
 
 struct LineDev {
-    int crop, img_w, resized_w, pad;
+    int crop, img_w, resized_w, kind;   // kind: BB_FF / BB_BB / BB_BF / BB_GEN (rec_batch.cu)
     unsigned long long dst_offset;
 };
 

@@ -24,12 +24,28 @@ struct FlipReader {   // crops are stored RGBX, one aligned word per pixel
 // One block = one (line, 128-column chunk); one thread = one output column over all img_h rows.
 // Everything that depends only on x is computed once per thread, everything that depends only on y once per block
 // (shared memory); the normalisation `(px as f32 / 255 - .5) / .5` (image_helper.rs:200-203) comes from a 256-entry
-// table built with the same three correctly-rounded operations.  Text crops are 20-60 px tall, so both thumbnail
-// windows are at most 2 px wide almost always: that case runs a branch-light path on the 2x2 source pixels
-// (i0|i1) x (j0|j1) that evaluates exactly the expression of the matching imageops::thumbnail branch; larger
-// windows fall back to the generic thumbnail_pixel.
+// table built with the same three correctly-rounded operations.
+//
+// A line is classified on the host by its two scale ratios (x: crop_w / resized_w, y: crop_h / img_h); with a ratio
+// <= 1 every thumbnail window on that axis is a single pixel or a fractional pair, with a ratio >= 1 it is a block of
+// >= 1 pixels (thumbnail.cuh).  Each class runs a straight-line loop that evaluates exactly the expression of the
+// imageops::thumbnail branch it can meet — no per-pixel branch chain:
+//   BB_FF  x <= 1, y <= 1 (rec lines up to 48 px tall): all four branches collapse into the bilinear expression when a
+//          1-px block axis is given the weights (1, 0) — x*1 = x, x*0 = 0, 0 + a = a are exact in f32
+//   BB_BB  x >= 1, y >= 1 (taller lines): integer block mean (sum + n/2) / n, the division as a multiply-shift
+//   BB_BF  x >  1, y <  1 (cls: wide lines squeezed into 192 columns): column sums of the two rows mixed with
+//          (1-f)/n and f/n from a per-(row, n) table; rows that hit a source row exactly are 1 x n block means
+//   BB_GEN anything else: generic thumbnail_pixel
+// u8 -> f32 goes through the 2^23 mantissa trick (PRMT + FADD, exact) and f32 -> u8 truncation through FADD.RZ with
+// 2^23 (exact for 0 <= v < 2^23): both stay on the full-rate pipes instead of the quarter-rate conversion unit.
 #define BB_COLS 128
 #define BB_MAX_H 64
+#define BB_FF 0
+#define BB_BB 1
+#define BB_BF 2
+#define BB_GEN 3
+#define BB_BF_MAXN 8      // widest column block of the BF path (table width)
+#define BB_BB_MAXN 32     // largest nx*ny of the BB path (multiply-shift exact for n < 64, see magic_div20)
 struct ChunkDev { int line, x0; };
 struct AxisS {
     int i0, i1;      // the two source indices the window touches (i1 == i0 for a 1-px block)
@@ -42,107 +58,162 @@ __device__ __forceinline__ AxisS axis_small(const ThumbAxis a, unsigned size) {
     else { r.n = 0; r.i0 = (int)a.hi - 1; r.i1 = (int)((a.hi > size - 1) ? size - 1 : a.hi); r.fract = a.fract; }
     return r;
 }
-struct RowS { int o0, o1; int n; float fract, omf, ft1, fb1, ft2, fb2; };   // per output row (pixel offsets of rows j0/j1)
+// per output row, 16 B: pixel offsets of the two source rows (flip applied) + the vertical weights (FF/BF) or the
+// first row offset + row count (BB)
+struct RowS { int o0, o1; float fv, omv; };
 
-__global__ void __launch_bounds__(BB_COLS, 6) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
+// k23 = 0x4B000000 held in a register (opaque to the optimiser) so that the PRMT selector can be the immediate
+__device__ __forceinline__ float u8f(unsigned word, unsigned k23, unsigned sel) {   // exact float of byte `sel & 3` of word
+    return __fsub_rn(__uint_as_float(__byte_perm(word, k23, sel)), 8388608.0f);
+}
+__device__ __forceinline__ float u32f(unsigned v) {                   // exact float of v < 2^23
+    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
+}
+// lut[floor(v)] for 0 <= v < 256 (NumCast truncation): FADD.RZ leaves 0x4B000000 + floor(v) in the register; the shared
+// address is (bits << 2) + (lut - (0x4B000000 << 2)) in wrapping 32-bit arithmetic, so no mask is needed
+__device__ __forceinline__ float lut_trunc(float v, unsigned lut_biased) {
+    float r;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"((__float_as_uint(__fadd_rz(v, 8388608.0f)) << 2) + lut_biased));
+    return r;
+}
+// q = (s * M) >> 20 with M = ceil(2^20 / n) equals s / n whenever s * n < 2^20 (here s <= 255.5 n, n <= 32)
+__host__ __device__ inline unsigned magic_div20(unsigned n) { return ((1u << 20) + n - 1) / n; }
+
+struct BBShared {
+    float lut[256];
+    RowS row[BB_MAX_H];
+    ThumbAxis ay[BB_MAX_H];                 // BB_GEN only
+    float fb[BB_MAX_H][BB_BF_MAXN];         // BB_BF only: (1 - fract) / n and fract / n
+    float ft[BB_MAX_H][BB_BF_MAXN];
+    unsigned magic[BB_BB_MAXN + 1];
+};
+
+__global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
                                                                  const CropDev* __restrict__ crops, const unsigned char* __restrict__ crop_pix,
                                                                  const int* __restrict__ flip_flags, int use_flip, int img_h,
-                                                                 float* __restrict__ out) {
-    __shared__ float s_lut[256];
-    __shared__ ThumbAxis s_ay[BB_MAX_H];
-    __shared__ RowS s_row[BB_MAX_H];
+                                                                 float* __restrict__ out, const unsigned k23) {
+    // k23 = 0x4B000000 comes in as a kernel parameter: a literal would be folded by ptxas into the PRMT immediate slot,
+    // which pushes the byte selector into a register that has to be re-materialised for every conversion
+    __shared__ BBShared sh;
     const ChunkDev ck = chunks[blockIdx.x];
     const LineDev ln = lines[ck.line];
     const CropDev& c = crops[ln.crop];
     const unsigned cw = (unsigned)c.w, chh = (unsigned)c.h;
     const int flip = use_flip ? flip_flags[ln.crop] : 0;
-    for (int v = threadIdx.x; v < 256; v += BB_COLS) s_lut[v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), 0.5f), 0.5f);
+    const int kind = ln.kind;
+    for (int v = threadIdx.x; v < 256; v += BB_COLS) sh.lut[v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), 0.5f), 0.5f);
+    if (threadIdx.x <= BB_BB_MAXN) sh.magic[threadIdx.x] = threadIdx.x ? magic_div20(threadIdx.x) : 0u;
     const float yr = __fdiv_rn((float)chh, (float)img_h);
     for (int y = threadIdx.x; y < img_h; y += BB_COLS) {
         const ThumbAxis ay = thumb_axis(y, yr, chh);
-        s_ay[y] = ay;
-        const AxisS a = axis_small(ay, chh);
         RowS r;
-        const int j0 = flip ? (int)chh - 1 - a.i0 : a.i0, j1 = flip ? (int)chh - 1 - a.i1 : a.i1;
-        r.o0 = j0 * (int)cw; r.o1 = j1 * (int)cw; r.n = a.n; r.fract = a.fract; r.omf = __fsub_rn(1.0f, a.fract);
-        r.ft1 = a.fract; r.fb1 = r.omf;                                   // fract / 1, (1 - fract) / 1
-        r.ft2 = __fdiv_rn(a.fract, 2.0f); r.fb2 = __fdiv_rn(r.omf, 2.0f);
-        s_row[y] = r;
+        if (kind == BB_BB) {            // rows [lo, hi): the sums do not depend on the order, so a flip only moves the start
+            const int ny = (int)(ay.hi - ay.lo);
+            r.o0 = (flip ? (int)chh - (int)ay.hi : (int)ay.lo) * (int)cw;
+            r.o1 = ny; r.fv = 0.0f; r.omv = 0.0f;
+        } else {
+            const AxisS a = axis_small(ay, chh);
+            const int j0 = flip ? (int)chh - 1 - a.i0 : a.i0, j1 = flip ? (int)chh - 1 - a.i1 : a.i1;
+            r.o0 = j0 * (int)cw; r.o1 = j1 * (int)cw;
+            if (kind == BB_FF) { r.fv = a.n ? 0.0f : a.fract; r.omv = a.n ? 1.0f : __fsub_rn(1.0f, a.fract); }   // (1, 0) for a 1-px block row
+            else { r.fv = a.n ? -1.0f : a.fract; r.omv = __fsub_rn(1.0f, a.fract); }                              // fv < 0 marks a block row (BF)
+            if (kind == BB_BF)
+                for (int k = 0; k < BB_BF_MAXN; ++k) {
+                    sh.fb[y][k] = __fdiv_rn(r.omv, (float)(k + 1));
+                    sh.ft[y][k] = __fdiv_rn(a.fract, (float)(k + 1));
+                }
+            if (kind == BB_GEN) sh.ay[y] = ay;
+        }
+        sh.row[y] = r;
     }
     __syncthreads();
     const int x = ck.x0 + threadIdx.x;
     if (x >= ln.img_w) return;
-    const size_t plane = (size_t)img_h * ln.img_w;
-    float* dst = out + ln.dst_offset + x;
+    const int stride = ln.img_w;
+    const size_t plane = (size_t)img_h * stride;
+    float* d0 = out + ln.dst_offset + x;
+    float* d1 = d0 + plane;
+    float* d2 = d1 + plane;
     if (x >= ln.resized_w) {
-        for (int y = 0; y < img_h; ++y) {
-            float* d = dst + (size_t)y * ln.img_w;
-            d[0] = 0.0f; d[plane] = 0.0f; d[2 * plane] = 0.0f;
+        for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) { *d0 = 0.0f; *d1 = 0.0f; *d2 = 0.0f; }
+        return;
+    }
+    const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(crop_pix + c.offset);   // RGBX words
+    const unsigned lut_biased = (unsigned)__cvta_generic_to_shared(sh.lut) - (k23 << 2);
+    const float xr = __fdiv_rn((float)cw, (float)ln.resized_w);
+    const ThumbAxis ax = thumb_axis(x, xr, cw);
+
+    if (kind == BB_FF) {
+        const AxisS xs = axis_small(ax, cw);
+        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - 1 - xs.i0 : xs.i0);
+        const unsigned* __restrict__ s1 = src + (flip ? (int)cw - 1 - xs.i1 : xs.i1);
+        const float fhu = xs.n ? 0.0f : xs.fract, omfhu = xs.n ? 1.0f : __fsub_rn(1.0f, xs.fract);
+#pragma unroll 2
+        for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
+            const RowS r = sh.row[y];
+            const unsigned p00 = __ldg(s0 + r.o0), p10 = __ldg(s1 + r.o0), p01 = __ldg(s0 + r.o1), p11 = __ldg(s1 + r.o1);
+            const float f_tr = __fmul_rn(r.fv, fhu), f_tl = __fmul_rn(r.fv, omfhu), f_br = __fmul_rn(r.omv, fhu), f_bl = __fmul_rn(r.omv, omfhu);
+#define RT_BL(sel) lut_trunc(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, u8f(p10, k23, sel)), __fmul_rn(f_tr, u8f(p11, k23, sel))), \
+                                                 __fmul_rn(f_bl, u8f(p00, k23, sel))), __fmul_rn(f_tl, u8f(p01, k23, sel))), lut_biased)
+            *d0 = RT_BL(0x7540u); *d1 = RT_BL(0x7541u); *d2 = RT_BL(0x7542u);
+#undef RT_BL
         }
         return;
     }
-    const uchar4* __restrict__ src = reinterpret_cast<const uchar4*>(crop_pix + c.offset);
-    const FlipReader rd{src, cw, chh, flip};
-    const float xr = __fdiv_rn((float)cw, (float)ln.resized_w);
-    const ThumbAxis ax = thumb_axis(x, xr, cw);
-    const AxisS xs = axis_small(ax, cw);
-    const int c0 = flip ? (int)cw - 1 - xs.i0 : xs.i0, c1 = flip ? (int)cw - 1 - xs.i1 : xs.i1;
-    const float fh = xs.fract, omfh = __fsub_rn(1.0f, fh);
-    const float fr1 = fh, fl1 = omfh, fr2 = __fdiv_rn(fh, 2.0f), fl2 = __fdiv_rn(omfh, 2.0f);
-    const float fhu = xs.n ? 0.0f : fh, omfhu = xs.n ? 1.0f : omfh;   // (1, 0) weights for a 1-px block column
-    // software pipeline: the four source pixels of row y+1 are in flight while row y is mixed and stored
-    float* d = dst;
-    const int stride = ln.img_w;
-    RowS r = s_row[0];
-    uchar4 p00 = __ldg(src + r.o0 + c0), p10 = __ldg(src + r.o0 + c1), p01 = __ldg(src + r.o1 + c0), p11 = __ldg(src + r.o1 + c1);
-#pragma unroll 2
-    for (int y = 0; y < img_h; ++y, d += stride) {
-        const RowS rn = s_row[(y + 1 < img_h) ? y + 1 : y];
-        const uchar4 n00 = __ldg(src + rn.o0 + c0), n10 = __ldg(src + rn.o0 + c1), n01 = __ldg(src + rn.o1 + c0), n11 = __ldg(src + rn.o1 + c1);
-        unsigned char px[3];
-        if (xs.n <= 1 && r.n <= 1) {
-            // Up-scaling regime (the common one: crops are shorter than 48 px): every window is a single pixel or a
-            // fractional pair, and all four imageops::thumbnail branches collapse into the bilinear expression when a
-            // 1-px block axis is given the weights (1, 0):  x*1 = x, x*0 = 0, 0 + a = a are exact, so
-            //   block/block -> p00;  h-fraction -> fl*p00 + fr*p10;  v-fraction -> fb*p00 + ft*p01   bit for bit.
-            // One divergence-free path for the whole warp.
-            const float fv = r.n ? 0.0f : r.fract, omv = r.n ? 1.0f : r.omf;
-            const float f_tr = __fmul_rn(fv, fhu), f_tl = __fmul_rn(fv, omfhu), f_br = __fmul_rn(omv, fhu), f_bl = __fmul_rn(omv, omfhu);
-#define RT_BL(ch) (unsigned char)__float2uint_rz(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, (float)p10.ch), __fmul_rn(f_tr, (float)p11.ch)), __fmul_rn(f_bl, (float)p00.ch)), __fmul_rn(f_tl, (float)p01.ch)))
-            px[0] = RT_BL(x); px[1] = RT_BL(y); px[2] = RT_BL(z);
-#undef RT_BL
-        } else if (xs.n > 2 || r.n > 2) {
-            thumbnail_pixel(rd, cw, chh, ax, s_ay[y], px);
-        } else if (xs.n > 0 && r.n > 0) {          // block mean over (1|2) x (1|2) pixels: (sum + n/2) / n
-            const unsigned n = (unsigned)(xs.n * r.n), h2 = n >> 1;
-            const unsigned w10 = xs.n > 1, w01 = r.n > 1, w11 = w10 & w01;
-            const unsigned sh = (n == 4) ? 2 : (n == 2) ? 1 : 0;   // n is 1, 2 or 4 here: the division is a shift
-            px[0] = (unsigned char)((p00.x + w10 * p10.x + w01 * p01.x + w11 * p11.x + h2) >> sh);
-            px[1] = (unsigned char)((p00.y + w10 * p10.y + w01 * p01.y + w11 * p11.y + h2) >> sh);
-            px[2] = (unsigned char)((p00.z + w10 * p10.z + w01 * p01.z + w11 * p11.z + h2) >> sh);
-        } else if (xs.n == 0 && r.n > 0) {  // horizontal fraction between columns i0,i1 summed over r.n rows
-            const float fl = r.n > 1 ? fl2 : fl1, fr = r.n > 1 ? fr2 : fr1;
-            const unsigned w01 = r.n > 1;
-#define RT_HF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fl, (float)(p00.ch + w01 * p01.ch)), __fmul_rn(fr, (float)(p10.ch + w01 * p11.ch))))
-            px[0] = RT_HF(x); px[1] = RT_HF(y); px[2] = RT_HF(z);
-#undef RT_HF
-        } else if (xs.n > 0 && r.n == 0) {  // vertical fraction between rows j0,j1 summed over xs.n columns
-            const float fb = xs.n > 1 ? r.fb2 : r.fb1, ft = xs.n > 1 ? r.ft2 : r.ft1;
-            const unsigned w10 = xs.n > 1;
-#define RT_VF(ch) f32_to_u8_numcast(__fadd_rn(__fmul_rn(fb, (float)(p00.ch + w10 * p10.ch)), __fmul_rn(ft, (float)(p01.ch + w10 * p11.ch))))
-            px[0] = RT_VF(x); px[1] = RT_VF(y); px[2] = RT_VF(z);
-#undef RT_VF
-        } else {                             // both fractional: bilinear on the 2x2
-            const float fv = r.fract;
-            const float f_tr = __fmul_rn(fv, fh), f_tl = __fmul_rn(fv, omfh), f_br = __fmul_rn(r.omf, fh), f_bl = __fmul_rn(r.omf, omfh);
-#define RT_BL(ch) f32_to_u8_numcast(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, (float)p10.ch), __fmul_rn(f_tr, (float)p11.ch)), __fmul_rn(f_bl, (float)p00.ch)), __fmul_rn(f_tl, (float)p01.ch)))
-            px[0] = RT_BL(x); px[1] = RT_BL(y); px[2] = RT_BL(z);
-#undef RT_BL
+    if (kind == BB_BB) {
+        const int nx = (int)(ax.hi - ax.lo);
+        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
+        for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
+            const RowS r = sh.row[y];
+            const int ny = r.o1;
+            const unsigned* __restrict__ p = s0 + r.o0;
+            unsigned a0 = 0, a1 = 0, a2 = 0;
+            for (int j = 0; j < ny; ++j, p += cw)
+                for (int i = 0; i < nx; ++i) {
+                    const unsigned w = __ldg(p + i);
+                    a0 = __dp4a(w, 0x00000001u, a0); a1 = __dp4a(w, 0x00000100u, a1); a2 = __dp4a(w, 0x00010000u, a2);
+                }
+            const unsigned n = (unsigned)(nx * ny), h2 = n >> 1, M = sh.magic[n];
+            *d0 = sh.lut[((a0 + h2) * M) >> 20];
+            *d1 = sh.lut[((a1 + h2) * M) >> 20];
+            *d2 = sh.lut[((a2 + h2) * M) >> 20];
         }
-        d[0] = s_lut[px[0]];
-        d[plane] = s_lut[px[1]];
-        d[2 * plane] = s_lut[px[2]];
-        r = rn; p00 = n00; p10 = n10; p01 = n01; p11 = n11;
+        return;
+    }
+    if (kind == BB_BF) {
+        const int nx = (int)(ax.hi - ax.lo);
+        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
+        const unsigned h2 = (unsigned)nx >> 1, M = sh.magic[nx];
+        for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
+            const RowS r = sh.row[y];
+            const unsigned* __restrict__ p = s0 + r.o0;
+            const unsigned* __restrict__ q = s0 + r.o1;
+            unsigned a0 = 0, a1 = 0, a2 = 0, c0 = 0, c1 = 0, c2 = 0;
+            for (int i = 0; i < nx; ++i) {
+                const unsigned w = __ldg(p + i), u = __ldg(q + i);
+                a0 = __dp4a(w, 0x00000001u, a0); a1 = __dp4a(w, 0x00000100u, a1); a2 = __dp4a(w, 0x00010000u, a2);
+                c0 = __dp4a(u, 0x00000001u, c0); c1 = __dp4a(u, 0x00000100u, c1); c2 = __dp4a(u, 0x00010000u, c2);
+            }
+            if (r.fv < 0.0f) {           // the window is one source row: 1 x nx block mean (block-uniform branch)
+                *d0 = sh.lut[((a0 + h2) * M) >> 20];
+                *d1 = sh.lut[((a1 + h2) * M) >> 20];
+                *d2 = sh.lut[((a2 + h2) * M) >> 20];
+            } else {
+                const float fb = sh.fb[y][nx - 1], ft = sh.ft[y][nx - 1];
+                *d0 = lut_trunc(__fadd_rn(__fmul_rn(fb, u32f(a0)), __fmul_rn(ft, u32f(c0))), lut_biased);
+                *d1 = lut_trunc(__fadd_rn(__fmul_rn(fb, u32f(a1)), __fmul_rn(ft, u32f(c1))), lut_biased);
+                *d2 = lut_trunc(__fadd_rn(__fmul_rn(fb, u32f(a2)), __fmul_rn(ft, u32f(c2))), lut_biased);
+            }
+        }
+        return;
+    }
+    {
+        const FlipReader rd{reinterpret_cast<const uchar4*>(src), cw, chh, flip};
+        for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
+            unsigned char px[3];
+            thumbnail_pixel(rd, cw, chh, ax, sh.ay[y], px);
+            *d0 = sh.lut[px[0]]; *d1 = sh.lut[px[1]]; *d2 = sh.lut[px[2]];
+        }
     }
 }
 
@@ -231,6 +302,7 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
     std::vector<LineDev> lines(n_lines);
     std::vector<ChunkDev> chunks;
     chunks.reserve((size_t)n_lines * 6);
+    const bool force_generic = getenv("RETTO_B200_BB_GENERIC") != nullptr;   // tests: every line through thumbnail_pixel
     for (int i = 0; i < n_lines; ++i) {
         const retto_b200_line_job& l = h_lines[i];
         if (l.crop < 0 || l.crop >= (int)ctx->crops.size() || l.img_w <= 0 || l.resized_w < 0 || l.resized_w > l.img_w ||
@@ -238,9 +310,20 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
             ctx->set_error("build_batches: bad line " + std::to_string(i));
             return RETTO_B200_ERR_INVALID_ARG;
         }
-        lines[i] = LineDev{l.crop, l.img_w, l.resized_w, 0, l.dst_offset};
+        // class of the line (see build_batches_kernel): integer comparisons decide on which side of 1 the f32 ratios fall
+        // (the division is correctly rounded and monotone), ceil(ratio) bounds every window length on that axis
+        const int cw = ctx->crops[l.crop].w, ch = ctx->crops[l.crop].h, rw = std::max(l.resized_w, 1);
+        const int nx_max = (cw + rw - 1) / rw, ny_max = (ch + img_h - 1) / img_h;
+        int kind = BB_GEN;
+        if (cw <= rw && ch <= img_h) kind = BB_FF;
+        else if (cw >= rw && ch >= img_h && nx_max * ny_max <= BB_BB_MAXN) kind = BB_BB;
+        else if (cw > rw && ch < img_h && nx_max <= BB_BF_MAXN) kind = BB_BF;
+        if (force_generic) kind = BB_GEN;
+        lines[i] = LineDev{l.crop, l.img_w, l.resized_w, kind, l.dst_offset};
         for (int x0 = 0; x0 < l.img_w; x0 += BB_COLS) chunks.push_back(ChunkDev{i, x0});
     }
+    // the slowest classes first: their blocks start early and the cheap ones fill the tail of the grid
+    std::stable_sort(chunks.begin(), chunks.end(), [&](const ChunkDev& a, const ChunkDev& b) { return lines[a.line].kind > lines[b.line].kind; });
     const size_t lb = (sizeof(LineDev) * n_lines + 15) & ~size_t(15);
     std::vector<char> blob(lb + sizeof(ChunkDev) * chunks.size());
     memcpy(blob.data(), lines.data(), sizeof(LineDev) * n_lines);
@@ -251,7 +334,7 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
     RT_LAUNCH_BEGIN(ctx, "build_batches_kernel");
     build_batches_kernel<<<(unsigned)chunks.size(), BB_COLS, 0, ctx->stream>>>(d_lines, d_chunks, ctx->d_crop_descs.as<CropDev>(),
                                                                              ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
-                                                                             kind == 1 ? 1 : 0, img_h, buf.as<float>());
+                                                                             kind == 1 ? 1 : 0, img_h, buf.as<float>(), 0x4B000000u);
     RT_LAUNCH_CHECK(ctx);
     return RETTO_B200_OK;
 }

@@ -154,6 +154,67 @@ def test_batches_and_cls_flip_parity(ctx):
     assert len({b.img_w for b in batches}) > 1
 
 
+@pytest.mark.parametrize("generic", [False, True])
+def test_batches_dims_matrix(ctx, generic, monkeypatch):
+    """K8 over a matrix of crop sizes that reaches every class of build_batches_kernel (rec_batch.cu): up-scaling on
+    both axes (FF), block means (BB: lines taller than 48 px), wide lines squeezed into 192 columns (BF), mixed /
+    very large windows (generic) — each bit-exact against the oracle's resize_norm_image, with and without the
+    180-degree flip, and once more with every line forced through the generic thumbnail_pixel path."""
+    import torch
+    from oracle import oracle as O
+    from oracle.pipeline import stable_order_desc_ratio
+    if generic:
+        monkeypatch.setenv("RETTO_B200_BB_GENERIC", "1")
+    else:
+        monkeypatch.delenv("RETTO_B200_BB_GENERIC", raising=False)
+    rng = np.random.default_rng(11)
+    page = rng.integers(0, 256, (1500, 2000, 3), dtype=np.uint8)
+    boxes = []
+    for h in (6, 20, 31, 47, 48, 49, 60, 76, 97, 130, 200, 420):
+        for w in (10, 40, 100, 191, 192, 193, 400, 777, 1100, 1900):
+            x0, y0 = int(rng.integers(3, 1996 - w)), int(rng.integers(3, 1496 - h))
+            boxes.append([[x0, y0], [x0 + w, y0], [x0 + w, y0 + h], [x0, y0 + h]])
+    boxes = np.array(boxes, np.float32)
+    g = _t(page)
+    torch.cuda.synchronize()
+    infos = ctx.crop_boxes([g], [0] * len(boxes), boxes)
+    crops = [O.get_crop_img(page, b) for b in boxes]
+    dims = [c.shape[:2] for c in crops]
+    order = stable_order_desc_ratio(dims)
+    lines, batches, total = ctx.plan_batches(0, infos)
+    assert [l.crop for l in lines] == order
+    base = ctx.build_batches(0, lines, total)
+    host = np.zeros(total, np.float32)
+    ctx._check(ctx._L.retto_b200_d2h(ctx._h, host.ctypes.data, base, total * 4))
+    ctx.sync()
+    for l in lines:
+        ref = O.resize_norm_image(crops[l.crop], (3, 48, 192), None)
+        got = host[l.dst_offset:l.dst_offset + 3 * 48 * 192].reshape(3, 48, 192)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"cls line crop {l.crop} dims {dims[l.crop]}"
+    # flip every third crop through the cls postprocess, then build the rec batches
+    n = len(lines)
+    logits = np.tile(np.array([[0.8, 0.2]], np.float32), (n, 1))
+    flipped = {c: (c % 3 == 0) for c in range(n)}
+    for k, l in enumerate(lines):
+        if flipped[l.crop]:
+            logits[k] = (0.05, 0.95)
+    gl = _t(logits)
+    torch.cuda.synchronize()
+    ctx.cls_postprocess(gl, [l.crop for l in lines])
+    lines, batches, total = ctx.plan_batches(1, infos)
+    base = ctx.build_batches(1, lines, total)
+    host = np.zeros(total, np.float32)
+    ctx._check(ctx._L.retto_b200_d2h(ctx._h, host.ctypes.data, base, total * 4))
+    ctx.sync()
+    for b in batches:
+        for k in range(b.n):
+            l = lines[b.first_line + k]
+            ref = O.resize_norm_image(crops[l.crop], (3, 48, 320), float(np.float32(b.max_wh_ratio)), flip180=flipped[l.crop])
+            assert ref.shape[2] == b.img_w == l.img_w
+            got = host[l.dst_offset:l.dst_offset + 3 * 48 * b.img_w].reshape(3, 48, b.img_w)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"rec line crop {l.crop} dims {dims[l.crop]} flip {flipped[l.crop]}"
+
+
 def _session(ctx, worker, synth_dict):
     from retto_b200.session import CallableWorker, RettoSession
     ctx.dict_load(synth_dict)
