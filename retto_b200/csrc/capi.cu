@@ -56,6 +56,8 @@ extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    if (c->ev_dp) cudaEventDestroy(c->ev_dp);
+    for (auto& sl : c->stage_slots) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     delete c;  // DevBuf / HostBuf members free their memory
     cudaStreamDestroy(s);
 }
@@ -137,8 +139,47 @@ extern "C" retto_b200_status retto_b200_kernel_times(retto_b200_ctx* c, char* bu
     return RETTO_B200_OK;
 }
 
-retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {
-    RT_CUDA_OK(ctx, dst.ensure(bytes ? bytes : 16, ctx->stream));
-    if (bytes) RT_CUDA_OK(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+// a free pinned staging slot of at least `bytes`: never used, or the copy that read it has completed
+retto_b200_status rt_stage_begin(retto_b200_ctx* ctx, size_t bytes, int* slot, void** p) {
+    int pick = -1;
+    for (size_t i = 0; i < ctx->stage_slots.size(); ++i) {
+        auto& sl = ctx->stage_slots[i];
+        if (sl.busy && cudaEventQuery(sl.ev) == cudaSuccess) sl.busy = false;
+        if (!sl.busy && (pick < 0 || (ctx->stage_slots[pick].cap < bytes && sl.cap > ctx->stage_slots[pick].cap))) pick = (int)i;
+    }
+    cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
+    if (pick < 0) {
+        retto_b200_ctx::StageSlot sl;
+        RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+        ctx->stage_slots.push_back(sl);
+        pick = (int)ctx->stage_slots.size() - 1;
+    }
+    auto& sl = ctx->stage_slots[pick];
+    if (sl.cap < bytes) {
+        if (sl.p) cudaFreeHost(sl.p);
+        sl.p = nullptr; sl.cap = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, 64 << 10);
+        RT_CUDA_OK(ctx, cudaHostAlloc(&sl.p, want, cudaHostAllocDefault));
+        sl.cap = want;
+    }
+    sl.busy = true;   // reserved until the commit's event completes
+    *slot = pick;
+    *p = sl.p;
     return RETTO_B200_OK;
+}
+// enqueue the H2D copy of a slot filled in place (no intermediate host copy)
+retto_b200_status rt_stage_commit(retto_b200_ctx* ctx, DevBuf& dst, int slot, size_t bytes) {
+    auto& sl = ctx->stage_slots[slot];
+    RT_CUDA_OK(ctx, dst.ensure(bytes ? bytes : 16, ctx->stream));
+    if (bytes) RT_CUDA_OK(ctx, cudaMemcpyAsync(dst.p, sl.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA_OK(ctx, cudaEventRecord(sl.ev, ctx->stream));
+    return RETTO_B200_OK;
+}
+retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {
+    if (!bytes) { RT_CUDA_OK(ctx, dst.ensure(16, ctx->stream)); return RETTO_B200_OK; }
+    int slot = -1;
+    void* p = nullptr;
+    RT_TRY(rt_stage_begin(ctx, bytes, &slot, &p));
+    memcpy(p, src, bytes);
+    return rt_stage_commit(ctx, dst, slot, bytes);
 }

@@ -169,8 +169,12 @@ struct retto_b200_ctx {
         timed.clear();
     }
 
-    // descriptor staging (device side; host side is pageable and snapshotted by cudaMemcpyAsync)
+    // descriptor staging: device side, and pinned host slots for rt_upload (a cudaMemcpyAsync from pageable memory
+    // larger than 64 KB waits for the stream to drain, which would serialise the host against the GPU)
     DevBuf d_stage, d_stage2, d_stage3;
+    struct StageSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool busy = false; };
+    std::vector<StageSlot> stage_slots;
+    HostBuf h_scale;   // deferred scale_and_clip read-back (session.cu)
 
     // dictionary (rec_processor.rs:29-46)
     std::vector<std::string> dict;
@@ -190,14 +194,19 @@ struct retto_b200_ctx {
     std::vector<int> dp_holes;   // per page: #hole borders of the last det_postprocess (components - Euler number)
     DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out, d_holes, d_hole_pages, d_key_at;
     HostBuf h_dp;
+    cudaEvent_t ev_dp = nullptr;   // behind the early counter read-back of det_postprocess
 
     // crops
-    std::vector<CropDev> crops;
+    struct CropHost { int w, h, rot, status; unsigned long long offset; };   // host view of the current crop set
+    std::vector<CropHost> crops;
     DevBuf d_crop_descs, d_crop_pix, d_crop_flip;
     HostBuf h_crops;
 
     // batches
-    DevBuf d_lines, d_batch_cls, d_batch_rec;
+    DevBuf d_lines, d_lines_rec, d_batch_cls, d_batch_rec;
+    std::vector<LineDev> bb_lines;            // build_batches host scratch (prepare -> launch, per kind: 0 cls, 1 rec)
+    std::vector<char> bb_blob;
+    size_t bb_chunks[2] = {0, 0}, bb_chunk_off[2] = {0, 0};
     DevBuf d_cls_idx, d_cls_out;
     HostBuf h_cls;
 
@@ -231,9 +240,12 @@ struct retto_b200_ctx {
         }                                                                                         \
     } while (0)
 
-// copy a host descriptor array to the device (async on the stream; the source is pageable host
-// memory, which cudaMemcpyAsync snapshots before returning, so callers may reuse it immediately)
+// copy a host descriptor array to the device, asynchronously on the stream: the bytes are snapshotted into a pinned
+// staging slot (recycled once the event recorded behind its copy has completed), so callers may reuse `src` at once
 retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes);
+// the same in two steps, for tables that are built in place in the pinned slot
+retto_b200_status rt_stage_begin(retto_b200_ctx* ctx, size_t bytes, int* slot, void** p);
+retto_b200_status rt_stage_commit(retto_b200_ctx* ctx, DevBuf& dst, int slot, size_t bytes);
 
 // binary search: largest p with prefix[p] <= v   (prefix has n+1 entries, prefix[0] = 0)
 __device__ __forceinline__ int rt_find_segment(const int* __restrict__ prefix, int n, int v) {

@@ -192,44 +192,49 @@ void rt_crop_dims(const float box[8], int* cw, int* ch, int* rot) {
     *ch = r ? (int)w : (int)h;
 }
 
-// async part: descriptors up, projection setup + row kernel enqueued, descriptor read-back enqueued (no sync)
-retto_b200_status rt_crop_launch(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int n, retto_b200_crop_info* h_infos) {
+// async part: descriptors built in place in a pinned staging slot and uploaded, projection setup + row kernel
+// enqueued, status read-back enqueued (no sync).  `get(i, &page, &page_h, &page_w)` returns the box of crop i.
+template <class Get>
+static retto_b200_status crop_launch_impl(retto_b200_ctx* ctx, int n, retto_b200_crop_info* h_infos, Get get) {
     ctx->crops.clear();
     if (n == 0) return RETTO_B200_OK;
-    std::vector<int> prefix(n + 1, 0);
+    ctx->crops.resize(n);
+    const size_t desc_bytes = sizeof(CropDev) * (size_t)n, blob_bytes = desc_bytes + sizeof(int) * ((size_t)n + 1);
+    int slot = -1;
+    void* sp = nullptr;
+    RT_TRY(rt_stage_begin(ctx, blob_bytes, &slot, &sp));
+    CropDev* hd = reinterpret_cast<CropDev*>(sp);
+    int* prefix = reinterpret_cast<int*>(reinterpret_cast<char*>(sp) + desc_bytes);
+    prefix[0] = 0;
     unsigned long long off = 0;
     for (int i = 0; i < n; ++i) {
-        const retto_b200_crop_job& j = h_jobs[i];
-        if (!j.d_page || j.page_h <= 0 || j.page_w <= 0) { ctx->set_error("crop_boxes: bad job " + std::to_string(i)); return RETTO_B200_ERR_INVALID_ARG; }
-        CropDev c;
-        memset(&c, 0, sizeof(c));
-        c.page = j.d_page; c.page_h = j.page_h; c.page_w = j.page_w;
-        memcpy(c.box, j.box.xy, sizeof(float) * 8);
+        CropDev& c = hd[i];
+        const float* box = get(i, &c.page, &c.page_h, &c.page_w);
+        if (!c.page || c.page_h <= 0 || c.page_w <= 0) { ctx->stage_slots[slot].busy = false; ctx->crops.clear(); ctx->set_error("crop_boxes: bad job " + std::to_string(i)); return RETTO_B200_ERR_INVALID_ARG; }
+        memcpy(c.box, box, sizeof(float) * 8);
+        for (int k = 0; k < 9; ++k) c.t[k] = 0.0f;
+        c.cls = 0;
         rt_crop_dims(c.box, &c.w, &c.h, &c.rot);
+        c.status = RETTO_B200_OK;
         c.offset = off;
         const long long px = (long long)c.w * c.h;
         const int rows = c.rot ? c.w : c.h;
         if (px <= 0 || px > 0x3fffffffLL || prefix[i] + (long long)rows > 0x7fffffffLL) { c.status = RETTO_B200_ERR_DEGENERATE_QUAD; c.w = c.h = 0; prefix[i + 1] = prefix[i]; }
         else { prefix[i + 1] = prefix[i] + rows; off += ((unsigned long long)px * 4 + 15) & ~15ULL; }   // crops are stored RGBX (4 B/px): one aligned word per pixel
-        ctx->crops.push_back(c);
+        ctx->crops[i] = retto_b200_ctx::CropHost{c.w, c.h, c.rot, c.status, c.offset};
         h_infos[i].w = c.w; h_infos[i].h = c.h; h_infos[i].rotated270 = c.rot; h_infos[i].status = c.status; h_infos[i].offset = c.offset;
     }
+    const int rows = prefix[n];
     cudaStream_t st = ctx->stream;
     RT_CUDA_OK(ctx, ctx->d_crop_pix.ensure((size_t)std::max<unsigned long long>(off, 16), st));
     RT_CUDA_OK(ctx, ctx->d_crop_flip.ensure(sizeof(int) * (size_t)n, st));
     RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_crop_flip.p, 0, sizeof(int) * (size_t)n, st));
-    {
-        std::vector<char> blob(sizeof(CropDev) * n + sizeof(int) * (n + 1));
-        memcpy(blob.data(), ctx->crops.data(), sizeof(CropDev) * n);
-        memcpy(blob.data() + sizeof(CropDev) * n, prefix.data(), sizeof(int) * (n + 1));
-        RT_TRY(rt_upload(ctx, ctx->d_crop_descs, blob.data(), blob.size()));
-    }
+    RT_TRY(rt_stage_commit(ctx, ctx->d_crop_descs, slot, blob_bytes));
     CropDev* d_crops = ctx->d_crop_descs.as<CropDev>();
-    const int* d_prefix = reinterpret_cast<const int*>(ctx->d_crop_descs.as<char>() + sizeof(CropDev) * n);
+    const int* d_prefix = reinterpret_cast<const int*>(ctx->d_crop_descs.as<char>() + desc_bytes);
     RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
     crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n);
     RT_LAUNCH_CHECK(ctx);
-    const int rows = prefix[n];
     if (rows > 0) {
         RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
         crop_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>());
@@ -240,11 +245,28 @@ retto_b200_status rt_crop_launch(retto_b200_ctx* ctx, const retto_b200_crop_job*
     RT_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_crops.p, sizeof(int), &d_crops[0].status, sizeof(CropDev), sizeof(int), n, cudaMemcpyDeviceToHost, st));
     return RETTO_B200_OK;
 }
-// sync + statuses
-retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos) {
+retto_b200_status rt_crop_launch(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int n, retto_b200_crop_info* h_infos) {
+    return crop_launch_impl(ctx, n, h_infos, [&](int i, const uint8_t** page, int* ph, int* pw) -> const float* {
+        *page = h_jobs[i].d_page; *ph = h_jobs[i].page_h; *pw = h_jobs[i].page_w;
+        return h_jobs[i].box.xy;
+    });
+}
+// session variant: boxes in page order (box_off[p] .. box_off[p+1]), one page descriptor per page — no job array
+retto_b200_status rt_crop_launch_pages(retto_b200_ctx* ctx, const retto_b200_box* h_boxes, const int32_t* box_off, int n_pages,
+                                       const uint8_t* const* page_ptr, const int* page_h, const int* page_w, retto_b200_crop_info* h_infos) {
+    int p = 0;
+    return crop_launch_impl(ctx, box_off[n_pages], h_infos, [&](int i, const uint8_t** page, int* ph, int* pw) -> const float* {
+        while (i >= box_off[p + 1]) ++p;   // boxes are visited in order
+        *page = page_ptr[p]; *ph = page_h[p]; *pw = page_w[p];
+        return h_boxes[i].xy;
+    });
+}
+// statuses; do_sync == false when the caller has synchronised the stream since rt_crop_launch (session.cu defers this
+// to the end of the page batch so that the host keeps running ahead of the GPU)
+retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos, bool do_sync) {
     const int n = (int)ctx->crops.size();
     if (n == 0) return RETTO_B200_OK;
-    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (do_sync) RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     const int* hs = ctx->h_crops.as<int>();
     retto_b200_status ret = RETTO_B200_OK;
     for (int i = 0; i < n; ++i) {
@@ -259,7 +281,7 @@ extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const re
                                                    retto_b200_crop_info* h_infos) {
     if (!ctx || n < 0 || (n > 0 && (!h_jobs || !h_infos))) return RETTO_B200_ERR_INVALID_ARG;
     RT_TRY(rt_crop_launch(ctx, h_jobs, n, h_infos));
-    return rt_crop_finish(ctx, h_infos);
+    return rt_crop_finish(ctx, h_infos, true);
 }
 
 __global__ void crop_flip_copy_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int n_px, int flip) {
@@ -271,7 +293,7 @@ __global__ void crop_flip_copy_kernel(const unsigned char* __restrict__ src, uns
 
 extern "C" retto_b200_status retto_b200_crop_fetch(retto_b200_ctx* ctx, int32_t i, uint8_t* h_out) {
     if (!ctx || i < 0 || i >= (int)ctx->crops.size() || !h_out) return RETTO_B200_ERR_INVALID_ARG;
-    const CropDev& c = ctx->crops[i];
+    const retto_b200_ctx::CropHost& c = ctx->crops[i];
     const int n_px = c.w * c.h;
     if (n_px == 0) return RETTO_B200_OK;
     int flip = 0;

@@ -120,6 +120,49 @@ __global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __
     text_len[line] = tl;
 }
 
+// Packing of the decoded strings: the fixed-stride text buffer is mostly padding (stride = max_t * longest entry), so
+// instead of copying it back whole, one block scans the line lengths into byte offsets and a warp per line writes
+// its bytes at that offset — both straight into pinned, device-mapped host memory, so only the real text crosses PCIe
+// and the host needs no further copy after its stream sync.
+__global__ void __launch_bounds__(1024) ctc_text_scan_kernel(const int* __restrict__ text_len, int n_lines, unsigned* __restrict__ d_offs,
+                                                             unsigned* __restrict__ h_offs) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_run;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_run = 0; d_offs[0] = 0; h_offs[0] = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_lines; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < n_lines ? (unsigned)text_len[i] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            unsigned t = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            s_warp[lane] = t;   // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned incl = s_run + (w ? s_warp[w - 1] : 0u) + x;
+        if (i < n_lines) { d_offs[i + 1] = incl; h_offs[i + 1] = incl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = incl;
+        __syncthreads();
+    }
+}
+__global__ void ctc_text_pack_kernel(const unsigned char* __restrict__ text, const unsigned* __restrict__ d_offs, int n_lines, int text_stride,
+                                     unsigned char* __restrict__ h_text, unsigned capacity) {
+    const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (line >= n_lines) return;
+    const unsigned b = d_offs[line], e = d_offs[line + 1];
+    if (e > capacity) return;
+    const unsigned char* src = text + (size_t)line * text_stride;
+    for (unsigned k = lane; k < e - b; k += 32) h_text[b + k] = src[k];
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 static retto_b200_status ctc_prepare(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int n_descs, int C,
                                      std::vector<CtcTensor>& tensors, std::vector<int>& prefix, std::vector<int>& line_t, int* max_t) {
@@ -212,31 +255,41 @@ extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const re
         ctx->d_dict_bytes.as<unsigned char>(), (int)ctx->dict.size(), text_stride, ctx->d_ctc_tok.as<int>(), d_cnt,
         ctx->d_ctc_score.as<float>(), ctx->d_ctc_text.as<unsigned char>(), d_tlen);
     RT_LAUNCH_CHECK(ctx);
-    // results -> host
-    const size_t hbytes = sizeof(int) * nl * 4 + sizeof(float) * nl + nl * text_stride + (h_tokens ? sizeof(int) * nl * max_t : 0);
+    // results -> host: counters/scores by copy, offsets + packed text written by the pack kernels into mapped pinned memory
+    const size_t text_cap = nl * text_stride;
+    const size_t o_score = sizeof(int) * nl * 4, o_offs = o_score + sizeof(float) * nl, o_text = (o_offs + sizeof(unsigned) * (nl + 1) + 15) & ~size_t(15);
+    const size_t o_tok = (o_text + text_cap + 15) & ~size_t(15);
+    const size_t hbytes = o_tok + (h_tokens ? sizeof(int) * nl * max_t : 0);
     RT_CUDA_OK(ctx, ctx->h_ctc.ensure(hbytes));
+    RT_CUDA_OK(ctx, ctx->d_ctc_tlen.ensure(sizeof(unsigned) * (nl + 1), ctx->stream));
     char* hb = ctx->h_ctc.as<char>();
+    char* hb_dev = nullptr;
+    RT_CUDA_OK(ctx, cudaHostGetDevicePointer((void**)&hb_dev, hb, 0));
     int* hc = reinterpret_cast<int*>(hb);
-    float* hs = reinterpret_cast<float*>(hb + sizeof(int) * nl * 4);
-    unsigned char* ht = reinterpret_cast<unsigned char*>(hb + sizeof(int) * nl * 4 + sizeof(float) * nl);
-    int* htok = reinterpret_cast<int*>(hb + sizeof(int) * nl * 4 + sizeof(float) * nl + nl * text_stride);
+    float* hs = reinterpret_cast<float*>(hb + o_score);
+    const unsigned* hoff = reinterpret_cast<const unsigned*>(hb + o_offs);
+    const unsigned char* ht = reinterpret_cast<const unsigned char*>(hb + o_text);
+    int* htok = reinterpret_cast<int*>(hb + o_tok);
+    RT_LAUNCH_BEGIN(ctx, "ctc_text_scan_kernel");
+    ctc_text_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_tlen, n_lines, ctx->d_ctc_tlen.as<unsigned>(), reinterpret_cast<unsigned*>(hb_dev + o_offs));
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "ctc_text_pack_kernel");
+    ctc_text_pack_kernel<<<(n_lines + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_ctc_text.as<unsigned char>(), ctx->d_ctc_tlen.as<unsigned>(), n_lines, text_stride,
+                                                                     reinterpret_cast<unsigned char*>(hb_dev + o_text), (unsigned)std::min<size_t>(text_cap, 0xffffffffu));
+    RT_LAUNCH_CHECK(ctx);
     RT_CUDA_OK(ctx, cudaMemcpyAsync(hc, d_cnt, sizeof(int) * nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA_OK(ctx, cudaMemcpyAsync(hs, ctx->d_ctc_score.p, sizeof(float) * nl, cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(ht, ctx->d_ctc_text.p, nl * text_stride, cudaMemcpyDeviceToHost, ctx->stream));
     if (h_tokens) RT_CUDA_OK(ctx, cudaMemcpyAsync(htok, ctx->d_ctc_tok.p, sizeof(int) * nl * max_t, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     const int* h_cnt = hc;
-    const int* h_tlen = hc + nl;
     const int* h_nan = hc + 3 * nl;
-    size_t off = 0;
     retto_b200_status st = RETTO_B200_OK;
+    const size_t total_text = hoff[n_lines];
+    if (total_text > text_capacity) { ctx->set_error("ctc_decode: text buffer too small"); return RETTO_B200_ERR_CAPACITY; }
+    memcpy(h_text, ht, total_text);
     for (int i = 0; i < n_lines; ++i) {
         if (h_nan[i]) { ctx->set_error("ctc_decode: NaN logits in line " + std::to_string(i)); st = RETTO_B200_ERR_NAN_LOGITS; }
-        const size_t len = (size_t)h_tlen[i];
-        if (off + len > text_capacity) { ctx->set_error("ctc_decode: text buffer too small"); return RETTO_B200_ERR_CAPACITY; }
-        memcpy(h_text + off, ht + (size_t)i * text_stride, len);
-        off += len;
-        h_text_offsets[i + 1] = (uint32_t)off;
+        h_text_offsets[i + 1] = hoff[i + 1];
         h_scores[i] = hs[i];
         if (h_token_counts) h_token_counts[i] = h_cnt[i];
         if (h_tokens) {

@@ -855,17 +855,29 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     RT_LAUNCH_BEGIN(ctx, "comp_sort_kernel");
     comp_sort_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_roots, d_comps, d_cid, d_key, d_rowtab, max_comps);
     RT_LAUNCH_CHECK(ctx);
+    // The geometry grid and the hole-border decision need the per-page component counts (n_roots, euler, status), which
+    // are final after comp_sort: their read-back is enqueued BEFORE the row-extreme kernel and the host waits on an
+    // event behind the copy only, so the round trip hides under run_end_kernel instead of idling the GPU.
+    const int cap = std::max(max_boxes_total, 0);
+    const size_t hdr_bytes = (sizeof(PageCounters) * n + sizeof(int) * (n + 1) + 63) & ~size_t(63);
+    RT_CUDA_OK(ctx, ctx->h_dp.ensure(2 * hdr_bytes + sizeof(retto_b200_box) * (size_t)std::max(cap, 1)));
+    PageCounters* h_cnt0 = ctx->h_dp.as<PageCounters>();                                                   // early snapshot
+    PageCounters* h_cnt = reinterpret_cast<PageCounters*>(ctx->h_dp.as<char>() + hdr_bytes);               // final
+    retto_b200_box* h_stage_boxes = reinterpret_cast<retto_b200_box*>(ctx->h_dp.as<char>() + 2 * hdr_bytes);
+    if (!ctx->ev_dp) RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_dp, cudaEventDisableTiming));
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt0, d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
+    RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_dp, st));
     RT_LAUNCH_BEGIN(ctx, "run_end_kernel<1>");
     run_end_kernel<1><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
     RT_LAUNCH_CHECK(ctx);
-    // H needs the per-page component counts for its grid: size it by the host-known cap when small,
-    // else by a device->host read of the maximum (one tiny sync)
-    RT_CUDA_OK(ctx, ctx->h_dp.ensure(sizeof(PageCounters) * n + sizeof(int) * (n + 1)));
-    PageCounters* h_cnt = ctx->h_dp.as<PageCounters>();
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
-    RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    RT_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_dp));
     int max_n = 0;
-    for (int i = 0; i < n; ++i) max_n = std::max(max_n, std::min(h_cnt[i].n_roots, max_comps));
+    long long box_bound = 0;   // every box comes from one outer or one hole border
+    for (int i = 0; i < n; ++i) {
+        const int nr = std::min(h_cnt0[i].n_roots, max_comps);
+        max_n = std::max(max_n, nr);
+        box_bound += nr + std::min(std::max(h_cnt0[i].n_roots - h_cnt0[i].euler, 0), MAX_HOLES);
+    }
     if (max_n > 0) {
         GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
         dim3 grid((max_n + 3) / 4, n);
@@ -883,7 +895,7 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     {
         std::vector<int> fp, fpre{0};
         for (int i = 0; i < n; ++i)
-            if (h_cnt[i].status == RETTO_B200_OK && h_cnt[i].n_roots <= max_comps && h_cnt[i].n_roots - h_cnt[i].euler > 0) {
+            if (h_cnt0[i].status == RETTO_B200_OK && h_cnt0[i].n_roots <= max_comps && h_cnt0[i].n_roots - h_cnt0[i].euler > 0) {
                 fp.push_back(i);
                 fpre.push_back(fpre.back() + ctx->dp_pages[i].h * ctx->dp_pages[i].w);
             }
@@ -921,7 +933,7 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
             hole_rows_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab, d_cnt, d_comps, d_rowtab, max_comps);
             RT_LAUNCH_CHECK(ctx);
             int max_h = 0;
-            for (int i : fp) max_h = std::max(max_h, std::min(h_cnt[i].n_roots - h_cnt[i].euler, MAX_HOLES));
+            for (int i : fp) max_h = std::max(max_h, std::min(h_cnt0[i].n_roots - h_cnt0[i].euler, MAX_HOLES));
             GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
             const dim3 hg((max_h + 3) / 4, nf);
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
@@ -953,14 +965,15 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     RT_LAUNCH_BEGIN(ctx, "pack_offsets_kernel");
     pack_offsets_kernel<<<1, 32, 0, st>>>(n, d_cnt, d_offsets);
     RT_LAUNCH_CHECK(ctx);
-    const int cap = std::max(max_boxes_total, 0);
     RT_CUDA_OK(ctx, ctx->d_boxes_out.ensure(sizeof(retto_b200_box) * (size_t)std::max(cap, 1), st));
     RT_LAUNCH_BEGIN(ctx, "pack_boxes_kernel");
     pack_boxes_kernel<<<n, 128, 0, st>>>(n, d_cnt, d_offsets, d_cand, max_comps, ctx->d_boxes_out.as<retto_b200_box>(), cap);
     RT_LAUNCH_CHECK(ctx);
-    int* h_off = reinterpret_cast<int*>(ctx->h_dp.as<char>() + sizeof(PageCounters) * n);
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_off, d_offsets, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, st));
+    // one read-back, one sync: counters, offsets and the boxes (as many as the early counts allow for) into pinned memory
+    int* h_off = reinterpret_cast<int*>(reinterpret_cast<char*>(h_cnt) + sizeof(PageCounters) * n);
+    const int nspec = (int)std::min<long long>(box_bound, cap);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(PageCounters) * n + sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, st));
+    if (nspec > 0 && h_boxes) RT_CUDA_OK(ctx, cudaMemcpyAsync(h_stage_boxes, ctx->d_boxes_out.p, sizeof(retto_b200_box) * (size_t)nspec, cudaMemcpyDeviceToHost, st));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
     retto_b200_status ret = RETTO_B200_OK;
     for (int i = 0; i < n; ++i) {
@@ -980,8 +993,11 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     }
     const int ncopy = std::min(total, cap);
     if (ncopy > 0 && h_boxes) {
-        RT_CUDA_OK(ctx, cudaMemcpyAsync(h_boxes, ctx->d_boxes_out.p, sizeof(retto_b200_box) * (size_t)ncopy, cudaMemcpyDeviceToHost, st));
-        RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        if (ncopy > nspec) {   // cannot happen (box_bound is an upper bound); kept as a safe path
+            RT_CUDA_OK(ctx, cudaMemcpyAsync(h_stage_boxes, ctx->d_boxes_out.p, sizeof(retto_b200_box) * (size_t)ncopy, cudaMemcpyDeviceToHost, st));
+            RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        }
+        memcpy(h_boxes, h_stage_boxes, sizeof(retto_b200_box) * (size_t)ncopy);
     }
     return ret;
 }
@@ -1087,7 +1103,8 @@ __global__ void scale_clip_multi_kernel(retto_b200_box* b, const double4* __rest
         b[i].xy[2 * k + 1] = scale_clip_1(b[i].xy[2 * k + 1], p.y, p.w);
     }
 }
-retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h_boxes, const double* h_params4, int n) {
+// defer == true: the read-back lands in ctx->h_scale (pinned) and the caller copies it out after its next stream sync
+retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h_boxes, const double* h_params4, int n, bool defer) {
     if (n == 0) return RETTO_B200_OK;
     const size_t bb = (sizeof(retto_b200_box) * (size_t)n + 31) & ~size_t(31);
     std::vector<char> blob(bb + sizeof(double) * 4 * (size_t)n);
@@ -1098,6 +1115,11 @@ retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h
     scale_clip_multi_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_stage3.as<retto_b200_box>(),
                                                                       reinterpret_cast<const double4*>(ctx->d_stage3.as<char>() + bb), n);
     RT_LAUNCH_CHECK(ctx);
+    if (defer) {
+        RT_CUDA_OK(ctx, ctx->h_scale.ensure(sizeof(retto_b200_box) * (size_t)n));
+        RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scale.p, ctx->d_stage3.p, sizeof(retto_b200_box) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        return RETTO_B200_OK;
+    }
     RT_CUDA_OK(ctx, cudaMemcpyAsync(h_boxes, ctx->d_stage3.p, sizeof(retto_b200_box) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return RETTO_B200_OK;

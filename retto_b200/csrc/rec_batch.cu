@@ -290,19 +290,23 @@ extern "C" retto_b200_status retto_b200_plan_batches(const retto_b200_config* cf
     return RETTO_B200_OK;
 }
 
-extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32_t kind, const retto_b200_line_job* h_lines, int32_t n_lines,
-                                                      uint64_t total_floats, float** d_base) {
-    if (!ctx || n_lines < 0 || (n_lines > 0 && !h_lines) || !d_base) return RETTO_B200_ERR_INVALID_ARG;
+// Host half of build_batches: validate + classify the lines, cut them into 128-column chunks (bucketed by class, the
+// slowest class first so its blocks start early and the cheap ones fill the tail of the grid) and upload both tables.
+// Only host-known facts are used (crop dims), so the session prepares the cls AND the rec batches while the crop
+// kernels are still running; rt_build_batches_launch then only enqueues the kernel.
+retto_b200_status rt_build_batches_prepare(retto_b200_ctx* ctx, int32_t kind, const retto_b200_line_job* h_lines, int32_t n_lines,
+                                           uint64_t total_floats, float** d_base) {
     DevBuf& buf = kind == 0 ? ctx->d_batch_cls : ctx->d_batch_rec;
     RT_CUDA_OK(ctx, buf.ensure(std::max<size_t>((size_t)total_floats * 4, 16), ctx->stream));
     *d_base = buf.as<float>();
+    ctx->bb_chunks[kind] = 0;
     if (n_lines == 0) return RETTO_B200_OK;
     const int img_h = kind == 0 ? ctx->cfg.cls_image_shape[1] : ctx->cfg.rec_image_shape[1];
     if (img_h > BB_MAX_H) { ctx->set_error("build_batches: image_shape height > 64 is not supported"); return RETTO_B200_ERR_UNSUPPORTED; }
-    std::vector<LineDev> lines(n_lines);
-    std::vector<ChunkDev> chunks;
-    chunks.reserve((size_t)n_lines * 6);
     const bool force_generic = getenv("RETTO_B200_BB_GENERIC") != nullptr;   // tests: every line through thumbnail_pixel
+    size_t n_chunks[4] = {0, 0, 0, 0};
+    std::vector<LineDev>& lines = ctx->bb_lines;
+    lines.resize(n_lines);
     for (int i = 0; i < n_lines; ++i) {
         const retto_b200_line_job& l = h_lines[i];
         if (l.crop < 0 || l.crop >= (int)ctx->crops.size() || l.img_w <= 0 || l.resized_w < 0 || l.resized_w > l.img_w ||
@@ -314,29 +318,54 @@ extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32
         // (the division is correctly rounded and monotone), ceil(ratio) bounds every window length on that axis
         const int cw = ctx->crops[l.crop].w, ch = ctx->crops[l.crop].h, rw = std::max(l.resized_w, 1);
         const int nx_max = (cw + rw - 1) / rw, ny_max = (ch + img_h - 1) / img_h;
-        int kind = BB_GEN;
-        if (cw <= rw && ch <= img_h) kind = BB_FF;
-        else if (cw >= rw && ch >= img_h && nx_max * ny_max <= BB_BB_MAXN) kind = BB_BB;
-        else if (cw > rw && ch < img_h && nx_max <= BB_BF_MAXN) kind = BB_BF;
-        if (force_generic) kind = BB_GEN;
-        lines[i] = LineDev{l.crop, l.img_w, l.resized_w, kind, l.dst_offset};
-        for (int x0 = 0; x0 < l.img_w; x0 += BB_COLS) chunks.push_back(ChunkDev{i, x0});
+        int k = BB_GEN;
+        if (cw <= rw && ch <= img_h) k = BB_FF;
+        else if (cw >= rw && ch >= img_h && nx_max * ny_max <= BB_BB_MAXN) k = BB_BB;
+        else if (cw > rw && ch < img_h && nx_max <= BB_BF_MAXN) k = BB_BF;
+        if (force_generic) k = BB_GEN;
+        lines[i] = LineDev{l.crop, l.img_w, l.resized_w, k, l.dst_offset};
+        n_chunks[k] += (size_t)(l.img_w + BB_COLS - 1) / BB_COLS;
     }
-    // the slowest classes first: their blocks start early and the cheap ones fill the tail of the grid
-    std::stable_sort(chunks.begin(), chunks.end(), [&](const ChunkDev& a, const ChunkDev& b) { return lines[a.line].kind > lines[b.line].kind; });
+    const size_t total_chunks = n_chunks[0] + n_chunks[1] + n_chunks[2] + n_chunks[3];
     const size_t lb = (sizeof(LineDev) * n_lines + 15) & ~size_t(15);
-    std::vector<char> blob(lb + sizeof(ChunkDev) * chunks.size());
+    std::vector<char>& blob = ctx->bb_blob;
+    blob.resize(lb + sizeof(ChunkDev) * total_chunks);
     memcpy(blob.data(), lines.data(), sizeof(LineDev) * n_lines);
-    memcpy(blob.data() + lb, chunks.data(), sizeof(ChunkDev) * chunks.size());
-    RT_TRY(rt_upload(ctx, ctx->d_lines, blob.data(), blob.size()));
-    const LineDev* d_lines = ctx->d_lines.as<LineDev>();
-    const ChunkDev* d_chunks = reinterpret_cast<const ChunkDev*>(ctx->d_lines.as<char>() + lb);
-    RT_LAUNCH_BEGIN(ctx, "build_batches_kernel");
-    build_batches_kernel<<<(unsigned)chunks.size(), BB_COLS, 0, ctx->stream>>>(d_lines, d_chunks, ctx->d_crop_descs.as<CropDev>(),
-                                                                             ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
-                                                                             kind == 1 ? 1 : 0, img_h, buf.as<float>(), 0x4B000000u);
-    RT_LAUNCH_CHECK(ctx);
+    ChunkDev* ck = reinterpret_cast<ChunkDev*>(blob.data() + lb);
+    size_t cur[4];
+    cur[BB_GEN] = 0; cur[BB_BF] = n_chunks[BB_GEN]; cur[BB_BB] = cur[BB_BF] + n_chunks[BB_BF]; cur[BB_FF] = cur[BB_BB] + n_chunks[BB_BB];
+    for (int i = 0; i < n_lines; ++i) {
+        size_t& c = cur[lines[i].kind];
+        for (int x0 = 0; x0 < lines[i].img_w; x0 += BB_COLS) ck[c++] = ChunkDev{i, x0};
+    }
+    DevBuf& dl = kind == 0 ? ctx->d_lines : ctx->d_lines_rec;
+    RT_TRY(rt_upload(ctx, dl, blob.data(), blob.size()));
+    ctx->bb_chunks[kind] = total_chunks;
+    ctx->bb_chunk_off[kind] = lb;
     return RETTO_B200_OK;
+}
+
+retto_b200_status rt_build_batches_launch(retto_b200_ctx* ctx, int32_t kind) {
+    if (ctx->bb_chunks[kind] == 0) return RETTO_B200_OK;
+    DevBuf& buf = kind == 0 ? ctx->d_batch_cls : ctx->d_batch_rec;
+    DevBuf& dl = kind == 0 ? ctx->d_lines : ctx->d_lines_rec;
+    const int img_h = kind == 0 ? ctx->cfg.cls_image_shape[1] : ctx->cfg.rec_image_shape[1];
+    const LineDev* d_lines = dl.as<LineDev>();
+    const ChunkDev* d_chunks = reinterpret_cast<const ChunkDev*>(dl.as<char>() + ctx->bb_chunk_off[kind]);
+    RT_LAUNCH_BEGIN(ctx, "build_batches_kernel");
+    build_batches_kernel<<<(unsigned)ctx->bb_chunks[kind], BB_COLS, 0, ctx->stream>>>(d_lines, d_chunks, ctx->d_crop_descs.as<CropDev>(),
+                                                                                    ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
+                                                                                    kind == 1 ? 1 : 0, img_h, buf.as<float>(), 0x4B000000u);
+    RT_LAUNCH_CHECK(ctx);
+    ctx->bb_chunks[kind] = 0;
+    return RETTO_B200_OK;
+}
+
+extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32_t kind, const retto_b200_line_job* h_lines, int32_t n_lines,
+                                                      uint64_t total_floats, float** d_base) {
+    if (!ctx || n_lines < 0 || (n_lines > 0 && !h_lines) || !d_base || (kind != 0 && kind != 1)) return RETTO_B200_ERR_INVALID_ARG;
+    RT_TRY(rt_build_batches_prepare(ctx, kind, h_lines, n_lines, total_floats, d_base));
+    return rt_build_batches_launch(ctx, kind);
 }
 
 // enqueue K9 + the result read-back; with defer == true the caller collects after its next stream sync

@@ -6,12 +6,16 @@
 // touch host memory between stages; the forward passes are the caller's (worker.rs:69-73 seam).
 #include "common.cuh"
 
-retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h_boxes, const double* h_params4, int n);
+retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h_boxes, const double* h_params4, int n, bool defer);
 retto_b200_status rt_cls_postprocess_ptrs(retto_b200_ctx* ctx, const std::vector<const float*>& logits, const int32_t* crop_index, int n,
                                           retto_b200_cls_result* h_results, bool defer);
 retto_b200_status rt_cls_collect(retto_b200_ctx* ctx, int n, retto_b200_cls_result* h_results);
-retto_b200_status rt_crop_launch(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int n, retto_b200_crop_info* h_infos);
-retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos);
+retto_b200_status rt_build_batches_prepare(retto_b200_ctx* ctx, int32_t kind, const retto_b200_line_job* h_lines, int32_t n_lines,
+                                           uint64_t total_floats, float** d_base);
+retto_b200_status rt_build_batches_launch(retto_b200_ctx* ctx, int32_t kind);
+retto_b200_status rt_crop_launch_pages(retto_b200_ctx* ctx, const retto_b200_box* h_boxes, const int32_t* box_off, int n_pages,
+                                       const uint8_t* const* page_ptr, const int* page_h, const int* page_w, retto_b200_crop_info* h_infos);
+retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos, bool do_sync);
 
 #include <chrono>
 #define RUN_CHUNK_PAGES_MAX 64
@@ -185,14 +189,13 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
     // ---- 5. crops from the resize_both-ed page (session.rs:88-92) --------------------------------------------------
     std::vector<retto_b200_crop_info> infos(n_lines);
     {
-        std::vector<retto_b200_crop_job> jobs(n_lines);
-        for (int i = 0; i < n_pages; ++i)
-            for (int k = box_off[i]; k < box_off[i + 1]; ++k) {
-                jobs[k].d_page = ps[i].d_img; jobs[k].page_h = ps[i].h; jobs[k].page_w = ps[i].w;
-                jobs[k].box = ctx->r_boxes[k];
-            }
-        RT_TRY(rt_crop_launch(ctx, jobs.data(), n_lines, infos.data()));   // async: the host plans the batches meanwhile
+        std::vector<const uint8_t*> pp(n_pages);
+        std::vector<int> ph(n_pages), pw(n_pages);
+        for (int i = 0; i < n_pages; ++i) { pp[i] = ps[i].d_img; ph[i] = ps[i].h; pw[i] = ps[i].w; }
+        // async: the host plans the batches meanwhile
+        RT_TRY(rt_crop_launch_pages(ctx, ctx->r_boxes.data(), box_off.data(), n_pages, pp.data(), ph.data(), pw.data(), infos.data()));
     }
+    tr.mark("crop_launch");
     // ---- 7. cls (cls_processor.rs:127-172) ------------------------------------------------------------------------------
     auto plan_all = [&](int kind, std::vector<retto_b200_line_job>& lines, std::vector<retto_b200_batch>& batches, std::vector<int>& batch_page,
                         uint64_t* total) -> retto_b200_status {
@@ -217,12 +220,13 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
     std::vector<retto_b200_batch> batches, rec_batches;
     std::vector<int> batch_page, rec_batch_page;
     uint64_t total = 0, rec_total = 0;
-    // the plans depend only on the crop dims (known on the host): the cls plan overlaps with the crop kernels, the rec
-    // plan with the cls batch build
+    // From here to the CTC read-back nothing waits for the GPU: the plans depend only on the crop dims (known on the
+    // host), descriptor uploads go through pinned staging slots, and the crop statuses / cls results / rescaled boxes
+    // are collected after the one final sync — the host runs ahead and the kernels queue back to back.
     RT_TRY(plan_all(0, lines, batches, batch_page, &total));
-    RT_TRY(rt_crop_finish(ctx, infos.data()));
     tr.mark("crops+plans");
     // ---- 6. boxes back to original-image coordinates (session.rs:94-97) ----------------------------------------------
+    bool scaled = false;
     {
         bool any = false;
         std::vector<double> prm((size_t)n_lines * 4);
@@ -235,13 +239,17 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
                 prm[4 * (size_t)k + 3] = (double)ps[i].ori_h;
             }
         }
-        if (any) RT_TRY(rt_scale_and_clip_multi(ctx, ctx->r_boxes.data(), prm.data(), n_lines));
+        if (any) { RT_TRY(rt_scale_and_clip_multi(ctx, ctx->r_boxes.data(), prm.data(), n_lines, true)); scaled = true; }
     }
 
     tr.mark("scale");
-    float* d_base = nullptr;
-    RT_TRY(retto_b200_build_batches(ctx, 0, lines.data(), n_lines, total, &d_base));
-    RT_TRY(plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total));   // host work while the GPU builds the cls batches
+    float *d_base = nullptr, *d_base_rec = nullptr;
+    RT_TRY(rt_build_batches_prepare(ctx, 0, lines.data(), n_lines, total, &d_base));
+    RT_TRY(rt_build_batches_launch(ctx, 0));
+    tr.mark("cls_build");
+    // host work while the GPU crops and builds the cls batches: the rec plan and the rec descriptor tables
+    RT_TRY(plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total));
+    RT_TRY(rt_build_batches_prepare(ctx, 1, rec_lines.data(), n_lines, rec_total, &d_base_rec));
     {
         uint64_t det_px = 0, crop_px = 0, rec_rows = 0;
         for (int i = 0; i < n_pages; ++i) det_px += (uint64_t)ps[i].det_h * ps[i].det_w;
@@ -250,6 +258,7 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
         const uint64_t st8[8] = {(uint64_t)n_pages, (uint64_t)n_lines, det_px, crop_px, total, rec_total, rec_rows, 0};
         memcpy(ctx->run_stats, st8, sizeof(st8));
     }
+    tr.mark("rec_prepare");
     std::vector<int32_t> cls_crop_idx;
     std::vector<retto_b200_tensor> tin(batches.size()), tout(batches.size());
     auto fill_inputs = [&](int img_h) {
@@ -260,7 +269,6 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
             memset(&tout[b], 0, sizeof(retto_b200_tensor));
         }
     };
-    tr.mark("cls_build");
     fill_inputs(cfg.cls_image_shape[1]);
     if (forward(user, 1, (int)batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: cls forward failed"); return RETTO_B200_ERR_WORKER; }
     {
@@ -284,8 +292,8 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
 
     tr.mark("cls_fwd+post");
     // ---- 8. rec (rec_processor.rs:214-270) ---------------------------------------------------------------------------------
-    lines.swap(rec_lines); batches.swap(rec_batches); total = rec_total;
-    RT_TRY(retto_b200_build_batches(ctx, 1, lines.data(), n_lines, total, &d_base));
+    lines.swap(rec_lines); batches.swap(rec_batches); total = rec_total; d_base = d_base_rec;
+    RT_TRY(rt_build_batches_launch(ctx, 1));
     tin.assign(batches.size(), retto_b200_tensor{});
     tout.assign(batches.size(), retto_b200_tensor{});
     tr.mark("rec_build");
@@ -309,10 +317,12 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
         retto_b200_status s = retto_b200_ctc_decode(ctx, descs.data(), (int)descs.size(), (int)ctx->dict.size(), toff.data(), text.data(), text.size(),
                                                     sc.data(), nullptr, nullptr, 0);
         if (s != RETTO_B200_OK) return s;
-        {   // the CTC call synchronised the stream: the deferred cls results are on the host now
+        {   // the CTC call synchronised the stream: the deferred cls results, crop statuses and rescaled boxes are on the host now
             std::vector<retto_b200_cls_result> res(n_lines);
             RT_TRY(rt_cls_collect(ctx, n_lines, res.data()));
             for (int k = 0; k < n_lines; ++k) ctx->r_cls[cls_crop_idx[k]] = res[k];  // final_res[idx].label = label (cls_processor.rs:167)
+            if (scaled) memcpy(ctx->r_boxes.data(), ctx->h_scale.p, sizeof(retto_b200_box) * (size_t)n_lines);
+            RT_TRY(rt_crop_finish(ctx, infos.data(), false));
         }
         // scatter from plan order back to detection order (rec_processor.rs:259-264)
         std::vector<uint32_t> len(n_lines, 0);
