@@ -289,11 +289,21 @@ typedef struct retto_b200_results {
     const char* text;
     const float* rec_scores;
 } retto_b200_results;
-/* RettoSession::process_pipeline (session.rs:75-106) for n pages at once.  Stage callbacks fire in
- * the reference's order (all Det, then all Cls, then all Rec).  The returned pointers are owned by
- * the context and valid until the next run. */
+/* RettoSession::process_pipeline (session.rs:75-106) for n pages at once.  The returned pointers are owned by
+ * the context and valid until the next run.
+ * Host-resident batches are cut into units of pages whose upload overlaps the kernels of earlier units; with
+ * retto_b200_set_pipeline(ctx, 2, unit) two units are kept in flight on two internal lanes, software-pipelined
+ * from the calling thread.  Per unit the stage callbacks fire in the reference's
+ * order (Det, then Cls, then Rec — session.rs:98,101,104), always on the calling thread and never concurrently, but
+ * the calls of consecutive units interleave (Det(u0), Det(u1), Cls(u0), Rec(u0), ...) and each call names the CUDA
+ * stream its tensors are ordered on (`stream` argument of retto_b200_forward_fn) — the worker must enqueue on that
+ * stream.  Units cover consecutive page ranges in page order; results do not depend on the cut. */
 retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
                                        retto_b200_forward_fn forward, void* user, retto_b200_results* out);
+
+/* run_pages pipeline: lanes = 1 (default: units run back to back on the context's own stream) or 2;
+ * unit_pages = pages per unit (0 = default: 64 device-resident / 32 host-resident pages).  0 keeps the default. */
+retto_b200_status retto_b200_set_pipeline(retto_b200_ctx* ctx, int32_t lanes, int32_t unit_pages);
 
 /* sizes of the last retto_b200_run_pages call: out8 = {pages, lines, det tensor pixels, crop pixels, cls batch floats,
  * rec batch floats, rec logit rows (sum n*img_w/8), 0} — used by bench.py for algorithmic byte counts */

@@ -114,6 +114,7 @@ EXPORTS = [
     "retto_b200_det_post_fetch_trace", "retto_b200_scale_and_clip", "retto_b200_crop_boxes",
     "retto_b200_crop_fetch", "retto_b200_plan_batches", "retto_b200_build_batches", "retto_b200_cls_postprocess",
     "retto_b200_dict_load", "retto_b200_dict_size", "retto_b200_ctc_decode", "retto_b200_ctc_argmax", "retto_b200_run_pages", "retto_b200_last_run_stats",
+    "retto_b200_set_pipeline",
 ]
 
 
@@ -181,6 +182,7 @@ def lib() -> C.CDLL:
     L.retto_b200_ctc_decode.argtypes = [vp, C.POINTER(LogitsDesc), i32, i32, C.POINTER(C.c_uint32), vp, C.c_size_t, C.POINTER(C.c_float), C.POINTER(i32), C.POINTER(i32), i32]
     L.retto_b200_ctc_argmax.argtypes = [vp, C.POINTER(LogitsDesc), i32, i32, vp, vp]
     L.retto_b200_last_run_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.retto_b200_set_pipeline.argtypes = [vp, i32, i32]
     L.retto_b200_run_pages.argtypes = [vp, C.POINTER(Page), i32, FORWARD_FN, vp, C.POINTER(Results)]
     for name in EXPORTS:
         fn = getattr(L, name)

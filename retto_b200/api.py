@@ -97,6 +97,10 @@ class Context:
     def sync(self):
         self._check(self._L.retto_b200_sync(self._h))
 
+    def set_pipeline(self, lanes: int = 0, unit_pages: int = 0):
+        """run_pages pipeline: lanes 1 or 2 (0 = default 1), pages per unit (0 = default)"""
+        self._check(self._L.retto_b200_set_pipeline(self._h, int(lanes), int(unit_pages)))
+
     @property
     def launch_count(self) -> int:
         return int(self._L.retto_b200_launch_count(self._h))

@@ -49,6 +49,8 @@ extern "C" retto_b200_status retto_b200_create(int32_t device_id, const retto_b2
 
 extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
     if (!c) return;
+    for (retto_b200_ctx* l : c->lanes) retto_b200_destroy(l);
+    c->lanes.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStream_t s = c->stream;
@@ -64,7 +66,12 @@ extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
 
 extern "C" const char* retto_b200_last_error(const retto_b200_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" void* retto_b200_stream(retto_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
-extern "C" uint64_t retto_b200_launch_count(const retto_b200_ctx* c) { return c ? c->launches : 0; }
+extern "C" uint64_t retto_b200_launch_count(const retto_b200_ctx* c) {
+    if (!c) return 0;
+    uint64_t n = c->launches;
+    for (const retto_b200_ctx* l : c->lanes) n += l->launches;   // pipeline lanes of run_pages
+    return n;
+}
 
 extern "C" retto_b200_status retto_b200_sync(retto_b200_ctx* c) {
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
@@ -173,6 +180,16 @@ retto_b200_status rt_stage_commit(retto_b200_ctx* ctx, DevBuf& dst, int slot, si
     RT_CUDA_OK(ctx, dst.ensure(bytes ? bytes : 16, ctx->stream));
     if (bytes) RT_CUDA_OK(ctx, cudaMemcpyAsync(dst.p, sl.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
     RT_CUDA_OK(ctx, cudaEventRecord(sl.ev, ctx->stream));
+    return RETTO_B200_OK;
+}
+retto_b200_status rt_upload_to(retto_b200_ctx* ctx, void* d_dst, const void* src, size_t bytes) {
+    if (!bytes) return RETTO_B200_OK;
+    int slot = -1;
+    void* p = nullptr;
+    RT_TRY(rt_stage_begin(ctx, bytes, &slot, &p));
+    memcpy(p, src, bytes);
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(d_dst, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA_OK(ctx, cudaEventRecord(ctx->stage_slots[slot].ev, ctx->stream));
     return RETTO_B200_OK;
 }
 retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {

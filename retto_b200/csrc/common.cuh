@@ -184,6 +184,7 @@ struct retto_b200_ctx {
     // ctc scratch
     DevBuf d_ctc_rows, d_ctc_idx, d_ctc_prob, d_ctc_tok, d_ctc_cnt, d_ctc_score, d_ctc_text, d_ctc_tlen, d_ctc_flag;
     HostBuf h_ctc;
+    struct CtcRun { int n_lines = 0, max_t = 0; size_t o_score = 0, o_offs = 0, o_text = 0, o_tok = 0; bool want_tokens = false; } ctc;   // begin -> end state
 
     // det post state (kept for the fetch_* taps and for crop jobs)
     std::vector<DetPostPage> dp_pages;
@@ -195,6 +196,7 @@ struct retto_b200_ctx {
     DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out, d_holes, d_hole_pages, d_key_at;
     HostBuf h_dp;
     cudaEvent_t ev_dp = nullptr;   // behind the early counter read-back of det_postprocess
+    struct DpRun { int n = 0, cap = 0, total_tiles = 0, nspec = 0; size_t hdr_bytes = 0; } dp;   // begin -> mid -> end state
 
     // crops
     struct CropHost { int w, h, rot, status; unsigned long long offset; };   // host view of the current crop set
@@ -210,6 +212,11 @@ struct retto_b200_ctx {
     DevBuf d_cls_idx, d_cls_out;
     HostBuf h_cls;
 
+    // run_pages pipeline (session.cu): child contexts ("lanes") on the same device, and the tunables
+    std::vector<retto_b200_ctx*> lanes;
+    int pipe_lanes = 0, pipe_unit_pages = 0;     // 0 = default / environment
+    std::string dict_source;                     // raw dictionary text, replayed into the lanes
+    uint64_t dict_version = 0;
     // sizes of the last run_pages call (bench.py algorithmic bytes): pages, lines, det px, crop px, cls floats, rec floats, rec rows
     uint64_t run_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // session scratch
@@ -243,6 +250,7 @@ struct retto_b200_ctx {
 // copy a host descriptor array to the device, asynchronously on the stream: the bytes are snapshotted into a pinned
 // staging slot (recycled once the event recorded behind its copy has completed), so callers may reuse `src` at once
 retto_b200_status rt_upload(retto_b200_ctx* ctx, DevBuf& dst, const void* src, size_t bytes);
+retto_b200_status rt_upload_to(retto_b200_ctx* ctx, void* d_dst, const void* src, size_t bytes);   // into an existing device range
 // the same in two steps, for tables that are built in place in the pinned slot
 retto_b200_status rt_stage_begin(retto_b200_ctx* ctx, size_t bytes, int* slot, void** p);
 retto_b200_status rt_stage_commit(retto_b200_ctx* ctx, DevBuf& dst, int slot, size_t bytes);

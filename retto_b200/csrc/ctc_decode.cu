@@ -218,10 +218,14 @@ extern "C" retto_b200_status retto_b200_ctc_argmax(retto_b200_ctx* ctx, const re
     return ctc_run_argmax(ctx, tensors, prefix, num_classes, max_t, n_lines, d_idx, d_prob, ctx->d_ctc_flag.as<int>());
 }
 
-extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs,
-                                                   int32_t num_classes, uint32_t* h_text_offsets, char* h_text, size_t text_capacity,
-                                                   float* h_scores, int32_t* h_tokens, int32_t* h_token_counts, int32_t max_t_out) {
-    if (!ctx) return RETTO_B200_ERR_INVALID_ARG;
+// ctc_decode in two host steps (session.cu keeps several page batches in flight): begin enqueues argmax, collapse,
+// text packing and the read-backs; end synchronises the stream and hands the results to the caller's arrays.
+// want_tokens: also read the token ids back (max_t_out columns per line in rt_ctc_end).
+retto_b200_status rt_ctc_begin(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs, int32_t num_classes,
+                               bool want_tokens, int32_t max_t_out) {
+    retto_b200_ctx::CtcRun& R = ctx->ctc;
+    R = retto_b200_ctx::CtcRun{};
+    int32_t* const h_tokens = want_tokens ? reinterpret_cast<int32_t*>(1) : nullptr;   // only tested for null below
     if (ctx->dict.empty()) { ctx->set_error("ctc_decode: no dictionary loaded"); return RETTO_B200_ERR_NO_DICT; }
     if ((int)ctx->dict.size() != num_classes) {
         ctx->set_error("ctc_decode: num_classes " + std::to_string(num_classes) + " != dictionary size " + std::to_string(ctx->dict.size()));
@@ -232,7 +236,6 @@ extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const re
     int max_t = 1;
     RT_TRY(ctc_prepare(ctx, h_descs, n_descs, num_classes, tensors, prefix, line_t, &max_t));
     const int n_lines = (int)line_t.size();
-    h_text_offsets[0] = 0;
     if (n_lines == 0) return RETTO_B200_OK;
     if (h_tokens && max_t_out < max_t) { ctx->set_error("ctc_decode: max_t too small for token output"); return RETTO_B200_ERR_INVALID_ARG; }
     const int text_stride = max_t * std::max(ctx->dict_max_len, 1);
@@ -247,7 +250,7 @@ extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const re
     int* d_tlen = d_cnt + nl;
     int* d_linet = d_cnt + 2 * nl;
     int* d_nan = d_cnt + 3 * nl;
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(d_linet, line_t.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, ctx->stream));
+    RT_TRY(rt_upload_to(ctx, d_linet, line_t.data(), sizeof(int) * nl));
     RT_TRY(ctc_run_argmax(ctx, tensors, prefix, num_classes, max_t, n_lines, ctx->d_ctc_idx.as<int>(), ctx->d_ctc_prob.as<float>(), d_nan));
     RT_LAUNCH_BEGIN(ctx, "ctc_collapse_kernel");
     ctc_collapse_kernel<<<(n_lines + 127) / 128, 128, 0, ctx->stream>>>(
@@ -280,6 +283,24 @@ extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const re
     RT_CUDA_OK(ctx, cudaMemcpyAsync(hc, d_cnt, sizeof(int) * nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA_OK(ctx, cudaMemcpyAsync(hs, ctx->d_ctc_score.p, sizeof(float) * nl, cudaMemcpyDeviceToHost, ctx->stream));
     if (h_tokens) RT_CUDA_OK(ctx, cudaMemcpyAsync(htok, ctx->d_ctc_tok.p, sizeof(int) * nl * max_t, cudaMemcpyDeviceToHost, ctx->stream));
+    R.n_lines = n_lines; R.max_t = max_t; R.o_score = o_score; R.o_offs = o_offs; R.o_text = o_text; R.o_tok = o_tok; R.want_tokens = want_tokens;
+    return RETTO_B200_OK;
+}
+
+retto_b200_status rt_ctc_end(retto_b200_ctx* ctx, uint32_t* h_text_offsets, char* h_text, size_t text_capacity, float* h_scores,
+                             int32_t* h_tokens, int32_t* h_token_counts, int32_t max_t_out) {
+    const retto_b200_ctx::CtcRun& R = ctx->ctc;
+    h_text_offsets[0] = 0;
+    const int n_lines = R.n_lines, max_t = R.max_t;
+    if (n_lines == 0) return RETTO_B200_OK;
+    const size_t nl = (size_t)n_lines;
+    char* hb = ctx->h_ctc.as<char>();
+    int* hc = reinterpret_cast<int*>(hb);
+    float* hs = reinterpret_cast<float*>(hb + R.o_score);
+    const unsigned* hoff = reinterpret_cast<const unsigned*>(hb + R.o_offs);
+    const unsigned char* ht = reinterpret_cast<const unsigned char*>(hb + R.o_text);
+    int* htok = reinterpret_cast<int*>(hb + R.o_tok);
+    if (!R.want_tokens) h_tokens = nullptr;
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     const int* h_cnt = hc;
     const int* h_nan = hc + 3 * nl;
@@ -297,6 +318,14 @@ extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const re
         }
     }
     return st;
+}
+
+extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs,
+                                                   int32_t num_classes, uint32_t* h_text_offsets, char* h_text, size_t text_capacity,
+                                                   float* h_scores, int32_t* h_tokens, int32_t* h_token_counts, int32_t max_t_out) {
+    if (!ctx || !h_text_offsets) return RETTO_B200_ERR_INVALID_ARG;
+    RT_TRY(rt_ctc_begin(ctx, h_descs, n_descs, num_classes, h_tokens != nullptr, max_t_out));
+    return rt_ctc_end(ctx, h_text_offsets, h_text, text_capacity, h_scores, h_tokens, h_token_counts, max_t_out);
 }
 
 extern "C" retto_b200_status retto_b200_dict_load(retto_b200_ctx* ctx, const char* utf8, size_t len) {
@@ -358,6 +387,8 @@ extern "C" retto_b200_status retto_b200_dict_load(retto_b200_ctx* ctx, const cha
     RT_TRY(rt_upload(ctx, ctx->d_dict_bytes, bytes.data(), bytes.size()));
     ctx->dict = std::move(d);
     ctx->dict_max_len = mx;
+    if (utf8 != ctx->dict_source.data()) ctx->dict_source.assign(utf8 ? utf8 : "", len);
+    ctx->dict_version++;
     return RETTO_B200_OK;
 }
 

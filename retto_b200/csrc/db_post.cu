@@ -772,11 +772,16 @@ __global__ void zero_counters_kernel(PageCounters* c, int n) {
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------------
-extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, const retto_b200_det_post_desc* h_descs, int32_t n,
-                                                        int32_t* h_page_status, int32_t* h_box_offsets, retto_b200_box* h_boxes,
-                                                        int32_t max_boxes_total) {
-    if (!ctx || n < 0 || (n > 0 && (!h_descs || !h_page_status)) || !h_box_offsets) return RETTO_B200_ERR_INVALID_ARG;
-    h_box_offsets[0] = 0;
+// det_postprocess runs in three host steps so that a caller with several page batches in flight (session.cu lanes) can
+// do other work at the two points where the host needs numbers from the device:
+//   begin : threshold/dilate, CCL, component table, row extremes enqueued; early counter read-back behind an event
+//   mid   : waits for that event only (it hides under run_end_kernel), then geometry, hole borders, sort, pack and
+//           the result read-back are enqueued
+//   end   : one stream sync, results to the caller's arrays
+retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_post_desc* h_descs, int32_t n, int32_t max_boxes_total) {
+    retto_b200_ctx::DpRun& R = ctx->dp;
+    R = retto_b200_ctx::DpRun{};
+    R.n = n;
     ctx->dp_pages.clear();
     if (n == 0) return RETTO_B200_OK;
     const int max_comps = ctx->cfg.max_components_per_page;
@@ -870,6 +875,31 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     RT_LAUNCH_BEGIN(ctx, "run_end_kernel<1>");
     run_end_kernel<1><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
     RT_LAUNCH_CHECK(ctx);
+    R.cap = cap; R.total_tiles = total_tiles; R.hdr_bytes = hdr_bytes;
+    return RETTO_B200_OK;
+}
+
+retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
+    retto_b200_ctx::DpRun& R = ctx->dp;
+    const int n = R.n;
+    if (n == 0) return RETTO_B200_OK;
+    const int max_comps = ctx->cfg.max_components_per_page;
+    const int cap = R.cap;
+    cudaStream_t st = ctx->stream;
+    const DetPostPage* d_pages = ctx->d_dp_pages.as<DetPostPage>();
+    PageCounters* d_cnt = ctx->d_dp_counters.as<PageCounters>();
+    int* d_offsets = reinterpret_cast<int*>(ctx->d_dp_counters.as<char>() + sizeof(PageCounters) * n);
+    unsigned char* d_bm = ctx->d_bitmap.as<unsigned char>();
+    int* d_lab = ctx->d_labels.as<int>();
+    int* d_cid = ctx->d_cid_at.as<int>();
+    CompRec* d_comps = ctx->d_comps.as<CompRec>();
+    int2* d_rowtab = ctx->d_rowtab.as<int2>();
+    int2* d_hull = d_rowtab + (size_t)n * ROWCAP;
+    BoxCand* d_cand = ctx->d_cand.as<BoxCand>();
+    PageCounters* h_cnt0 = ctx->h_dp.as<PageCounters>();
+    PageCounters* h_cnt = reinterpret_cast<PageCounters*>(ctx->h_dp.as<char>() + R.hdr_bytes);
+    retto_b200_box* h_stage_boxes = reinterpret_cast<retto_b200_box*>(ctx->h_dp.as<char>() + 2 * R.hdr_bytes);
+    (void)d_bm; (void)d_lab; (void)d_cid; (void)d_comps; (void)d_rowtab; (void)d_hull; (void)d_cand; (void)h_cnt0; (void)h_cnt; (void)h_stage_boxes; (void)d_offsets; (void)max_comps; (void)cap; (void)st; (void)d_pages; (void)d_cnt;
     RT_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_dp));
     int max_n = 0;
     long long box_bound = 0;   // every box comes from one outer or one hole border
@@ -973,7 +1003,35 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
     int* h_off = reinterpret_cast<int*>(reinterpret_cast<char*>(h_cnt) + sizeof(PageCounters) * n);
     const int nspec = (int)std::min<long long>(box_bound, cap);
     RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(PageCounters) * n + sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, st));
-    if (nspec > 0 && h_boxes) RT_CUDA_OK(ctx, cudaMemcpyAsync(h_stage_boxes, ctx->d_boxes_out.p, sizeof(retto_b200_box) * (size_t)nspec, cudaMemcpyDeviceToHost, st));
+    if (nspec > 0) RT_CUDA_OK(ctx, cudaMemcpyAsync(h_stage_boxes, ctx->d_boxes_out.p, sizeof(retto_b200_box) * (size_t)nspec, cudaMemcpyDeviceToHost, st));
+    R.nspec = nspec;
+    return RETTO_B200_OK;
+}
+
+retto_b200_status rt_det_post_end(retto_b200_ctx* ctx, int32_t* h_page_status, int32_t* h_box_offsets, retto_b200_box* h_boxes) {
+    h_box_offsets[0] = 0;
+    retto_b200_ctx::DpRun& R = ctx->dp;
+    const int n = R.n;
+    if (n == 0) return RETTO_B200_OK;
+    const int max_comps = ctx->cfg.max_components_per_page;
+    const int cap = R.cap;
+    cudaStream_t st = ctx->stream;
+    const DetPostPage* d_pages = ctx->d_dp_pages.as<DetPostPage>();
+    PageCounters* d_cnt = ctx->d_dp_counters.as<PageCounters>();
+    int* d_offsets = reinterpret_cast<int*>(ctx->d_dp_counters.as<char>() + sizeof(PageCounters) * n);
+    unsigned char* d_bm = ctx->d_bitmap.as<unsigned char>();
+    int* d_lab = ctx->d_labels.as<int>();
+    int* d_cid = ctx->d_cid_at.as<int>();
+    CompRec* d_comps = ctx->d_comps.as<CompRec>();
+    int2* d_rowtab = ctx->d_rowtab.as<int2>();
+    int2* d_hull = d_rowtab + (size_t)n * ROWCAP;
+    BoxCand* d_cand = ctx->d_cand.as<BoxCand>();
+    PageCounters* h_cnt0 = ctx->h_dp.as<PageCounters>();
+    PageCounters* h_cnt = reinterpret_cast<PageCounters*>(ctx->h_dp.as<char>() + R.hdr_bytes);
+    retto_b200_box* h_stage_boxes = reinterpret_cast<retto_b200_box*>(ctx->h_dp.as<char>() + 2 * R.hdr_bytes);
+    (void)d_bm; (void)d_lab; (void)d_cid; (void)d_comps; (void)d_rowtab; (void)d_hull; (void)d_cand; (void)h_cnt0; (void)h_cnt; (void)h_stage_boxes; (void)d_offsets; (void)max_comps; (void)cap; (void)st; (void)d_pages; (void)d_cnt;
+    const int nspec = R.nspec;
+    int* h_off = reinterpret_cast<int*>(reinterpret_cast<char*>(h_cnt) + sizeof(PageCounters) * n);
     RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
     retto_b200_status ret = RETTO_B200_OK;
     for (int i = 0; i < n; ++i) {
@@ -1000,6 +1058,15 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
         memcpy(h_boxes, h_stage_boxes, sizeof(retto_b200_box) * (size_t)ncopy);
     }
     return ret;
+}
+
+extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, const retto_b200_det_post_desc* h_descs, int32_t n,
+                                                        int32_t* h_page_status, int32_t* h_box_offsets, retto_b200_box* h_boxes,
+                                                        int32_t max_boxes_total) {
+    if (!ctx || n < 0 || (n > 0 && (!h_descs || !h_page_status)) || !h_box_offsets) return RETTO_B200_ERR_INVALID_ARG;
+    RT_TRY(rt_det_post_begin(ctx, h_descs, n, max_boxes_total));
+    RT_TRY(rt_det_post_mid(ctx));
+    return rt_det_post_end(ctx, h_page_status, h_box_offsets, h_boxes);
 }
 
 extern "C" retto_b200_status retto_b200_det_post_fetch_bitmap(retto_b200_ctx* ctx, int32_t page, uint8_t* h_bitmap) {

@@ -4,6 +4,16 @@
 //   boxes.scale_and_clip to the original image -> cls.process (may flip crops) -> rec.process
 // with every stage executed once for the whole batch (one launch per kernel, not per page).  Pages never
 // touch host memory between stages; the forward passes are the caller's (worker.rs:69-73 seam).
+//
+// A batch is cut into units of pages; a unit is a resumable PageRun with three host steps (begin / mid / finish)
+// separated by the only points where the host needs numbers from the device (component counts, boxes, strings).
+// With retto_b200_set_pipeline(ctx, 2, unit) two units are kept in flight on two lanes (contexts with their own stream
+// and buffers), software-pipelined from ONE host thread: while the host waits for / post-processes one unit, the
+// kernels of the other are queued.  Measured on B200 this only pays for a continuous flow of units: a
+// 256-page batch that must drain at the end of the call is faster as one unit on one stream (6.4 ms vs 7.1 ms for
+// two units of 128), because the streams share the SMs evenly instead of letting the older unit run ahead — so the
+// default is one lane.  Results are concatenated in page order; pages are independent, so the results do not depend
+// on the cut.
 #include "common.cuh"
 
 retto_b200_status rt_scale_and_clip_multi(retto_b200_ctx* ctx, retto_b200_box* h_boxes, const double* h_params4, int n, bool defer);
@@ -16,8 +26,16 @@ retto_b200_status rt_build_batches_launch(retto_b200_ctx* ctx, int32_t kind);
 retto_b200_status rt_crop_launch_pages(retto_b200_ctx* ctx, const retto_b200_box* h_boxes, const int32_t* box_off, int n_pages,
                                        const uint8_t* const* page_ptr, const int* page_h, const int* page_w, retto_b200_crop_info* h_infos);
 retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos, bool do_sync);
+retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_post_desc* h_descs, int32_t n, int32_t max_boxes_total);
+retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx);
+retto_b200_status rt_det_post_end(retto_b200_ctx* ctx, int32_t* h_page_status, int32_t* h_box_offsets, retto_b200_box* h_boxes);
+retto_b200_status rt_ctc_begin(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs, int32_t num_classes,
+                               bool want_tokens, int32_t max_t_out);
+retto_b200_status rt_ctc_end(retto_b200_ctx* ctx, uint32_t* h_text_offsets, char* h_text, size_t text_capacity, float* h_scores,
+                             int32_t* h_tokens, int32_t* h_token_counts, int32_t max_t_out);
 
 #include <chrono>
+#include <memory>
 #define RUN_CHUNK_PAGES_MAX 64
 static int env_int(const char* name, int dflt, int lo, int hi) {
     const char* v = getenv(name);
@@ -53,27 +71,55 @@ struct PageState {
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 }  // namespace
 
-static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
-                                        retto_b200_forward_fn forward, void* user, retto_b200_results* out) {
-    if (!ctx || n_pages < 0 || (n_pages > 0 && !h_pages) || !forward || !out) return RETTO_B200_ERR_INVALID_ARG;
-    cudaStream_t st = ctx->stream;
+namespace {
+struct PageRun {
+    retto_b200_ctx* ctx = nullptr;          // the lane this unit runs on
+    const retto_b200_page* h_pages = nullptr;
+    int n_pages = 0;
+    retto_b200_forward_fn forward = nullptr;
+    void* user = nullptr;
+    cudaEvent_t wait_for = nullptr;         // pages uploaded by the copy stream (chunked host batches)
+    bool done = false;                      // finished early (no pages / no lines / error)
+    retto_b200_status ret = RETTO_B200_OK;
     HostTrace tr;
+    std::vector<PageState> ps;
+    std::vector<retto_b200_tensor> det_in, det_out, tin, tout;
+    std::vector<retto_b200_det_post_desc> dp_descs;
+    std::vector<int32_t> page_status, box_off, cls_crop_idx;
+    std::vector<retto_b200_crop_info> infos;
+    std::vector<retto_b200_line_job> lines, rec_lines;
+    std::vector<retto_b200_batch> batches, rec_batches;
+    std::vector<int> batch_page, rec_batch_page;
+    std::vector<uint32_t> toff;
+    std::vector<float> sc;
+    std::vector<char> text;
+    int n_lines = 0, det_cap = 0;
+    bool scaled = false;
+
+    retto_b200_status fail(retto_b200_status s) { done = true; ret = s; return s; }
+    retto_b200_status begin();
+    retto_b200_status mid();
+    retto_b200_status finish();
+    retto_b200_status plan_all(int kind, std::vector<retto_b200_line_job>& ln, std::vector<retto_b200_batch>& bt, std::vector<int>& bpage, uint64_t* total);
+};
+
+// ---- steps 1-4a: pages to the device, resize_both, det preprocess, worker.det, det postprocess up to the component table
+retto_b200_status PageRun::begin() {
+    cudaStream_t st = ctx->stream;
     const retto_b200_config& cfg = ctx->cfg;
     ctx->r_pages.assign(n_pages, retto_b200_page_result{0, 0, 0});
-    ctx->r_boxes.clear(); ctx->r_cls.clear(); ctx->r_text_offs.assign(1, 0); ctx->r_text.clear(); ctx->r_scores.clear();
-    memset(out, 0, sizeof(*out));
-    out->n_pages = n_pages;
-    out->pages = ctx->r_pages.data();
-    out->text_offsets = ctx->r_text_offs.data();
-    if (n_pages == 0) return RETTO_B200_OK;
+    ctx->r_boxes.clear(); ctx->r_cls.clear(); ctx->r_text_offs.assign(1, 0); ctx->r_text.assign(1, 0); ctx->r_scores.clear();
+    memset(ctx->run_stats, 0, sizeof(ctx->run_stats));
+    if (n_pages == 0) { done = true; return RETTO_B200_OK; }
+    if (wait_for) RT_CUDA_OK(ctx, cudaStreamWaitEvent(st, wait_for, 0));
 
     // ---- 1. pages to the device, resize_both (image_helper.rs:106-148) ------------------------------------
-    std::vector<PageState> ps(n_pages);
+    ps.resize(n_pages);
     size_t raw_bytes = 0, rs_bytes = 0, det_floats = 0;
     std::vector<std::vector<std::pair<int, int>>> rs_steps(n_pages);
     for (int i = 0; i < n_pages; ++i) {
         const retto_b200_page& p = h_pages[i];
-        if (!p.rgb || p.h <= 0 || p.w <= 0) { ctx->set_error("run_pages: bad page " + std::to_string(i)); return RETTO_B200_ERR_INVALID_ARG; }
+        if (!p.rgb || p.h <= 0 || p.w <= 0) { ctx->set_error("run_pages: bad page " + std::to_string(i)); return fail(RETTO_B200_ERR_INVALID_ARG); }
         ps[i].ori_h = p.h; ps[i].ori_w = p.w;
         if (!p.on_device) raw_bytes += align256((size_t)p.h * p.w * 3);
         int dims[4], ns = 0;
@@ -81,7 +127,7 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
         int h = p.h, w = p.w;
         for (int s = 0; s < ns; ++s) {
             h = dims[2 * s]; w = dims[2 * s + 1];
-            if (h <= 0 || w <= 0) { ctx->set_error("run_pages: page " + std::to_string(i) + " resizes to nothing"); return RETTO_B200_ERR_INVALID_ARG; }
+            if (h <= 0 || w <= 0) { ctx->set_error("run_pages: page " + std::to_string(i) + " resizes to nothing"); return fail(RETTO_B200_ERR_INVALID_ARG); }
             rs_steps[i].push_back({h, w});
             rs_bytes += align256((size_t)h * w * 3);
         }
@@ -90,7 +136,7 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
         if (ps[i].det_h <= 0 || ps[i].det_w <= 0 || ps[i].det_h > cfg.max_det_side || ps[i].det_w > cfg.max_det_side) {
             ctx->set_error("run_pages: det tensor of page " + std::to_string(i) + " is " + std::to_string(ps[i].det_h) + "x" + std::to_string(ps[i].det_w) +
                            " (cap max_det_side=" + std::to_string(cfg.max_det_side) + ")");
-            return RETTO_B200_ERR_CAPACITY;
+            return fail(RETTO_B200_ERR_CAPACITY);
         }
         det_floats += (align256((size_t)3 * ps[i].det_h * ps[i].det_w * 4)) / 4;
     }
@@ -121,10 +167,9 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
         if (!step1.empty()) RT_TRY(retto_b200_thumbnail(ctx, step1.data(), (int)step1.size()));
         if (!step2.empty()) RT_TRY(retto_b200_thumbnail(ctx, step2.data(), (int)step2.size()));
     }
-
     tr.mark("upload+resize");
     // ---- 2. det preprocess (det_processor.rs:256-274) --------------------------------------------------------
-    std::vector<retto_b200_tensor> det_in(n_pages), det_out(n_pages);
+    det_in.resize(n_pages); det_out.resize(n_pages);
     {
         std::vector<retto_b200_det_pre_desc> descs(n_pages);
         size_t off = 0;
@@ -141,34 +186,67 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
     }
     tr.mark("det_pre");
     // ---- 3. worker.det (session.rs:86) ------------------------------------------------------------------------
-    if (forward(user, 0, n_pages, det_in.data(), det_out.data(), (void*)st) != 0) { ctx->set_error("run_pages: det forward failed"); return RETTO_B200_ERR_WORKER; }
+    if (forward(user, 0, n_pages, det_in.data(), det_out.data(), (void*)st) != 0) { ctx->set_error("run_pages: det forward failed"); return fail(RETTO_B200_ERR_WORKER); }
     tr.mark("det_fwd");
-    // ---- 4. det postprocess (det_processor.rs:279-335) ----------------------------------------------------------
-    std::vector<int32_t> page_status(n_pages, 0), box_off(n_pages + 1, 0);
-    {
-        std::vector<retto_b200_det_post_desc> descs(n_pages);
-        for (int i = 0; i < n_pages; ++i) {
-            const retto_b200_tensor& t = det_out[i];
-            if (!t.d_data || t.ndim != 4 || t.shape[0] != 1 || t.shape[1] != 1 || t.shape[2] <= 0 || t.shape[3] <= 0) {
-                ctx->set_error("run_pages: det forward returned a bad tensor for page " + std::to_string(i));
-                return RETTO_B200_ERR_WORKER;
-            }
-            // DetProcessor::new(cfg, after_h, after_w): boxes are scaled to the resize_both-ed page (session.rs:85)
-            descs[i] = retto_b200_det_post_desc{t.d_data, (int32_t)t.shape[2], (int32_t)t.shape[3], ps[i].h, ps[i].w};
+    // ---- 4. det postprocess (det_processor.rs:279-335), first part ------------------------------------------------
+    page_status.assign(n_pages, 0); box_off.assign(n_pages + 1, 0);
+    dp_descs.resize(n_pages);
+    for (int i = 0; i < n_pages; ++i) {
+        const retto_b200_tensor& t = det_out[i];
+        if (!t.d_data || t.ndim != 4 || t.shape[0] != 1 || t.shape[1] != 1 || t.shape[2] <= 0 || t.shape[3] <= 0) {
+            ctx->set_error("run_pages: det forward returned a bad tensor for page " + std::to_string(i));
+            return fail(RETTO_B200_ERR_WORKER);
         }
-        int cap = std::max(4096, n_pages * 256);
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            ctx->r_boxes.resize(cap);
-            retto_b200_status s = retto_b200_det_postprocess(ctx, descs.data(), n_pages, page_status.data(), box_off.data(), ctx->r_boxes.data(), cap);
-            if (s == RETTO_B200_ERR_CAPACITY && box_off[n_pages] > cap && attempt == 0) { cap = box_off[n_pages]; continue; }
-            if (s != RETTO_B200_OK) return s;
-            break;
+        // DetProcessor::new(cfg, after_h, after_w): boxes are scaled to the resize_both-ed page (session.rs:85)
+        dp_descs[i] = retto_b200_det_post_desc{t.d_data, (int32_t)t.shape[2], (int32_t)t.shape[3], ps[i].h, ps[i].w};
+    }
+    det_cap = std::max(4096, n_pages * 256);
+    retto_b200_status s = rt_det_post_begin(ctx, dp_descs.data(), n_pages, det_cap);
+    if (s != RETTO_B200_OK) return fail(s);
+    tr.mark("det_post_begin");
+    return RETTO_B200_OK;
+}
+
+retto_b200_status PageRun::plan_all(int kind, std::vector<retto_b200_line_job>& ln, std::vector<retto_b200_batch>& bt, std::vector<int>& bpage, uint64_t* total) {
+    ln.assign(n_lines, retto_b200_line_job{});
+    bt.clear(); bpage.clear();
+    uint64_t off = 0;
+    std::vector<retto_b200_batch> pb;
+    for (int i = 0; i < n_pages; ++i) {
+        const int nb = box_off[i + 1] - box_off[i];
+        if (nb == 0) continue;
+        pb.assign((size_t)nb, retto_b200_batch{});
+        int32_t nbat = 0; uint64_t tot = 0;
+        RT_TRY(retto_b200_plan_batches(&ctx->cfg, kind, infos.data() + box_off[i], nb, ln.data() + box_off[i], pb.data(), &nbat, &tot));
+        for (int k = box_off[i]; k < box_off[i + 1]; ++k) { ln[k].crop += box_off[i]; ln[k].dst_offset += off; }
+        for (int b = 0; b < nbat; ++b) { pb[b].first_line += box_off[i]; pb[b].offset += off; bt.push_back(pb[b]); bpage.push_back(i); }
+        off += tot;
+    }
+    *total = off;
+    return RETTO_B200_OK;
+}
+
+// ---- steps 4b-8: geometry, boxes to the host, crops, cls, rec enqueued up to the CTC read-back
+retto_b200_status PageRun::mid() {
+    if (done) return ret;
+    cudaStream_t st = ctx->stream;
+    const retto_b200_config& cfg = ctx->cfg;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ctx->r_boxes.resize(det_cap);
+        retto_b200_status s = rt_det_post_mid(ctx);
+        if (s == RETTO_B200_OK) s = rt_det_post_end(ctx, page_status.data(), box_off.data(), ctx->r_boxes.data());
+        if (s == RETTO_B200_ERR_CAPACITY && box_off[n_pages] > det_cap && attempt == 0) {   // more boxes than planned for: redo with room
+            det_cap = box_off[n_pages];
+            s = rt_det_post_begin(ctx, dp_descs.data(), n_pages, det_cap);
+            if (s != RETTO_B200_OK) return fail(s);
+            continue;
         }
+        if (s != RETTO_B200_OK) return fail(s);
+        break;
     }
     tr.mark("det_post");
-    const int n_lines = box_off[n_pages];
+    n_lines = box_off[n_pages];
     ctx->r_boxes.resize(n_lines);
-    retto_b200_status ret = RETTO_B200_OK;
     for (int i = 0; i < n_pages; ++i) {
         ctx->r_pages[i].status = page_status[i];
         ctx->r_pages[i].first_line = box_off[i];
@@ -178,78 +256,49 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
     ctx->r_cls.assign(n_lines, retto_b200_cls_result{0, 0.0f});
     ctx->r_scores.assign(n_lines, 0.0f);
     ctx->r_text_offs.assign(n_lines + 1, 0);
-    out->n_lines = n_lines;
-    out->boxes = ctx->r_boxes.data();
-    out->cls = ctx->r_cls.data();
-    out->text_offsets = ctx->r_text_offs.data();
-    out->rec_scores = ctx->r_scores.data();
-    out->text = ctx->r_text.data();
-    if (n_lines == 0) return ret;
+    if (n_lines == 0) { done = true; return ret; }
 
     // ---- 5. crops from the resize_both-ed page (session.rs:88-92) --------------------------------------------------
-    std::vector<retto_b200_crop_info> infos(n_lines);
+    // From here to the CTC read-back nothing waits for the GPU: the plans depend only on the crop dims (known on the
+    // host), descriptor tables are built in pinned staging slots, and the crop statuses / cls results / rescaled boxes
+    // are collected after the one final sync — the host runs ahead and the kernels queue back to back.
+    infos.resize(n_lines);
     {
         std::vector<const uint8_t*> pp(n_pages);
         std::vector<int> ph(n_pages), pw(n_pages);
         for (int i = 0; i < n_pages; ++i) { pp[i] = ps[i].d_img; ph[i] = ps[i].h; pw[i] = ps[i].w; }
-        // async: the host plans the batches meanwhile
-        RT_TRY(rt_crop_launch_pages(ctx, ctx->r_boxes.data(), box_off.data(), n_pages, pp.data(), ph.data(), pw.data(), infos.data()));
+        retto_b200_status s = rt_crop_launch_pages(ctx, ctx->r_boxes.data(), box_off.data(), n_pages, pp.data(), ph.data(), pw.data(), infos.data());
+        if (s != RETTO_B200_OK) return fail(s);
     }
     tr.mark("crop_launch");
     // ---- 7. cls (cls_processor.rs:127-172) ------------------------------------------------------------------------------
-    auto plan_all = [&](int kind, std::vector<retto_b200_line_job>& lines, std::vector<retto_b200_batch>& batches, std::vector<int>& batch_page,
-                        uint64_t* total) -> retto_b200_status {
-        lines.assign(n_lines, retto_b200_line_job{});
-        batches.clear(); batch_page.clear();
-        uint64_t off = 0;
-        std::vector<retto_b200_batch> pb;
-        for (int i = 0; i < n_pages; ++i) {
-            const int nb = box_off[i + 1] - box_off[i];
-            if (nb == 0) continue;
-            pb.assign((size_t)nb, retto_b200_batch{});
-            int32_t nbat = 0; uint64_t tot = 0;
-            RT_TRY(retto_b200_plan_batches(&cfg, kind, infos.data() + box_off[i], nb, lines.data() + box_off[i], pb.data(), &nbat, &tot));
-            for (int k = box_off[i]; k < box_off[i + 1]; ++k) { lines[k].crop += box_off[i]; lines[k].dst_offset += off; }
-            for (int b = 0; b < nbat; ++b) { pb[b].first_line += box_off[i]; pb[b].offset += off; batches.push_back(pb[b]); batch_page.push_back(i); }
-            off += tot;
-        }
-        *total = off;
-        return RETTO_B200_OK;
-    };
-    std::vector<retto_b200_line_job> lines, rec_lines;
-    std::vector<retto_b200_batch> batches, rec_batches;
-    std::vector<int> batch_page, rec_batch_page;
     uint64_t total = 0, rec_total = 0;
-    // From here to the CTC read-back nothing waits for the GPU: the plans depend only on the crop dims (known on the
-    // host), descriptor uploads go through pinned staging slots, and the crop statuses / cls results / rescaled boxes
-    // are collected after the one final sync — the host runs ahead and the kernels queue back to back.
-    RT_TRY(plan_all(0, lines, batches, batch_page, &total));
-    tr.mark("crops+plans");
+    retto_b200_status s = plan_all(0, lines, batches, batch_page, &total);
+    if (s != RETTO_B200_OK) return fail(s);
+    float *d_base = nullptr, *d_base_rec = nullptr;
+    if ((s = rt_build_batches_prepare(ctx, 0, lines.data(), n_lines, total, &d_base)) != RETTO_B200_OK) return fail(s);
+    if ((s = rt_build_batches_launch(ctx, 0)) != RETTO_B200_OK) return fail(s);
+    tr.mark("cls_build");
     // ---- 6. boxes back to original-image coordinates (session.rs:94-97) ----------------------------------------------
-    bool scaled = false;
     {
         bool any = false;
-        std::vector<double> prm((size_t)n_lines * 4);
-        for (int i = 0; i < n_pages; ++i) {
-            if (ps[i].h != ps[i].ori_h || ps[i].w != ps[i].ori_w) any = true;  // identity otherwise: round(x * 1) clamped == x
-            for (int k = box_off[i]; k < box_off[i + 1]; ++k) {
-                prm[4 * (size_t)k] = (double)ps[i].ori_w / (double)ps[i].w;
-                prm[4 * (size_t)k + 1] = (double)ps[i].ori_h / (double)ps[i].h;
-                prm[4 * (size_t)k + 2] = (double)ps[i].ori_w;
-                prm[4 * (size_t)k + 3] = (double)ps[i].ori_h;
-            }
+        for (int i = 0; i < n_pages; ++i) if (ps[i].h != ps[i].ori_h || ps[i].w != ps[i].ori_w) any = true;  // identity otherwise: round(x * 1) clamped == x
+        if (any) {
+            std::vector<double> prm((size_t)n_lines * 4);
+            for (int i = 0; i < n_pages; ++i)
+                for (int k = box_off[i]; k < box_off[i + 1]; ++k) {
+                    prm[4 * (size_t)k] = (double)ps[i].ori_w / (double)ps[i].w;
+                    prm[4 * (size_t)k + 1] = (double)ps[i].ori_h / (double)ps[i].h;
+                    prm[4 * (size_t)k + 2] = (double)ps[i].ori_w;
+                    prm[4 * (size_t)k + 3] = (double)ps[i].ori_h;
+                }
+            if ((s = rt_scale_and_clip_multi(ctx, ctx->r_boxes.data(), prm.data(), n_lines, true)) != RETTO_B200_OK) return fail(s);
+            scaled = true;
         }
-        if (any) { RT_TRY(rt_scale_and_clip_multi(ctx, ctx->r_boxes.data(), prm.data(), n_lines, true)); scaled = true; }
     }
-
-    tr.mark("scale");
-    float *d_base = nullptr, *d_base_rec = nullptr;
-    RT_TRY(rt_build_batches_prepare(ctx, 0, lines.data(), n_lines, total, &d_base));
-    RT_TRY(rt_build_batches_launch(ctx, 0));
-    tr.mark("cls_build");
     // host work while the GPU crops and builds the cls batches: the rec plan and the rec descriptor tables
-    RT_TRY(plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total));
-    RT_TRY(rt_build_batches_prepare(ctx, 1, rec_lines.data(), n_lines, rec_total, &d_base_rec));
+    if ((s = plan_all(1, rec_lines, rec_batches, rec_batch_page, &rec_total)) != RETTO_B200_OK) return fail(s);
+    if ((s = rt_build_batches_prepare(ctx, 1, rec_lines.data(), n_lines, rec_total, &d_base_rec)) != RETTO_B200_OK) return fail(s);
     {
         uint64_t det_px = 0, crop_px = 0, rec_rows = 0;
         for (int i = 0; i < n_pages; ++i) det_px += (uint64_t)ps[i].det_h * ps[i].det_w;
@@ -259,87 +308,98 @@ static retto_b200_status run_pages_once(retto_b200_ctx* ctx, const retto_b200_pa
         memcpy(ctx->run_stats, st8, sizeof(st8));
     }
     tr.mark("rec_prepare");
-    std::vector<int32_t> cls_crop_idx;
-    std::vector<retto_b200_tensor> tin(batches.size()), tout(batches.size());
-    auto fill_inputs = [&](int img_h) {
-        for (size_t b = 0; b < batches.size(); ++b) {
-            tin[b].d_data = d_base + batches[b].offset;
-            tin[b].shape[0] = batches[b].n; tin[b].shape[1] = 3; tin[b].shape[2] = img_h; tin[b].shape[3] = batches[b].img_w;
+    auto fill_inputs = [&](const std::vector<retto_b200_batch>& bt, float* base, int img_h) {
+        tin.assign(bt.size(), retto_b200_tensor{});
+        tout.assign(bt.size(), retto_b200_tensor{});
+        for (size_t b = 0; b < bt.size(); ++b) {
+            tin[b].d_data = base + bt[b].offset;
+            tin[b].shape[0] = bt[b].n; tin[b].shape[1] = 3; tin[b].shape[2] = img_h; tin[b].shape[3] = bt[b].img_w;
             tin[b].ndim = 4;
-            memset(&tout[b], 0, sizeof(retto_b200_tensor));
         }
     };
-    fill_inputs(cfg.cls_image_shape[1]);
-    if (forward(user, 1, (int)batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: cls forward failed"); return RETTO_B200_ERR_WORKER; }
+    fill_inputs(batches, d_base, cfg.cls_image_shape[1]);
+    if (forward(user, 1, (int)batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: cls forward failed"); return fail(RETTO_B200_ERR_WORKER); }
     {
         std::vector<const float*> ptrs(n_lines);
-        std::vector<int32_t> crop_idx(n_lines);
-        std::vector<retto_b200_cls_result> res(n_lines);
+        cls_crop_idx.resize(n_lines);
         for (size_t b = 0; b < batches.size(); ++b) {
             const retto_b200_tensor& t = tout[b];
             if (!t.d_data || t.ndim != 2 || t.shape[0] != batches[b].n || t.shape[1] != 2) {
                 ctx->set_error("run_pages: cls forward returned a bad tensor");
-                return RETTO_B200_ERR_WORKER;
+                return fail(RETTO_B200_ERR_WORKER);
             }
             for (int k = 0; k < batches[b].n; ++k) {
                 ptrs[batches[b].first_line + k] = t.d_data + 2 * (size_t)k;
-                crop_idx[batches[b].first_line + k] = lines[batches[b].first_line + k].crop;
+                cls_crop_idx[batches[b].first_line + k] = lines[batches[b].first_line + k].crop;
             }
         }
-        RT_TRY(rt_cls_postprocess_ptrs(ctx, ptrs, crop_idx.data(), n_lines, nullptr, true));   // results collected after the final sync
-        cls_crop_idx = crop_idx;
+        if ((s = rt_cls_postprocess_ptrs(ctx, ptrs, cls_crop_idx.data(), n_lines, nullptr, true)) != RETTO_B200_OK) return fail(s);   // collected after the final sync
     }
-
     tr.mark("cls_fwd+post");
     // ---- 8. rec (rec_processor.rs:214-270) ---------------------------------------------------------------------------------
-    lines.swap(rec_lines); batches.swap(rec_batches); total = rec_total; d_base = d_base_rec;
-    RT_TRY(rt_build_batches_launch(ctx, 1));
-    tin.assign(batches.size(), retto_b200_tensor{});
-    tout.assign(batches.size(), retto_b200_tensor{});
-    tr.mark("rec_build");
-    fill_inputs(cfg.rec_image_shape[1]);
-    if (forward(user, 2, (int)batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: rec forward failed"); return RETTO_B200_ERR_WORKER; }
+    if ((s = rt_build_batches_launch(ctx, 1)) != RETTO_B200_OK) return fail(s);
+    fill_inputs(rec_batches, d_base_rec, cfg.rec_image_shape[1]);
+    if (forward(user, 2, (int)rec_batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: rec forward failed"); return fail(RETTO_B200_ERR_WORKER); }
     {
-        std::vector<retto_b200_logits_desc> descs(batches.size());
+        std::vector<retto_b200_logits_desc> descs(rec_batches.size());
         int max_t = 1;
-        for (size_t b = 0; b < batches.size(); ++b) {
+        for (size_t b = 0; b < rec_batches.size(); ++b) {
             const retto_b200_tensor& t = tout[b];
-            if (!t.d_data || t.ndim != 3 || t.shape[0] != batches[b].n || t.shape[1] <= 0 || t.shape[2] != (int64_t)ctx->dict.size()) {
+            if (!t.d_data || t.ndim != 3 || t.shape[0] != rec_batches[b].n || t.shape[1] <= 0 || t.shape[2] != (int64_t)ctx->dict.size()) {
                 ctx->set_error("run_pages: rec forward returned a bad tensor (classes must equal the dictionary size " + std::to_string(ctx->dict.size()) + ")");
-                return ctx->dict.empty() ? RETTO_B200_ERR_NO_DICT : RETTO_B200_ERR_WORKER;
+                return fail(ctx->dict.empty() ? RETTO_B200_ERR_NO_DICT : RETTO_B200_ERR_WORKER);
             }
             descs[b] = retto_b200_logits_desc{t.d_data, (int32_t)t.shape[0], (int32_t)t.shape[1]};
             max_t = std::max(max_t, (int)t.shape[1]);
         }
-        std::vector<uint32_t> toff(n_lines + 1, 0);
-        std::vector<float> sc(n_lines, 0.0f);
-        std::vector<char> text((size_t)n_lines * max_t * std::max(ctx->dict_max_len, 1) + 16);
-        retto_b200_status s = retto_b200_ctc_decode(ctx, descs.data(), (int)descs.size(), (int)ctx->dict.size(), toff.data(), text.data(), text.size(),
-                                                    sc.data(), nullptr, nullptr, 0);
-        if (s != RETTO_B200_OK) return s;
-        {   // the CTC call synchronised the stream: the deferred cls results, crop statuses and rescaled boxes are on the host now
-            std::vector<retto_b200_cls_result> res(n_lines);
-            RT_TRY(rt_cls_collect(ctx, n_lines, res.data()));
-            for (int k = 0; k < n_lines; ++k) ctx->r_cls[cls_crop_idx[k]] = res[k];  // final_res[idx].label = label (cls_processor.rs:167)
-            if (scaled) memcpy(ctx->r_boxes.data(), ctx->h_scale.p, sizeof(retto_b200_box) * (size_t)n_lines);
-            RT_TRY(rt_crop_finish(ctx, infos.data(), false));
-        }
-        // scatter from plan order back to detection order (rec_processor.rs:259-264)
-        std::vector<uint32_t> len(n_lines, 0);
-        for (int k = 0; k < n_lines; ++k) len[lines[k].crop] = toff[k + 1] - toff[k];
-        for (int k = 0; k < n_lines; ++k) ctx->r_text_offs[k + 1] = ctx->r_text_offs[k] + len[k];
-        ctx->r_text.assign(ctx->r_text_offs[n_lines] + 1, 0);
-        for (int k = 0; k < n_lines; ++k) {
-            const int dst = lines[k].crop;
-            memcpy(ctx->r_text.data() + ctx->r_text_offs[dst], text.data() + toff[k], toff[k + 1] - toff[k]);
-            ctx->r_scores[dst] = sc[k];
-        }
+        if (ctx->dict.empty()) { ctx->set_error("ctc_decode: no dictionary loaded"); return fail(RETTO_B200_ERR_NO_DICT); }
+        toff.assign(n_lines + 1, 0);
+        sc.assign(n_lines, 0.0f);
+        text.resize((size_t)n_lines * max_t * std::max(ctx->dict_max_len, 1) + 16);
+        if ((s = rt_ctc_begin(ctx, descs.data(), (int)descs.size(), (int)ctx->dict.size(), false, 0)) != RETTO_B200_OK) return fail(s);
     }
-    tr.mark("rec_fwd+ctc");
-    out->text = ctx->r_text.data();
-    out->text_offsets = ctx->r_text_offs.data();
+    tr.mark("rec_fwd+ctc_begin");
+    return RETTO_B200_OK;
+}
+
+// ---- the one final sync of the unit + results in detection order
+retto_b200_status PageRun::finish() {
+    if (done) return ret;
+    done = true;
+    retto_b200_status s = rt_ctc_end(ctx, toff.data(), text.data(), text.size(), sc.data(), nullptr, nullptr, 0);
+    if (s != RETTO_B200_OK) return (ret = s);
+    tr.mark("ctc_wait");
+    // the CTC call synchronised the stream: the deferred cls results, crop statuses and rescaled boxes are on the host now
+    std::vector<retto_b200_cls_result> res(n_lines);
+    if ((s = rt_cls_collect(ctx, n_lines, res.data())) != RETTO_B200_OK) return (ret = s);
+    for (int k = 0; k < n_lines; ++k) ctx->r_cls[cls_crop_idx[k]] = res[k];  // final_res[idx].label = label (cls_processor.rs:167)
+    if (scaled) memcpy(ctx->r_boxes.data(), ctx->h_scale.p, sizeof(retto_b200_box) * (size_t)n_lines);
+    if ((s = rt_crop_finish(ctx, infos.data(), false)) != RETTO_B200_OK) return (ret = s);
+    // scatter from plan order back to detection order (rec_processor.rs:259-264)
+    std::vector<uint32_t> len(n_lines, 0);
+    for (int k = 0; k < n_lines; ++k) len[rec_lines[k].crop] = toff[k + 1] - toff[k];
+    for (int k = 0; k < n_lines; ++k) ctx->r_text_offs[k + 1] = ctx->r_text_offs[k] + len[k];
+    ctx->r_text.assign(ctx->r_text_offs[n_lines] + 1, 0);
+    for (int k = 0; k < n_lines; ++k) {
+        const int dst = rec_lines[k].crop;
+        memcpy(ctx->r_text.data() + ctx->r_text_offs[dst], text.data() + toff[k], toff[k + 1] - toff[k]);
+        ctx->r_scores[dst] = sc[k];
+    }
+    tr.mark("collect");
     return ret;
 }
+
+void fill_results(retto_b200_ctx* ctx, retto_b200_results* out) {
+    out->n_pages = (int)ctx->r_pages.size();
+    out->pages = ctx->r_pages.data();
+    out->n_lines = (int)ctx->r_boxes.size();
+    out->boxes = ctx->r_boxes.data();
+    out->cls = ctx->r_cls.data();
+    out->text_offsets = ctx->r_text_offs.data();
+    out->text = ctx->r_text.data();
+    out->rec_scores = ctx->r_scores.data();
+}
+}  // namespace
 
 // Page upload by the SMs: pinned host memory is device-accessible under UVA, so a copy kernel on the copy stream can
 // pull the pages over PCIe without occupying the DMA engine — the many small descriptor uploads of the compute stream
@@ -366,20 +426,134 @@ __global__ void __launch_bounds__(512) pull_pages_kernel(PullArgs a) {
     }
 }
 
-// Host-resident batches larger than one chunk are pipelined: every page is uploaded on a separate copy stream up front
-// (one event per chunk), and chunk k is processed on the compute stream as soon as its pages have landed, so the PCIe
-// transfer of the later chunks overlaps with the kernels of the earlier ones.  Results are concatenated in page order.
+// lane 1: a child context on the same device (own stream, buffers, dictionary copy), created on first use
+static retto_b200_status lane_ctx(retto_b200_ctx* ctx, int lane, retto_b200_ctx** out) {
+    if (lane == 0) { *out = ctx; return RETTO_B200_OK; }
+    while ((int)ctx->lanes.size() < lane) {
+        retto_b200_ctx* c = nullptr;
+        retto_b200_status s = retto_b200_create(ctx->device, &ctx->cfg, &c);
+        if (s != RETTO_B200_OK) { ctx->set_error("run_pages: cannot create a pipeline lane"); return s; }
+        ctx->lanes.push_back(c);
+    }
+    retto_b200_ctx* c = ctx->lanes[lane - 1];
+    if (c->dict_version != ctx->dict_version) {
+        retto_b200_status s = retto_b200_dict_load(c, ctx->dict_source.data(), ctx->dict_source.size());
+        if (s != RETTO_B200_OK) return s;
+        c->dict_version = ctx->dict_version;
+    }
+    c->cfg = ctx->cfg;
+    c->timing_enabled = false;
+    *out = c;
+    return RETTO_B200_OK;
+}
+
+struct Unit { const retto_b200_page* pages; int n; cudaEvent_t wait_for; };
+
+// Software pipeline over the units, two in flight: finish(u[k-2]) -> begin(u[k]) -> mid(u[k-1]).  Unit k runs on lane
+// k % 2, which unit k-2 has just left.  With one lane the units run back to back.
+static retto_b200_status run_units(retto_b200_ctx* ctx, const std::vector<Unit>& units, int n_lanes, retto_b200_forward_fn forward, void* user,
+                                   retto_b200_results* out) {
+    const int nu = (int)units.size();
+    n_lanes = std::max(1, std::min(n_lanes, std::min(nu, 2)));
+    std::vector<retto_b200_ctx*> lane(n_lanes);
+    for (int l = 0; l < n_lanes; ++l) RT_TRY(lane_ctx(ctx, l, &lane[l]));
+    std::vector<retto_b200_page_result> a_pages;
+    std::vector<retto_b200_box> a_boxes;
+    std::vector<retto_b200_cls_result> a_cls;
+    std::vector<uint32_t> a_toffs(1, 0);
+    std::vector<char> a_text;
+    std::vector<float> a_scores;
+    uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    retto_b200_status ret = RETTO_B200_OK;
+    std::vector<std::unique_ptr<PageRun>> runs(nu);
+    auto hard = [](retto_b200_status s) { return s != RETTO_B200_OK && s != RETTO_B200_ERR_DEGENERATE_QUAD && s != RETTO_B200_ERR_CAPACITY; };
+    auto drain = [&](retto_b200_status s, retto_b200_ctx* from) {
+        for (auto* l : lane) cudaStreamSynchronize(l->stream);
+        if (from != ctx) ctx->set_error(from->err);
+        return s;
+    };
+    auto collect = [&](PageRun& r) {   // append the unit's results (units complete in page order)
+        retto_b200_results u;
+        fill_results(r.ctx, &u);
+        const int line0 = (int)a_boxes.size();
+        for (int i = 0; i < u.n_pages; ++i) { retto_b200_page_result pr = u.pages[i]; pr.first_line += line0; a_pages.push_back(pr); }
+        a_boxes.insert(a_boxes.end(), u.boxes, u.boxes + u.n_lines);
+        a_cls.insert(a_cls.end(), u.cls, u.cls + u.n_lines);
+        a_scores.insert(a_scores.end(), u.rec_scores, u.rec_scores + u.n_lines);
+        const uint32_t t0 = a_toffs.back();
+        for (int k = 0; k < u.n_lines; ++k) a_toffs.push_back(t0 + u.text_offsets[k + 1]);
+        if (u.n_lines) a_text.insert(a_text.end(), u.text, u.text + u.text_offsets[u.n_lines]);
+        for (int k = 0; k < 8; ++k) stats[k] += r.ctx->run_stats[k];
+    };
+    auto start = [&](int k) {
+        runs[k].reset(new PageRun());
+        PageRun& r = *runs[k];
+        r.ctx = lane[k % n_lanes]; r.h_pages = units[k].pages; r.n_pages = units[k].n; r.forward = forward; r.user = user; r.wait_for = units[k].wait_for;
+        return r.begin();
+    };
+    if (n_lanes == 1) {
+        for (int k = 0; k < nu; ++k) {
+            retto_b200_status s = start(k);
+            if (!hard(s)) s = runs[k]->mid();
+            if (!hard(s)) s = runs[k]->finish();
+            if (hard(s)) return drain(s, lane[0]);
+            if (s != RETTO_B200_OK) ret = s;
+            if (nu == 1) { fill_results(ctx, out); return ret; }   // single unit: the context's own vectors are the result
+            collect(*runs[k]);
+            runs[k].reset();
+        }
+    } else {
+        for (int k = 0; k < nu + 2; ++k) {
+            if (k >= 2) {
+                retto_b200_status s = runs[k - 2]->finish();
+                if (hard(s)) return drain(s, runs[k - 2]->ctx);
+                if (s != RETTO_B200_OK) { ret = s; if (runs[k - 2]->ctx != ctx) ctx->set_error(runs[k - 2]->ctx->err); }
+                collect(*runs[k - 2]);
+                runs[k - 2].reset();
+            }
+            if (k < nu) {
+                retto_b200_status s = start(k);
+                if (hard(s)) return drain(s, runs[k]->ctx);
+            }
+            if (k >= 1 && k <= nu) {
+                retto_b200_status s = runs[k - 1]->mid();
+                if (hard(s)) return drain(s, runs[k - 1]->ctx);
+            }
+        }
+    }
+    memcpy(ctx->run_stats, stats, sizeof(stats));
+    a_text.push_back(0);
+    ctx->r_pages.swap(a_pages); ctx->r_boxes.swap(a_boxes); ctx->r_cls.swap(a_cls);
+    ctx->r_text_offs.swap(a_toffs); ctx->r_text.swap(a_text); ctx->r_scores.swap(a_scores);
+    fill_results(ctx, out);
+    return ret;
+}
+
+// Host-resident batches larger than one unit are uploaded by the pull kernel on a separate copy stream up front (one event
+// per unit); a unit starts as soon as its pages have landed, so the PCIe transfer of the later units overlaps with the
+// kernels of the earlier ones.  Device-resident batches are cut into units only to keep two lanes busy.
 extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
                                                   retto_b200_forward_fn forward, void* user, retto_b200_results* out) {
     if (!ctx || n_pages < 0 || (n_pages > 0 && !h_pages) || !forward || !out) return RETTO_B200_ERR_INVALID_ARG;
-    // pages per chunk / blocks of the pull kernel: tunables for experiments, defaults measured on B200
-    static const int RUN_CHUNK_PAGES = env_int("RETTO_B200_CHUNK_PAGES", 32, 1, RUN_CHUNK_PAGES_MAX);
+    memset(out, 0, sizeof(*out));
+    // tunables (retto_b200_set_pipeline or the environment); defaults measured on B200
+    const int n_lanes = ctx->pipe_lanes > 0 ? ctx->pipe_lanes : env_int("RETTO_B200_LANES", 1, 1, 2);
+    const int unit_dev = ctx->pipe_unit_pages > 0 ? ctx->pipe_unit_pages : env_int("RETTO_B200_UNIT_PAGES", 64, 1, 1 << 20);
+    const int RUN_CHUNK_PAGES = std::min(RUN_CHUNK_PAGES_MAX, ctx->pipe_unit_pages > 0 ? ctx->pipe_unit_pages : env_int("RETTO_B200_CHUNK_PAGES", 32, 1, RUN_CHUNK_PAGES_MAX));
     static const int PULL_BLOCKS = env_int("RETTO_B200_PULL_BLOCKS", 16, 1, 1024);
     static const int USE_DMA = env_int("RETTO_B200_PULL_DMA", 0, 0, 1);
-    bool all_host = n_pages > RUN_CHUNK_PAGES;
-    for (int i = 0; i < n_pages && all_host; ++i) if (h_pages[i].on_device || !h_pages[i].rgb || h_pages[i].h <= 0 || h_pages[i].w <= 0) all_host = false;
-    if (!all_host) return run_pages_once(ctx, h_pages, n_pages, forward, user, out);
-
+    bool all_host = n_pages > RUN_CHUNK_PAGES, all_dev = true;
+    for (int i = 0; i < n_pages; ++i) {
+        if (h_pages[i].on_device || !h_pages[i].rgb || h_pages[i].h <= 0 || h_pages[i].w <= 0) all_host = false;
+        if (!h_pages[i].on_device) all_dev = false;
+    }
+    std::vector<Unit> units;
+    if (!all_host) {
+        // one unit, or (device-resident pages, two lanes) units of unit_dev pages
+        const int up = (all_dev && n_lanes > 1 && n_pages > unit_dev) ? unit_dev : std::max(n_pages, 1);
+        for (int p0 = 0; p0 < std::max(n_pages, 1); p0 += up) units.push_back(Unit{h_pages + p0, std::min(up, n_pages - p0), nullptr});
+        return run_units(ctx, units, n_lanes, forward, user, out);
+    }
     if (!ctx->copy_stream) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -429,49 +603,20 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
             }
         }
     }
-    std::vector<retto_b200_page_result> a_pages;
-    std::vector<retto_b200_box> a_boxes;
-    std::vector<retto_b200_cls_result> a_cls;
-    std::vector<uint32_t> a_toffs(1, 0);
-    std::vector<char> a_text;
-    std::vector<float> a_scores;
-    uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    retto_b200_status ret = RETTO_B200_OK;
     for (int c = 0; c < n_chunks; ++c) {
-        const int p0 = c * RUN_CHUNK_PAGES, np = std::min(RUN_CHUNK_PAGES, n_pages - p0);
-        RT_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[c], 0));
-        retto_b200_results r;
-        retto_b200_status s = run_pages_once(ctx, dev_pages.data() + p0, np, forward, user, &r);
-        if (s != RETTO_B200_OK && s != RETTO_B200_ERR_DEGENERATE_QUAD && s != RETTO_B200_ERR_CAPACITY) { cudaStreamSynchronize(ctx->copy_stream); return s; }
-        if (s != RETTO_B200_OK) ret = s;
-        const int line0 = (int)a_boxes.size();
-        for (int i = 0; i < r.n_pages; ++i) {
-            retto_b200_page_result pr = r.pages[i];
-            pr.first_line += line0;
-            a_pages.push_back(pr);
-        }
-        a_boxes.insert(a_boxes.end(), r.boxes, r.boxes + r.n_lines);
-        a_cls.insert(a_cls.end(), r.cls, r.cls + r.n_lines);
-        a_scores.insert(a_scores.end(), r.rec_scores, r.rec_scores + r.n_lines);
-        const uint32_t t0 = a_toffs.back();
-        for (int k = 0; k < r.n_lines; ++k) a_toffs.push_back(t0 + r.text_offsets[k + 1]);
-        if (r.n_lines) a_text.insert(a_text.end(), r.text, r.text + r.text_offsets[r.n_lines]);
-        for (int k = 0; k < 8; ++k) stats[k] += ctx->run_stats[k];
+        const int p0 = c * RUN_CHUNK_PAGES;
+        units.push_back(Unit{dev_pages.data() + p0, std::min(RUN_CHUNK_PAGES, n_pages - p0), ctx->copy_events[c]});
     }
-    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    memcpy(ctx->run_stats, stats, sizeof(stats));
-    a_text.push_back(0);
-    ctx->r_pages.swap(a_pages); ctx->r_boxes.swap(a_boxes); ctx->r_cls.swap(a_cls);
-    ctx->r_text_offs.swap(a_toffs); ctx->r_text.swap(a_text); ctx->r_scores.swap(a_scores);
-    out->n_pages = n_pages;
-    out->pages = ctx->r_pages.data();
-    out->n_lines = (int)ctx->r_boxes.size();
-    out->boxes = ctx->r_boxes.data();
-    out->cls = ctx->r_cls.data();
-    out->text_offsets = ctx->r_text_offs.data();
-    out->text = ctx->r_text.data();
-    out->rec_scores = ctx->r_scores.data();
+    retto_b200_status ret = run_units(ctx, units, n_lanes, forward, user, out);
+    cudaStreamSynchronize(ctx->copy_stream);
     return ret;
+}
+
+extern "C" retto_b200_status retto_b200_set_pipeline(retto_b200_ctx* ctx, int32_t lanes, int32_t unit_pages) {
+    if (!ctx || lanes < 0 || lanes > 2 || unit_pages < 0) return RETTO_B200_ERR_INVALID_ARG;
+    ctx->pipe_lanes = lanes;
+    ctx->pipe_unit_pages = unit_pages;
+    return RETTO_B200_OK;
 }
 
 extern "C" retto_b200_status retto_b200_last_run_stats(const retto_b200_ctx* ctx, uint64_t* out8) {

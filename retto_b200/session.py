@@ -200,7 +200,9 @@ class RettoSession:
         import torch
         try:
             dev = f"cuda:{self.ctx.device_id}"
-            with torch.cuda.stream(self.ctx.torch_stream()):
+            # the tensors of this call are ordered on `stream` (the lane of the unit being processed, include/retto_b200.h)
+            ts = self.ctx.torch_stream() if (not stream or stream == self.ctx.stream_ptr) else torch.cuda.ExternalStream(int(stream), device=dev)
+            with torch.cuda.stream(ts):
                 xs = [_wrap(inputs[i], dev) for i in range(n)]
                 ys = (self.worker.det, self.worker.cls, self.worker.rec)[stage](xs)
                 if len(ys) != n:
@@ -215,7 +217,9 @@ class RettoSession:
                     outputs[i].ndim = y.dim()
                     for k in range(y.dim()):
                         outputs[i].shape[k] = y.shape[k]
-                self._keep[stage] = keep
+                lst = self._keep.setdefault((stage, int(stream or 0)), [])   # a lane has one unit in flight: keep its outputs alive
+                lst.append(keep)
+                del lst[:-2]
             return 0
         except Exception as e:  # surfaced as ERR_WORKER
             self._err = e
@@ -235,7 +239,7 @@ class RettoSession:
                 hold.append(a)
                 pages[i] = Page(a.ctypes.data, a.shape[0], a.shape[1], 0)
         res = Results()
-        self._keep = {0: None, 1: None, 2: None}
+        self._keep = {}
         self._err = None
         st = self.ctx._L.retto_b200_run_pages(self.ctx.handle, pages, n, self._cb, None, C.byref(res))
         if self._err is not None:

@@ -311,6 +311,70 @@ def test_session_empty_page(ctx, synth_dict):
     assert r.status == 0 and r.det_result == [] and r.cls_result == [] and r.rec_result == []
 
 
+class StatelessWorker:
+    """stand-in forwards whose every output is a function of the input tensor only (any batching gives the same rows)"""
+
+    def det(self, x):
+        g = (x[0].mean(axis=0) + 1.0) / 2.0
+        return np.clip(1.0 - g, 0.0, 1.0).astype(np.float32)[None, None]
+
+    def cls(self, x):
+        s = x.reshape(x.shape[0], -1).mean(axis=1)
+        return np.stack([np.where(s > -0.6, 0.95, 0.05), np.where(s > -0.6, 0.05, 0.95)], 1).astype(np.float32)
+
+    def rec(self, x):
+        n, T = x.shape[0], x.shape[3] // 8
+        out = np.zeros((n, T, 6625), np.float32)
+        for i in range(n):
+            rng2 = np.random.default_rng(zlib.crc32(np.ascontiguousarray(x[i]).tobytes()))
+            out[i, np.arange(T), rng2.integers(0, 6625, T)] = 0.5 + 0.5 * rng2.random(T, dtype=np.float32)
+        return out
+
+
+def _small_pages(n, seed):
+    rng = np.random.default_rng(seed)
+    imgs = []
+    for i in range(n):
+        im = np.full((160 + 8 * (i % 5), 240 + 16 * (i % 3), 3), 255, np.uint8)
+        for k in range(int(rng.integers(1, 4))):
+            y0, x0 = 20 + 40 * k, int(rng.integers(10, 60))
+            im[y0:y0 + int(rng.integers(10, 22)), x0:x0 + int(rng.integers(60, 150))] = int(rng.integers(0, 60))
+        imgs.append(im)
+    return imgs
+
+
+def _same_results(a, b):
+    assert len(a.det_result) == len(b.det_result)
+    for x, y in zip(a.det_result, b.det_result):
+        assert np.array_equal(x.boxes, y.boxes) and x.score == y.score
+    assert [(c.label, c.score) for c in a.cls_result] == [(c.label, c.score) for c in b.cls_result]
+    assert [r.text for r in a.rec_result] == [r.text for r in b.rec_result]
+    assert [r.score for r in a.rec_result] == [r.score for r in b.rec_result] or all(
+        (x.score == y.score) or (x.score != x.score and y.score != y.score) for x, y in zip(a.rec_result, b.rec_result))
+
+
+def test_session_lanes_equal_serial(ctx, synth_dict):
+    """device-resident pages: units of 16 pages software-pipelined on two lanes (csrc/session.cu) give exactly the
+    results of the same batch run as one unit on one stream"""
+    import torch
+    imgs = _small_pages(75, 9)
+    dev = [torch.from_numpy(im).cuda() for im in imgs]
+    torch.cuda.synchronize()
+    sess = _session(ctx, StatelessWorker(), synth_dict)
+    try:
+        ctx.set_pipeline(1, 1 << 20)
+        serial = sess.run_pages(dev, on_device=True)
+        ctx.set_pipeline(2, 16)
+        l0 = ctx.launch_count
+        piped = sess.run_pages(dev, on_device=True)
+        assert ctx.launch_count - l0 > 5 * 20   # five units, each with its own kernel chain
+    finally:
+        ctx.set_pipeline(0, 0)
+    assert len(serial) == len(piped) == 75 and sum(len(r.det_result) for r in serial) > 75
+    for a, b in zip(serial, piped):
+        _same_results(a, b)
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_session_chunked_pipeline_equals_unchunked(ctx, synth_dict, pinned):
     """more host pages than one chunk take the chunked H2D/compute pipeline (csrc/session.cu): results must equal
@@ -327,24 +391,7 @@ def test_session_chunked_pipeline_equals_unchunked(ctx, synth_dict, pinned):
             im = torch.from_numpy(im).pin_memory().numpy()
         imgs.append(im)
 
-    class W:   # stateless stand-ins: every output is a function of the input tensor only
-        def det(self, x):
-            g = (x[0].mean(axis=0) + 1.0) / 2.0
-            return np.clip(1.0 - g, 0.0, 1.0).astype(np.float32)[None, None]
-
-        def cls(self, x):
-            s = x.reshape(x.shape[0], -1).mean(axis=1)
-            return np.stack([np.where(s > s.mean(), 0.95, 0.05), np.where(s > s.mean(), 0.05, 0.95)], 1).astype(np.float32)
-
-        def rec(self, x):
-            n, T = x.shape[0], x.shape[3] // 8
-            out = np.zeros((n, T, 6625), np.float32)
-            for i in range(n):
-                rng2 = np.random.default_rng(zlib.crc32(np.ascontiguousarray(x[i]).tobytes()))
-                out[i, np.arange(T), rng2.integers(0, 6625, T)] = 0.5 + 0.5 * rng2.random(T, dtype=np.float32)
-            return out
-
-    sess = _session(ctx, W(), synth_dict)
+    sess = _session(ctx, StatelessWorker(), synth_dict)
     batch = sess.run_pages(imgs)
     assert len(batch) == 70 and sum(len(r.det_result) for r in batch) > 70
     for i in (0, 1, 63, 64, 65, 69):
