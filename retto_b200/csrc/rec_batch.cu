@@ -44,6 +44,7 @@ struct FlipReader {   // crops are stored RGBX, one aligned word per pixel
 #define BB_BB 1
 #define BB_BF 2
 #define BB_GEN 3
+#define BB_BB2 4          // BB with every window at most 2 x 2
 #define BB_BF_MAXN 8      // widest column block of the BF path (table width)
 #define BB_BB_MAXN 32     // largest nx*ny of the BB path (multiply-shift exact for n < 64, see magic_div20)
 struct ChunkDev { int line, x0; };
@@ -107,10 +108,11 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
     for (int y = threadIdx.x; y < img_h; y += BB_COLS) {
         const ThumbAxis ay = thumb_axis(y, yr, chh);
         RowS r;
-        if (kind == BB_BB) {            // rows [lo, hi): the sums do not depend on the order, so a flip only moves the start
+        if (kind == BB_BB || kind == BB_BB2) {   // rows [lo, hi): the sums do not depend on the order, so a flip only moves the start
             const int ny = (int)(ay.hi - ay.lo);
             r.o0 = (flip ? (int)chh - (int)ay.hi : (int)ay.lo) * (int)cw;
-            r.o1 = ny; r.fv = 0.0f; r.omv = 0.0f;
+            r.o1 = kind == BB_BB ? ny : r.o0 + (ny - 1) * (int)cw;   // BB: row count; BB2: offset of the second row (or the first again)
+            r.fv = 0.0f; r.omv = 0.0f;
         } else {
             const AxisS a = axis_small(ay, chh);
             const int j0 = flip ? (int)chh - 1 - a.i0 : a.i0, j1 = flip ? (int)chh - 1 - a.i1 : a.i1;
@@ -148,15 +150,45 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
         const unsigned* __restrict__ s0 = src + (flip ? (int)cw - 1 - xs.i0 : xs.i0);
         const unsigned* __restrict__ s1 = src + (flip ? (int)cw - 1 - xs.i1 : xs.i1);
         const float fhu = xs.n ? 0.0f : xs.fract, omfhu = xs.n ? 1.0f : __fsub_rn(1.0f, xs.fract);
+        // software pipeline: the four source words of row y+1 are in flight while row y is mixed and stored
+        RowS r = sh.row[0];
+        unsigned p00 = __ldg(s0 + r.o0), p10 = __ldg(s1 + r.o0), p01 = __ldg(s0 + r.o1), p11 = __ldg(s1 + r.o1);
 #pragma unroll 2
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
-            const RowS r = sh.row[y];
-            const unsigned p00 = __ldg(s0 + r.o0), p10 = __ldg(s1 + r.o0), p01 = __ldg(s0 + r.o1), p11 = __ldg(s1 + r.o1);
+            const RowS rn = sh.row[y + 1 < img_h ? y + 1 : y];
+            const unsigned n00 = __ldg(s0 + rn.o0), n10 = __ldg(s1 + rn.o0), n01 = __ldg(s0 + rn.o1), n11 = __ldg(s1 + rn.o1);
             const float f_tr = __fmul_rn(r.fv, fhu), f_tl = __fmul_rn(r.fv, omfhu), f_br = __fmul_rn(r.omv, fhu), f_bl = __fmul_rn(r.omv, omfhu);
 #define RT_BL(sel) lut_trunc(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, u8f(p10, k23, sel)), __fmul_rn(f_tr, u8f(p11, k23, sel))), \
                                                  __fmul_rn(f_bl, u8f(p00, k23, sel))), __fmul_rn(f_tl, u8f(p01, k23, sel))), lut_biased)
             *d0 = RT_BL(0x7540u); *d1 = RT_BL(0x7541u); *d2 = RT_BL(0x7542u);
 #undef RT_BL
+            r = rn; p00 = n00; p10 = n10; p01 = n01; p11 = n11;
+        }
+        return;
+    }
+    if (kind == BB_BB2) {
+        // windows of 1-2 x 1-2 pixels (scale ratios in [1, 2]): always four loads (a missing column / row repeats the
+        // first one and is masked out of the sums), n = 1, 2 or 4 so the division is a shift; row y+1 prefetched
+        const int nx = (int)(ax.hi - ax.lo);
+        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
+        const unsigned* __restrict__ s1 = s0 + (nx - 1);
+        const unsigned mx = nx > 1 ? 0xFFFFFFFFu : 0u;
+        RowS r = sh.row[0];
+        unsigned w00 = __ldg(s0 + r.o0), w10 = __ldg(s1 + r.o0), w01 = __ldg(s0 + r.o1), w11 = __ldg(s1 + r.o1);
+#pragma unroll 2
+        for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
+            const RowS rn = sh.row[y + 1 < img_h ? y + 1 : y];
+            const unsigned n00 = __ldg(s0 + rn.o0), n10 = __ldg(s1 + rn.o0), n01 = __ldg(s0 + rn.o1), n11 = __ldg(s1 + rn.o1);
+            const unsigned my = r.o1 != r.o0 ? 0xFFFFFFFFu : 0u;
+            const unsigned shn = (mx & 1u) + (my & 1u), h2 = (1u << shn) >> 1;
+            w10 &= mx; w01 &= my; w11 &= mx & my;
+            unsigned a0 = h2, a1 = h2, a2 = h2;
+            a0 = __dp4a(w00, 0x00000001u, a0); a1 = __dp4a(w00, 0x00000100u, a1); a2 = __dp4a(w00, 0x00010000u, a2);
+            a0 = __dp4a(w10, 0x00000001u, a0); a1 = __dp4a(w10, 0x00000100u, a1); a2 = __dp4a(w10, 0x00010000u, a2);
+            a0 = __dp4a(w01, 0x00000001u, a0); a1 = __dp4a(w01, 0x00000100u, a1); a2 = __dp4a(w01, 0x00010000u, a2);
+            a0 = __dp4a(w11, 0x00000001u, a0); a1 = __dp4a(w11, 0x00000100u, a1); a2 = __dp4a(w11, 0x00010000u, a2);
+            *d0 = sh.lut[a0 >> shn]; *d1 = sh.lut[a1 >> shn]; *d2 = sh.lut[a2 >> shn];
+            r = rn; w00 = n00; w10 = n10; w01 = n01; w11 = n11;
         }
         return;
     }
@@ -304,7 +336,7 @@ retto_b200_status rt_build_batches_prepare(retto_b200_ctx* ctx, int32_t kind, co
     const int img_h = kind == 0 ? ctx->cfg.cls_image_shape[1] : ctx->cfg.rec_image_shape[1];
     if (img_h > BB_MAX_H) { ctx->set_error("build_batches: image_shape height > 64 is not supported"); return RETTO_B200_ERR_UNSUPPORTED; }
     const bool force_generic = getenv("RETTO_B200_BB_GENERIC") != nullptr;   // tests: every line through thumbnail_pixel
-    size_t n_chunks[4] = {0, 0, 0, 0};
+    size_t n_chunks[5] = {0, 0, 0, 0, 0};
     std::vector<LineDev>& lines = ctx->bb_lines;
     lines.resize(n_lines);
     for (int i = 0; i < n_lines; ++i) {
@@ -320,20 +352,22 @@ retto_b200_status rt_build_batches_prepare(retto_b200_ctx* ctx, int32_t kind, co
         const int nx_max = (cw + rw - 1) / rw, ny_max = (ch + img_h - 1) / img_h;
         int k = BB_GEN;
         if (cw <= rw && ch <= img_h) k = BB_FF;
+        else if (cw >= rw && ch >= img_h && nx_max <= 2 && ny_max <= 2) k = BB_BB2;
         else if (cw >= rw && ch >= img_h && nx_max * ny_max <= BB_BB_MAXN) k = BB_BB;
         else if (cw > rw && ch < img_h && nx_max <= BB_BF_MAXN) k = BB_BF;
         if (force_generic) k = BB_GEN;
         lines[i] = LineDev{l.crop, l.img_w, l.resized_w, k, l.dst_offset};
         n_chunks[k] += (size_t)(l.img_w + BB_COLS - 1) / BB_COLS;
     }
-    const size_t total_chunks = n_chunks[0] + n_chunks[1] + n_chunks[2] + n_chunks[3];
+    const size_t total_chunks = n_chunks[0] + n_chunks[1] + n_chunks[2] + n_chunks[3] + n_chunks[4];
     const size_t lb = (sizeof(LineDev) * n_lines + 15) & ~size_t(15);
     std::vector<char>& blob = ctx->bb_blob;
     blob.resize(lb + sizeof(ChunkDev) * total_chunks);
     memcpy(blob.data(), lines.data(), sizeof(LineDev) * n_lines);
     ChunkDev* ck = reinterpret_cast<ChunkDev*>(blob.data() + lb);
-    size_t cur[4];
-    cur[BB_GEN] = 0; cur[BB_BF] = n_chunks[BB_GEN]; cur[BB_BB] = cur[BB_BF] + n_chunks[BB_BF]; cur[BB_FF] = cur[BB_BB] + n_chunks[BB_BB];
+    size_t cur[5];
+    cur[BB_GEN] = 0; cur[BB_BF] = n_chunks[BB_GEN]; cur[BB_BB] = cur[BB_BF] + n_chunks[BB_BF]; cur[BB_BB2] = cur[BB_BB] + n_chunks[BB_BB];
+    cur[BB_FF] = cur[BB_BB2] + n_chunks[BB_BB2];
     for (int i = 0; i < n_lines; ++i) {
         size_t& c = cur[lines[i].kind];
         for (int x0 = 0; x0 < lines[i].img_w; x0 += BB_COLS) ck[c++] = ChunkDev{i, x0};
