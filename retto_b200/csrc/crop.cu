@@ -157,10 +157,17 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restric
         const int xlo = max(0, 1 - tx), xhi = min(w - 1, c.page_w - 4 - tx);   // columns whose 4x4 window is inside the page
         uchar4* dst = reinterpret_cast<uchar4*>(pix + c.offset) + (size_t)y * w;
         const unsigned char* src = c.page + ((size_t)iy * c.page_w + tx) * 3;
-        for (int x = lane; x < w; x += 32) {
-            uchar4 o = make_uchar4(255, 255, 255, 255);
-            if (row_ok && x >= xlo && x <= xhi) { const unsigned char* sp = src + 3 * x; o.x = __ldg(sp); o.y = __ldg(sp + 1); o.z = __ldg(sp + 2); }
-            dst[x] = o;
+        // four pixels per lane per trip: the twelve byte loads are independent and issued before the first store
+        for (int x = lane; x < w; x += 128) {
+            uchar4 o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xx = x + 32 * k;
+                o[k] = make_uchar4(255, 255, 255, 255);
+                if (row_ok && xx >= xlo && xx <= xhi) { const unsigned char* sp = src + 3 * xx; o[k].x = __ldg(sp); o[k].y = __ldg(sp + 1); o[k].z = __ldg(sp + 2); }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x + 32 * k < w) dst[x + 32 * k] = o[k];
         }
         return;
     }

@@ -45,6 +45,7 @@ struct FlipReader {   // crops are stored RGBX, one aligned word per pixel
 #define BB_BF 2
 #define BB_GEN 3
 #define BB_BB2 4          // BB with every window at most 2 x 2
+#define BB_BF4 5          // BF with every column block at most 4 wide
 #define BB_BF_MAXN 8      // widest column block of the BF path (table width)
 #define BB_BB_MAXN 32     // largest nx*ny of the BB path (multiply-shift exact for n < 64, see magic_div20)
 struct ChunkDev { int line, x0; };
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
             r.o0 = j0 * (int)cw; r.o1 = j1 * (int)cw;
             if (kind == BB_FF) { r.fv = a.n ? 0.0f : a.fract; r.omv = a.n ? 1.0f : __fsub_rn(1.0f, a.fract); }   // (1, 0) for a 1-px block row
             else { r.fv = a.n ? -1.0f : a.fract; r.omv = __fsub_rn(1.0f, a.fract); }                              // fv < 0 marks a block row (BF)
-            if (kind == BB_BF)
+            if (kind == BB_BF || kind == BB_BF4)
                 for (int k = 0; k < BB_BF_MAXN; ++k) {
                     sh.fb[y][k] = __fdiv_rn(r.omv, (float)(k + 1));
                     sh.ft[y][k] = __fdiv_rn(a.fract, (float)(k + 1));
@@ -209,6 +210,42 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
             *d0 = sh.lut[((a0 + h2) * M) >> 20];
             *d1 = sh.lut[((a1 + h2) * M) >> 20];
             *d2 = sh.lut[((a2 + h2) * M) >> 20];
+        }
+        return;
+    }
+    if (kind == BB_BF4) {
+        // column blocks of at most 4 pixels: a fixed set of 2 x 4 predicated loads per output row, those of row y+1 in
+        // flight while row y is summed and mixed (consecutive output rows mostly re-read the same two source rows: L1 hits)
+        const int nx = (int)(ax.hi - ax.lo);
+        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
+        const unsigned h2 = (unsigned)nx >> 1, M = sh.magic[nx];
+        const bool e1 = nx > 1, e2 = nx > 2, e3 = nx > 3;
+        RowS r = sh.row[0];
+        unsigned p0 = __ldg(s0 + r.o0), p1 = e1 ? __ldg(s0 + r.o0 + 1) : 0u, p2 = e2 ? __ldg(s0 + r.o0 + 2) : 0u, p3 = e3 ? __ldg(s0 + r.o0 + 3) : 0u;
+        unsigned q0 = __ldg(s0 + r.o1), q1 = e1 ? __ldg(s0 + r.o1 + 1) : 0u, q2 = e2 ? __ldg(s0 + r.o1 + 2) : 0u, q3 = e3 ? __ldg(s0 + r.o1 + 3) : 0u;
+        for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
+            const RowS rn = sh.row[y + 1 < img_h ? y + 1 : y];
+            const unsigned* __restrict__ pn = s0 + rn.o0;
+            const unsigned* __restrict__ qn = s0 + rn.o1;
+            const unsigned np0 = __ldg(pn), np1 = e1 ? __ldg(pn + 1) : 0u, np2 = e2 ? __ldg(pn + 2) : 0u, np3 = e3 ? __ldg(pn + 3) : 0u;
+            const unsigned nq0 = __ldg(qn), nq1 = e1 ? __ldg(qn + 1) : 0u, nq2 = e2 ? __ldg(qn + 2) : 0u, nq3 = e3 ? __ldg(qn + 3) : 0u;
+            unsigned a0 = 0, a1 = 0, a2 = 0;
+#define RT_ACC(w, x0, x1, x2) x0 = __dp4a(w, 0x00000001u, x0); x1 = __dp4a(w, 0x00000100u, x1); x2 = __dp4a(w, 0x00010000u, x2)
+            RT_ACC(p0, a0, a1, a2); RT_ACC(p1, a0, a1, a2); RT_ACC(p2, a0, a1, a2); RT_ACC(p3, a0, a1, a2);
+            if (r.fv < 0.0f) {           // the window is one source row: 1 x nx block mean (block-uniform branch)
+                *d0 = sh.lut[((a0 + h2) * M) >> 20];
+                *d1 = sh.lut[((a1 + h2) * M) >> 20];
+                *d2 = sh.lut[((a2 + h2) * M) >> 20];
+            } else {
+                unsigned c0 = 0, c1 = 0, c2 = 0;
+                RT_ACC(q0, c0, c1, c2); RT_ACC(q1, c0, c1, c2); RT_ACC(q2, c0, c1, c2); RT_ACC(q3, c0, c1, c2);
+                const float fb = sh.fb[y][nx - 1], ft = sh.ft[y][nx - 1];
+                *d0 = lut_trunc(__fadd_rn(__fmul_rn(fb, u32f(a0)), __fmul_rn(ft, u32f(c0))), lut_biased);
+                *d1 = lut_trunc(__fadd_rn(__fmul_rn(fb, u32f(a1)), __fmul_rn(ft, u32f(c1))), lut_biased);
+                *d2 = lut_trunc(__fadd_rn(__fmul_rn(fb, u32f(a2)), __fmul_rn(ft, u32f(c2))), lut_biased);
+            }
+#undef RT_ACC
+            r = rn; p0 = np0; p1 = np1; p2 = np2; p3 = np3; q0 = nq0; q1 = nq1; q2 = nq2; q3 = nq3;
         }
         return;
     }
@@ -336,7 +373,7 @@ retto_b200_status rt_build_batches_prepare(retto_b200_ctx* ctx, int32_t kind, co
     const int img_h = kind == 0 ? ctx->cfg.cls_image_shape[1] : ctx->cfg.rec_image_shape[1];
     if (img_h > BB_MAX_H) { ctx->set_error("build_batches: image_shape height > 64 is not supported"); return RETTO_B200_ERR_UNSUPPORTED; }
     const bool force_generic = getenv("RETTO_B200_BB_GENERIC") != nullptr;   // tests: every line through thumbnail_pixel
-    size_t n_chunks[5] = {0, 0, 0, 0, 0};
+    size_t n_chunks[6] = {0, 0, 0, 0, 0, 0};
     std::vector<LineDev>& lines = ctx->bb_lines;
     lines.resize(n_lines);
     for (int i = 0; i < n_lines; ++i) {
@@ -354,20 +391,21 @@ retto_b200_status rt_build_batches_prepare(retto_b200_ctx* ctx, int32_t kind, co
         if (cw <= rw && ch <= img_h) k = BB_FF;
         else if (cw >= rw && ch >= img_h && nx_max <= 2 && ny_max <= 2) k = BB_BB2;
         else if (cw >= rw && ch >= img_h && nx_max * ny_max <= BB_BB_MAXN) k = BB_BB;
+        else if (cw > rw && ch < img_h && nx_max <= 4) k = BB_BF4;
         else if (cw > rw && ch < img_h && nx_max <= BB_BF_MAXN) k = BB_BF;
         if (force_generic) k = BB_GEN;
         lines[i] = LineDev{l.crop, l.img_w, l.resized_w, k, l.dst_offset};
         n_chunks[k] += (size_t)(l.img_w + BB_COLS - 1) / BB_COLS;
     }
-    const size_t total_chunks = n_chunks[0] + n_chunks[1] + n_chunks[2] + n_chunks[3] + n_chunks[4];
+    const size_t total_chunks = n_chunks[0] + n_chunks[1] + n_chunks[2] + n_chunks[3] + n_chunks[4] + n_chunks[5];
     const size_t lb = (sizeof(LineDev) * n_lines + 15) & ~size_t(15);
     std::vector<char>& blob = ctx->bb_blob;
     blob.resize(lb + sizeof(ChunkDev) * total_chunks);
     memcpy(blob.data(), lines.data(), sizeof(LineDev) * n_lines);
     ChunkDev* ck = reinterpret_cast<ChunkDev*>(blob.data() + lb);
-    size_t cur[5];
-    cur[BB_GEN] = 0; cur[BB_BF] = n_chunks[BB_GEN]; cur[BB_BB] = cur[BB_BF] + n_chunks[BB_BF]; cur[BB_BB2] = cur[BB_BB] + n_chunks[BB_BB];
-    cur[BB_FF] = cur[BB_BB2] + n_chunks[BB_BB2];
+    size_t cur[6];
+    cur[BB_GEN] = 0; cur[BB_BF] = n_chunks[BB_GEN]; cur[BB_BB] = cur[BB_BF] + n_chunks[BB_BF]; cur[BB_BF4] = cur[BB_BB] + n_chunks[BB_BB];
+    cur[BB_BB2] = cur[BB_BF4] + n_chunks[BB_BF4]; cur[BB_FF] = cur[BB_BB2] + n_chunks[BB_BB2];
     for (int i = 0; i < n_lines; ++i) {
         size_t& c = cur[lines[i].kind];
         for (int x0 = 0; x0 < lines[i].img_w; x0 += BB_COLS) ck[c++] = ChunkDev{i, x0};
