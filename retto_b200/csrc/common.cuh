@@ -189,6 +189,7 @@ struct retto_b200_ctx {
     // det post state (kept for the fetch_* taps and for crop jobs)
     std::vector<DetPostPage> dp_pages;
     std::vector<int> dp_ncomp;
+    std::vector<char> dp_labels_final;   // per page: run-interior labels resolved (lazily, by fetch_labels)
     std::vector<int32_t> dbg_extra;
     bool dp_trace_enabled = false, dp_trace_valid = false;
     DevBuf d_trace;

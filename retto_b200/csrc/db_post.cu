@@ -250,6 +250,12 @@ __global__ void __launch_bounds__(128) ccl_flatten_kernel(const DetPostPage* __r
         for (int j = 0; j < 4; ++j) {
             const unsigned cb = cur >> j;
             if (!(cb & 2u)) continue;
+            // Only the two ends of a run are resolved to the component root here: nothing downstream reads the label of a
+            // run-interior pixel (run_end_kernel looks at run ends only), and such a pixel still points at its run start,
+            // whose label IS the root after this pass — labels_finalize_kernel resolves that one hop when the label plane
+            // is asked for (retto_b200_det_post_fetch_labels).
+            // (runs are labelled per 128-px strip: the first pixel of a strip is the representative of a run entering from the left)
+            if ((cb & 5u) == 5u && !(j == 0 && lane == 0)) continue;
             const int p = y * W + x + j;
             const int l = L[p];
             const int r = find_root(L, l);
@@ -267,6 +273,14 @@ __global__ void __launch_bounds__(128) ccl_flatten_kernel(const DetPostPage* __r
             if ((is_start && x + j > 0) || (is_end && x + j + 1 < W)) atomicMin(&keyp[r], p);
         }
     }
+}
+
+// labels of run-interior pixels: one hop through their run start (see ccl_flatten_kernel)
+__global__ void labels_finalize_kernel(const unsigned char* __restrict__ bitmap, int* __restrict__ labels, long long base, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !bitmap[base + i]) return;
+    const int l = labels[base + i];
+    if (l >= 0) labels[base + i] = labels[base + l];
 }
 
 // ascending bitonic sort of r[0..n) by the whole block (r must have room for the next power of two)
@@ -808,6 +822,7 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
         ctx->dp_pages.push_back(pg);
     }
     const int total_tiles = tile_prefix[n];
+    ctx->dp_labels_final.assign(n, 0);
     cudaStream_t st = ctx->stream;
     // device state
     {
@@ -1079,6 +1094,12 @@ extern "C" retto_b200_status retto_b200_det_post_fetch_bitmap(retto_b200_ctx* ct
 extern "C" retto_b200_status retto_b200_det_post_fetch_labels(retto_b200_ctx* ctx, int32_t page, int32_t* h_labels) {
     if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !h_labels) return RETTO_B200_ERR_INVALID_ARG;
     const DetPostPage& pg = ctx->dp_pages[page];
+    if (!ctx->dp_labels_final[page]) {
+        RT_LAUNCH_BEGIN(ctx, "labels_finalize_kernel");
+        labels_finalize_kernel<<<(pg.h * pg.w + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_bitmap.as<unsigned char>(), ctx->d_labels.as<int>(), pg.px_base, pg.h * pg.w);
+        RT_LAUNCH_CHECK(ctx);
+        ctx->dp_labels_final[page] = 1;
+    }
     RT_CUDA_OK(ctx, cudaMemcpyAsync(h_labels, ctx->d_labels.as<int>() + pg.px_base, sizeof(int) * (size_t)pg.h * pg.w, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return RETTO_B200_OK;
