@@ -178,6 +178,35 @@ __device__ __forceinline__ void load_bits6(const unsigned char* __restrict__ bm,
     bits6 = left | (t << 1) | (right << 5);
 }
 
+// load_bits6 in two halves, so that the loads of row y+1 can be issued before row y is processed (the tile passes below
+// are chains of dependent global accesses per row; this takes the bitmap load out of the chain)
+struct RawRow { unsigned v, e; };   // v: the 4 bitmap bytes of this lane; e: neighbour byte of lane 0 / lane 31
+__device__ __forceinline__ RawRow load_raw_row(const unsigned char* __restrict__ bm, int W, int y, int x, int x0, int lane, bool valid_row) {
+    RawRow r; r.v = 0; r.e = 0;
+    if (!valid_row) return r;
+    if (x < W) {
+        if ((W & 3) == 0) r.v = *reinterpret_cast<const unsigned*>(bm + (size_t)y * W + x);
+        else {
+            unsigned t = 0;
+            for (int j = 0; j < 4; ++j)
+                if (x + j < W && bm[(size_t)y * W + x + j]) t |= 0xffu << (8 * j);
+            r.v = t;
+        }
+    }
+    if (lane == 0 && x0 > 0) r.e = bm[(size_t)y * W + x0 - 1];
+    if (lane == 31 && x0 + TILE_W < W) r.e = bm[(size_t)y * W + x0 + TILE_W];
+    return r;
+}
+__device__ __forceinline__ unsigned bits6_of(const RawRow r, int lane) {
+    const unsigned v = r.v;
+    const unsigned t = ((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 2u : 0u) | ((v & 0xff0000u) ? 4u : 0u) | ((v & 0xff000000u) ? 8u : 0u);
+    unsigned left = __shfl_up_sync(RT_FULL, (t >> 3) & 1u, 1);
+    unsigned right = __shfl_down_sync(RT_FULL, t & 1u, 1);
+    if (lane == 0) left = r.e ? 1u : 0u;
+    if (lane == 31) right = r.e ? 1u : 0u;
+    return left | (t << 1) | (right << 5);
+}
+
 // ---- B: merge runs (8-connectivity) + Euler number ----------------------------------------------
 __global__ void __launch_bounds__(128) ccl_merge_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix, int n_pages,
                                                          int total_tiles, const unsigned char* __restrict__ bitmap, int* __restrict__ labels,
@@ -194,9 +223,11 @@ __global__ void __launch_bounds__(128) ccl_merge_kernel(const DetPostPage* __res
     unsigned up;
     load_bits6(bm, W, y0 - 1, x, x0, lane, y0 > 0, up);
     int euler = 0;
+    RawRow nxt = load_raw_row(bm, W, y0, x, x0, lane, true);
     for (int y = y0; y < y1; ++y) {
-        unsigned cur;
-        load_bits6(bm, W, y, x, x0, lane, true, cur);
+        const RawRow raw = nxt;
+        nxt = load_raw_row(bm, W, y + 1, x, x0, lane, y + 1 < y1);
+        const unsigned cur = bits6_of(raw, lane);
         if (cur & 0x1eu) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -242,9 +273,11 @@ __global__ void __launch_bounds__(128) ccl_flatten_kernel(const DetPostPage* __r
     int* L = labels + pg.px_base;
     int* ymax_at = cid_at + pg.px_base;
     int* keyp = key_at + pg.px_base;
+    RawRow nxt = load_raw_row(bm, W, y0, x, x0, lane, true);
     for (int y = y0; y < y1; ++y) {
-        unsigned cur;
-        load_bits6(bm, W, y, x, x0, lane, true, cur);
+        const RawRow raw = nxt;
+        nxt = load_raw_row(bm, W, y + 1, x, x0, lane, y + 1 < y1);
+        const unsigned cur = bits6_of(raw, lane);
         if (!(cur & 0x1eu)) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -372,9 +405,11 @@ __global__ void __launch_bounds__(128) run_end_kernel(const DetPostPage* __restr
     const int* cid = cid_at + pg.px_base;
     CompRec* c = comps + (size_t)page * max_comps;
     int2* rt = rowtab + (size_t)page * ROWCAP;
+    RawRow nxt = load_raw_row(bm, W, y0, x, x0, lane, true);
     for (int y = y0; y < y1; ++y) {
-        unsigned cur;
-        load_bits6(bm, W, y, x, x0, lane, true, cur);
+        const RawRow raw = nxt;
+        nxt = load_raw_row(bm, W, y + 1, x, x0, lane, y + 1 < y1);
+        const unsigned cur = bits6_of(raw, lane);
         if (!(cur & 0x1eu)) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
