@@ -68,6 +68,13 @@ __global__ void __launch_bounds__(256) det_pre_identity_kernel(const DetPreDev* 
 // general path: one thread per 4 consecutive output pixels of one row (out_w is a multiple of 32)
 __global__ void __launch_bounds__(256) det_pre_resize_kernel(const DetPreDev* __restrict__ pages, const int* __restrict__ unit_prefix,
                                                               int n_pages, int total_units, NormParams np) {
+    // normalisation table: the reference's three separately rounded f32 operations per (channel, byte value)
+    __shared__ float s_lut[3][256];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        s_lut[c][v] = norm1((unsigned char)v, np.scale, np.mean[c], np.stdv[c]);
+    }
+    __syncthreads();
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= total_units) return;
     const int p = rt_find_segment(unit_prefix, n_pages, u);
@@ -85,9 +92,9 @@ __global__ void __launch_bounds__(256) det_pre_resize_kernel(const DetPreDev* __
         const ThumbAxis ax = thumb_axis(ox0 + i, xr, (unsigned)pg.w);
         unsigned char px[3];
         thumbnail_pixel(rd, (unsigned)pg.w, (unsigned)pg.h, ax, ay, px);
-        o[0][i] = norm1(px[2], np.scale, np.mean[0], np.stdv[0]);
-        o[1][i] = norm1(px[1], np.scale, np.mean[1], np.stdv[1]);
-        o[2][i] = norm1(px[0], np.scale, np.mean[2], np.stdv[2]);
+        o[0][i] = s_lut[0][px[2]];
+        o[1][i] = s_lut[1][px[1]];
+        o[2][i] = s_lut[2][px[0]];
     }
     const size_t off = (size_t)oy * pg.ow + ox0;
 #pragma unroll

@@ -46,7 +46,16 @@ __device__ __forceinline__ void thumbnail_pixel(const Reader& rd, unsigned w, un
             }
         const unsigned n = (right - left) * (top - bottom);
         const unsigned r = n >> 1;
-        unsigned v0 = (s0 + r) / n, v1 = (s1 + r) / n, v2 = (s2 + r) / n;
+        unsigned v0, v1, v2;
+        if (n == 1) { v0 = s0; v1 = s1; v2 = s2; }
+        else if (n < 4096) {
+            // (s + r) / n without three integer divisions: floor((x + 0.5) * (1/n)) is exact here — (x + 0.5) / n is at least
+            // 0.5/n away from every integer, and the two roundings move the product by less than 255.5 * 2^-22 < 0.5/4096
+            const float inv = __frcp_rn((float)n);
+            v0 = __float2uint_rd(__fmul_rn(__fadd_rn((float)(s0 + r), 0.5f), inv));
+            v1 = __float2uint_rd(__fmul_rn(__fadd_rn((float)(s1 + r), 0.5f), inv));
+            v2 = __float2uint_rd(__fmul_rn(__fadd_rn((float)(s2 + r), 0.5f), inv));
+        } else { v0 = (s0 + r) / n; v1 = (s1 + r) / n; v2 = (s2 + r) / n; }
         out[0] = (unsigned char)(v0 > 255 ? 255 : v0);
         out[1] = (unsigned char)(v1 > 255 ? 255 : v1);
         out[2] = (unsigned char)(v2 > 255 ? 255 : v2);
