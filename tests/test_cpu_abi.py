@@ -105,3 +105,17 @@ def test_shard_indices_lpt():
     loads = [sum(sizes[i] for i in p) for p in parts]
     assert max(loads) == 100 and all(p == sorted(p) for p in parts)
     assert shard_indices([5, 5, 5, 5], 2) == [[0, 2], [1, 3]]
+
+
+def test_cli_surface(tmp_path):
+    """retto-cli flags (main.rs:18-39) are accepted under the same names, files are found like WalkDir does"""
+    from retto_b200 import cli
+    a = cli.build_parser().parse_args(["-i", str(tmp_path), "--det-model-path", "d.onnx", "--cls-model-path", "c.onnx", "--rec-model-path", "r.onnx",
+                                       "--rec-keys-path", "k.txt", "--device", "b200", "--device-id", "1", "--gpus", "2"])
+    assert (a.images, a.det_model_path, a.device, a.device_id, a.gpus) == (str(tmp_path), "d.onnx", "b200", 1, 2)
+    assert cli.build_parser().prog == "ratio-cli"
+    (tmp_path / "sub").mkdir()
+    for n in ("b.png", "a.png", "sub/c.png"):
+        (tmp_path / n).write_bytes(b"x")
+    assert [os.path.relpath(f, tmp_path) for f in cli.find_files(str(tmp_path))] == ["a.png", "b.png", "sub/c.png"]
+    assert cli.find_files(str(tmp_path / "a.png")) == [str(tmp_path / "a.png")]

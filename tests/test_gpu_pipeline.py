@@ -1,5 +1,6 @@
 """GPU parity: rotate-crop (K7), cls/rec batch build (K8), cls postprocess + flip (K9) and the whole
 RettoSession::process_pipeline against the CPU oracle pipeline — boxes, labels, strings bit-exact."""
+import os
 import zlib
 
 import numpy as np
@@ -311,24 +312,7 @@ def test_session_empty_page(ctx, synth_dict):
     assert r.status == 0 and r.det_result == [] and r.cls_result == [] and r.rec_result == []
 
 
-class StatelessWorker:
-    """stand-in forwards whose every output is a function of the input tensor only (any batching gives the same rows)"""
-
-    def det(self, x):
-        g = (x[0].mean(axis=0) + 1.0) / 2.0
-        return np.clip(1.0 - g, 0.0, 1.0).astype(np.float32)[None, None]
-
-    def cls(self, x):
-        s = x.reshape(x.shape[0], -1).mean(axis=1)
-        return np.stack([np.where(s > -0.6, 0.95, 0.05), np.where(s > -0.6, 0.05, 0.95)], 1).astype(np.float32)
-
-    def rec(self, x):
-        n, T = x.shape[0], x.shape[3] // 8
-        out = np.zeros((n, T, 6625), np.float32)
-        for i in range(n):
-            rng2 = np.random.default_rng(zlib.crc32(np.ascontiguousarray(x[i]).tobytes()))
-            out[i, np.arange(T), rng2.integers(0, 6625, T)] = 0.5 + 0.5 * rng2.random(T, dtype=np.float32)
-        return out
+from tools.demo_worker import StatelessWorker  # noqa: E402  (forwards that depend on the input tensor only)
 
 
 def _small_pages(n, seed):
@@ -401,3 +385,34 @@ def test_session_chunked_pipeline_equals_unchunked(ctx, synth_dict, pinned):
             assert np.array_equal(a.boxes, b.boxes) and a.score == b.score
         assert [c.label for c in one.cls_result] == [c.label for c in batch[i].cls_result]
         assert [r.text for r in one.rec_result] == [r.text for r in batch[i].rec_result]
+
+
+def test_cli_entry_point(ctx, synth_dict, tmp_path, capsys):
+    """retto-cli surface (main.rs:18-95): files in a directory -> the three result lines per image + the summary line;
+    the JSON objects equal a direct RettoSession run on the decoded pages"""
+    import json
+    from PIL import Image
+    from retto_b200 import cli
+    imgs = _small_pages(5, 21)
+    (tmp_path / "imgs" / "sub").mkdir(parents=True)
+    names = ["imgs/a.png", "imgs/b.png", "imgs/sub/c.png", "imgs/sub/d.png", "imgs/z.png"]
+    for n, im in zip(names, imgs):
+        Image.fromarray(im).save(tmp_path / n)
+    (tmp_path / "keys.txt").write_text(synth_dict, encoding="utf-8")
+    rc = cli.main(["-i", str(tmp_path / "imgs"), "--device", "b200", "--rec-keys-path", str(tmp_path / "keys.txt"),
+                   "--worker", "tools.demo_worker:make_worker", "--batch-pages", "2", "--json"])
+    assert rc == 0
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "Found 5 files, processing..." and out[-1].startswith("Successfully processed 5 images, avg time: ")
+    assert sum(l.startswith("Det result: DetProcessorResult([") for l in out) == 5
+    assert sum(l.startswith("Cls result: ClsProcessorResult([") for l in out) == 5
+    assert sum(l.startswith("Rec result: RecProcessorResult([") for l in out) == 5
+    js = [json.loads(l) for l in out if l.startswith("{")]
+    files = sorted(str(tmp_path / n) for n in names)
+    assert [j["file"] for j in js] == files
+    sess = _session(ctx, StatelessWorker(), synth_dict)
+    for j in js:
+        im = imgs[names.index(os.path.relpath(j["file"], tmp_path))]
+        want = sess.run(im).to_json()
+        assert len(want["det_result"]) > 0
+        assert json.dumps(want, sort_keys=True) == json.dumps({k: j[k] for k in ("det_result", "cls_result", "rec_result")}, sort_keys=True)
