@@ -174,11 +174,34 @@ retto_b200_status rt_stage_begin(retto_b200_ctx* ctx, size_t bytes, int* slot, v
     *p = sl.p;
     return RETTO_B200_OK;
 }
+// Descriptor upload by the SMs (pinned memory is device-accessible): used while run_pages streams host pages through the
+// H2D copy engine, where a small cudaMemcpyAsync on the compute stream would queue behind megabytes of page copies in
+// the same engine FIFO and stall the kernels waiting for their tables.
+__global__ void __launch_bounds__(256) stage_pull_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t bytes) {
+    const size_t n16 = bytes / 16;
+    const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src);
+    uint4* __restrict__ d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+    for (size_t i = n16 * 16 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static retto_b200_status stage_copy(retto_b200_ctx* ctx, void* d_dst, const void* h_pinned, size_t bytes) {
+    if (ctx->uploads_by_sm && ((uintptr_t)d_dst % 16 == 0)) {
+        void* dp = nullptr;
+        RT_CUDA_OK(ctx, cudaHostGetDevicePointer(&dp, const_cast<void*>(h_pinned), 0));
+        const unsigned blocks = (unsigned)std::min<size_t>(8, (bytes + 16383) / 16384);
+        stage_pull_kernel<<<std::max(1u, blocks), 256, 0, ctx->stream>>>(reinterpret_cast<unsigned char*>(d_dst), reinterpret_cast<const unsigned char*>(dp), bytes);
+        ctx->launches++;
+        RT_CUDA_OK(ctx, cudaGetLastError());
+        return RETTO_B200_OK;
+    }
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(d_dst, h_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return RETTO_B200_OK;
+}
 // enqueue the H2D copy of a slot filled in place (no intermediate host copy)
 retto_b200_status rt_stage_commit(retto_b200_ctx* ctx, DevBuf& dst, int slot, size_t bytes) {
     auto& sl = ctx->stage_slots[slot];
     RT_CUDA_OK(ctx, dst.ensure(bytes ? bytes : 16, ctx->stream));
-    if (bytes) RT_CUDA_OK(ctx, cudaMemcpyAsync(dst.p, sl.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) RT_TRY(stage_copy(ctx, dst.p, sl.p, bytes));
     RT_CUDA_OK(ctx, cudaEventRecord(sl.ev, ctx->stream));
     return RETTO_B200_OK;
 }
@@ -188,7 +211,7 @@ retto_b200_status rt_upload_to(retto_b200_ctx* ctx, void* d_dst, const void* src
     void* p = nullptr;
     RT_TRY(rt_stage_begin(ctx, bytes, &slot, &p));
     memcpy(p, src, bytes);
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(d_dst, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RT_TRY(stage_copy(ctx, d_dst, p, bytes));
     RT_CUDA_OK(ctx, cudaEventRecord(ctx->stage_slots[slot].ev, ctx->stream));
     return RETTO_B200_OK;
 }

@@ -174,6 +174,7 @@ struct retto_b200_ctx {
     DevBuf d_stage, d_stage2, d_stage3;
     struct StageSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool busy = false; };
     std::vector<StageSlot> stage_slots;
+    bool uploads_by_sm = false;   // descriptor uploads through stage_pull_kernel instead of the H2D copy engine (capi.cu)
     HostBuf h_scale;   // deferred scale_and_clip read-back (session.cu)
 
     // dictionary (rec_processor.rs:29-46)
