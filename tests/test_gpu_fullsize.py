@@ -1,6 +1,7 @@
 """BASELINE.json full-size configurations, checked through size-independent properties plus oracle spot checks.
   config 2: DB postprocess on 1024 synthetic 960x960 probability maps in ONE batched call
   config 3: CTC decode of 16384 lines of 40 x 6625 logits (17.4 GB) in ONE call
+  config 4: 256 pages 1280x1280 end to end from host memory (batch independence + oracle spot checks)
 """
 import numpy as np
 import pytest
@@ -87,3 +88,42 @@ def test_config3_ctc_16k_lines(ctx, synth_dict):
     chars = O.rec_character(synth_dict)
     assert np.array_equal(tokens[sel][:, :T], ot) and np.array_equal(scores[sel], osc, equal_nan=True)
     assert [texts[i] for i in sel] == [O.tokens_to_text(ot[k], oc[k], chars) for k in range(256)]
+
+
+def test_config4_256_pages_1280_end_to_end(ctx, synth_dict):
+    """config 4: 256 rendered 1280x1280 pages (32 unique x 8) from HOST memory through retto_b200_run_pages — the chunked
+    upload pipeline, every stage batched over the unit.  Properties: replicas of a page give identical results wherever
+    they sit in the batch (batch independence), every detected line has a box / label / string, and two of the pages
+    are checked against the CPU oracle pipeline run with the same stand-in forwards."""
+    from oracle import oracle as O
+    from oracle.pipeline import run_page
+    from retto_b200.session import CallableWorker, RettoSession
+    from tools.demo_worker import StatelessWorker
+    from tools.synth import gen_page
+    uniq = [gen_page(4 + i, 1280, 1280)[0] for i in range(32)]
+    pages = [uniq[i % 32] for i in range(256)]
+    w = StatelessWorker()
+    ctx.dict_load(synth_dict)
+    sess = RettoSession(worker=CallableWorker(w.det, w.cls, w.rec), ctx=ctx)
+    got = sess.run_pages(pages)
+    assert len(got) == 256 and all(r.status == 0 for r in got)
+    n_lines = sum(len(r.det_result) for r in got)
+    assert n_lines > 256 * 10
+    for i in range(32, 256):
+        a, b = got[i % 32], got[i]
+        assert len(a.det_result) == len(b.det_result) == len(b.cls_result) == len(b.rec_result)
+        for x, y in zip(a.det_result, b.det_result):
+            assert np.array_equal(x.boxes, y.boxes) and x.score == y.score
+        assert [c.label for c in a.cls_result] == [c.label for c in b.cls_result]
+        assert [r.text for r in a.rec_result] == [r.text for r in b.rec_result]
+    O.set_libm(1)
+    try:
+        for i in (0, 17):
+            ref = run_page(uniq[i], w, synth_dict)
+            assert len(ref["boxes"]) == len(got[i].det_result) > 0
+            for k in range(len(ref["boxes"])):
+                assert np.array_equal(got[i].det_result[k].boxes, ref["boxes"][k])
+                assert got[i].cls_result[k].label == ref["cls"][k][0]
+                assert got[i].rec_result[k].text == ref["rec"][k][0]
+    finally:
+        O.set_libm(0)
