@@ -13,7 +13,16 @@
 struct DetPreDev {
     const unsigned char* src; int h, w;
     float* dst; int oh, ow;
+    float xr, yr;   // w / ow, h / oh as f32 (thumbnail's x_ratio / y_ratio), computed once on the host: IEEE division, same bits
 };
+// the page a work unit belongs to: one binary search per block (thread 0), per-thread search only for the units of a
+// block that straddle a page boundary
+__device__ __forceinline__ int unit_page(const int* __restrict__ unit_prefix, int n, int u, int* s_first) {
+    if (threadIdx.x == 0) *s_first = rt_find_segment(unit_prefix, n, blockIdx.x * blockDim.x);
+    __syncthreads();
+    const int p = *s_first;
+    return u < unit_prefix[p + 1] ? p : rt_find_segment(unit_prefix, n, u);
+}
 
 struct NormParams {
     float scale, mean[3], stdv[3];  // tensor channel c (B,G,R) uses mean[c], std[c]
@@ -74,15 +83,15 @@ __global__ void __launch_bounds__(256) det_pre_resize_kernel(const DetPreDev* __
         const int c = i >> 8, v = i & 255;
         s_lut[c][v] = norm1((unsigned char)v, np.scale, np.mean[c], np.stdv[c]);
     }
-    __syncthreads();
+    __shared__ int s_first;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = unit_page(unit_prefix, n_pages, min(u, total_units - 1), &s_first);   // (also the barrier for s_lut)
     if (u >= total_units) return;
-    const int p = rt_find_segment(unit_prefix, n_pages, u);
     const DetPreDev pg = pages[p];
     const int lu = u - unit_prefix[p];
     const int upr = pg.ow >> 2;
     const int oy = lu / upr, ox0 = (lu - oy * upr) << 2;
-    const float xr = __fdiv_rn((float)pg.w, (float)pg.ow), yr = __fdiv_rn((float)pg.h, (float)pg.oh);
+    const float xr = pg.xr, yr = pg.yr;
     const ThumbAxis ay = thumb_axis(oy, yr, (unsigned)pg.h);
     const PlainReader rd{pg.src, (unsigned)pg.w};
     const size_t plane = (size_t)pg.oh * pg.ow;
@@ -118,23 +127,46 @@ __global__ void det_pre_scalar_kernel(DetPreDev pg, NormParams np) {
     pg.dst[2 * plane + i] = norm1(px[0], np.scale, np.mean[2], np.stdv[2]);
 }
 
-// stand-alone thumbnail (u8 HWC -> u8 HWC), one thread per output pixel
+// stand-alone thumbnail (u8 HWC -> u8 HWC): one thread per PXT consecutive output pixels of a row (4 when the output
+// width is a multiple of 4 — resize_both always yields multiples of 32 — so the row axis and the index arithmetic are
+// shared and the 12 result bytes leave as three aligned words)
 struct ResizeDev {
     const unsigned char* src; int h, w;
     unsigned char* dst; int oh, ow;
+    float xr, yr;
+    int pxt;
 };
 __global__ void __launch_bounds__(256) thumbnail_kernel(const ResizeDev* __restrict__ jobs, const int* __restrict__ unit_prefix, int n_jobs,
                                                          int total_units) {
+    __shared__ int s_first;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = unit_page(unit_prefix, n_jobs, min(u, total_units - 1), &s_first);
     if (u >= total_units) return;
-    const int p = rt_find_segment(unit_prefix, n_jobs, u);
     const ResizeDev jb = jobs[p];
     const int lu = u - unit_prefix[p];
-    const int oy = lu / jb.ow, ox = lu - oy * jb.ow;
-    const float xr = __fdiv_rn((float)jb.w, (float)jb.ow), yr = __fdiv_rn((float)jb.h, (float)jb.oh);
     const PlainReader rd{jb.src, (unsigned)jb.w};
+    if (jb.pxt == 4) {
+        const int upr = jb.ow >> 2;
+        const int oy = lu / upr, ox0 = (lu - oy * upr) << 2;
+        const ThumbAxis ay = thumb_axis(oy, jb.yr, (unsigned)jb.h);
+        unsigned char px[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) thumbnail_pixel(rd, (unsigned)jb.w, (unsigned)jb.h, thumb_axis(ox0 + i, jb.xr, (unsigned)jb.w), ay, px[i]);
+        unsigned char* d = jb.dst + ((size_t)oy * jb.ow + ox0) * 3;
+        if ((((uintptr_t)d) & 3) == 0) {
+            unsigned* dw = reinterpret_cast<unsigned*>(d);
+            dw[0] = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | ((unsigned)px[1][0] << 24);
+            dw[1] = px[1][1] | (px[1][2] << 8) | (px[2][0] << 16) | ((unsigned)px[2][1] << 24);
+            dw[2] = px[2][2] | (px[3][0] << 8) | (px[3][1] << 16) | ((unsigned)px[3][2] << 24);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { d[3 * i] = px[i][0]; d[3 * i + 1] = px[i][1]; d[3 * i + 2] = px[i][2]; }
+        }
+        return;
+    }
+    const int oy = lu / jb.ow, ox = lu - oy * jb.ow;
     unsigned char px[3];
-    thumbnail_pixel(rd, (unsigned)jb.w, (unsigned)jb.h, thumb_axis(ox, xr, (unsigned)jb.w), thumb_axis(oy, yr, (unsigned)jb.h), px);
+    thumbnail_pixel(rd, (unsigned)jb.w, (unsigned)jb.h, thumb_axis(ox, jb.xr, (unsigned)jb.w), thumb_axis(oy, jb.yr, (unsigned)jb.h), px);
     unsigned char* d = jb.dst + (size_t)lu * 3;
     d[0] = px[0]; d[1] = px[1]; d[2] = px[2];
 }
@@ -201,7 +233,7 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
             ctx->set_error("det_preprocess: bad descriptor " + std::to_string(i));
             return RETTO_B200_ERR_INVALID_ARG;
         }
-        const DetPreDev dv{d.d_rgb, d.h, d.w, d.d_out, d.out_h, d.out_w};
+        const DetPreDev dv{d.d_rgb, d.h, d.w, d.d_out, d.out_h, d.out_w, (float)d.w / (float)d.out_w, (float)d.h / (float)d.out_h};
         const long long px = (long long)d.out_h * d.out_w;
         const bool aligned = ((uintptr_t)d.d_rgb % 16 == 0) && ((uintptr_t)d.d_out % 16 == 0);
         if (d.out_h == d.h && d.out_w == d.w && (px % 512 == 0) && aligned) {
@@ -246,8 +278,9 @@ extern "C" retto_b200_status retto_b200_thumbnail(retto_b200_ctx* ctx, const ret
             ctx->set_error("thumbnail: bad descriptor " + std::to_string(i));
             return RETTO_B200_ERR_INVALID_ARG;
         }
-        jobs.push_back(ResizeDev{d.d_src, d.h, d.w, d.d_dst, d.out_h, d.out_w});
-        pre.push_back(pre.back() + d.out_h * d.out_w);
+        const int pxt = (d.out_w % 4 == 0) ? 4 : 1;
+        jobs.push_back(ResizeDev{d.d_src, d.h, d.w, d.d_dst, d.out_h, d.out_w, (float)d.w / (float)d.out_w, (float)d.h / (float)d.out_h, pxt});
+        pre.push_back(pre.back() + d.out_h * d.out_w / pxt);
     }
     const ResizeDev* dv; const int* dp;
     RT_TRY(upload_with_prefix(ctx, ctx->d_stage3, jobs, pre, &dv, &dp));

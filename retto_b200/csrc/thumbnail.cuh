@@ -23,7 +23,7 @@ __device__ __forceinline__ ThumbAxis thumb_axis(int out_i, float ratio, unsigned
     ThumbAxis a;
     a.lo = lo;
     a.hi = hi;
-    a.fract = __fdiv_rn(__fadd_rn(rt_fract(lof), rt_fract(hif)), 2.0f);
+    a.fract = __fmul_rn(__fadd_rn(rt_fract(lof), rt_fract(hif)), 0.5f);   // "/ 2.0": halving is exact, same bits as the division
     return a;
 }
 
