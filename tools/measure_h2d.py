@@ -1,3 +1,5 @@
+"""pure copy-engine H2D bandwidth from pinned memory: one 1.26 GB copy, then the same bytes as 256 page-sized copies
+(B200 pod, this round: 55.6 GB/s and 53.0 GB/s) — the ceiling the e2e number of bench.py is measured against"""
 import sys, time, ctypes as C, numpy as np, torch
 sys.path.insert(0, '.')
 from retto_b200.api import Context
