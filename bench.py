@@ -257,6 +257,8 @@ def algorithmic_bytes(name, info, launch_idx=0):
         return 4.0 * info["rec_rows"] * C_CLASSES
     if name.startswith("det_pre_identity"):
         return 15.0 * HW                      # 3 B in + 12 B out per pixel
+    if name.startswith("bitmap_runs2"):
+        return 5.0 * HW                       # prob read 4 + bitmap write 1 (run-table CCL: the label plane is not materialised)
     if name.startswith("bitmap_runs"):
         return 9.0 * HW                       # prob read 4 + bitmap write 1 + label write 4
     if name.startswith("crop_rows"):
@@ -453,12 +455,13 @@ def main():
                 "timed_in": "a repeat of the value pass with per-kernel CUDA events enabled (summary.serial_pass)",
                 "frac_of_nominal_8TBs": (top_k["gbs"] / 8000.0) if top_k.get("gbs") else None}
     # the DB-postprocess unit (K2..K6) as SURVEY §8(d) defines it: 9*H*W bytes over the sum of its kernels
-    db_names = ["zero_counters", "bitmap_runs", "ccl_merge", "ccl_flatten", "comp_sort", "run_end", "row_alloc", "box_geometry", "page_sort", "pack_"]
+    db_names = ["zero_counters", "bitmap_runs", "ccl_runs", "ccl_merge", "ccl_flatten", "comp_sort", "run_end", "row_alloc", "box_geometry", "page_sort", "pack_"]
     db_ms = sum(v["ms_per_step"] for k, v in kernels.items() if any(k.startswith(n) for n in db_names))
-    path_bytes = (15.0 * info["det_px"] + 9.0 * info["det_px"] + 6.0 * crop_px + 2 * 3.0 * crop_px + 4.0 * (info["cls_floats"] + info["rec_floats"])
+    path_bytes = (15.0 * info["det_px"] + 5.0 * info["det_px"] + 6.0 * crop_px + 2 * 3.0 * crop_px + 4.0 * (info["cls_floats"] + info["rec_floats"])
                   + 4.0 * info["rec_rows"] * C_CLASSES)
     summary = {"db_postprocess_unit": {"ms_per_step": db_ms, "algorithmic_bytes": 9.0 * info["det_px"],
-                                       "gbs": 9.0 * info["det_px"] / (db_ms * 1e-3) / 1e9 if db_ms else None},
+                                       "gbs": 9.0 * info["det_px"] / (db_ms * 1e-3) / 1e9 if db_ms else None,
+                                       "note": "SURVEY 8(d) unit: 9*H*W (prob read + bitmap + label plane); the run-table CCL moves 5*H*W — the label plane is only materialised on request"},
                "whole_path": {"algorithmic_bytes_per_step": path_bytes, "gbs_at_value": path_bytes * (value / world / P) / 1e9,
                               "kernel_ms_per_step": sum(v["ms_per_step"] for v in kernels.values()), "ms_per_step": ms_dev / args.steps},
                "serial_pass": {"ms_per_step": ms_serial / args.steps, "pages_per_s": P * world * args.steps / (ms_serial / 1000.0),

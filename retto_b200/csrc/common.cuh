@@ -93,7 +93,8 @@ struct PageCounters {      // per page, zeroed before each det_postprocess
     int status;
     int row_total;           // rows allocated in the row-extreme table
     int n_holes;             // hole borders (background components not connected to the frame)
-    int pad[2];
+    int n_runs;              // run-table CCL: horizontal foreground runs emitted by bitmap_runs2_kernel
+    int fallback;            // run-table CCL: more runs than the on-chip table holds -> the batch is redone on the pixel path
 };
 
 struct CompRec {           // per connected component (dense id)
@@ -190,15 +191,18 @@ struct retto_b200_ctx {
     // det post state (kept for the fetch_* taps and for crop jobs)
     std::vector<DetPostPage> dp_pages;
     std::vector<int> dp_ncomp;
+    std::vector<int> dp_nruns;           // per page: runs in the run table of the last det_postprocess
     std::vector<char> dp_labels_final;   // per page: run-interior labels resolved (lazily, by fetch_labels)
     std::vector<int32_t> dbg_extra;
     bool dp_trace_enabled = false, dp_trace_valid = false;
     DevBuf d_trace;
     std::vector<int> dp_holes;   // per page: #hole borders of the last det_postprocess (components - Euler number)
     DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out, d_holes, d_hole_pages, d_key_at;
+    DevBuf d_runs;           // run-table CCL: per page RUN_CAP raw records + RUN_CAP sorted records (key, x1|flags) + RUN_CAP labels
+    bool dp_run_path = false;   // the last det_postprocess used the run-table CCL (labels are materialised lazily from the runs)
     HostBuf h_dp;
     cudaEvent_t ev_dp = nullptr;   // behind the early counter read-back of det_postprocess
-    struct DpRun { int n = 0, cap = 0, total_tiles = 0, nspec = 0; size_t hdr_bytes = 0; } dp;   // begin -> mid -> end state
+    struct DpRun { int n = 0, cap = 0, total_tiles = 0, nspec = 0; size_t hdr_bytes = 0; bool vec = true; } dp;   // begin -> mid -> end state
 
     // crops
     struct CropHost { int w, h, rot, status; unsigned long long offset; };   // host view of the current crop set

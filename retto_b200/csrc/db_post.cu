@@ -633,10 +633,12 @@ __device__ __forceinline__ bool hole_px(const HoleArgs& h, int& page, DetPostPag
     p = u - h.flag_prefix[k];
     return true;
 }
-__global__ void bg_init_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, int* __restrict__ bgl) {
+__global__ void bg_init_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, int* __restrict__ bgl, int* __restrict__ labels_init) {
     int page, p; DetPostPage pg;
     if (!hole_px(h, page, pg, p)) return;
     bgl[pg.px_base + p] = bitmap[pg.px_base + p] ? -1 : p;
+    // run-table path: the label plane has not been written; the hole kernels use its background entries as scratch
+    if (labels_init) labels_init[pg.px_base + p] = -1;
 }
 __global__ void bg_merge_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, int* __restrict__ bgl) {
     int page, p; DetPostPage pg;
@@ -815,9 +817,395 @@ __global__ void __launch_bounds__(128) pack_boxes_kernel(int n_pages, const Page
     }
 }
 
+
+// =====================================================================================================================
+// Run-table CCL (default path).  Text probability maps are sparse and blobby: a 1280x1280 page has ~10^3 horizontal
+// foreground runs against 1.6 * 10^6 pixels, so connected components are resolved on the RUN table, on chip, instead
+// of with three more passes of dependent global accesses over the pixel label plane:
+//   A' bitmap_runs2   threshold + 2x2 dilate -> bitmap, appends one record per run (per 128-px strip) to the page's run
+//                     table, and counts the Euler number of the bitmap on the fly           [HBM: 4 B/px in, 1 B/px out]
+//   B' ccl_runs       one block per page, everything in shared memory: sort the runs into raster order, union runs
+//                     that touch (8-connectivity: previous row, x ranges within 1; same row for strip-split runs),
+//                     components in raster order of their first pixel (== find_contours discovery order), per-component
+//                     last row / discovery key, row-table allocation and per-row extremes
+// The pixel label plane is not needed downstream; retto_b200_det_post_fetch_labels materialises it from the runs.
+// A page with more runs than the on-chip table holds (noise) sends the batch to the pixel path (kernels A-G above).
+#define RUN_CAP 6144                       // runs per page held in shared memory by ccl_runs_kernel (88 KB: two blocks per SM)
+#define RUN_ROW_MAX 256                    // runs in one image row handled on chip (insertion sort + linear neighbour scan)
+#define RUN_MAX_H 4096                     // rows of the per-row index (== the cap on max_det_side)
+#define RUN_X_MASK ((1 << 29) - 1)
+struct RunRec { int key; int x1; };        // key = y * W + x0 (raster index of the first pixel), x1 = last pixel
+
+// Same row walk as bitmap_runs_kernel (threshold, 2x2 dilate, bitmap store), but instead of a label plane it appends one
+// record per horizontal run of the 128-px strip row, emitted by the lane that holds the run's last pixel (run start
+// from the same ballot "carry" as the pixel path).  Runs are cut at strip boundaries; ccl_runs_kernel re-joins them.
+template <bool VEC>
+__global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix,
+                                                            int n_pages, int total_tiles, float thr, int dilate,
+                                                            unsigned char* __restrict__ bitmap, RunRec* __restrict__ runs,
+                                                            PageCounters* __restrict__ counters) {
+    DetPostPage pg; int page, s, rb, tile;
+    if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
+    const int lane = threadIdx.x & 31;
+    const int W = pg.w, H = pg.h;
+    const int x0 = s * TILE_W, x = x0 + lane * 4;
+    const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
+    unsigned char* bm = bitmap + pg.px_base;
+    const float* __restrict__ prob = pg.prob;
+    RunRec* prun = runs + (size_t)page * 3 * RUN_CAP;
+
+    // raw (float4, left-edge scalar) of one row; the threshold / shuffles are applied when the row is consumed, so the
+    // loads of row y+1 are in flight while row y is processed
+    struct Raw { float4 v; float l; };
+    auto fetch = [&](int y) -> Raw {
+        Raw r; r.v = make_float4(0.f, 0.f, 0.f, 0.f); r.l = 0.f;
+        if (y < 0 || y >= y1) return r;
+        const float* row = prob + (size_t)y * W;
+        if (VEC) { if (x < W) r.v = __ldg(reinterpret_cast<const float4*>(row + x)); }
+        else {
+            if (x < W) r.v.x = __ldg(row + x);
+            if (x + 1 < W) r.v.y = __ldg(row + x + 1);
+            if (x + 2 < W) r.v.z = __ldg(row + x + 2);
+            if (x + 3 < W) r.v.w = __ldg(row + x + 3);
+        }
+        if (lane == 0 && x0 > 0) r.l = __ldg(row + x0 - 1);
+        return r;
+    };
+    auto bits5 = [&](const Raw& r, bool valid) -> unsigned {   // bit0 = t(x-1), bits1..4 = t(x..x+3)
+        unsigned t = 0;
+        if (valid) t = (r.v.x > thr ? 1u : 0u) | (r.v.y > thr ? 2u : 0u) | (r.v.z > thr ? 4u : 0u) | (r.v.w > thr ? 8u : 0u);
+        if (VEC) { if (x >= W) t = 0; }
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (x + j >= W) t &= ~(1u << j);
+        }
+        unsigned left = __shfl_up_sync(RT_FULL, (t >> 3) & 1u, 1);
+        if (lane == 0) left = (valid && x0 > 0 && r.l > thr) ? 1u : 0u;
+        return (t << 1) | left;
+    };
+    unsigned prev = 0;
+    if (dilate && y0 > 0) { const Raw r = fetch(y0 - 1); prev = bits5(r, true); }
+    Raw nxt = fetch(y0);
+    for (int y = y0; y < y1; ++y) {
+        const Raw rawc = nxt;
+        nxt = fetch(y + 1);
+        const unsigned cur = bits5(rawc, true);
+        unsigned nib;
+        if (dilate) {
+            const unsigned m = cur | prev;          // vertical OR
+            nib = ((m >> 1) | m) & 0xfu;            // bit j = m[j+1] | m[j]  (pixel j sits at bit j+1)
+        } else nib = (cur >> 1) & 0xfu;
+        prev = cur;
+        if (VEC) { if (x >= W) nib = 0; }
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j >= W) nib &= ~(1u << j);
+        }
+        if (VEC) {
+            if (x < W) *reinterpret_cast<unsigned*>(bm + (size_t)y * W + x) =
+                ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < W) bm[(size_t)y * W + x + j] = (nib & (1u << j)) ? 255 : 0;
+        }
+        if (!__ballot_sync(RT_FULL, nib != 0)) continue;
+        // ---- runs of this strip row
+        const unsigned notfull = __ballot_sync(RT_FULL, nib != 0xfu);
+        const unsigned below = notfull & ((1u << lane) - 1u);
+        const int l = below ? 31 - __clz(below) : 0;
+        const unsigned nibl = __shfl_sync(RT_FULL, nib, l);
+        unsigned nb = __shfl_down_sync(RT_FULL, nib & 1u, 1);            // pixel x+4; the strip ends after lane 31
+        if (lane == 31) nb = 0;
+        int start = below ? x0 + 4 * l + (31 - __clz((~nibl) & 0xfu)) + 1 : x0;
+        const unsigned ext = nib | (nb << 4);
+        int ends[2], starts[2], cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (nib & (1u << j)) {
+                if (!((ext >> (j + 1)) & 1u)) { starts[cnt] = start; ends[cnt] = x + j; ++cnt; }   // at most two runs end in 4 pixels
+            } else start = x + j + 1;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(RT_FULL, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(RT_FULL, incl, 31);
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&counters[page].n_runs, total);
+        base = __shfl_sync(RT_FULL, base, 31) + incl - cnt;
+        for (int k = 0; k < cnt; ++k)
+            if (base + k < RUN_CAP) prun[base + k] = RunRec{y * W + starts[k], ends[k]};
+    }
+}
+
+// B': one block per page.  Shared memory: sorted runs (key, x1) | parent | per-row index.
+__device__ __forceinline__ int sm_find(const int* par, int a) {
+    int p = par[a];
+    while (p != a) { a = p; p = par[a]; }
+    return a;
+}
+__device__ __forceinline__ void sm_union(int* par, int a, int b) {
+    bool done;
+    do {
+        a = sm_find(par, a);
+        b = sm_find(par, b);
+        if (a < b) { const int old = atomicMin(&par[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&par[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+__device__ __forceinline__ int block_excl_scan(int v, int* s_scan, int* total) {   // exclusive prefix over the block's threads
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(RT_FULL, x, o); if (lane >= o) x += t; }
+    if (lane == 31) s_scan[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int t = lane < nw ? s_scan[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(RT_FULL, t, o); if (lane >= o) t += u; }
+        s_scan[lane] = t;
+    }
+    __syncthreads();
+    const int incl = x + (w ? s_scan[w - 1] : 0);
+    *total = s_scan[nw - 1];
+    __syncthreads();
+    return incl - v;
+}
+__global__ void __launch_bounds__(1024, 2) ccl_runs_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
+                                                            RunRec* __restrict__ runs, CompRec* __restrict__ comps, int2* __restrict__ rowtab,
+                                                            int max_comps) {
+    extern __shared__ int s_mem[];
+    __shared__ int s_scan[1024];
+    __shared__ int s_flag;
+    const int page = blockIdx.x;
+    const DetPostPage pg = pages[page];
+    const int W = pg.w, H = pg.h;
+    const int n = counters[page].n_runs;
+    if (n > RUN_CAP || H > RUN_MAX_H) {
+        if (threadIdx.x == 0) counters[page].fallback = 1;
+        return;
+    }
+    int2* srt = reinterpret_cast<int2*>(s_mem);          // RUN_CAP x (key, x1), raster order
+    int* par = s_mem + 2 * RUN_CAP;                      // RUN_CAP
+    int* rowp = par + RUN_CAP;                           // RUN_MAX_H + 1: first run of every row (rowp[H] = n)
+    RunRec* praw = runs + (size_t)page * 3 * RUN_CAP;
+    if (threadIdx.x == 0) s_flag = 0;
+    for (int y = threadIdx.x; y <= H; y += blockDim.x) rowp[y] = 0;
+    __syncthreads();
+    // counting sort by row: histogram -> inclusive scan (row ends) -> scatter from the back (leaves the row starts)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&rowp[praw[i].key / W], 1);
+    __syncthreads();
+    {
+        const int per = (H + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int r0 = min(H, (int)threadIdx.x * per), r1 = min(H, r0 + per);
+        int sum = 0;
+        for (int y = r0; y < r1; ++y) { sum += rowp[y]; if (rowp[y] > RUN_ROW_MAX) s_flag = 1; }
+        int tot;
+        int run = block_excl_scan(sum, s_scan, &tot);
+        for (int y = r0; y < r1; ++y) { run += rowp[y]; rowp[y] = run; }   // inclusive: end of row y
+        if (threadIdx.x == 0) rowp[H] = n;
+    }
+    __syncthreads();
+    if (s_flag) {   // a row with hundreds of runs (noise): the pixel path handles it
+        if (threadIdx.x == 0) counters[page].fallback = 1;
+        return;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const RunRec r = praw[i];
+        const int pos = atomicSub(&rowp[r.key / W], 1) - 1;
+        srt[pos] = make_int2(r.key, r.x1);
+    }
+    __syncthreads();
+    // rows are short: one thread sorts one row by x0 (insertion sort)
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        const int a = rowp[y], b = rowp[y + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const int2 v = srt[i];
+            int j = i;
+            while (j > a && srt[j - 1].x > v.x) { srt[j] = srt[j - 1]; --j; }
+            srt[j] = v;
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) par[i] = i;
+    __syncthreads();
+    // unions over touching pieces (8-connectivity: previous row, x ranges within one pixel; same row: the pieces of a run
+    // cut at strip boundaries).  The Euler number of the bitmap (#components - #holes) is #runs - #touching pairs of
+    // WHOLE runs in consecutive rows: every independent cycle of the run adjacency graph encloses exactly one background
+    // region (counted on whole runs — the pieces of a cut run would add cycles that enclose nothing).
+    auto is_head = [&](int i, int row_first) { return !(i > row_first && srt[i - 1].y + 1 == srt[i].x - (srt[i].x / W) * W); };
+    auto chain_end = [&](int i, int row_end) {   // last pixel of the whole run that piece i starts
+        int e = srt[i].y;
+        for (int k = i + 1; k < row_end && srt[k].x - (srt[k].x / W) * W == e + 1; ++k) e = srt[k].y;
+        return e;
+    };
+    int pairs = 0, heads = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int2 r = srt[i];
+        const int y = r.x / W, xa = r.x - y * W, xb = r.y;
+        const bool head = !(i > rowp[y] && srt[i - 1].y + 1 == xa);
+        if (!head) sm_union(par, i, i - 1);
+        if (y > 0) {
+            const int lim = (y - 1) * W + min(xb + 1, W - 1);
+            for (int j = rowp[y - 1]; j < rowp[y]; ++j) {
+                const int2 q = srt[j];
+                if (q.x > lim) break;
+                if (q.y >= xa - 1) sm_union(par, i, j);
+            }
+        }
+        if (head) {
+            ++heads;
+            if (y > 0) {
+                const int b = chain_end(i, rowp[y + 1]);
+                for (int j = rowp[y - 1]; j < rowp[y]; ++j) {
+                    const int c = srt[j].x - (y - 1) * W;
+                    if (c > b + 1) break;
+                    if (!is_head(j, rowp[y - 1])) continue;
+                    if (chain_end(j, rowp[y]) >= xa - 1) ++pairs;
+                }
+            }
+        }
+    }
+    int tot_pairs, tot_heads;
+    block_excl_scan(pairs, s_scan, &tot_pairs);
+    block_excl_scan(heads, s_scan, &tot_heads);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) par[i] = sm_find(par, i);   // concurrent reads only ever move towards the root
+    __syncthreads();
+    // dense component ids in raster order of the root run
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int b0 = min(n, (int)threadIdx.x * per), e0 = min(n, b0 + per);
+    int cntr = 0;
+    for (int i = b0; i < e0; ++i) cntr += (par[i] == i);
+    int n_roots;
+    int id = block_excl_scan(cntr, s_scan, &n_roots);
+    if (n_roots > max_comps) {
+        if (threadIdx.x == 0) { counters[page].status = RETTO_B200_ERR_CAPACITY; counters[page].n_roots = 0; counters[page].euler = tot_heads - tot_pairs; }
+        return;
+    }
+    CompRec* c = comps + (size_t)page * max_comps;
+    for (int i = b0; i < e0; ++i)
+        if (par[i] == i) {
+            const int key = srt[i].x;
+            CompRec cr;
+            cr.root = key; cr.ymax = key / W; cr.xmin = 0; cr.xmax = 0; cr.row_off = 0; cr.key = 0x7fffffff; cr.ymin = key / W; cr.pad = 0;
+            c[id] = cr;
+            par[i] = -1 - id;      // roots now carry their component id
+            ++id;
+        }
+    __syncthreads();
+    auto comp_of = [&](int i) { const int p = par[i]; return p < 0 ? -1 - p : -1 - par[p]; };
+    // per-component last row and discovery key (imageproc's scan, RECALLED: a border starts at x > 0 with a zero to the
+    // left, or at x + 1 < width with a zero to the right — see ccl_flatten_kernel); a run cut at a strip boundary has no
+    // true start / end there
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int2 r = srt[i];
+        const int y = r.x / W, xa = r.x - y * W, xb = r.y;
+        const bool tstart = !(i > rowp[y] && srt[i - 1].y + 1 == xa);
+        const bool tend = !(i + 1 < rowp[y + 1] && srt[i + 1].x == r.x + (xb - xa) + 1);
+        CompRec* cr = c + comp_of(i);
+        atomicMax(&cr->ymax, y);
+        if (tstart && xa > 0) atomicMin(&cr->key, r.x);
+        if (tend && xb + 1 < W) atomicMin(&cr->key, y * W + xb);
+    }
+    __syncthreads();
+    // row-table allocation: exclusive prefix over the components of (ymax - ymin + 1)
+    const int perc = (n_roots + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int cb0 = min(n_roots, (int)threadIdx.x * perc), ce0 = min(n_roots, cb0 + perc);
+    int sum = 0;
+    for (int i = cb0; i < ce0; ++i) sum += c[i].ymax - c[i].ymin + 1;
+    int row_total;
+    int off = block_excl_scan(sum, s_scan, &row_total);
+    for (int i = cb0; i < ce0; ++i) { c[i].row_off = off; off += c[i].ymax - c[i].ymin + 1; }
+    if (threadIdx.x == 0) {
+        counters[page].n_roots = n_roots;
+        counters[page].euler = tot_heads - tot_pairs;
+        counters[page].row_total = row_total;
+        if (row_total > ROWCAP) counters[page].status = RETTO_B200_ERR_CAPACITY;
+    }
+    const int total_rows = min(row_total, ROWCAP);
+    int2* rt = rowtab + (size_t)page * ROWCAP;
+    for (int i = threadIdx.x; i < total_rows; i += blockDim.x) rt[i] = make_int2(0x7fffffff, -1);
+    __syncthreads();
+    if (row_total > ROWCAP) return;
+    // per-row extremes (true run starts / ends only, like run_end_kernel<1>) + the sorted table and the labels for the tap
+    RunRec* psorted = praw + RUN_CAP;
+    int* plabel = reinterpret_cast<int*>(praw + 2 * RUN_CAP);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int2 r = srt[i];
+        const int y = r.x / W, xa = r.x - y * W, xb = r.y;
+        const bool tstart = !(i > rowp[y] && srt[i - 1].y + 1 == xa);
+        const bool tend = !(i + 1 < rowp[y + 1] && srt[i + 1].x == r.x + (xb - xa) + 1);
+        const CompRec cr = c[comp_of(i)];
+        const int ridx = cr.row_off + (y - cr.ymin);
+        if (tstart) atomicMin(&rt[ridx].x, xa);
+        if (tend) atomicMax(&rt[ridx].y, xb);
+        psorted[i] = RunRec{r.x, xb};
+        plabel[i] = cr.root;
+    }
+}
+
+// label plane from the run table (parity tap): background -1, every run pixel = raster index of its component's first pixel
+__global__ void labels_from_runs_kernel(const RunRec* __restrict__ sorted, const int* __restrict__ label, int n, int W, int* __restrict__ labels) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int key = sorted[i].key, xb = sorted[i].x1, lab = label[i];
+    const int y = key / W, xa = key - y * W;
+    for (int x = xa + lane; x <= xb; x += 32) labels[(size_t)y * W + x] = lab;
+}
+
 __global__ void zero_counters_kernel(PageCounters* c, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { PageCounters z; memset(&z, 0, sizeof(z)); c[i] = z; }
+}
+
+// pixel-plane CCL chain (kernels A-G): the fallback of the run-table path, and the path under RETTO_B200_PIXEL_CCL=1.
+// Ends with the early counter read-back (event) enqueued before the row-extreme kernel.
+static retto_b200_status dp_pixel_ccl(retto_b200_ctx* ctx) {
+    retto_b200_ctx::DpRun& R = ctx->dp;
+    const int n = R.n, total_tiles = R.total_tiles, max_comps = ctx->cfg.max_components_per_page;
+    cudaStream_t st = ctx->stream;
+    const DetPostPage* d_pages = ctx->d_dp_pages.as<DetPostPage>();
+    const int* d_tile_prefix = reinterpret_cast<const int*>(ctx->d_dp_pages.as<char>() + sizeof(DetPostPage) * n);
+    PageCounters* d_cnt = ctx->d_dp_counters.as<PageCounters>();
+    unsigned char* d_bm = ctx->d_bitmap.as<unsigned char>();
+    int* d_lab = ctx->d_labels.as<int>();
+    int* d_cid = ctx->d_cid_at.as<int>();
+    int* d_key = ctx->d_key_at.as<int>();
+    unsigned char* d_tf = ctx->d_tileflags.as<unsigned char>();
+    int* d_roots = ctx->d_roots.as<int>();
+    CompRec* d_comps = ctx->d_comps.as<CompRec>();
+    int2* d_rowtab = ctx->d_rowtab.as<int2>();
+    ctx->dp_run_path = false;
+    RT_LAUNCH_BEGIN(ctx, "zero_counters_kernel");
+    zero_counters_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, n);
+    RT_LAUNCH_CHECK(ctx);
+    const int tgrid = (total_tiles + 3) / 4;
+    RT_LAUNCH_BEGIN(ctx, "bitmap_runs_kernel");
+    if (R.vec)
+        bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
+    else
+        bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "ccl_merge_kernel");
+    ccl_merge_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt);
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "ccl_flatten_kernel");
+    ccl_flatten_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt, d_roots, max_comps, d_cid, d_key);
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "comp_sort_kernel");
+    comp_sort_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_roots, d_comps, d_cid, d_key, d_rowtab, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    // The geometry grid and the hole-border decision need the per-page component counts (n_roots, euler, status), which
+    // are final after comp_sort: their read-back is enqueued BEFORE the row-extreme kernel and the host waits on an
+    // event behind the copy only, so the round trip hides under run_end_kernel instead of idling the GPU.
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_dp.as<PageCounters>(), d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
+    RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_dp, st));
+    RT_LAUNCH_BEGIN(ctx, "run_end_kernel<1>");
+    run_end_kernel<1><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
+    RT_LAUNCH_CHECK(ctx);
+    return RETTO_B200_OK;
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------------
@@ -891,42 +1279,37 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
     int2* d_hull = d_rowtab + (size_t)n * ROWCAP;
     BoxCand* d_cand = ctx->d_cand.as<BoxCand>();
 
-    RT_LAUNCH_BEGIN(ctx, "zero_counters_kernel");
-    zero_counters_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, n);
-    RT_LAUNCH_CHECK(ctx);
-    const int tgrid = (total_tiles + 3) / 4;
-    RT_LAUNCH_BEGIN(ctx, "bitmap_runs_kernel");
-    if (vec)
-        bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
-    else
-        bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
-    RT_LAUNCH_CHECK(ctx);
-    RT_LAUNCH_BEGIN(ctx, "ccl_merge_kernel");
-    ccl_merge_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt);
-    RT_LAUNCH_CHECK(ctx);
-    RT_LAUNCH_BEGIN(ctx, "ccl_flatten_kernel");
-    ccl_flatten_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt, d_roots, max_comps, d_cid, d_key);
-    RT_LAUNCH_CHECK(ctx);
-    RT_LAUNCH_BEGIN(ctx, "comp_sort_kernel");
-    comp_sort_kernel<<<n, 1024, 0, st>>>(d_pages, d_cnt, d_roots, d_comps, d_cid, d_key, d_rowtab, max_comps);
-    RT_LAUNCH_CHECK(ctx);
-    // The geometry grid and the hole-border decision need the per-page component counts (n_roots, euler, status), which
-    // are final after comp_sort: their read-back is enqueued BEFORE the row-extreme kernel and the host waits on an
-    // event behind the copy only, so the round trip hides under run_end_kernel instead of idling the GPU.
+    (void)d_lab; (void)d_cid; (void)d_key; (void)d_tf; (void)d_roots; (void)d_rowtab; (void)d_hull; (void)d_cand; (void)d_offsets; (void)d_bm; (void)d_comps;
     const int cap = std::max(max_boxes_total, 0);
     const size_t hdr_bytes = (sizeof(PageCounters) * n + sizeof(int) * (n + 1) + 63) & ~size_t(63);
     RT_CUDA_OK(ctx, ctx->h_dp.ensure(2 * hdr_bytes + sizeof(retto_b200_box) * (size_t)std::max(cap, 1)));
-    PageCounters* h_cnt0 = ctx->h_dp.as<PageCounters>();                                                   // early snapshot
-    PageCounters* h_cnt = reinterpret_cast<PageCounters*>(ctx->h_dp.as<char>() + hdr_bytes);               // final
-    retto_b200_box* h_stage_boxes = reinterpret_cast<retto_b200_box*>(ctx->h_dp.as<char>() + 2 * hdr_bytes);
     if (!ctx->ev_dp) RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_dp, cudaEventDisableTiming));
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt0, d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
-    RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_dp, st));
-    RT_LAUNCH_BEGIN(ctx, "run_end_kernel<1>");
-    run_end_kernel<1><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cid, d_comps, d_rowtab, d_cnt, max_comps);
-    RT_LAUNCH_CHECK(ctx);
-    R.cap = cap; R.total_tiles = total_tiles; R.hdr_bytes = hdr_bytes;
-    return RETTO_B200_OK;
+    R.cap = cap; R.total_tiles = total_tiles; R.hdr_bytes = hdr_bytes; R.vec = vec;
+    // default: run-table CCL; RETTO_B200_PIXEL_CCL=1 (tests) or a page with too many runs: the pixel-plane passes
+    ctx->dp_run_path = getenv("RETTO_B200_PIXEL_CCL") == nullptr;
+    if (ctx->dp_run_path) {
+        static bool attr_set = false;
+        const int smem = RUN_CAP * 12 + (RUN_MAX_H + 1) * 4;   // sorted runs (8 B) + parent per run, per-row index
+        if (!attr_set) { RT_CUDA_OK(ctx, cudaFuncSetAttribute(ccl_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+        RT_CUDA_OK(ctx, ctx->d_runs.ensure(sizeof(RunRec) * 3 * RUN_CAP * (size_t)n, st));
+        RT_LAUNCH_BEGIN(ctx, "zero_counters_kernel");
+        zero_counters_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, n);
+        RT_LAUNCH_CHECK(ctx);
+        const int tgrid = (total_tiles + 3) / 4;
+        RT_LAUNCH_BEGIN(ctx, "bitmap_runs2_kernel");
+        if (vec)
+            bitmap_runs2_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt);
+        else
+            bitmap_runs2_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt);
+        RT_LAUNCH_CHECK(ctx);
+        RT_LAUNCH_BEGIN(ctx, "ccl_runs_kernel");
+        ccl_runs_kernel<<<n, 1024, smem, st>>>(d_pages, d_cnt, ctx->d_runs.as<RunRec>(), d_comps, d_rowtab, max_comps);
+        RT_LAUNCH_CHECK(ctx);
+        RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_dp.as<PageCounters>(), d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
+        RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_dp, st));
+        return RETTO_B200_OK;
+    }
+    return dp_pixel_ccl(ctx);
 }
 
 retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
@@ -951,6 +1334,14 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
     retto_b200_box* h_stage_boxes = reinterpret_cast<retto_b200_box*>(ctx->h_dp.as<char>() + 2 * R.hdr_bytes);
     (void)d_bm; (void)d_lab; (void)d_cid; (void)d_comps; (void)d_rowtab; (void)d_hull; (void)d_cand; (void)h_cnt0; (void)h_cnt; (void)h_stage_boxes; (void)d_offsets; (void)max_comps; (void)cap; (void)st; (void)d_pages; (void)d_cnt;
     RT_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_dp));
+    if (ctx->dp_run_path) {
+        bool fb = false;
+        for (int i = 0; i < n; ++i) fb |= h_cnt0[i].fallback != 0;
+        if (fb) {   // a page has more runs than ccl_runs_kernel holds on chip: redo the batch on the pixel planes
+            RT_TRY(dp_pixel_ccl(ctx));
+            RT_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_dp));
+        }
+    }
     int max_n = 0;
     long long box_bound = 0;   // every box comes from one outer or one hole border
     for (int i = 0; i < n; ++i) {
@@ -989,7 +1380,7 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
             int* d_holes = ctx->d_holes.as<int>();
             const int g = (total + 255) / 256;
             RT_LAUNCH_BEGIN(ctx, "bg_init_kernel");
-            bg_init_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid);
+            bg_init_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, ctx->dp_run_path ? d_lab : nullptr);
             RT_LAUNCH_CHECK(ctx);
             RT_LAUNCH_BEGIN(ctx, "bg_merge_kernel");
             bg_merge_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid);
@@ -1093,7 +1484,8 @@ retto_b200_status rt_det_post_end(retto_b200_ctx* ctx, int32_t* h_page_status, i
     h_box_offsets[n] = h_off[n];
     ctx->dp_holes.assign(n, 0);
     ctx->dp_ncomp.assign(n, 0);
-    for (int i = 0; i < n; ++i) { ctx->dp_holes[i] = h_cnt[i].n_holes; ctx->dp_ncomp[i] = h_cnt[i].n_roots + h_cnt[i].n_holes; }
+    ctx->dp_nruns.assign(n, 0);
+    for (int i = 0; i < n; ++i) { ctx->dp_holes[i] = h_cnt[i].n_holes; ctx->dp_ncomp[i] = h_cnt[i].n_roots + h_cnt[i].n_holes; ctx->dp_nruns[i] = h_cnt[i].n_runs; }
     const int total = h_off[n];
     if (total > cap) {
         ctx->set_error("det_postprocess: " + std::to_string(total) + " boxes exceed max_boxes_total " + std::to_string(cap));
@@ -1129,6 +1521,20 @@ extern "C" retto_b200_status retto_b200_det_post_fetch_bitmap(retto_b200_ctx* ct
 extern "C" retto_b200_status retto_b200_det_post_fetch_labels(retto_b200_ctx* ctx, int32_t page, int32_t* h_labels) {
     if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !h_labels) return RETTO_B200_ERR_INVALID_ARG;
     const DetPostPage& pg = ctx->dp_pages[page];
+    if (!ctx->dp_labels_final[page] && ctx->dp_run_path) {
+        // run-table path: the plane is materialised from the page's sorted run table
+        int* plane = ctx->d_labels.as<int>() + pg.px_base;
+        RT_CUDA_OK(ctx, cudaMemsetAsync(plane, 0xff, sizeof(int) * (size_t)pg.h * pg.w, ctx->stream));
+        const int nr = page < (int)ctx->dp_nruns.size() ? ctx->dp_nruns[page] : 0;
+        if (nr > 0) {
+            const RunRec* sorted = ctx->d_runs.as<RunRec>() + (size_t)page * 3 * RUN_CAP + RUN_CAP;
+            const int* lab = reinterpret_cast<const int*>(ctx->d_runs.as<RunRec>() + (size_t)page * 3 * RUN_CAP + 2 * RUN_CAP);
+            RT_LAUNCH_BEGIN(ctx, "labels_from_runs_kernel");
+            labels_from_runs_kernel<<<(nr + 7) / 8, 256, 0, ctx->stream>>>(sorted, lab, nr, pg.w, plane);
+            RT_LAUNCH_CHECK(ctx);
+        }
+        ctx->dp_labels_final[page] = 1;
+    }
     if (!ctx->dp_labels_final[page]) {
         RT_LAUNCH_BEGIN(ctx, "labels_finalize_kernel");
         labels_finalize_kernel<<<(pg.h * pg.w + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_bitmap.as<unsigned char>(), ctx->d_labels.as<int>(), pg.px_base, pg.h * pg.w);

@@ -5,6 +5,17 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["run-table", "pixel-planes"])
+def ccl_path(request, monkeypatch):
+    """every test of this module runs on both CCL formulations of csrc/db_post.cu: the run-table path (default) and the
+    pixel-plane passes (its fallback)"""
+    if request.param == "pixel-planes":
+        monkeypatch.setenv("RETTO_B200_PIXEL_CCL", "1")
+    else:
+        monkeypatch.delenv("RETTO_B200_PIXEL_CCL", raising=False)
+    return request.param
+
+
 def _t(a):
     import torch
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
@@ -146,3 +157,39 @@ def test_hole_borders(ctx):
         assert ctx.fetch_trace(i)["n_holes"] == n_holes_ref
     ctx.enable_trace(False)
     assert ctx.fetch_trace(0)["n_holes"] == 3 and len(out.page(0)[0]) == 3   # 2 outer boxes + 1 surviving hole-border box
+
+
+def test_run_table_overflow_falls_back(ctx, ccl_path):
+    """a page with more horizontal runs than ccl_runs_kernel keeps on chip (8192) sends the batch to the pixel-plane
+    passes: same boxes, labels and bitmaps, also for the well-behaved page next to it"""
+    from tools.synth import gen_probmap
+    rng = np.random.default_rng(5)
+    noisy = np.full((1024, 1024), 0.05, np.float32)
+    ys, xs = rng.integers(2, 1020, 7000), rng.integers(2, 1020, 7000)
+    noisy[ys, xs] = 0.9                     # isolated pixels -> 2x2 blobs after dilation: two runs each
+    noisy[400:440, 100:700] = 0.85
+    probs = [_consistent_maps(4242, 1, 512, 512, k_range=(5, 12))[0], noisy]
+    out = _check_pages(ctx, probs, allow_inconsistent=True)
+    assert len(out.page(1)[0]) >= 1
+
+
+def test_no_spurious_hole_path(ctx, ccl_path):
+    """pages without holes must not take the hole-border path: the Euler number (#components - #holes) has to come out
+    right also for runs that cross the 128-px strips of the bitmap kernel (wide rectangles on a 1280-px page)"""
+    import torch
+    from oracle import oracle as O
+    p = np.full((640, 1280), 0.05, np.float32)
+    p[40:80, 30:1250] = 0.9          # crosses nine strips
+    p[120:170, 100:700] = 0.85
+    p[200:230, 127:129] = 0.9        # a thin bar on a strip boundary
+    for k in range(12):              # a staircase: diagonal contacts between consecutive rows
+        p[300 + 4 * k:304 + 4 * k, 200 + 37 * k:260 + 37 * k] = 0.9
+    assert sum(h for _, h in O.find_contours(O.threshold_dilate(p), quirk_x0=0)) == 0
+    g = _t(p)
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count
+    out = ctx.det_postprocess([g], [p.shape])
+    used = ctx.launch_count - l0
+    assert used <= (9 if ccl_path == "run-table" else 12), used    # no bg_* / hole_* kernels
+    ref = O.det_postprocess(p, *p.shape)
+    assert np.array_equal(out.page(0)[0], ref.boxes)
