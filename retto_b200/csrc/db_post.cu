@@ -940,9 +940,15 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
 }
 
 // B': one block per page.  Shared memory: sorted runs (key, x1) | parent | per-row index.
-__device__ __forceinline__ int sm_find(const int* par, int a) {
+// find with path halving: every visited node is re-pointed at its grandparent (atomicMin keeps the parent pointers
+// monotonically decreasing under concurrent unions, so a shortcut can never undo a link)
+__device__ __forceinline__ int sm_find(int* par, int a) {
     int p = par[a];
-    while (p != a) { a = p; p = par[a]; }
+    while (p != a) {
+        const int g = par[p];
+        if (g != p) atomicMin(&par[a], g);
+        a = p; p = g;
+    }
     return a;
 }
 __device__ __forceinline__ void sm_union(int* par, int a, int b) {
