@@ -257,7 +257,7 @@ def algorithmic_bytes(name, info, launch_idx=0):
         return 4.0 * info["rec_rows"] * C_CLASSES
     if name.startswith("det_pre_identity"):
         return 15.0 * HW                      # 3 B in + 12 B out per pixel
-    if name.startswith("bitmap_runs2"):
+    if name.startswith("bitmap_runs2") or name.startswith("bitmap_runs3"):
         return 5.0 * HW                       # prob read 4 + bitmap write 1 (run-table CCL: the label plane is not materialised)
     if name.startswith("bitmap_runs"):
         return 9.0 * HW                       # prob read 4 + bitmap write 1 + label write 4

@@ -202,7 +202,7 @@ struct retto_b200_ctx {
     bool dp_run_path = false;   // the last det_postprocess used the run-table CCL (labels are materialised lazily from the runs)
     HostBuf h_dp;
     cudaEvent_t ev_dp = nullptr;   // behind the early counter read-back of det_postprocess
-    struct DpRun { int n = 0, cap = 0, total_tiles = 0, nspec = 0; size_t hdr_bytes = 0; bool vec = true; } dp;   // begin -> mid -> end state
+    struct DpRun { int n = 0, cap = 0, total_tiles = 0, total_tiles2 = 0, nspec = 0, w_or = 0; size_t hdr_bytes = 0; bool vec = true, a8 = true; } dp;   // begin -> mid -> end state
 
     // crops
     struct CropHost { int w, h, rot, status; unsigned long long offset; };   // host view of the current crop set

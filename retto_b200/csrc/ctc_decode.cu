@@ -84,15 +84,18 @@ __global__ void __launch_bounds__(WARPS * 32) ctc_argmax_kernel(const CtcTensor*
     }
 }
 
-// one thread per line: CTC collapse (rec_processor.rs:57-95): keep t iff idx != 0 && (t == 0 || idx[t]
+// one warp per line: CTC collapse (rec_processor.rs:57-95): keep t iff idx != 0 && (t == 0 || idx[t]
 // != idx[t-1]) && idx not in ignored_tokens ([0]); score = sum(p) / count, sequential f32 (NaN when
 // count == 0).  Text = concatenation of dict[idx] written at a fixed per-line stride.
-__global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ prob, const int* __restrict__ line_t,
+// 32 time steps per trip: the keep mask is a ballot, token / text positions are prefix counts over it, and the score
+// is still the reference's sequential fold — the kept probabilities are added one by one in time order (a shuffle
+// broadcast per kept step, every lane carrying the same accumulator).
+__global__ void __launch_bounds__(256) ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ prob, const int* __restrict__ line_t,
                                     int n_lines, int max_t, const unsigned* __restrict__ dict_offs,
                                     const unsigned char* __restrict__ dict_bytes, int n_dict, int text_stride, int* __restrict__ tokens,
                                     int* __restrict__ counts, float* __restrict__ scores, unsigned char* __restrict__ text,
                                     int* __restrict__ text_len) {
-    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (line >= n_lines) return;
     const int T = line_t[line];
     const int* li = idx + (size_t)line * max_t;
@@ -100,24 +103,39 @@ __global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __
     int* tk = tokens + (size_t)line * max_t;
     unsigned char* tx = text + (size_t)line * text_stride;
     float acc = 0.0f;
-    int cnt = 0, tl = 0, prev = -1;
-    for (int t = 0; t < T; ++t) {
-        const int c = li[t];
-        const bool sel = (c != 0) && (t == 0 || c != prev);
-        prev = c;
+    int cnt = 0, tl = 0, carry = -1;
+    for (int base = 0; base < T; base += 32) {
+        const int t = base + lane;
+        const int c = t < T ? li[t] : 0;
+        const float p = t < T ? lp[t] : 0.0f;
+        int prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0) prev = carry;
+        carry = __shfl_sync(0xffffffffu, c, 31);
+        const bool sel = (t < T) && (c != 0) && (t == 0 || c != prev);
+        const unsigned m = __ballot_sync(0xffffffffu, sel);
+        const unsigned below = m & ((1u << lane) - 1u);
+        unsigned b = 0, e = 0;
         if (sel) {
-            tk[cnt++] = c;
-            acc = __fadd_rn(acc, lp[t]);
-            if (c < n_dict) {
-                const unsigned b = dict_offs[c], e = dict_offs[c + 1];
-                for (unsigned q = b; q < e; ++q) tx[tl++] = dict_bytes[q];
-            }
+            tk[cnt + __popc(below)] = c;
+            if (c < n_dict) { b = dict_offs[c]; e = dict_offs[c + 1]; }
         }
+        // byte offsets of the kept entries: inclusive scan of their lengths
+        const int len = (int)(e - b);
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        unsigned char* dst = tx + tl + incl - len;
+        for (int q = 0; q < len; ++q) dst[q] = dict_bytes[b + q];
+        tl += __shfl_sync(0xffffffffu, incl, 31);
+        cnt += __popc(m);
+        for (unsigned r = m; r; r &= r - 1) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, __ffs(r) - 1));   // time order
     }
-    for (int t = cnt; t < max_t; ++t) tk[t] = -1;
-    counts[line] = cnt;
-    scores[line] = __fdiv_rn(acc, (float)cnt);  // 0/0 -> NaN like the reference (rec_processor.rs:94)
-    text_len[line] = tl;
+    for (int t = cnt + lane; t < max_t; t += 32) tk[t] = -1;
+    if (lane == 0) {
+        counts[line] = cnt;
+        scores[line] = __fdiv_rn(acc, (float)cnt);  // 0/0 -> NaN like the reference (rec_processor.rs:94)
+        text_len[line] = tl;
+    }
 }
 
 // Packing of the decoded strings: the fixed-stride text buffer is mostly padding (stride = max_t * longest entry), so
@@ -253,7 +271,7 @@ retto_b200_status rt_ctc_begin(retto_b200_ctx* ctx, const retto_b200_logits_desc
     RT_TRY(rt_upload_to(ctx, d_linet, line_t.data(), sizeof(int) * nl));
     RT_TRY(ctc_run_argmax(ctx, tensors, prefix, num_classes, max_t, n_lines, ctx->d_ctc_idx.as<int>(), ctx->d_ctc_prob.as<float>(), d_nan));
     RT_LAUNCH_BEGIN(ctx, "ctc_collapse_kernel");
-    ctc_collapse_kernel<<<(n_lines + 127) / 128, 128, 0, ctx->stream>>>(
+    ctc_collapse_kernel<<<(n_lines + 7) / 8, 256, 0, ctx->stream>>>(
         ctx->d_ctc_idx.as<int>(), ctx->d_ctc_prob.as<float>(), d_linet, n_lines, max_t, ctx->d_dict_offs.as<unsigned>(),
         ctx->d_dict_bytes.as<unsigned char>(), (int)ctx->dict.size(), text_stride, ctx->d_ctc_tok.as<int>(), d_cnt,
         ctx->d_ctc_score.as<float>(), ctx->d_ctc_text.as<unsigned char>(), d_tlen);

@@ -939,6 +939,152 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
     }
 }
 
+// A'' (default): the same stage with one warp per 256-px strip and the row held as EIGHT warp-uniform 32-bit words —
+// lane l loads pixels x0 + 32 j + l (eight fully coalesced 128-B loads per row), and a ballot per load turns the
+// threshold test straight into the bit word of 32 consecutive pixels.  Dilation, run starts and run ends are then a
+// handful of funnel shifts on uniform words instead of per-lane nibble logic + shuffles (bitmap_runs2 issues ~115
+// instructions per 128-px row and is issue-bound at 73 % issue utilisation; this form needs about half per pixel).
+// Runs are buffered per warp in shared memory and appended to the page's run table with ONE atomic per tile.
+#define BR3_BUF 96
+template <bool ALIGNED, int NW>   // NW words of 32 pixels per strip row (4: 128-px strips on the tile grid of the pixel path, 8: 256-px strips)
+__global__ void __launch_bounds__(128, NW == 4 ? 12 : 8) bitmap_runs3_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix,
+                                                            int n_pages, int total_tiles, float thr, int dilate,
+                                                            unsigned char* __restrict__ bitmap, RunRec* __restrict__ runs,
+                                                            PageCounters* __restrict__ counters) {
+    constexpr int SW = 32 * NW;
+    __shared__ RunRec s_buf[4][BR3_BUF];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int tile = blockIdx.x * 4 + wib;
+    if (tile >= total_tiles) return;
+    const int page = rt_find_segment(tile_prefix, n_pages, tile);
+    const DetPostPage pg = pages[page];
+    const int W = pg.w, H = pg.h;
+    const int strips = (W + SW - 1) / SW;
+    const int lt = tile - tile_prefix[page];
+    const int rb = lt / strips, s = lt - rb * strips;
+    const int x0 = s * SW;
+    const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
+    unsigned char* bm = bitmap + pg.px_base;
+    const float* __restrict__ prob = pg.prob;
+    RunRec* prun = runs + (size_t)page * 3 * RUN_CAP;
+    RunRec* buf = s_buf[wib];
+    int nbuf = 0;
+    auto flush = [&]() {
+        __syncwarp();
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&counters[page].n_runs, nbuf);
+        base = __shfl_sync(RT_FULL, base, 0);
+        for (int i = lane; i < nbuf; i += 32)
+            if (base + i < RUN_CAP) prun[base + i] = buf[i];
+        __syncwarp();
+        nbuf = 0;
+    };
+    const int nv = W - x0;                  // pixels of the strip inside the page (only the last strip of a row is partial)
+    const bool partial = nv < SW;
+    struct Raw { float v[NW]; float l; };
+    auto fetch = [&](int y) -> Raw {
+        Raw r;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) r.v[j] = -CUDART_INF_F;   // outside the page: below every threshold
+        r.l = -CUDART_INF_F;
+        if (y < 0 || y >= y1) return r;
+        const float* row = prob + (size_t)y * W + x0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) r.v[j] = __ldg(row + 32 * j + lane);
+        if (lane == 0 && x0 > 0) r.l = __ldg(row - 1);
+        return r;
+    };
+    unsigned prev[NW], prevL = 0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) prev[j] = 0;
+    if (dilate && y0 > 0) {
+        const Raw r = fetch(y0 - 1);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) prev[j] = __ballot_sync(RT_FULL, r.v[j] > thr);
+        prevL = __ballot_sync(RT_FULL, r.l > thr) & 1u;
+    }
+    Raw nxt = fetch(y0);
+    for (int y = y0; y < y1; ++y) {
+        const Raw rc = nxt;
+        nxt = fetch(y + 1);
+        unsigned d[NW];
+        {
+            const unsigned curL = __ballot_sync(RT_FULL, rc.l > thr) & 1u;
+            unsigned carry = dilate ? (curL | prevL) << 31 : 0u;
+            prevL = curL;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const unsigned c = __ballot_sync(RT_FULL, rc.v[j] > thr);
+                if (dilate) {
+                    const unsigned m = c | prev[j];
+                    d[j] = m | __funnelshift_l(carry, m, 1);   // out(x) = m(x) | m(x - 1)
+                    carry = m;
+                } else d[j] = c;
+                prev[j] = c;
+            }
+            if (partial && dilate) {   // the dilation may reach one pixel past the page
+#pragma unroll
+                for (int j = 0; j < NW; ++j) d[j] &= nv >= 32 * (j + 1) ? 0xFFFFFFFFu : (nv <= 32 * j ? 0u : (1u << (nv - 32 * j)) - 1u);
+            }
+        }
+        // bitmap: lane l stores pixels x0 + NW l .. + NW - 1
+        {
+            unsigned wsel;
+            if (NW == 8) {
+                const unsigned a0 = (lane & 4) ? d[1] : d[0], a1 = (lane & 4) ? d[3] : d[2], a2 = (lane & 4) ? d[5 % NW] : d[4 % NW], a3 = (lane & 4) ? d[7 % NW] : d[6 % NW];
+                const unsigned b0 = (lane & 8) ? a1 : a0, b1 = (lane & 8) ? a3 : a2;
+                wsel = (lane & 16) ? b1 : b0;
+            } else {
+                const unsigned a0 = (lane & 8) ? d[1] : d[0], a1 = (lane & 8) ? d[3] : d[2];
+                wsel = (lane & 16) ? a1 : a0;
+            }
+            const unsigned bits = wsel >> ((NW * lane) & 31);
+            const unsigned lo = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            const int x = x0 + NW * lane;
+            if (NW == 8) {
+                const unsigned hi = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                if (ALIGNED) { if (x < W) *reinterpret_cast<uint2*>(bm + (size_t)y * W + x) = make_uint2(lo, hi); }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (x + k < W) bm[(size_t)y * W + x + k] = (unsigned char)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFFu);
+                }
+            } else {
+                if (ALIGNED) { if (x < W) *reinterpret_cast<unsigned*>(bm + (size_t)y * W + x) = lo; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (x + k < W) bm[(size_t)y * W + x + k] = (unsigned char)((lo >> (8 * k)) & 0xFFu);
+                }
+            }
+        }
+        unsigned any = 0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) any |= d[j];
+        if (!any) continue;
+        // runs of this strip row: starts / ends alternate, so the k-th start pairs with the k-th end (all values warp-uniform)
+        int open_start = -1;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            unsigned st = d[j] & ~__funnelshift_l(j ? d[j ? j - 1 : 0] : 0u, d[j], 1);
+            unsigned en = d[j] & ~__funnelshift_r(d[j], j < NW - 1 ? d[j < NW - 1 ? j + 1 : j] : 0u, 1);
+            const int xb = x0 + 32 * j;
+            while (en) {
+                int sx;
+                if (open_start >= 0) { sx = open_start; open_start = -1; }
+                else { sx = xb + __ffs(st) - 1; st &= st - 1; }
+                const int ex = xb + __ffs(en) - 1;
+                en &= en - 1;
+                if (nbuf == BR3_BUF) flush();
+                if (lane == 0) buf[nbuf] = RunRec{y * W + sx, ex};
+                ++nbuf;
+            }
+            if (st) open_start = xb + __ffs(st) - 1;
+        }
+    }
+    if (nbuf) flush();
+}
+
 // B': one block per page.  Shared memory: sorted runs (key, x1) | parent | per-row index.
 // find with path halving: every visited node is re-pointed at its grandparent (atomicMin keeps the parent pointers
 // monotonically decreasing under concurrent unions, so a shortcut can never undo a link)
@@ -1228,9 +1374,10 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
     ctx->dp_pages.clear();
     if (n == 0) return RETTO_B200_OK;
     const int max_comps = ctx->cfg.max_components_per_page;
-    std::vector<int> tile_prefix(n + 1, 0);
+    std::vector<int> tile_prefix(n + 1, 0), tile2_prefix(n + 1, 0);   // 128-px strips (pixel path, bitmap_runs2) / 256-px strips (bitmap_runs3)
     long long px = 0;
-    bool vec = true;
+    bool vec = true, a8 = true;
+    int w_or = 0;
     for (int i = 0; i < n; ++i) {
         const retto_b200_det_post_desc& d = h_descs[i];
         if (!d.d_prob || d.h <= 0 || d.w <= 0 || d.ori_h <= 0 || d.ori_w <= 0 || (long long)d.h * d.w > 0x7fffffffLL) {
@@ -1246,8 +1393,11 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
         pg.comp_base = i * max_comps;
         pg.box_base = 0;
         tile_prefix[i + 1] = tile_prefix[i] + pg.strips * pg.rowblocks;
+        tile2_prefix[i + 1] = tile2_prefix[i] + ((d.w + 255) / 256) * pg.rowblocks;
         px += ((long long)d.h * d.w + 15) & ~15LL;
         if ((d.w & 3) || ((uintptr_t)d.d_prob & 15)) vec = false;
+        if (d.w & 7) a8 = false;
+        w_or |= d.w;
         ctx->dp_pages.push_back(pg);
     }
     const int total_tiles = tile_prefix[n];
@@ -1255,13 +1405,15 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
     cudaStream_t st = ctx->stream;
     // device state
     {
-        std::vector<char> blob(sizeof(DetPostPage) * n + sizeof(int) * (n + 1));
+        std::vector<char> blob(sizeof(DetPostPage) * n + 2 * sizeof(int) * (n + 1));
         memcpy(blob.data(), ctx->dp_pages.data(), sizeof(DetPostPage) * n);
         memcpy(blob.data() + sizeof(DetPostPage) * n, tile_prefix.data(), sizeof(int) * (n + 1));
+        memcpy(blob.data() + sizeof(DetPostPage) * n + sizeof(int) * (n + 1), tile2_prefix.data(), sizeof(int) * (n + 1));
         RT_TRY(rt_upload(ctx, ctx->d_dp_pages, blob.data(), blob.size()));
     }
     const DetPostPage* d_pages = ctx->d_dp_pages.as<DetPostPage>();
     const int* d_tile_prefix = reinterpret_cast<const int*>(ctx->d_dp_pages.as<char>() + sizeof(DetPostPage) * n);
+    const int* d_tile2_prefix = d_tile_prefix + (n + 1);
     RT_CUDA_OK(ctx, ctx->d_dp_counters.ensure(sizeof(PageCounters) * n + sizeof(int) * (n + 1), st));
     RT_CUDA_OK(ctx, ctx->d_bitmap.ensure((size_t)px, st));
     RT_CUDA_OK(ctx, ctx->d_labels.ensure((size_t)px * 4, st));
@@ -1290,7 +1442,7 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
     const size_t hdr_bytes = (sizeof(PageCounters) * n + sizeof(int) * (n + 1) + 63) & ~size_t(63);
     RT_CUDA_OK(ctx, ctx->h_dp.ensure(2 * hdr_bytes + sizeof(retto_b200_box) * (size_t)std::max(cap, 1)));
     if (!ctx->ev_dp) RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_dp, cudaEventDisableTiming));
-    R.cap = cap; R.total_tiles = total_tiles; R.hdr_bytes = hdr_bytes; R.vec = vec;
+    R.cap = cap; R.total_tiles = total_tiles; R.hdr_bytes = hdr_bytes; R.vec = vec; R.total_tiles2 = tile2_prefix[n]; R.a8 = a8; R.w_or = w_or;
     // default: run-table CCL; RETTO_B200_PIXEL_CCL=1 (tests) or a page with too many runs: the pixel-plane passes
     ctx->dp_run_path = getenv("RETTO_B200_PIXEL_CCL") == nullptr;
     if (ctx->dp_run_path) {
@@ -1301,13 +1453,34 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
         RT_LAUNCH_BEGIN(ctx, "zero_counters_kernel");
         zero_counters_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, n);
         RT_LAUNCH_CHECK(ctx);
-        const int tgrid = (total_tiles + 3) / 4;
-        RT_LAUNCH_BEGIN(ctx, "bitmap_runs2_kernel");
-        if (vec)
-            bitmap_runs2_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt);
-        else
-            bitmap_runs2_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt);
-        RT_LAUNCH_CHECK(ctx);
+        static const bool use_br2 = getenv("RETTO_B200_BR2") != nullptr;   // A/B: the 4-px-per-lane kernel
+        if (use_br2) {
+            const int tgrid = (total_tiles + 3) / 4;
+            RT_LAUNCH_BEGIN(ctx, "bitmap_runs2_kernel");
+            if (vec)
+                bitmap_runs2_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt);
+            else
+                bitmap_runs2_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt);
+            RT_LAUNCH_CHECK(ctx);
+        } else {
+            // NW = 4: 128-px strips (the tile grid of the pixel path), NW = 8: 256-px strips; rows are stored with 4- / 8-byte words
+            // when every page width allows it
+            static const int nw = getenv("RETTO_B200_BR3_NW") ? atoi(getenv("RETTO_B200_BR3_NW")) : 8;   // measured: 0.43 ms (8) / 0.58 ms (4) / 0.49 ms (bitmap_runs2) per 256 pages 1280x1280
+            const bool a4 = vec || !(R.w_or & 3);
+#define BR3_ARGS(pre, tot) d_pages, pre, n, tot, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt
+            RT_LAUNCH_BEGIN(ctx, "bitmap_runs3_kernel");
+            if (nw == 8) {
+                const int tgrid = (R.total_tiles2 + 3) / 4;
+                if (R.a8) bitmap_runs3_kernel<true, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
+                else bitmap_runs3_kernel<false, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
+            } else {
+                const int tgrid = (total_tiles + 3) / 4;
+                if (a4) bitmap_runs3_kernel<true, 4><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile_prefix, total_tiles));
+                else bitmap_runs3_kernel<false, 4><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile_prefix, total_tiles));
+            }
+#undef BR3_ARGS
+            RT_LAUNCH_CHECK(ctx);
+        }
         RT_LAUNCH_BEGIN(ctx, "ccl_runs_kernel");
         ccl_runs_kernel<<<n, 1024, smem, st>>>(d_pages, d_cnt, ctx->d_runs.as<RunRec>(), d_comps, d_rowtab, max_comps);
         RT_LAUNCH_CHECK(ctx);
