@@ -59,6 +59,7 @@ extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_dp) cudaEventDestroy(c->ev_dp);
+    if (c->ev_dp2) cudaEventDestroy(c->ev_dp2);
     for (auto& sl : c->stage_slots) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     delete c;  // DevBuf / HostBuf members free their memory
     cudaStreamDestroy(s);

@@ -202,12 +202,17 @@ struct retto_b200_ctx {
     bool dp_run_path = false;   // the last det_postprocess used the run-table CCL (labels are materialised lazily from the runs)
     HostBuf h_dp;
     cudaEvent_t ev_dp = nullptr;   // behind the early counter read-back of det_postprocess
+    cudaEvent_t ev_dp2 = nullptr;  // behind the box read-back of det_postprocess
     struct DpRun { int n = 0, cap = 0, total_tiles = 0, total_tiles2 = 0, nspec = 0, w_or = 0; size_t hdr_bytes = 0; bool vec = true, a8 = true; } dp;   // begin -> mid -> end state
 
     // crops
     struct CropHost { int w, h, rot, status; unsigned long long offset; };   // host view of the current crop set
     std::vector<CropHost> crops;
-    DevBuf d_crop_descs, d_crop_pix, d_crop_flip;
+    DevBuf d_crop_descs, d_crop_pix, d_crop_flip, d_crop_pages;
+    int crop_dev_cap = 0;                 // device-built descriptor table (crop.cu): capacities at enqueue time, 0 = not enqueued
+    size_t crop_dev_cap_bytes = 0, crop_dev_desc_bytes = 0;
+    bool crop_dev_check = false;          // rt_crop_finish compares the device's crop sizes with the host's
+    int crops_seen_max = 0, crop_rows_seen_max = 0, crop_dev_row_cap = 0;
     HostBuf h_crops;
 
     // batches

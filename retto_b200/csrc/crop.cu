@@ -29,8 +29,9 @@ static __device__ bool solve8(double A[8][9]) {
     return true;
 }
 
-__global__ void crop_setup_kernel(CropDev* __restrict__ crops, int n) {
+__global__ void crop_setup_kernel(CropDev* __restrict__ crops, int n, const int* __restrict__ n_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(n, *n_dev);   // device-built table: n is the capacity, *n_dev the count (0 on overflow)
     if (i >= n) return;
     CropDev c = crops[i];
     const float* box = c.box;
@@ -140,8 +141,13 @@ __device__ __forceinline__ void crop_pixel(const CropDev& c, int x, int y, unsig
 // sample exact pixel centres: both cubic weights are 0 and cubic(p0,p1,p2,p3,0) == p1, so the row is a guarded byte
 // copy, fully coalesced on both sides (same white-border rule: any tap of the 4x4 window outside the page -> white).
 // Everything else (affine / projective / rotate270) takes the bicubic path, lanes striding the row.
+struct CropTotals { int n, rows, overflow, pad; unsigned long long bytes; };   // written by crop_scan_kernel
 __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restrict__ crops, const int* __restrict__ row_prefix, int n_crops,
-                                                         int total_rows, unsigned char* __restrict__ pix) {
+                                                         int total_rows, unsigned char* __restrict__ pix, const CropTotals* __restrict__ totals) {
+    if (totals) {   // device-built descriptor table: the sizes come from the device, the grid from the host's row hint
+        if (totals->overflow) return;
+        n_crops = totals->n; total_rows = totals->rows;
+    }
     const int lane = threadIdx.x & 31;
     const int ru = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (ru >= total_rows) return;
@@ -158,6 +164,8 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restric
         uchar4* dst = reinterpret_cast<uchar4*>(pix + c.offset) + (size_t)y * w;
         const unsigned char* src = c.page + ((size_t)iy * c.page_w + tx) * 3;
         // four pixels per lane per trip: the twelve byte loads are independent and issued before the first store
+        // (a variant that read the row as aligned words and re-cut them with funnel shifts / PRMT into 16-byte stores was
+        // measured slower on B200: 0.31 ms vs 0.28 ms per 256 pages)
         for (int x = lane; x < w; x += 128) {
             uchar4 o[4];
 #pragma unroll
@@ -178,6 +186,103 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restric
         if (c.rot) o = (size_t)(w - 1 - x) * h + y;  // rotate270: out(y, w-1-x) = in(x, y), out is h wide
         else o = (size_t)y * w + x;
         reinterpret_cast<uchar4*>(pix + c.offset)[o] = make_uchar4(rgb[0], rgb[1], rgb[2], 255);
+    }
+}
+
+// ---- descriptor table built on the device (session path) ---------------------------------------------------------
+// The host needs the boxes to plan the cls / rec batches, but the GPU does not need the host to start cropping: two small
+// kernels turn the packed boxes of the batch into the CropDev table (dims with the same IEEE operations as rt_crop_dims,
+// byte offsets and row prefix by a block scan), and the setup / row kernels are enqueued behind it BEFORE the host
+// waits for the boxes — the 0.15 ms the host spends on its copy of the table no longer leaves the GPU idle.
+// Capacities (table entries, pixel bytes) are those of the grow-only buffers at enqueue time; if the batch does not
+// fit, the kernels do nothing and the host — which computes the same sizes — falls back to the host-built table.
+struct CropPageDev { const uint8_t* page; int h, w; int pad; };
+// pass 1, one thread per box: everything of the descriptor but its offset
+__global__ void __launch_bounds__(128) crop_dims_kernel(const retto_b200_box* __restrict__ boxes, const int* __restrict__ box_off, int n_pages,
+                                                         const CropPageDev* __restrict__ pages, CropDev* __restrict__ crops, int cap_crops, int max_boxes,
+                                                         int* __restrict__ flip_flags) {
+    const int n = box_off[n_pages];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > cap_crops || n > max_boxes || i >= n) return;
+    const float* box = boxes[i].xy;
+    const float w_brc = side_len(box[6], box[7], box[4], box[5]);
+    const float w_tlc = side_len(box[0], box[1], box[2], box[3]);
+    const float h_brc = side_len(box[2], box[3], box[4], box[5]);
+    const float h_tlc = side_len(box[0], box[1], box[6], box[7]);
+    const float W = fmaxf(w_brc, w_tlc), H = fmaxf(h_brc, h_tlc);
+    const unsigned uw = (unsigned)W, uh = (unsigned)H;
+    const int rot = (uw > 0) && (__fdiv_rn((float)uh, (float)uw) >= 1.5f);
+    int cw = rot ? (int)uh : (int)uw, ch = rot ? (int)uw : (int)uh, status = RETTO_B200_OK;
+    const long long px = (long long)cw * ch;
+    if (px <= 0 || px > 0x3fffffffLL) { status = RETTO_B200_ERR_DEGENERATE_QUAD; cw = ch = 0; }
+    const int pg = rt_find_segment(box_off, n_pages, i);
+    CropDev c;
+    c.page = pages[pg].page; c.page_h = pages[pg].h; c.page_w = pages[pg].w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c.box[k] = box[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c.t[k] = 0.0f;
+    c.cls = 0; c.w = cw; c.h = ch; c.rot = rot; c.status = status; c.offset = 0;
+    crops[i] = c;
+    flip_flags[i] = 0;
+}
+// pass 2, one block: byte offsets and row prefix (exclusive scans over the boxes), totals
+__global__ void __launch_bounds__(1024) crop_scan_kernel(const int* __restrict__ box_off, int n_pages, CropDev* __restrict__ crops, int* __restrict__ row_prefix,
+                                                          int cap_crops, unsigned long long cap_bytes, CropTotals* __restrict__ totals, int max_boxes) {
+    __shared__ unsigned long long s_b[32];
+    __shared__ int s_r[32];
+    __shared__ unsigned long long s_carry_b;
+    __shared__ int s_carry_r;
+    const int n = box_off[n_pages];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (n > cap_crops || n > max_boxes) {   // more boxes than the table (or the packed box array) holds
+        if (threadIdx.x == 0) { totals->n = 0; totals->rows = 0; totals->overflow = 1; totals->bytes = 0; }
+        return;
+    }
+    if (threadIdx.x == 0) { s_carry_b = 0; s_carry_r = 0; row_prefix[0] = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        int rows = 0;
+        unsigned long long bytes = 0;
+        if (i < n) {
+            const int cw = crops[i].w, ch = crops[i].h;
+            rows = crops[i].rot ? cw : ch;
+            bytes = ((unsigned long long)cw * ch * 4 + 15) & ~15ULL;
+        }
+        unsigned long long xb = bytes;
+        int xr = rows;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long tb = __shfl_up_sync(0xffffffffu, xb, o);
+            const int t2 = __shfl_up_sync(0xffffffffu, xr, o);
+            if (lane >= o) { xb += tb; xr += t2; }
+        }
+        if (lane == 31) { s_b[w] = xb; s_r[w] = xr; }
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long tb = s_b[lane];
+            int t2 = s_r[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long ub = __shfl_up_sync(0xffffffffu, tb, o);
+                const int u2 = __shfl_up_sync(0xffffffffu, t2, o);
+                if (lane >= o) { tb += ub; t2 += u2; }
+            }
+            s_b[lane] = tb; s_r[lane] = t2;
+        }
+        __syncthreads();
+        const unsigned long long incl_b = s_carry_b + (w ? s_b[w - 1] : 0ULL) + xb;
+        const int incl_r = s_carry_r + (w ? s_r[w - 1] : 0) + xr;
+        if (i < n) { crops[i].offset = incl_b - bytes; row_prefix[i + 1] = incl_r; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_carry_b = incl_b; s_carry_r = incl_r; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long tot = s_carry_b;
+        const bool over = tot > cap_bytes;
+        totals->n = over ? 0 : n; totals->rows = over ? 0 : s_carry_r; totals->overflow = over ? 1 : 0; totals->bytes = tot;
     }
 }
 
@@ -204,6 +309,7 @@ void rt_crop_dims(const float box[8], int* cw, int* ch, int* rot) {
 template <class Get>
 static retto_b200_status crop_launch_impl(retto_b200_ctx* ctx, int n, retto_b200_crop_info* h_infos, Get get) {
     ctx->crops.clear();
+    ctx->crop_dev_check = false;
     if (n == 0) return RETTO_B200_OK;
     ctx->crops.resize(n);
     const size_t desc_bytes = sizeof(CropDev) * (size_t)n, blob_bytes = desc_bytes + sizeof(int) * ((size_t)n + 1);
@@ -240,11 +346,11 @@ static retto_b200_status crop_launch_impl(retto_b200_ctx* ctx, int n, retto_b200
     CropDev* d_crops = ctx->d_crop_descs.as<CropDev>();
     const int* d_prefix = reinterpret_cast<const int*>(ctx->d_crop_descs.as<char>() + desc_bytes);
     RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
-    crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n);
+    crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n, nullptr);
     RT_LAUNCH_CHECK(ctx);
     if (rows > 0) {
         RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
-        crop_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>());
+        crop_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr);
         RT_LAUNCH_CHECK(ctx);
     }
     // projection degeneracy is only known on the device: statuses (strided gather of one int per crop) come back async
@@ -276,12 +382,103 @@ retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_in
     if (do_sync) RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     const int* hs = ctx->h_crops.as<int>();
     retto_b200_status ret = RETTO_B200_OK;
+    if (ctx->crop_dev_check) {
+        ctx->crop_dev_check = false;
+        for (int i = 0; i < n; ++i)
+            if (hs[n + 2 * i] != ctx->crops[i].w || hs[n + 2 * i + 1] != ctx->crops[i].h) {
+                ctx->set_error("crop_boxes: host and device disagree on the size of crop " + std::to_string(i));
+                return RETTO_B200_ERR_CUDA;
+            }
+    }
     for (int i = 0; i < n; ++i) {
         ctx->crops[i].status = hs[i];
         h_infos[i].status = hs[i];
         if (hs[i] != RETTO_B200_OK) { ctx->set_error("crop_boxes: degenerate quad " + std::to_string(i) + " (reference: from_control_points().unwrap() panics)"); ret = RETTO_B200_ERR_DEGENERATE_QUAD; }
     }
     return ret;
+}
+
+// session path, step 1 (before the host has the boxes): descriptor table, projection setup and the row kernel, all sized
+// on the device.  `d_boxes` / `d_box_off` are the packed boxes of det_postprocess (box_off has n_pages + 1 entries).
+retto_b200_status rt_crop_enqueue_device(retto_b200_ctx* ctx, const retto_b200_box* d_boxes, const int* d_box_off, int n_pages,
+                                         const uint8_t* const* page_ptr, const int* page_h, const int* page_w, int crops_hint, int max_boxes) {
+    cudaStream_t st = ctx->stream;
+    ctx->crop_dev_cap = 0;
+    if (n_pages <= 0) return RETTO_B200_OK;
+    // capacities: grow-only buffers; the first batches of a context may fall back to the host-built table
+    const int cap_crops = std::max(crops_hint, 1024);
+    const size_t desc_bytes = sizeof(CropDev) * (size_t)cap_crops;
+    const size_t tab_bytes = desc_bytes + sizeof(int) * ((size_t)cap_crops + 1) + 64;
+    RT_CUDA_OK(ctx, ctx->d_crop_descs.ensure(tab_bytes, st));
+    RT_CUDA_OK(ctx, ctx->d_crop_flip.ensure(sizeof(int) * (size_t)cap_crops, st));
+    RT_CUDA_OK(ctx, ctx->d_crop_pix.ensure(1 << 20, st));
+    std::vector<CropPageDev> pt(n_pages);
+    for (int i = 0; i < n_pages; ++i) pt[i] = CropPageDev{page_ptr[i], page_h[i], page_w[i], 0};
+    RT_TRY(rt_upload(ctx, ctx->d_crop_pages, pt.data(), sizeof(CropPageDev) * (size_t)n_pages));
+    CropDev* d_crops = ctx->d_crop_descs.as<CropDev>();
+    int* d_prefix = reinterpret_cast<int*>(ctx->d_crop_descs.as<char>() + desc_bytes);
+    CropTotals* d_tot = reinterpret_cast<CropTotals*>(ctx->d_crop_descs.as<char>() + ((desc_bytes + sizeof(int) * ((size_t)cap_crops + 1) + 15) & ~size_t(15)));
+    RT_LAUNCH_BEGIN(ctx, "crop_dims_kernel");
+    crop_dims_kernel<<<(cap_crops + 127) / 128, 128, 0, st>>>(d_boxes, d_box_off, n_pages, ctx->d_crop_pages.as<CropPageDev>(), d_crops, cap_crops, max_boxes,
+                                                             ctx->d_crop_flip.as<int>());
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "crop_scan_kernel");
+    crop_scan_kernel<<<1, 1024, 0, st>>>(d_box_off, n_pages, d_crops, d_prefix, cap_crops, (unsigned long long)ctx->d_crop_pix.cap, d_tot, max_boxes);
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
+    crop_setup_kernel<<<(cap_crops + 63) / 64, 64, 0, st>>>(d_crops, cap_crops, &d_tot->n);
+    RT_LAUNCH_CHECK(ctx);
+    // one warp per row like the host-sized launch, the grid sized from the largest batch seen so far (+25 %); a batch with more
+    // rows than that falls back to the host-built table (a persistent grid-stride variant was measured 0.03-0.05 ms slower:
+    // more registers, no dynamic balancing of the rows)
+    const int row_hint = std::max(ctx->crop_rows_seen_max + ctx->crop_rows_seen_max / 4, 8192);
+    ctx->crop_dev_row_cap = (row_hint + 7) / 8 * 8;
+    RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
+    crop_rows_kernel<<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot);
+    RT_LAUNCH_CHECK(ctx);
+    ctx->crop_dev_cap = cap_crops;
+    ctx->crop_dev_cap_bytes = ctx->d_crop_pix.cap;
+    ctx->crop_dev_desc_bytes = desc_bytes;
+    return RETTO_B200_OK;
+}
+// step 2 (the host has the boxes): the host's copy of the sizes; *fits == false when the device table did not hold the
+// batch (the caller then runs rt_crop_launch_pages).  Enqueues the status read-back.
+retto_b200_status rt_crop_adopt_device(retto_b200_ctx* ctx, const retto_b200_box* h_boxes, int n, retto_b200_crop_info* h_infos, bool* fits) {
+    *fits = false;
+    ctx->crops.clear();
+    if (n == 0) { *fits = true; return RETTO_B200_OK; }
+    if (ctx->crop_dev_cap <= 0 || n > ctx->crop_dev_cap) return RETTO_B200_OK;
+    ctx->crops.resize(n);
+    unsigned long long off = 0;
+    for (int i = 0; i < n; ++i) {
+        int cw, ch, rot, status = RETTO_B200_OK;
+        rt_crop_dims(h_boxes[i].xy, &cw, &ch, &rot);
+        const long long px = (long long)cw * ch;
+        const unsigned long long o = off;
+        if (px <= 0 || px > 0x3fffffffLL) { status = RETTO_B200_ERR_DEGENERATE_QUAD; cw = ch = 0; }
+        else off += ((unsigned long long)px * 4 + 15) & ~15ULL;
+        ctx->crops[i] = retto_b200_ctx::CropHost{cw, ch, rot, status, o};
+        h_infos[i].w = cw; h_infos[i].h = ch; h_infos[i].rotated270 = rot; h_infos[i].status = status; h_infos[i].offset = o;
+    }
+    {
+        long long rows = 0;
+        for (int i = 0; i < n; ++i) rows += ctx->crops[i].rot ? ctx->crops[i].w : ctx->crops[i].h;
+        ctx->crop_rows_seen_max = (int)std::min<long long>(std::max<long long>(ctx->crop_rows_seen_max, rows), 1 << 28);
+        if (rows > ctx->crop_dev_row_cap) { ctx->crops.clear(); return RETTO_B200_OK; }   // the row grid was too small: host-built table
+    }
+    if (off > ctx->crop_dev_cap_bytes) {   // the device saw the same total and did nothing: grow with headroom for the next batch
+        RT_CUDA_OK(ctx, ctx->d_crop_pix.ensure((size_t)(off + off / 4), ctx->stream));
+        ctx->crops.clear();
+        return RETTO_B200_OK;
+    }
+    CropDev* d_crops = ctx->d_crop_descs.as<CropDev>();
+    RT_CUDA_OK(ctx, ctx->h_crops.ensure(sizeof(int) * 3 * (size_t)n));
+    // status + (w, h) of every crop: the host's sizes must be the device's (same IEEE operations; checked in rt_crop_finish)
+    RT_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_crops.p, sizeof(int), &d_crops[0].status, sizeof(CropDev), sizeof(int), n, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_crops.as<int>() + n, 2 * sizeof(int), &d_crops[0].w, sizeof(CropDev), 2 * sizeof(int), n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->crop_dev_check = true;
+    *fits = true;
+    return RETTO_B200_OK;
 }
 
 extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int32_t n,

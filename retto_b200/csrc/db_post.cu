@@ -1625,6 +1625,9 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
     RT_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(PageCounters) * n + sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, st));
     if (nspec > 0) RT_CUDA_OK(ctx, cudaMemcpyAsync(h_stage_boxes, ctx->d_boxes_out.p, sizeof(retto_b200_box) * (size_t)nspec, cudaMemcpyDeviceToHost, st));
     R.nspec = nspec;
+    // rt_det_post_end waits for THIS point, not for the stream: the session enqueues the crop kernels behind it
+    if (!ctx->ev_dp2) RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_dp2, cudaEventDisableTiming));
+    RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_dp2, st));
     return RETTO_B200_OK;
 }
 
@@ -1652,7 +1655,7 @@ retto_b200_status rt_det_post_end(retto_b200_ctx* ctx, int32_t* h_page_status, i
     (void)d_bm; (void)d_lab; (void)d_cid; (void)d_comps; (void)d_rowtab; (void)d_hull; (void)d_cand; (void)h_cnt0; (void)h_cnt; (void)h_stage_boxes; (void)d_offsets; (void)max_comps; (void)cap; (void)st; (void)d_pages; (void)d_cnt;
     const int nspec = R.nspec;
     int* h_off = reinterpret_cast<int*>(reinterpret_cast<char*>(h_cnt) + sizeof(PageCounters) * n);
-    RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    RT_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_dp2));
     retto_b200_status ret = RETTO_B200_OK;
     for (int i = 0; i < n; ++i) {
         int s = h_cnt[i].status;

@@ -145,6 +145,17 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
     const unsigned lut_biased = (unsigned)__cvta_generic_to_shared(sh.lut) - (k23 << 2);
     const float xr = __fdiv_rn((float)cw, (float)ln.resized_w);
     const ThumbAxis ax = thumb_axis(x, xr, cw);
+    // Pull the block's source tile into L2 before the row loops start.  The loops keep one output row of loads in flight
+    // per thread, which hides an L2 hit but not a DRAM miss (ncu: 59 % of the stall samples sat on the first use of the
+    // loaded words); every source row is used by some output row, so one prefetch per thread and row — at the thread's
+    // first source column, neighbouring threads cover neighbouring columns — touches every sector of the tile.
+    // Measured: 0.94 -> 0.88 ms per 256 pages.  (Two rows of loads in flight per thread: no further gain; a cp.async
+    // shared-memory tile per band of rows: slower, 1.01 ms.)
+    {
+        const unsigned first = ax.lo != ax.hi ? ax.lo : ax.hi - 1, last = ax.lo != ax.hi ? ax.hi - 1 : (ax.hi > cw - 1 ? cw - 1 : ax.hi);
+        const unsigned* __restrict__ pf = src + (flip ? cw - 1 - last : first);
+        for (unsigned r = 0; r < chh; ++r, pf += cw) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    }
 
     if (kind == BB_FF) {
         const AxisS xs = axis_small(ax, cw);

@@ -26,6 +26,9 @@ retto_b200_status rt_build_batches_launch(retto_b200_ctx* ctx, int32_t kind);
 retto_b200_status rt_crop_launch_pages(retto_b200_ctx* ctx, const retto_b200_box* h_boxes, const int32_t* box_off, int n_pages,
                                        const uint8_t* const* page_ptr, const int* page_h, const int* page_w, retto_b200_crop_info* h_infos);
 retto_b200_status rt_crop_finish(retto_b200_ctx* ctx, retto_b200_crop_info* h_infos, bool do_sync);
+retto_b200_status rt_crop_enqueue_device(retto_b200_ctx* ctx, const retto_b200_box* d_boxes, const int* d_box_off, int n_pages,
+                                         const uint8_t* const* page_ptr, const int* page_h, const int* page_w, int crops_hint, int max_boxes);
+retto_b200_status rt_crop_adopt_device(retto_b200_ctx* ctx, const retto_b200_box* h_boxes, int n, retto_b200_crop_info* h_infos, bool* fits);
 retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_post_desc* h_descs, int32_t n, int32_t max_boxes_total);
 retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx);
 retto_b200_status rt_det_post_end(retto_b200_ctx* ctx, int32_t* h_page_status, int32_t* h_box_offsets, retto_b200_box* h_boxes);
@@ -231,9 +234,19 @@ retto_b200_status PageRun::mid() {
     if (done) return ret;
     cudaStream_t st = ctx->stream;
     const retto_b200_config& cfg = ctx->cfg;
+    static const bool dev_crops = getenv("RETTO_B200_HOST_CROP_TABLE") == nullptr;   // A/B + tests: the host-built descriptor table
+    std::vector<const uint8_t*> pp(n_pages);
+    std::vector<int> ph(n_pages), pw(n_pages);
+    for (int i = 0; i < n_pages; ++i) { pp[i] = ps[i].d_img; ph[i] = ps[i].h; pw[i] = ps[i].w; }
     for (int attempt = 0; attempt < 2; ++attempt) {
         ctx->r_boxes.resize(det_cap);
         retto_b200_status s = rt_det_post_mid(ctx);
+        if (s == RETTO_B200_OK && dev_crops) {
+            // 5a. crops straight from the packed device boxes (session.rs:88-92), enqueued before the host waits for them
+            const int* d_off = reinterpret_cast<const int*>(ctx->d_dp_counters.as<char>() + sizeof(PageCounters) * (size_t)n_pages);
+            const int hint = ctx->crops_seen_max + ctx->crops_seen_max / 4 + 64;
+            s = rt_crop_enqueue_device(ctx, ctx->d_boxes_out.as<retto_b200_box>(), d_off, n_pages, pp.data(), ph.data(), pw.data(), hint, det_cap);
+        }
         if (s == RETTO_B200_OK) s = rt_det_post_end(ctx, page_status.data(), box_off.data(), ctx->r_boxes.data());
         if (s == RETTO_B200_ERR_CAPACITY && box_off[n_pages] > det_cap && attempt == 0) {   // more boxes than planned for: redo with room
             det_cap = box_off[n_pages];
@@ -264,10 +277,12 @@ retto_b200_status PageRun::mid() {
     // are collected after the one final sync — the host runs ahead and the kernels queue back to back.
     infos.resize(n_lines);
     {
-        std::vector<const uint8_t*> pp(n_pages);
-        std::vector<int> ph(n_pages), pw(n_pages);
-        for (int i = 0; i < n_pages; ++i) { pp[i] = ps[i].d_img; ph[i] = ps[i].h; pw[i] = ps[i].w; }
-        retto_b200_status s = rt_crop_launch_pages(ctx, ctx->r_boxes.data(), box_off.data(), n_pages, pp.data(), ph.data(), pw.data(), infos.data());
+        bool fits = false;
+        retto_b200_status s = RETTO_B200_OK;
+        if (dev_crops) s = rt_crop_adopt_device(ctx, ctx->r_boxes.data(), n_lines, infos.data(), &fits);
+        ctx->crops_seen_max = std::max(ctx->crops_seen_max, n_lines);
+        if (s == RETTO_B200_OK && !fits)   // first batches of a context (tables still growing) or RETTO_B200_HOST_CROP_TABLE: host-built table
+            s = rt_crop_launch_pages(ctx, ctx->r_boxes.data(), box_off.data(), n_pages, pp.data(), ph.data(), pw.data(), infos.data());
         if (s != RETTO_B200_OK) return fail(s);
     }
     tr.mark("crop_launch");
