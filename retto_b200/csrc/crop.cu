@@ -142,6 +142,7 @@ __device__ __forceinline__ void crop_pixel(const CropDev& c, int x, int y, unsig
 // copy, fully coalesced on both sides (same white-border rule: any tap of the 4x4 window outside the page -> white).
 // Everything else (affine / projective / rotate270) takes the bicubic path, lanes striding the row.
 struct CropTotals { int n, rows, overflow, pad; unsigned long long bytes; };   // written by crop_scan_kernel
+template <bool VEC>
 __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restrict__ crops, const int* __restrict__ row_prefix, int n_crops,
                                                          int total_rows, unsigned char* __restrict__ pix, const CropTotals* __restrict__ totals) {
     if (totals) {   // device-built descriptor table: the sizes come from the device, the grid from the host's row hint
@@ -161,11 +162,46 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restric
         const int iy = y + ty;
         const bool row_ok = !(iy - 1 < 0 || iy + 3 >= c.page_h);
         const int xlo = max(0, 1 - tx), xhi = min(w - 1, c.page_w - 4 - tx);   // columns whose 4x4 window is inside the page
-        uchar4* dst = reinterpret_cast<uchar4*>(pix + c.offset) + (size_t)y * w;
+        unsigned* dst = reinterpret_cast<unsigned*>(pix + c.offset) + (size_t)y * w;
         const unsigned char* src = c.page + ((size_t)iy * c.page_w + tx) * 3;
+        if (VEC) {
+            auto one = [&](int xx) {   // scalar pixel (row head / tail around the 16-byte-aligned groups)
+                unsigned o = 0xFFFFFFFFu;
+                if (row_ok && xx >= xlo && xx <= xhi) { const unsigned char* sp = src + 3 * xx; o = __ldg(sp) | (__ldg(sp + 1) << 8) | (__ldg(sp + 2) << 16) | 0xFF000000u; }
+                dst[xx] = o;
+            };
+            // groups of four pixels whose RGBX words form one aligned 16-byte store; their 12 source bytes are read as four
+            // aligned words (the byte phase of the row is the same for every group) and re-cut with funnel shifts / PRMT
+            // (0.280 -> 0.265 ms per 256 pages against the byte-load path below, at the same 40 registers; an unrolled
+            // variant at 48 registers lost a resident block per SM and was slower than both)
+            const int head = min(w, (int)((4u - ((unsigned)((size_t)y * w) & 3u)) & 3u));
+            const int G = (w - head) >> 2;
+            if (lane < head) one(lane);
+            { const int t0 = head + 4 * G; if (t0 + lane < w) one(t0 + lane); }
+            const unsigned sh8 = (unsigned)((uintptr_t)src + 3u * (unsigned)head) & 3u;   // (src + 3 x) & 3 for x = head + 4 g
+            const unsigned* wsrc = reinterpret_cast<const unsigned*>(src + 3 * head - sh8);
+            const unsigned shift = 8u * sh8;
+#pragma unroll 1
+            for (int g = lane; g < G; g += 32) {
+                const int x = head + 4 * g;
+                uint4 o = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                if (row_ok && x + 3 >= xlo && x <= xhi) {
+                    const unsigned* wp = wsrc + 3 * g;
+                    const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+                    const unsigned v0 = __funnelshift_r(w0, w1, shift), v1 = __funnelshift_r(w1, w2, shift), v2 = __funnelshift_r(w2, w3, shift);
+                    const unsigned p0 = v0 | 0xFF000000u, p1 = __byte_perm(v0, v1, 0x0543) | 0xFF000000u, p2 = __byte_perm(v1, v2, 0x0432) | 0xFF000000u,
+                                   p3 = (v2 >> 8) | 0xFF000000u;
+                    if (x >= xlo && x <= xhi) o.x = p0;
+                    if (x + 1 >= xlo && x + 1 <= xhi) o.y = p1;
+                    if (x + 2 >= xlo && x + 2 <= xhi) o.z = p2;
+                    if (x + 3 >= xlo && x + 3 <= xhi) o.w = p3;
+                }
+                *reinterpret_cast<uint4*>(dst + x) = o;
+            }
+            return;
+        }
         // four pixels per lane per trip: the twelve byte loads are independent and issued before the first store
-        // (a variant that read the row as aligned words and re-cut them with funnel shifts / PRMT into 16-byte stores was
-        // measured slower on B200: 0.31 ms vs 0.28 ms per 256 pages)
+        uchar4* dst4 = reinterpret_cast<uchar4*>(dst);
         for (int x = lane; x < w; x += 128) {
             uchar4 o[4];
 #pragma unroll
@@ -175,7 +211,7 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restric
                 if (row_ok && xx >= xlo && xx <= xhi) { const unsigned char* sp = src + 3 * xx; o[k].x = __ldg(sp); o[k].y = __ldg(sp + 1); o[k].z = __ldg(sp + 2); }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (x + 32 * k < w) dst[x + 32 * k] = o[k];
+            for (int k = 0; k < 4; ++k) if (x + 32 * k < w) dst4[x + 32 * k] = o[k];
         }
         return;
     }
@@ -350,7 +386,8 @@ static retto_b200_status crop_launch_impl(retto_b200_ctx* ctx, int n, retto_b200
     RT_LAUNCH_CHECK(ctx);
     if (rows > 0) {
         RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
-        crop_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr);
+        if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr);
+        else crop_rows_kernel<false><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr);
         RT_LAUNCH_CHECK(ctx);
     }
     // projection degeneracy is only known on the device: statuses (strided gather of one int per crop) come back async
@@ -434,7 +471,8 @@ retto_b200_status rt_crop_enqueue_device(retto_b200_ctx* ctx, const retto_b200_b
     const int row_hint = std::max(ctx->crop_rows_seen_max + ctx->crop_rows_seen_max / 4, 8192);
     ctx->crop_dev_row_cap = (row_hint + 7) / 8 * 8;
     RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
-    crop_rows_kernel<<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot);
+    if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot);
+    else crop_rows_kernel<false><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot);
     RT_LAUNCH_CHECK(ctx);
     ctx->crop_dev_cap = cap_crops;
     ctx->crop_dev_cap_bytes = ctx->d_crop_pix.cap;

@@ -946,8 +946,8 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
 // instructions per 128-px row and is issue-bound at 73 % issue utilisation; this form needs about half per pixel).
 // Runs are buffered per warp in shared memory and appended to the page's run table with ONE atomic per tile.
 #define BR3_BUF 96
-template <bool ALIGNED, int NW>   // NW words of 32 pixels per strip row (4: 128-px strips on the tile grid of the pixel path, 8: 256-px strips)
-__global__ void __launch_bounds__(128, NW == 4 ? 12 : 8) bitmap_runs3_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix,
+template <bool ALIGNED, int NW, int MINB>   // NW words of 32 pixels per strip row (4: 128-px strips on the tile grid of the pixel path, 8: 256-px strips)
+__global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix,
                                                             int n_pages, int total_tiles, float thr, int dilate,
                                                             unsigned char* __restrict__ bitmap, RunRec* __restrict__ runs,
                                                             PageCounters* __restrict__ counters) {
@@ -1469,14 +1469,14 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
             const bool a4 = vec || !(R.w_or & 3);
 #define BR3_ARGS(pre, tot) d_pages, pre, n, tot, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, ctx->d_runs.as<RunRec>(), d_cnt
             RT_LAUNCH_BEGIN(ctx, "bitmap_runs3_kernel");
-            if (nw == 8) {
+            if (nw == 8) {   // 62 registers, 8 blocks per SM; capping the registers for 10 / 12 blocks spills and is slower (0.59 / 0.92 ms)
                 const int tgrid = (R.total_tiles2 + 3) / 4;
-                if (R.a8) bitmap_runs3_kernel<true, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
-                else bitmap_runs3_kernel<false, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
+                if (R.a8) bitmap_runs3_kernel<true, 8, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
+                else bitmap_runs3_kernel<false, 8, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
             } else {
                 const int tgrid = (total_tiles + 3) / 4;
-                if (a4) bitmap_runs3_kernel<true, 4><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile_prefix, total_tiles));
-                else bitmap_runs3_kernel<false, 4><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile_prefix, total_tiles));
+                if (a4) bitmap_runs3_kernel<true, 4, 12><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile_prefix, total_tiles));
+                else bitmap_runs3_kernel<false, 4, 12><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile_prefix, total_tiles));
             }
 #undef BR3_ARGS
             RT_LAUNCH_CHECK(ctx);
