@@ -310,6 +310,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    numa_cores = 0
+    if world > 1 and not os.environ.get("RETTO_B200_NO_NUMA_BIND"):
+        # rank-local NUMA placement of the pinned page buffers (allocated below): matters for e2e at N > 1 only
+        from retto_b200.shard import bind_host_to_gpu
+        pr = torch.cuda.get_device_properties(local_rank)
+        try:
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        except Exception:
+            bus = None
+        numa_cores = bind_host_to_gpu(local_rank, bus)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -472,7 +482,7 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": P * page_bytes,
                     "d2h_bytes_per_step": int(n_lines * (36 + 8 + 4 + 4) + text_bytes + P * 32), "ms_per_step": ms_e2e / args.steps,
-                    "wall_ms_per_step": 1000.0 * wall_e2e / args.steps},
+                    "wall_ms_per_step": 1000.0 * wall_e2e / args.steps, "host_cores_bound_to_gpu_numa": numa_cores},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "summary": summary,
             "lines_per_step": int(n_lines), "wall_ms_per_step": 1000.0 * wall_dev / args.steps}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -60,6 +60,9 @@ extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->ev_dp) cudaEventDestroy(c->ev_dp);
     if (c->ev_dp2) cudaEventDestroy(c->ev_dp2);
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto& sl : c->stage_slots) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     delete c;  // DevBuf / HostBuf members free their memory
     cudaStreamDestroy(s);

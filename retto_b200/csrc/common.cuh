@@ -141,6 +141,7 @@ struct retto_b200_ctx {
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
     int timer_pending = -1;
+    cudaStream_t timer_stream = nullptr;   // set around a launch on an auxiliary stream
     std::vector<double> timer_total_ms;
     std::vector<uint64_t> timer_count;
     cudaEvent_t get_event() {
@@ -152,13 +153,13 @@ struct retto_b200_ctx {
         for (size_t i = 0; i < timer_names.size(); ++i) if (timer_names[i] == name) { id = (int)i; break; }
         if (id < 0) { id = (int)timer_names.size(); timer_names.push_back(name); timer_total_ms.push_back(0); timer_count.push_back(0); }
         TimedLaunch t{id, get_event(), get_event()};
-        cudaEventRecord(t.a, stream);
+        cudaEventRecord(t.a, timer_stream ? timer_stream : stream);
         timed.push_back(t);
         timer_pending = (int)timed.size() - 1;
     }
     void timer_end() {
         if (timer_pending < 0) return;
-        cudaEventRecord(timed[timer_pending].b, stream);
+        cudaEventRecord(timed[timer_pending].b, timer_stream ? timer_stream : stream);
         timer_pending = -1;
     }
     void timer_collect() {  // caller synchronises the stream first
@@ -203,6 +204,8 @@ struct retto_b200_ctx {
     HostBuf h_dp;
     cudaEvent_t ev_dp = nullptr;   // behind the early counter read-back of det_postprocess
     cudaEvent_t ev_dp2 = nullptr;  // behind the box read-back of det_postprocess
+    cudaStream_t aux_stream = nullptr;             // box_score_fast || unclip (db_post.cu): fork / join around the two kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     struct DpRun { int n = 0, cap = 0, total_tiles = 0, total_tiles2 = 0, nspec = 0, w_or = 0; size_t hdr_bytes = 0; bool vec = true, a8 = true; } dp;   // begin -> mid -> end state
 
     // crops

@@ -37,6 +37,8 @@ struct BoxCand {
     int rect2[8];   // second min_area_rect (after unclip), before scale_and_clip
     float dist;     // unclip distance
     int n_off;      // hull size of the unclipped polygon
+    int st0;        // status after the first rect (immutable once PHASE 0 has run)
+    int st2, err2;  // PHASE 3 (unclip running beside the score kernel): its status / page error, merged by geom_merge_kernel
 };
 
 __device__ __forceinline__ int find_root(const int* __restrict__ L, int a) {
@@ -481,6 +483,10 @@ struct GeomParams {
 //   PHASE 1  box_score_fast                                                  (long sequential chain: light kernel, so
 //                                                                             every box of an SM is resident at once)
 //   PHASE 2  unclip -> second min_area_rect -> scale_and_clip -> filters     (f64 trig: register heavy)
+//   PHASE 3  = PHASE 2 for every box that reached the score stage, launched on a second stream BESIDE the score kernel
+//            (the score kernel is a set of long dependent add chains — its tail leaves the SMs nearly empty, and the
+//            unclip of a box does not need its score, only the decision).  It writes st2 / err2 instead of status /
+//            valid / the page status; geom_merge_kernel applies them to the boxes whose score passed.
 #define ST_NEED_SCORE 7
 #define ST_NEED_UNCLIP 8
 template <int PHASE>
@@ -522,7 +528,7 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
             int st = ST_NEED_SCORE;
             if (cr.key == 0x7fffffff) st = 6;                          // every run spans the full width: never discovered
             else if (sside < (float)gp.min_mini_box_size) st = 1;
-            out->status = st;
+            out->status = st; out->st0 = st; out->st2 = -2; out->err2 = 0;
         }
         return;
     }
@@ -542,15 +548,14 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
         if (lane == 0) { out->score = score; out->status = (score < gp.box_thresh) ? 2 : ST_NEED_UNCLIP; }
         return;
     }
-    if (PHASE == 2) {
+    if (PHASE == 2 || PHASE == 3) {
         __shared__ int2 s_pts[4][MAX_OFFSET_PTS];
         __shared__ int2 s_hull[4][2 * MAX_OFFSET_PTS];
         __shared__ int s_n[4];
-        if (out->status != ST_NEED_UNCLIP) return;
+        if (PHASE == 2 ? out->status != ST_NEED_UNCLIP : out->st0 != ST_NEED_SCORE) return;
         int qx[4], qy[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { qx[i] = out->rect1[2 * i]; qy[i] = out->rect1[2 * i + 1]; }
-        const float score = out->score;
         __syncwarp();
         if (lane == 0) {
             const float dist = unclip_distance(qx, qy, gp.unclip_ratio);
@@ -583,16 +588,20 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
         const int nh = s_n[wib];
         if (nh <= 0) {
             // Clipper returned nothing (or overflow): the reference would panic in min_area_rect(&[])
-            if (lane == 0) { atomicMax(&counters[page].status, nh < 0 ? RETTO_B200_ERR_CAPACITY : RETTO_B200_ERR_DEGENERATE_QUAD); out->status = 5; }
+            if (lane == 0) {
+                const int code = nh < 0 ? RETTO_B200_ERR_CAPACITY : RETTO_B200_ERR_DEGENERATE_QUAD;
+                if (PHASE == 2) { atomicMax(&counters[page].status, code); out->status = 5; }
+                else { out->err2 = code; out->st2 = 5; }
+            }
             return;
         }
         double q2[8];
         warp_min_area_rect(s_hull[wib], nh, q2);
         const float sside2 = sside_of(q2);
         if (lane == 0) { out->n_off = nh; for (int i = 0; i < 8; ++i) out->rect2[i] = (int)q2[i]; }
-        if (sside2 < (float)(gp.min_mini_box_size + 2)) { if (lane == 0) out->status = 3; return; }
+        if (sside2 < (float)(gp.min_mini_box_size + 2)) { if (lane == 0) { if (PHASE == 2) out->status = 3; else out->st2 = 3; } return; }
         if (lane == 0) {
-            out->status = 4;
+            if (PHASE == 2) out->status = 4; else out->st2 = 4;
             const double inv_w = __ddiv_rn((double)pg.ori_w, (double)pg.w), inv_h = __ddiv_rn((double)pg.ori_h, (double)pg.h);
             float b[8];
 #pragma unroll
@@ -605,12 +614,25 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
             if (!(pb_h <= 3.0f || pb_w <= 3.0f)) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) out->xy[i] = b[i];
-                out->score = score;
-                out->valid = 1;
-                out->status = 0;
+                if (PHASE == 2) { out->valid = 1; out->status = 0; }   // out->score is already the box score (PHASE 1)
+                else out->st2 = 0;
             }
         }
     }
+}
+
+// after the join of box_geometry_kernel<1> (main stream) and <3> (auxiliary stream): boxes whose score passed take the
+// outcome of their unclip, everything else keeps the status the score stage gave it
+__global__ void __launch_bounds__(128) geom_merge_kernel(int n_pages, PageCounters* __restrict__ counters, BoxCand* __restrict__ cand, int max_comps) {
+    const int page = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (page >= n_pages || counters[page].status == RETTO_B200_ERR_CAPACITY || i >= counters[page].n_roots || i >= max_comps) return;
+    BoxCand& b = cand[(size_t)page * max_comps + i];
+    if (b.st0 != ST_NEED_SCORE || b.status != ST_NEED_UNCLIP) return;
+    const int st2 = b.st2;
+    b.status = st2;
+    b.valid = st2 == 0;
+    if (st2 == 5) atomicMax(&counters[page].status, b.err2);
 }
 
 // ---- hole borders ---------------------------------------------------------------------------------------------
@@ -988,9 +1010,14 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
         for (int j = 0; j < NW; ++j) r.v[j] = -CUDART_INF_F;   // outside the page: below every threshold
         r.l = -CUDART_INF_F;
         if (y < 0 || y >= y1) return r;
-        const float* row = prob + (size_t)y * W + x0;
+        const float* row = prob + (size_t)y * W + x0 + lane;
+        if (!partial) {   // full strip (all but the last of a page row): unpredicated loads
 #pragma unroll
-        for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) r.v[j] = __ldg(row + 32 * j + lane);
+            for (int j = 0; j < NW; ++j) r.v[j] = __ldg(row + 32 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) r.v[j] = __ldg(row + 32 * j);
+        }
         if (lane == 0 && x0 > 0) r.l = __ldg(row - 1);
         return r;
     };
@@ -1066,6 +1093,7 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
         int open_start = -1;
 #pragma unroll
         for (int j = 0; j < NW; ++j) {
+            if (!d[j]) continue;   // no start and no end in an empty word (warp-uniform)
             unsigned st = d[j] & ~__funnelshift_l(j ? d[j ? j - 1 : 0] : 0u, d[j], 1);
             unsigned en = d[j] & ~__funnelshift_r(d[j], j < NW - 1 ? d[j < NW - 1 ? j + 1 : j] : 0u, 1);
             const int xb = x0 + 32 * j;
@@ -1534,12 +1562,39 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
         RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<0:rect1>");
         box_geometry_kernel<0><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
         RT_LAUNCH_CHECK(ctx);
-        RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
-        box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
-        RT_LAUNCH_CHECK(ctx);
-        RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<2:unclip>");
-        box_geometry_kernel<2><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
-        RT_LAUNCH_CHECK(ctx);
+        const bool concurrent = getenv("RETTO_B200_GEOM_CONCURRENT") != nullptr;   // opt-in: no gain on 256 text pages (4.89 vs 4.90 ms), -5 % on config 2 (40 k boxes)
+        if (!concurrent) {
+            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
+            box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+            RT_LAUNCH_CHECK(ctx);
+            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<2:unclip>");
+            box_geometry_kernel<2><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+            RT_LAUNCH_CHECK(ctx);
+        } else {
+            // score (main stream) || unclip of every box that reached the score stage (auxiliary stream), then the merge
+            if (!ctx->aux_stream) {
+                RT_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+                RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            }
+            RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork, st));
+            RT_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
+            box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+            RT_LAUNCH_CHECK(ctx);
+            ctx->timer_stream = ctx->aux_stream;
+            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<3:unclip||score>");
+            box_geometry_kernel<3><<<grid, 128, 0, ctx->aux_stream>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+            ctx->launches++;
+            if (ctx->timing_enabled) ctx->timer_end();
+            ctx->timer_stream = nullptr;
+            if (cudaGetLastError() != cudaSuccess) { ctx->set_error("kernel launch: box_geometry_kernel<3>"); return RETTO_B200_ERR_CUDA; }
+            RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+            RT_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+            RT_LAUNCH_BEGIN(ctx, "geom_merge_kernel");
+            geom_merge_kernel<<<dim3((max_n + 127) / 128, n), 128, 0, st>>>(n, d_cnt, d_cand, max_comps);
+            RT_LAUNCH_CHECK(ctx);
+        }
     }
     // hole borders: pages with #components - Euler number > 0
     {

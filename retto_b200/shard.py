@@ -37,3 +37,27 @@ def gather_by_page(local_results, local_indices, n_pages: int, group=None):
         for i, r in part:
             full[i] = r
     return full
+
+
+def bind_host_to_gpu(device_index: int, pci_bus_id: str | None = None) -> int:
+    """Pin the calling process to the CPU cores NVML reports as local to the GPU (same NUMA node / PCIe root), so
+    that the pinned page buffers it allocates afterwards are placed on that node (first-touch) and each rank's
+    host->device stream runs over its own memory controller.  Matters only for the host-resident (e2e) path with
+    several ranks on one box: unbound, the 8 x 50 GB/s of page uploads share whichever node the ranks happened to
+    start on.  Returns the number of cores bound to (0 = NVML / affinity unavailable, nothing changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if isinstance(pci_bus_id, str) else pci_bus_id) \
+            if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0

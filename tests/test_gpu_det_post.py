@@ -5,14 +5,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["run-table", "pixel-planes"])
+@pytest.fixture(autouse=True, params=["run-table", "pixel-planes", "run-table+concurrent-geometry"])
 def ccl_path(request, monkeypatch):
-    """every test of this module runs on both CCL formulations of csrc/db_post.cu: the run-table path (default) and the
-    pixel-plane passes (its fallback)"""
+    """every test of this module runs on both CCL formulations of csrc/db_post.cu — the run-table path (default) and the
+    pixel-plane passes (its fallback) — and on the opt-in mode that runs unclip beside the score kernel on a second stream"""
+    monkeypatch.delenv("RETTO_B200_PIXEL_CCL", raising=False)
+    monkeypatch.delenv("RETTO_B200_GEOM_CONCURRENT", raising=False)
     if request.param == "pixel-planes":
         monkeypatch.setenv("RETTO_B200_PIXEL_CCL", "1")
-    else:
-        monkeypatch.delenv("RETTO_B200_PIXEL_CCL", raising=False)
+    elif request.param == "run-table+concurrent-geometry":
+        monkeypatch.setenv("RETTO_B200_GEOM_CONCURRENT", "1")
     return request.param
 
 
@@ -190,6 +192,6 @@ def test_no_spurious_hole_path(ctx, ccl_path):
     l0 = ctx.launch_count
     out = ctx.det_postprocess([g], [p.shape])
     used = ctx.launch_count - l0
-    assert used <= (9 if ccl_path == "run-table" else 12), used    # no bg_* / hole_* kernels
+    assert used <= {"run-table": 9, "run-table+concurrent-geometry": 10}.get(ccl_path, 12), used    # no bg_* / hole_* kernels
     ref = O.det_postprocess(p, *p.shape)
     assert np.array_equal(out.page(0)[0], ref.boxes)

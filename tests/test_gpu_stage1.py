@@ -71,7 +71,9 @@ def test_ctc_nan_is_error(ctx, synth_dict):
     assert e.value.status == 5  # ERR_NAN_LOGITS (reference: argmax().unwrap() panics, rec_processor.rs:198)
 
 
-@pytest.mark.parametrize("hw", [(960, 960), (736, 1280), (640, 480), (480, 640), (100, 333), (1000, 740)])
+# identity, both axes up, and every mix of an axis rounded up / down to the multiple of 32 (windows of 1-2 pixels)
+@pytest.mark.parametrize("hw", [(960, 960), (736, 1280), (640, 480), (480, 640), (100, 333), (1000, 740), (1010, 745), (745, 1010), (750, 1500),
+                                (1111, 1999), (737, 737), (1487, 751), (300, 1400)])
 def test_det_preprocess_parity(ctx, hw):
     import torch
     from oracle import oracle as O
@@ -102,7 +104,9 @@ def test_det_preprocess_batch_mixed(ctx):
 
 
 @pytest.mark.parametrize("case", [((200, 300), (200, 300)), ((400, 600), (200, 300)), ((2896, 4096), (1408, 1984)),
-                                  ((480, 640), (736, 992)), ((37, 211), (48, 274)), ((61, 150), (48, 118)), ((20, 20), (32, 32))])
+                                  ((480, 640), (736, 992)), ((37, 211), (48, 274)), ((61, 150), (48, 118)), ((20, 20), (32, 32)),
+                                  ((3000, 2000), (1984, 1312)), ((900, 2500), (704, 1984)), ((2001, 2001), (1984, 1984)), ((96, 96), (32, 32)),
+                                  ((100, 97), (32, 32))])
 def test_thumbnail_parity(ctx, case):
     import torch
     from oracle import oracle as O
