@@ -234,7 +234,7 @@ retto_b200_status PageRun::mid() {
     if (done) return ret;
     cudaStream_t st = ctx->stream;
     const retto_b200_config& cfg = ctx->cfg;
-    static const bool dev_crops = getenv("RETTO_B200_HOST_CROP_TABLE") == nullptr;   // A/B + tests: the host-built descriptor table
+    const bool dev_crops = getenv("RETTO_B200_HOST_CROP_TABLE") == nullptr;   // A/B + tests: the host-built descriptor table
     std::vector<const uint8_t*> pp(n_pages);
     std::vector<int> ph(n_pages), pw(n_pages);
     for (int i = 0; i < n_pages; ++i) { pp[i] = ps[i].d_img; ph[i] = ps[i].h; pw[i] = ps[i].w; }

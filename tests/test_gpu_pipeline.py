@@ -359,6 +359,39 @@ def test_session_lanes_equal_serial(ctx, synth_dict):
         _same_results(a, b)
 
 
+def test_session_device_crop_table_paths(synth_dict, monkeypatch):
+    """csrc/crop.cu builds the crop descriptor table on the device and enqueues the crop kernels before the host has the
+    boxes; a batch that does not fit the capacities of the moment (table entries, pixel bytes, row grid) must fall back to the
+    host-built table.  A fresh context sees: a small batch (fallback: nothing sized yet), a much larger one (fallback again:
+    more rows / bytes than the hints), the same large one (device path), the small one (device path, oversized grid) — all
+    four must equal the host-table results."""
+    import torch
+    from retto_b200.api import Context
+    small, large = _small_pages(6, 21), _small_pages(90, 22)
+    dev_s = [torch.from_numpy(im).cuda() for im in small]
+    dev_l = [torch.from_numpy(im).cuda() for im in large]
+    torch.cuda.synchronize()
+    monkeypatch.setenv("RETTO_B200_HOST_CROP_TABLE", "1")
+    c0 = Context(0)
+    try:
+        s0 = _session(c0, StatelessWorker(), synth_dict)
+        ref_s, ref_l = s0.run_pages(dev_s, on_device=True), s0.run_pages(dev_l, on_device=True)
+    finally:
+        c0.close()
+    assert sum(len(r.det_result) for r in ref_l) > 90
+    monkeypatch.delenv("RETTO_B200_HOST_CROP_TABLE")
+    c1 = Context(0)
+    try:
+        s1 = _session(c1, StatelessWorker(), synth_dict)
+        for dev, ref in [(dev_s, ref_s), (dev_l, ref_l), (dev_l, ref_l), (dev_s, ref_s), (dev_l, ref_l)]:
+            got = s1.run_pages(dev, on_device=True)
+            assert len(got) == len(ref)
+            for a, b in zip(got, ref):
+                _same_results(a, b)
+    finally:
+        c1.close()
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_session_chunked_pipeline_equals_unchunked(ctx, synth_dict, pinned):
     """more host pages than one chunk take the chunked H2D/compute pipeline (csrc/session.cu): results must equal
