@@ -36,15 +36,33 @@ def main():
     from bench import ReplayWorker
     from retto_b200._lib import Page, Results
     from retto_b200.api import Context
+    from retto_b200.shard import shard_indices
     from tools.synth import synth_dict_text
-    ctx = Context(0)
+    # under torchrun: `--pages` per GPU; the global list of pages * world pages is LPT-sharded by H*W over the ranks
+    # (retto_b200.shard, the page-parallel driver's rule), no collective on the data path; times are the max over ranks
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        saved = os.dup(1); os.dup2(2, 1)   # NCCL banner off stdout
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            dist.barrier()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    ctx = Context(local_rank)
     ctx.dict_load(synth_dict_text())
     L, H = ctx._L, ctx._h
     pages_np, probs_np = make_mixed(args.unique)
-    P, U = args.pages, len(pages_np)
-    pages_dev = [torch.from_numpy(pages_np[i % U]).cuda() for i in range(P)]
-    probs_dev = [torch.from_numpy(probs_np[i % U]).cuda() for i in range(P)]
-    sizes = [pages_np[i % U].shape[:2] for i in range(P)]
+    U = len(pages_np)
+    mine = shard_indices([pages_np[i % U].shape[0] * pages_np[i % U].shape[1] for i in range(args.pages * world)], world)[rank]
+    P = len(mine)
+    pages_dev = [torch.from_numpy(pages_np[i % U]).cuda() for i in mine]
+    probs_dev = [torch.from_numpy(probs_np[i % U]).cuda() for i in mine]
+    sizes = [pages_np[i % U].shape[:2] for i in mine]
+    pages_np = [pages_np[i % U] for i in mine]
+    U = P
     total_bytes = sum(h * w * 3 for h, w in sizes)
     hp = C.c_void_p()
     ctx._check(L.retto_b200_host_alloc(H, total_bytes + 64 * P, C.byref(hp)))
@@ -56,7 +74,7 @@ def main():
         o += (h * w * 3 + 63) & ~63
     pg_dev = (Page * P)(*[Page(pages_dev[i].data_ptr(), sizes[i][0], sizes[i][1], 1) for i in range(P)])
     pg_host = (Page * P)(*[Page(hp.value + offs[i], sizes[i][0], sizes[i][1], 0) for i in range(P)])
-    worker = ReplayWorker(torch, "cuda:0", probs_dev, seed=0)
+    worker = ReplayWorker(torch, f"cuda:{local_rank}", probs_dev, seed=rank)
     res = Results()
 
     def step(pg):
@@ -72,6 +90,9 @@ def main():
         for _ in range(3):
             step(pg)
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
         if kernels:
             ctx.enable_kernel_timing(True); ctx.reset_kernel_times()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -84,16 +105,25 @@ def main():
         if kernels:
             kt = {k: v[1] / steps for k, v in ctx.kernel_times().items() if v[0]}
             ctx.enable_kernel_timing(False)
-        return e0.elapsed_time(e1) / steps, kt
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, kt
 
     ms_dev, _ = timed(pg_dev, args.steps)
     ms_k, kt = timed(pg_dev, args.steps, kernels=True)
     ms_host, _ = timed(pg_host, args.steps)
-    print(json.dumps({"config": f"{P} mixed-size pages (long side logU[640,4096], aspect U[0.5,1]; {U} unique), 1 GPU",
-                      "pixels_per_step": int(sum(h * w for h, w in sizes)), "lines_per_step": int(res.n_lines),
-                      "ms_device_resident": ms_dev, "pages_per_s_device_resident": P / ms_dev * 1e3,
-                      "ms_host_resident": ms_host, "pages_per_s_host_resident": P / ms_host * 1e3, "h2d_bytes_per_step": total_bytes,
-                      "kernels_ms": dict(sorted(kt.items(), key=lambda kv: -kv[1]))}))
+    PT = args.pages * world
+    if rank == 0:
+        print(json.dumps({"config": f"{PT} mixed-size pages per step (long side logU[640,4096], aspect U[0.5,1]; {args.unique} unique), LPT-sharded by H*W over {world} GPU(s)",
+                          "n_gpus": world, "pages_rank0": P, "pixels_per_step_rank0": int(sum(h * w for h, w in sizes)), "lines_per_step_rank0": int(res.n_lines),
+                          "ms_device_resident": ms_dev, "pages_per_s_device_resident": PT / ms_dev * 1e3,
+                          "ms_host_resident": ms_host, "pages_per_s_host_resident": PT / ms_host * 1e3, "h2d_bytes_per_step_rank0": total_bytes,
+                          "kernels_ms_rank0": dict(sorted(kt.items(), key=lambda kv: -kv[1]))}))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
