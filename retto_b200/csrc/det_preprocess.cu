@@ -111,6 +111,97 @@ __global__ void __launch_bounds__(256) det_pre_resize_kernel(const DetPreDev* __
         __stcs(reinterpret_cast<float4*>(pg.dst + c * plane + off), make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
 }
 
+// Resizes with both ratios <= 2 (every window at most 2 x 2 — everything resize_either produces from a resize_both-ed page:
+// up-scaling of a short side below limit_side_len, and the slight up / down scaling of each axis to its multiple of 32),
+// laid out like build_batches (rec_batch.cu): one block = 128 output columns x 64 output rows of one page, one thread =
+// one output COLUMN.  Everything that depends only on x is computed once per thread, everything that depends only on y
+// once per block (shared memory), so the per-pixel work is the window arithmetic alone — the generic kernel spends most
+// of its ~180 instructions per pixel on axes, unit lookup and addressing (ncu: 65 % issue utilisation).  The four
+// branches of imageops::thumbnail are written out for windows of one or two pixels (branch (i) is the integer mean
+// (s + n/2) / n with n in {1, 2, 4}); u8 -> f32 through the 2^23 mantissa trick, f32 -> u8 truncation through FADD.RZ.
+#define RS_COLS 128
+#define RS_ROWS 64
+__device__ __forceinline__ float dp_u8f(unsigned b) { return __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f); }   // exact float of b < 2^23
+struct RsRow { unsigned o0, o1; float f, omf, f2, omf2; int kind, pad; };   // kind 0: rows (o0, o1) mixed with f; 1 / 2: block of 1 / 2 rows
+__global__ void __launch_bounds__(RS_COLS) det_pre_resize_cols_kernel(const DetPreDev* __restrict__ pages, const int* __restrict__ block_prefix,
+                                                                      int n_pages, NormParams np) {
+    __shared__ float s_lut[3][256];
+    __shared__ RsRow s_row[RS_ROWS];
+    __shared__ int s_page;
+    for (int i = threadIdx.x; i < 768; i += RS_COLS) {
+        const int c = i >> 8, v = i & 255;
+        s_lut[c][v] = norm1((unsigned char)v, np.scale, np.mean[c], np.stdv[c]);
+    }
+    if (threadIdx.x == 0) s_page = rt_find_segment(block_prefix, n_pages, (int)blockIdx.x);
+    __syncthreads();
+    const int p = s_page;
+    const DetPreDev pg = pages[p];
+    const int nbx = (pg.ow + RS_COLS - 1) / RS_COLS;
+    const int lb = (int)blockIdx.x - block_prefix[p];
+    const int by = lb / nbx, bx = lb - by * nbx;
+    const int y0 = by * RS_ROWS, rows = min(RS_ROWS, pg.oh - y0);
+    const unsigned W = (unsigned)pg.w, H = (unsigned)pg.h;
+    if ((int)threadIdx.x < rows) {
+        const ThumbAxis ay = thumb_axis(y0 + (int)threadIdx.x, pg.yr, H);
+        const bool yb = ay.lo != ay.hi;
+        const unsigned r0 = yb ? ay.lo : ay.hi - 1, r1 = yb ? ay.hi - 1 : (ay.hi > H - 1 ? H - 1 : ay.hi);
+        RsRow r;
+        r.o0 = r0 * W * 3u; r.o1 = r1 * W * 3u;
+        r.f = ay.fract; r.omf = __fsub_rn(1.0f, ay.fract);
+        r.f2 = __fdiv_rn(r.f, 2.0f); r.omf2 = __fdiv_rn(r.omf, 2.0f);
+        r.kind = yb ? (ay.hi - ay.lo > 1 ? 2 : 1) : 0; r.pad = 0;
+        s_row[threadIdx.x] = r;
+    }
+    __syncthreads();
+    const int x = bx * RS_COLS + (int)threadIdx.x;
+    if (x >= pg.ow) return;
+    const ThumbAxis ax = thumb_axis(x, pg.xr, W);
+    const bool xb = ax.lo != ax.hi;
+    const unsigned c0 = xb ? ax.lo : ax.hi - 1, c1 = xb ? ax.hi - 1 : (ax.hi > W - 1 ? W - 1 : ax.hi);
+    const bool nx2 = xb && (ax.hi - ax.lo > 1);
+    const float fh = ax.fract, omh = __fsub_rn(1.0f, ax.fract);
+    const float fh2 = __fdiv_rn(fh, 2.0f), omh2 = __fdiv_rn(omh, 2.0f);
+    const unsigned char* __restrict__ sa = pg.src + 3u * c0;
+    const unsigned char* __restrict__ sb = pg.src + 3u * c1;
+    const size_t plane = (size_t)pg.oh * pg.ow;
+    float* dst = pg.dst + (size_t)y0 * pg.ow + x;
+    for (int yy = 0; yy < rows; ++yy, dst += pg.ow) {
+        const RsRow r = s_row[yy];
+        const bool yb = r.kind != 0, ny2 = r.kind == 2;
+        const unsigned char* p00 = sa + r.o0;
+        const unsigned char* p10 = sb + r.o0;
+        const unsigned char* p01 = sa + r.o1;
+        const unsigned char* p11 = sb + r.o1;
+        unsigned q[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const unsigned v00 = __ldg(p00 + ch), v10 = __ldg(p10 + ch), v01 = __ldg(p01 + ch), v11 = __ldg(p11 + ch);
+            if (xb && yb) {
+                const unsigned sh = (nx2 ? 1u : 0u) + (ny2 ? 1u : 0u);
+                const unsigned sum = v00 + (nx2 ? v10 : 0u) + (ny2 ? v01 : 0u) + ((nx2 && ny2) ? v11 : 0u);
+                q[ch] = (sum + ((1u << sh) >> 1)) >> sh;
+            } else {
+                float v;
+                if (!xb && !yb) {
+                    const float f_tr = __fmul_rn(r.f, fh), f_tl = __fmul_rn(r.f, omh), f_br = __fmul_rn(r.omf, fh), f_bl = __fmul_rn(r.omf, omh);
+                    v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, dp_u8f(v10)), __fmul_rn(f_tr, dp_u8f(v11))), __fmul_rn(f_bl, dp_u8f(v00))),
+                                  __fmul_rn(f_tl, dp_u8f(v01)));
+                } else if (!xb) {   // columns (c0, c1) mixed, summed over the 1-2 rows of the block: fl = (1 - fx) / ny, fr = fx / ny
+                    const float fr = ny2 ? fh2 : fh, fl = ny2 ? omh2 : omh;
+                    v = __fadd_rn(__fmul_rn(fl, dp_u8f(v00 + (ny2 ? v01 : 0u))), __fmul_rn(fr, dp_u8f(v10 + (ny2 ? v11 : 0u))));
+                } else {            // rows (o0, o1) mixed, summed over the 1-2 columns of the block: fb = (1 - fy) / nx, ft = fy / nx
+                    const float ft = nx2 ? r.f2 : r.f, fb = nx2 ? r.omf2 : r.omf;
+                    v = __fadd_rn(__fmul_rn(fb, dp_u8f(v00 + (nx2 ? v10 : 0u))), __fmul_rn(ft, dp_u8f(v01 + (nx2 ? v11 : 0u))));
+                }
+                q[ch] = __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xFFu;   // NumCast truncation of 0 <= v < 256
+            }
+        }
+        __stcs(dst, s_lut[0][q[2]]);              // tensor planes are B, G, R
+        __stcs(dst + plane, s_lut[1][q[1]]);
+        __stcs(dst + 2 * plane, s_lut[2][q[0]]);
+    }
+}
+
 // scalar fallback for output widths that are not a multiple of 4 (only reachable through a direct API
 // call with hand-picked dims; resize_either always yields multiples of 32)
 __global__ void det_pre_scalar_kernel(DetPreDev pg, NormParams np) {
@@ -225,8 +316,9 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
     NormParams np;
     np.scale = ctx->cfg.det_scale;
     for (int c = 0; c < 3; ++c) { np.mean[c] = ctx->cfg.det_mean[c]; np.stdv[c] = ctx->cfg.det_std[c]; }
-    std::vector<DetPreDev> ident, rs;
-    std::vector<int> ident_pre{0}, rs_pre{0};
+    std::vector<DetPreDev> ident, rs, cols;
+    std::vector<int> ident_pre{0}, rs_pre{0}, cols_pre{0};
+    const bool generic_only = getenv("RETTO_B200_DETPRE_GENERIC") != nullptr;   // tests / A-B: every resize through thumbnail_pixel
     for (int i = 0; i < n; ++i) {
         const retto_b200_det_pre_desc& d = h_descs[i];
         if (!d.d_rgb || !d.d_out || d.h <= 0 || d.w <= 0 || d.out_h <= 0 || d.out_w <= 0) {
@@ -239,6 +331,10 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
         if (d.out_h == d.h && d.out_w == d.w && (px % 512 == 0) && aligned) {
             ident.push_back(dv);
             ident_pre.push_back(ident_pre.back() + (int)(px / 512));
+        } else if (!generic_only && d.w <= 2LL * d.out_w && d.h <= 2LL * d.out_h && (long long)d.h * d.w * 3 < 0xffffffffLL &&
+                   cols_pre.back() + (long long)((d.out_w + RS_COLS - 1) / RS_COLS) * ((d.out_h + RS_ROWS - 1) / RS_ROWS) < 0x7fffffffLL) {
+            cols.push_back(dv);   // both f32 ratios <= 2 (correctly rounded division is monotone): windows of at most 2 x 2
+            cols_pre.push_back(cols_pre.back() + ((d.out_w + RS_COLS - 1) / RS_COLS) * ((d.out_h + RS_ROWS - 1) / RS_ROWS));
         } else if (d.out_w % 4 == 0 && ((uintptr_t)d.d_out % 16 == 0)) {
             rs.push_back(dv);
             rs_pre.push_back(rs_pre.back() + (int)(px / 4));
@@ -254,6 +350,13 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
         const int total = ident_pre.back();
         RT_LAUNCH_BEGIN(ctx, "det_pre_identity_kernel");
         det_pre_identity_kernel<<<(total + 7) / 8, 256, 0, ctx->stream>>>(dv, dp, (int)ident.size(), total, np);
+        RT_LAUNCH_CHECK(ctx);
+    }
+    if (!cols.empty()) {
+        const DetPreDev* dv; const int* dp;
+        RT_TRY(upload_with_prefix(ctx, ctx->d_stage_cols, cols, cols_pre, &dv, &dp));
+        RT_LAUNCH_BEGIN(ctx, "det_pre_resize_cols_kernel");
+        det_pre_resize_cols_kernel<<<cols_pre.back(), RS_COLS, 0, ctx->stream>>>(dv, dp, (int)cols.size(), np);
         RT_LAUNCH_CHECK(ctx);
     }
     if (!rs.empty()) {

@@ -71,12 +71,16 @@ def test_ctc_nan_is_error(ctx, synth_dict):
     assert e.value.status == 5  # ERR_NAN_LOGITS (reference: argmax().unwrap() panics, rec_processor.rs:198)
 
 
-# identity, both axes up, and every mix of an axis rounded up / down to the multiple of 32 (windows of 1-2 pixels)
+# identity, both axes up, and every mix of an axis rounded up / down to the multiple of 32 (windows of 1-2 pixels): the
+# column-per-thread kernel of det_preprocess.cu, and the generic thumbnail_pixel kernel forced through the environment switch
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("hw", [(960, 960), (736, 1280), (640, 480), (480, 640), (100, 333), (1000, 740), (1010, 745), (745, 1010), (750, 1500),
                                 (1111, 1999), (737, 737), (1487, 751), (300, 1400)])
-def test_det_preprocess_parity(ctx, hw):
+def test_det_preprocess_parity(ctx, hw, generic, monkeypatch):
     import torch
     from oracle import oracle as O
+    if generic:
+        monkeypatch.setenv("RETTO_B200_DETPRE_GENERIC", "1")
     h, w = hw
     rng = np.random.default_rng(h * 7 + w)
     img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
