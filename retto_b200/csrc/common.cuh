@@ -173,7 +173,7 @@ struct retto_b200_ctx {
 
     // descriptor staging: device side, and pinned host slots for rt_upload (a cudaMemcpyAsync from pageable memory
     // larger than 64 KB waits for the stream to drain, which would serialise the host against the GPU)
-    DevBuf d_stage, d_stage2, d_stage3, d_stage_cols;
+    DevBuf d_stage, d_stage2, d_stage3, d_stage_cols, d_stage_tcols;
     struct StageSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool busy = false; };
     std::vector<StageSlot> stage_slots;
     bool uploads_by_sm = false;   // descriptor uploads through stage_pull_kernel instead of the H2D copy engine (capi.cu)

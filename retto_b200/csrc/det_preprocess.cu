@@ -227,6 +227,55 @@ struct ResizeDev {
     float xr, yr;
     int pxt;
 };
+// Down-scaling with both ratios in [1, 3] (resize_both's reduction of a > max_side_len page: ratio <= 4096 / 2000): every
+// window is a BLOCK of 1-3 x 1-3 pixels, so imageops::thumbnail is its branch (i) everywhere — the integer mean
+// (s + n/2) / n, the division as a multiply-shift (exact for s * n < 2^20).  Same layout as det_pre_resize_cols_kernel:
+// one block = 128 output columns x 64 rows, one thread = one output column, the row windows in shared memory.
+struct TcRow { unsigned o0; int ny; };
+__global__ void __launch_bounds__(RS_COLS) thumbnail_cols_kernel(const ResizeDev* __restrict__ jobs, const int* __restrict__ block_prefix, int n_jobs) {
+    __shared__ TcRow s_row[RS_ROWS];
+    __shared__ int s_job;
+    if (threadIdx.x == 0) s_job = rt_find_segment(block_prefix, n_jobs, (int)blockIdx.x);
+    __syncthreads();
+    const int p = s_job;
+    const ResizeDev jb = jobs[p];
+    const int nbx = (jb.ow + RS_COLS - 1) / RS_COLS;
+    const int lb = (int)blockIdx.x - block_prefix[p];
+    const int by = lb / nbx, bx = lb - by * nbx;
+    const int y0 = by * RS_ROWS, rows = min(RS_ROWS, jb.oh - y0);
+    const unsigned W = (unsigned)jb.w, H = (unsigned)jb.h;
+    if ((int)threadIdx.x < rows) {
+        const ThumbAxis ay = thumb_axis(y0 + (int)threadIdx.x, jb.yr, H);
+        s_row[threadIdx.x] = TcRow{ay.lo * W * 3u, (int)(ay.hi - ay.lo)};
+    }
+    __syncthreads();
+    const int x = bx * RS_COLS + (int)threadIdx.x;
+    if (x >= jb.ow) return;
+    const ThumbAxis ax = thumb_axis(x, jb.xr, W);
+    const unsigned nx = ax.hi - ax.lo;
+    const unsigned char* __restrict__ sa = jb.src + 3u * ax.lo;
+    const unsigned M1 = ((1u << 20) + nx - 1) / nx, M2 = ((1u << 20) + 2 * nx - 1) / (2 * nx), M3 = ((1u << 20) + 3 * nx - 1) / (3 * nx);
+    const unsigned stride = W * 3u;
+    unsigned char* dst = jb.dst + ((size_t)y0 * jb.ow + x) * 3;
+    for (int yy = 0; yy < rows; ++yy, dst += (size_t)jb.ow * 3) {
+        const TcRow r = s_row[yy];
+        const unsigned char* q = sa + r.o0;
+        unsigned s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j < r.ny) {   // block-uniform
+#pragma unroll
+                for (unsigned i = 0; i < 3; ++i)
+                    if (i < nx) { s0 += __ldg(q + 3 * i); s1 += __ldg(q + 3 * i + 1); s2 += __ldg(q + 3 * i + 2); }
+            }
+            q += stride;
+        }
+        const unsigned n = nx * (unsigned)r.ny, h2 = n >> 1, M = r.ny == 1 ? M1 : (r.ny == 2 ? M2 : M3);
+        dst[0] = (unsigned char)(((s0 + h2) * M) >> 20);
+        dst[1] = (unsigned char)(((s1 + h2) * M) >> 20);
+        dst[2] = (unsigned char)(((s2 + h2) * M) >> 20);
+    }
+}
 __global__ void __launch_bounds__(256) thumbnail_kernel(const ResizeDev* __restrict__ jobs, const int* __restrict__ unit_prefix, int n_jobs,
                                                          int total_units) {
     __shared__ int s_first;
@@ -373,8 +422,9 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
 extern "C" retto_b200_status retto_b200_thumbnail(retto_b200_ctx* ctx, const retto_b200_resize_desc* h_descs, int32_t n) {
     if (!ctx || (!h_descs && n > 0) || n < 0) return RETTO_B200_ERR_INVALID_ARG;
     if (n == 0) return RETTO_B200_OK;
-    std::vector<ResizeDev> jobs;
-    std::vector<int> pre{0};
+    std::vector<ResizeDev> jobs, cjobs;
+    std::vector<int> pre{0}, cpre{0};
+    const bool generic_only = getenv("RETTO_B200_DETPRE_GENERIC") != nullptr;
     for (int i = 0; i < n; ++i) {
         const retto_b200_resize_desc& d = h_descs[i];
         if (!d.d_src || !d.d_dst || d.h <= 0 || d.w <= 0 || d.out_h <= 0 || d.out_w <= 0) {
@@ -382,14 +432,30 @@ extern "C" retto_b200_status retto_b200_thumbnail(retto_b200_ctx* ctx, const ret
             return RETTO_B200_ERR_INVALID_ARG;
         }
         const int pxt = (d.out_w % 4 == 0) ? 4 : 1;
-        jobs.push_back(ResizeDev{d.d_src, d.h, d.w, d.d_dst, d.out_h, d.out_w, (float)d.w / (float)d.out_w, (float)d.h / (float)d.out_h, pxt});
-        pre.push_back(pre.back() + d.out_h * d.out_w / pxt);
+        const ResizeDev jd{d.d_src, d.h, d.w, d.d_dst, d.out_h, d.out_w, (float)d.w / (float)d.out_w, (float)d.h / (float)d.out_h, pxt};
+        const long long nblk = (long long)((d.out_w + RS_COLS - 1) / RS_COLS) * ((d.out_h + RS_ROWS - 1) / RS_ROWS);
+        if (!generic_only && d.w >= d.out_w && d.h >= d.out_h && d.w <= 3LL * d.out_w && d.h <= 3LL * d.out_h && (long long)d.h * d.w * 3 < 0xffffffffLL &&
+            cpre.back() + nblk < 0x7fffffffLL) {
+            cjobs.push_back(jd);   // both ratios in [1, 3]: block windows of at most 3 x 3
+            cpre.push_back(cpre.back() + (int)nblk);
+        } else {
+            jobs.push_back(jd);
+            pre.push_back(pre.back() + d.out_h * d.out_w / pxt);
+        }
     }
+    if (!cjobs.empty()) {
+        const ResizeDev* dv; const int* dp;
+        RT_TRY(upload_with_prefix(ctx, ctx->d_stage_tcols, cjobs, cpre, &dv, &dp));
+        RT_LAUNCH_BEGIN(ctx, "thumbnail_cols_kernel");
+        thumbnail_cols_kernel<<<cpre.back(), RS_COLS, 0, ctx->stream>>>(dv, dp, (int)cjobs.size());
+        RT_LAUNCH_CHECK(ctx);
+    }
+    if (jobs.empty()) return RETTO_B200_OK;
     const ResizeDev* dv; const int* dp;
     RT_TRY(upload_with_prefix(ctx, ctx->d_stage3, jobs, pre, &dv, &dp));
     const int total = pre.back();
     RT_LAUNCH_BEGIN(ctx, "thumbnail_kernel");
-    thumbnail_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dv, dp, n, total);
+    thumbnail_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dv, dp, (int)jobs.size(), total);
     RT_LAUNCH_CHECK(ctx);
     return RETTO_B200_OK;
 }

@@ -107,13 +107,16 @@ def test_det_preprocess_batch_mixed(ctx):
         assert np.array_equal(o.cpu().numpy().view(np.uint32), O.det_preprocess(i).view(np.uint32))
 
 
+@pytest.mark.parametrize("generic", [False, True])   # thumbnail_cols_kernel (ratios in [1, 3]) / the generic kernel for every case
 @pytest.mark.parametrize("case", [((200, 300), (200, 300)), ((400, 600), (200, 300)), ((2896, 4096), (1408, 1984)),
                                   ((480, 640), (736, 992)), ((37, 211), (48, 274)), ((61, 150), (48, 118)), ((20, 20), (32, 32)),
                                   ((3000, 2000), (1984, 1312)), ((900, 2500), (704, 1984)), ((2001, 2001), (1984, 1984)), ((96, 96), (32, 32)),
                                   ((100, 97), (32, 32))])
-def test_thumbnail_parity(ctx, case):
+def test_thumbnail_parity(ctx, case, generic, monkeypatch):
     import torch
     from oracle import oracle as O
+    if generic:
+        monkeypatch.setenv("RETTO_B200_DETPRE_GENERIC", "1")
     (h, w), (nh, nw) = case
     rng = np.random.default_rng(h + 3 * w + nh)
     img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
