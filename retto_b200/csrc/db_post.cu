@@ -789,48 +789,120 @@ __global__ void trace_copy_kernel(int n_pages, const PageCounters* __restrict__ 
     trace[(size_t)page * max_comps + i] = t;
 }
 
-__global__ void __launch_bounds__(32) page_sort_kernel(int n_pages, PageCounters* __restrict__ counters, BoxCand* __restrict__ cand, int max_comps) {
-    const int page = blockIdx.x;
-    if (threadIdx.x != 0 || page >= n_pages) return;
-    if (counters[page].status == RETTO_B200_ERR_CAPACITY) { counters[page].n_boxes = 0; return; }
+// One warp per page.  The candidates are compacted by ballot into shared memory as (discovery key, centre x, centre y, index)
+// tuples, lane 0 runs the two stable insertion sorts on those 16-byte tuples (the reference's comparator is not a strict weak
+// order, so it is the ALGORITHM that has to be reproduced, not just an ordering), and the result is a permutation that
+// pack_boxes_kernel reads through — no 140-byte BoxCand records are moved in global memory (0.033 -> see DESIGN.md).
+#define PS_CAP 1024
+__global__ void __launch_bounds__(32) page_sort_kernel(int n_pages, PageCounters* __restrict__ counters, BoxCand* __restrict__ cand, int max_comps,
+                                                       int* __restrict__ order) {
+    __shared__ int s_key[PS_CAP], s_idx[PS_CAP];
+    __shared__ float s_cx[PS_CAP], s_cy[PS_CAP];
+    const int page = blockIdx.x, lane = threadIdx.x;
+    if (page >= n_pages) return;
+    if (counters[page].status == RETTO_B200_ERR_CAPACITY) { if (lane == 0) counters[page].n_boxes = 0; return; }
     const int n = counters[page].n_roots + counters[page].n_holes;
     BoxCand* c = cand + (size_t)page * max_comps;
+    int* ord = order + (size_t)page * max_comps;
     int m = 0;
-    for (int i = 0; i < n; ++i)
-        if (c[i].valid) { if (m != i) c[m] = c[i]; ++m; }
-    // contours come in find_contours discovery order
-    for (int i = 1; i < m; ++i) {
-        const BoxCand v = c[i];
-        int j = i;
-        while (j > 0 && v.key < c[j - 1].key) { c[j] = c[j - 1]; --j; }
-        c[j] = v;
+    bool fits = true;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool v = i < n && c[i].valid;
+        const unsigned bal = __ballot_sync(RT_FULL, v);
+        const int pos = m + __popc(bal & ((1u << lane) - 1u));
+        if (v && pos < PS_CAP) {
+            s_idx[pos] = i; s_key[pos] = c[i].key;
+            s_cx[pos] = __fdiv_rn(__fadd_rn(c[i].xy[0], c[i].xy[4]), 2.0f);
+            s_cy[pos] = __fdiv_rn(__fadd_rn(c[i].xy[1], c[i].xy[5]), 2.0f);
+        }
+        m += __popc(bal);
     }
-    // stable insertion sort == Rust's sort_by for n <= 20, and for any n when the comparator is consistent
-    for (int i = 1; i < m; ++i) {
-        const BoxCand v = c[i];
-        int j = i;
-        while (j > 0 && box_less(v, c[j - 1])) { c[j] = c[j - 1]; --j; }
-        c[j] = v;
+    if (m > PS_CAP) fits = false;
+    __syncwarp();
+    if (!fits) {   // more valid boxes than the shared-memory table holds: the record-moving path (one thread)
+        if (lane == 0) {
+            int mm = 0;
+            for (int i = 0; i < n; ++i)
+                if (c[i].valid) { if (mm != i) c[mm] = c[i]; ++mm; }
+            for (int i = 1; i < mm; ++i) {
+                const BoxCand v = c[i];
+                int j = i;
+                while (j > 0 && v.key < c[j - 1].key) { c[j] = c[j - 1]; --j; }
+                c[j] = v;
+            }
+            for (int i = 1; i < mm; ++i) {
+                const BoxCand v = c[i];
+                int j = i;
+                while (j > 0 && box_less(v, c[j - 1])) { c[j] = c[j - 1]; --j; }
+                c[j] = v;
+            }
+            for (int i = 0; i < mm; ++i) ord[i] = i;
+            counters[page].n_boxes = mm;
+        }
+        return;
     }
-    counters[page].n_boxes = m;
+    if (lane == 0) {
+        // contours come in find_contours discovery order
+        for (int i = 1; i < m; ++i) {
+            const int k = s_key[i], id = s_idx[i];
+            const float x = s_cx[i], y = s_cy[i];
+            int j = i;
+            while (j > 0 && k < s_key[j - 1]) { s_key[j] = s_key[j - 1]; s_idx[j] = s_idx[j - 1]; s_cx[j] = s_cx[j - 1]; s_cy[j] = s_cy[j - 1]; --j; }
+            s_key[j] = k; s_idx[j] = id; s_cx[j] = x; s_cy[j] = y;
+        }
+        // stable insertion sort == Rust's sort_by for n <= 20, and for any n when the comparator is consistent
+        for (int i = 1; i < m; ++i) {
+            const int id = s_idx[i];
+            const float x = s_cx[i], y = s_cy[i];
+            int j = i;
+            while (j > 0 && (fabsf(__fsub_rn(y, s_cy[j - 1])) < 10.0f ? x < s_cx[j - 1] : y < s_cy[j - 1])) {
+                s_idx[j] = s_idx[j - 1]; s_cx[j] = s_cx[j - 1]; s_cy[j] = s_cy[j - 1]; --j;
+            }
+            s_idx[j] = id; s_cx[j] = x; s_cy[j] = y;
+        }
+        counters[page].n_boxes = m;
+    }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) ord[i] = s_idx[i];
 }
 
 // ---- J: dense packing ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_offsets_kernel(int n_pages, const PageCounters* __restrict__ counters, int* __restrict__ offsets) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int run = 0;
-        for (int p = 0; p < n_pages; ++p) { offsets[p] = run; run += counters[p].n_boxes; }
-        offsets[n_pages] = run;
+    // exclusive prefix of the per-page box counts: one block, 256 pages per trip (warp scans + a scan of the warp totals)
+    __shared__ int s_w[8];
+    __shared__ int s_carry;
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_pages; base += 256) {
+        const int p = base + (int)threadIdx.x;
+        const int v = p < n_pages ? counters[p].n_boxes : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(RT_FULL, x, o); if (lane >= o) x += t; }
+        if (lane == 31) s_w[w] = x;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int t = s_w[k]; if (k < w) before += t; total += t; }
+        const int carry = s_carry;
+        if (p < n_pages) offsets[p] = carry + before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) offsets[n_pages] = s_carry;
 }
 __global__ void __launch_bounds__(128) pack_boxes_kernel(int n_pages, const PageCounters* __restrict__ counters, const int* __restrict__ offsets,
                                                           const BoxCand* __restrict__ cand, int max_comps, retto_b200_box* __restrict__ dense,
-                                                          int cap) {
+                                                          int cap, const int* __restrict__ order) {
     const int page = blockIdx.x;
     const int n = counters[page].n_boxes, base = offsets[page];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (base + i >= cap) break;
-        const BoxCand b = cand[(size_t)page * max_comps + i];
+        const BoxCand b = cand[(size_t)page * max_comps + order[(size_t)page * max_comps + i]];
         retto_b200_box o;
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.xy[k] = b.xy[k];
@@ -1665,14 +1737,15 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
         ctx->dp_trace_valid = true;
     }
     RT_LAUNCH_BEGIN(ctx, "page_sort_kernel");
-    page_sort_kernel<<<n, 32, 0, st>>>(n, d_cnt, d_cand, max_comps);
+    RT_CUDA_OK(ctx, ctx->d_order.ensure(sizeof(int) * (size_t)n * max_comps, st));
+    page_sort_kernel<<<n, 32, 0, st>>>(n, d_cnt, d_cand, max_comps, ctx->d_order.as<int>());
     RT_LAUNCH_CHECK(ctx);
     RT_LAUNCH_BEGIN(ctx, "pack_offsets_kernel");
-    pack_offsets_kernel<<<1, 32, 0, st>>>(n, d_cnt, d_offsets);
+    pack_offsets_kernel<<<1, 256, 0, st>>>(n, d_cnt, d_offsets);
     RT_LAUNCH_CHECK(ctx);
     RT_CUDA_OK(ctx, ctx->d_boxes_out.ensure(sizeof(retto_b200_box) * (size_t)std::max(cap, 1), st));
     RT_LAUNCH_BEGIN(ctx, "pack_boxes_kernel");
-    pack_boxes_kernel<<<n, 128, 0, st>>>(n, d_cnt, d_offsets, d_cand, max_comps, ctx->d_boxes_out.as<retto_b200_box>(), cap);
+    pack_boxes_kernel<<<n, 128, 0, st>>>(n, d_cnt, d_offsets, d_cand, max_comps, ctx->d_boxes_out.as<retto_b200_box>(), cap, ctx->d_order.as<int>());
     RT_LAUNCH_CHECK(ctx);
     // one read-back, one sync: counters, offsets and the boxes (as many as the early counts allow for) into pinned memory
     int* h_off = reinterpret_cast<int*>(reinterpret_cast<char*>(h_cnt) + sizeof(PageCounters) * n);
