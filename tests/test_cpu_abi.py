@@ -119,3 +119,32 @@ def test_cli_surface(tmp_path):
         (tmp_path / n).write_bytes(b"x")
     assert [os.path.relpath(f, tmp_path) for f in cli.find_files(str(tmp_path))] == ["a.png", "b.png", "sub/c.png"]
     assert cli.find_files(str(tmp_path / "a.png")) == [str(tmp_path / "a.png")]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) prints ONE JSON line with the driver's keys; it needs no GPU"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "4",
+                          "--size", "640"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "impl", "cpu_baseline", "e2e"]:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "pages/s" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bind_host_to_gpu_is_harmless_without_nvml():
+    from retto_b200.shard import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    n = bind_host_to_gpu(0)
+    assert isinstance(n, int) and n >= 0
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
