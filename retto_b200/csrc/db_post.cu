@@ -1546,7 +1546,7 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
     // default: run-table CCL; RETTO_B200_PIXEL_CCL=1 (tests) or a page with too many runs: the pixel-plane passes
     ctx->dp_run_path = getenv("RETTO_B200_PIXEL_CCL") == nullptr;
     if (ctx->dp_run_path) {
-        static bool attr_set = false;
+        bool& attr_set = ctx->ccl_runs_attr_set;   // per context = per device: a process may drive several GPUs (retto_b200/cli.py --gpus N)
         const int smem = RUN_CAP * 12 + (RUN_MAX_H + 1) * 4;   // sorted runs (8 B) + parent per run, per-row index
         if (!attr_set) { RT_CUDA_OK(ctx, cudaFuncSetAttribute(ccl_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
         RT_CUDA_OK(ctx, ctx->d_runs.ensure(sizeof(RunRec) * 3 * RUN_CAP * (size_t)n, st));
