@@ -17,14 +17,18 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libretto_oracle.so")
+_SHIM_SO = os.path.join(_HERE, "diag", "libcrmath_shim.so")
 
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "retto_oracle.cpp")
+    shim_src = os.path.join(_HERE, "diag", "crmath_shim.cpp")
     hdr = os.path.join(_HERE, "..", "retto_b200", "csrc", "rt_fmath.h")
-    stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
-    )
+
+    def _stale(so, deps):
+        return (not os.path.exists(so)) or any(os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in deps)
+
+    stale = _stale(_SO, (src,)) or _stale(_SHIM_SO, (shim_src, hdr))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -40,6 +44,8 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.orc_det_postprocess.restype = C.c_int
         _lib.orc_find_contours.restype = C.c_int
+        _lib.orc_set_trig_hooks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_trig_hooked.restype = C.c_int
     return _lib
 
 
@@ -65,9 +71,26 @@ def default_det_cfg(**kw) -> DetCfg:
     return DetCfg(**d)
 
 
+_shim = None
+
+
 def set_libm(mode: int):
-    """0 = host glibc (reference-faithful), 1 = rt_fmath (bit-identical to the CUDA path)."""
-    lib().orc_set_libm(C.c_int(mode))
+    """0 = host glibc: what the reference's f64 trig calls, the ASSERTED mode of every parity test.
+    1 = DIAGNOSTIC: install oracle/diag/libcrmath_shim.so (the CUDA path's correctly-rounded trig) through the
+    oracle's hooks, for second runs that count glibc-vs-CUDA differences; never the asserted mode."""
+    global _shim
+    L = lib()
+    if mode == 0:
+        L.orc_set_trig_hooks(None, None, None)
+        return
+    if _shim is None:
+        _shim = C.CDLL(_SHIM_SO)
+    L.orc_set_trig_hooks(C.cast(_shim.diag_cr_atan2, C.c_void_p), C.cast(_shim.diag_cr_sincos, C.c_void_p),
+                         C.cast(_shim.diag_cr_acos, C.c_void_p))
+
+
+def libm_mode() -> int:
+    return int(lib().orc_trig_hooked())
 
 
 def thumbnail(img: np.ndarray, nh: int, nw: int) -> np.ndarray:

@@ -24,22 +24,25 @@
 #include <string>
 #include <vector>
 
-#include "../retto_b200/csrc/rt_fmath.h"  // deterministic CR trig (see orc_set_libm)
-
 namespace orc {
 
 // ------------------------------------------------------------------------------------------
-// libm selection.  mode 0 = host glibc (what the reference's Rust f64::atan2/sin/cos/acos call on
-// Linux); mode 1 = rt_fmath (correctly-rounded double-double, bit-identical to the CUDA path).
-// tests/test_fmath.py quantifies the difference; tests/test_det_post.py asserts box outputs are
-// identical in both modes on the whole corpus.
-static int g_libm_mode = 0;
-static inline double m_atan2(double y, double x) { return g_libm_mode ? rtm::rt_atan2(y, x) : std::atan2(y, x); }
+// libm.  The restatement calls the host glibc — what the reference's Rust f64::atan2/sin/cos/acos call on
+// Linux — and includes NO product source.  orc_set_trig_hooks lets a test install other implementations for a
+// DIAGNOSTIC second run (oracle/diag/crmath_shim.cpp wraps the CUDA path's correctly-rounded routines); every
+// asserted parity comparison runs with the hooks cleared (tests/conftest.py resets them around each test).
+typedef double (*trig_atan2_fn)(double, double);
+typedef void (*trig_sincos_fn)(double, double*, double*);
+typedef double (*trig_acos_fn)(double);
+static trig_atan2_fn g_hook_atan2 = nullptr;
+static trig_sincos_fn g_hook_sincos = nullptr;
+static trig_acos_fn g_hook_acos = nullptr;
+static inline double m_atan2(double y, double x) { return g_hook_atan2 ? g_hook_atan2(y, x) : std::atan2(y, x); }
 static inline void m_sincos(double a, double* s, double* c) {
-    if (g_libm_mode) rtm::rt_sincos(a, s, c);
+    if (g_hook_sincos) g_hook_sincos(a, s, c);
     else { *s = std::sin(a); *c = std::cos(a); }
 }
-static inline double m_acos(double v) { return g_libm_mode ? rtm::rt_acos(v) : std::acos(v); }
+static inline double m_acos(double v) { return g_hook_acos ? g_hook_acos(v) : std::acos(v); }
 
 static inline float round_half_away_f(float v) { return roundf(v); }      // Rust f32::round
 static inline double round_half_away_d(double v) { return std::round(v); }  // Rust f64::round
@@ -860,7 +863,10 @@ static int argmax_first(const float* v, int n, int* idx) {
 // C ABI for ctypes (tests) — prefix orc_
 extern "C" {
 
-void orc_set_libm(int mode) { orc::g_libm_mode = mode; }
+void orc_set_trig_hooks(orc::trig_atan2_fn a, orc::trig_sincos_fn sc, orc::trig_acos_fn ac) {
+    orc::g_hook_atan2 = a; orc::g_hook_sincos = sc; orc::g_hook_acos = ac;
+}
+int orc_trig_hooked() { return orc::g_hook_atan2 != nullptr; }
 void orc_set_calipers_wrap(int v) { orc::g_calipers_wrap = v; }
 
 void orc_thumbnail(const uint8_t* src, int h, int w, int c, uint8_t* dst, int nh, int nw) { orc::thumbnail(src, h, w, c, dst, nh, nw); }

@@ -50,10 +50,12 @@ def _consistent_maps(seed0, n, h, w, **kw):
     return out
 
 
-def _check_pages(ctx, probs, ori_hw=None, libm=1, allow_inconsistent=False):
+def _check_pages(ctx, probs, ori_hw=None, allow_inconsistent=False, diag=None):
+    """asserted mode: the oracle on glibc trig (tests/conftest.py); `diag` = the libm_diag fixture for a second,
+    counted-only run with the CUDA path's trig hooked into the oracle"""
     import torch
     from oracle import oracle as O
-    O.set_libm(libm)
+    assert O.libm_mode() == 0
     gs = [_t(p) for p in probs]
     torch.cuda.synchronize()
     ori = ori_hw or [p.shape for p in probs]
@@ -72,7 +74,9 @@ def _check_pages(ctx, probs, ori_hw=None, libm=1, allow_inconsistent=False):
         assert boxes.shape == ref.boxes.shape, f"page {i}: {len(boxes)} vs {len(ref.boxes)} boxes"
         assert np.array_equal(boxes, ref.boxes), f"box mismatch page {i}"
         assert np.array_equal(scores.view(np.uint32), ref.scores.view(np.uint32)), f"score mismatch page {i}"
-    O.set_libm(0)
+    if diag is not None:
+        diag("det_post_tests", lambda: [O.det_postprocess(p, ori[i][0], ori[i][1]).boxes for i, p in enumerate(probs)],
+             [out.page(i)[0] for i in range(len(probs))])
     return out
 
 
@@ -91,16 +95,16 @@ def test_empty_and_full(ctx):
 
 
 @pytest.mark.parametrize("seed", range(6))
-def test_planted_rects_256(ctx, seed):
+def test_planted_rects_256(ctx, seed, libm_diag):
     from tools.synth import gen_probmap
     probs = sum([_consistent_maps(100 + seed * 4 + i, 1, 256, 256, k_range=(3, 10), wide_angle=(i % 2 == 1), border_touch_p=0.3) for i in range(4)], [])
-    _check_pages(ctx, probs)
+    _check_pages(ctx, probs, diag=libm_diag)
 
 
-def test_planted_rects_960_batch(ctx):
+def test_planted_rects_960_batch(ctx, libm_diag):
     from tools.synth import gen_probmap
     probs = sum([_consistent_maps(7 + i, 1, 960, 960) for i in range(6)], [])
-    out = _check_pages(ctx, probs)
+    out = _check_pages(ctx, probs, diag=libm_diag)
     assert out.offsets[-1] > 60
 
 
@@ -112,11 +116,12 @@ def test_mixed_sizes_and_scaling(ctx):
     _check_pages(ctx, probs, ori)
 
 
-def test_glibc_vs_rtmath_same_boxes(ctx):
-    """the oracle in reference-faithful libm mode (glibc) gives the same boxes as the CUDA path here"""
+def test_wide_angle_rects_glibc_and_diag(ctx, libm_diag):
+    """wide-angle rectangles (the f64 trig of min_area_rect / Clipper matters most here): asserted against the glibc
+    oracle like every other test; the diagnostic second run counts boxes that change with the CUDA path's trig"""
     from tools.synth import gen_probmap
-    probs = sum([_consistent_maps(900 + i, 1, 512, 512, k_range=(5, 15), wide_angle=True) for i in range(4)], [])
-    _check_pages(ctx, probs, libm=0)
+    probs = sum([_consistent_maps(900 + i, 1, 512, 512, k_range=(5, 15), wide_angle=True) for i in range(8)], [])
+    _check_pages(ctx, probs, diag=libm_diag)
 
 
 def test_noise_speckles(ctx):

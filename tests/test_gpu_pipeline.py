@@ -227,7 +227,6 @@ def test_session_matches_oracle_pipeline(ctx, synth_dict, seed, hw):
     from oracle import oracle as O
     from oracle.pipeline import run_page
     from tools.synth import gen_page, probmap_from_rects
-    O.set_libm(1)
     h, w = hw
     img, rects = gen_page(seed, h, w)
     dh, dw = O.resize_either_plan(h, w)
@@ -239,7 +238,6 @@ def test_session_matches_oracle_pipeline(ctx, synth_dict, seed, hw):
     assert not taps["det"].comparator_inconsistent
     sess = _session(ctx, wk, synth_dict)
     got = sess.run(img)
-    O.set_libm(0)
     assert got.status == 0
     assert len(got.det_result) == len(ref["boxes"]) > 5
     for i in range(len(ref["boxes"])):
@@ -263,7 +261,6 @@ def test_session_batch_of_pages_with_resizes(ctx, synth_dict):
     from oracle import oracle as O
     from oracle.pipeline import run_page
     from tools.synth import gen_page, probmap_from_rects
-    O.set_libm(1)
     specs = [(11, 900, 1400), (12, 2300, 1700), (13, 500, 640), (14, 1280, 1280)]
     imgs, refs, workers = [], [], []
     for seed, h, w in specs:
@@ -295,7 +292,6 @@ def test_session_batch_of_pages_with_resizes(ctx, synth_dict):
 
     sess = _session(ctx, Multi(), synth_dict)
     got = sess.run_pages(imgs)
-    O.set_libm(0)
     for g, r in zip(got, refs):
         assert g.status == 0 and len(g.det_result) == len(r["boxes"]) > 0
         for i in range(len(r["boxes"])):
