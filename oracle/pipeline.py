@@ -15,12 +15,16 @@ def stable_order_desc_ratio(dims):
 
 
 def run_page(img: np.ndarray, worker, dict_text: str, max_side_len=2000, min_side_len=30, det_cfg=None, cls_shape=(3, 48, 192),
-             rec_shape=(3, 48, 320), batch_num=6, cls_thresh=0.9, cls_label=(0, 180), taps=None):
+             rec_shape=(3, 48, 320), batch_num=6, cls_thresh=0.9, cls_label=(0, 180), taps=None, limit_type=0, limit_len=736,
+             cls_batch_num=None, rec_batch_num=None):
+    """limit_type 0 = LimitType::Min, 1 = Max (det_processor.rs:75-93); cls_/rec_batch_num default to batch_num"""
+    cls_batch_num = cls_batch_num or batch_num
+    rec_batch_num = rec_batch_num or batch_num
     chars = O.rec_character(dict_text)
     ori_h, ori_w = img.shape[:2]
     page = O.resize_both(img, max_side_len, min_side_len)                       # session.rs:81-82
     after_h, after_w = page.shape[:2]
-    det_in = O.det_preprocess(page)                                             # det_processor.rs:256-274
+    det_in = O.det_preprocess(page, limit_type, limit_len)                      # det_processor.rs:256-274
     pred = np.ascontiguousarray(worker.det(det_in), dtype=np.float32)           # session.rs:86
     det = O.det_postprocess(pred[0, 0], after_h, after_w, det_cfg)              # det_processor.rs:279-335
     assert det.status >= 0, "reference would panic in det postprocess"
@@ -32,8 +36,8 @@ def run_page(img: np.ndarray, worker, dict_text: str, max_side_len=2000, min_sid
     order = stable_order_desc_ratio(dims)
     cls_res = [None] * len(crops)
     cls_batches = []
-    for b0 in range(0, len(order), batch_num):
-        idxs = order[b0:b0 + batch_num]
+    for b0 in range(0, len(order), cls_batch_num):
+        idxs = order[b0:b0 + cls_batch_num]
         batch = np.stack([O.resize_norm_image(crops[i], cls_shape, None) for i in idxs])
         cls_batches.append(batch)
         logits = np.ascontiguousarray(worker.cls(batch), dtype=np.float32)
@@ -48,8 +52,8 @@ def run_page(img: np.ndarray, worker, dict_text: str, max_side_len=2000, min_sid
     rec_res = [None] * len(crops)
     max_wh_ratio = np.float32(rec_shape[2]) / np.float32(rec_shape[1])
     rec_batches = []
-    for b0 in range(0, len(order), batch_num):
-        idxs = order[b0:b0 + batch_num]
+    for b0 in range(0, len(order), rec_batch_num):
+        idxs = order[b0:b0 + rec_batch_num]
         for i in idxs:
             wh = np.float32(dims[i][1]) / np.float32(dims[i][0])
             if wh > max_wh_ratio:

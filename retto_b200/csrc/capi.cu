@@ -36,9 +36,13 @@ extern "C" retto_b200_status retto_b200_create(int32_t device_id, const retto_b2
     *out = nullptr;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n) return RETTO_B200_ERR_CUDA;
-    if (cudaSetDevice(device_id) != cudaSuccess) return RETTO_B200_ERR_CUDA;
     retto_b200_ctx* c = new retto_b200_ctx();
     c->device = device_id;
+    RtDeviceGuard _dg(c);   // the caller's current device is restored on return
+    if (!_dg.switched) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != device_id) { delete c; return RETTO_B200_ERR_CUDA; }
+    }
     if (cfg) c->cfg = *cfg; else retto_b200_config_default(&c->cfg);
     if (c->cfg.max_components_per_page <= 0) c->cfg.max_components_per_page = 16384;
     if (c->cfg.max_det_side <= 0) c->cfg.max_det_side = 4096;
@@ -51,7 +55,7 @@ extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
     if (!c) return;
     for (retto_b200_ctx* l : c->lanes) retto_b200_destroy(l);
     c->lanes.clear();
-    cudaSetDevice(c->device);
+    RtDeviceGuard _dg(c);
     cudaStreamSynchronize(c->stream);
     cudaStream_t s = c->stream;
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -78,41 +82,47 @@ extern "C" uint64_t retto_b200_launch_count(const retto_b200_ctx* c) {
 }
 
 extern "C" retto_b200_status retto_b200_sync(retto_b200_ctx* c) {
+    RtDeviceGuard _dg(c);
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return RETTO_B200_OK;
 }
 
 extern "C" retto_b200_status retto_b200_dev_alloc(retto_b200_ctx* c, size_t bytes, void** d_out) {
+    RtDeviceGuard _dg(c);
     if (!c || !d_out) return RETTO_B200_ERR_INVALID_ARG;
-    cudaSetDevice(c->device);
     cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 1);
     if (e != cudaSuccess) { c->set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return RETTO_B200_ERR_OOM; }
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_dev_free(retto_b200_ctx* c, void* p) {
+    RtDeviceGuard _dg(c);
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     RT_CUDA_OK(c, cudaFree(p));
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_host_alloc(retto_b200_ctx* c, size_t bytes, void** h_out) {
+    RtDeviceGuard _dg(c);
     if (!c || !h_out) return RETTO_B200_ERR_INVALID_ARG;
     cudaError_t e = cudaHostAlloc(h_out, bytes ? bytes : 1, cudaHostAllocDefault);
     if (e != cudaSuccess) { c->set_error(std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return RETTO_B200_ERR_OOM; }
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_host_free(retto_b200_ctx* c, void* p) {
+    RtDeviceGuard _dg(c);
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaFreeHost(p));
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_h2d(retto_b200_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
+    RtDeviceGuard _dg(c);
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_d2h(retto_b200_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+    RtDeviceGuard _dg(c);
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
     return RETTO_B200_OK;
@@ -120,6 +130,7 @@ extern "C" retto_b200_status retto_b200_d2h(retto_b200_ctx* c, void* h_dst, cons
 
 // ---- per-kernel timing taps (bench.py roofline) ---------------------------------------------------------
 extern "C" retto_b200_status retto_b200_enable_kernel_timing(retto_b200_ctx* c, int32_t on) {
+    RtDeviceGuard _dg(c);
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     c->timer_collect();
@@ -127,6 +138,7 @@ extern "C" retto_b200_status retto_b200_enable_kernel_timing(retto_b200_ctx* c, 
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_reset_kernel_times(retto_b200_ctx* c) {
+    RtDeviceGuard _dg(c);
     if (!c) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     c->timer_collect();
@@ -136,6 +148,7 @@ extern "C" retto_b200_status retto_b200_reset_kernel_times(retto_b200_ctx* c) {
 }
 // writes "name\tcount\ttotal_ms\n" lines into buf (NUL terminated); returns ERR_CAPACITY if it does not fit
 extern "C" retto_b200_status retto_b200_kernel_times(retto_b200_ctx* c, char* buf, size_t cap) {
+    RtDeviceGuard _dg(c);
     if (!c || !buf || cap == 0) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     c->timer_collect();

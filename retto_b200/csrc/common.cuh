@@ -95,6 +95,8 @@ struct PageCounters {      // per page, zeroed before each det_postprocess
     int n_holes;             // hole borders (background components not connected to the frame)
     int n_runs;              // run-table CCL: horizontal foreground runs emitted by bitmap_runs2_kernel
     int fallback;            // run-table CCL: more runs than the on-chip table holds -> the batch is redone on the pixel path
+    int nonfinite;           // the probability map holds NaN / +-Inf: box_score_fast takes the exact (whole-bbox, v * m) fold
+    int pad;
 };
 
 struct CompRec {           // per connected component (dense id)
@@ -245,6 +247,22 @@ struct retto_b200_ctx {
     std::vector<uint32_t> r_text_offs;
     std::vector<char> r_text;
     std::vector<float> r_scores;
+};
+
+// Every extern "C" entry that takes a context makes the context's device current for the duration of the call and
+// restores the caller's device on return: a host thread may own contexts on several GPUs (retto_b200_run_pages_multi,
+// `--gpus N`), and torch or the host application may change the current device between calls.
+struct RtDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit RtDeviceGuard(const retto_b200_ctx* c) {
+        if (!c) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+    }
+    ~RtDeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+    RtDeviceGuard(const RtDeviceGuard&) = delete;
+    RtDeviceGuard& operator=(const RtDeviceGuard&) = delete;
 };
 
 #define RT_LAUNCH_BEGIN(ctx, name)                                                                \

@@ -521,6 +521,7 @@ retto_b200_status rt_crop_adopt_device(retto_b200_ctx* ctx, const retto_b200_box
 
 extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const retto_b200_crop_job* h_jobs, int32_t n,
                                                    retto_b200_crop_info* h_infos) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || n < 0 || (n > 0 && (!h_jobs || !h_infos))) return RETTO_B200_ERR_INVALID_ARG;
     RT_TRY(rt_crop_launch(ctx, h_jobs, n, h_infos));
     return rt_crop_finish(ctx, h_infos, true);
@@ -534,6 +535,7 @@ __global__ void crop_flip_copy_kernel(const unsigned char* __restrict__ src, uns
 }
 
 extern "C" retto_b200_status retto_b200_crop_fetch(retto_b200_ctx* ctx, int32_t i, uint8_t* h_out) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || i < 0 || i >= (int)ctx->crops.size() || !h_out) return RETTO_B200_ERR_INVALID_ARG;
     const retto_b200_ctx::CropHost& c = ctx->crops[i];
     const int n_px = c.w * c.h;

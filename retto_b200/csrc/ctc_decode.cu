@@ -225,6 +225,7 @@ static retto_b200_status ctc_run_argmax(retto_b200_ctx* ctx, const std::vector<C
 
 extern "C" retto_b200_status retto_b200_ctc_argmax(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs,
                                                    int32_t num_classes, int32_t* d_idx, float* d_prob) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx) return RETTO_B200_ERR_INVALID_ARG;
     std::vector<CtcTensor> tensors;
     std::vector<int> prefix, line_t;
@@ -341,12 +342,14 @@ retto_b200_status rt_ctc_end(retto_b200_ctx* ctx, uint32_t* h_text_offsets, char
 extern "C" retto_b200_status retto_b200_ctc_decode(retto_b200_ctx* ctx, const retto_b200_logits_desc* h_descs, int32_t n_descs,
                                                    int32_t num_classes, uint32_t* h_text_offsets, char* h_text, size_t text_capacity,
                                                    float* h_scores, int32_t* h_tokens, int32_t* h_token_counts, int32_t max_t_out) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || !h_text_offsets) return RETTO_B200_ERR_INVALID_ARG;
     RT_TRY(rt_ctc_begin(ctx, h_descs, n_descs, num_classes, h_tokens != nullptr, max_t_out));
     return rt_ctc_end(ctx, h_text_offsets, h_text, text_capacity, h_scores, h_tokens, h_token_counts, max_t_out);
 }
 
 extern "C" retto_b200_status retto_b200_dict_load(retto_b200_ctx* ctx, const char* utf8, size_t len) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || (!utf8 && len)) return RETTO_B200_ERR_INVALID_ARG;
     // RecCharacter::new (rec_processor.rs:29-46): content.lines().map(str::trim) ; insert(0,"blank") ; push(" ")
     std::vector<std::string> d;

@@ -325,6 +325,43 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
     return true;
 }
 
+// box_score_fast on a map that holds NaN / +-Inf.  The reference's fold is sum += v * (m as f32) over every pixel of the
+// bounding box in raster order, then sum / count: a NaN anywhere in the box, or an Inf outside the polygon (Inf * 0),
+// makes the sum NaN; Infs inside the polygon make it +-Inf (NaN when both signs occur); finite partial sums cannot
+// overflow (|v| <= FLT_MAX is excluded by the flag, ordinary maps hold [0, 1]).  Returns `finite_score` when the box
+// holds no non-finite value.  Rare path: lanes take rows, each scans its row serially.
+static __device__ __noinline__ float warp_box_score_nonfinite(const float* __restrict__ pred, int h, int w, const int qx[4], const int qy[4], float finite_score) {
+    const int lane = threadIdx.x & 31;
+    int x_min = min(min(qx[0], qx[1]), min(qx[2], qx[3])), x_max = max(max(qx[0], qx[1]), max(qx[2], qx[3]));
+    int y_min = min(min(qy[0], qy[1]), min(qy[2], qy[3])), y_max = max(max(qy[0], qy[1]), max(qy[2], qy[3]));
+    x_min = min(max(x_min, 0), w - 1); x_max = min(max(x_max, 0), w - 1);
+    y_min = min(max(y_min, 0), h - 1); y_max = min(max(y_max, 0), h - 1);
+    const int bw = x_max - x_min + 1, bh = y_max - y_min + 1;
+    int px[4], py[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { px[i] = qx[i] - x_min; py[i] = qy[i] - y_min; }
+    unsigned f = 0;   // bit 0: NaN result, bit 1: +Inf inside the polygon, bit 2: -Inf inside the polygon
+    for (int y = lane; y < bh; y += 32) {
+        RowCover rc;
+        rc.n = 0;
+        polygon_row_cover(px, py, bw, bh, y, rc);
+        const float* row = pred + (size_t)(y + y_min) * w + x_min;
+        for (int x = 0; x < bw; ++x) {
+            const float v = __ldg(row + x);
+            if (fabsf(v) <= 3.402823466e+38f) continue;
+            bool m = false;
+            for (int k = 0; k < rc.n; ++k) m |= (x >= rc.a[k] && x <= rc.b[k]);
+            if (v != v || !m) f |= 1u;
+            else f |= v > 0.0f ? 2u : 4u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, o);
+    if (f == 0) return finite_score;
+    if ((f & 1u) || (f & 6u) == 6u) return CUDART_NAN_F;
+    return (f & 2u) ? CUDART_INF_F : -CUDART_INF_F;
+}
+
 // ---- unclip (det_processor.rs:223-252) ---------------------------------------------------------------
 // geo 0.30 unsigned_area (f32 shoelace, shifted by the first vertex) and Euclidean length (f32 sum of
 // hypotf, restated as (float)sqrt((double)dx*dx + (double)dy*dy)); distance = area * ratio / perimeter.

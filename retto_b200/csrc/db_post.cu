@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
                                                            int n_pages, int total_tiles, float thr, int dilate,
                                                            unsigned char* __restrict__ bitmap, int* __restrict__ labels,
                                                            unsigned char* __restrict__ tileflags, int* __restrict__ cid_at,
-                                                           int* __restrict__ key_at) {
+                                                           int* __restrict__ key_at, PageCounters* __restrict__ counters) {
     DetPostPage pg; int page, s, rb, tile;
     if (!tile_lookup(pages, tile_prefix, n_pages, total_tiles, 4, pg, page, s, rb, tile)) return;
     const int lane = threadIdx.x & 31;
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
     const int x0 = s * TILE_W, x = x0 + lane * 4;
     const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
     unsigned char* bm = bitmap + pg.px_base;
+    float nf = 0.0f;   // v * 0 accumulates to NaN iff some loaded probability is NaN / +-Inf (see PageCounters::nonfinite)
     int* lab = labels + pg.px_base;
     int* ymax_at = cid_at + pg.px_base;   // root-indexed slots, initialised at every run start (a root is always one)
     int* keyp = key_at + pg.px_base;
@@ -95,11 +96,12 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
             if (x < W) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(row + x));
                 t = (v.x > thr ? 1u : 0u) | (v.y > thr ? 2u : 0u) | (v.z > thr ? 4u : 0u) | (v.w > thr ? 8u : 0u);
+                nf = __fmaf_rn(v.x, 0.0f, nf); nf = __fmaf_rn(v.y, 0.0f, nf); nf = __fmaf_rn(v.z, 0.0f, nf); nf = __fmaf_rn(v.w, 0.0f, nf);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (x + j < W && __ldg(row + x + j) > thr) t |= 1u << j;
+                if (x + j < W) { const float v = __ldg(row + x + j); nf = __fmaf_rn(v, 0.0f, nf); if (v > thr) t |= 1u << j; }
         }
         unsigned left = __shfl_up_sync(RT_FULL, (t >> 3) & 1u, 1);
         if (lane == 0) left = (x0 > 0 && __ldg(row + x0 - 1) > thr) ? 1u : 0u;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
     }
     const unsigned anyw = __ballot_sync(RT_FULL, any != 0);
     if (lane == 0) tileflags[tile] = anyw ? 1 : 0;
+    if (__any_sync(RT_FULL, nf != nf) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
 }
 
 // neighbourhood bits of a 4-pixel group for rows y (c) and y-1 (u): bit k = pixel x-1+k, k = 0..5
@@ -545,6 +548,21 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
             if (lane == 0) { atomicMax(&counters[page].status, RETTO_B200_ERR_DEGENERATE_QUAD); out->status = -1; }
             return;
         }
+        if (lane == 0) { out->score = score; out->status = (score < gp.box_thresh) ? 2 : ST_NEED_UNCLIP; }
+        return;
+    }
+    if (PHASE == 4) {
+        // Pages whose map holds NaN / +-Inf (PageCounters::nonfinite, set by the bitmap kernel; the host launches this phase
+        // only when its early counter read-back shows such a page): the reference folds v * m over the WHOLE bounding box
+        // (det_processor.rs:212-219), so a non-finite value outside the polygon (m = 0) still poisons the sum — redo the
+        // scored boxes of these pages with the exact classification.  NaN is not < box_thresh: the box is kept, as in the reference.
+        if (!counters[page].nonfinite || out->st0 != ST_NEED_SCORE || out->status == -1) return;
+        int qx[4], qy[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qx[i] = out->rect1[2 * i]; qy[i] = out->rect1[2 * i + 1]; }
+        const float prev = out->score;
+        __syncwarp();
+        const float score = warp_box_score_nonfinite(pg.prob, pg.h, pg.w, qx, qy, prev);
         if (lane == 0) { out->score = score; out->status = (score < gp.box_thresh) ? 2 : ST_NEED_UNCLIP; }
         return;
     }
@@ -947,6 +965,7 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
     unsigned char* bm = bitmap + pg.px_base;
     const float* __restrict__ prob = pg.prob;
     RunRec* prun = runs + (size_t)page * 3 * RUN_CAP;
+    float nf = 0.0f;   // v * 0 accumulates to NaN iff some loaded probability is NaN / +-Inf (see PageCounters::nonfinite)
 
     // raw (float4, left-edge scalar) of one row; the threshold / shuffles are applied when the row is consumed, so the
     // loads of row y+1 are in flight while row y is processed
@@ -962,6 +981,7 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
             if (x + 2 < W) r.v.z = __ldg(row + x + 2);
             if (x + 3 < W) r.v.w = __ldg(row + x + 3);
         }
+        nf = __fmaf_rn(r.v.x, 0.0f, nf); nf = __fmaf_rn(r.v.y, 0.0f, nf); nf = __fmaf_rn(r.v.z, 0.0f, nf); nf = __fmaf_rn(r.v.w, 0.0f, nf);
         if (lane == 0 && x0 > 0) r.l = __ldg(row + x0 - 1);
         return r;
     };
@@ -1031,6 +1051,7 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
         for (int k = 0; k < cnt; ++k)
             if (base + k < RUN_CAP) prun[base + k] = RunRec{y * W + starts[k], ends[k]};
     }
+    if (__any_sync(RT_FULL, nf != nf) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
 }
 
 // A'' (default): the same stage with one warp per 256-px strip and the row held as EIGHT warp-uniform 32-bit words —
@@ -1075,6 +1096,7 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
     };
     const int nv = W - x0;                  // pixels of the strip inside the page (only the last strip of a row is partial)
     const bool partial = nv < SW;
+    float nf = 0.0f;   // v * 0 accumulates to NaN iff some loaded probability is NaN / +-Inf (see PageCounters::nonfinite)
     struct Raw { float v[NW]; float l; };
     auto fetch = [&](int y) -> Raw {
         Raw r;
@@ -1085,10 +1107,10 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
         const float* row = prob + (size_t)y * W + x0 + lane;
         if (!partial) {   // full strip (all but the last of a page row): unpredicated loads
 #pragma unroll
-            for (int j = 0; j < NW; ++j) r.v[j] = __ldg(row + 32 * j);
+            for (int j = 0; j < NW; ++j) { r.v[j] = __ldg(row + 32 * j); nf = __fmaf_rn(r.v[j], 0.0f, nf); }
         } else {
 #pragma unroll
-            for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) r.v[j] = __ldg(row + 32 * j);
+            for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) { r.v[j] = __ldg(row + 32 * j); nf = __fmaf_rn(r.v[j], 0.0f, nf); }
         }
         if (lane == 0 && x0 > 0) r.l = __ldg(row - 1);
         return r;
@@ -1183,6 +1205,7 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
         }
     }
     if (nbuf) flush();
+    if (__any_sync(RT_FULL, nf != nf) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
 }
 
 // B': one block per page.  Shared memory: sorted runs (key, x1) | parent | per-row index.
@@ -1436,9 +1459,9 @@ static retto_b200_status dp_pixel_ccl(retto_b200_ctx* ctx) {
     const int tgrid = (total_tiles + 3) / 4;
     RT_LAUNCH_BEGIN(ctx, "bitmap_runs_kernel");
     if (R.vec)
-        bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
+        bitmap_runs_kernel<true><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key, d_cnt);
     else
-        bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key);
+        bitmap_runs_kernel<false><<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, ctx->cfg.det_thresh, ctx->cfg.det_dilation_2x2, d_bm, d_lab, d_tf, d_cid, d_key, d_cnt);
     RT_LAUNCH_CHECK(ctx);
     RT_LAUNCH_BEGIN(ctx, "ccl_merge_kernel");
     ccl_merge_kernel<<<tgrid, 128, 0, st>>>(d_pages, d_tile_prefix, n, total_tiles, d_bm, d_lab, d_tf, d_cnt);
@@ -1628,6 +1651,8 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
         max_n = std::max(max_n, nr);
         box_bound += nr + std::min(std::max(h_cnt0[i].n_roots - h_cnt0[i].euler, 0), MAX_HOLES);
     }
+    bool any_nonfinite = false;
+    for (int i = 0; i < n; ++i) any_nonfinite |= h_cnt0[i].nonfinite != 0;
     if (max_n > 0) {
         GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
         dim3 grid((max_n + 3) / 4, n);
@@ -1639,6 +1664,11 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
             box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
             RT_LAUNCH_CHECK(ctx);
+            if (any_nonfinite) {
+                RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<4:score,nonfinite>");
+                box_geometry_kernel<4><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+                RT_LAUNCH_CHECK(ctx);
+            }
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<2:unclip>");
             box_geometry_kernel<2><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
             RT_LAUNCH_CHECK(ctx);
@@ -1654,6 +1684,11 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
             box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
             RT_LAUNCH_CHECK(ctx);
+            if (any_nonfinite) {
+                RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<4:score,nonfinite>");
+                box_geometry_kernel<4><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+                RT_LAUNCH_CHECK(ctx);
+            }
             ctx->timer_stream = ctx->aux_stream;
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<3:unclip||score>");
             box_geometry_kernel<3><<<grid, 128, 0, ctx->aux_stream>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
@@ -1719,6 +1754,11 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
             box_geometry_kernel<1><<<hg, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
             RT_LAUNCH_CHECK(ctx);
+            if (any_nonfinite) {
+                RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
+                box_geometry_kernel<4><<<hg, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
+                RT_LAUNCH_CHECK(ctx);
+            }
             RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel(holes)");
             box_geometry_kernel<2><<<hg, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, ha.flag_pages);
             RT_LAUNCH_CHECK(ctx);
@@ -1815,6 +1855,7 @@ retto_b200_status rt_det_post_end(retto_b200_ctx* ctx, int32_t* h_page_status, i
 extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, const retto_b200_det_post_desc* h_descs, int32_t n,
                                                         int32_t* h_page_status, int32_t* h_box_offsets, retto_b200_box* h_boxes,
                                                         int32_t max_boxes_total) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || n < 0 || (n > 0 && (!h_descs || !h_page_status)) || !h_box_offsets) return RETTO_B200_ERR_INVALID_ARG;
     RT_TRY(rt_det_post_begin(ctx, h_descs, n, max_boxes_total));
     RT_TRY(rt_det_post_mid(ctx));
@@ -1822,6 +1863,7 @@ extern "C" retto_b200_status retto_b200_det_postprocess(retto_b200_ctx* ctx, con
 }
 
 extern "C" retto_b200_status retto_b200_det_post_fetch_bitmap(retto_b200_ctx* ctx, int32_t page, uint8_t* h_bitmap) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !h_bitmap) return RETTO_B200_ERR_INVALID_ARG;
     const DetPostPage& pg = ctx->dp_pages[page];
     RT_CUDA_OK(ctx, cudaMemcpyAsync(h_bitmap, ctx->d_bitmap.as<unsigned char>() + pg.px_base, (size_t)pg.h * pg.w, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1829,6 +1871,7 @@ extern "C" retto_b200_status retto_b200_det_post_fetch_bitmap(retto_b200_ctx* ct
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_det_post_fetch_labels(retto_b200_ctx* ctx, int32_t page, int32_t* h_labels) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !h_labels) return RETTO_B200_ERR_INVALID_ARG;
     const DetPostPage& pg = ctx->dp_pages[page];
     if (!ctx->dp_labels_final[page] && ctx->dp_run_path) {
@@ -1869,6 +1912,7 @@ __global__ void scale_clip_kernel(retto_b200_box* b, int n, double inv_w, double
 }
 extern "C" retto_b200_status retto_b200_scale_and_clip(retto_b200_ctx* ctx, retto_b200_box* h_boxes, int32_t n, double bitmap_w,
                                                        double bitmap_h, double ori_w, double ori_h) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || n < 0 || (n > 0 && !h_boxes)) return RETTO_B200_ERR_INVALID_ARG;
     if (n == 0) return RETTO_B200_OK;
     RT_TRY(rt_upload(ctx, ctx->d_stage3, h_boxes, sizeof(retto_b200_box) * (size_t)n));
@@ -1889,6 +1933,7 @@ extern "C" retto_b200_status retto_b200_det_post_enable_trace(retto_b200_ctx* ct
 extern "C" retto_b200_status retto_b200_det_post_fetch_trace(retto_b200_ctx* ctx, int32_t page, int32_t* n_components, int32_t* n_holes,
                                                              int32_t* h_key, int32_t* h_status, int32_t* h_rect1, float* h_sside1,
                                                              float* h_score, int32_t max_components) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size() || !n_components) return RETTO_B200_ERR_INVALID_ARG;
     const int n = ctx->dp_ncomp[page];
     *n_components = n;
@@ -1917,6 +1962,7 @@ extern "C" const int32_t* retto_b200_debug_extra(retto_b200_ctx* ctx) { return c
 
 // debug tap: raw CompRec table of a page (8 ints per component)
 extern "C" retto_b200_status retto_b200_debug_comps(retto_b200_ctx* ctx, int32_t page, int32_t* out, int32_t max_n) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size()) return RETTO_B200_ERR_INVALID_ARG;
     const int n = std::min(ctx->dp_ncomp[page], max_n);
     RT_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_comps.as<CompRec>() + (size_t)page * ctx->cfg.max_components_per_page, sizeof(CompRec) * n,
@@ -1925,6 +1971,7 @@ extern "C" retto_b200_status retto_b200_debug_comps(retto_b200_ctx* ctx, int32_t
     return RETTO_B200_OK;
 }
 extern "C" retto_b200_status retto_b200_debug_rowtab(retto_b200_ctx* ctx, int32_t page, int32_t* out, int32_t n_rows) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size()) return RETTO_B200_ERR_INVALID_ARG;
     RT_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_rowtab.as<int2>() + (size_t)page * ROWCAP, sizeof(int2) * n_rows, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

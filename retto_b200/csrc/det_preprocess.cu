@@ -361,6 +361,7 @@ static retto_b200_status upload_with_prefix(retto_b200_ctx* ctx, DevBuf& buf, co
 }
 
 extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, const retto_b200_det_pre_desc* h_descs, int32_t n) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || (!h_descs && n > 0) || n < 0) return RETTO_B200_ERR_INVALID_ARG;
     NormParams np;
     np.scale = ctx->cfg.det_scale;
@@ -420,6 +421,7 @@ extern "C" retto_b200_status retto_b200_det_preprocess(retto_b200_ctx* ctx, cons
 }
 
 extern "C" retto_b200_status retto_b200_thumbnail(retto_b200_ctx* ctx, const retto_b200_resize_desc* h_descs, int32_t n) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || (!h_descs && n > 0) || n < 0) return RETTO_B200_ERR_INVALID_ARG;
     if (n == 0) return RETTO_B200_OK;
     std::vector<ResizeDev> jobs, cjobs;

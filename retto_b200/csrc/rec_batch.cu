@@ -446,6 +446,7 @@ retto_b200_status rt_build_batches_launch(retto_b200_ctx* ctx, int32_t kind) {
 
 extern "C" retto_b200_status retto_b200_build_batches(retto_b200_ctx* ctx, int32_t kind, const retto_b200_line_job* h_lines, int32_t n_lines,
                                                       uint64_t total_floats, float** d_base) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || n_lines < 0 || (n_lines > 0 && !h_lines) || !d_base || (kind != 0 && kind != 1)) return RETTO_B200_ERR_INVALID_ARG;
     RT_TRY(rt_build_batches_prepare(ctx, kind, h_lines, n_lines, total_floats, d_base));
     return rt_build_batches_launch(ctx, kind);
@@ -488,6 +489,7 @@ retto_b200_status rt_cls_collect(retto_b200_ctx* ctx, int n, retto_b200_cls_resu
 
 extern "C" retto_b200_status retto_b200_cls_postprocess(retto_b200_ctx* ctx, const float* d_logits, int32_t n, const int32_t* h_crop_index,
                                                         retto_b200_cls_result* h_results) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || n < 0 || (n > 0 && (!d_logits || !h_crop_index || !h_results))) return RETTO_B200_ERR_INVALID_ARG;
     std::vector<const float*> ptrs(n);
     for (int i = 0; i < n; ++i) ptrs[i] = d_logits + 2 * (size_t)i;

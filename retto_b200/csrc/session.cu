@@ -550,6 +550,7 @@ static retto_b200_status run_units(retto_b200_ctx* ctx, const std::vector<Unit>&
 // kernels of the earlier ones.  Device-resident batches are cut into units only to keep two lanes busy.
 extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
                                                   retto_b200_forward_fn forward, void* user, retto_b200_results* out) {
+    RtDeviceGuard _dg(ctx);
     if (!ctx || n_pages < 0 || (n_pages > 0 && !h_pages) || !forward || !out) return RETTO_B200_ERR_INVALID_ARG;
     memset(out, 0, sizeof(*out));
     // tunables (retto_b200_set_pipeline or the environment); defaults measured on B200

@@ -1,0 +1,304 @@
+"""GPU parity on the configurations round 1 left untested ("What's weak" #3): dilation_kernel = None,
+LimitType::Max, non-default thresh / box_thresh / unclip_ratio / min_mini_box_size, cls / rec batch_num 1 and 8,
+non-default cls / rec image widths, NaN / Inf probability maps, and a 64-page batch of mixed page sizes
+(640-4096 px long side) — every one against the CPU oracle (glibc trig), bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(params=["run-table", "pixel-planes"])
+def ccl_path(request, monkeypatch):
+    monkeypatch.delenv("RETTO_B200_PIXEL_CCL", raising=False)
+    if request.param == "pixel-planes":
+        monkeypatch.setenv("RETTO_B200_PIXEL_CCL", "1")
+    return request.param
+
+
+def _ctx_with(**kw):
+    from retto_b200.api import Context, default_config
+    cfg = default_config()
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return Context(0, cfg)
+
+
+def _same_scores(a, b):
+    """f32 bits equal, except that any NaN equals any NaN (x86 and the GPU produce different NaN payloads)"""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and np.array_equal(a[~na].view(np.uint32), b[~nb].view(np.uint32))
+
+
+def _check(c, probs, det_cfg, ori=None, allow_inconsistent=True):
+    import torch
+    from oracle import oracle as O
+    assert O.libm_mode() == 0
+    gs = [_t(p) for p in probs]
+    torch.cuda.synchronize()
+    ori = ori or [p.shape for p in probs]
+    out = c.det_postprocess(gs, ori)
+    n_boxes = 0
+    for i, p in enumerate(probs):
+        ref = O.det_postprocess(p, ori[i][0], ori[i][1], det_cfg, want_bitmap=True)
+        assert ref.status >= 0 and out.page_status[i] == 0
+        assert allow_inconsistent or not ref.comparator_inconsistent
+        assert np.array_equal(c.fetch_bitmap(i, *p.shape), ref.bitmap), f"bitmap mismatch page {i}"
+        boxes, scores = out.page(i)
+        assert boxes.shape == ref.boxes.shape, f"page {i}: {len(boxes)} vs {len(ref.boxes)} boxes"
+        assert np.array_equal(boxes, ref.boxes), f"box mismatch page {i}"
+        assert _same_scores(scores, ref.scores), f"score mismatch page {i}"
+        n_boxes += len(boxes)
+    return out, n_boxes
+
+
+def test_no_dilation(ccl_path):
+    """DetProcessorConfig.dilation_kernel = None (det_processor.rs:290): planted rectangles, speckles (1-px components are
+    legal contours here), thin bars and 1-px gaps that the 2x2 dilation would have closed"""
+    from oracle import oracle as O
+    from tools.synth import gen_probmap
+    c = _ctx_with(det_dilation_2x2=0)
+    try:
+        cfg = O.default_det_cfg(dilate=0)
+        probs = [gen_probmap(300 + i, 384, 512, k_range=(4, 12), wide_angle=(i % 2 == 1), border_touch_p=0.2) for i in range(6)]
+        rng = np.random.default_rng(9)
+        sp = (rng.random((200, 300)) < 0.02).astype(np.float32) * 0.9
+        sp[50:90, 40:200] = 0.8
+        sp[120:121, 20:280] = 0.9          # a 1-px-high bar
+        sp[130:170, 250:251] = 0.9         # a 1-px-wide bar
+        sp[60:80, 100:101] = 0.1           # a 1-px gap inside the rectangle
+        probs.append(sp)
+        _, nb = _check(c, probs, cfg)
+        assert nb > 20
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("prm", [dict(thresh=0.2, box_thresh=0.6, unclip_ratio=2.0, min_mini_box_size=5),
+                                 dict(thresh=0.5, box_thresh=0.3, unclip_ratio=1.2, min_mini_box_size=2)])
+def test_non_default_det_thresholds(ccl_path, prm):
+    from oracle import oracle as O
+    from tools.synth import gen_probmap
+    c = _ctx_with(det_thresh=prm["thresh"], det_box_thresh=prm["box_thresh"], det_unclip_ratio=prm["unclip_ratio"],
+                  det_min_mini_box_size=prm["min_mini_box_size"])
+    try:
+        cfg = O.default_det_cfg(**prm)
+        probs = [gen_probmap(400 + i, 512, 640, k_range=(5, 14), wide_angle=(i % 3 == 2), border_touch_p=0.2) for i in range(6)]
+        small = np.full((96, 128), 0.05, np.float32)
+        small[10:14, 10:60] = 0.9          # 4-px-high line: kept or dropped depending on min_mini_box_size
+        small[30:33, 10:60] = 0.58         # passes box_thresh .3 only
+        small[50:60, 10:100] = 0.45        # foreground at thresh .2 only
+        probs.append(small)
+        _, nb = _check(c, probs, cfg)
+        assert nb > 20
+    finally:
+        c.close()
+
+
+def test_nonfinite_probability_maps(ccl_path):
+    """NaN / +-Inf in the probability map.  The reference does not panic here (its only partial_cmp().unwrap(), det_processor.rs:
+    329-331, sees box centres, which stay finite): NaN > thresh is false, Inf > thresh is true, and box_score_fast folds v * m over
+    the whole bounding box, so a non-finite value anywhere inside it — even outside the polygon — makes the score NaN (kept:
+    NaN < box_thresh is false) or +-Inf.  The CUDA path reproduces exactly that (PageCounters::nonfinite -> exact fold)."""
+    from oracle import oracle as O
+    from retto_b200.api import Context
+    from tools.synth import gen_probmap
+    c = Context(0)
+    try:
+        cfg = O.default_det_cfg()
+        base = [gen_probmap(500 + i, 320, 480, k_range=(4, 9), wide_angle=True) for i in range(4)]
+        maps = []
+        for i, p in enumerate(base):
+            ref = O.det_postprocess(p, *p.shape)
+            assert len(ref.boxes) >= 3
+            q = p.copy()
+            b = ref.boxes[0]
+            cx, cy = int(b[:, 0].mean()), int(b[:, 1].mean())
+            x0, y0 = int(b[:, 0].min()), int(b[:, 1].min())
+            if i == 0:
+                q[cy, cx] = np.nan                 # inside the polygon
+            elif i == 1:
+                q[min(y0 + 3, q.shape[0] - 1), min(x0 + 3, q.shape[1] - 1)] = np.nan    # bounding-box corner: usually outside the rotated polygon
+            elif i == 2:
+                q[cy, cx] = np.inf                 # +Inf inside: foreground, score +Inf
+            else:
+                q[cy, cx] = -np.inf                # -Inf inside: background pixel, score -Inf -> dropped
+                q[2, 2] = np.nan                   # far from every box: no effect at all
+            maps.append(q)
+        clean = base[0]
+        out, _ = _check(c, maps + [clean], cfg)
+        assert np.isnan(out.page(0)[1]).any()
+        assert np.isinf(out.page(2)[1]).any()
+        assert np.isfinite(out.page(4)[1]).all()
+    finally:
+        c.close()
+
+
+class _Worker:
+    """deterministic stand-in forwards used on BOTH sides (see tests/test_gpu_pipeline.py::NpWorker)"""
+
+    def __init__(self, prob):
+        from _workers import NpWorker
+        self._w = NpWorker(prob)
+        self.probmap = prob
+
+    def det(self, x):
+        return self._w.det(x)
+
+    def cls(self, x):
+        n = x.shape[0]
+        out = np.zeros((n, 2), np.float32)
+        half = x.shape[3] // 2
+        for i in range(n):
+            left, right = float(x[i, :, :, :half].sum()), float(x[i, :, :, half:].sum())
+            s = np.float32(0.95 if (int(abs(left) * 7) % 3 == 0) else 0.6)
+            out[i] = (1 - s, s) if left > right else (s, 1 - s)
+        return out
+
+    def rec(self, x):
+        return self._w.rec(x)
+
+
+def _session_case(synth_dict, img, prob, scfg, **orc_kw):
+    from oracle.pipeline import run_page
+    from retto_b200.session import CallableWorker, RettoSession
+    wk = _Worker(prob)
+    ref = run_page(img, wk, synth_dict, **orc_kw)
+    scfg.rec_processor_config.character_source = synth_dict
+    sess = RettoSession(cfg=scfg, worker=CallableWorker(wk.det, wk.cls, wk.rec))
+    try:
+        got = sess.run(img)
+    finally:
+        sess.ctx.close()
+    assert got.status == 0 and len(got.det_result) == len(ref["boxes"]) > 3
+    for i in range(len(ref["boxes"])):
+        assert np.array_equal(got.det_result[i].boxes, ref["boxes"][i]), i
+        assert np.float32(got.det_result[i].score).view(np.uint32) == np.float32(ref["scores"][i]).view(np.uint32)
+        assert got.cls_result[i].label == ref["cls"][i][0] and np.float32(got.cls_result[i].score) == np.float32(ref["cls"][i][1])
+        assert got.rec_result[i].text == ref["rec"][i][0], i
+        a, b = np.float32(got.rec_result[i].score), np.float32(ref["rec"][i][1])
+        assert (np.isnan(a) and np.isnan(b)) or a.view(np.uint32) == b.view(np.uint32)
+    return got
+
+
+def _page_and_prob(seed, h, w, limit_type, limit_len):
+    from oracle import oracle as O
+    from tools.synth import gen_page, probmap_from_rects
+    img, rects = gen_page(seed, h, w, n_lines=(8, 16))
+    page = O.resize_both(img)
+    dh, dw = O.resize_either_plan(page.shape[0], page.shape[1], limit_type, limit_len)
+    sx, sy = dw / w, dh / h
+    prob = probmap_from_rects(seed, [(r[0] * sx, r[1] * sy, r[2] * sx, r[3] * sy, r[4]) for r in rects], dh, dw)
+    return img, prob
+
+
+@pytest.mark.parametrize("hw,limit_len", [((1280, 1280), 960), ((900, 1500), 736), ((600, 500), 960)])
+def test_limit_type_max(synth_dict, hw, limit_len):
+    """LimitType::Max (image_helper.rs:150-174): the long side is capped at limit_side_len, so pages are DOWN-scaled for the det
+    tensor (thumbnail block means) and the boxes scale back up to the page; the third case is below the cap (ratio 1)"""
+    from retto_b200.session import RettoSessionConfig
+    img, prob = _page_and_prob(31, hw[0], hw[1], 1, limit_len)
+    scfg = RettoSessionConfig()
+    scfg.det_processor_config.limit_type = "Max"
+    scfg.det_processor_config.limit_side_len = limit_len
+    _session_case(synth_dict, img, prob, scfg, limit_type=1, limit_len=limit_len)
+
+
+@pytest.mark.parametrize("cls_bn,rec_bn", [(1, 1), (8, 8), (1, 8), (4, 3)])
+def test_batch_num(synth_dict, cls_bn, rec_bn):
+    """cls / rec batch_num 1 and 8 (cls_processor.rs:139, rec_processor.rs:228): batch composition, the running max_wh_ratio and
+    with it every rec tensor width change with the chunking"""
+    from retto_b200.session import RettoSessionConfig
+    img, prob = _page_and_prob(32, 1000, 1400, 0, 736)
+    scfg = RettoSessionConfig()
+    scfg.cls_processor_config.batch_num = cls_bn
+    scfg.rec_processor_config.batch_num = rec_bn
+    _session_case(synth_dict, img, prob, scfg, cls_batch_num=cls_bn, rec_batch_num=rec_bn)
+
+
+def test_non_default_cls_rec_shapes(synth_dict):
+    """cls [3,48,160] / rec [3,32,256], cls thresh .5 (flips more lines)"""
+    from retto_b200.session import RettoSessionConfig
+    img, prob = _page_and_prob(33, 900, 1200, 0, 736)
+    scfg = RettoSessionConfig()
+    scfg.cls_processor_config.image_shape = (3, 48, 160)
+    scfg.cls_processor_config.thresh = 0.5
+    scfg.rec_processor_config.image_shape = (3, 32, 256)
+    _session_case(synth_dict, img, prob, scfg, cls_shape=(3, 48, 160), rec_shape=(3, 32, 256), cls_thresh=0.5)
+
+
+def _gen_mixed(args):
+    seed, h, w = args
+    from oracle import oracle as O
+    from tools.synth import gen_page, probmap_from_rects
+    img, rects = gen_page(seed, h, w, n_lines=(6, 14))
+    page = O.resize_both(img)
+    dh, dw = O.resize_either_plan(page.shape[0], page.shape[1])
+    sx, sy = dw / w, dh / h
+    prob = probmap_from_rects(seed, [(r[0] * sx, r[1] * sy, r[2] * sx, r[3] * sy, r[4]) for r in rects], dh, dw)
+    return img, prob
+
+
+def _ref_mixed(args):
+    img, prob, dict_text = args
+    from oracle.pipeline import run_page
+    return run_page(img, _Worker(prob), dict_text)
+
+
+def test_mixed_size_batch_64_pages(synth_dict):
+    """BASELINE configs[4] shape at test size: 64 pages, long side logU[640, 4096], aspect U[.5, 1], both orientations, in ONE
+    run_pages call (resize_both for > 2000 px, up-scaling for < 736 px, every resize class of det_preprocess) against the oracle"""
+    import multiprocessing as mp
+    from retto_b200.session import CallableWorker, RettoSession
+    rng = np.random.default_rng(64)
+    specs = []
+    for i in range(64):
+        long_side = int(round(np.exp(rng.uniform(np.log(640), np.log(4096)))))
+        short = max(320, int(round(long_side * rng.uniform(0.5, 1.0))))
+        specs.append((700 + i, long_side, short) if rng.random() < 0.5 else (700 + i, short, long_side))
+    with mp.get_context("fork").Pool(min(16, mp.cpu_count())) as pool:
+        made = pool.map(_gen_mixed, specs)
+        refs = pool.map(_ref_mixed, [(im, pr, synth_dict) for im, pr in made])
+    imgs = [m[0] for m in made]
+    workers = [_Worker(m[1]) for m in made]
+
+    class Multi:
+        def __init__(self):
+            self.k = 0
+
+        def det(self, x):
+            w = workers[self.k]
+            self.k += 1
+            return w.det(x)
+
+        def cls(self, x):
+            return workers[0].cls(x)
+
+        def rec(self, x):
+            return workers[0].rec(x)
+
+    from retto_b200.api import Context
+    c = Context(0)
+    try:
+        c.dict_load(synth_dict)
+        m = Multi()
+        sess = RettoSession(worker=CallableWorker(m.det, m.cls, m.rec), ctx=c)
+        got = sess.run_pages(imgs)
+    finally:
+        c.close()
+    n_lines = 0
+    for k, (g, r) in enumerate(zip(got, refs)):
+        assert g.status == 0 and len(g.det_result) == len(r["boxes"]), (k, specs[k])
+        for i in range(len(r["boxes"])):
+            assert np.array_equal(g.det_result[i].boxes, r["boxes"][i]), (k, i)
+            assert g.cls_result[i].label == r["cls"][i][0]
+            assert g.rec_result[i].text == r["rec"][i][0], (k, i)
+        n_lines += len(r["boxes"])
+    assert n_lines > 64 * 4
+    assert sum(1 for s in specs if max(s[1], s[2]) > 2000) >= 8 and sum(1 for s in specs if min(s[1], s[2]) < 736) >= 8
