@@ -301,9 +301,44 @@ typedef struct retto_b200_results {
 retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_page* h_pages, int32_t n_pages,
                                        retto_b200_forward_fn forward, void* user, retto_b200_results* out);
 
+/* Per-stage result delivery == the `callback(RettoWorkerStageResult::{Det,Cls,Rec})` of process_pipeline (session.rs:98,101,104),
+ * which RettoSession::run_stream forwards to its mpsc::Sender (session.rs:133-143; consumer retto-wasm/src/wasm_lib.rs:142-189).
+ * When a callback is set, run_pages calls it three times per unit of pages, on the calling thread, in the reference's order:
+ *   stage 0 (Det) after the boxes are final and rescaled to original-image coordinates, BEFORE the cls forward of that unit;
+ *   stage 1 (Cls) after the cls postprocess (flip flags set), BEFORE the rec forward of that unit;
+ *   stage 2 (Rec) when the unit's strings are on the host.
+ * A unit without detections still reports its three (empty) stages.  The arrays belong to the context and are valid during the
+ * call only.  pages[i].first_line indexes the unit's own arrays (box i <-> cls i <-> rec i, as in retto_b200_results).
+ * Cost: two extra stream synchronisations per unit (the host must hold the Det / Cls results before it may continue), which is why
+ * the batch path leaves the callback unset.  Pass fn = NULL to clear. */
+typedef struct retto_b200_stage_result {
+    int32_t stage;                          /* 0 Det, 1 Cls, 2 Rec */
+    int32_t first_page;                     /* index of the unit's first page in the h_pages array of the run_pages call */
+    int32_t n_pages;
+    const retto_b200_page_result* pages;    /* n_pages entries */
+    int32_t n_lines;
+    const retto_b200_box* boxes;            /* stage 0, else NULL */
+    const retto_b200_cls_result* cls;       /* stage 1, else NULL */
+    const uint32_t* text_offsets;           /* stage 2, else NULL: n_lines + 1 */
+    const char* text;                       /* stage 2 */
+    const float* rec_scores;                /* stage 2 */
+} retto_b200_stage_result;
+typedef void (*retto_b200_stage_fn)(void* user, const retto_b200_stage_result* result);
+retto_b200_status retto_b200_set_stage_callback(retto_b200_ctx* ctx, retto_b200_stage_fn fn, void* user);
+
 /* run_pages pipeline: lanes = 1 (default: units run back to back on the context's own stream) or 2;
  * unit_pages = pages per unit (0 = default: 64 device-resident / 32 host-resident pages).  0 keeps the default. */
 retto_b200_status retto_b200_set_pipeline(retto_b200_ctx* ctx, int32_t lanes, int32_t unit_pages);
+
+/* The same for one batch spread over N contexts — one per GPU of the box (several contexts on one GPU are allowed): pages are
+ * independent (session.rs:75-106), so they are sharded per image with no collective.  One host thread per context
+ * pulls chunks of `chunk_pages` pages (0 = default) from a shared cursor over the pages sorted by descending H*W and runs
+ * retto_b200_run_pages on its context; `forward` is therefore called from N threads concurrently, with users[i] for ctxs[i] (users
+ * may be NULL).  Pages must be host-resident.  The result, in page order (== the sequential CLI's order), is owned by ctxs[0]
+ * and valid until its next run. */
+retto_b200_status retto_b200_run_pages_multi(retto_b200_ctx* const* ctxs, int32_t n_ctx, const retto_b200_page* h_pages, int32_t n_pages,
+                                             int32_t chunk_pages, retto_b200_forward_fn forward, void* const* users,
+                                             retto_b200_results* out);
 
 /* sizes of the last retto_b200_run_pages call: out8 = {pages, lines, det tensor pixels, crop pixels, cls batch floats,
  * rec batch floats, rec logit rows (sum n*img_w/8), 0} — used by bench.py for algorithmic byte counts */

@@ -233,6 +233,8 @@ struct retto_b200_ctx {
     // run_pages pipeline (session.cu): child contexts ("lanes") on the same device, and the tunables
     std::vector<retto_b200_ctx*> lanes;
     int pipe_lanes = 0, pipe_unit_pages = 0;     // 0 = default / environment
+    retto_b200_stage_fn stage_cb = nullptr;      // per-stage result delivery (retto_b200_set_stage_callback)
+    void* stage_user = nullptr;
     std::string dict_source;                     // raw dictionary text, replayed into the lanes
     uint64_t dict_version = 0;
     // sizes of the last run_pages call (bench.py algorithmic bytes): pages, lines, det px, crop px, cls floats, rec floats, rec rows

@@ -37,8 +37,10 @@ retto_b200_status rt_ctc_begin(retto_b200_ctx* ctx, const retto_b200_logits_desc
 retto_b200_status rt_ctc_end(retto_b200_ctx* ctx, uint32_t* h_text_offsets, char* h_text, size_t text_capacity, float* h_scores,
                              int32_t* h_tokens, int32_t* h_token_counts, int32_t max_t_out);
 
+#include <atomic>
 #include <chrono>
 #include <memory>
+#include <thread>
 #define RUN_CHUNK_PAGES_MAX 64
 static int env_int(const char* name, int dflt, int lo, int hi) {
     const char* v = getenv(name);
@@ -81,6 +83,9 @@ struct PageRun {
     int n_pages = 0;
     retto_b200_forward_fn forward = nullptr;
     void* user = nullptr;
+    retto_b200_stage_fn stage_cb = nullptr; // RettoWorkerStageResult delivery (session.rs:98,101,104), optional
+    void* stage_user = nullptr;
+    int first_page = 0;                     // index of this unit's first page in the caller's page array
     cudaEvent_t wait_for = nullptr;         // pages uploaded by the copy stream (chunked host batches)
     bool done = false;                      // finished early (no pages / no lines / error)
     retto_b200_status ret = RETTO_B200_OK;
@@ -100,6 +105,17 @@ struct PageRun {
     bool scaled = false;
 
     retto_b200_status fail(retto_b200_status s) { done = true; ret = s; return s; }
+    // stage 0 = Det (boxes), 1 = Cls, 2 = Rec: the unit's results so far, in the reference's order and BEFORE the next stage's forward
+    void emit_stage(int stage) {
+        if (!stage_cb) return;
+        retto_b200_stage_result r;
+        memset(&r, 0, sizeof(r));
+        r.stage = stage; r.first_page = first_page; r.n_pages = n_pages; r.pages = ctx->r_pages.data(); r.n_lines = n_lines;
+        if (stage == 0) r.boxes = ctx->r_boxes.data();
+        else if (stage == 1) r.cls = ctx->r_cls.data();
+        else { r.text_offsets = ctx->r_text_offs.data(); r.text = ctx->r_text.data(); r.rec_scores = ctx->r_scores.data(); }
+        stage_cb(stage_user, &r);
+    }
     retto_b200_status begin();
     retto_b200_status mid();
     retto_b200_status finish();
@@ -269,7 +285,11 @@ retto_b200_status PageRun::mid() {
     ctx->r_cls.assign(n_lines, retto_b200_cls_result{0, 0.0f});
     ctx->r_scores.assign(n_lines, 0.0f);
     ctx->r_text_offs.assign(n_lines + 1, 0);
-    if (n_lines == 0) { done = true; return ret; }
+    if (n_lines == 0) {   // no detections: cls / rec run zero batches and return empty results (App. A #20); the three stages still report
+        done = true;
+        emit_stage(0); emit_stage(1); emit_stage(2);
+        return ret;
+    }
 
     // ---- 5. crops from the resize_both-ed page (session.rs:88-92) --------------------------------------------------
     // From here to the CTC read-back nothing waits for the GPU: the plans depend only on the crop dims (known on the
@@ -332,6 +352,13 @@ retto_b200_status PageRun::mid() {
             tin[b].ndim = 4;
         }
     };
+    if (stage_cb) {
+        // streaming callers get the Det result before worker.cls runs (session.rs:98): that needs the rescaled boxes on the host
+        // now instead of at the end of the unit — one extra stream sync per unit, paid only when a stage callback is set
+        RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        if (scaled) { memcpy(ctx->r_boxes.data(), ctx->h_scale.p, sizeof(retto_b200_box) * (size_t)n_lines); scaled = false; }
+        emit_stage(0);
+    }
     fill_inputs(batches, d_base, cfg.cls_image_shape[1]);
     if (forward(user, 1, (int)batches.size(), tin.data(), tout.data(), (void*)st) != 0) { ctx->set_error("run_pages: cls forward failed"); return fail(RETTO_B200_ERR_WORKER); }
     {
@@ -349,6 +376,13 @@ retto_b200_status PageRun::mid() {
             }
         }
         if ((s = rt_cls_postprocess_ptrs(ctx, ptrs, cls_crop_idx.data(), n_lines, nullptr, true)) != RETTO_B200_OK) return fail(s);   // collected after the final sync
+        if (stage_cb) {   // the Cls result before worker.rec runs (session.rs:101)
+            RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+            std::vector<retto_b200_cls_result> res(n_lines);
+            if ((s = rt_cls_collect(ctx, n_lines, res.data())) != RETTO_B200_OK) return fail(s);
+            for (int k = 0; k < n_lines; ++k) ctx->r_cls[cls_crop_idx[k]] = res[k];
+            emit_stage(1);
+        }
     }
     tr.mark("cls_fwd+post");
     // ---- 8. rec (rec_processor.rs:214-270) ---------------------------------------------------------------------------------
@@ -401,6 +435,7 @@ retto_b200_status PageRun::finish() {
         ctx->r_scores[dst] = sc[k];
     }
     tr.mark("collect");
+    emit_stage(2);   // session.rs:104
     return ret;
 }
 
@@ -463,7 +498,7 @@ static retto_b200_status lane_ctx(retto_b200_ctx* ctx, int lane, retto_b200_ctx*
     return RETTO_B200_OK;
 }
 
-struct Unit { const retto_b200_page* pages; int n; cudaEvent_t wait_for; };
+struct Unit { const retto_b200_page* pages; int n; cudaEvent_t wait_for; int first_page; };
 
 // Software pipeline over the units, two in flight: finish(u[k-2]) -> begin(u[k]) -> mid(u[k-1]).  Unit k runs on lane
 // k % 2, which unit k-2 has just left.  With one lane the units run back to back.
@@ -505,6 +540,7 @@ static retto_b200_status run_units(retto_b200_ctx* ctx, const std::vector<Unit>&
         runs[k].reset(new PageRun());
         PageRun& r = *runs[k];
         r.ctx = lane[k % n_lanes]; r.h_pages = units[k].pages; r.n_pages = units[k].n; r.forward = forward; r.user = user; r.wait_for = units[k].wait_for;
+        r.stage_cb = ctx->stage_cb; r.stage_user = ctx->stage_user; r.first_page = units[k].first_page;
         return r.begin();
     };
     if (n_lanes == 1) {
@@ -570,7 +606,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     if (!all_host) {
         // one unit, or (device-resident pages, two lanes) units of unit_dev pages
         const int up = (all_dev && n_lanes > 1 && n_pages > unit_dev) ? unit_dev : std::max(n_pages, 1);
-        for (int p0 = 0; p0 < std::max(n_pages, 1); p0 += up) units.push_back(Unit{h_pages + p0, std::min(up, n_pages - p0), nullptr});
+        for (int p0 = 0; p0 < std::max(n_pages, 1); p0 += up) units.push_back(Unit{h_pages + p0, std::min(up, n_pages - p0), nullptr, p0});
         return run_units(ctx, units, n_lanes, forward, user, out);
     }
     if (!ctx->copy_stream) {
@@ -624,7 +660,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     }
     for (int c = 0; c < n_chunks; ++c) {
         const int p0 = c * RUN_CHUNK_PAGES;
-        units.push_back(Unit{dev_pages.data() + p0, std::min(RUN_CHUNK_PAGES, n_pages - p0), ctx->copy_events[c]});
+        units.push_back(Unit{dev_pages.data() + p0, std::min(RUN_CHUNK_PAGES, n_pages - p0), ctx->copy_events[c], p0});
     }
     const bool by_sm = USE_DMA != 0;
     ctx->uploads_by_sm = by_sm;
@@ -634,6 +670,13 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     for (retto_b200_ctx* l : ctx->lanes) l->uploads_by_sm = false;
     cudaStreamSynchronize(ctx->copy_stream);
     return ret;
+}
+
+extern "C" retto_b200_status retto_b200_set_stage_callback(retto_b200_ctx* ctx, retto_b200_stage_fn fn, void* user) {
+    if (!ctx) return RETTO_B200_ERR_INVALID_ARG;
+    ctx->stage_cb = fn;
+    ctx->stage_user = user;
+    return RETTO_B200_OK;
 }
 
 extern "C" retto_b200_status retto_b200_set_pipeline(retto_b200_ctx* ctx, int32_t lanes, int32_t unit_pages) {
@@ -647,4 +690,105 @@ extern "C" retto_b200_status retto_b200_last_run_stats(const retto_b200_ctx* ctx
     if (!ctx || !out8) return RETTO_B200_ERR_INVALID_ARG;
     memcpy(out8, ctx->run_stats, sizeof(ctx->run_stats));
     return RETTO_B200_OK;
+}
+
+// ---- several contexts, one batch: RettoSession::run over pages sharded per image ---------------------------------------
+// Pages are independent (session.rs:75-106 reads no state of another page), so a batch is spread over N contexts — normally one per
+// GPU of the box — with no collective: one host thread per context pulls chunks of pages from a shared atomic cursor over the page
+// list sorted by descending H*W (longest-processing-time first, so the stragglers are the small pages), runs retto_b200_run_pages on
+// its own context / device / stream, and files the results under the pages' original indices.  The assembled result (page order ==
+// the sequential CLI's order) is owned by ctxs[0].
+namespace {
+struct PageOut {
+    int32_t status = 0;
+    std::vector<retto_b200_box> boxes;
+    std::vector<retto_b200_cls_result> cls;
+    std::vector<float> scores;
+    std::vector<uint32_t> text_len;
+    std::string text;
+};
+}  // namespace
+
+extern "C" retto_b200_status retto_b200_run_pages_multi(retto_b200_ctx* const* ctxs, int32_t n_ctx, const retto_b200_page* h_pages, int32_t n_pages,
+                                                        int32_t chunk_pages, retto_b200_forward_fn forward, void* const* users,
+                                                        retto_b200_results* out) {
+    if (!ctxs || n_ctx <= 0 || !ctxs[0] || n_pages < 0 || (n_pages > 0 && !h_pages) || !forward || !out || chunk_pages < 0) return RETTO_B200_ERR_INVALID_ARG;
+    retto_b200_ctx* c0 = ctxs[0];
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < n_ctx; ++i) {
+        if (!ctxs[i]) { c0->set_error("run_pages_multi: null context"); return RETTO_B200_ERR_INVALID_ARG; }
+        for (int j = 0; j < i; ++j) if (ctxs[j] == ctxs[i]) { c0->set_error("run_pages_multi: a context is listed twice"); return RETTO_B200_ERR_INVALID_ARG; }
+    }
+    for (int i = 0; i < n_pages; ++i)
+        if (h_pages[i].on_device) { c0->set_error("run_pages_multi: pages must be host-resident (a device pointer belongs to one GPU)"); return RETTO_B200_ERR_INVALID_ARG; }
+    std::vector<int> order(n_pages);
+    for (int i = 0; i < n_pages; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (long long)h_pages[a].h * h_pages[a].w > (long long)h_pages[b].h * h_pages[b].w;
+    });
+    const int chunk = chunk_pages > 0 ? chunk_pages : std::max(1, std::min(32, n_pages / (n_ctx * 3)));
+    std::vector<PageOut> outs(n_pages);
+    std::atomic<int> cursor{0};
+    std::atomic<int> first_error{RETTO_B200_OK};
+    std::vector<retto_b200_status> soft(n_ctx, RETTO_B200_OK);
+    std::vector<uint64_t> stats((size_t)n_ctx * 8, 0);
+    auto work = [&](int ci) {
+        retto_b200_ctx* ctx = ctxs[ci];
+        std::vector<retto_b200_page> mine;
+        for (;;) {
+            if (first_error.load() != RETTO_B200_OK) return;
+            const int start = cursor.fetch_add(chunk);
+            if (start >= n_pages) return;
+            const int n = std::min(chunk, n_pages - start);
+            mine.resize(n);
+            for (int k = 0; k < n; ++k) mine[k] = h_pages[order[start + k]];
+            retto_b200_results r;
+            const retto_b200_status s = retto_b200_run_pages(ctx, mine.data(), n, forward, users ? users[ci] : nullptr, &r);
+            const bool hard = s != RETTO_B200_OK && s != RETTO_B200_ERR_DEGENERATE_QUAD && s != RETTO_B200_ERR_CAPACITY;
+            if (hard || r.n_pages != n) {
+                int expect = RETTO_B200_OK;
+                if (first_error.compare_exchange_strong(expect, hard ? (int)s : (int)RETTO_B200_ERR_CUDA) && ctx != c0) c0->set_error(ctx->err);
+                return;
+            }
+            if (s != RETTO_B200_OK) soft[ci] = s;
+            for (int k = 0; k < n; ++k) {
+                PageOut& o = outs[order[start + k]];
+                const retto_b200_page_result& pr = r.pages[k];
+                o.status = pr.status;
+                o.boxes.assign(r.boxes + pr.first_line, r.boxes + pr.first_line + pr.n_lines);
+                o.cls.assign(r.cls + pr.first_line, r.cls + pr.first_line + pr.n_lines);
+                o.scores.assign(r.rec_scores + pr.first_line, r.rec_scores + pr.first_line + pr.n_lines);
+                o.text_len.resize(pr.n_lines);
+                for (int l = 0; l < pr.n_lines; ++l) o.text_len[l] = r.text_offsets[pr.first_line + l + 1] - r.text_offsets[pr.first_line + l];
+                if (pr.n_lines) o.text.assign(r.text + r.text_offsets[pr.first_line], r.text + r.text_offsets[pr.first_line + pr.n_lines]);
+            }
+            for (int k = 0; k < 8; ++k) stats[(size_t)ci * 8 + k] += ctx->run_stats[k];
+        }
+    };
+    if (n_ctx == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int ci = 0; ci < n_ctx; ++ci) th.emplace_back(work, ci);
+        for (auto& t : th) t.join();
+    }
+    if (first_error.load() != RETTO_B200_OK) return (retto_b200_status)first_error.load();
+    retto_b200_status ret = RETTO_B200_OK;
+    for (int ci = 0; ci < n_ctx; ++ci) if (soft[ci] != RETTO_B200_OK) { ret = soft[ci]; if (ctxs[ci] != c0) c0->set_error(ctxs[ci]->err); }
+    // assemble in page order
+    c0->r_pages.assign(n_pages, retto_b200_page_result{0, 0, 0});
+    c0->r_boxes.clear(); c0->r_cls.clear(); c0->r_scores.clear(); c0->r_text_offs.assign(1, 0); c0->r_text.clear();
+    for (int p = 0; p < n_pages; ++p) {
+        const PageOut& o = outs[p];
+        c0->r_pages[p] = retto_b200_page_result{o.status, (int32_t)c0->r_boxes.size(), (int32_t)o.boxes.size()};
+        c0->r_boxes.insert(c0->r_boxes.end(), o.boxes.begin(), o.boxes.end());
+        c0->r_cls.insert(c0->r_cls.end(), o.cls.begin(), o.cls.end());
+        c0->r_scores.insert(c0->r_scores.end(), o.scores.begin(), o.scores.end());
+        for (uint32_t l : o.text_len) c0->r_text_offs.push_back(c0->r_text_offs.back() + l);
+        c0->r_text.insert(c0->r_text.end(), o.text.begin(), o.text.end());
+    }
+    c0->r_text.push_back(0);
+    memset(c0->run_stats, 0, sizeof(c0->run_stats));
+    for (int ci = 0; ci < n_ctx; ++ci) for (int k = 0; k < 8; ++k) c0->run_stats[k] += stats[(size_t)ci * 8 + k];
+    fill_results(c0, out);
+    return ret;
 }

@@ -114,28 +114,46 @@ def test_nonfinite_probability_maps(ccl_path):
         cfg = O.default_det_cfg()
         base = [gen_probmap(500 + i, 320, 480, k_range=(4, 9), wide_angle=True) for i in range(4)]
         maps = []
+        n_clean = []
         for i, p in enumerate(base):
             ref = O.det_postprocess(p, *p.shape)
-            assert len(ref.boxes) >= 3
-            q = p.copy()
-            b = ref.boxes[0]
+            n_clean.append(len(ref.boxes))
+            # a box whose centre lies well inside its text rectangle
+            k = next(k for k, b in enumerate(ref.boxes) if p[int(b[:, 1].mean()), int(b[:, 0].mean())] > 0.6)
+            b = ref.boxes[k]
             cx, cy = int(b[:, 0].mean()), int(b[:, 1].mean())
             x0, y0 = int(b[:, 0].min()), int(b[:, 1].min())
+            q = p.copy()
             if i == 0:
                 q[cy, cx] = np.nan                 # inside the polygon
             elif i == 1:
-                q[min(y0 + 3, q.shape[0] - 1), min(x0 + 3, q.shape[1] - 1)] = np.nan    # bounding-box corner: usually outside the rotated polygon
+                # a background pixel inside the bounding box of a rotated first rectangle but OUTSIDE its polygon (m = 0)
+                rect1, _ss, _sc, st = O.det_trace(p, *p.shape)
+                done = False
+                for r1, s1 in zip(rect1, st):
+                    r1 = r1.reshape(4, 2)
+                    bx0, by0 = max(int(r1[:, 0].min()), 0), max(int(r1[:, 1].min()), 0)
+                    bx1, by1 = min(int(r1[:, 0].max()), p.shape[1] - 1), min(int(r1[:, 1].max()), p.shape[0] - 1)
+                    if s1 != 0 or bx1 - bx0 < 8 or by1 - by0 < 8:
+                        continue
+                    rc, mask = O.polygon_mask(bx1 - bx0 + 1, by1 - by0 + 1, r1 - np.array([bx0, by0]))
+                    ys, xs = np.nonzero(mask == 0)
+                    if rc == 0 and len(ys):
+                        q[by0 + ys[0], bx0 + xs[0]] = np.nan
+                        done = True
+                        break
+                assert done
             elif i == 2:
-                q[cy, cx] = np.inf                 # +Inf inside: foreground, score +Inf
+                q[cy, cx] = np.inf                 # +Inf inside: foreground, score +Inf (NaN for a neighbour whose bbox covers it)
             else:
-                q[cy, cx] = -np.inf                # -Inf inside: background pixel, score -Inf -> dropped
+                q[cy, cx] = -np.inf                # -Inf inside: score -Inf < box_thresh -> the box is dropped
                 q[2, 2] = np.nan                   # far from every box: no effect at all
             maps.append(q)
-        clean = base[0]
-        out, _ = _check(c, maps + [clean], cfg)
-        assert np.isnan(out.page(0)[1]).any()
+        out, _ = _check(c, maps + [base[0]], cfg)
+        assert np.isnan(out.page(0)[1]).any() and np.isnan(out.page(1)[1]).any()
         assert np.isinf(out.page(2)[1]).any()
-        assert np.isfinite(out.page(4)[1]).all()
+        assert len(out.page(3)[0]) == n_clean[3] - 1 and np.isfinite(out.page(3)[1]).all()
+        assert np.isfinite(out.page(4)[1]).all() and len(out.page(4)[0]) == n_clean[0]
     finally:
         c.close()
 

@@ -22,7 +22,7 @@ def test_config2_dbpost_1024_maps_960(ctx, libm_diag):
     from oracle import oracle as O
     NU = 256
     with mp.get_context("fork").Pool(min(16, mp.cpu_count())) as pool:
-        cand = pool.map(_gen960, range(2000, 2000 + NU + 64))
+        cand = pool.map(_gen960, range(2000, 2000 + NU + 192))
     uniq = [p for p in cand if not O.det_postprocess(p, 960, 960).comparator_inconsistent][:NU]
     assert len(uniq) == NU
     refs = [O.det_postprocess(p, 960, 960) for p in uniq]
