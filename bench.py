@@ -1,33 +1,38 @@
 #!/usr/bin/env python
-"""bench.py — pages/sec of the det+cls+rec image path (BASELINE.json metric) on N B200s of one node.
+"""bench.py — pages/sec of the det+cls+rec IMAGE PATH (BASELINE.json metric) on N B200s of one node.
 
-Workload (config.workload): BASELINE.json configs[3] "256 pages 1280x1280 end-to-end det+cls+rec on
-1 B200" — synthetic rendered-text pages; the DBNet/SVTR forward passes are NOT part of the path (they stay
-on the inference runtime) and are stood in for by a zero-copy REPLAY worker that hands back
-pre-resident probability maps / logits (distinct buffers, total far larger than L2).  One step = one pass
-of the whole hot path (resize plan, det preprocess, DB postprocess, rotate-crop, cls batches + flip, rec
-batches, CTC decode) over one batch of 256 pages per GPU.  Pages are independent: ranks shard per page,
-no collective on the data path ("scaling": "weak").
+Workloads (`--workload`, named in config.workload):
+  pages1280 (default) BASELINE.json configs[3]: 256 synthetic rendered-text pages 1280x1280 per GPU per step
+  mixed               BASELINE.json configs[4]: 64k mixed-size pages (long side logU[640, 4096] px, aspect U[.5, 1]) per step over
+                      all GPUs, drawn from a pool of 512 unique pages, sharded per image (LPT by H*W), processed in chunks
 
-  value : pages/s with the pages already resident in HBM when the timed region starts
-  e2e   : pages/s through the public C-ABI call (retto_b200_run_pages) with HOST pinned pages, H2D of every
-          page and D2H of boxes/labels/strings inside the timed region
-  roofline / kernels : per-kernel CUDA-event durations measured inside the timed region (events on the
-          launching stream) against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the CPU oracle (port of the reference's scalar path) on a bounded sample, all host cores
+What is timed.  One step = one pass of the whole hot path (image decode, resize plan, det preprocess, DB postprocess, rotate-crop,
+cls batches + flip, rec batches, CTC decode) over one batch of pages per GPU.  The DBNet / SVTR forward passes are NOT part of the
+path (they stay on the inference runtime): in `value` / `e2e` a zero-copy REPLAY worker hands back pre-resident
+probability maps / logits (distinct buffers, far larger than L2); `with_forward` repeats the step with a torch stand-in network of
+PP-OCRv4-mobile I/O shape EXECUTED on the context's tensors (zero-copy) before the replayed outputs are substituted.
+Pages are independent: ranks shard per page, no collective on the data path ("scaling": "weak").
 
-`--impl reference` times the CPU oracle itself (the reference is Rust and cannot be built here).
+  value  : pages/s with the decoded pages already resident in HBM when the timed region starts
+  e2e    : pages/s through the public C-ABI call (retto_b200_run_pages) from HOST memory — the page FILES (JPEG, the wire format of
+           retto-cli, main.rs:83-84) in pinned memory, uploaded and decoded on the device inside the timed region, boxes / labels /
+           strings read back.  e2e_variants: the same from raw RGB pixels (round 1's e2e) and other JPEG encodings.
+  roofline / kernels : per-kernel CUDA-event durations measured inside a timed pass (events on the launching stream) against
+           MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the CPU oracle (port of the reference's scalar path; libjpeg-turbo decode) on a bounded sample, one PROCESS per core
+
+`--impl reference` times that CPU path itself on the same workload (the reference is Rust and cannot be built here).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import io
 import json
 import os
 import sys
 import threading
 import time
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -35,6 +40,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C_CLASSES = 6625
+METRIC = "pages/sec det+cls+rec image path (decode + pre/post kernels; DBNet/SVTR forwards replayed, see with_forward)"
+JPEG_KW = {"dri_mcu_row": dict(restart_marker_rows=1), "no_restart": dict(), "dri_8_mcus": dict(restart_marker_blocks=8)}
+JPEG_DESC = {"dri_mcu_row": "JPEG q90 4:2:0, one restart interval per MCU row", "no_restart": "JPEG q90 4:2:0, no restart markers",
+             "dri_8_mcus": "JPEG q90 4:2:0, restart interval 8 MCUs"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -44,11 +53,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pages", type=int, default=256, help="pages per GPU per step")
+    ap.add_argument("--workload", default="pages1280", choices=["pages1280", "mixed"])
+    ap.add_argument("--pages", type=int, default=0, help="pages per GPU per step (default 256; mixed: 65536 / gpus)")
     ap.add_argument("--size", type=int, default=1280)
-    ap.add_argument("--unique", type=int, default=32, help="unique rendered pages (cycled into distinct device buffers)")
+    ap.add_argument("--unique", type=int, default=0, help="unique rendered pages (default 32; mixed: 512)")
+    ap.add_argument("--chunk", type=int, default=512, help="mixed: pages per retto_b200_run_pages call")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pages in the bounded CPU-baseline sample (0 = 12 per host core: ~20-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-forward", action="store_true", help="skip the with_forward figure")
+    ap.add_argument("--no-variants", action="store_true", help="skip e2e_variants")
     return ap.parse_args()
 
 
@@ -62,15 +75,54 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(n_unique, size, seed0=4):
-    """rendered pages + the DB probability maps a det model would emit for them (tools/synth.py)"""
+# ---- synthetic workload ------------------------------------------------------------------------------
+def _encode(img, kind):
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", quality=90, subsampling=2, **JPEG_KW[kind])
+    return b.getvalue()
+
+
+def _decode_host(data):
+    """libjpeg-turbo through OpenCV: the host-side decode of the CPU arm (bit-identical to the device decode, tests/test_gpu_jpeg.py)"""
+    import cv2
+    return cv2.cvtColor(cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+
+
+def _make_one(args):
+    """one unique page: rendered text -> JPEG files -> the decoded pixels every arm works on + the DB probability map a det model
+    would emit for it (tools/synth.py)"""
+    seed, h, w, kinds = args
+    from oracle import oracle as O
     from tools.synth import gen_page, probmap_from_rects
-    pages, probs = [], []
-    for i in range(n_unique):
-        img, rects = gen_page(seed0 + i, size, size)
-        pages.append(img)
-        probs.append(probmap_from_rects(seed0 + i, rects, size, size))
-    return pages, probs
+    img, rects = gen_page(seed, h, w, n_lines=(max(4, h // 64), max(6, h // 28)) if (h, w) != (1280, 1280) else (20, 45))
+    files = {k: _encode(img, k) for k in kinds}
+    rgb = _decode_host(files[kinds[0]])
+    plan = O.resize_both_plan(h, w)
+    ah, aw = plan[-1] if plan else (h, w)
+    dh, dw = O.resize_either_plan(ah, aw)
+    sx, sy = dw / w, dh / h
+    prob = probmap_from_rects(seed, [(r[0] * sx, r[1] * sy, r[2] * sx, r[3] * sy, r[4]) for r in rects], dh, dw)
+    return dict(rgb=rgb, prob=prob, files=files, hw=(h, w))
+
+
+def make_workload(workload, n_unique, size, seed0, kinds):
+    import multiprocessing as mp
+    specs = []
+    if workload == "pages1280":
+        specs = [(seed0 + i, size, size, kinds) for i in range(n_unique)]
+    else:
+        rng = np.random.default_rng(seed0)
+        for i in range(n_unique):
+            long_side = int(round(np.exp(rng.uniform(np.log(640), np.log(4096)))))
+            short = max(64, int(round(long_side * rng.uniform(0.5, 1.0))))
+            h, w = (long_side, short) if rng.random() < 0.5 else (short, long_side)
+            specs.append((seed0 + i, h, w, kinds))
+    procs = min(len(specs), os.cpu_count() or 1, 32)
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            return pool.map(_make_one, specs)
+    return [_make_one(s) for s in specs]
 
 
 class ClockSampler(threading.Thread):
@@ -117,15 +169,23 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------------------
+# ---- forward stand-ins -----------------------------------------------------------------------------------
+# Replay statistics, IDENTICAL on the GPU arm (ReplayWorker) and the CPU arm (OracleReplay):
+#   cls: 30 % of the lines say "180"; the winning score is .95 with probability .3, else .55  ->  9 % of the lines are flipped
+#   rec: per time step the winner is blank with p = .45, repeats the previous winner with p = .2, else uniform over the classes;
+#        winner in [.5, 1), background U[0, 1e-3); every batch reads its own rows of a large pool
+CLS_P180, CLS_PHIGH, REC_PBLANK, REC_PREPEAT = 0.3, 0.3, 0.45, 0.2
+
+
 class ReplayWorker:
     """Zero-copy replay of pre-resident forward outputs through the retto_b200_forward_fn seam.
-    det: page i -> its probability map; cls: pseudo-random [n,2] rows (30 % say "180, score .95");
-    rec: random CTC-shaped logits carved out of one big pool so every batch reads its own HBM region.
-    The pipeline is deterministic, so the tensor list of every stage is built during the first (warm-up)
-    call and replayed with one memmove afterwards (the callback then costs microseconds)."""
+    det: page i -> its probability map; cls / rec: see the replay statistics above, carved out of pools so that every batch reads
+    its own HBM region.  The pipeline is deterministic, so the tensor list of every (stage, call) is built during the first
+    (warm-up) pass and replayed with one memmove afterwards (the callback then costs microseconds).
+    `standin` (optional): torch modules of PP-OCRv4-mobile I/O shape that are EXECUTED on the input tensors (wrapped zero-copy)
+    before the replayed outputs are handed back."""
 
-    def __init__(self, torch, device, probs_dev, seed=0):
+    def __init__(self, torch, device, probs_dev, seed=0, standin=None):
         from retto_b200._lib import FORWARD_FN, Tensor
         self.torch, self.device, self.probs = torch, device, probs_dev
         self.Tensor = Tensor
@@ -135,15 +195,41 @@ class ReplayWorker:
         self.gen.manual_seed(seed)
         self.cb = FORWARD_FN(self._call)
         self.err = None
+        self.standin = standin
+        self.fwd_ms = 0.0
+        self.zero_copy_checked = 0
         self.begin_step()
 
     def begin_step(self):
-        """run_pages may split a host-resident batch into chunks: each (stage, call index) has its own tensor list"""
+        """run_pages may split a batch into units: each (stage, call index) has its own tensor list"""
         self.seq = {0: 0, 1: 0, 2: 0}
         self.page_cursor = 0
 
+    def new_mode(self):
+        """a different page list / unit split follows: forget the cached tensor lists"""
+        self.cache.clear()
+        self.keep.clear()
+
+    def _run_standin(self, stage, n, inputs, stream):
+        """the forwards a real worker would run, on the context's own buffers (zero-copy, on the stream the call names)"""
+        torch = self.torch
+        from retto_b200.session import _wrap
+        ts = torch.cuda.ExternalStream(int(stream), device=self.device)
+        with torch.cuda.stream(ts), torch.no_grad():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            xs = [_wrap(inputs[i], self.device) for i in range(n)]
+            for i in range(n):
+                assert xs[i].data_ptr() == inputs[i].d_data          # the network reads the context's tensor itself: no D2D copy
+                self.zero_copy_checked += 1
+            self.standin.run(stage, xs)
+            e1.record(ts)
+        self.keep.setdefault("ev", []).append((e0, e1))
+
     def _call(self, user, stage, n, inputs, outputs, stream):
         try:
+            if self.standin is not None:
+                self._run_standin(stage, n, inputs, stream)
             key = (stage, self.seq[stage])
             self.seq[stage] += 1
             page0 = self.page_cursor
@@ -162,8 +248,8 @@ class ReplayWorker:
             elif stage == 1:
                 tot = sum(int(inputs[i].shape[0]) for i in range(n))
                 u = torch.rand(max(tot, 1), device=self.device, generator=self.gen)
-                s = torch.where(torch.rand(max(tot, 1), device=self.device, generator=self.gen) < 0.3, 0.95, 0.55)
-                is180 = u < 0.3
+                s = torch.where(torch.rand(max(tot, 1), device=self.device, generator=self.gen) < CLS_PHIGH, 0.95, 0.55)
+                is180 = u < CLS_P180
                 buf = torch.stack([torch.where(is180, 1 - s, s), torch.where(is180, s, 1 - s)], 1).contiguous().float()
                 self.keep[key] = buf
                 o = 0
@@ -178,8 +264,8 @@ class ReplayWorker:
                 pool = torch.rand(max(tot_rows, 1) * C_CLASSES, device=self.device, generator=self.gen) * 1e-3
                 v = pool.view(-1, C_CLASSES)
                 win = torch.randint(1, C_CLASSES, (v.shape[0],), device=self.device, generator=self.gen)
-                win[torch.rand(v.shape[0], device=self.device, generator=self.gen) < 0.45] = 0
-                rep = torch.rand(v.shape[0], device=self.device, generator=self.gen) < 0.2
+                win[torch.rand(v.shape[0], device=self.device, generator=self.gen) < REC_PBLANK] = 0
+                rep = torch.rand(v.shape[0], device=self.device, generator=self.gen) < REC_PREPEAT
                 win[1:][rep[1:]] = win[:-1][rep[1:]]
                 v[torch.arange(v.shape[0], device=self.device), win] = 0.5 + 0.5 * torch.rand(v.shape[0], device=self.device, generator=self.gen)
                 self.keep[key] = pool
@@ -197,61 +283,88 @@ class ReplayWorker:
             self.err = e
             return 1
 
+    def forward_ms(self):
+        """device time of the stand-in forwards recorded since the last call (events on the stream of the call)"""
+        ms = 0.0
+        for e0, e1 in self.keep.pop("ev", []):
+            ms += e0.elapsed_time(e1)
+        return ms
 
-# ------------------------------------------------------------------------------------------------------
+
+# ---- CPU arm: the oracle pipeline, one process per core ------------------------------------------------------
+_CPU = {}
+
+
 class OracleReplay:
-    """numpy replay worker for the CPU oracle pipeline (same roles as ReplayWorker)"""
+    """numpy replay worker for the CPU oracle pipeline: the statistics of ReplayWorker (see above); rec rows come from a pool shared
+    by all pages (fork: read-only, no copies), each call starting at its own offset"""
 
-    def __init__(self, prob, seed=0, pool_rows=6 * 400):
-        rng = np.random.default_rng(seed)
-        self.prob = prob
-        self.pool = (rng.random((pool_rows, C_CLASSES), dtype=np.float32) * np.float32(1e-3))
-        win = rng.integers(1, C_CLASSES, pool_rows)
-        win[rng.random(pool_rows) < 0.45] = 0
-        self.pool[np.arange(pool_rows), win] = 0.5 + 0.5 * rng.random(pool_rows, dtype=np.float32)
-        self.rng = rng
+    def __init__(self, prob, seed, pool):
+        self.rng = np.random.default_rng(seed)
+        self.prob, self.pool = prob, pool
+        self.off = int(self.rng.integers(0, pool.shape[0]))
 
     def det(self, x):
         return self.prob[None, None]
 
     def cls(self, x):
         n = x.shape[0]
-        out = np.tile(np.array([[0.55, 0.45]], np.float32), (n, 1))
-        out[self.rng.random(n) < 0.1] = (0.05, 0.95)
-        return out
+        is180 = self.rng.random(n) < CLS_P180
+        s = np.where(self.rng.random(n) < CLS_PHIGH, np.float32(0.95), np.float32(0.55)).astype(np.float32)
+        return np.stack([np.where(is180, 1 - s, s), np.where(is180, s, 1 - s)], 1).astype(np.float32)
 
     def rec(self, x):
         n, T = x.shape[0], x.shape[3] // 8
-        need = n * T
-        if need > self.pool.shape[0]:
-            reps = (need + self.pool.shape[0] - 1) // self.pool.shape[0]
-            return np.tile(self.pool, (reps, 1))[:need].reshape(n, T, C_CLASSES)
-        return self.pool[:need].reshape(n, T, C_CLASSES)
+        need, R = n * T, self.pool.shape[0]
+        if self.off + need > R:
+            self.off = 0
+        out = self.pool[self.off:self.off + need].reshape(n, T, C_CLASSES)
+        self.off += need
+        return out
 
 
-def cpu_oracle_pages_per_s(pages, probs, n_sample, dict_text, threads, repeats=1):
-    from oracle import oracle as O
+def _cpu_pool(rows=16384, seed=7):
+    rng = np.random.default_rng(seed)
+    pool = (rng.random((rows, C_CLASSES), dtype=np.float32) * np.float32(1e-3))
+    win = rng.integers(1, C_CLASSES, rows)
+    win[rng.random(rows) < REC_PBLANK] = 0
+    rep = rng.random(rows) < REC_PREPEAT
+    win[1:][rep[1:]] = win[:-1][rep[1:]]
+    pool[np.arange(rows), win] = (0.5 + 0.5 * rng.random(rows)).astype(np.float32)
+    return pool
+
+
+def _cpu_one(i):
+    """one page of the CPU arm: file bytes -> libjpeg-turbo decode -> oracle pipeline (what retto-cli does per image on the CPU)"""
     from oracle.pipeline import run_page
-    O.lib()
-    workers = [OracleReplay(probs[i % len(probs)], seed=i) for i in range(min(n_sample, len(probs)))]
+    w = _CPU["work"][i % len(_CPU["work"])]
+    img = _decode_host(w["files"][_CPU["kind"]])
+    r = run_page(img, OracleReplay(w["prob"], i, _CPU["pool"]), _CPU["dict"])
+    return len(r["boxes"])
 
-    def one(i):
-        run_page(pages[i % len(pages)], workers[i % len(workers)], dict_text)
-        return 1
 
-    best = None
-    for _ in range(repeats):
+class CpuArm:
+    def __init__(self, work, kind, dict_text, procs):
+        import multiprocessing as mp
+        from oracle import oracle as O
+        O.lib()
+        _CPU.update(work=work, kind=kind, dict=dict_text, pool=_cpu_pool())
+        self.procs = procs
+        self.pool = mp.get_context("fork").Pool(procs)
+
+    def run(self, n_pages):
         t0 = time.perf_counter()
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            list(ex.map(one, range(n_sample)))
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_sample / best, best
+        lines = sum(self.pool.map(_cpu_one, range(n_pages), chunksize=1))
+        return time.perf_counter() - t0, lines
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(name, info, launch_idx=0):
-    """SURVEY.md §8(d) / DESIGN.md per-unit figures x the units one launch processes"""
+def algorithmic_bytes(name, info):
+    """SURVEY.md §8(d) / DESIGN.md per-unit figures x the units one STEP processes (all launches of the kernel in a step together)"""
     HW = info["det_px"]
     if name.startswith("ctc_argmax"):
         return 4.0 * info["rec_rows"] * C_CLASSES
@@ -263,8 +376,12 @@ def algorithmic_bytes(name, info, launch_idx=0):
         return 9.0 * HW                       # prob read 4 + bitmap write 1 + label write 4
     if name.startswith("crop_rows"):
         return 6.0 * info["crop_px"]          # 3 B read + 3 B written per crop pixel
-    if name.startswith("build_batches"):      # two launches per step (cls + rec): sum of both, per launch = half the time
-        return (2 * 3.0 * info["crop_px"] + 4.0 * (info["cls_floats"] + info["rec_floats"])) / 2.0
+    if name.startswith("build_batches"):      # two launches per unit (cls + rec): both together
+        return 2 * 3.0 * info["crop_px"] + 4.0 * (info["cls_floats"] + info["rec_floats"])
+    if name.startswith("jpeg_idct"):
+        return info.get("jpeg_px", 0) * 1.5 * 3.0     # 2 B coefficient read + 1 B sample written per sample (4:2:0: 1.5 samples per pixel)
+    if name.startswith("jpeg_color"):
+        return info.get("jpeg_px", 0) * 4.5           # 1.5 B of samples read + 3 B RGB written per pixel
     return None
 
 
@@ -276,31 +393,46 @@ def main():
     from tools.synth import synth_dict_text
     dict_text = synth_dict_text()
     cores = os.cpu_count() or 1
-    config = {"workload": f"{args.pages} pages {args.size}x{args.size} end-to-end det+cls+rec per GPU (BASELINE.json configs[3])",
-              "pages_per_gpu": args.pages, "page_hw": [args.size, args.size], "unique_pages": min(args.unique, args.pages),
-              "forward": "replay worker (pre-resident prob maps / logits; DBNet/SVTR forwards stay on the inference runtime, out of the path)",
+    mixed = args.workload == "mixed"
+    P = args.pages or (max(1, 65536 // max(world, args.gpus, 1)) if mixed else 256)
+    U = args.unique or (512 if mixed else 32)
+    U = min(U, P)
+    S = args.size
+    kinds = ["dri_mcu_row"] if (mixed or args.no_variants or args.impl == "reference") else ["dri_mcu_row", "no_restart", "dri_8_mcus"]
+    if mixed:
+        wl = (f"{P * world} mixed-size pages per step over {world} GPU(s) (BASELINE.json configs[4]: long side logU[640, 4096] px, aspect U[.5, 1]; pool of {U} "
+              f"unique pages), sharded per image by LPT on H*W, {args.chunk} pages per run_pages call")
+    else:
+        wl = f"{P} pages {S}x{S} end-to-end det+cls+rec per GPU (BASELINE.json configs[3])"
+    config = {"workload": wl, "pages_per_gpu": P, "page_hw": "mixed" if mixed else [S, S], "unique_pages": U,
+              "input": JPEG_DESC["dri_mcu_row"] + "; `value` starts from the decoded pixels resident in HBM, `e2e` from the files in pinned host memory",
+              "forward": "replay worker (pre-resident prob maps / logits; DBNet/SVTR forwards stay on the inference runtime, out of the path); "
+                         "with_forward = torch stand-in networks executed on the context's tensors, then the same replay",
               "l2": "inputs larger than L2 (pages, prob maps and logits are distinct buffers, GBs per step)", "parallelism": f"page-sharded x{world}",
-              "pipeline": "device-resident batch = one unit on one stream; host-resident batch = units of 32 pages whose PCIe pull overlaps the kernels of earlier units"}
+              "pipeline": "device-resident batch = one unit on one stream; JPEG batch = files uploaded on a copy stream, units of 128 pages decoded and processed "
+                          "on the compute stream; raw-RGB batch = units of 32 pages whose PCIe pull overlaps the kernels of earlier units"}
 
     if args.impl == "reference":
-        # the reference's CPU path == the oracle port (Rust reference cannot be compiled in this image)
+        # the reference's CPU path == the oracle port (the Rust reference cannot be compiled in this image), one process per core,
+        # same workload: file bytes -> decode -> pipeline with the same replay statistics
         if rank != 0:
             return
-        pages, probs = make_workload(min(args.unique, 8), args.size)
-        n_sample = args.cpu_sample or 8 * max(cores, 8)   # ~1-2 s of wall clock per step on all cores
-        for _ in range(max(args.warmup, 1) if args.warmup else 0):
-            cpu_oracle_pages_per_s(pages, probs, min(n_sample, cores), dict_text, cores)
-        times = []
+        work = make_workload(args.workload, min(U, 64 if mixed else 32), S, 500 if mixed else 4, kinds)
+        arm = CpuArm(work, "dri_mcu_row", dict_text, cores)
+        n_sample = args.cpu_sample or (2 if mixed else 8) * max(cores, 8)   # ~1-2 s of wall clock per step on all cores
+        for _ in range(min(args.warmup, 1)):
+            arm.run(min(n_sample, cores))
+        tot = 0.0
         for _ in range(args.steps):
-            _, dt = cpu_oracle_pages_per_s(pages, probs, n_sample, dict_text, cores)
-            times.append(dt)
-        tot = sum(times)
+            dt, _ = arm.run(n_sample)
+            tot += dt
+        arm.close()
         val = n_sample * args.steps / tot
-        line = {"metric": "pages/sec det+cls+rec", "value": val, "unit": "pages/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC, "value": val, "unit": "pages/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32",
                 "data": "synthetic", "impl": "reference", "config": config,
-                "cpu_baseline": {"value": val, "unit": "pages/s", "cores": cores, "kind": "port",
-                                 "sample": f"{n_sample} pages {args.size}x{args.size} per step, oracle pipeline, {cores} threads"},
+                "cpu_baseline": {"value": val, "unit": "pages/s", "cores": cores, "kind": "port", "pages_per_s_per_core": val / cores,
+                                 "sample": f"{n_sample} pages of the workload per step: JPEG file -> libjpeg-turbo decode -> oracle pipeline, {cores} processes"},
                 "e2e": {"value": val, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -312,7 +444,6 @@ def main():
     dev = f"cuda:{local_rank}"
     numa_cores = 0
     if world > 1 and not os.environ.get("RETTO_B200_NO_NUMA_BIND"):
-        # rank-local NUMA placement of the pinned page buffers (allocated below): matters for e2e at N > 1 only
         from retto_b200.shard import bind_host_to_gpu
         pr = torch.cuda.get_device_properties(local_rank)
         try:
@@ -320,13 +451,17 @@ def main():
         except Exception:
             bus = None
         numa_cores = bind_host_to_gpu(local_rank, bus)
+    # the workload is generated BEFORE the process group exists (fork pool) and identically on every rank
+    work = make_workload(args.workload, U, S, 500 if mixed else 4 + 1000 * rank, kinds)
+    cpu_arm = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_arm = CpuArm(work, "dri_mcu_row", dict_text, cores)   # forked NOW, before this process creates its CUDA context; idle until the end
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL writes its version banner to stdout at communicator creation; keep stdout to the one JSON line
         sys.stdout.flush()
         saved = os.dup(1)
-        os.dup2(2, 1)
+        os.dup2(2, 1)   # NCCL writes its version banner to stdout at communicator creation; keep stdout to the one JSON line
         try:
             dist.init_process_group("nccl", device_id=torch.device(dev))
             dist.barrier()
@@ -335,36 +470,91 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    from retto_b200 import _lib
     from retto_b200._lib import Page, Results
     from retto_b200.api import Context
 
     ctx = Context(local_rank)
     ctx.dict_load(dict_text)
     L, H = ctx._L, ctx._h
-    P, S = args.pages, args.size
-    pages_np, probs_np = make_workload(min(args.unique, P), S, seed0=4 + 1000 * rank)
-    U = len(pages_np)
-    # distinct device + pinned-host buffers for every page of the batch
-    pages_dev = [torch.from_numpy(pages_np[i % U]).to(dev) for i in range(P)]
-    probs_dev = [torch.from_numpy(probs_np[i % U]).to(dev) for i in range(P)]
-    page_bytes = S * S * 3
-    hp = C.c_void_p()
-    ctx._check(L.retto_b200_host_alloc(H, page_bytes * P, C.byref(hp)))
-    host_all = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(P, S, S, 3))
-    for i in range(P):
-        host_all[i] = pages_np[i % U]
-    pg_dev = (Page * P)(*[Page(pages_dev[i].data_ptr(), S, S, 1) for i in range(P)])
-    pg_host = (Page * P)(*[Page(hp.value + i * page_bytes, S, S, 0) for i in range(P)])
+    if mixed:
+        from retto_b200.shard import shard_indices
+        glob = [work[i % U]["hw"][0] * work[i % U]["hw"][1] for i in range(P * world)]
+        mine = [i % U for i in shard_indices(glob, world)[rank]]
+    else:
+        mine = [i % U for i in range(P)]
+    NP = len(mine)
+    # device buffers: the decoded pixels and probability maps of the unique pages (mixed: shared by the pages that cycle the pool;
+    # pages1280: one distinct buffer per page of the batch)
+    if mixed:
+        rgb_u = [torch.from_numpy(w["rgb"]).to(dev) for w in work]
+        prob_u = [torch.from_numpy(w["prob"]).to(dev) for w in work]
+        pages_dev = [rgb_u[u] for u in mine]
+        probs_dev = [prob_u[u] for u in mine]
+    else:
+        pages_dev = [torch.from_numpy(work[u]["rgb"]).to(dev) for u in mine]
+        probs_dev = [torch.from_numpy(work[u]["prob"]).to(dev) for u in mine]
+    hw = [work[u]["hw"] for u in mine]
+
+    def pinned_arena(blobs):
+        """one pinned host allocation holding `blobs` (numpy u8 arrays) back to back, 64-byte aligned; returns (ptr, offsets, keepalive)"""
+        tot = sum((b.size + 63) & ~63 for b in blobs) + 64
+        hp = C.c_void_p()
+        ctx._check(L.retto_b200_host_alloc(H, tot, C.byref(hp)))
+        offs, o = [], 0
+        for b in blobs:
+            C.memmove(hp.value + o, b.ctypes.data, b.size)
+            offs.append(o)
+            o += (b.size + 63) & ~63
+        return hp, offs
+
+    arenas = []
+    page_lists = {}
+    page_lists["device"] = (Page * NP)(*[Page(pages_dev[i].data_ptr(), hw[i][0], hw[i][1], _lib.PAGE_DEVICE_RGB, 0) for i in range(NP)])
+    h2d = {"device": 0}
+    for kind in kinds:
+        if mixed:
+            ublobs = [np.frombuffer(w["files"][kind], np.uint8) for w in work]
+            hp, offs = pinned_arena(ublobs)
+            sel = [(hp.value + offs[u], ublobs[u].size) for u in mine]
+        else:
+            blobs = [np.frombuffer(work[u]["files"][kind], np.uint8) for u in mine]
+            hp, offs = pinned_arena(blobs)
+            sel = [(hp.value + offs[i], blobs[i].size) for i in range(NP)]
+        arenas.append(hp)
+        page_lists["jpeg_" + kind] = (Page * NP)(*[Page(p, 0, 0, _lib.PAGE_HOST_ENCODED, n) for p, n in sel])
+        h2d["jpeg_" + kind] = int(sum(n for _, n in sel))
+    if not mixed and not args.no_variants:
+        blobs = [work[u]["rgb"].reshape(-1) for u in mine]
+        hp, offs = pinned_arena(blobs)
+        arenas.append(hp)
+        page_lists["raw_rgb"] = (Page * NP)(*[Page(hp.value + offs[i], hw[i][0], hw[i][1], _lib.PAGE_HOST_RGB, 0) for i in range(NP)])
+        h2d["raw_rgb"] = int(sum(b.size for b in blobs))
     worker = ReplayWorker(torch, dev, probs_dev, seed=rank)
     res = Results()
     torch.cuda.synchronize()
+    chunk = args.chunk if mixed else NP
+    stats_acc = np.zeros(8, np.float64)
+    last = {"lines": 0, "text": 0}
 
-    def step(pg):
-        worker.begin_step()
-        st = L.retto_b200_run_pages(H, pg, P, worker.cb, None, C.byref(res))
-        if worker.err is not None:
-            raise worker.err
-        ctx._check(st)
+    def step(mode, w=None, collect=False):
+        w = w or worker
+        w.begin_step()
+        pg = page_lists[mode]
+        lines = text = 0
+        for p0 in range(0, NP, chunk):
+            n = min(chunk, NP - p0)
+            st = L.retto_b200_run_pages(H, C.cast(C.byref(pg, p0 * C.sizeof(Page)), C.POINTER(Page)), n, w.cb, None, C.byref(res))
+            if w.err is not None:
+                raise w.err
+            ctx._check(st)
+            lines += res.n_lines
+            text += int(res.text_offsets[res.n_lines]) if res.n_lines else 0
+            if collect:
+                st8 = (C.c_uint64 * 8)()
+                ctx._check(L.retto_b200_last_run_stats(H, st8))
+                stats_acc[:] += np.array(list(st8), np.float64)
+        last["lines"], last["text"] = lines, text
 
     stream = ctx.torch_stream()
 
@@ -374,13 +564,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(pg, steps):
+    def timed(mode, steps, w=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(steps):
-            step(pg)
+            step(mode, w)
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -392,109 +582,175 @@ def main():
         barrier()
         return ms, wall
 
-    for _ in range(max(args.warmup, 3)):
-        step(pg_dev)
-    n_lines = res.n_lines
-    text_bytes = int(res.text_offsets[n_lines]) if n_lines else 0
-    crop_px = 0  # filled from the library's crop table via the plan: approximate with det boxes' areas
-    for k in range(n_lines):
-        b = res.boxes[k].xy
-        w_ = max(np.hypot(b[0] - b[2], b[1] - b[3]), np.hypot(b[6] - b[4], b[7] - b[5]))
-        h_ = max(np.hypot(b[0] - b[6], b[1] - b[7]), np.hypot(b[2] - b[4], b[3] - b[5]))
-        crop_px += int(w_) * int(h_)
+    def warm(mode, n, w=None):
+        (w or worker).new_mode()
+        for _ in range(n):
+            step(mode, w)
 
+    W = max(args.warmup, 3)
+    K = args.steps
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- value: pages resident in HBM --------------------------------------------------------------------------
+    # ---- value: decoded pages resident in HBM --------------------------------------------------------------
+    warm("device", W)
     l0 = ctx.launch_count
-    ms_dev, wall_dev = timed(pg_dev, args.steps)
+    ms_dev, wall_dev = timed("device", K)
     launches = ctx.launch_count - l0
-    # ---- e2e: host pinned pages through the public call ---------------------------------------------------
-    for _ in range(2):
-        step(pg_host)
-    ms_e2e, wall_e2e = timed(pg_host, args.steps)
-    # ---- per-kernel pass: the same step as ONE unit on ONE stream (kernels back to back, nothing overlapping), every
-    # launch bracketed by CUDA events on that stream — the per-kernel durations the roofline figures are computed from
+    n_lines, text_bytes = last["lines"], last["text"]
+    # ---- e2e: page files in pinned host memory through the public call ---------------------------------------
+    warm("jpeg_dri_mcu_row", W)
+    l1 = ctx.launch_count
+    ms_e2e, wall_e2e = timed("jpeg_dri_mcu_row", K)
+    launches_e2e = ctx.launch_count - l1
+    d2h = int(n_lines * (36 + 8 + 4 + 4) + text_bytes + NP * 32)
+    variants = {}
+    Kv = max(3, K // 4)
+    for mode in [m for m in page_lists if m not in ("device", "jpeg_dri_mcu_row")]:
+        warm(mode, 3)
+        ms_v, _ = timed(mode, Kv)
+        variants[mode] = {"value": NP * world * Kv / (ms_v / 1000.0), "unit": "pages/s", "ms_per_step": ms_v / Kv, "h2d_bytes_per_step": h2d[mode], "steps": Kv,
+                          "input": JPEG_DESC.get(mode[5:], "decoded RGB pixels (HWC u8) in pinned host memory: round 1's e2e")}
+    # ---- per-kernel passes: the same steps with every launch bracketed by CUDA events on the launching stream ----
     ctx.set_pipeline(1, 1 << 20)
-    for _ in range(3):
-        step(pg_dev)
+    warm("device", 3)
     ctx.enable_kernel_timing(True)
     ctx.reset_kernel_times()
-    ms_serial, _ = timed(pg_dev, args.steps)
+    stats_acc[:] = 0
+    worker.begin_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step("device", collect=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_serial = e0.elapsed_time(e1)
     ktimes = ctx.kernel_times()
-    ctx.enable_kernel_timing(False)
     ctx.set_pipeline(0, 0)
+    warm("jpeg_dri_mcu_row", 2)
+    ctx.reset_kernel_times()
+    for _ in range(Kv):
+        step("jpeg_dri_mcu_row")
+    jtimes = {k: v for k, v in ctx.kernel_times().items() if k.startswith("jpeg")}
+    ctx.enable_kernel_timing(False)
     clocks = sampler.result()
 
-    total_pages = P * world * args.steps
+    # ---- with_forward: torch stand-in networks executed through the seam ---------
+    with_forward = None
+    if not args.no_forward and not mixed:
+        from retto_b200.standin import StandInNets
+        nets = StandInNets(torch, dev, C_CLASSES)
+        fworker = ReplayWorker(torch, dev, probs_dev, seed=rank, standin=nets)
+        Kf = 2
+        warm("jpeg_dri_mcu_row", 2, fworker)
+        fworker.forward_ms()
+        ms_f, _ = timed("jpeg_dri_mcu_row", Kf, fworker)
+        fms = fworker.forward_ms()
+        with_forward = {"value": NP * world * Kf / (ms_f / 1000.0), "unit": "pages/s", "ms_per_step": ms_f / Kf, "steps": Kf,
+                        "forward": "torch stand-in, executed: random-init conv nets of PP-OCRv4-mobile I/O shape (det [1,3,H,W]->[1,1,H,W] sigmoid, cls "
+                                   "[n,3,48,192]->[n,2] softmax, rec [n,3,48,W]->[n,W/8,6625] softmax), fp32/TF32, run on the context's own tensors "
+                                   "(zero-copy: data_ptr asserted equal, no D2D copy of inputs); their outputs are discarded and the replayed prob maps / "
+                                   "logits substituted so that the post-processing sees realistic work",
+                        "forward_ms_per_step": fms / Kf, "forward_share_of_step": (fms / Kf) / (ms_f / Kf), "tensors_checked_zero_copy": fworker.zero_copy_checked,
+                        "params": nets.n_params(), "input": "jpeg_dri_mcu_row (same as e2e)"}
+        del fworker, nets
+        torch.cuda.empty_cache()
+
+    total_pages = NP * world * K
     value = total_pages / (ms_dev / 1000.0)
     e2e_value = total_pages / (ms_e2e / 1000.0)
     peak, peak_src = peaks()
-    st8 = (C.c_uint64 * 8)()
-    ctx._check(L.retto_b200_last_run_stats(H, st8))
-    info = {"pages": P, "det_px": float(st8[2]), "crop_px": float(st8[3]), "cls_floats": float(st8[4]), "rec_floats": float(st8[5]), "rec_rows": float(st8[6])}
+    st = stats_acc / K
+    info = {"pages": NP, "det_px": st[2], "crop_px": st[3], "cls_floats": st[4], "rec_floats": st[5], "rec_rows": st[6],
+            "jpeg_px": float(sum(h * w for h, w in hw))}
     crop_px = info["crop_px"]
     kernels = {}
-    for name, (cnt, ms) in ktimes.items():
-        if cnt == 0:
-            continue
-        per = ms / cnt
-        ab = algorithmic_bytes(name, info)
-        kernels[name] = {"launches_per_step": cnt / args.steps, "ms_per_launch": per, "ms_per_step": ms / args.steps}
-        if ab:
-            kernels[name]["algorithmic_bytes"] = ab
-            kernels[name]["gbs"] = ab / (per * 1e-3) / 1e9
-            kernels[name]["frac_of_hbm_peak"] = kernels[name]["gbs"] / peak
-    top = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"])
-    top_name, top_k = top
-    # DRAM traffic of the same kernel on the same (deterministic) workload from the committed ncu --set full capture
+
+    def add_kernels(times, steps, tag=None):
+        for name, (cnt, ms) in times.items():
+            if cnt == 0:
+                continue
+            lps = cnt / steps
+            k = {"launches_per_step": lps, "ms_per_launch": ms / cnt, "ms_per_step": ms / steps}
+            if tag:
+                k["in"] = tag
+            ab = algorithmic_bytes(name, info)          # per STEP, all launches of this kernel together
+            if ab:
+                k["algorithmic_bytes"] = ab / lps       # per launch (average)
+                k["gbs"] = ab / (ms / steps * 1e-3) / 1e9
+                k["frac_of_hbm_peak"] = k["gbs"] / peak
+            kernels[name] = k
+
+    add_kernels({k: v for k, v in ktimes.items() if not k.startswith("jpeg")}, K)
+    add_kernels(jtimes, Kv, "e2e (JPEG) pass")
+    path_kernels = {k: v for k, v in kernels.items() if not k.startswith("jpeg")}
+    top_name, top_k = max(path_kernels.items(), key=lambda kv: kv[1]["ms_per_step"])
+    # DRAM traffic of the same kernel on the same (deterministic) workload: a COMMITTED ncu --set full capture (tools/final_profile.sh),
+    # not measured in this run — the file names the commit it was taken on
     traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if P == 256 and S == 1280:
-            for k, v in tj["kernels"].items():
-                if k.split("<")[0] == top_name.split("<")[0]:
-                    traffic, traffic_src = v["dram_bytes_per_launch"], "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
-                    break
-    except Exception:
-        pass
+    for fn in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
+            if NP == 256 and S == 1280 and not mixed:
+                for k, v in tj["kernels"].items():
+                    if k.split("<")[0] == top_name.split("<")[0]:
+                        traffic = v["dram_bytes_per_launch"]
+                        traffic_src = f"committed capture profiles/{fn} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum; taken on {tj.get('commit', 'an earlier tree')}), not re-measured in this run"
+                        break
+            if traffic is not None:
+                break
+        except Exception:
+            pass
     roofline = {"kernel": top_name, "bound": "hbm", "achieved": top_k.get("gbs"), "peak": peak, "unit": "GB/s",
                 "frac": (top_k["gbs"] / peak) if top_k.get("gbs") else None, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": top_k.get("algorithmic_bytes"), "peak_source": peak_src,
-                "ms_per_launch": top_k["ms_per_launch"], "share_of_step": top_k["ms_per_step"] / (ms_serial / args.steps),
+                "ms_per_launch": top_k["ms_per_launch"], "share_of_step": top_k["ms_per_step"] / (ms_serial / K),
                 "timed_in": "a repeat of the value pass with per-kernel CUDA events enabled (summary.serial_pass)",
                 "frac_of_nominal_8TBs": (top_k["gbs"] / 8000.0) if top_k.get("gbs") else None}
-    # the DB-postprocess unit (K2..K6) as SURVEY §8(d) defines it: 9*H*W bytes over the sum of its kernels
-    db_names = ["zero_counters", "bitmap_runs", "ccl_runs", "ccl_merge", "ccl_flatten", "comp_sort", "run_end", "row_alloc", "box_geometry", "page_sort", "pack_"]
-    db_ms = sum(v["ms_per_step"] for k, v in kernels.items() if any(k.startswith(n) for n in db_names))
-    path_bytes = (15.0 * info["det_px"] + 5.0 * info["det_px"] + 6.0 * crop_px + 2 * 3.0 * crop_px + 4.0 * (info["cls_floats"] + info["rec_floats"])
-                  + 4.0 * info["rec_rows"] * C_CLASSES)
-    summary = {"db_postprocess_unit": {"ms_per_step": db_ms, "algorithmic_bytes": 9.0 * info["det_px"],
-                                       "gbs": 9.0 * info["det_px"] / (db_ms * 1e-3) / 1e9 if db_ms else None,
-                                       "note": "SURVEY 8(d) unit: 9*H*W (prob read + bitmap + label plane); the run-table CCL moves 5*H*W — the label plane is only materialised on request"},
-               "whole_path": {"algorithmic_bytes_per_step": path_bytes, "gbs_at_value": path_bytes * (value / world / P) / 1e9,
-                              "kernel_ms_per_step": sum(v["ms_per_step"] for v in kernels.values()), "ms_per_step": ms_dev / args.steps},
-               "serial_pass": {"ms_per_step": ms_serial / args.steps, "pages_per_s": P * world * args.steps / (ms_serial / 1000.0),
+    db_names = ["zero_counters", "bitmap_runs", "ccl_runs", "ccl_merge", "ccl_flatten", "comp_sort", "run_end", "row_alloc", "box_geometry", "geom_merge", "page_sort", "pack_"]
+    db_ms = sum(v["ms_per_step"] for k, v in path_kernels.items() if any(k.startswith(n) for n in db_names))
+    cb_ms = sum(v["ms_per_step"] for k, v in path_kernels.items() if k.startswith("crop_") or k.startswith("build_batches"))
+    cb_bytes = 6.0 * crop_px + 2 * 3.0 * crop_px + 4.0 * (info["cls_floats"] + info["rec_floats"])
+    path_bytes = 15.0 * info["det_px"] + 5.0 * info["det_px"] + cb_bytes + 4.0 * info["rec_rows"] * C_CLASSES
+
+    def unit(ms, nbytes):
+        return {"ms_per_step": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9 if ms else None,
+                "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak if ms else None}
+
+    summary = {"db_postprocess_unit_moved_bytes": dict(unit(db_ms, 5.0 * info["det_px"]), note="K2..K6 + sort/pack over the bytes the path MOVES: 5*H*W (prob read + bitmap write)"),
+               "db_postprocess_unit_survey_bytes": dict(unit(db_ms, 9.0 * info["det_px"]), note="the same time over SURVEY 8(d)'s 9*H*W, which counts a label plane the run-table CCL never writes"),
+               "crop_batch_unit": dict(unit(cb_ms, cb_bytes), note="K7 + K8 (crop_* + both build_batches launches) over SURVEY 8(d)'s bytes: 6*crop px + per line 3*w*h + 12*48*img_w"),
+               "decode_unit": {"ms_per_step": sum(v["ms_per_step"] for k, v in kernels.items() if k.startswith("jpeg")), "encoded_bytes_per_step": h2d["jpeg_dri_mcu_row"],
+                               "decoded_bytes_per_step": 3.0 * info["jpeg_px"], "note": "K-J1..J4 in the e2e pass; the Huffman kernel is a latency-bound serial chain per restart interval"},
+               "whole_path": {"algorithmic_bytes_per_step": path_bytes, "gbs_at_value": path_bytes * (value / world / NP) / 1e9,
+                              "kernel_ms_per_step": sum(v["ms_per_step"] for v in path_kernels.values()), "ms_per_step": ms_dev / K},
+               "serial_pass": {"ms_per_step": ms_serial / K, "pages_per_s": NP * world * K / (ms_serial / 1000.0),
                                "what": "one unit of all pages on one stream, per-kernel CUDA events enabled"}}
 
-    line = {"metric": "pages/sec det+cls+rec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 (bytes, labels i32, boxes f64->f32)",
+    line = {"metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 (bytes, labels i32, boxes f64->f32)",
             "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": P * page_bytes,
-                    "d2h_bytes_per_step": int(n_lines * (36 + 8 + 4 + 4) + text_bytes + P * 32), "ms_per_step": ms_e2e / args.steps,
-                    "wall_ms_per_step": 1000.0 * wall_e2e / args.steps, "host_cores_bound_to_gpu_numa": numa_cores},
+            "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d["jpeg_dri_mcu_row"], "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+                    "wall_ms_per_step": 1000.0 * wall_e2e / K, "input": JPEG_DESC["dri_mcu_row"] + ", files in pinned host memory, decoded on the device",
+                    "gpu_launches": int(launches_e2e), "host_cores_bound_to_gpu_numa": numa_cores},
+            "e2e_variants": variants, "with_forward": with_forward,
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "summary": summary,
-            "lines_per_step": int(n_lines), "wall_ms_per_step": 1000.0 * wall_dev / args.steps}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_s = args.cpu_sample or 12 * max(cores, 8)
-        v, dt = cpu_oracle_pages_per_s(pages_np, probs_np, n_s, dict_text, cores)
-        line["cpu_baseline"] = {"value": v, "unit": "pages/s", "cores": cores, "kind": "port",
-                                "sample": f"{n_s} pages {S}x{S} of the same workload through the oracle pipeline on {cores} threads ({dt:.1f} s)"}
+            "lines_per_step": int(n_lines), "wall_ms_per_step": 1000.0 * wall_dev / K}
+    if cpu_arm is not None:
+        procs, arm = cores, cpu_arm
+        n_s = args.cpu_sample or (3 if mixed else 12) * max(cores, 8)
+        arm.run(procs)
+        dt, _ = arm.run(n_s)
+        arm.close()
+        v = n_s / dt
+        line["cpu_baseline"] = {"value": v, "unit": "pages/s", "cores": procs, "kind": "port", "pages_per_s_per_core": v / procs,
+                                "sample": f"{n_s} pages of the same workload: JPEG file -> libjpeg-turbo decode -> oracle pipeline, {procs} processes ({dt:.1f} s)"}
     else:
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line))
-    L.retto_b200_host_free(H, hp)
+    for hp in arenas:
+        L.retto_b200_host_free(H, hp)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RETTO_B200_ABI_VERSION 1
+#define RETTO_B200_ABI_VERSION 2
 
 typedef enum retto_b200_status {
     RETTO_B200_OK = 0,
@@ -39,7 +39,8 @@ typedef enum retto_b200_status {
     RETTO_B200_ERR_DEGENERATE_QUAD = 6, /* reference: draw_polygon_mut / from_control_points().unwrap() panic (det_processor.rs:209, image_helper.rs:237) */
     RETTO_B200_ERR_NO_DICT = 7,
     RETTO_B200_ERR_WORKER = 8,          /* forward callback failed */
-    RETTO_B200_ERR_UNSUPPORTED = 9
+    RETTO_B200_ERR_UNSUPPORTED = 9,
+    RETTO_B200_ERR_DECODE = 10          /* not an image / truncated or corrupt file (reference: ImageError from image::load_from_memory, error.rs:2-19) */
 } retto_b200_status;
 
 typedef struct retto_b200_ctx retto_b200_ctx;
@@ -105,6 +106,32 @@ retto_b200_status retto_b200_host_alloc(retto_b200_ctx* ctx, size_t bytes, void*
 retto_b200_status retto_b200_host_free(retto_b200_ctx* ctx, void* h_ptr);
 retto_b200_status retto_b200_h2d(retto_b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async */
 retto_b200_status retto_b200_d2h(retto_b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async */
+
+/* ---- image decode ------------------------------------------------------------------------------ */
+/* ImageHelper::new_from_raw_img_flow (image_helper.rs:34-44: image::load_from_memory(bytes).to_rgb8()) on the device, for the file
+ * kind that matters at scale: baseline JPEG (Huffman, 8 bit, YCbCr 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 or grayscale, interleaved scan).
+ * Pixels are bit-exact with libjpeg-turbo's default decode (integer "islow" IDCT, fancy up-sampling — what Pillow / OpenCV give).
+ * Restart intervals (DRI) are decoded in parallel, one GPU thread each; a file without DRI is one interval.
+ * Anything else (progressive / arithmetic / 12-bit JPEG, CMYK, PNG, ...) reports RETTO_B200_ERR_UNSUPPORTED — the caller decodes
+ * those on the host and passes RGB; a damaged file reports RETTO_B200_ERR_DECODE.  There is no silent CPU fallback. */
+typedef struct retto_b200_encoded {
+    const uint8_t* bytes;      /* host memory: the whole file */
+    uint64_t n_bytes;
+} retto_b200_encoded;
+typedef struct retto_b200_image_info_t {
+    int32_t h, w;
+    int32_t format;            /* 1 = baseline JPEG */
+    int32_t components;        /* 1 or 3 */
+    int32_t subsampling;       /* 0 = 4:4:4, 1 = 4:2:2, 2 = 4:2:0, 3 = grayscale, 4 = 4:4:0 */
+    int32_t restart_interval;  /* MCUs per restart interval, 0 = none */
+    int32_t status;            /* OK / ERR_UNSUPPORTED / ERR_DECODE */
+} retto_b200_image_info_t;
+/* header parse only (host, no context needed): the (h, w) a caller needs to size its buffers */
+retto_b200_status retto_b200_image_info(const uint8_t* bytes, uint64_t n_bytes, retto_b200_image_info_t* out);
+/* decode n files into caller-provided device buffers (d_out[i]: h*w*3 bytes HWC u8 RGB, sized from retto_b200_image_info).
+ * h_status[i] is per file; the call returns the last non-OK status (the other files are still decoded).  Synchronises. */
+retto_b200_status retto_b200_decode_images(retto_b200_ctx* ctx, const retto_b200_encoded* h_imgs, int32_t n, uint8_t* const* d_out,
+                                           int32_t* h_status);
 
 /* ---- resizes -------------------------------------------------------------------------------- */
 /* ImageHelper::resize_both size math (image_helper.rs:106-148). dims = up to 2 (h,w) pairs applied
@@ -267,10 +294,16 @@ typedef struct retto_b200_tensor {
 typedef int32_t (*retto_b200_forward_fn)(void* user, int32_t stage, int32_t n, const retto_b200_tensor* inputs,
                                          retto_b200_tensor* outputs, void* stream);
 
+#define RETTO_B200_PAGE_HOST_RGB 0      /* rgb = HWC u8 RGB in host memory (copied inside the call) */
+#define RETTO_B200_PAGE_DEVICE_RGB 1    /* rgb = HWC u8 RGB device pointer */
+#define RETTO_B200_PAGE_HOST_ENCODED 2  /* rgb = the image FILE bytes in host memory (n_bytes of them): RettoSession::run's own input
+                                           (session.rs:75-79, main.rs:83-84); decoded on the device (see "image decode" above);
+                                           h, w are ignored on input */
 typedef struct retto_b200_page {
-    const uint8_t* rgb;    /* HWC u8 RGB (decoded image, image_helper.rs:34-44 is out of scope) */
+    const uint8_t* rgb;
     int32_t h, w;
-    int32_t on_device;     /* 0: rgb is host memory (copied inside the call), 1: device pointer */
+    int32_t on_device;     /* one of RETTO_B200_PAGE_* */
+    uint64_t n_bytes;      /* HOST_ENCODED only */
 } retto_b200_page;
 
 /* RettoWorkerResult (session.rs:42-48) for a batch: box i of page p <-> cls i <-> rec i */

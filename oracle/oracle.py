@@ -28,7 +28,7 @@ def build(force: bool = False) -> str:
     def _stale(so, deps):
         return (not os.path.exists(so)) or any(os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in deps)
 
-    stale = _stale(_SO, (src,)) or _stale(_SHIM_SO, (shim_src, hdr))
+    stale = _stale(_SO, (src, os.path.join(_HERE, "jpeg_oracle.cpp"))) or _stale(_SHIM_SO, (shim_src, hdr))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -307,3 +307,21 @@ def rec_character(dict_text: str):
 
 def tokens_to_text(tokens_row, count, chars):
     return "".join(chars[t] for t in tokens_row[:count])
+
+
+def jpeg_decode(data: bytes) -> np.ndarray:
+    """libjpeg-turbo's default decode of a baseline JPEG (jpeg_oracle.cpp) -> HWC u8 RGB.  Raises ValueError(status) for files the
+    restatement does not cover (1 = not a JPEG / truncated, 2 = unsupported kind: progressive, CMYK, ...)."""
+    buf = np.frombuffer(data, np.uint8)
+    h, w = C.c_int(), C.c_int()
+    L = lib()
+    L.orc_jpeg_decode.restype = C.c_int
+    L.orc_jpeg_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    st = L.orc_jpeg_decode(buf.ctypes.data, len(buf), None, 0, C.byref(h), C.byref(w))
+    if st:
+        raise ValueError(st)
+    out = np.zeros((h.value, w.value, 3), np.uint8)
+    st = L.orc_jpeg_decode(buf.ctypes.data, len(buf), out.ctypes.data, out.size, C.byref(h), C.byref(w))
+    if st:
+        raise ValueError(st)
+    return out

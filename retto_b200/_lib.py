@@ -22,9 +22,11 @@ class RettoB200Error(RuntimeError):
 
 STATUS_NAMES = {
     0: "OK", 1: "ERR_INVALID_ARG", 2: "ERR_CUDA", 3: "ERR_OOM", 4: "ERR_CAPACITY", 5: "ERR_NAN_LOGITS",
-    6: "ERR_DEGENERATE_QUAD", 7: "ERR_NO_DICT", 8: "ERR_WORKER", 9: "ERR_UNSUPPORTED",
+    6: "ERR_DEGENERATE_QUAD", 7: "ERR_NO_DICT", 8: "ERR_WORKER", 9: "ERR_UNSUPPORTED", 10: "ERR_DECODE",
 }
-OK, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_CAPACITY, ERR_NAN_LOGITS, ERR_DEGENERATE_QUAD, ERR_NO_DICT, ERR_WORKER, ERR_UNSUPPORTED = range(10)
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_CAPACITY, ERR_NAN_LOGITS, ERR_DEGENERATE_QUAD, ERR_NO_DICT, ERR_WORKER, ERR_UNSUPPORTED, ERR_DECODE = range(11)
+ABI_VERSION = 2
+PAGE_HOST_RGB, PAGE_DEVICE_RGB, PAGE_HOST_ENCODED = 0, 1, 2
 
 
 class Config(C.Structure):
@@ -86,7 +88,16 @@ class Tensor(C.Structure):
 
 
 class Page(C.Structure):
-    _fields_ = [("rgb", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("on_device", C.c_int32)]
+    _fields_ = [("rgb", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("on_device", C.c_int32), ("n_bytes", C.c_uint64)]
+
+
+class Encoded(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64)]
+
+
+class ImageInfo(C.Structure):
+    _fields_ = [("h", C.c_int32), ("w", C.c_int32), ("format", C.c_int32), ("components", C.c_int32), ("subsampling", C.c_int32),
+                ("restart_interval", C.c_int32), ("status", C.c_int32)]
 
 
 class PageResult(C.Structure):
@@ -101,6 +112,15 @@ class Results(C.Structure):
     ]
 
 
+class StageResult(C.Structure):
+    _fields_ = [
+        ("stage", C.c_int32), ("first_page", C.c_int32), ("n_pages", C.c_int32), ("pages", C.POINTER(PageResult)), ("n_lines", C.c_int32),
+        ("boxes", C.POINTER(Box)), ("cls", C.POINTER(ClsResult)), ("text_offsets", C.POINTER(C.c_uint32)), ("text", C.POINTER(C.c_char)),
+        ("rec_scores", C.POINTER(C.c_float)),
+    ]
+
+
+STAGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(StageResult))
 FORWARD_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p)
 
 # every symbol include/retto_b200.h declares (tests/test_abi.py checks the .so exports all of them)
@@ -114,7 +134,7 @@ EXPORTS = [
     "retto_b200_det_post_fetch_trace", "retto_b200_scale_and_clip", "retto_b200_crop_boxes",
     "retto_b200_crop_fetch", "retto_b200_plan_batches", "retto_b200_build_batches", "retto_b200_cls_postprocess",
     "retto_b200_dict_load", "retto_b200_dict_size", "retto_b200_ctc_decode", "retto_b200_ctc_argmax", "retto_b200_run_pages", "retto_b200_last_run_stats",
-    "retto_b200_set_pipeline",
+    "retto_b200_set_pipeline", "retto_b200_set_stage_callback", "retto_b200_run_pages_multi", "retto_b200_image_info", "retto_b200_decode_images",
 ]
 
 
@@ -184,6 +204,10 @@ def lib() -> C.CDLL:
     L.retto_b200_last_run_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.retto_b200_set_pipeline.argtypes = [vp, i32, i32]
     L.retto_b200_run_pages.argtypes = [vp, C.POINTER(Page), i32, FORWARD_FN, vp, C.POINTER(Results)]
+    L.retto_b200_set_stage_callback.argtypes = [vp, STAGE_FN, vp]
+    L.retto_b200_run_pages_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(Page), i32, i32, FORWARD_FN, C.POINTER(vp), C.POINTER(Results)]
+    L.retto_b200_image_info.argtypes = [vp, u64, C.POINTER(ImageInfo)]
+    L.retto_b200_decode_images.argtypes = [vp, C.POINTER(Encoded), i32, C.POINTER(vp), C.POINTER(i32)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("retto_b200_abi_version", "retto_b200_dict_size"):

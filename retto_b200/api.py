@@ -38,6 +38,14 @@ def resize_either_plan(h: int, w: int, limit_type: int = 0, limit_len: int = 736
     return oh.value, ow.value
 
 
+def image_info(data: bytes) -> _lib.ImageInfo:
+    """header parse of an image file (host only): dims, sub-sampling, restart interval, status"""
+    buf = np.frombuffer(data, np.uint8)
+    info = _lib.ImageInfo()
+    _lib.lib().retto_b200_image_info(buf.ctypes.data, len(buf), C.byref(info))
+    return info
+
+
 @dataclass
 class DetPostOut:
     page_status: np.ndarray   # [n] int32
@@ -120,6 +128,30 @@ class Context:
             name, cnt, ms = ln.split("\t")
             out[name] = (int(cnt), float(ms))
         return out
+
+    # ---- image decode ---------------------------------------------------------------------------
+    def decode_images(self, files: Sequence[bytes]):
+        """ImageHelper::new_from_raw_img_flow (image_helper.rs:34-44) for baseline JPEG files on the device.
+        Returns (list of torch uint8 CUDA tensors [h,w,3] or None, list of statuses)."""
+        import torch
+        n = len(files)
+        bufs = [np.frombuffer(f, np.uint8) for f in files]
+        enc = (_lib.Encoded * max(n, 1))()
+        outs, ptrs = [], (C.c_void_p * max(n, 1))()
+        for i, b in enumerate(bufs):
+            enc[i] = _lib.Encoded(b.ctypes.data, len(b))
+            info = image_info(files[i])
+            if info.status == 0:
+                t = torch.empty((info.h, info.w, 3), dtype=torch.uint8, device=f"cuda:{self.device_id}")
+                outs.append(t)
+                ptrs[i] = t.data_ptr()
+            else:
+                outs.append(None)
+                ptrs[i] = None
+        torch.cuda.synchronize()
+        status = (C.c_int32 * max(n, 1))()
+        self._L.retto_b200_decode_images(self._h, enc, n, ptrs, status)
+        return outs, [int(status[i]) for i in range(n)]
 
     # ---- resizes ------------------------------------------------------------------------------
     def thumbnail(self, srcs: Sequence, out_dims: Sequence):

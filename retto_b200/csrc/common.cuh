@@ -127,6 +127,20 @@ struct LogitsRow {         // one (line) entry of a CTC batch
     const float* logits; int t; int out_base;  // out_base: first (line, t) slot in idx/prob arrays
 };
 
+struct JpegInfo {          // host: the parsed markers of one baseline JPEG file (jpeg_decode.cu)
+    int status;
+    int X, Y, nc;
+    int h[3], v[3], tq[3], td[3], ta[3];
+    int max_h, max_v, mcux, mcuy, ri, n_seg;
+    size_t ecs_off, ecs_len;   // entropy-coded data: offset in the file, bytes up to the end of the file
+    uint16_t qt[4][64];        // natural order
+    uint8_t qt_present[4];
+    struct Huff { uint8_t present; uint8_t bits[17]; uint8_t vals[256]; } dc[4], ac[4];
+};
+retto_b200_status rt_jpeg_parse(const uint8_t* d, size_t n, JpegInfo* out);
+struct retto_b200_ctx;
+retto_b200_status rt_jpeg_decode_enqueue(retto_b200_ctx* ctx, const JpegInfo* infos, const uint8_t* const* d_bytes, uint8_t* const* d_out, int n);
+
 struct retto_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -239,6 +253,11 @@ struct retto_b200_ctx {
     uint64_t dict_version = 0;
     // sizes of the last run_pages call (bench.py algorithmic bytes): pages, lines, det px, crop px, cls floats, rec floats, rec rows
     uint64_t run_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // image decode (jpeg_decode.cu)
+    DevBuf d_jpeg_blob, d_jpeg_desc, d_jpeg_seg, d_jpeg_coef, d_jpeg_planes;
+    int* jpeg_status_dev = nullptr;              // per-file device status of the last decode (inside d_jpeg_seg)
+    HostBuf h_jpeg_status;
+    std::vector<JpegInfo> jpeg_infos;            // parsed headers of the encoded pages of the current run_pages call
     // session scratch
     DevBuf d_pages_raw, d_pages_rs, d_det_in, d_pages_up;
     cudaStream_t copy_stream = nullptr;          // H2D of later chunks overlaps the kernels of earlier ones (run_pages)

@@ -1,0 +1,748 @@
+// jpeg_decode.cu — image decode on the device: ImageHelper::new_from_raw_img_flow
+// (retto-core/src/image_helper.rs:34-44: image::load_from_memory(..).to_rgb8()) for baseline JPEG files, the wire format of
+// retto-cli (retto-cli/src/main.rs:83-84 reads the file bytes and hands them to RettoSession::run).
+//
+// Why: a decoded 1280x1280 page is 4.9 MB, its JPEG ~0.2 MB.  With raw RGB pages the end-to-end path is PCIe-bound at ~10 k pages/s
+// per GPU and does not scale on a shared host; with file bytes on the wire the upload shrinks 20x and the pixels are
+// produced in HBM.  nvJPEG on this box: the hardware backend is unavailable (nvjpegCreateEx(HARDWARE) -> status 7) and the
+// GPU-hybrid backend decodes 3.0 k 1280^2 pages/s (profiles/r02_nvjpeg_probe.txt) — below the raw-RGB PCIe path — so the decoder
+// is hand-written:
+//   host  : marker parse only (tables, frame, scan header: a few hundred bytes per file) -> JpegInfo
+//   K-J1  jpeg_scan_kernel   : one block per file finds the RSTn markers of the entropy-coded segment (ordered compaction)
+//   K-J2  jpeg_huff_kernel   : one THREAD per restart interval — intervals are independently decodable (DC prediction resets,
+//                              byte-aligned) — 64-bit bit buffer refilled with aligned 32-bit loads (byte path only around 0xFF),
+//                              9-bit Huffman look-up tables built in shared memory; non-zero coefficients are scattered into a
+//                              pre-zeroed int16 coefficient plane (a file without DRI is one interval = one thread)
+//   K-J3  jpeg_idct_kernel   : 8 threads per 8x8 block: dequantise + libjpeg's jidctint "islow" integer IDCT (columns, then rows)
+//   K-J4  jpeg_color_kernel  : libjpeg's fancy (triangle) chroma up-sampling h2v1 / h2v2 / h1v2 + YCbCr->RGB fixed point -> HWC u8
+// Pixel policy: bit-exact with libjpeg-turbo's default decode (what Pillow / OpenCV produce); the oracle for this row is
+// oracle/jpeg_oracle.cpp, itself pinned against both libraries (tests/test_cpu_jpeg.py).  The reference's own decoder (zune-jpeg via
+// `image 0.25.6`) is an un-vendored dependency; JPEG decoders agree to +-1 LSB, not bit for bit — stated in DESIGN.md.
+// Unsupported (status RETTO_B200_ERR_UNSUPPORTED, never a silent fallback): progressive / arithmetic / lossless / 12-bit JPEG,
+// CMYK / RGB colour spaces, non-interleaved scans, sampling factors other than 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 / grayscale, PNG & co.
+#include "common.cuh"
+
+#define JPEG_ZZ {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63}
+static const uint8_t H_ZIGZAG[64] = JPEG_ZZ;
+__constant__ uint8_t D_ZIGZAG[64] = JPEG_ZZ;
+
+// ---- host: marker parse (jdmarker.c) ----------------------------------------------------------------------------------------
+retto_b200_status rt_jpeg_parse(const uint8_t* d, size_t n, JpegInfo* out) {
+    JpegInfo& J = *out;
+    memset(&J, 0, sizeof(J));
+    J.status = RETTO_B200_ERR_DECODE;
+    if (!d || n < 4 || d[0] != 0xFF || d[1] != 0xD8) { J.status = (d && n >= 8 && d[0] == 0x89 && d[1] == 'P') ? RETTO_B200_ERR_UNSUPPORTED : RETTO_B200_ERR_DECODE; return (retto_b200_status)J.status; }
+    bool sof = false, jfif = false, adobe = false;
+    int adobe_transform = -1;
+    int ids[3] = {0, 0, 0};
+    size_t pos = 2;
+    for (;;) {
+        if (pos + 4 > n || d[pos] != 0xFF) return RETTO_B200_ERR_DECODE;
+        while (pos < n && d[pos] == 0xFF) ++pos;
+        if (pos >= n) return RETTO_B200_ERR_DECODE;
+        const int m = d[pos++];
+        if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (m == 0xD9 || pos + 2 > n) return RETTO_B200_ERR_DECODE;
+        const size_t L = ((size_t)d[pos] << 8) | d[pos + 1];
+        if (L < 2 || pos + L > n) return RETTO_B200_ERR_DECODE;
+        const uint8_t* s = d + pos + 2;
+        const size_t sl = L - 2;
+        if (m == 0xDB) {
+            size_t i = 0;
+            while (i < sl) {
+                const int pq = s[i] >> 4, tq = s[i] & 15;
+                ++i;
+                if (tq > 3 || pq > 1 || i + (pq ? 128 : 64) > sl) return RETTO_B200_ERR_DECODE;
+                for (int k = 0; k < 64; ++k) {
+                    J.qt[tq][H_ZIGZAG[k]] = (uint16_t)(pq ? ((s[i] << 8) | s[i + 1]) : s[i]);
+                    i += pq ? 2 : 1;
+                }
+                J.qt_present[tq] = 1;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {
+            if (sl < 6) return RETTO_B200_ERR_DECODE;
+            if (s[0] != 8) { J.status = RETTO_B200_ERR_UNSUPPORTED; return RETTO_B200_ERR_UNSUPPORTED; }
+            J.Y = (s[1] << 8) | s[2]; J.X = (s[3] << 8) | s[4];
+            J.nc = s[5];
+            if (J.X <= 0 || J.Y <= 0) return RETTO_B200_ERR_DECODE;
+            if (J.nc != 1 && J.nc != 3) { J.status = RETTO_B200_ERR_UNSUPPORTED; return RETTO_B200_ERR_UNSUPPORTED; }
+            if (sl < (size_t)6 + 3 * J.nc) return RETTO_B200_ERR_DECODE;
+            for (int i = 0; i < J.nc; ++i) {
+                ids[i] = s[6 + 3 * i]; J.h[i] = s[7 + 3 * i] >> 4; J.v[i] = s[7 + 3 * i] & 15; J.tq[i] = s[8 + 3 * i];
+                if (J.h[i] < 1 || J.h[i] > 4 || J.v[i] < 1 || J.v[i] > 4 || J.tq[i] > 3) return RETTO_B200_ERR_DECODE;
+            }
+            sof = true;
+        } else if (m == 0xC4) {
+            size_t i = 0;
+            while (i < sl) {
+                const int tc = s[i] >> 4, th = s[i] & 15;
+                ++i;
+                if (tc > 1 || th > 3 || i + 16 > sl) return RETTO_B200_ERR_DECODE;
+                JpegInfo::Huff& t = tc ? J.ac[th] : J.dc[th];
+                int cnt = 0;
+                t.bits[0] = 0;
+                for (int k = 1; k <= 16; ++k) { t.bits[k] = s[i + k - 1]; cnt += t.bits[k]; }
+                i += 16;
+                if (cnt > 256 || i + cnt > sl) return RETTO_B200_ERR_DECODE;
+                memset(t.vals, 0, sizeof(t.vals));
+                memcpy(t.vals, s + i, cnt);
+                i += cnt;
+                t.present = 1;
+            }
+        } else if (m >= 0xC2 && m <= 0xCF) {   // progressive, lossless, differential, arithmetic (C4 / C0 / C1 handled above)
+            J.status = RETTO_B200_ERR_UNSUPPORTED;
+            return RETTO_B200_ERR_UNSUPPORTED;
+        } else if (m == 0xDD) {
+            if (sl < 2) return RETTO_B200_ERR_DECODE;
+            J.ri = (s[0] << 8) | s[1];
+        } else if (m == 0xE0) {
+            if (sl >= 5 && s[0] == 'J' && s[1] == 'F' && s[2] == 'I' && s[3] == 'F' && s[4] == 0) jfif = true;
+        } else if (m == 0xEE) {
+            if (sl >= 12 && s[0] == 'A' && s[1] == 'd' && s[2] == 'o' && s[3] == 'b' && s[4] == 'e') { adobe = true; adobe_transform = s[11]; }
+        } else if (m == 0xDA) {
+            if (!sof || sl < 1) return RETTO_B200_ERR_DECODE;
+            const int ns = s[0];
+            if (ns != J.nc) { J.status = RETTO_B200_ERR_UNSUPPORTED; return RETTO_B200_ERR_UNSUPPORTED; }   // non-interleaved scans
+            if (sl < (size_t)1 + 2 * ns + 3) return RETTO_B200_ERR_DECODE;
+            for (int i = 0; i < ns; ++i) {
+                if (s[1 + 2 * i] != ids[i]) { J.status = RETTO_B200_ERR_UNSUPPORTED; return RETTO_B200_ERR_UNSUPPORTED; }
+                J.td[i] = s[2 + 2 * i] >> 4; J.ta[i] = s[2 + 2 * i] & 15;
+                if (J.td[i] > 3 || J.ta[i] > 3) return RETTO_B200_ERR_DECODE;
+            }
+            pos += L;
+            break;
+        }
+        pos += L;
+    }
+    J.ecs_off = pos;
+    J.ecs_len = n - pos;
+    if (J.nc == 3) {   // jdapimin.c default_decompress_parms: JFIF -> YCbCr; Adobe transform 0 -> RGB; ids 'R','G','B' -> RGB
+        bool ycc = true;
+        if (!jfif) { if (adobe) ycc = adobe_transform != 0; else if (ids[0] == 'R' && ids[1] == 'G' && ids[2] == 'B') ycc = false; }
+        if (!ycc) { J.status = RETTO_B200_ERR_UNSUPPORTED; return RETTO_B200_ERR_UNSUPPORTED; }
+        if (J.h[1] != 1 || J.v[1] != 1 || J.h[2] != 1 || J.v[2] != 1 || J.h[0] > 2 || J.v[0] > 2) { J.status = RETTO_B200_ERR_UNSUPPORTED; return RETTO_B200_ERR_UNSUPPORTED; }
+    } else { J.h[0] = J.v[0] = 1; }   // a single-component scan is non-interleaved: one block per MCU whatever the frame header says
+    J.max_h = J.h[0]; J.max_v = J.v[0];
+    J.mcux = (J.X + 8 * J.max_h - 1) / (8 * J.max_h);
+    J.mcuy = (J.Y + 8 * J.max_v - 1) / (8 * J.max_v);
+    for (int i = 0; i < J.nc; ++i)
+        if (!J.qt_present[J.tq[i]] || !J.dc[J.td[i]].present || !J.ac[J.ta[i]].present) return RETTO_B200_ERR_DECODE;
+    const long long n_mcu = (long long)J.mcux * J.mcuy;
+    J.n_seg = J.ri > 0 ? (int)((n_mcu + J.ri - 1) / J.ri) : 1;
+    J.status = RETTO_B200_OK;
+    return RETTO_B200_OK;
+}
+
+extern "C" retto_b200_status retto_b200_image_info(const uint8_t* bytes, uint64_t n_bytes, retto_b200_image_info_t* out) {
+    if (!bytes || !out) return RETTO_B200_ERR_INVALID_ARG;
+    JpegInfo J;
+    const retto_b200_status s = rt_jpeg_parse(bytes, (size_t)n_bytes, &J);
+    memset(out, 0, sizeof(*out));
+    out->status = s;
+    if (s != RETTO_B200_OK) return s;
+    out->h = J.Y; out->w = J.X; out->format = 1; out->components = J.nc; out->restart_interval = J.ri;
+    out->subsampling = J.nc == 1 ? 3 : (J.max_h == 1 ? (J.max_v == 1 ? 0 : 4) : (J.max_v == 1 ? 1 : 2));
+    return RETTO_B200_OK;
+}
+
+// ---- device descriptors --------------------------------------------------------------------------------------------------------
+struct JpegComp {
+    int h, v, tq, td, ta;
+    int wb, hb;                   // blocks per row / column (whole MCUs)
+    int ds_w, ds_h;               // real (down-sampled) samples
+    unsigned coef_base;           // first 8x8 block of this component in the batch's coefficient array
+    unsigned long long plane_off; // byte offset of the component's sample plane (stride wb*8)
+};
+struct JpegDev {
+    const uint8_t* ecs;           // device pointer to the entropy-coded data
+    unsigned ecs_len;
+    int X, Y, nc, max_h, max_v, mcux, mcuy, ri, n_seg;
+    int seg_base;                 // first entry of this file in the segment-start table (n_seg entries)
+    int thread_base;              // first decode thread of this file (== seg_base)
+    unsigned block_base, n_blocks;   // 8x8 blocks of all components (IDCT work list)
+    JpegComp c[3];
+    uint8_t* out;                 // HWC u8 RGB
+    int status_slot;
+};
+struct JpegHuffRaw { uint8_t bits[17]; uint8_t pad[3]; uint8_t vals[256]; };   // 276 B
+struct JpegTables { uint16_t qt[4][64]; JpegHuffRaw dc[4], ac[4]; };
+
+// ---- K-J1: restart markers -----------------------------------------------------------------------------------------------------
+// seg[seg_base + j] = byte offset (in the entropy-coded data) at which restart interval j starts.  Inside the entropy-coded data
+// 0xFF is always followed by 0x00 (stuffing) or by a marker, so every "FF D0..D7" pair is an RSTn marker.
+__global__ void __launch_bounds__(256) jpeg_scan_kernel(const JpegDev* __restrict__ files, unsigned* __restrict__ seg, int* __restrict__ status) {
+    const JpegDev& f = files[blockIdx.x];
+    unsigned* sg = seg + f.seg_base;
+    const int n_seg = f.n_seg;
+    for (int j = threadIdx.x; j < n_seg; j += blockDim.x) sg[j] = j == 0 ? 0u : f.ecs_len;   // missing markers: empty intervals (zeros)
+    __syncthreads();
+    if (n_seg <= 1) return;
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const uint8_t* p = f.ecs;
+    const unsigned len = f.ecs_len;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (unsigned base = 0; base < len; base += 256 * 16) {
+        const unsigned o = base + threadIdx.x * 16;
+        // 17 bytes: 16 of this thread + the first of the next
+        unsigned char b[17];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) b[k] = (o + k < len) ? __ldg(p + o + k) : 0;
+        unsigned mask = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (b[k] == 0xFF && b[k + 1] >= 0xD0 && b[k + 1] <= 0xD7) mask |= 1u << k;
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        int before = s_base;
+        for (int k = 0; k < w; ++k) before += s_warp[k];
+        int idx = before + incl - cnt;
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            ++idx;   // marker number idx (1-based) starts interval idx
+            if (idx < n_seg) sg[idx] = o + k + 2;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_base = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && s_base != n_seg - 1) status[f.status_slot] = RETTO_B200_ERR_DECODE;   // marker count does not match DRI
+}
+
+// ---- K-J2: Huffman decode, one thread per restart interval ------------------------------------------------------------------------
+// The kernel is a set of long serial chains (one per interval; ~1 warp per scheduler), so what counts is the dependent latency and
+// the instruction count PER SYMBOL (ncu, first version: 10 cycles per issued instruction, 4.5 active lanes per instruction):
+//  * one flat loop over symbols — the lanes of a warp decode different intervals and must not sit in different loop nests;
+//  * 10-bit look-up tables whose entries also carry the EXTENDed coefficient when code + magnitude bits fit in the window
+//    (entry = total bits | run << 5 | size << 9 | fast << 13 | value << 16), so most symbols cost one shared-memory load;
+//  * the bit buffer is refilled 32 bits at a time from words loaded one refill AHEAD (the load latency is off the chain); words
+//    are read through an aligned-pair funnel shift so the stream may start at any byte; a word holding 0xFF (stuffing or the
+//    marker that ends the interval) takes a byte-wise slow path.
+#define JH_LUT_BITS 10
+struct HuffDev {               // shared memory, one per distinct table of the file
+    unsigned lut[1 << JH_LUT_BITS];
+    int maxcode[17];           // canonical code ranges for codes longer than the window
+    int valoff[17];            // valptr - mincode
+    unsigned char vals[256];
+};
+#define JH_THREADS 128
+__device__ __forceinline__ int jh_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+__device__ __forceinline__ unsigned jh_has_ff(unsigned w) { return __vcmpeq4(w, 0xFFFFFFFFu); }
+
+// Bit reader state lives in plain local variables of the kernel (a struct whose address escapes into a non-inlined call is
+// kept in local memory: LDL/STL on the per-symbol chain).  The byte-wise slow path returns its results by value.
+struct JhSlow { unsigned word, pos; int eof; };
+static __device__ __noinline__ JhSlow jh_slow_word(const uint8_t* base, unsigned len, unsigned pos, int eof) {
+    // 4 data bytes starting at pos: stuffed zeros skipped; a marker or the end of the data ends the interval (zeros from there on)
+    unsigned acc = 0;
+    for (int i = 0; i < 4; ++i) {
+        unsigned b = 0;
+        if (!eof && pos < len) {
+            b = __ldg(base + pos); ++pos;
+            if (b == 0xFF) {
+                if (pos < len && __ldg(base + pos) == 0) ++pos;
+                else { eof = 1; b = 0; }
+            }
+        } else eof = 1;
+        acc = (acc << 8) | b;
+    }
+    JhSlow r; r.word = acc; r.pos = pos; r.eof = eof;
+    return r;
+}
+// refill 32 bits into the MSB-aligned window `buf` holding n <= 32 valid bits
+#define JH_REFILL()                                                                                                     \
+    do {                                                                                                                \
+        const unsigned raw_ = __funnelshift_r(w_prev, w_cur, 8u * (pos & 3u));                                          \
+        unsigned w_;                                                                                                    \
+        if (!eof && jh_has_ff(raw_) == 0 && pos + 4 <= len) {                                                           \
+            w_ = __byte_perm(raw_, 0, 0x0123);                                                                          \
+            pos += 4;                                                                                                   \
+            w_prev = w_cur;                                                                                             \
+            w_cur = __ldg(reinterpret_cast<const unsigned*>(base + (pos & ~3u)) + 1);                                   \
+        } else if (eof) w_ = 0u;                                                                                        \
+        else {                                                                                                          \
+            const JhSlow sl_ = jh_slow_word(base, len, pos, eof);                                                       \
+            w_ = sl_.word; pos = sl_.pos; eof = sl_.eof;                                                                \
+            const unsigned* ap_ = reinterpret_cast<const unsigned*>(base + (pos & ~3u));                                \
+            w_prev = __ldg(ap_); w_cur = __ldg(ap_ + 1);                                                                \
+        }                                                                                                               \
+        buf |= (unsigned long long)w_ << (32 - n);                                                                      \
+        n += 32;                                                                                                        \
+    } while (0)
+
+__global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file,
+                                                              const int* __restrict__ block_first, const JpegTables* __restrict__ tables,
+                                                              const unsigned* __restrict__ seg, short* __restrict__ coef) {
+    __shared__ HuffDev s_tab[6];     // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
+    __shared__ unsigned char s_zz[64];
+    __shared__ int s_slot[6];
+    const int fi = block_file[blockIdx.x];
+    const JpegDev& f = files[fi];
+    const JpegTables& T = tables[fi];
+    if (threadIdx.x < 64) s_zz[threadIdx.x] = D_ZIGZAG[threadIdx.x];
+    // distinct tables -> shared memory (canonical codes, jdhuff.c jpeg_make_d_derived_tbl)
+    for (int t = 0; t < 2 * f.nc; ++t) {
+        const int ci = t >> 1, is_ac = t & 1;
+        const int id = is_ac ? f.c[ci].ta : f.c[ci].td;
+        int alias = -1;
+        for (int c2 = 0; c2 < ci; ++c2) if ((is_ac ? f.c[c2].ta : f.c[c2].td) == id) { alias = 2 * c2 + is_ac; break; }
+        if (threadIdx.x == 0) s_slot[t] = alias >= 0 ? alias : t;
+        if (alias >= 0) continue;   // block-uniform
+        const JpegHuffRaw& raw = is_ac ? T.ac[id] : T.dc[id];
+        HuffDev& H = s_tab[t];
+        if (threadIdx.x == 0) {
+            int code = 0, k = 0;
+            for (int l = 1; l <= 16; ++l) {
+                H.valoff[l] = k - code;
+                code += raw.bits[l];
+                k += raw.bits[l];
+                H.maxcode[l] = raw.bits[l] ? code - 1 : -1;
+                code <<= 1;
+            }
+            H.maxcode[0] = -1; H.valoff[0] = 0;
+        }
+        for (int i = threadIdx.x; i < 256; i += JH_THREADS) H.vals[i] = raw.vals[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < (1 << JH_LUT_BITS); i += JH_THREADS) {
+            unsigned e = 0;
+            for (int l = 1; l <= JH_LUT_BITS; ++l) {
+                const int code = i >> (JH_LUT_BITS - l);
+                if (code <= H.maxcode[l]) {
+                    const unsigned sym = H.vals[(H.valoff[l] + code) & 255];
+                    const unsigned r = is_ac ? sym >> 4 : 0u, sz = is_ac ? sym & 15u : sym & 15u;
+                    if (l + (int)sz <= JH_LUT_BITS) {
+                        const int bits = (i >> (JH_LUT_BITS - l - (int)sz)) & ((1 << sz) - 1);
+                        const int v = sz ? jh_extend(bits, (int)sz) : 0;
+                        e = (unsigned)(l + sz) | (r << 5) | (sz << 9) | (1u << 13) | ((unsigned)(v & 0xFFFF) << 16);
+                    } else e = (unsigned)l | (r << 5) | (sz << 9);
+                    break;
+                }
+            }
+            H.lut[i] = e;
+        }
+    }
+    __syncthreads();
+    const int j = block_first[blockIdx.x] + threadIdx.x;   // restart interval of this thread
+    if (j >= f.n_seg) return;
+    // positions are taken relative to the 4-byte-aligned address at or below the start of the data, so that word loads are aligned
+    const unsigned mis = (unsigned)((uintptr_t)f.ecs & 3u);
+    const uint8_t* base = f.ecs - mis;
+    const unsigned len = f.ecs_len + mis;
+    unsigned pos = min(seg[f.seg_base + j], f.ecs_len) + mis;
+    unsigned long long buf = 0;
+    int n = 0, eof = 0;
+    unsigned w_prev, w_cur;
+    { const unsigned* ap = reinterpret_cast<const unsigned*>(base + (pos & ~3u)); w_prev = __ldg(ap); w_cur = __ldg(ap + 1); }
+    JH_REFILL();
+    const long long n_mcu = (long long)f.mcux * f.mcuy;
+    long long m = f.ri > 0 ? (long long)j * f.ri : 0;
+    const long long m1 = f.ri > 0 ? min(m + f.ri, n_mcu) : n_mcu;
+    int my = (int)(m / f.mcux), mx = (int)(m - (long long)my * f.mcux);
+    const int nb0 = f.c[0].h * f.c[0].v, nb = f.nc == 1 ? 1 : nb0 + 2;   // blocks per MCU: luma blocks, then Cb, Cr
+    // per-component constants in registers
+    const int h0 = f.c[0].h, v0 = f.c[0].v;
+    // (three-way selects instead of arrays indexed by ci: a dynamically indexed array would live in local memory)
+    const int c1 = f.nc > 1 ? 1 : 0, c2 = f.nc > 2 ? 2 : 0;
+    const HuffDev* tdc0 = &s_tab[s_slot[0]];
+    const HuffDev* tac0 = &s_tab[s_slot[1]];
+    const HuffDev* tdc1 = &s_tab[s_slot[2 * c1]];
+    const HuffDev* tac1 = &s_tab[s_slot[2 * c1 + 1]];
+    const HuffDev* tdc2 = &s_tab[s_slot[2 * c2]];
+    const HuffDev* tac2 = &s_tab[s_slot[2 * c2 + 1]];
+    const unsigned cbase0 = f.c[0].coef_base, cbase1 = f.c[c1].coef_base, cbase2 = f.c[c2].coef_base;
+    const int cwb0 = f.c[0].wb, cwb1 = f.c[c1].wb, cwb2 = f.c[c2].wb;
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    int b = 0, k = 0, ci = 0;
+    short* blk = coef + ((size_t)cbase0 + (size_t)(my * v0) * cwb0 + mx * h0) * 64;
+    const HuffDev* tab = tdc0;
+    while (m < m1) {
+        if (n <= 32) JH_REFILL();
+        unsigned e = tab->lut[(unsigned)(buf >> (64 - JH_LUT_BITS))];
+        if ((e & 31u) == 0) {   // a code longer than the window: canonical search (rare)
+            const unsigned top = (unsigned)(buf >> 48);
+            unsigned sym = 0, l = 16;
+#pragma unroll 1
+            for (int q = JH_LUT_BITS + 1; q <= 16; ++q) {
+                const int code = (int)(top >> (16 - q));
+                if (code <= tab->maxcode[q]) { sym = tab->vals[(tab->valoff[q] + code) & 255]; l = q; break; }
+            }
+            e = k == 0 ? (l | ((sym & 15u) << 9)) : (l | ((sym >> 4) << 5) | ((sym & 15u) << 9));
+        }
+        const int L = (int)(e & 31u);
+        buf <<= L; n -= L;
+        const int r = (int)((e >> 5) & 15u), sz = (int)((e >> 9) & 15u);
+        int v = (int)e >> 16;
+        if (!(e & (1u << 13)) && sz) {   // magnitude bits outside the window
+            if (n < sz) JH_REFILL();
+            v = jh_extend((int)(buf >> (64 - sz)), sz);
+            buf <<= sz; n -= sz;
+        }
+        if (k == 0) {
+            int pv;
+            if (ci == 0) { pred0 += v; pv = pred0; } else if (ci == 1) { pred1 += v; pv = pred1; } else { pred2 += v; pv = pred2; }
+            if (pv) blk[0] = (short)pv;
+            k = 1;
+            tab = ci == 0 ? tac0 : (ci == 1 ? tac1 : tac2);
+        } else if (sz) {
+            k += r;
+            if (k < 64) blk[s_zz[k]] = (short)v;
+            ++k;
+        } else {
+            k = r == 15 ? k + 16 : 64;
+        }
+        if (k >= 64) {   // next block of the MCU / next MCU
+            k = 0;
+            if (++b == nb) { b = 0; ++m; if (++mx == f.mcux) { mx = 0; ++my; } }
+            ci = max(0, b - nb0 + 1);
+            const int bi = ci == 0 ? b : 0;
+            const int dy = h0 == 2 ? (bi >> 1) : bi, dx = h0 == 2 ? (bi & 1) : 0;
+            const int hh = ci == 0 ? h0 : 1, vv = ci == 0 ? v0 : 1;
+            const unsigned cb_ = ci == 0 ? cbase0 : (ci == 1 ? cbase1 : cbase2);
+            const int wb_ = ci == 0 ? cwb0 : (ci == 1 ? cwb1 : cwb2);
+            blk = coef + ((size_t)cb_ + (size_t)(my * vv + dy) * wb_ + (mx * hh + dx)) * 64;
+            tab = ci == 0 ? tdc0 : (ci == 1 ? tdc1 : tdc2);
+        }
+    }
+}
+
+// ---- K-J3: dequantise + jidctint.c jpeg_idct_islow ------------------------------------------------------------------------------
+#define JI_CONST_BITS 13
+#define JI_PASS1_BITS 2
+__device__ __forceinline__ int ji_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+__device__ __forceinline__ void ji_idct_1d(const int in[8], int out[8], int shift) {
+    int z2 = in[2], z3 = in[6];
+    int z1 = (z2 + z3) * 4433;
+    int tmp2 = z1 + z3 * (-15137);
+    int tmp3 = z1 + z2 * 6270;
+    z2 = in[0]; z3 = in[4];
+    int tmp0 = (z2 + z3) * (1 << JI_CONST_BITS);
+    int tmp1 = (z2 - z3) * (1 << JI_CONST_BITS);
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * 9633;
+    tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    out[0] = ji_descale(tmp10 + tmp3, shift); out[7] = ji_descale(tmp10 - tmp3, shift);
+    out[1] = ji_descale(tmp11 + tmp2, shift); out[6] = ji_descale(tmp11 - tmp2, shift);
+    out[2] = ji_descale(tmp12 + tmp1, shift); out[5] = ji_descale(tmp12 - tmp1, shift);
+    out[3] = ji_descale(tmp13 + tmp0, shift); out[4] = ji_descale(tmp13 - tmp0, shift);
+}
+__device__ __forceinline__ unsigned ji_range_limit(int x) {   // range_limit[x & RANGE_MASK] of libjpeg's post-IDCT table (jdmaster.c)
+    const int i = x & 1023;
+    return i < 128 ? 128u + i : (i < 512 ? 255u : (i < 896 ? 0u : (unsigned)(i - 896)));
+}
+// 256 threads = 32 blocks of 8x8; thread (g, t): row t of the coefficient load, column t of pass 1, row t of pass 2
+__global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDev* __restrict__ files, const JpegTables* __restrict__ tables,
+                                                        const short* __restrict__ coef, unsigned char* __restrict__ planes) {
+    __shared__ short s_coef[32][72];
+    __shared__ int s_ws[32][72];
+    const int g = threadIdx.x >> 3, t = threadIdx.x & 7;
+    const int fi = blockIdx.y;                       // grid: (32-block groups of the largest file, files)
+    const JpegDev& f = files[fi];
+    const unsigned lb = blockIdx.x * 32u + g;        // block index inside the file
+    const bool live = lb < f.n_blocks;
+    const unsigned B = f.block_base + lb;
+    int ci = 0;
+    unsigned local = 0;
+    if (live) {
+        while (ci + 1 < f.nc && B >= f.c[ci + 1].coef_base) ++ci;
+        local = B - f.c[ci].coef_base;
+        *reinterpret_cast<uint4*>(&s_coef[g][t * 8]) = __ldg(reinterpret_cast<const uint4*>(coef + (size_t)B * 64 + t * 8));
+    }
+    __syncwarp();
+    if (live) {
+        const unsigned short* q = tables[fi].qt[f.c[ci].tq];
+        int in[8], o[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = (int)s_coef[g][r * 8 + t] * (int)__ldg(q + r * 8 + t);
+        ji_idct_1d(in, o, JI_CONST_BITS - JI_PASS1_BITS);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s_ws[g][r * 8 + t] = o[r];
+    }
+    __syncwarp();
+    if (live) {
+        const JpegComp& c = f.c[ci];
+        int in[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) in[k] = s_ws[g][t * 8 + k];
+        ji_idct_1d(in, o, JI_CONST_BITS + JI_PASS1_BITS + 3);
+        const unsigned lo4 = ji_range_limit(o[0]) | (ji_range_limit(o[1]) << 8) | (ji_range_limit(o[2]) << 16) | (ji_range_limit(o[3]) << 24);
+        const unsigned hi4 = ji_range_limit(o[4]) | (ji_range_limit(o[5]) << 8) | (ji_range_limit(o[6]) << 16) | (ji_range_limit(o[7]) << 24);
+        const unsigned by = local / (unsigned)c.wb, bx = local - by * (unsigned)c.wb;
+        unsigned char* dst = planes + c.plane_off + ((size_t)by * 8 + t) * ((size_t)c.wb * 8) + (size_t)bx * 8;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(lo4, hi4);
+    }
+}
+
+// ---- K-J4: jdsample.c fancy up-sampling + jdcolor.c YCbCr -> RGB -------------------------------------------------------------------
+// One block = 1024 pixels of one output row of one file (grid: x chunks, rows, files; blocks outside a file's extent exit), one
+// thread = 8 consecutive pixels: Y as one aligned 8-byte load, chroma as aligned words plus the two neighbour columns the triangle
+// filter needs (libjpeg's edge rules are exactly "clamp the neighbour index": (3c + c + 8) >> 4 == (4c + 8) >> 4).  The 24 output
+// bytes per thread are staged in shared memory and leave as coalesced 32-bit stores whatever the alignment of the row.
+#define JC_PX 8
+#define JC_THREADS 256   // upper bound; the launch uses the smallest multiple of 32 threads that covers the widest row (<= 2048 px per block)
+__device__ __forceinline__ void jc_chroma8(const unsigned char* __restrict__ pl, int stride, int w, int h, int hs, int vs, int x0, int y, int out[8]) {
+    if (hs == 1) {
+        const int r = vs == 2 ? (y >> 1) : y;
+        const unsigned char* a = pl + (size_t)r * stride + x0;
+        const uint2 va = __ldg(reinterpret_cast<const uint2*>(a));
+        if (vs == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = (int)(((k < 4 ? va.x : va.y) >> (8 * (k & 3))) & 0xFFu);
+            return;
+        }
+        const int lower = y & 1;
+        const int r1 = lower ? min(r + 1, h - 1) : max(r - 1, 0);
+        const uint2 vb = __ldg(reinterpret_cast<const uint2*>(pl + (size_t)r1 * stride + x0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int n0 = (int)(((k < 4 ? va.x : va.y) >> (8 * (k & 3))) & 0xFFu), n1 = (int)(((k < 4 ? vb.x : vb.y) >> (8 * (k & 3))) & 0xFFu);
+            out[k] = (n0 * 3 + n1 + (lower ? 2 : 1)) >> 2;
+        }
+        return;
+    }
+    // hs == 2: chroma columns i0 .. i0+3 cover the 8 pixels; neighbours i0-1 and i0+4 clamped into [0, w-1]
+    const int i0 = x0 >> 1;
+    const int r = vs == 2 ? (y >> 1) : y;
+    const unsigned char* a = pl + (size_t)r * stride;
+    const unsigned wa = __ldg(reinterpret_cast<const unsigned*>(a + i0));
+    const int il = max(i0 - 1, 0), ir = min(i0 + 4, w - 1);
+    int c[6];
+    if (vs == 1) {
+        c[0] = __ldg(a + il); c[5] = __ldg(a + ir);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[1 + k] = (int)((wa >> (8 * k)) & 0xFFu);
+        if (w <= 2) {   // h2v1_upsample: replication
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = c[1 + (k >> 1)];
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k;
+            const int prev = i == 0 ? c[1 + k] : c[k], next = i >= w - 1 ? c[1 + k] : c[2 + k];
+            out[2 * k] = (c[1 + k] * 3 + prev + 1) >> 2;
+            out[2 * k + 1] = (c[1 + k] * 3 + next + 2) >> 2;
+        }
+        return;
+    }
+    const int lower = y & 1;
+    const int r1 = lower ? min(r + 1, h - 1) : max(r - 1, 0);
+    const unsigned char* b = pl + (size_t)r1 * stride;
+    const unsigned wb = __ldg(reinterpret_cast<const unsigned*>(b + i0));
+    if (w <= 2) {       // h2v2_upsample: replication
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = (int)((wa >> (8 * (k >> 1))) & 0xFFu);
+        return;
+    }
+    c[0] = __ldg(a + il) * 3 + __ldg(b + il);
+    c[5] = __ldg(a + ir) * 3 + __ldg(b + ir);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[1 + k] = (int)((wa >> (8 * k)) & 0xFFu) * 3 + (int)((wb >> (8 * k)) & 0xFFu);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        const int prev = i == 0 ? c[1 + k] : c[k], next = i >= w - 1 ? c[1 + k] : c[2 + k];
+        out[2 * k] = (c[1 + k] * 3 + prev + 8) >> 4;
+        out[2 * k + 1] = (c[1 + k] * 3 + next + 7) >> 4;
+    }
+}
+__global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* __restrict__ files, const unsigned char* __restrict__ planes) {
+    __shared__ unsigned s_rgb[JC_THREADS * 6 + 1];
+    const JpegDev& f = files[blockIdx.z];
+    const int y = blockIdx.y, xb = blockIdx.x * (blockDim.x * JC_PX);
+    if (y >= f.Y || xb >= f.X) return;
+    const int x0 = xb + threadIdx.x * JC_PX;
+    // the sample planes are padded to whole blocks (stride wb*8 >= X rounded up to 8), so a thread with x0 < X may read its 8 samples
+    if (x0 < f.X) {
+        const uint2 yv = __ldg(reinterpret_cast<const uint2*>(planes + f.c[0].plane_off + (size_t)y * ((size_t)f.c[0].wb * 8) + x0));
+        unsigned char o[24];
+        if (f.nc == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const unsigned v = ((k < 4 ? yv.x : yv.y) >> (8 * (k & 3))) & 0xFFu; o[3 * k] = o[3 * k + 1] = o[3 * k + 2] = (unsigned char)v; }
+        } else {
+            const int hs = f.max_h / f.c[1].h, vs = f.max_v / f.c[1].v;
+            int cb[8], cr[8];
+            jc_chroma8(planes + f.c[1].plane_off, f.c[1].wb * 8, f.c[1].ds_w, f.c[1].ds_h, hs, vs, x0, y, cb);
+            jc_chroma8(planes + f.c[2].plane_off, f.c[2].wb * 8, f.c[2].ds_w, f.c[2].ds_h, hs, vs, x0, y, cr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int yy = (int)(((k < 4 ? yv.x : yv.y) >> (8 * (k & 3))) & 0xFFu);
+                const int u = cb[k] - 128, v = cr[k] - 128;
+                const int r = yy + ((91881 * v + 32768) >> 16);
+                const int g = yy + ((-22554 * u + 32768 - 46802 * v) >> 16);
+                const int b = yy + ((116130 * u + 32768) >> 16);
+                o[3 * k] = (unsigned char)min(max(r, 0), 255); o[3 * k + 1] = (unsigned char)min(max(g, 0), 255); o[3 * k + 2] = (unsigned char)min(max(b, 0), 255);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_rgb[threadIdx.x * 6 + k] = o[4 * k] | (o[4 * k + 1] << 8) | (o[4 * k + 2] << 16) | ((unsigned)o[4 * k + 3] << 24);
+    }
+    __syncthreads();
+    const int npx = min((int)blockDim.x * JC_PX, f.X - xb);
+    const int nbytes = 3 * npx;
+    unsigned char* gp = f.out + ((size_t)y * f.X + xb) * 3;
+    const int head = min((int)((4u - ((unsigned)(uintptr_t)gp & 3u)) & 3u), nbytes);
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(s_rgb);
+    if ((int)threadIdx.x < head) gp[threadIdx.x] = sb[threadIdx.x];
+    const int nw = (nbytes - head) >> 2;
+    unsigned* gw = reinterpret_cast<unsigned*>(gp + head);
+    const unsigned sh = 8u * (unsigned)(head & 3);
+    for (int wi = threadIdx.x; wi < nw; wi += blockDim.x) {
+        const int so = (head + 4 * wi) >> 2;
+        gw[wi] = __funnelshift_r(s_rgb[so], s_rgb[so + 1], sh);
+    }
+    const int tail0 = head + 4 * nw;
+    if ((int)threadIdx.x < nbytes - tail0) gp[tail0 + threadIdx.x] = sb[tail0 + threadIdx.x];
+}
+
+// ---- host: enqueue the decode of n parsed files ------------------------------------------------------------------------------------
+// d_bytes[i]: device pointer to file i (the whole file; the entropy-coded data starts at infos[i].ecs_off), d_out[i]: HWC u8 RGB
+// of infos[i].Y x infos[i].X.  Everything is enqueued on the context's stream; d_status (n ints, device) receives a non-zero
+// status for files whose restart markers do not match their DRI header.
+retto_b200_status rt_jpeg_decode_enqueue(retto_b200_ctx* ctx, const JpegInfo* infos, const uint8_t* const* d_bytes, uint8_t* const* d_out, int n) {
+    if (n <= 0) return RETTO_B200_OK;
+    cudaStream_t st = ctx->stream;
+    // layout
+    const size_t desc_bytes = (sizeof(JpegDev) * (size_t)n + 15) & ~size_t(15);
+    const size_t pfx_blocks_bytes = (sizeof(unsigned) * ((size_t)n + 1) + 15) & ~size_t(15);
+    const size_t pfx_px_bytes = (sizeof(unsigned long long) * ((size_t)n + 1) + 15) & ~size_t(15);
+    long long total_seg = 0;
+    size_t n_tblocks = 0;
+    for (int i = 0; i < n; ++i) { total_seg += infos[i].n_seg; n_tblocks += ((size_t)infos[i].n_seg + JH_THREADS - 1) / JH_THREADS; }
+    if (total_seg > 0x3fffffffLL) { ctx->set_error("jpeg decode: too many restart intervals"); return RETTO_B200_ERR_CAPACITY; }
+    const size_t tb_bytes = (sizeof(int) * 2 * n_tblocks + 15) & ~size_t(15);
+    const size_t head_bytes = desc_bytes + pfx_blocks_bytes + pfx_px_bytes + tb_bytes;
+    const size_t tab_bytes = sizeof(JpegTables) * (size_t)n;
+    int slot = -1;
+    void* sp = nullptr;
+    RT_TRY(rt_stage_begin(ctx, head_bytes + tab_bytes, &slot, &sp));
+    char* hp = reinterpret_cast<char*>(sp);
+    JpegDev* hd = reinterpret_cast<JpegDev*>(hp);
+    unsigned* h_bpfx = reinterpret_cast<unsigned*>(hp + desc_bytes);
+    unsigned long long* h_ppfx = reinterpret_cast<unsigned long long*>(hp + desc_bytes + pfx_blocks_bytes);
+    int* h_tb_file = reinterpret_cast<int*>(hp + desc_bytes + pfx_blocks_bytes + pfx_px_bytes);
+    int* h_tb_first = h_tb_file + n_tblocks;
+    JpegTables* h_tab = reinterpret_cast<JpegTables*>(hp + head_bytes);
+    unsigned long long blocks = 0, plane_bytes = 0, px = 0;
+    int seg_base = 0, max_x = 1, max_y = 1;
+    unsigned max_file_blocks = 1;
+    size_t tb = 0;
+    for (int i = 0; i < n; ++i) {
+        const JpegInfo& J = infos[i];
+        JpegDev& D = hd[i];
+        memset(&D, 0, sizeof(D));
+        if (J.status != RETTO_B200_OK || J.ecs_len > 0xfffffff0u) { ctx->stage_slots[slot].busy = false; ctx->set_error("jpeg decode: file " + std::to_string(i) + " was not parsed"); return RETTO_B200_ERR_INVALID_ARG; }
+        D.ecs = d_bytes[i] + J.ecs_off; D.ecs_len = (unsigned)J.ecs_len;
+        max_x = std::max(max_x, J.X); max_y = std::max(max_y, J.Y);
+        D.X = J.X; D.Y = J.Y; D.nc = J.nc; D.max_h = J.max_h; D.max_v = J.max_v; D.mcux = J.mcux; D.mcuy = J.mcuy; D.ri = J.ri; D.n_seg = J.n_seg;
+        D.seg_base = seg_base; D.thread_base = seg_base; D.status_slot = i;
+        D.block_base = (unsigned)blocks;
+        h_bpfx[i] = (unsigned)blocks;
+        for (int c = 0; c < J.nc; ++c) {
+            JpegComp& C = D.c[c];
+            C.h = J.h[c]; C.v = J.v[c]; C.tq = J.tq[c]; C.td = J.td[c]; C.ta = J.ta[c];
+            C.wb = J.mcux * J.h[c]; C.hb = J.mcuy * J.v[c];
+            C.ds_w = (J.X * J.h[c] + J.max_h - 1) / J.max_h; C.ds_h = (J.Y * J.v[c] + J.max_v - 1) / J.max_v;
+            C.coef_base = (unsigned)blocks;
+            C.plane_off = plane_bytes;
+            blocks += (unsigned long long)C.wb * C.hb;
+            plane_bytes += ((unsigned long long)C.wb * C.hb * 64 + 15) & ~15ULL;
+        }
+        if (blocks > 0x7fffffffULL) { ctx->stage_slots[slot].busy = false; ctx->set_error("jpeg decode: batch too large (coefficient blocks)"); return RETTO_B200_ERR_CAPACITY; }
+        D.n_blocks = (unsigned)blocks - D.block_base;
+        max_file_blocks = std::max(max_file_blocks, D.n_blocks);
+        D.out = d_out[i];
+        h_ppfx[i] = px;
+        px += (unsigned long long)J.X * J.Y;
+        for (int j0 = 0; j0 < J.n_seg; j0 += JH_THREADS) { h_tb_file[tb] = i; h_tb_first[tb] = j0; ++tb; }
+        seg_base += J.n_seg;
+        for (int k = 0; k < 4; ++k) {
+            memcpy(h_tab[i].qt[k], J.qt[k], sizeof(J.qt[k]));
+            memcpy(h_tab[i].dc[k].bits, J.dc[k].bits, 17); memcpy(h_tab[i].dc[k].vals, J.dc[k].vals, 256);
+            memcpy(h_tab[i].ac[k].bits, J.ac[k].bits, 17); memcpy(h_tab[i].ac[k].vals, J.ac[k].vals, 256);
+        }
+    }
+    h_bpfx[n] = (unsigned)blocks;
+    h_ppfx[n] = px;
+    RT_TRY(rt_stage_commit(ctx, ctx->d_jpeg_desc, slot, head_bytes + tab_bytes));
+    const char* dp = ctx->d_jpeg_desc.as<char>();
+    const JpegDev* d_files = reinterpret_cast<const JpegDev*>(dp);
+    const unsigned* d_bpfx = reinterpret_cast<const unsigned*>(dp + desc_bytes);
+    const unsigned long long* d_ppfx = reinterpret_cast<const unsigned long long*>(dp + desc_bytes + pfx_blocks_bytes);
+    const int* d_tb_file = reinterpret_cast<const int*>(dp + desc_bytes + pfx_blocks_bytes + pfx_px_bytes);
+    const int* d_tb_first = d_tb_file + n_tblocks;
+    const JpegTables* d_tab = reinterpret_cast<const JpegTables*>(dp + head_bytes);
+    RT_CUDA_OK(ctx, ctx->d_jpeg_seg.ensure(sizeof(unsigned) * (size_t)std::max(seg_base, 1) + sizeof(int) * (size_t)n, st));
+    RT_CUDA_OK(ctx, ctx->d_jpeg_coef.ensure((size_t)blocks * 128, st));
+    RT_CUDA_OK(ctx, ctx->d_jpeg_planes.ensure((size_t)plane_bytes, st));
+    unsigned* d_seg = ctx->d_jpeg_seg.as<unsigned>();
+    int* d_status = reinterpret_cast<int*>(d_seg + std::max(seg_base, 1));
+    ctx->jpeg_status_dev = d_status;
+    RT_CUDA_OK(ctx, cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)n, st));
+    RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_jpeg_coef.p, 0, (size_t)blocks * 128, st));
+    RT_LAUNCH_BEGIN(ctx, "jpeg_scan_kernel");
+    jpeg_scan_kernel<<<n, 256, 0, st>>>(d_files, d_seg, d_status);
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "jpeg_huff_kernel");
+    jpeg_huff_kernel<<<(unsigned)n_tblocks, JH_THREADS, 0, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg, ctx->d_jpeg_coef.as<short>());
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "jpeg_idct_kernel");
+    jpeg_idct_kernel<<<dim3((max_file_blocks + 31) / 32, (unsigned)n), 256, 0, st>>>(d_files, d_tab, ctx->d_jpeg_coef.as<short>(),
+                                                                                    ctx->d_jpeg_planes.as<unsigned char>());
+    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(ctx, "jpeg_color_kernel");
+    const int jc_threads = std::min(JC_THREADS, ((max_x + JC_PX - 1) / JC_PX + 31) / 32 * 32);
+    jpeg_color_kernel<<<dim3((unsigned)((max_x + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)max_y, (unsigned)n), jc_threads, 0, st>>>(d_files, ctx->d_jpeg_planes.as<unsigned char>());
+    RT_LAUNCH_CHECK(ctx);
+    return RETTO_B200_OK;
+}
+
+// ImageHelper::new_from_raw_img_flow for a batch of files: upload, decode, per-file status
+extern "C" retto_b200_status retto_b200_decode_images(retto_b200_ctx* ctx, const retto_b200_encoded* h_imgs, int32_t n, uint8_t* const* d_out,
+                                                      int32_t* h_status) {
+    RtDeviceGuard _dg(ctx);
+    if (!ctx || n < 0 || (n > 0 && (!h_imgs || !d_out || !h_status))) return RETTO_B200_ERR_INVALID_ARG;
+    if (n == 0) return RETTO_B200_OK;
+    std::vector<JpegInfo> infos(n);
+    std::vector<int> ok;
+    size_t blob = 0;
+    for (int i = 0; i < n; ++i) {
+        h_status[i] = rt_jpeg_parse(h_imgs[i].bytes, (size_t)h_imgs[i].n_bytes, &infos[i]);
+        if (h_status[i] == RETTO_B200_OK) { ok.push_back(i); blob += ((size_t)h_imgs[i].n_bytes + 15 + 16) & ~size_t(15); }
+    }
+    retto_b200_status ret = RETTO_B200_OK;
+    for (int i = 0; i < n; ++i) if (h_status[i] != RETTO_B200_OK) { ret = (retto_b200_status)h_status[i]; ctx->set_error("decode_images: file " + std::to_string(i) + " is not a supported baseline JPEG"); }
+    if (ok.empty()) return ret;
+    cudaStream_t st = ctx->stream;
+    RT_CUDA_OK(ctx, ctx->d_jpeg_blob.ensure(blob + 16, st));
+    std::vector<JpegInfo> sel(ok.size());
+    std::vector<const uint8_t*> db(ok.size());
+    std::vector<uint8_t*> dout(ok.size());
+    size_t off = 0;
+    for (size_t k = 0; k < ok.size(); ++k) {
+        const int i = ok[k];
+        uint8_t* d = ctx->d_jpeg_blob.as<uint8_t>() + off;
+        RT_CUDA_OK(ctx, cudaMemcpyAsync(d, h_imgs[i].bytes, (size_t)h_imgs[i].n_bytes, cudaMemcpyHostToDevice, st));
+        off += ((size_t)h_imgs[i].n_bytes + 15 + 16) & ~size_t(15);
+        sel[k] = infos[i]; db[k] = d; dout[k] = d_out[i];
+        if (!d_out[i]) { ctx->set_error("decode_images: null output"); return RETTO_B200_ERR_INVALID_ARG; }
+    }
+    RT_TRY(rt_jpeg_decode_enqueue(ctx, sel.data(), db.data(), dout.data(), (int)ok.size()));
+    std::vector<int> dev_status(ok.size());
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(dev_status.data(), ctx->jpeg_status_dev, sizeof(int) * ok.size(), cudaMemcpyDeviceToHost, st));
+    RT_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    for (size_t k = 0; k < ok.size(); ++k)
+        if (dev_status[k] != 0) { h_status[ok[k]] = dev_status[k]; ret = (retto_b200_status)dev_status[k]; ctx->set_error("decode_images: restart markers of file " + std::to_string(ok[k]) + " do not match its DRI header"); }
+    return ret;
+}

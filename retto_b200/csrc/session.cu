@@ -42,6 +42,7 @@ retto_b200_status rt_ctc_end(retto_b200_ctx* ctx, uint32_t* h_text_offsets, char
 #include <memory>
 #include <thread>
 #define RUN_CHUNK_PAGES_MAX 64
+#define PAGE_DEVICE_ENCODED 3   // internal: rgb = device copy of the file bytes, (h, w) from the parsed header
 static int env_int(const char* name, int dflt, int lo, int hi) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
@@ -86,6 +87,19 @@ struct PageRun {
     retto_b200_stage_fn stage_cb = nullptr; // RettoWorkerStageResult delivery (session.rs:98,101,104), optional
     void* stage_user = nullptr;
     int first_page = 0;                     // index of this unit's first page in the caller's page array
+    const JpegInfo* jinfo = nullptr;        // encoded pages: parsed headers, aligned with h_pages (the file bytes are already on the device)
+    int n_encoded = 0;
+    std::vector<int> enc_page;              // page index of every decoded file of this unit
+    // restart markers that do not match the DRI header are only seen by the device: per-file status, read after a stream sync
+    void check_decode_status() {
+        const int* hs = ctx->h_jpeg_status.as<int>();
+        for (int k = 0; k < n_encoded; ++k)
+            if (hs[k] != 0) {
+                ctx->r_pages[enc_page[k]].status = hs[k];
+                ret = (retto_b200_status)hs[k];
+                ctx->set_error("run_pages: page " + std::to_string(first_page + enc_page[k]) + ": restart markers do not match the DRI header (damaged JPEG)");
+            }
+    }
     cudaEvent_t wait_for = nullptr;         // pages uploaded by the copy stream (chunked host batches)
     bool done = false;                      // finished early (no pages / no lines / error)
     retto_b200_status ret = RETTO_B200_OK;
@@ -140,7 +154,7 @@ retto_b200_status PageRun::begin() {
         const retto_b200_page& p = h_pages[i];
         if (!p.rgb || p.h <= 0 || p.w <= 0) { ctx->set_error("run_pages: bad page " + std::to_string(i)); return fail(RETTO_B200_ERR_INVALID_ARG); }
         ps[i].ori_h = p.h; ps[i].ori_w = p.w;
-        if (!p.on_device) raw_bytes += align256((size_t)p.h * p.w * 3);
+        if (p.on_device == RETTO_B200_PAGE_HOST_RGB || p.on_device == PAGE_DEVICE_ENCODED) raw_bytes += align256((size_t)p.h * p.w * 3);
         int dims[4], ns = 0;
         RT_TRY(retto_b200_resize_both_plan(p.h, p.w, cfg.max_side_len, cfg.min_side_len, dims, &ns));
         int h = p.h, w = p.w;
@@ -165,13 +179,21 @@ retto_b200_status PageRun::begin() {
     {
         size_t off = 0, roff = 0;
         std::vector<retto_b200_resize_desc> step1, step2;
+        std::vector<JpegInfo> enc_info;
+        std::vector<const uint8_t*> enc_src;
+        std::vector<uint8_t*> enc_dst;
         for (int i = 0; i < n_pages; ++i) {
             const retto_b200_page& p = h_pages[i];
             const uint8_t* cur = p.rgb;
-            if (!p.on_device) {
+            if (p.on_device == RETTO_B200_PAGE_HOST_RGB) {
                 uint8_t* d = ctx->d_pages_raw.as<uint8_t>() + off;
                 RT_CUDA_OK(ctx, cudaMemcpyAsync(d, p.rgb, (size_t)p.h * p.w * 3, cudaMemcpyHostToDevice, st));
                 off += align256((size_t)p.h * p.w * 3);
+                cur = d;
+            } else if (p.on_device == PAGE_DEVICE_ENCODED) {   // image_helper.rs:34-44 on the device: the decoded page lands in the raw-page arena
+                uint8_t* d = ctx->d_pages_raw.as<uint8_t>() + off;
+                off += align256((size_t)p.h * p.w * 3);
+                enc_info.push_back(jinfo[i]); enc_src.push_back(p.rgb); enc_dst.push_back(d); enc_page.push_back(i);
                 cur = d;
             }
             int ch = p.h, cw = p.w;
@@ -182,6 +204,13 @@ retto_b200_status PageRun::begin() {
                 cur = d; ch = rs_steps[i][s].first; cw = rs_steps[i][s].second;
             }
             ps[i].d_img = cur;
+        }
+        n_encoded = (int)enc_info.size();
+        if (n_encoded) {
+            retto_b200_status js = rt_jpeg_decode_enqueue(ctx, enc_info.data(), enc_src.data(), enc_dst.data(), n_encoded);
+            if (js != RETTO_B200_OK) return fail(js);
+            RT_CUDA_OK(ctx, ctx->h_jpeg_status.ensure(sizeof(int) * (size_t)n_encoded));
+            RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_jpeg_status.p, ctx->jpeg_status_dev, sizeof(int) * (size_t)n_encoded, cudaMemcpyDeviceToHost, st));
         }
         if (!step1.empty()) RT_TRY(retto_b200_thumbnail(ctx, step1.data(), (int)step1.size()));
         if (!step2.empty()) RT_TRY(retto_b200_thumbnail(ctx, step2.data(), (int)step2.size()));
@@ -287,6 +316,7 @@ retto_b200_status PageRun::mid() {
     ctx->r_text_offs.assign(n_lines + 1, 0);
     if (n_lines == 0) {   // no detections: cls / rec run zero batches and return empty results (App. A #20); the three stages still report
         done = true;
+        check_decode_status();
         emit_stage(0); emit_stage(1); emit_stage(2);
         return ret;
     }
@@ -435,6 +465,7 @@ retto_b200_status PageRun::finish() {
         ctx->r_scores[dst] = sc[k];
     }
     tr.mark("collect");
+    check_decode_status();
     emit_stage(2);   // session.rs:104
     return ret;
 }
@@ -498,7 +529,7 @@ static retto_b200_status lane_ctx(retto_b200_ctx* ctx, int lane, retto_b200_ctx*
     return RETTO_B200_OK;
 }
 
-struct Unit { const retto_b200_page* pages; int n; cudaEvent_t wait_for; int first_page; };
+struct Unit { const retto_b200_page* pages; int n; cudaEvent_t wait_for; int first_page; const JpegInfo* jinfo; };
 
 // Software pipeline over the units, two in flight: finish(u[k-2]) -> begin(u[k]) -> mid(u[k-1]).  Unit k runs on lane
 // k % 2, which unit k-2 has just left.  With one lane the units run back to back.
@@ -540,7 +571,7 @@ static retto_b200_status run_units(retto_b200_ctx* ctx, const std::vector<Unit>&
         runs[k].reset(new PageRun());
         PageRun& r = *runs[k];
         r.ctx = lane[k % n_lanes]; r.h_pages = units[k].pages; r.n_pages = units[k].n; r.forward = forward; r.user = user; r.wait_for = units[k].wait_for;
-        r.stage_cb = ctx->stage_cb; r.stage_user = ctx->stage_user; r.first_page = units[k].first_page;
+        r.stage_cb = ctx->stage_cb; r.stage_user = ctx->stage_user; r.first_page = units[k].first_page; r.jinfo = units[k].jinfo;
         return r.begin();
     };
     if (n_lanes == 1) {
@@ -597,6 +628,55 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     // pages by the copy engine (55 GB/s measured) with the descriptor tables of the compute stream pulled by the SMs, or
     // pages pulled by pull_pages_kernel (48 GB/s) with ordinary descriptor copies
     static const int USE_DMA = env_int("RETTO_B200_PULL_DMA", 1, 0, 1);
+    // ---- encoded pages (file bytes): parse the headers here, upload the files on the copy stream, decode per unit on the device
+    {
+        int n_enc = 0;
+        for (int i = 0; i < n_pages; ++i) n_enc += h_pages[i].on_device == RETTO_B200_PAGE_HOST_ENCODED;
+        if (n_enc > 0) {
+            if (n_enc != n_pages) { ctx->set_error("run_pages: encoded and decoded pages cannot be mixed in one call"); return RETTO_B200_ERR_INVALID_ARG; }
+            std::vector<JpegInfo>& infos = ctx->jpeg_infos;
+            infos.resize(n_pages);
+            size_t blob = 0;
+            for (int i = 0; i < n_pages; ++i) {
+                const retto_b200_status s = h_pages[i].rgb ? rt_jpeg_parse(h_pages[i].rgb, (size_t)h_pages[i].n_bytes, &infos[i]) : RETTO_B200_ERR_INVALID_ARG;
+                if (s != RETTO_B200_OK) {
+                    ctx->set_error("run_pages: page " + std::to_string(i) + (s == RETTO_B200_ERR_UNSUPPORTED ? ": not a baseline JPEG this decoder covers (decode it on the host and pass RGB)" : ": damaged or unknown image file"));
+                    return s;
+                }
+                blob += ((size_t)h_pages[i].n_bytes + 31) & ~size_t(15);
+            }
+            const int unit = ctx->pipe_unit_pages > 0 ? ctx->pipe_unit_pages : env_int("RETTO_B200_ENC_UNIT_PAGES", 128, 1, 1 << 20);
+            if (!ctx->copy_stream) {
+                int lo = 0, hi = 0;
+                cudaDeviceGetStreamPriorityRange(&lo, &hi);
+                RT_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi));
+            }
+            const int n_units = (n_pages + unit - 1) / unit;
+            while ((int)ctx->copy_events.size() < n_units) {
+                cudaEvent_t e;
+                RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->copy_events.push_back(e);
+            }
+            RT_CUDA_OK(ctx, ctx->d_jpeg_blob.ensure(blob + 16, ctx->stream));
+            std::vector<retto_b200_page> dev_pages(n_pages);
+            size_t off = 0;
+            uint64_t enc_bytes = 0;
+            for (int i = 0; i < n_pages; ++i) {
+                uint8_t* d = ctx->d_jpeg_blob.as<uint8_t>() + off;
+                off += ((size_t)h_pages[i].n_bytes + 31) & ~size_t(15);
+                enc_bytes += h_pages[i].n_bytes;
+                RT_CUDA_OK(ctx, cudaMemcpyAsync(d, h_pages[i].rgb, (size_t)h_pages[i].n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                dev_pages[i] = retto_b200_page{d, infos[i].Y, infos[i].X, PAGE_DEVICE_ENCODED, h_pages[i].n_bytes};
+                if ((i + 1) % unit == 0 || i + 1 == n_pages) RT_CUDA_OK(ctx, cudaEventRecord(ctx->copy_events[i / unit], ctx->copy_stream));
+            }
+            std::vector<Unit> units;
+            for (int u = 0; u < n_units; ++u) units.push_back(Unit{dev_pages.data() + u * unit, std::min(unit, n_pages - u * unit), ctx->copy_events[u], u * unit, infos.data() + u * unit});
+            const retto_b200_status ret = run_units(ctx, units, n_lanes, forward, user, out);
+            ctx->run_stats[7] = enc_bytes;
+            cudaStreamSynchronize(ctx->copy_stream);
+            return ret;
+        }
+    }
     bool all_host = n_pages > RUN_CHUNK_PAGES, all_dev = true;
     for (int i = 0; i < n_pages; ++i) {
         if (h_pages[i].on_device || !h_pages[i].rgb || h_pages[i].h <= 0 || h_pages[i].w <= 0) all_host = false;
@@ -606,7 +686,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     if (!all_host) {
         // one unit, or (device-resident pages, two lanes) units of unit_dev pages
         const int up = (all_dev && n_lanes > 1 && n_pages > unit_dev) ? unit_dev : std::max(n_pages, 1);
-        for (int p0 = 0; p0 < std::max(n_pages, 1); p0 += up) units.push_back(Unit{h_pages + p0, std::min(up, n_pages - p0), nullptr, p0});
+        for (int p0 = 0; p0 < std::max(n_pages, 1); p0 += up) units.push_back(Unit{h_pages + p0, std::min(up, n_pages - p0), nullptr, p0, nullptr});
         return run_units(ctx, units, n_lanes, forward, user, out);
     }
     if (!ctx->copy_stream) {
@@ -660,7 +740,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
     }
     for (int c = 0; c < n_chunks; ++c) {
         const int p0 = c * RUN_CHUNK_PAGES;
-        units.push_back(Unit{dev_pages.data() + p0, std::min(RUN_CHUNK_PAGES, n_pages - p0), ctx->copy_events[c], p0});
+        units.push_back(Unit{dev_pages.data() + p0, std::min(RUN_CHUNK_PAGES, n_pages - p0), ctx->copy_events[c], p0, nullptr});
     }
     const bool by_sm = USE_DMA != 0;
     ctx->uploads_by_sm = by_sm;
@@ -720,7 +800,7 @@ extern "C" retto_b200_status retto_b200_run_pages_multi(retto_b200_ctx* const* c
         for (int j = 0; j < i; ++j) if (ctxs[j] == ctxs[i]) { c0->set_error("run_pages_multi: a context is listed twice"); return RETTO_B200_ERR_INVALID_ARG; }
     }
     for (int i = 0; i < n_pages; ++i)
-        if (h_pages[i].on_device) { c0->set_error("run_pages_multi: pages must be host-resident (a device pointer belongs to one GPU)"); return RETTO_B200_ERR_INVALID_ARG; }
+        if (h_pages[i].on_device == RETTO_B200_PAGE_DEVICE_RGB) { c0->set_error("run_pages_multi: pages must be host-resident (a device pointer belongs to one GPU)"); return RETTO_B200_ERR_INVALID_ARG; }
     std::vector<int> order(n_pages);
     for (int i = 0; i < n_pages; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {

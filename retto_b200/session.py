@@ -17,7 +17,7 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import FORWARD_FN, Page, Results, RettoB200Error, Tensor
+from ._lib import FORWARD_FN, STAGE_FN, Page, Results, RettoB200Error, StageResult, Tensor
 from .api import Context, default_config
 
 
@@ -225,27 +225,28 @@ class RettoSession:
             self._err = e
             return 1
 
-    def run_pages(self, images: Sequence, on_device: bool = False) -> List[RettoWorkerResult]:
-        """process_pipeline for a batch of pages.  images: HWC u8 numpy arrays (host) or torch CUDA tensors."""
+    def _pages(self, images: Sequence, on_device: bool):
+        """retto_b200_page array for a list of pages: HWC u8 numpy arrays (host RGB), torch CUDA tensors (on_device) or `bytes`
+        objects = the image FILE as RettoSession::run receives it (session.rs:75-79), decoded on the device"""
         n = len(images)
         pages = (Page * max(n, 1))()
         hold = []
         for i, im in enumerate(images):
-            if on_device:
+            if isinstance(im, (bytes, bytearray, memoryview)):
+                a = np.frombuffer(im, np.uint8)
+                hold.append(a)
+                pages[i] = Page(a.ctypes.data, 0, 0, _lib.PAGE_HOST_ENCODED, len(a))
+            elif on_device:
                 assert im.is_cuda and im.is_contiguous()
-                pages[i] = Page(im.data_ptr(), im.shape[0], im.shape[1], 1)
+                pages[i] = Page(im.data_ptr(), im.shape[0], im.shape[1], _lib.PAGE_DEVICE_RGB, 0)
             else:
                 a = np.ascontiguousarray(im, dtype=np.uint8)
                 hold.append(a)
-                pages[i] = Page(a.ctypes.data, a.shape[0], a.shape[1], 0)
-        res = Results()
-        self._keep = {}
-        self._err = None
-        st = self.ctx._L.retto_b200_run_pages(self.ctx.handle, pages, n, self._cb, None, C.byref(res))
-        if self._err is not None:
-            raise self._err
-        if st not in (_lib.OK, _lib.ERR_DEGENERATE_QUAD, _lib.ERR_CAPACITY) or (st != _lib.OK and res.n_pages == 0):
-            self.ctx._check(st)
+                pages[i] = Page(a.ctypes.data, a.shape[0], a.shape[1], _lib.PAGE_HOST_RGB, 0)
+        return pages, hold
+
+    @staticmethod
+    def _collect(res, n) -> List[RettoWorkerResult]:
         out = []
         text = C.string_at(res.text, res.text_offsets[res.n_lines]) if res.n_lines else b""
         for p in range(n):
@@ -259,13 +260,80 @@ class RettoSession:
             out.append(RettoWorkerResult(det, cls, rec, pr.status))
         return out
 
+    def run_pages(self, images: Sequence, on_device: bool = False) -> List[RettoWorkerResult]:
+        """process_pipeline for a batch of pages (see _pages for the accepted page kinds)."""
+        n = len(images)
+        pages, hold = self._pages(images, on_device)
+        res = Results()
+        self._keep = {}
+        self._err = None
+        st = self.ctx._L.retto_b200_run_pages(self.ctx.handle, pages, n, self._cb, None, C.byref(res))
+        if self._err is not None:
+            raise self._err
+        if st not in (_lib.OK, _lib.ERR_DEGENERATE_QUAD, _lib.ERR_CAPACITY) or (st != _lib.OK and res.n_pages == 0):
+            self.ctx._check(st)
+        del hold
+        return self._collect(res, n)
+
     def run(self, image) -> RettoWorkerResult:
-        """RettoSession::run (session.rs:108-131)"""
+        """RettoSession::run (session.rs:108-131); `image` may be the file bytes (the reference's own input) or decoded RGB"""
         return self.run_pages([image])[0]
 
     def run_stream(self, image, sender: Callable):
-        """RettoSession::run_stream (session.rs:133-143): stage results in order Det -> Cls -> Rec"""
-        r = self.run(image)
-        sender(("Det", r.det_result))
-        sender(("Cls", r.cls_result))
-        sender(("Rec", r.rec_result))
+        """RettoSession::run_stream (session.rs:133-143): each stage result is sent as soon as it exists — Det before the cls forward
+        runs, Cls before the rec forward, Rec at the end — through retto_b200_set_stage_callback."""
+        err = []
+
+        def on_stage(user, rp):
+            try:
+                r = rp.contents
+                if r.n_pages < 1:
+                    return
+                pr = r.pages[0]
+                rng = range(pr.first_line, pr.first_line + pr.n_lines)
+                if r.stage == 0:
+                    sender(("Det", [DetProcessorInnerResult(np.array(r.boxes[k].xy[:], np.float32).reshape(4, 2), float(np.float32(r.boxes[k].score))) for k in rng]))
+                elif r.stage == 1:
+                    sender(("Cls", [ClsPostProcessLabel(int(r.cls[k].label), float(np.float32(r.cls[k].score))) for k in rng]))
+                else:
+                    text = C.string_at(r.text, r.text_offsets[r.n_lines]) if r.n_lines else b""
+                    sender(("Rec", [RecProcessorSingleResult(text[r.text_offsets[k]:r.text_offsets[k + 1]].decode("utf-8"), float(np.float32(r.rec_scores[k]))) for k in rng]))
+            except Exception as e:  # noqa
+                err.append(e)
+
+        cb = STAGE_FN(on_stage)
+        self.ctx._check(self.ctx._L.retto_b200_set_stage_callback(self.ctx.handle, cb, None))
+        try:
+            self.run(image)
+        finally:
+            self.ctx._L.retto_b200_set_stage_callback(self.ctx.handle, C.cast(None, STAGE_FN), None)
+        if err:
+            raise err[0]
+
+
+def run_pages_multi(sessions: Sequence[RettoSession], images: Sequence, chunk_pages: int = 0) -> List[RettoWorkerResult]:
+    """One batch over several sessions — one per GPU of the box (retto_b200_run_pages_multi): pages are sharded per image, the
+    sessions' host threads pull LPT-sorted chunks from a shared cursor, results come back in page order.  Every session's worker is
+    called from its own thread."""
+    n_ctx, n = len(sessions), len(images)
+    s0 = sessions[0]
+    pages, hold = s0._pages(images, False)
+    ctxs = (C.c_void_p * n_ctx)(*[s.ctx.handle for s in sessions])
+    handles = {int(s.ctx.handle.value): s for s in sessions}
+    for s in sessions:
+        s._keep, s._err = {}, None
+
+    def fwd(user, stage, k, inputs, outputs, stream):
+        return handles[int(user)]._forward(None, stage, k, inputs, outputs, stream)
+
+    cb = FORWARD_FN(fwd)
+    users = (C.c_void_p * n_ctx)(*[s.ctx.handle for s in sessions])
+    res = Results()
+    st = s0.ctx._L.retto_b200_run_pages_multi(ctxs, n_ctx, pages, n, int(chunk_pages), cb, users, C.byref(res))
+    for s in sessions:
+        if s._err is not None:
+            raise s._err
+    if st not in (_lib.OK, _lib.ERR_DEGENERATE_QUAD, _lib.ERR_CAPACITY) or (st != _lib.OK and res.n_pages == 0):
+        s0.ctx._check(st)
+    del hold
+    return RettoSession._collect(res, n)

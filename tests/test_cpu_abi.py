@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert L.retto_b200_abi_version() == 1
+    assert L.retto_b200_abi_version() == 2
 
 
 def test_config_defaults_match_reference():

@@ -1,0 +1,219 @@
+"""GPU parity of the device image decode (csrc/jpeg_decode.cu) and of the entry points built on it:
+decoded pixels bit-exact vs the oracle AND vs Pillow (libjpeg-turbo); RettoSession.run on file bytes == run on decoded RGB;
+per-stage callbacks fire in the reference's order; run_pages_multi == run_pages."""
+import io
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _enc(a, **kw):
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(a).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+def _pil(data):
+    from PIL import Image
+    return np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+
+
+def test_decode_matrix(ctx):
+    """sub-samplings x qualities x {no DRI, optimised tables, restart per MCU row, restart every 3 MCUs} x odd sizes, one batch"""
+    import cv2
+    from PIL import Image
+    from oracle import oracle as O
+    from tools.synth import gen_page
+    rng = np.random.default_rng(1)
+    imgs = [gen_page(5, 333, 517, n_lines=(4, 8))[0], rng.integers(0, 256, (123, 77, 3), dtype=np.uint8),
+            cv2.GaussianBlur(rng.integers(0, 256, (200, 310, 3), dtype=np.uint8), (0, 0), 3), rng.integers(0, 256, (9, 5, 3), dtype=np.uint8),
+            gen_page(6, 736, 992, n_lines=(6, 12))[0], rng.integers(0, 256, (20, 4, 3), dtype=np.uint8), rng.integers(0, 256, (3, 2, 3), dtype=np.uint8)]
+    files = []
+    for img in imgs:
+        for sub in (0, 1, 2):
+            for q in (35, 90, 100):
+                for kw in (dict(), dict(optimize=True), dict(restart_marker_rows=1), dict(restart_marker_blocks=3)):
+                    files.append(_enc(img, quality=q, subsampling=sub, **kw))
+    files.append(_enc(np.asarray(Image.fromarray(imgs[0]).convert("L")), quality=80))
+    files.append(_enc(np.asarray(Image.fromarray(imgs[4]).convert("L")), quality=80, restart_marker_rows=2))
+    outs, status = ctx.decode_images(files)
+    assert all(s == 0 for s in status)
+    for k, (f, t) in enumerate(zip(files, outs)):
+        got = t.cpu().numpy()
+        assert np.array_equal(got, _pil(f)), k
+        if k % 7 == 0:
+            assert np.array_equal(got, O.jpeg_decode(f)), k
+
+
+def test_decode_statuses(ctx):
+    from retto_b200 import _lib
+    from tools.synth import gen_page
+    img = gen_page(7, 200, 300, n_lines=(3, 5))[0]
+    good = _enc(img, quality=85, restart_marker_rows=1)
+    prog = _enc(img, quality=85, progressive=True)
+    png = io.BytesIO()
+    from PIL import Image
+    Image.fromarray(img).save(png, "PNG")
+    broken = bytearray(good)
+    pos = [i for i in range(600, len(broken) - 1) if broken[i] == 0xFF and 0xD0 <= broken[i + 1] <= 0xD7]
+    broken[pos[2] + 1] = 0x00          # turn one restart marker into a stuffed byte: the marker count no longer matches DRI
+    outs, status = ctx.decode_images([good, prog, png.getvalue(), bytes(broken), good[:300]])
+    assert status[0] == 0 and np.array_equal(outs[0].cpu().numpy(), _pil(good))
+    assert status[1] == _lib.ERR_UNSUPPORTED and status[2] == _lib.ERR_UNSUPPORTED
+    assert status[3] == _lib.ERR_DECODE and status[4] == _lib.ERR_DECODE
+
+
+def _worker():
+    from retto_b200.session import CallableWorker
+    from tools.demo_worker import StatelessWorker
+    w = StatelessWorker()
+    return w, CallableWorker(w.det, w.cls, w.rec)
+
+
+def test_session_on_file_bytes_equals_session_on_pixels(ctx, synth_dict):
+    """RettoSession::run's own input is the file (session.rs:75-79): bytes in == the same results as the decoded page in, and
+    both equal the oracle pipeline on the oracle-decoded page"""
+    from oracle import oracle as O
+    from oracle.pipeline import run_page
+    from retto_b200.session import RettoSession
+    from tools.synth import gen_page
+    ctx.dict_load(synth_dict)
+    pages = [gen_page(40 + i, h, w, n_lines=(6, 12))[0] for i, (h, w) in enumerate([(900, 1200), (1280, 1280), (500, 640), (2300, 1700)])]
+    files = [_enc(p, quality=90, subsampling=2, restart_marker_rows=1) for p in pages[:3]] + [_enc(pages[3], quality=85, subsampling=0)]
+    w, cw = _worker()
+    sess = RettoSession(worker=cw, ctx=ctx)
+    a = sess.run_pages(files)
+    b = sess.run_pages([_pil(f) for f in files])
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert x.status == 0 and len(x.det_result) == len(y.det_result) > 0
+        for i in range(len(x.det_result)):
+            assert np.array_equal(x.det_result[i].boxes, y.det_result[i].boxes) and x.det_result[i].score == y.det_result[i].score
+            assert x.cls_result[i].label == y.cls_result[i].label and x.rec_result[i].text == y.rec_result[i].text
+        ref = run_page(O.jpeg_decode(files[k]), w, synth_dict)
+        assert len(ref["boxes"]) == len(x.det_result)
+        for i in range(len(ref["boxes"])):
+            assert np.array_equal(x.det_result[i].boxes, ref["boxes"][i]) and x.rec_result[i].text == ref["rec"][i][0]
+
+
+def test_unsupported_file_fails_loudly(ctx, synth_dict):
+    from retto_b200 import _lib
+    from retto_b200._lib import RettoB200Error
+    from retto_b200.session import RettoSession
+    from tools.synth import gen_page
+    ctx.dict_load(synth_dict)
+    _, cw = _worker()
+    sess = RettoSession(worker=cw, ctx=ctx)
+    with pytest.raises(RettoB200Error) as e:
+        sess.run(_enc(gen_page(3, 300, 400, n_lines=(3, 5))[0], progressive=True))
+    assert e.value.status == _lib.ERR_UNSUPPORTED
+
+
+def test_run_stream_is_incremental(ctx, synth_dict):
+    """session.rs:98,101,104: Det is delivered before worker.cls runs, Cls before worker.rec, Rec last"""
+    from retto_b200.session import CallableWorker, RettoSession
+    from tools.demo_worker import StatelessWorker
+    from tools.synth import gen_page
+    ctx.dict_load(synth_dict)
+    w = StatelessWorker()
+    events = []
+
+    def tap(name, f):
+        def g(x):
+            events.append(name)
+            return f(x)
+        return g
+
+    sess = RettoSession(worker=CallableWorker(tap("fwd_det", w.det), tap("fwd_cls", w.cls), tap("fwd_rec", w.rec)), ctx=ctx)
+    got = {}
+
+    def sender(item):
+        events.append("send_" + item[0])
+        got[item[0]] = item[1]
+
+    img = gen_page(44, 800, 1000, n_lines=(5, 9))[0]
+    sess.run_stream(img, sender)
+    order = [e for i, e in enumerate(events) if i == 0 or events[i - 1] != e]     # collapse the per-batch repeats
+    assert order == ["fwd_det", "send_Det", "fwd_cls", "send_Cls", "fwd_rec", "send_Rec"], order
+    ref = sess.run(img)
+    assert len(got["Det"]) == len(ref.det_result) > 0
+    assert all(np.array_equal(a.boxes, b.boxes) for a, b in zip(got["Det"], ref.det_result))
+    assert [c.label for c in got["Cls"]] == [c.label for c in ref.cls_result]
+    assert [r.text for r in got["Rec"]] == [r.text for r in ref.rec_result]
+    # an empty page still reports its three (empty) stages
+    events.clear()
+    sess.run_stream(np.full((300, 400, 3), 255, np.uint8), sender)
+    assert [e for e in events if e.startswith("send_")] == ["send_Det", "send_Cls", "send_Rec"] and got["Det"] == []
+
+
+def _multi_case(devices, synth_dict):
+    from retto_b200.api import Context
+    from retto_b200.session import CallableWorker, RettoSession, run_pages_multi
+    from tools.demo_worker import StatelessWorker
+    from tools.synth import gen_page
+    rng = np.random.default_rng(5)
+    pages = []
+    for i in range(14):
+        h, w = int(rng.integers(400, 1500)), int(rng.integers(400, 1500))
+        pages.append(gen_page(60 + i, h, w, n_lines=(3, 8))[0])
+    files = [_enc(p, quality=88, restart_marker_rows=1) for p in pages]
+    w = StatelessWorker()
+    sessions = []
+    try:
+        for d in devices:
+            c = Context(d)
+            c.dict_load(synth_dict)
+            sessions.append(RettoSession(worker=CallableWorker(w.det, w.cls, w.rec), ctx=c))
+        for inputs in (pages, files):
+            one = sessions[0].run_pages(inputs)
+            many = run_pages_multi(sessions, inputs, chunk_pages=3)
+            assert len(one) == len(many) == len(pages)
+            for a, b in zip(one, many):
+                assert a.status == b.status == 0 and len(a.det_result) == len(b.det_result)
+                for x, y in zip(a.det_result, b.det_result):
+                    assert np.array_equal(x.boxes, y.boxes) and x.score == y.score
+                assert [r.text for r in a.rec_result] == [r.text for r in b.rec_result]
+                assert [c.label for c in a.cls_result] == [c.label for c in b.cls_result]
+        assert sum(len(r.det_result) for r in one) > 30
+    finally:
+        for s in sessions:
+            s.ctx.close()
+
+
+def test_run_pages_multi_two_contexts_one_gpu(synth_dict):
+    """the shared-cursor driver with two contexts (two host threads) on ONE device: same results, page order kept"""
+    _multi_case([0, 0], synth_dict)
+
+
+def test_run_pages_multi_two_gpus(synth_dict):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _multi_case([0, 1], synth_dict)
+
+
+def test_contexts_on_two_devices_from_one_thread(synth_dict):
+    """every C-ABI entry makes its context's device current; one thread driving two devices in turn"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from retto_b200.api import Context
+    from tools.synth import gen_probmap
+    p = gen_probmap(3, 256, 256, k_range=(3, 6))
+    c0, c1 = Context(0), Context(1)
+    try:
+        outs = []
+        for rep in range(2):
+            for c, dev in ((c0, 0), (c1, 1)):
+                torch.cuda.set_device(1 - dev)          # the caller's current device is the OTHER one
+                g = torch.from_numpy(p).to(f"cuda:{dev}")
+                torch.cuda.synchronize(dev)
+                outs.append(c.det_postprocess([g], [p.shape]))
+                assert torch.cuda.current_device() == 1 - dev
+        assert all(np.array_equal(o.boxes, outs[0].boxes) for o in outs) and len(outs[0].boxes) > 0
+    finally:
+        c0.close()
+        c1.close()
+        torch.cuda.set_device(0)
