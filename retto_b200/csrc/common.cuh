@@ -139,7 +139,8 @@ struct JpegInfo {          // host: the parsed markers of one baseline JPEG file
 };
 retto_b200_status rt_jpeg_parse(const uint8_t* d, size_t n, JpegInfo* out);
 struct retto_b200_ctx;
-retto_b200_status rt_jpeg_decode_enqueue(retto_b200_ctx* ctx, const JpegInfo* infos, const uint8_t* const* d_bytes, uint8_t* const* d_out, int n);
+retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, const JpegInfo* infos, const uint8_t* const* d_bytes, int n);
+retto_b200_status rt_jpeg_pixels_enqueue(retto_b200_ctx* owner, retto_b200_ctx* lane, int first, int n, uint8_t* const* d_out);
 
 struct retto_b200_ctx {
     int device = 0;
@@ -254,7 +255,14 @@ struct retto_b200_ctx {
     // sizes of the last run_pages call (bench.py algorithmic bytes): pages, lines, det px, crop px, cls floats, rec floats, rec rows
     uint64_t run_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // image decode (jpeg_decode.cu)
-    DevBuf d_jpeg_blob, d_jpeg_desc, d_jpeg_seg, d_jpeg_coef, d_jpeg_planes;
+    DevBuf d_jpeg_blob, d_jpeg_desc, d_jpeg_seg, d_jpeg_coef, d_jpeg_planes, d_jpeg_clean, d_jpeg_out;
+    struct JpegBatch {                           // the batch whose entropy phase ran last: what the pixel phase of its units needs
+        int n = 0;
+        size_t desc_bytes = 0, head_bytes = 0;
+        std::vector<int> X, Y;
+        std::vector<unsigned> n_blocks;
+        HostBuf h_desc;
+    } jpeg;
     int* jpeg_status_dev = nullptr;              // per-file device status of the last decode (inside d_jpeg_seg)
     HostBuf h_jpeg_status;
     std::vector<JpegInfo> jpeg_infos;            // parsed headers of the encoded pages of the current run_pages call

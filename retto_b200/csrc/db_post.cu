@@ -1107,7 +1107,12 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
         const float* row = prob + (size_t)y * W + x0 + lane;
         if (!partial) {   // full strip (all but the last of a page row): unpredicated loads
 #pragma unroll
-            for (int j = 0; j < NW; ++j) { r.v[j] = __ldg(row + 32 * j); nf = __fmaf_rn(r.v[j], 0.0f, nf); }
+            for (int j = 0; j < NW; ++j) r.v[j] = __ldg(row + 32 * j);
+            // non-finite probe: a pairwise sum tree (NaN and +-Inf propagate; a finite overflow would only send the page down the exact
+            // — still correct — score path) and ONE fused multiply by zero per row, off the load -> ballot chain
+            float t0 = __fadd_rn(r.v[0], r.v[1 % NW]), t1 = __fadd_rn(r.v[2 % NW], r.v[3 % NW]);
+            if (NW == 8) { t0 = __fadd_rn(t0, __fadd_rn(r.v[4 % NW], r.v[5 % NW])); t1 = __fadd_rn(t1, __fadd_rn(r.v[6 % NW], r.v[7 % NW])); }
+            nf = __fmaf_rn(__fadd_rn(t0, t1), 0.0f, nf);
         } else {
 #pragma unroll
             for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) { r.v[j] = __ldg(row + 32 * j); nf = __fmaf_rn(r.v[j], 0.0f, nf); }

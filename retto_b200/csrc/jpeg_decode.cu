@@ -8,10 +8,12 @@
 // GPU-hybrid backend decodes 3.0 k 1280^2 pages/s (profiles/r02_nvjpeg_probe.txt) — below the raw-RGB PCIe path — so the decoder
 // is hand-written:
 //   host  : marker parse only (tables, frame, scan header: a few hundred bytes per file) -> JpegInfo
-//   K-J1  jpeg_scan_kernel   : one block per file finds the RSTn markers of the entropy-coded segment (ordered compaction)
+//   K-J1  jpeg_scan_kernel   : one block per file turns the entropy-coded segment into a CLEAN bit stream (stuffed zeros and RSTn
+//                              markers removed by an ordered block-wide compaction) and records where every restart interval starts
 //   K-J2  jpeg_huff_kernel   : one THREAD per restart interval — intervals are independently decodable (DC prediction resets,
-//                              byte-aligned) — 64-bit bit buffer refilled with aligned 32-bit loads (byte path only around 0xFF),
-//                              9-bit Huffman look-up tables built in shared memory; non-zero coefficients are scattered into a
+//                              byte-aligned) — a 64-bit window of two big-endian words read with one funnel shift per symbol,
+//                              words loaded one refill ahead; 10-bit Huffman look-up tables in shared memory whose entries carry
+//                              the EXTENDed value when code + magnitude bits fit; non-zero coefficients are scattered into a
 //                              pre-zeroed int16 coefficient plane (a file without DRI is one interval = one thread)
 //   K-J3  jpeg_idct_kernel   : 8 threads per 8x8 block: dequantise + libjpeg's jidctint "islow" integer IDCT (columns, then rows)
 //   K-J4  jpeg_color_kernel  : libjpeg's fancy (triangle) chroma up-sampling h2v1 / h2v2 / h1v2 + YCbCr->RGB fixed point -> HWC u8
@@ -161,58 +163,89 @@ struct JpegDev {
     int thread_base;              // first decode thread of this file (== seg_base)
     unsigned block_base, n_blocks;   // 8x8 blocks of all components (IDCT work list)
     JpegComp c[3];
-    uint8_t* out;                 // HWC u8 RGB
+    unsigned long long clean_off; // byte offset of this file's clean bit stream (K-J1) in the clean arena, 16-byte aligned
     int status_slot;
 };
 struct JpegHuffRaw { uint8_t bits[17]; uint8_t pad[3]; uint8_t vals[256]; };   // 276 B
 struct JpegTables { uint16_t qt[4][64]; JpegHuffRaw dc[4], ac[4]; };
 
-// ---- K-J1: restart markers -----------------------------------------------------------------------------------------------------
-// seg[seg_base + j] = byte offset (in the entropy-coded data) at which restart interval j starts.  Inside the entropy-coded data
-// 0xFF is always followed by 0x00 (stuffing) or by a marker, so every "FF D0..D7" pair is an RSTn marker.
-__global__ void __launch_bounds__(256) jpeg_scan_kernel(const JpegDev* __restrict__ files, unsigned* __restrict__ seg, int* __restrict__ status) {
+// ---- K-J1: clean bit stream + restart intervals ------------------------------------------------------------------------------
+// Inside the entropy-coded data 0xFF is always followed by 0x00 (stuffing) or by a marker, so every "FF D0..D7" pair is an RSTn
+// marker.  The kernel copies the data bytes to clean + f.clean_off, dropping stuffed zeros and markers (everything from the EOI
+// marker on is dropped too), seg[seg_base + j] = clean byte offset at which restart interval j starts, clean_len[file] = length.
+__global__ void __launch_bounds__(256) jpeg_scan_kernel(const JpegDev* __restrict__ files, unsigned* __restrict__ seg, int* __restrict__ status,
+                                                        unsigned char* __restrict__ clean, unsigned* __restrict__ clean_len) {
     const JpegDev& f = files[blockIdx.x];
     unsigned* sg = seg + f.seg_base;
     const int n_seg = f.n_seg;
-    for (int j = threadIdx.x; j < n_seg; j += blockDim.x) sg[j] = j == 0 ? 0u : f.ecs_len;   // missing markers: empty intervals (zeros)
-    __syncthreads();
-    if (n_seg <= 1) return;
-    __shared__ int s_warp[8];
-    __shared__ int s_base;
-    if (threadIdx.x == 0) s_base = 0;
+    unsigned char* out = clean + f.clean_off;
+    __shared__ int s_wm[8], s_wk[8];
+    __shared__ int s_base_m;
+    __shared__ unsigned s_base_k, s_eoi;
+    if (threadIdx.x == 0) { s_base_m = 0; s_base_k = 0; s_eoi = 0xFFFFFFFFu; }
     __syncthreads();
     const uint8_t* p = f.ecs;
     const unsigned len = f.ecs_len;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (unsigned base = 0; base < len; base += 256 * 16) {
         const unsigned o = base + threadIdx.x * 16;
-        // 17 bytes: 16 of this thread + the first of the next
-        unsigned char b[17];
+        // 18 bytes: the last of the previous thread, 16 of this thread, the first of the next
+        unsigned char b[18];
 #pragma unroll
-        for (int k = 0; k < 17; ++k) b[k] = (o + k < len) ? __ldg(p + o + k) : 0;
-        unsigned mask = 0;
+        for (int k = 0; k < 18; ++k) b[k] = (o + k >= 1 && o + k - 1 < len) ? __ldg(p + o + k - 1) : 0;
+        unsigned keep = 0, mark = 0;
+        unsigned eoi_at = 0xFFFFFFFFu;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) if (b[k] == 0xFF && b[k + 1] >= 0xD0 && b[k + 1] <= 0xD7) mask |= 1u << k;
-        const int cnt = __popc(mask);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-        if (lane == 31) s_warp[w] = incl;
+        for (int k = 0; k < 16; ++k) {
+            if (o + k >= len) break;
+            const unsigned c = b[k + 1], prev = b[k], next = b[k + 2];
+            const bool rst_ff = c == 0xFF && next >= 0xD0 && next <= 0xD7;
+            const bool rst_code = prev == 0xFF && c >= 0xD0 && c <= 0xD7;
+            const bool stuffed = prev == 0xFF && c == 0x00;
+            if (c == 0xFF && next == 0xD9 && eoi_at == 0xFFFFFFFFu) eoi_at = o + k;
+            if (!(rst_ff || rst_code || stuffed)) keep |= 1u << k;
+            if (rst_ff) mark |= 1u << k;
+        }
+        if (eoi_at != 0xFFFFFFFFu) atomicMin(&s_eoi, eoi_at);
         __syncthreads();
-        int before = s_base;
-        for (int k = 0; k < w; ++k) before += s_warp[k];
-        int idx = before + incl - cnt;
-        while (mask) {
-            const int k = __ffs(mask) - 1;
-            mask &= mask - 1;
-            ++idx;   // marker number idx (1-based) starts interval idx
-            if (idx < n_seg) sg[idx] = o + k + 2;
+        const unsigned eoi = s_eoi;          // first EOI seen so far (this tile or an earlier one): nothing at or after it is data
+        if (eoi != 0xFFFFFFFFu) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (o + k >= eoi) { keep &= ~(1u << k); mark &= ~(1u << k); }
+        }
+        const int cm = __popc(mark), ck = __popc(keep);
+        int im = cm, ik = ck;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int vm = __shfl_up_sync(0xffffffffu, im, d), vk = __shfl_up_sync(0xffffffffu, ik, d);
+            if (lane >= d) { im += vm; ik += vk; }
+        }
+        if (lane == 31) { s_wm[w] = im; s_wk[w] = ik; }
+        __syncthreads();
+        int bm = s_base_m;
+        unsigned bk = s_base_k;
+        for (int k = 0; k < w; ++k) { bm += s_wm[k]; bk += (unsigned)s_wk[k]; }
+        int idx = bm + im - cm;               // markers before this thread
+        unsigned dst = bk + (unsigned)(ik - ck);   // clean bytes before this thread
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (keep & (1u << k)) out[dst++] = b[k + 1];
+            if (mark & (1u << k)) { ++idx; if (idx < n_seg) sg[idx] = dst; }   // interval idx starts at the current clean position
         }
         __syncthreads();
-        if (threadIdx.x == 255) s_base = before + incl;
+        if (threadIdx.x == 255) { s_base_m = bm + im; s_base_k = bk + (unsigned)ik; }
         __syncthreads();
     }
-    if (threadIdx.x == 0 && s_base != n_seg - 1) status[f.status_slot] = RETTO_B200_ERR_DECODE;   // marker count does not match DRI
+    const unsigned total = s_base_k;
+    for (int j = threadIdx.x; j < n_seg; j += blockDim.x) {
+        if (j == 0) sg[0] = 0;
+        else if (j > s_base_m) sg[j] = total;      // missing markers: empty intervals (zeros)
+    }
+    if (threadIdx.x < 16) out[total + threadIdx.x] = 0;   // zero padding: the bit reader runs a few words past the end
+    if (threadIdx.x == 0) {
+        clean_len[blockIdx.x] = total;
+        if (s_base_m != n_seg - 1) status[f.status_slot] = RETTO_B200_ERR_DECODE;   // marker count does not match DRI
+    }
 }
 
 // ---- K-J2: Huffman decode, one thread per restart interval ------------------------------------------------------------------------
@@ -235,50 +268,12 @@ struct HuffDev {               // shared memory, one per distinct table of the f
 __device__ __forceinline__ int jh_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
 __device__ __forceinline__ unsigned jh_has_ff(unsigned w) { return __vcmpeq4(w, 0xFFFFFFFFu); }
 
-// Bit reader state lives in plain local variables of the kernel (a struct whose address escapes into a non-inlined call is
-// kept in local memory: LDL/STL on the per-symbol chain).  The byte-wise slow path returns its results by value.
-struct JhSlow { unsigned word, pos; int eof; };
-static __device__ __noinline__ JhSlow jh_slow_word(const uint8_t* base, unsigned len, unsigned pos, int eof) {
-    // 4 data bytes starting at pos: stuffed zeros skipped; a marker or the end of the data ends the interval (zeros from there on)
-    unsigned acc = 0;
-    for (int i = 0; i < 4; ++i) {
-        unsigned b = 0;
-        if (!eof && pos < len) {
-            b = __ldg(base + pos); ++pos;
-            if (b == 0xFF) {
-                if (pos < len && __ldg(base + pos) == 0) ++pos;
-                else { eof = 1; b = 0; }
-            }
-        } else eof = 1;
-        acc = (acc << 8) | b;
-    }
-    JhSlow r; r.word = acc; r.pos = pos; r.eof = eof;
-    return r;
-}
-// refill 32 bits into the MSB-aligned window `buf` holding n <= 32 valid bits
-#define JH_REFILL()                                                                                                     \
-    do {                                                                                                                \
-        const unsigned raw_ = __funnelshift_r(w_prev, w_cur, 8u * (pos & 3u));                                          \
-        unsigned w_;                                                                                                    \
-        if (!eof && jh_has_ff(raw_) == 0 && pos + 4 <= len) {                                                           \
-            w_ = __byte_perm(raw_, 0, 0x0123);                                                                          \
-            pos += 4;                                                                                                   \
-            w_prev = w_cur;                                                                                             \
-            w_cur = __ldg(reinterpret_cast<const unsigned*>(base + (pos & ~3u)) + 1);                                   \
-        } else if (eof) w_ = 0u;                                                                                        \
-        else {                                                                                                          \
-            const JhSlow sl_ = jh_slow_word(base, len, pos, eof);                                                       \
-            w_ = sl_.word; pos = sl_.pos; eof = sl_.eof;                                                                \
-            const unsigned* ap_ = reinterpret_cast<const unsigned*>(base + (pos & ~3u));                                \
-            w_prev = __ldg(ap_); w_cur = __ldg(ap_ + 1);                                                                \
-        }                                                                                                               \
-        buf |= (unsigned long long)w_ << (32 - n);                                                                      \
-        n += 32;                                                                                                        \
-    } while (0)
-
+// Bit reader over the CLEAN stream (K-J1): w0:w1 = the next 64 bits (big-endian words), o = bits of w0 already consumed;
+// the 32-bit window at the read position is one funnel shift; `nxt` is the raw word after w1, loaded one refill ahead.
 __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file,
                                                               const int* __restrict__ block_first, const JpegTables* __restrict__ tables,
-                                                              const unsigned* __restrict__ seg, short* __restrict__ coef) {
+                                                              const unsigned* __restrict__ seg, const unsigned char* __restrict__ clean,
+                                                              const unsigned* __restrict__ clean_len, short* __restrict__ coef) {
     __shared__ HuffDev s_tab[6];     // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
     __shared__ unsigned char s_zz[64];
     __shared__ int s_slot[6];
@@ -330,16 +325,15 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
     __syncthreads();
     const int j = block_first[blockIdx.x] + threadIdx.x;   // restart interval of this thread
     if (j >= f.n_seg) return;
-    // positions are taken relative to the 4-byte-aligned address at or below the start of the data, so that word loads are aligned
-    const unsigned mis = (unsigned)((uintptr_t)f.ecs & 3u);
-    const uint8_t* base = f.ecs - mis;
-    const unsigned len = f.ecs_len + mis;
-    unsigned pos = min(seg[f.seg_base + j], f.ecs_len) + mis;
-    unsigned long long buf = 0;
-    int n = 0, eof = 0;
-    unsigned w_prev, w_cur;
-    { const unsigned* ap = reinterpret_cast<const unsigned*>(base + (pos & ~3u)); w_prev = __ldg(ap); w_cur = __ldg(ap + 1); }
-    JH_REFILL();
+    const unsigned char* base = clean + f.clean_off;             // 16-byte aligned
+    const unsigned clen = clean_len[fi];
+    const unsigned start = min(seg[f.seg_base + j], clen);
+    const unsigned* wp = reinterpret_cast<const unsigned*>(base + (start & ~3u));
+    const unsigned* wend = reinterpret_cast<const unsigned*>(base + ((clen + 3u) & ~3u)) + 4;   // zero padding of K-J1 included
+    unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
+    unsigned nxt = __ldg(wp + 2);
+    wp += 3;
+    unsigned o = 8u * (start & 3u);
     const long long n_mcu = (long long)f.mcux * f.mcuy;
     long long m = f.ri > 0 ? (long long)j * f.ri : 0;
     const long long m1 = f.ri > 0 ? min(m + f.ri, n_mcu) : n_mcu;
@@ -362,10 +356,10 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
     short* blk = coef + ((size_t)cbase0 + (size_t)(my * v0) * cwb0 + mx * h0) * 64;
     const HuffDev* tab = tdc0;
     while (m < m1) {
-        if (n <= 32) JH_REFILL();
-        unsigned e = tab->lut[(unsigned)(buf >> (64 - JH_LUT_BITS))];
+        const unsigned win = __funnelshift_l(w1, w0, o);          // the 32 bits at the read position
+        unsigned e = tab->lut[win >> (32 - JH_LUT_BITS)];
         if ((e & 31u) == 0) {   // a code longer than the window: canonical search (rare)
-            const unsigned top = (unsigned)(buf >> 48);
+            const unsigned top = win >> 16;
             unsigned sym = 0, l = 16;
 #pragma unroll 1
             for (int q = JH_LUT_BITS + 1; q <= 16; ++q) {
@@ -374,14 +368,20 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
             }
             e = k == 0 ? (l | ((sym & 15u) << 9)) : (l | ((sym >> 4) << 5) | ((sym & 15u) << 9));
         }
-        const int L = (int)(e & 31u);
-        buf <<= L; n -= L;
+        unsigned L = e & 31u;
         const int r = (int)((e >> 5) & 15u), sz = (int)((e >> 9) & 15u);
         int v = (int)e >> 16;
-        if (!(e & (1u << 13)) && sz) {   // magnitude bits outside the window
-            if (n < sz) JH_REFILL();
-            v = jh_extend((int)(buf >> (64 - sz)), sz);
-            buf <<= sz; n -= sz;
+        if (!(e & (1u << 13)) && sz) {   // magnitude bits outside the table window: still inside `win` (code <= 16, size <= 15 bits)
+            v = jh_extend((int)((win << L) >> (32 - sz)), sz);
+            L += (unsigned)sz;
+        }
+        o += L;
+        if (o >= 32u) {
+            o -= 32u;
+            w0 = w1;
+            w1 = __byte_perm(nxt, 0, 0x0123);
+            nxt = wp < wend ? __ldg(wp) : 0u;
+            ++wp;
         }
         if (k == 0) {
             int pv;
@@ -444,6 +444,7 @@ __device__ __forceinline__ unsigned ji_range_limit(int x) {   // range_limit[x &
 // 256 threads = 32 blocks of 8x8; thread (g, t): row t of the coefficient load, column t of pass 1, row t of pass 2
 __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDev* __restrict__ files, const JpegTables* __restrict__ tables,
                                                         const short* __restrict__ coef, unsigned char* __restrict__ planes) {
+    // `files` / `tables` point at the first file of the unit
     __shared__ short s_coef[32][72];
     __shared__ int s_ws[32][72];
     const int g = threadIdx.x >> 3, t = threadIdx.x & 7;
@@ -557,7 +558,8 @@ __device__ __forceinline__ void jc_chroma8(const unsigned char* __restrict__ pl,
         out[2 * k + 1] = (c[1 + k] * 3 + next + 7) >> 4;
     }
 }
-__global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* __restrict__ files, const unsigned char* __restrict__ planes) {
+__global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* __restrict__ files, const unsigned char* __restrict__ planes,
+                                                                uint8_t* const* __restrict__ outs) {
     __shared__ unsigned s_rgb[JC_THREADS * 6 + 1];
     const JpegDev& f = files[blockIdx.z];
     const int y = blockIdx.y, xb = blockIdx.x * (blockDim.x * JC_PX);
@@ -591,7 +593,7 @@ __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* _
     __syncthreads();
     const int npx = min((int)blockDim.x * JC_PX, f.X - xb);
     const int nbytes = 3 * npx;
-    unsigned char* gp = f.out + ((size_t)y * f.X + xb) * 3;
+    unsigned char* gp = outs[blockIdx.z] + ((size_t)y * f.X + xb) * 3;
     const int head = min((int)((4u - ((unsigned)(uintptr_t)gp & 3u)) & 3u), nbytes);
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(s_rgb);
     if ((int)threadIdx.x < head) gp[threadIdx.x] = sb[threadIdx.x];
@@ -606,49 +608,46 @@ __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* _
     if ((int)threadIdx.x < nbytes - tail0) gp[tail0 + threadIdx.x] = sb[tail0 + threadIdx.x];
 }
 
-// ---- host: enqueue the decode of n parsed files ------------------------------------------------------------------------------------
-// d_bytes[i]: device pointer to file i (the whole file; the entropy-coded data starts at infos[i].ecs_off), d_out[i]: HWC u8 RGB
-// of infos[i].Y x infos[i].X.  Everything is enqueued on the context's stream; d_status (n ints, device) receives a non-zero
-// status for files whose restart markers do not match their DRI header.
-retto_b200_status rt_jpeg_decode_enqueue(retto_b200_ctx* ctx, const JpegInfo* infos, const uint8_t* const* d_bytes, uint8_t* const* d_out, int n) {
+// ---- host: two phases ---------------------------------------------------------------------------------------------------------------
+// Phase 1 (entropy): everything that is a serial chain per restart interval — K-J1 + K-J2 for ALL files of a call in one launch each,
+// on the stream the caller names (run_pages: the copy stream, right behind the upload of the files).  The Huffman kernel's
+// duration is the longest interval's chain whatever the number of files, so it is paid once per call, not once per unit.
+// Phase 2 (pixels): K-J3 + K-J4 for a range of files, on the stream of the unit that consumes the pages.
+// d_bytes[i]: device pointer to file i (the whole file; the entropy-coded data starts at infos[i].ecs_off).
+retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, const JpegInfo* infos, const uint8_t* const* d_bytes, int n) {
+    retto_b200_ctx::JpegBatch& JB = ctx->jpeg;
+    JB.n = 0;
     if (n <= 0) return RETTO_B200_OK;
-    cudaStream_t st = ctx->stream;
-    // layout
     const size_t desc_bytes = (sizeof(JpegDev) * (size_t)n + 15) & ~size_t(15);
-    const size_t pfx_blocks_bytes = (sizeof(unsigned) * ((size_t)n + 1) + 15) & ~size_t(15);
-    const size_t pfx_px_bytes = (sizeof(unsigned long long) * ((size_t)n + 1) + 15) & ~size_t(15);
     long long total_seg = 0;
     size_t n_tblocks = 0;
     for (int i = 0; i < n; ++i) { total_seg += infos[i].n_seg; n_tblocks += ((size_t)infos[i].n_seg + JH_THREADS - 1) / JH_THREADS; }
     if (total_seg > 0x3fffffffLL) { ctx->set_error("jpeg decode: too many restart intervals"); return RETTO_B200_ERR_CAPACITY; }
     const size_t tb_bytes = (sizeof(int) * 2 * n_tblocks + 15) & ~size_t(15);
-    const size_t head_bytes = desc_bytes + pfx_blocks_bytes + pfx_px_bytes + tb_bytes;
+    const size_t head_bytes = desc_bytes + tb_bytes;
     const size_t tab_bytes = sizeof(JpegTables) * (size_t)n;
-    int slot = -1;
-    void* sp = nullptr;
-    RT_TRY(rt_stage_begin(ctx, head_bytes + tab_bytes, &slot, &sp));
-    char* hp = reinterpret_cast<char*>(sp);
+    // the descriptor blob is built in pinned memory owned by the batch (not a recycled staging slot: the copy runs on `st`)
+    RT_CUDA_OK(ctx, JB.h_desc.ensure(head_bytes + tab_bytes));
+    char* hp = JB.h_desc.as<char>();
     JpegDev* hd = reinterpret_cast<JpegDev*>(hp);
-    unsigned* h_bpfx = reinterpret_cast<unsigned*>(hp + desc_bytes);
-    unsigned long long* h_ppfx = reinterpret_cast<unsigned long long*>(hp + desc_bytes + pfx_blocks_bytes);
-    int* h_tb_file = reinterpret_cast<int*>(hp + desc_bytes + pfx_blocks_bytes + pfx_px_bytes);
+    int* h_tb_file = reinterpret_cast<int*>(hp + desc_bytes);
     int* h_tb_first = h_tb_file + n_tblocks;
     JpegTables* h_tab = reinterpret_cast<JpegTables*>(hp + head_bytes);
-    unsigned long long blocks = 0, plane_bytes = 0, px = 0;
-    int seg_base = 0, max_x = 1, max_y = 1;
-    unsigned max_file_blocks = 1;
+    unsigned long long blocks = 0, plane_bytes = 0, clean_bytes = 0;
+    int seg_base = 0;
     size_t tb = 0;
+    JB.X.resize(n); JB.Y.resize(n); JB.n_blocks.resize(n);
     for (int i = 0; i < n; ++i) {
         const JpegInfo& J = infos[i];
         JpegDev& D = hd[i];
         memset(&D, 0, sizeof(D));
-        if (J.status != RETTO_B200_OK || J.ecs_len > 0xfffffff0u) { ctx->stage_slots[slot].busy = false; ctx->set_error("jpeg decode: file " + std::to_string(i) + " was not parsed"); return RETTO_B200_ERR_INVALID_ARG; }
+        if (J.status != RETTO_B200_OK || J.ecs_len > 0xfffffff0u) { ctx->set_error("jpeg decode: file " + std::to_string(i) + " was not parsed"); return RETTO_B200_ERR_INVALID_ARG; }
         D.ecs = d_bytes[i] + J.ecs_off; D.ecs_len = (unsigned)J.ecs_len;
-        max_x = std::max(max_x, J.X); max_y = std::max(max_y, J.Y);
         D.X = J.X; D.Y = J.Y; D.nc = J.nc; D.max_h = J.max_h; D.max_v = J.max_v; D.mcux = J.mcux; D.mcuy = J.mcuy; D.ri = J.ri; D.n_seg = J.n_seg;
         D.seg_base = seg_base; D.thread_base = seg_base; D.status_slot = i;
         D.block_base = (unsigned)blocks;
-        h_bpfx[i] = (unsigned)blocks;
+        D.clean_off = clean_bytes;
+        clean_bytes += ((unsigned long long)J.ecs_len + 32 + 15) & ~15ULL;
         for (int c = 0; c < J.nc; ++c) {
             JpegComp& C = D.c[c];
             C.h = J.h[c]; C.v = J.v[c]; C.tq = J.tq[c]; C.td = J.td[c]; C.ta = J.ta[c];
@@ -659,12 +658,9 @@ retto_b200_status rt_jpeg_decode_enqueue(retto_b200_ctx* ctx, const JpegInfo* in
             blocks += (unsigned long long)C.wb * C.hb;
             plane_bytes += ((unsigned long long)C.wb * C.hb * 64 + 15) & ~15ULL;
         }
-        if (blocks > 0x7fffffffULL) { ctx->stage_slots[slot].busy = false; ctx->set_error("jpeg decode: batch too large (coefficient blocks)"); return RETTO_B200_ERR_CAPACITY; }
+        if (blocks > 0x7fffffffULL) { ctx->set_error("jpeg decode: batch too large (coefficient blocks)"); return RETTO_B200_ERR_CAPACITY; }
         D.n_blocks = (unsigned)blocks - D.block_base;
-        max_file_blocks = std::max(max_file_blocks, D.n_blocks);
-        D.out = d_out[i];
-        h_ppfx[i] = px;
-        px += (unsigned long long)J.X * J.Y;
+        JB.X[i] = J.X; JB.Y[i] = J.Y; JB.n_blocks[i] = D.n_blocks;
         for (int j0 = 0; j0 < J.n_seg; j0 += JH_THREADS) { h_tb_file[tb] = i; h_tb_first[tb] = j0; ++tb; }
         seg_base += J.n_seg;
         for (int k = 0; k < 4; ++k) {
@@ -673,38 +669,60 @@ retto_b200_status rt_jpeg_decode_enqueue(retto_b200_ctx* ctx, const JpegInfo* in
             memcpy(h_tab[i].ac[k].bits, J.ac[k].bits, 17); memcpy(h_tab[i].ac[k].vals, J.ac[k].vals, 256);
         }
     }
-    h_bpfx[n] = (unsigned)blocks;
-    h_ppfx[n] = px;
-    RT_TRY(rt_stage_commit(ctx, ctx->d_jpeg_desc, slot, head_bytes + tab_bytes));
+    // grow-only buffers (growth synchronises ctx->stream; `st` holds no work on them: run_pages drains the copy stream before it returns)
+    RT_CUDA_OK(ctx, ctx->d_jpeg_desc.ensure(head_bytes + tab_bytes, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_jpeg_seg.ensure(sizeof(unsigned) * ((size_t)std::max(seg_base, 1) + (size_t)n) + sizeof(int) * (size_t)n, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_jpeg_coef.ensure((size_t)blocks * 128, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_jpeg_planes.ensure((size_t)plane_bytes, ctx->stream));
+    RT_CUDA_OK(ctx, ctx->d_jpeg_clean.ensure((size_t)clean_bytes + 64, ctx->stream));
+    RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_jpeg_desc.p, hp, head_bytes + tab_bytes, cudaMemcpyHostToDevice, st));
     const char* dp = ctx->d_jpeg_desc.as<char>();
     const JpegDev* d_files = reinterpret_cast<const JpegDev*>(dp);
-    const unsigned* d_bpfx = reinterpret_cast<const unsigned*>(dp + desc_bytes);
-    const unsigned long long* d_ppfx = reinterpret_cast<const unsigned long long*>(dp + desc_bytes + pfx_blocks_bytes);
-    const int* d_tb_file = reinterpret_cast<const int*>(dp + desc_bytes + pfx_blocks_bytes + pfx_px_bytes);
+    const int* d_tb_file = reinterpret_cast<const int*>(dp + desc_bytes);
     const int* d_tb_first = d_tb_file + n_tblocks;
     const JpegTables* d_tab = reinterpret_cast<const JpegTables*>(dp + head_bytes);
-    RT_CUDA_OK(ctx, ctx->d_jpeg_seg.ensure(sizeof(unsigned) * (size_t)std::max(seg_base, 1) + sizeof(int) * (size_t)n, st));
-    RT_CUDA_OK(ctx, ctx->d_jpeg_coef.ensure((size_t)blocks * 128, st));
-    RT_CUDA_OK(ctx, ctx->d_jpeg_planes.ensure((size_t)plane_bytes, st));
     unsigned* d_seg = ctx->d_jpeg_seg.as<unsigned>();
-    int* d_status = reinterpret_cast<int*>(d_seg + std::max(seg_base, 1));
+    unsigned* d_clean_len = d_seg + std::max(seg_base, 1);
+    int* d_status = reinterpret_cast<int*>(d_clean_len + n);
     ctx->jpeg_status_dev = d_status;
+    JB.n = n; JB.desc_bytes = desc_bytes; JB.head_bytes = head_bytes;
     RT_CUDA_OK(ctx, cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)n, st));
     RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_jpeg_coef.p, 0, (size_t)blocks * 128, st));
+    ctx->timer_stream = st;
     RT_LAUNCH_BEGIN(ctx, "jpeg_scan_kernel");
-    jpeg_scan_kernel<<<n, 256, 0, st>>>(d_files, d_seg, d_status);
+    jpeg_scan_kernel<<<n, 256, 0, st>>>(d_files, d_seg, d_status, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len);
     RT_LAUNCH_CHECK(ctx);
+    ctx->timer_stream = st;
     RT_LAUNCH_BEGIN(ctx, "jpeg_huff_kernel");
-    jpeg_huff_kernel<<<(unsigned)n_tblocks, JH_THREADS, 0, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg, ctx->d_jpeg_coef.as<short>());
+    jpeg_huff_kernel<<<(unsigned)n_tblocks, JH_THREADS, 0, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len,
+                                                                 ctx->d_jpeg_coef.as<short>());
     RT_LAUNCH_CHECK(ctx);
-    RT_LAUNCH_BEGIN(ctx, "jpeg_idct_kernel");
-    jpeg_idct_kernel<<<dim3((max_file_blocks + 31) / 32, (unsigned)n), 256, 0, st>>>(d_files, d_tab, ctx->d_jpeg_coef.as<short>(),
-                                                                                    ctx->d_jpeg_planes.as<unsigned char>());
-    RT_LAUNCH_CHECK(ctx);
-    RT_LAUNCH_BEGIN(ctx, "jpeg_color_kernel");
+    ctx->timer_stream = nullptr;
+    return RETTO_B200_OK;
+}
+
+// Phase 2 for files [first, first + n) of the batch whose entropy phase `owner` ran; kernels go on lane->stream (lane == owner unless
+// run_pages pipelines units over two lanes).  d_out[k]: HWC u8 RGB of file first + k.
+retto_b200_status rt_jpeg_pixels_enqueue(retto_b200_ctx* owner, retto_b200_ctx* lane, int first, int n, uint8_t* const* d_out) {
+    const retto_b200_ctx::JpegBatch& JB = owner->jpeg;
+    if (n <= 0) return RETTO_B200_OK;
+    if (first < 0 || first + n > JB.n) { lane->set_error("jpeg decode: unit outside the decoded batch"); return RETTO_B200_ERR_INVALID_ARG; }
+    int max_x = 1, max_y = 1;
+    unsigned max_file_blocks = 1;
+    for (int i = first; i < first + n; ++i) { max_x = std::max(max_x, JB.X[i]); max_y = std::max(max_y, JB.Y[i]); max_file_blocks = std::max(max_file_blocks, JB.n_blocks[i]); }
+    RT_TRY(rt_upload(lane, lane->d_jpeg_out, d_out, sizeof(uint8_t*) * (size_t)n));
+    const char* dp = owner->d_jpeg_desc.as<char>();
+    const JpegDev* d_files = reinterpret_cast<const JpegDev*>(dp) + first;
+    const JpegTables* d_tab = reinterpret_cast<const JpegTables*>(dp + JB.head_bytes) + first;
+    cudaStream_t st = lane->stream;
+    RT_LAUNCH_BEGIN(lane, "jpeg_idct_kernel");
+    jpeg_idct_kernel<<<dim3((max_file_blocks + 31) / 32, (unsigned)n), 256, 0, st>>>(d_files, d_tab, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
+    RT_LAUNCH_CHECK(lane);
     const int jc_threads = std::min(JC_THREADS, ((max_x + JC_PX - 1) / JC_PX + 31) / 32 * 32);
-    jpeg_color_kernel<<<dim3((unsigned)((max_x + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)max_y, (unsigned)n), jc_threads, 0, st>>>(d_files, ctx->d_jpeg_planes.as<unsigned char>());
-    RT_LAUNCH_CHECK(ctx);
+    RT_LAUNCH_BEGIN(lane, "jpeg_color_kernel");
+    jpeg_color_kernel<<<dim3((unsigned)((max_x + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)max_y, (unsigned)n), jc_threads, 0, st>>>(
+        d_files, owner->d_jpeg_planes.as<unsigned char>(), lane->d_jpeg_out.as<uint8_t*>());
+    RT_LAUNCH_CHECK(lane);
     return RETTO_B200_OK;
 }
 
@@ -738,7 +756,8 @@ extern "C" retto_b200_status retto_b200_decode_images(retto_b200_ctx* ctx, const
         sel[k] = infos[i]; db[k] = d; dout[k] = d_out[i];
         if (!d_out[i]) { ctx->set_error("decode_images: null output"); return RETTO_B200_ERR_INVALID_ARG; }
     }
-    RT_TRY(rt_jpeg_decode_enqueue(ctx, sel.data(), db.data(), dout.data(), (int)ok.size()));
+    RT_TRY(rt_jpeg_entropy_enqueue(ctx, st, sel.data(), db.data(), (int)ok.size()));
+    RT_TRY(rt_jpeg_pixels_enqueue(ctx, ctx, 0, (int)ok.size(), dout.data()));
     std::vector<int> dev_status(ok.size());
     RT_CUDA_OK(ctx, cudaMemcpyAsync(dev_status.data(), ctx->jpeg_status_dev, sizeof(int) * ok.size(), cudaMemcpyDeviceToHost, st));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(st));

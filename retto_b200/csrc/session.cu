@@ -88,6 +88,7 @@ struct PageRun {
     void* stage_user = nullptr;
     int first_page = 0;                     // index of this unit's first page in the caller's page array
     const JpegInfo* jinfo = nullptr;        // encoded pages: parsed headers, aligned with h_pages (the file bytes are already on the device)
+    retto_b200_ctx* jowner = nullptr;       // the context whose entropy phase decoded the files of this call (the parent of a lane)
     int n_encoded = 0;
     std::vector<int> enc_page;              // page index of every decoded file of this unit
     // restart markers that do not match the DRI header are only seen by the device: per-file status, read after a stream sync
@@ -179,8 +180,6 @@ retto_b200_status PageRun::begin() {
     {
         size_t off = 0, roff = 0;
         std::vector<retto_b200_resize_desc> step1, step2;
-        std::vector<JpegInfo> enc_info;
-        std::vector<const uint8_t*> enc_src;
         std::vector<uint8_t*> enc_dst;
         for (int i = 0; i < n_pages; ++i) {
             const retto_b200_page& p = h_pages[i];
@@ -193,7 +192,7 @@ retto_b200_status PageRun::begin() {
             } else if (p.on_device == PAGE_DEVICE_ENCODED) {   // image_helper.rs:34-44 on the device: the decoded page lands in the raw-page arena
                 uint8_t* d = ctx->d_pages_raw.as<uint8_t>() + off;
                 off += align256((size_t)p.h * p.w * 3);
-                enc_info.push_back(jinfo[i]); enc_src.push_back(p.rgb); enc_dst.push_back(d); enc_page.push_back(i);
+                enc_dst.push_back(d); enc_page.push_back(i);
                 cur = d;
             }
             int ch = p.h, cw = p.w;
@@ -205,12 +204,13 @@ retto_b200_status PageRun::begin() {
             }
             ps[i].d_img = cur;
         }
-        n_encoded = (int)enc_info.size();
-        if (n_encoded) {
-            retto_b200_status js = rt_jpeg_decode_enqueue(ctx, enc_info.data(), enc_src.data(), enc_dst.data(), n_encoded);
+        n_encoded = (int)enc_dst.size();
+        if (n_encoded) {   // pixel phase of this unit's files (the entropy phase of the whole call ran on the copy stream)
+            if (n_encoded != n_pages || !jowner) { ctx->set_error("run_pages: internal: a unit mixes encoded and decoded pages"); return fail(RETTO_B200_ERR_INVALID_ARG); }
+            retto_b200_status js = rt_jpeg_pixels_enqueue(jowner, ctx, first_page, n_encoded, enc_dst.data());
             if (js != RETTO_B200_OK) return fail(js);
             RT_CUDA_OK(ctx, ctx->h_jpeg_status.ensure(sizeof(int) * (size_t)n_encoded));
-            RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_jpeg_status.p, ctx->jpeg_status_dev, sizeof(int) * (size_t)n_encoded, cudaMemcpyDeviceToHost, st));
+            RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_jpeg_status.p, jowner->jpeg_status_dev + first_page, sizeof(int) * (size_t)n_encoded, cudaMemcpyDeviceToHost, st));
         }
         if (!step1.empty()) RT_TRY(retto_b200_thumbnail(ctx, step1.data(), (int)step1.size()));
         if (!step2.empty()) RT_TRY(retto_b200_thumbnail(ctx, step2.data(), (int)step2.size()));
@@ -571,7 +571,7 @@ static retto_b200_status run_units(retto_b200_ctx* ctx, const std::vector<Unit>&
         runs[k].reset(new PageRun());
         PageRun& r = *runs[k];
         r.ctx = lane[k % n_lanes]; r.h_pages = units[k].pages; r.n_pages = units[k].n; r.forward = forward; r.user = user; r.wait_for = units[k].wait_for;
-        r.stage_cb = ctx->stage_cb; r.stage_user = ctx->stage_user; r.first_page = units[k].first_page; r.jinfo = units[k].jinfo;
+        r.stage_cb = ctx->stage_cb; r.stage_user = ctx->stage_user; r.first_page = units[k].first_page; r.jinfo = units[k].jinfo; r.jowner = ctx;
         return r.begin();
     };
     if (n_lanes == 1) {
@@ -645,20 +645,21 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
                 }
                 blob += ((size_t)h_pages[i].n_bytes + 31) & ~size_t(15);
             }
-            const int unit = ctx->pipe_unit_pages > 0 ? ctx->pipe_unit_pages : env_int("RETTO_B200_ENC_UNIT_PAGES", 128, 1, 1 << 20);
+            const int unit = ctx->pipe_unit_pages > 0 ? ctx->pipe_unit_pages : env_int("RETTO_B200_ENC_UNIT_PAGES", 1 << 20, 1, 1 << 20);   // default: one unit
             if (!ctx->copy_stream) {
                 int lo = 0, hi = 0;
                 cudaDeviceGetStreamPriorityRange(&lo, &hi);
                 RT_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi));
             }
             const int n_units = (n_pages + unit - 1) / unit;
-            while ((int)ctx->copy_events.size() < n_units) {
+            if (ctx->copy_events.empty()) {
                 cudaEvent_t e;
                 RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 ctx->copy_events.push_back(e);
             }
             RT_CUDA_OK(ctx, ctx->d_jpeg_blob.ensure(blob + 16, ctx->stream));
             std::vector<retto_b200_page> dev_pages(n_pages);
+            std::vector<const uint8_t*> d_files(n_pages);
             size_t off = 0;
             uint64_t enc_bytes = 0;
             for (int i = 0; i < n_pages; ++i) {
@@ -667,10 +668,14 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
                 enc_bytes += h_pages[i].n_bytes;
                 RT_CUDA_OK(ctx, cudaMemcpyAsync(d, h_pages[i].rgb, (size_t)h_pages[i].n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
                 dev_pages[i] = retto_b200_page{d, infos[i].Y, infos[i].X, PAGE_DEVICE_ENCODED, h_pages[i].n_bytes};
-                if ((i + 1) % unit == 0 || i + 1 == n_pages) RT_CUDA_OK(ctx, cudaEventRecord(ctx->copy_events[i / unit], ctx->copy_stream));
+                d_files[i] = d;
             }
+            // entropy phase of ALL files behind the uploads, on the copy stream: its duration is the longest restart interval's
+            // serial chain whatever the number of files, so it is paid once per call; the units' pixel phases wait for its event
+            RT_TRY(rt_jpeg_entropy_enqueue(ctx, ctx->copy_stream, infos.data(), d_files.data(), n_pages));
+            RT_CUDA_OK(ctx, cudaEventRecord(ctx->copy_events[0], ctx->copy_stream));
             std::vector<Unit> units;
-            for (int u = 0; u < n_units; ++u) units.push_back(Unit{dev_pages.data() + u * unit, std::min(unit, n_pages - u * unit), ctx->copy_events[u], u * unit, infos.data() + u * unit});
+            for (int u = 0; u < n_units; ++u) units.push_back(Unit{dev_pages.data() + u * unit, std::min(unit, n_pages - u * unit), ctx->copy_events[0], u * unit, infos.data() + u * unit});
             const retto_b200_status ret = run_units(ctx, units, n_lanes, forward, user, out);
             ctx->run_stats[7] = enc_bytes;
             cudaStreamSynchronize(ctx->copy_stream);
