@@ -116,6 +116,9 @@ struct CropDev {
     int rot;
     int status;
     unsigned long long offset;
+    int direct;              // the crop is the page rectangle at (tx, ty): translation by whole pixels, not rotated, every bicubic window inside the page
+    int tx, ty;
+    int pad;
 };
 
 struct LineDev {
@@ -235,6 +238,8 @@ struct retto_b200_ctx {
     size_t crop_dev_cap_bytes = 0, crop_dev_desc_bytes = 0;
     bool crop_dev_check = false;          // rt_crop_finish compares the device's crop sizes with the host's
     int crops_seen_max = 0, crop_rows_seen_max = 0, crop_dev_row_cap = 0;
+    bool crops_lazy = false;              // session path: direct crops (CropDev::direct) are not materialised — the batch build reads the page
+    struct CropLaunch { const int* d_prefix = nullptr; int n = 0, rows = 0; const void* d_totals = nullptr; } crop_launch;   // for retto_b200_crop_fetch
     HostBuf h_crops;
 
     // batches
@@ -263,6 +268,7 @@ struct retto_b200_ctx {
         std::vector<unsigned> n_blocks;
         HostBuf h_desc;
     } jpeg;
+    bool jpeg_huff_attr_set = false;             // dynamic shared memory opt-in of jpeg_huff_kernel done on this context's device
     int* jpeg_status_dev = nullptr;              // per-file device status of the last decode (inside d_jpeg_seg)
     HostBuf h_jpeg_status;
     std::vector<JpegInfo> jpeg_infos;            // parsed headers of the encoded pages of the current run_pages call

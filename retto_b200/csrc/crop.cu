@@ -88,6 +88,18 @@ __global__ void crop_setup_kernel(CropDev* __restrict__ crops, int n, const int*
     if (status == RETTO_B200_OK) { for (int k = 0; k < 9; ++k) crops[i].t[k] = inv[k]; }
     crops[i].cls = cls;
     crops[i].status = status;
+    // direct crops: translation by whole pixels, not rotated, the 4x4 bicubic window of EVERY pixel inside the page (the conditions of
+    // crop_rows_kernel's copy path with no white pixel) — the crop is then exactly the page rectangle at (tx, ty), and the batch build may
+    // read the page instead of a materialised copy
+    int direct = 0, itx = 0, ity = 0;
+    if (status == RETTO_B200_OK && cls == 0 && !c.rot) {
+        const float tx = inv[2], ty = inv[5];
+        if (tx == floorf(tx) && ty == floorf(ty) && fabsf(tx) < 1e6f && fabsf(ty) < 1e6f) {
+            itx = (int)tx; ity = (int)ty;
+            if (itx >= 1 && itx + c.w - 1 <= c.page_w - 4 && ity >= 1 && ity + c.h - 1 + 3 < c.page_h) direct = 1;
+        }
+    }
+    crops[i].direct = direct; crops[i].tx = itx; crops[i].ty = ity; crops[i].pad = 0;
 }
 
 __device__ __forceinline__ unsigned char clamp_u8_trunc(float x) { return x < 255.0f ? (x > 0.0f ? (unsigned char)x : 0) : 255; }
@@ -144,7 +156,7 @@ __device__ __forceinline__ void crop_pixel(const CropDev& c, int x, int y, unsig
 struct CropTotals { int n, rows, overflow, pad; unsigned long long bytes; };   // written by crop_scan_kernel
 template <bool VEC>
 __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restrict__ crops, const int* __restrict__ row_prefix, int n_crops,
-                                                         int total_rows, unsigned char* __restrict__ pix, const CropTotals* __restrict__ totals) {
+                                                         int total_rows, unsigned char* __restrict__ pix, const CropTotals* __restrict__ totals, int lazy) {
     if (totals) {   // device-built descriptor table: the sizes come from the device, the grid from the host's row hint
         if (totals->overflow) return;
         n_crops = totals->n; total_rows = totals->rows;
@@ -155,6 +167,7 @@ __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restric
     const int k = rt_find_segment(row_prefix, n_crops, ru);
     const CropDev& c = crops[k];
     if (c.status != RETTO_B200_OK) return;
+    if (lazy && c.direct) return;   // session path: the batch build reads the page itself (rec_batch.cu bb_px<true>); retto_b200_crop_fetch materialises on demand
     const int y = ru - row_prefix[k];
     const int w = c.rot ? c.h : c.w, h = c.rot ? c.w : c.h;  // un-rotated warp size
     if (c.cls == 0 && !c.rot && c.t[2] == floorf(c.t[2]) && c.t[5] == floorf(c.t[5]) && fabsf(c.t[2]) < 1e6f && fabsf(c.t[5]) < 1e6f) {
@@ -259,6 +272,7 @@ __global__ void __launch_bounds__(128) crop_dims_kernel(const retto_b200_box* __
 #pragma unroll
     for (int k = 0; k < 9; ++k) c.t[k] = 0.0f;
     c.cls = 0; c.w = cw; c.h = ch; c.rot = rot; c.status = status; c.offset = 0;
+    c.direct = 0; c.tx = 0; c.ty = 0; c.pad = 0;
     crops[i] = c;
     flip_flags[i] = 0;
 }
@@ -362,7 +376,7 @@ static retto_b200_status crop_launch_impl(retto_b200_ctx* ctx, int n, retto_b200
         if (!c.page || c.page_h <= 0 || c.page_w <= 0) { ctx->stage_slots[slot].busy = false; ctx->crops.clear(); ctx->set_error("crop_boxes: bad job " + std::to_string(i)); return RETTO_B200_ERR_INVALID_ARG; }
         memcpy(c.box, box, sizeof(float) * 8);
         for (int k = 0; k < 9; ++k) c.t[k] = 0.0f;
-        c.cls = 0;
+        c.cls = 0; c.direct = 0; c.tx = 0; c.ty = 0; c.pad = 0;
         rt_crop_dims(c.box, &c.w, &c.h, &c.rot);
         c.status = RETTO_B200_OK;
         c.offset = off;
@@ -386,10 +400,11 @@ static retto_b200_status crop_launch_impl(retto_b200_ctx* ctx, int n, retto_b200
     RT_LAUNCH_CHECK(ctx);
     if (rows > 0) {
         RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
-        if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr);
-        else crop_rows_kernel<false><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr);
+        if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr, ctx->crops_lazy ? 1 : 0);
+        else crop_rows_kernel<false><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr, ctx->crops_lazy ? 1 : 0);
         RT_LAUNCH_CHECK(ctx);
     }
+    ctx->crop_launch.d_prefix = d_prefix; ctx->crop_launch.n = n; ctx->crop_launch.rows = rows; ctx->crop_launch.d_totals = nullptr;
     // projection degeneracy is only known on the device: statuses (strided gather of one int per crop) come back async
     RT_CUDA_OK(ctx, ctx->h_crops.ensure(sizeof(int) * (size_t)n));
     RT_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_crops.p, sizeof(int), &d_crops[0].status, sizeof(CropDev), sizeof(int), n, cudaMemcpyDeviceToHost, st));
@@ -471,9 +486,10 @@ retto_b200_status rt_crop_enqueue_device(retto_b200_ctx* ctx, const retto_b200_b
     const int row_hint = std::max(ctx->crop_rows_seen_max + ctx->crop_rows_seen_max / 4, 8192);
     ctx->crop_dev_row_cap = (row_hint + 7) / 8 * 8;
     RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
-    if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot);
-    else crop_rows_kernel<false><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot);
+    if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot, ctx->crops_lazy ? 1 : 0);
+    else crop_rows_kernel<false><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot, ctx->crops_lazy ? 1 : 0);
     RT_LAUNCH_CHECK(ctx);
+    ctx->crop_launch.d_prefix = d_prefix; ctx->crop_launch.n = 0; ctx->crop_launch.rows = ctx->crop_dev_row_cap; ctx->crop_launch.d_totals = d_tot;
     ctx->crop_dev_cap = cap_crops;
     ctx->crop_dev_cap_bytes = ctx->d_crop_pix.cap;
     ctx->crop_dev_desc_bytes = desc_bytes;
@@ -523,6 +539,7 @@ extern "C" retto_b200_status retto_b200_crop_boxes(retto_b200_ctx* ctx, const re
                                                    retto_b200_crop_info* h_infos) {
     RtDeviceGuard _dg(ctx);
     if (!ctx || n < 0 || (n > 0 && (!h_jobs || !h_infos))) return RETTO_B200_ERR_INVALID_ARG;
+    ctx->crops_lazy = getenv("RETTO_B200_CROP_LAZY") != nullptr;   // stage API: crops are materialised (tests may ask for the session's lazy mode)
     RT_TRY(rt_crop_launch(ctx, h_jobs, n, h_infos));
     return rt_crop_finish(ctx, h_infos, true);
 }
@@ -540,6 +557,14 @@ extern "C" retto_b200_status retto_b200_crop_fetch(retto_b200_ctx* ctx, int32_t 
     const retto_b200_ctx::CropHost& c = ctx->crops[i];
     const int n_px = c.w * c.h;
     if (n_px == 0) return RETTO_B200_OK;
+    if (ctx->crops_lazy && ctx->crop_launch.d_prefix) {   // direct crops were left to the batch build: materialise them now
+        const retto_b200_ctx::CropLaunch& cl = ctx->crop_launch;
+        RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
+        crop_rows_kernel<true><<<(std::max(cl.rows, 1) + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_crop_descs.as<CropDev>(), cl.d_prefix, cl.n, cl.rows, ctx->d_crop_pix.as<unsigned char>(),
+                                                                                      reinterpret_cast<const CropTotals*>(cl.d_totals), 0);
+        RT_LAUNCH_CHECK(ctx);
+        ctx->crops_lazy = false;
+    }
     int flip = 0;
     RT_CUDA_OK(ctx, cudaMemcpyAsync(&flip, ctx->d_crop_flip.as<int>() + i, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -25,6 +25,8 @@
 #define ROWCAP 131072        // row-table entries per page
 #define MAX_OFFSET_PTS 256   // points of one unclipped polygon
 
+#define RUN_CAP 6144                       // runs per page held in shared memory by ccl_runs_kernel (88 KB: two blocks per SM)
+struct RunRec { int key; int x1; };        // key = y * W + x0 (raster index of the first pixel), x1 = last pixel
 struct BoxCand {
     float xy[8];
     float score;
@@ -779,6 +781,70 @@ __global__ void hole_rows_kernel(HoleArgs h, const unsigned char* __restrict__ b
     if (bm[p - pg.w]) { atomicMin(&rt[y - 1 - cr.ymin].x, x); atomicMax(&rt[y - 1 - cr.ymin].y, x); }
     if (bm[p + pg.w]) { atomicMin(&rt[y + 1 - cr.ymin].x, x); atomicMax(&rt[y + 1 - cr.ymin].y, x); }
 }
+// Outer borders on pages with holes.  imageproc's scan starts an outer border at a pixel with a zero to its LEFT (x > 0), or — typed
+// "hole" but still the outer border — at a pixel with a zero to its RIGHT (x + 1 < width), provided the pixel has not been marked by an
+// earlier trace.  A run start / end that faces a HOLE of its own component never qualifies: the hole's border was traced (and its pixels
+// marked) from the pixel left of the hole's first pixel, which precedes every other pixel around the hole in raster order.  So the
+// discovery key of a component is the minimum over run starts / ends that face background the component does not enclose (frame-
+// connected background, or the hole of ANOTHER component in which this one is an island); a component that
+// touches x = 0 in its first row and otherwise only faces its own holes (a page-filling background with letters as holes) is never
+// discovered at all.  ccl_runs / ccl_flatten computed the key over all starts / ends (exact when the page has no holes); these three
+// kernels recompute it for the pages the hole path runs on, using the background labelling that path has just built.
+__device__ __forceinline__ int root_of_fg_pixel(bool run_path, const RunRec* __restrict__ psorted, const int* __restrict__ plabel, int n_runs,
+                                                const int* __restrict__ lab, int p) {
+    if (!run_path) return lab[p];      // run starts / ends are resolved to the root by ccl_flatten
+    int lo = 0, hi = n_runs;           // last run with key <= p
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (psorted[mid].key <= p) lo = mid; else hi = mid; }
+    return plabel[lo];
+}
+__global__ void outer_key_init_kernel(HoleArgs h, const PageCounters* __restrict__ counters, const CompRec* __restrict__ comps, int max_comps,
+                                      int* __restrict__ key_at) {
+    const int page = h.flag_pages[blockIdx.y];
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (counters[page].status == RETTO_B200_ERR_CAPACITY || id >= counters[page].n_roots) return;
+    key_at[h.pages[page].px_base + comps[(size_t)page * max_comps + id].root] = 0x7fffffff;
+}
+__global__ void outer_key_scan_kernel(HoleArgs h, const unsigned char* __restrict__ bitmap, const int* __restrict__ bgl, const int* __restrict__ labels,
+                                      const PageCounters* __restrict__ counters, int run_path, const RunRec* __restrict__ runs,
+                                      int* __restrict__ key_at) {
+    int page, p; DetPostPage pg;
+    if (!hole_px(h, page, pg, p)) return;
+    const unsigned char* bm = bitmap + pg.px_base;
+    if (!bm[p] || counters[page].status == RETTO_B200_ERR_CAPACITY) return;
+    const int y = p / pg.w, x = p - y * pg.w;
+    const bool left0 = x > 0 && !bm[p - 1], right0 = x + 1 < pg.w && !bm[p + 1];
+    if (!left0 && !right0) return;
+    const RunRec* prun = runs ? runs + (size_t)page * 3 * RUN_CAP : nullptr;
+    const RunRec* psorted = prun ? prun + RUN_CAP : nullptr;
+    const int* plabel = prun ? reinterpret_cast<const int*>(prun + 2 * RUN_CAP) : nullptr;
+    const int n_runs = counters[page].n_runs;
+    const int* lab = labels + pg.px_base;
+    const int root = root_of_fg_pixel(run_path != 0, psorted, plabel, n_runs, lab, p);
+    // the background region a start / end faces: frame-connected -> the pixel starts the border; a hole -> only if this component does
+    // NOT enclose it (an island inside another component's hole).  The encloser of a hole is the component of the foreground pixel left
+    // of the hole's first pixel (= its root: labels are minimum raster indices).
+    auto faces_outside = [&](int q) {
+        const int br = bgl[pg.px_base + q];
+        if (lab[br] == -2) return true;
+        return root_of_fg_pixel(run_path != 0, psorted, plabel, n_runs, lab, br - 1) != root;
+    };
+    bool cand = false;
+    if (left0 && faces_outside(p - 1)) cand = true;
+    if (!cand && right0 && faces_outside(p + 1)) cand = true;
+    if (!cand) return;
+    atomicMin(&key_at[pg.px_base + root], p);
+}
+__global__ void outer_key_apply_kernel(HoleArgs h, const PageCounters* __restrict__ counters, const CompRec* __restrict__ comps, int max_comps,
+                                       const int* __restrict__ key_at, BoxCand* __restrict__ cand) {
+    const int page = h.flag_pages[blockIdx.y];
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (counters[page].status == RETTO_B200_ERR_CAPACITY || id >= counters[page].n_roots) return;
+    const int nk = key_at[h.pages[page].px_base + comps[(size_t)page * max_comps + id].root];
+    BoxCand& b = cand[(size_t)page * max_comps + id];
+    if (nk == b.key) return;
+    b.key = nk;
+    if (nk == 0x7fffffff) { b.valid = 0; b.status = 6; b.st0 = 6; }   // only ever faces its own holes: find_contours never starts its outer border
+}
 __global__ void hole_restore_kernel(HoleArgs h, int* __restrict__ labels) {
     int page, p; DetPostPage pg;
     if (!hole_px(h, page, pg, p)) return;
@@ -942,11 +1008,9 @@ __global__ void __launch_bounds__(128) pack_boxes_kernel(int n_pages, const Page
 //                     last row / discovery key, row-table allocation and per-row extremes
 // The pixel label plane is not needed downstream; retto_b200_det_post_fetch_labels materialises it from the runs.
 // A page with more runs than the on-chip table holds (noise) sends the batch to the pixel path (kernels A-G above).
-#define RUN_CAP 6144                       // runs per page held in shared memory by ccl_runs_kernel (88 KB: two blocks per SM)
 #define RUN_ROW_MAX 256                    // runs in one image row handled on chip (insertion sort + linear neighbour scan)
 #define RUN_MAX_H 4096                     // rows of the per-row index (== the cap on max_det_side)
 #define RUN_X_MASK ((1 << 29) - 1)
-struct RunRec { int key; int x1; };        // key = y * W + x0 (raster index of the first pixel), x1 = last pixel
 
 // Same row walk as bitmap_runs_kernel (threshold, 2x2 dilate, bitmap store), but instead of a label plane it appends one
 // record per horizontal run of the 128-px strip row, emitted by the lane that holds the run's last pixel (run start
@@ -1734,6 +1798,22 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
             RT_LAUNCH_BEGIN(ctx, "bg_flatten_kernel");
             bg_flatten_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab);
             RT_LAUNCH_CHECK(ctx);
+            {   // discovery keys of the outer borders of these pages: only run starts / ends that face frame-connected background count
+                int max_r = 1;
+                for (int i : fp) max_r = std::max(max_r, std::min(h_cnt0[i].n_roots, max_comps));
+                const dim3 kg((max_r + 255) / 256, nf);
+                int* d_key = ctx->d_key_at.as<int>();
+                RT_LAUNCH_BEGIN(ctx, "outer_key_init_kernel");
+                outer_key_init_kernel<<<kg, 256, 0, st>>>(ha, d_cnt, d_comps, max_comps, d_key);
+                RT_LAUNCH_CHECK(ctx);
+                RT_LAUNCH_BEGIN(ctx, "outer_key_scan_kernel");
+                outer_key_scan_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab, d_cnt, ctx->dp_run_path ? 1 : 0,
+                                                        ctx->dp_run_path ? ctx->d_runs.as<RunRec>() : nullptr, d_key);
+                RT_LAUNCH_CHECK(ctx);
+                RT_LAUNCH_BEGIN(ctx, "outer_key_apply_kernel");
+                outer_key_apply_kernel<<<kg, 256, 0, st>>>(ha, d_cnt, d_comps, max_comps, d_key, d_cand);
+                RT_LAUNCH_CHECK(ctx);
+            }
             RT_LAUNCH_BEGIN(ctx, "hole_collect_kernel");
             hole_collect_kernel<<<g, 256, 0, st>>>(ha, d_bm, d_cid, d_lab, d_cnt, d_holes);
             RT_LAUNCH_CHECK(ctx);

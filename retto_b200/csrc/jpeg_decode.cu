@@ -258,9 +258,12 @@ __global__ void __launch_bounds__(256) jpeg_scan_kernel(const JpegDev* __restric
 //    are read through an aligned-pair funnel shift so the stream may start at any byte; a word holding 0xFF (stuffing or the
 //    marker that ends the interval) takes a byte-wise slow path.
 #define JH_LUT_BITS 10
+#define JH_SUB_SLOTS 16
 struct HuffDev {               // shared memory, one per distinct table of the file
     unsigned lut[1 << JH_LUT_BITS];
-    int maxcode[17];           // canonical code ranges for codes longer than the window
+    unsigned sub[JH_SUB_SLOTS * 64];   // second level: one 64-entry table (the 6 bits after the window) per 10-bit prefix of the long codes
+    int nsub;
+    int maxcode[17];           // canonical code ranges (table build, and the fallback when a table has more than JH_SUB_SLOTS long prefixes)
     int valoff[17];            // valptr - mincode
     unsigned char vals[256];
 };
@@ -274,7 +277,8 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
                                                               const int* __restrict__ block_first, const JpegTables* __restrict__ tables,
                                                               const unsigned* __restrict__ seg, const unsigned char* __restrict__ clean,
                                                               const unsigned* __restrict__ clean_len, short* __restrict__ coef) {
-    __shared__ HuffDev s_tab[6];     // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
+    extern __shared__ __align__(16) unsigned char jh_smem[];
+    HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);   // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
     __shared__ unsigned char s_zz[64];
     __shared__ int s_slot[6];
     const int fi = block_file[blockIdx.x];
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
                 H.maxcode[l] = raw.bits[l] ? code - 1 : -1;
                 code <<= 1;
             }
-            H.maxcode[0] = -1; H.valoff[0] = 0;
+            H.maxcode[0] = -1; H.valoff[0] = 0; H.nsub = 0;
         }
         for (int i = threadIdx.x; i < 256; i += JH_THREADS) H.vals[i] = raw.vals[i];
         __syncthreads();
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
                 const int code = i >> (JH_LUT_BITS - l);
                 if (code <= H.maxcode[l]) {
                     const unsigned sym = H.vals[(H.valoff[l] + code) & 255];
-                    const unsigned r = is_ac ? sym >> 4 : 0u, sz = is_ac ? sym & 15u : sym & 15u;
+                    const unsigned r = is_ac ? sym >> 4 : 0u, sz = sym & 15u;
                     if (l + (int)sz <= JH_LUT_BITS) {
                         const int bits = (i >> (JH_LUT_BITS - l - (int)sz)) & ((1 << sz) - 1);
                         const int v = sz ? jh_extend(bits, (int)sz) : 0;
@@ -318,6 +322,24 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
                     } else e = (unsigned)l | (r << 5) | (sz << 9);
                     break;
                 }
+            }
+            if (e == 0) {   // prefix of codes longer than the window: second-level table over the next 6 bits
+                const int slot = atomicAdd(&H.nsub, 1);
+                e = (unsigned)(slot < JH_SUB_SLOTS ? slot : 0xFFFF) << 16;
+                if (slot < JH_SUB_SLOTS)
+                    for (int t2 = 0; t2 < 64; ++t2) {
+                        const int code16 = (i << 6) | t2;
+                        unsigned e2 = 16u;   // no such code: skip 16 bits as symbol 0 (jdhuff.c: corrupt data)
+                        for (int l = JH_LUT_BITS + 1; l <= 16; ++l) {
+                            const int code = code16 >> (16 - l);
+                            if (code <= H.maxcode[l]) {
+                                const unsigned sym = H.vals[(H.valoff[l] + code) & 255];
+                                e2 = (unsigned)l | ((is_ac ? sym >> 4 : 0u) << 5) | ((sym & 15u) << 9);
+                                break;
+                            }
+                        }
+                        H.sub[slot * 64 + t2] = e2;
+                    }
             }
             H.lut[i] = e;
         }
@@ -329,7 +351,6 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
     const unsigned clen = clean_len[fi];
     const unsigned start = min(seg[f.seg_base + j], clen);
     const unsigned* wp = reinterpret_cast<const unsigned*>(base + (start & ~3u));
-    const unsigned* wend = reinterpret_cast<const unsigned*>(base + ((clen + 3u) & ~3u)) + 4;   // zero padding of K-J1 included
     unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
     unsigned nxt = __ldg(wp + 2);
     wp += 3;
@@ -358,15 +379,19 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
     while (m < m1) {
         const unsigned win = __funnelshift_l(w1, w0, o);          // the 32 bits at the read position
         unsigned e = tab->lut[win >> (32 - JH_LUT_BITS)];
-        if ((e & 31u) == 0) {   // a code longer than the window: canonical search (rare)
-            const unsigned top = win >> 16;
-            unsigned sym = 0, l = 16;
+        if ((e & 31u) == 0) {   // a code longer than the window
+            const unsigned slot = e >> 16;
+            if (slot < JH_SUB_SLOTS) e = tab->sub[slot * 64 + ((win >> 16) & 63u)];
+            else {              // more long prefixes than sub-tables (never with the standard tables): canonical search
+                const unsigned top = win >> 16;
+                unsigned sym = 0, l = 16;
 #pragma unroll 1
-            for (int q = JH_LUT_BITS + 1; q <= 16; ++q) {
-                const int code = (int)(top >> (16 - q));
-                if (code <= tab->maxcode[q]) { sym = tab->vals[(tab->valoff[q] + code) & 255]; l = q; break; }
+                for (int q = JH_LUT_BITS + 1; q <= 16; ++q) {
+                    const int code = (int)(top >> (16 - q));
+                    if (code <= tab->maxcode[q]) { sym = tab->vals[(tab->valoff[q] + code) & 255]; l = q; break; }
+                }
+                e = k == 0 ? (l | ((sym & 15u) << 9)) : (l | ((sym >> 4) << 5) | ((sym & 15u) << 9));
             }
-            e = k == 0 ? (l | ((sym & 15u) << 9)) : (l | ((sym >> 4) << 5) | ((sym & 15u) << 9));
         }
         unsigned L = e & 31u;
         const int r = (int)((e >> 5) & 15u), sz = (int)((e >> 9) & 15u);
@@ -380,7 +405,7 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
             o -= 32u;
             w0 = w1;
             w1 = __byte_perm(nxt, 0, 0x0123);
-            nxt = wp < wend ? __ldg(wp) : 0u;
+            nxt = __ldg(wp);     // unconditional (the clean arena is padded): a select here made the compiler consume the load at once
             ++wp;
         }
         if (k == 0) {
@@ -694,7 +719,11 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     RT_LAUNCH_CHECK(ctx);
     ctx->timer_stream = st;
     RT_LAUNCH_BEGIN(ctx, "jpeg_huff_kernel");
-    jpeg_huff_kernel<<<(unsigned)n_tblocks, JH_THREADS, 0, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len,
+    if (!ctx->jpeg_huff_attr_set) {
+        RT_CUDA_OK(ctx, cudaFuncSetAttribute(jpeg_huff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HuffDev) * 6)));
+        ctx->jpeg_huff_attr_set = true;
+    }
+    jpeg_huff_kernel<<<(unsigned)n_tblocks, JH_THREADS, sizeof(HuffDev) * 6, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len,
                                                                  ctx->d_jpeg_coef.as<short>());
     RT_LAUNCH_CHECK(ctx);
     ctx->timer_stream = nullptr;

@@ -10,14 +10,16 @@
 #include "common.cuh"
 #include "thumbnail.cuh"
 
-struct FlipReader {   // crops are stored RGBX, one aligned word per pixel
-    const uchar4* __restrict__ src;
+template <bool DIRECT> __device__ __forceinline__ unsigned bb_px(const unsigned char* __restrict__ base, int idx);
+template <bool DIRECT>
+struct FlipReaderT {   // generic-class reader: RGBX crop words, or the page itself for a direct crop (see bb_px)
+    const unsigned char* __restrict__ base;
     unsigned w, h;
-    int flip;
+    int flip, rstride, rbase;
     __device__ __forceinline__ uchar3 operator()(unsigned x, unsigned y) const {
         if (flip) { x = w - 1 - x; y = h - 1 - y; }
-        const uchar4 p = __ldg(src + (size_t)y * w + x);
-        return make_uchar3(p.x, p.y, p.z);
+        const unsigned p = bb_px<DIRECT>(base, (int)y * rstride + rbase + (int)x);
+        return make_uchar3((unsigned char)(p & 0xFFu), (unsigned char)((p >> 8) & 0xFFu), (unsigned char)((p >> 16) & 0xFFu));
     }
 };
 
@@ -90,19 +92,68 @@ struct BBShared {
     unsigned magic[BB_BB_MAXN + 1];
 };
 
-__global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
-                                                                 const CropDev* __restrict__ crops, const unsigned char* __restrict__ crop_pix,
-                                                                 const int* __restrict__ flip_flags, int use_flip, int img_h,
-                                                                 float* __restrict__ out, const unsigned k23) {
-    // k23 = 0x4B000000 comes in as a kernel parameter: a literal would be folded by ptxas into the PRMT immediate slot,
-    // which pushes the byte selector into a register that has to be re-materialised for every conversion
-    __shared__ BBShared sh;
-    const ChunkDev ck = chunks[blockIdx.x];
-    const LineDev ln = lines[ck.line];
-    const CropDev& c = crops[ln.crop];
+// Source pixel access.  DIRECT == false: the crop was materialised by crop_rows_kernel as RGBX words (one aligned load per pixel).
+// DIRECT == true: the crop is a pure translation of the page by whole pixels with every bicubic window inside the page
+// (CropDev::direct — axis-aligned boxes, the common case for text lines): cubic(p0,p1,p2,p3,0) == p1, so crop pixel (x, y) IS page
+// pixel (x + tx, y + ty) and the batch build reads the page itself — the crop is never written nor re-read (K7 and K8 fused).
+// A page pixel is 3 unaligned bytes: two aligned words + one funnel shift (byte 3 of the result is garbage; every consumer
+// selects bytes 0..2 by PRMT or multiplies byte 3 by zero in DP4A).
+template <bool DIRECT>
+__device__ __forceinline__ unsigned bb_px(const unsigned char* __restrict__ base, int idx) {
+    if (!DIRECT) return __ldg(reinterpret_cast<const unsigned*>(base) + idx);
+    const unsigned char* a = base + 3 * (size_t)(unsigned)idx;
+    const unsigned* w = reinterpret_cast<const unsigned*>(reinterpret_cast<uintptr_t>(a) & ~uintptr_t(3));
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), 8u * (unsigned)(reinterpret_cast<uintptr_t>(a) & 3u));
+}
+// two horizontally adjacent pixels idx, idx + 1 (DIRECT: 6 bytes out of three aligned words)
+template <bool DIRECT>
+__device__ __forceinline__ void bb_px2(const unsigned char* __restrict__ base, int idx, unsigned& p0, unsigned& p1) {
+    if (!DIRECT) {
+        const unsigned* w = reinterpret_cast<const unsigned*>(base) + idx;
+        p0 = __ldg(w); p1 = __ldg(w + 1);
+        return;
+    }
+    const unsigned char* a = base + 3 * (size_t)(unsigned)idx;
+    const unsigned* w = reinterpret_cast<const unsigned*>(reinterpret_cast<uintptr_t>(a) & ~uintptr_t(3));
+    const unsigned ph = (unsigned)(reinterpret_cast<uintptr_t>(a) & 3u);
+    const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    p0 = __funnelshift_r(w0, w1, 8u * ph);
+    p1 = __funnelshift_r(ph == 0 ? w0 : w1, ph == 0 ? w1 : w2, 8u * ((ph + 3u) & 3u));
+}
+
+// the pixels of source columns c0 and c1 (equal or neighbours; cl = the left one) of the row at index `row`
+template <bool DIRECT>
+__device__ __forceinline__ void bb_ff_pair(const unsigned char* __restrict__ base, int row, int c0, int c1, int cl, bool swp, bool same, unsigned& pa, unsigned& pb) {
+    if (!DIRECT) {
+        const unsigned* w = reinterpret_cast<const unsigned*>(base) + row;
+        pa = __ldg(w + c0); pb = __ldg(w + c1);
+        return;
+    }
+    unsigned a, b;
+    bb_px2<true>(base, row + cl, a, b);
+    pa = swp ? b : a;
+    pb = same ? pa : (swp ? a : b);
+}
+// the pixels of columns cl and cl + dx (dx = 0 or 1)
+template <bool DIRECT>
+__device__ __forceinline__ void bb_bb2_pair(const unsigned char* __restrict__ base, int idx, int dx, unsigned& pa, unsigned& pb) {
+    if (!DIRECT) {
+        const unsigned* w = reinterpret_cast<const unsigned*>(base) + idx;
+        pa = __ldg(w); pb = __ldg(w + dx);
+        return;
+    }
+    bb_px2<true>(base, idx, pa, pb);   // (for dx == 0 the second pixel is masked out of the sums by the caller)
+}
+
+template <bool DIRECT>
+__device__ __forceinline__ void bb_body(BBShared& sh, const ChunkDev ck, const LineDev ln, const CropDev& c, const unsigned char* __restrict__ crop_pix,
+                                        const int flip, int img_h, float* __restrict__ out, const unsigned k23) {
     const unsigned cw = (unsigned)c.w, chh = (unsigned)c.h;
-    const int flip = use_flip ? flip_flags[ln.crop] : 0;
     const int kind = ln.kind;
+    // pixel (x, y) of the crop lives at index y * rstride + rbase + x of `pbase` (RGBX words, or 3-byte page pixels)
+    const int rstride = DIRECT ? c.page_w : (int)cw;
+    const int rbase = DIRECT ? c.ty * c.page_w + c.tx : 0;
+    const unsigned char* __restrict__ pbase = DIRECT ? c.page : crop_pix + c.offset;
     for (int v = threadIdx.x; v < 256; v += BB_COLS) sh.lut[v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), 0.5f), 0.5f);
     if (threadIdx.x <= BB_BB_MAXN) sh.magic[threadIdx.x] = threadIdx.x ? magic_div20(threadIdx.x) : 0u;
     const float yr = __fdiv_rn((float)chh, (float)img_h);
@@ -111,13 +162,13 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
         RowS r;
         if (kind == BB_BB || kind == BB_BB2) {   // rows [lo, hi): the sums do not depend on the order, so a flip only moves the start
             const int ny = (int)(ay.hi - ay.lo);
-            r.o0 = (flip ? (int)chh - (int)ay.hi : (int)ay.lo) * (int)cw;
-            r.o1 = kind == BB_BB ? ny : r.o0 + (ny - 1) * (int)cw;   // BB: row count; BB2: offset of the second row (or the first again)
+            r.o0 = (flip ? (int)chh - (int)ay.hi : (int)ay.lo) * rstride + rbase;
+            r.o1 = kind == BB_BB ? ny : r.o0 + (ny - 1) * rstride;   // BB: row count; BB2: offset of the second row (or the first again)
             r.fv = 0.0f; r.omv = 0.0f;
         } else {
             const AxisS a = axis_small(ay, chh);
             const int j0 = flip ? (int)chh - 1 - a.i0 : a.i0, j1 = flip ? (int)chh - 1 - a.i1 : a.i1;
-            r.o0 = j0 * (int)cw; r.o1 = j1 * (int)cw;
+            r.o0 = j0 * rstride + rbase; r.o1 = j1 * rstride + rbase;
             if (kind == BB_FF) { r.fv = a.n ? 0.0f : a.fract; r.omv = a.n ? 1.0f : __fsub_rn(1.0f, a.fract); }   // (1, 0) for a 1-px block row
             else { r.fv = a.n ? -1.0f : a.fract; r.omv = __fsub_rn(1.0f, a.fract); }                              // fv < 0 marks a block row (BF)
             if (kind == BB_BF || kind == BB_BF4)
@@ -141,7 +192,6 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) { *d0 = 0.0f; *d1 = 0.0f; *d2 = 0.0f; }
         return;
     }
-    const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(crop_pix + c.offset);   // RGBX words
     const unsigned lut_biased = (unsigned)__cvta_generic_to_shared(sh.lut) - (k23 << 2);
     const float xr = __fdiv_rn((float)cw, (float)ln.resized_w);
     const ThumbAxis ax = thumb_axis(x, xr, cw);
@@ -153,22 +203,28 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
     // shared-memory tile per band of rows: slower, 1.01 ms.)
     {
         const unsigned first = ax.lo != ax.hi ? ax.lo : ax.hi - 1, last = ax.lo != ax.hi ? ax.hi - 1 : (ax.hi > cw - 1 ? cw - 1 : ax.hi);
-        const unsigned* __restrict__ pf = src + (flip ? cw - 1 - last : first);
-        for (unsigned r = 0; r < chh; ++r, pf += cw) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        const unsigned char* __restrict__ pf = pbase + (size_t)(DIRECT ? 3 : 4) * (size_t)(rbase + (int)(flip ? cw - 1 - last : first));
+        for (unsigned r = 0; r < chh; ++r, pf += (size_t)(DIRECT ? 3 : 4) * rstride) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
     }
 
     if (kind == BB_FF) {
         const AxisS xs = axis_small(ax, cw);
-        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - 1 - xs.i0 : xs.i0);
-        const unsigned* __restrict__ s1 = src + (flip ? (int)cw - 1 - xs.i1 : xs.i1);
+        // the two source columns are the same pixel or neighbours (i1 = i0 + 1; with the flip i1 lies LEFT of i0): one pair load per row
+        const int c0 = flip ? (int)cw - 1 - xs.i0 : xs.i0, c1 = flip ? (int)cw - 1 - xs.i1 : xs.i1;
+        const int cl = min(c0, c1);
+        const bool swp = c1 < c0, same = c1 == c0;
         const float fhu = xs.n ? 0.0f : xs.fract, omfhu = xs.n ? 1.0f : __fsub_rn(1.0f, xs.fract);
-        // software pipeline: the four source words of row y+1 are in flight while row y is mixed and stored
+        // software pipeline: the source words of row y+1 are in flight while row y is mixed and stored
         RowS r = sh.row[0];
-        unsigned p00 = __ldg(s0 + r.o0), p10 = __ldg(s1 + r.o0), p01 = __ldg(s0 + r.o1), p11 = __ldg(s1 + r.o1);
+        unsigned p00, p10, p01, p11;
+        bb_ff_pair<DIRECT>(pbase, r.o0, c0, c1, cl, swp, same, p00, p10);
+        bb_ff_pair<DIRECT>(pbase, r.o1, c0, c1, cl, swp, same, p01, p11);
 #pragma unroll 2
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
             const RowS rn = sh.row[y + 1 < img_h ? y + 1 : y];
-            const unsigned n00 = __ldg(s0 + rn.o0), n10 = __ldg(s1 + rn.o0), n01 = __ldg(s0 + rn.o1), n11 = __ldg(s1 + rn.o1);
+            unsigned n00, n10, n01, n11;
+            bb_ff_pair<DIRECT>(pbase, rn.o0, c0, c1, cl, swp, same, n00, n10);
+            bb_ff_pair<DIRECT>(pbase, rn.o1, c0, c1, cl, swp, same, n01, n11);
             const float f_tr = __fmul_rn(r.fv, fhu), f_tl = __fmul_rn(r.fv, omfhu), f_br = __fmul_rn(r.omv, fhu), f_bl = __fmul_rn(r.omv, omfhu);
 #define RT_BL(sel) lut_trunc(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f_br, u8f(p10, k23, sel)), __fmul_rn(f_tr, u8f(p11, k23, sel))), \
                                                  __fmul_rn(f_bl, u8f(p00, k23, sel))), __fmul_rn(f_tl, u8f(p01, k23, sel))), lut_biased)
@@ -182,15 +238,18 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
         // windows of 1-2 x 1-2 pixels (scale ratios in [1, 2]): always four loads (a missing column / row repeats the
         // first one and is masked out of the sums), n = 1, 2 or 4 so the division is a shift; row y+1 prefetched
         const int nx = (int)(ax.hi - ax.lo);
-        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
-        const unsigned* __restrict__ s1 = s0 + (nx - 1);
+        const int cl = flip ? (int)cw - (int)ax.hi : (int)ax.lo;   // left column of the window; the right one (nx == 2) is its neighbour
         const unsigned mx = nx > 1 ? 0xFFFFFFFFu : 0u;
         RowS r = sh.row[0];
-        unsigned w00 = __ldg(s0 + r.o0), w10 = __ldg(s1 + r.o0), w01 = __ldg(s0 + r.o1), w11 = __ldg(s1 + r.o1);
+        unsigned w00, w10, w01, w11;
+        bb_bb2_pair<DIRECT>(pbase, r.o0 + cl, nx - 1, w00, w10);
+        bb_bb2_pair<DIRECT>(pbase, r.o1 + cl, nx - 1, w01, w11);
 #pragma unroll 2
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
             const RowS rn = sh.row[y + 1 < img_h ? y + 1 : y];
-            const unsigned n00 = __ldg(s0 + rn.o0), n10 = __ldg(s1 + rn.o0), n01 = __ldg(s0 + rn.o1), n11 = __ldg(s1 + rn.o1);
+            unsigned n00, n10, n01, n11;
+            bb_bb2_pair<DIRECT>(pbase, rn.o0 + cl, nx - 1, n00, n10);
+            bb_bb2_pair<DIRECT>(pbase, rn.o1 + cl, nx - 1, n01, n11);
             const unsigned my = r.o1 != r.o0 ? 0xFFFFFFFFu : 0u;
             const unsigned shn = (mx & 1u) + (my & 1u), h2 = (1u << shn) >> 1;
             w10 &= mx; w01 &= my; w11 &= mx & my;
@@ -206,15 +265,15 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
     }
     if (kind == BB_BB) {
         const int nx = (int)(ax.hi - ax.lo);
-        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
+        const int cl = flip ? (int)cw - (int)ax.hi : (int)ax.lo;
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
             const RowS r = sh.row[y];
             const int ny = r.o1;
-            const unsigned* __restrict__ p = s0 + r.o0;
+            int p = r.o0 + cl;
             unsigned a0 = 0, a1 = 0, a2 = 0;
-            for (int j = 0; j < ny; ++j, p += cw)
+            for (int j = 0; j < ny; ++j, p += rstride)
                 for (int i = 0; i < nx; ++i) {
-                    const unsigned w = __ldg(p + i);
+                    const unsigned w = bb_px<DIRECT>(pbase, p + i);
                     a0 = __dp4a(w, 0x00000001u, a0); a1 = __dp4a(w, 0x00000100u, a1); a2 = __dp4a(w, 0x00010000u, a2);
                 }
             const unsigned n = (unsigned)(nx * ny), h2 = n >> 1, M = sh.magic[n];
@@ -228,18 +287,18 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
         // column blocks of at most 4 pixels: a fixed set of 2 x 4 predicated loads per output row, those of row y+1 in
         // flight while row y is summed and mixed (consecutive output rows mostly re-read the same two source rows: L1 hits)
         const int nx = (int)(ax.hi - ax.lo);
-        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
+        const int s0 = flip ? (int)cw - (int)ax.hi : (int)ax.lo;
         const unsigned h2 = (unsigned)nx >> 1, M = sh.magic[nx];
         const bool e1 = nx > 1, e2 = nx > 2, e3 = nx > 3;
         RowS r = sh.row[0];
-        unsigned p0 = __ldg(s0 + r.o0), p1 = e1 ? __ldg(s0 + r.o0 + 1) : 0u, p2 = e2 ? __ldg(s0 + r.o0 + 2) : 0u, p3 = e3 ? __ldg(s0 + r.o0 + 3) : 0u;
-        unsigned q0 = __ldg(s0 + r.o1), q1 = e1 ? __ldg(s0 + r.o1 + 1) : 0u, q2 = e2 ? __ldg(s0 + r.o1 + 2) : 0u, q3 = e3 ? __ldg(s0 + r.o1 + 3) : 0u;
+#define RT_LDP(i) bb_px<DIRECT>(pbase, (i))
+        unsigned p0 = RT_LDP(s0 + r.o0), p1 = e1 ? RT_LDP(s0 + r.o0 + 1) : 0u, p2 = e2 ? RT_LDP(s0 + r.o0 + 2) : 0u, p3 = e3 ? RT_LDP(s0 + r.o0 + 3) : 0u;
+        unsigned q0 = RT_LDP(s0 + r.o1), q1 = e1 ? RT_LDP(s0 + r.o1 + 1) : 0u, q2 = e2 ? RT_LDP(s0 + r.o1 + 2) : 0u, q3 = e3 ? RT_LDP(s0 + r.o1 + 3) : 0u;
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
             const RowS rn = sh.row[y + 1 < img_h ? y + 1 : y];
-            const unsigned* __restrict__ pn = s0 + rn.o0;
-            const unsigned* __restrict__ qn = s0 + rn.o1;
-            const unsigned np0 = __ldg(pn), np1 = e1 ? __ldg(pn + 1) : 0u, np2 = e2 ? __ldg(pn + 2) : 0u, np3 = e3 ? __ldg(pn + 3) : 0u;
-            const unsigned nq0 = __ldg(qn), nq1 = e1 ? __ldg(qn + 1) : 0u, nq2 = e2 ? __ldg(qn + 2) : 0u, nq3 = e3 ? __ldg(qn + 3) : 0u;
+            const int pn = s0 + rn.o0, qn = s0 + rn.o1;
+            const unsigned np0 = RT_LDP(pn), np1 = e1 ? RT_LDP(pn + 1) : 0u, np2 = e2 ? RT_LDP(pn + 2) : 0u, np3 = e3 ? RT_LDP(pn + 3) : 0u;
+            const unsigned nq0 = RT_LDP(qn), nq1 = e1 ? RT_LDP(qn + 1) : 0u, nq2 = e2 ? RT_LDP(qn + 2) : 0u, nq3 = e3 ? RT_LDP(qn + 3) : 0u;
             unsigned a0 = 0, a1 = 0, a2 = 0;
 #define RT_ACC(w, x0, x1, x2) x0 = __dp4a(w, 0x00000001u, x0); x1 = __dp4a(w, 0x00000100u, x1); x2 = __dp4a(w, 0x00010000u, x2)
             RT_ACC(p0, a0, a1, a2); RT_ACC(p1, a0, a1, a2); RT_ACC(p2, a0, a1, a2); RT_ACC(p3, a0, a1, a2);
@@ -262,15 +321,14 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
     }
     if (kind == BB_BF) {
         const int nx = (int)(ax.hi - ax.lo);
-        const unsigned* __restrict__ s0 = src + (flip ? (int)cw - (int)ax.hi : (int)ax.lo);
+        const int s0 = flip ? (int)cw - (int)ax.hi : (int)ax.lo;
         const unsigned h2 = (unsigned)nx >> 1, M = sh.magic[nx];
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
             const RowS r = sh.row[y];
-            const unsigned* __restrict__ p = s0 + r.o0;
-            const unsigned* __restrict__ q = s0 + r.o1;
+            const int p = s0 + r.o0, q = s0 + r.o1;
             unsigned a0 = 0, a1 = 0, a2 = 0, c0 = 0, c1 = 0, c2 = 0;
             for (int i = 0; i < nx; ++i) {
-                const unsigned w = __ldg(p + i), u = __ldg(q + i);
+                const unsigned w = RT_LDP(p + i), u = RT_LDP(q + i);
                 a0 = __dp4a(w, 0x00000001u, a0); a1 = __dp4a(w, 0x00000100u, a1); a2 = __dp4a(w, 0x00010000u, a2);
                 c0 = __dp4a(u, 0x00000001u, c0); c1 = __dp4a(u, 0x00000100u, c1); c2 = __dp4a(u, 0x00010000u, c2);
             }
@@ -288,13 +346,29 @@ __global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev
         return;
     }
     {
-        const FlipReader rd{reinterpret_cast<const uchar4*>(src), cw, chh, flip};
+        const FlipReaderT<DIRECT> rd{pbase, cw, chh, flip, rstride, rbase};
         for (int y = 0; y < img_h; ++y, d0 += stride, d1 += stride, d2 += stride) {
             unsigned char px[3];
             thumbnail_pixel(rd, cw, chh, ax, sh.ay[y], px);
             *d0 = sh.lut[px[0]]; *d1 = sh.lut[px[1]]; *d2 = sh.lut[px[2]];
         }
     }
+}
+#undef RT_LDP
+
+__global__ void __launch_bounds__(BB_COLS, 8) build_batches_kernel(const LineDev* __restrict__ lines, const ChunkDev* __restrict__ chunks,
+                                                                 const CropDev* __restrict__ crops, const unsigned char* __restrict__ crop_pix,
+                                                                 const int* __restrict__ flip_flags, int use_flip, int img_h,
+                                                                 float* __restrict__ out, const unsigned k23, int allow_direct) {
+    // k23 = 0x4B000000 comes in as a kernel parameter: a literal would be folded by ptxas into the PRMT immediate slot,
+    // which pushes the byte selector into a register that has to be re-materialised for every conversion
+    __shared__ BBShared sh;
+    const ChunkDev ck = chunks[blockIdx.x];
+    const LineDev ln = lines[ck.line];
+    const CropDev& c = crops[ln.crop];
+    const int flip = use_flip ? flip_flags[ln.crop] : 0;
+    if (allow_direct && c.direct) bb_body<true>(sh, ck, ln, c, crop_pix, flip, img_h, out, k23);   // block-uniform
+    else bb_body<false>(sh, ck, ln, c, crop_pix, flip, img_h, out, k23);
 }
 
 // ---- K9 ------------------------------------------------------------------------------------------------
@@ -438,7 +512,7 @@ retto_b200_status rt_build_batches_launch(retto_b200_ctx* ctx, int32_t kind) {
     RT_LAUNCH_BEGIN(ctx, "build_batches_kernel");
     build_batches_kernel<<<(unsigned)ctx->bb_chunks[kind], BB_COLS, 0, ctx->stream>>>(d_lines, d_chunks, ctx->d_crop_descs.as<CropDev>(),
                                                                                     ctx->d_crop_pix.as<unsigned char>(), ctx->d_crop_flip.as<int>(),
-                                                                                    kind == 1 ? 1 : 0, img_h, buf.as<float>(), 0x4B000000u);
+                                                                                    kind == 1 ? 1 : 0, img_h, buf.as<float>(), 0x4B000000u, ctx->crops_lazy ? 1 : 0);
     RT_LAUNCH_CHECK(ctx);
     ctx->bb_chunks[kind] = 0;
     return RETTO_B200_OK;

@@ -280,6 +280,7 @@ retto_b200_status PageRun::mid() {
     cudaStream_t st = ctx->stream;
     const retto_b200_config& cfg = ctx->cfg;
     const bool dev_crops = getenv("RETTO_B200_HOST_CROP_TABLE") == nullptr;   // A/B + tests: the host-built descriptor table
+    ctx->crops_lazy = getenv("RETTO_B200_CROP_EAGER") == nullptr;             // direct crops are read from the page by the batch build (A/B: materialise all)
     std::vector<const uint8_t*> pp(n_pages);
     std::vector<int> ph(n_pages), pw(n_pages);
     for (int i = 0; i < n_pages; ++i) { pp[i] = ps[i].d_img; ph[i] = ps[i].h; pw[i] = ps[i].w; }

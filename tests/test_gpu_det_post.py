@@ -150,6 +150,20 @@ def test_hole_borders(ctx):
     b[50:54, 50:90] = 0.0
     b[70:73, 10:13] = 0.0
     maps.append(b)
+    # a page-filling foreground whose first row starts at x = 0, with letters as holes (an inverted page): imageproc never starts its
+    # outer border — every run start / end at x > 0 faces one of its own holes, whose border was traced first — so only the hole
+    # borders yield contours
+    c = np.full((120, 200), 0.9, np.float32)
+    c[20:40, 30:60] = 0.05
+    c[20:40, 80:130] = 0.05
+    c[70:100, 50:150] = 0.05
+    c[80:90, 90:110] = 0.9             # an island inside the third hole
+    maps.append(c)
+    # the same, but the blob leaves the frame further down (an L-shaped outside notch): the outer border IS discovered there, late
+    d = c.copy()
+    d[60:120, 170:200] = 0.05          # outside background reaching the right / bottom frame
+    d[50:56, 0:20] = 0.05              # and a notch on the left frame
+    maps.append(d)
     rng = np.random.default_rng(11)
     for _ in range(4):                 # random blobs: many irregular holes
         m = (rng.random((80, 120)) < 0.62).astype(np.uint8) * 255

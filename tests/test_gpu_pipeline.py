@@ -17,9 +17,16 @@ def _t(a):
 from _workers import NpWorker  # noqa: E402
 
 
-def test_crop_parity(ctx):
+@pytest.mark.parametrize("lazy", [False, True])
+def test_crop_parity(ctx, lazy, monkeypatch):
+    """lazy = the session's mode: direct crops (whole-pixel translations inside the page) are left to the batch build and only
+    materialised when retto_b200_crop_fetch asks for them"""
     import torch
     from oracle import oracle as O
+    if lazy:
+        monkeypatch.setenv("RETTO_B200_CROP_LAZY", "1")
+    else:
+        monkeypatch.delenv("RETTO_B200_CROP_LAZY", raising=False)
     rng = np.random.default_rng(0)
     page = rng.integers(0, 256, (700, 900, 3), dtype=np.uint8)
     boxes = []
@@ -123,13 +130,19 @@ def test_batches_and_cls_flip_parity(ctx):
     assert len({b.img_w for b in batches}) > 1
 
 
-@pytest.mark.parametrize("generic", [False, True])
-def test_batches_dims_matrix(ctx, generic, monkeypatch):
+@pytest.mark.parametrize("generic,lazy,page_w", [(False, False, 2000), (True, False, 2000), (False, True, 2000), (False, True, 2001), (True, True, 2003)])
+def test_batches_dims_matrix(ctx, generic, lazy, page_w, monkeypatch):
     """K8 over a matrix of crop sizes that reaches every class of build_batches_kernel (rec_batch.cu): up-scaling on
     both axes (FF), block means (BB: lines taller than 48 px), wide lines squeezed into 192 columns (BF), mixed /
     very large windows (generic) — each bit-exact against the oracle's resize_norm_image, with and without the
-    180-degree flip, and once more with every line forced through the generic thumbnail_pixel path."""
+    180-degree flip, and once more with every line forced through the generic thumbnail_pixel path.
+    lazy = the session's fused mode: these axis-aligned boxes are "direct" crops, so the batch build reads the 3-byte page pixels
+    itself (every byte phase: page widths 2000 / 2001 / 2003) instead of a materialised RGBX copy."""
     import torch
+    if lazy:
+        monkeypatch.setenv("RETTO_B200_CROP_LAZY", "1")
+    else:
+        monkeypatch.delenv("RETTO_B200_CROP_LAZY", raising=False)
     from oracle import oracle as O
     from oracle.pipeline import stable_order_desc_ratio
     if generic:
@@ -137,7 +150,7 @@ def test_batches_dims_matrix(ctx, generic, monkeypatch):
     else:
         monkeypatch.delenv("RETTO_B200_BB_GENERIC", raising=False)
     rng = np.random.default_rng(11)
-    page = rng.integers(0, 256, (1500, 2000, 3), dtype=np.uint8)
+    page = rng.integers(0, 256, (1500, page_w, 3), dtype=np.uint8)
     boxes = []
     for h in (6, 20, 31, 47, 48, 49, 60, 76, 97, 130, 200, 420):
         for w in (10, 40, 100, 191, 192, 193, 400, 777, 1100, 1900):
