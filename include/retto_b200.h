@@ -343,7 +343,7 @@ retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const retto_b200_pag
  * A unit without detections still reports its three (empty) stages.  The arrays belong to the context and are valid during the
  * call only.  pages[i].first_line indexes the unit's own arrays (box i <-> cls i <-> rec i, as in retto_b200_results).
  * Cost: two extra stream synchronisations per unit (the host must hold the Det / Cls results before it may continue), which is why
- * the batch path leaves the callback unset.  Pass fn = NULL to clear. */
+ * the batch path leaves the callback unset.  Pass callback = NULL to clear. */
 typedef struct retto_b200_stage_result {
     int32_t stage;                          /* 0 Det, 1 Cls, 2 Rec */
     int32_t first_page;                     /* index of the unit's first page in the h_pages array of the run_pages call */
@@ -357,7 +357,7 @@ typedef struct retto_b200_stage_result {
     const float* rec_scores;                /* stage 2 */
 } retto_b200_stage_result;
 typedef void (*retto_b200_stage_fn)(void* user, const retto_b200_stage_result* result);
-retto_b200_status retto_b200_set_stage_callback(retto_b200_ctx* ctx, retto_b200_stage_fn fn, void* user);
+retto_b200_status retto_b200_set_stage_callback(retto_b200_ctx* ctx, retto_b200_stage_fn callback, void* user);
 
 /* run_pages pipeline: lanes = 1 (default: units run back to back on the context's own stream) or 2;
  * unit_pages = pages per unit (0 = default: 64 device-resident / 32 host-resident pages).  0 keeps the default. */

@@ -214,7 +214,6 @@ struct retto_b200_ctx {
     std::vector<int> dp_ncomp;
     std::vector<int> dp_nruns;           // per page: runs in the run table of the last det_postprocess
     std::vector<char> dp_labels_final;   // per page: run-interior labels resolved (lazily, by fetch_labels)
-    std::vector<int32_t> dbg_extra;
     bool dp_trace_enabled = false, dp_trace_valid = false;
     DevBuf d_trace;
     std::vector<int> dp_holes;   // per page: #hole borders of the last det_postprocess (components - Euler number)

@@ -27,6 +27,14 @@
 
 #define RUN_CAP 6144                       // runs per page held in shared memory by ccl_runs_kernel (88 KB: two blocks per SM)
 struct RunRec { int key; int x1; };        // key = y * W + x0 (raster index of the first pixel), x1 = last pixel
+// non-finite probe of the probability map (PageCounters::nonfinite): a running NaN-propagating maximum of |v| — one FMNMX3.NAN per
+// two pixels (the |.| is an operand modifier) — that ends up NaN or +Inf iff some probability is NaN / +-Inf
+__device__ __forceinline__ float nf_max3(float m, float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(fabsf(a)), "f"(fabsf(b)));
+    return r;
+}
+__device__ __forceinline__ bool nf_bad(float m) { return !(m <= 3.402823466e+38f); }
 struct BoxCand {
     float xy[8];
     float score;
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
     const int x0 = s * TILE_W, x = x0 + lane * 4;
     const int y0 = rb * TILE_H, y1 = min(y0 + TILE_H, H);
     unsigned char* bm = bitmap + pg.px_base;
-    float nf = 0.0f;   // v * 0 accumulates to NaN iff some loaded probability is NaN / +-Inf (see PageCounters::nonfinite)
+    float nf = 0.0f;   // running NaN-propagating max of |v| over the loaded probabilities (see nf_max3 / PageCounters::nonfinite)
     int* lab = labels + pg.px_base;
     int* ymax_at = cid_at + pg.px_base;   // root-indexed slots, initialised at every run start (a root is always one)
     int* keyp = key_at + pg.px_base;
@@ -98,12 +106,12 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
             if (x < W) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(row + x));
                 t = (v.x > thr ? 1u : 0u) | (v.y > thr ? 2u : 0u) | (v.z > thr ? 4u : 0u) | (v.w > thr ? 8u : 0u);
-                nf = __fmaf_rn(v.x, 0.0f, nf); nf = __fmaf_rn(v.y, 0.0f, nf); nf = __fmaf_rn(v.z, 0.0f, nf); nf = __fmaf_rn(v.w, 0.0f, nf);
+                nf = nf_max3(nf_max3(nf, v.x, v.y), v.z, v.w);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (x + j < W) { const float v = __ldg(row + x + j); nf = __fmaf_rn(v, 0.0f, nf); if (v > thr) t |= 1u << j; }
+                if (x + j < W) { const float v = __ldg(row + x + j); nf = nf_max3(nf, v, v); if (v > thr) t |= 1u << j; }
         }
         unsigned left = __shfl_up_sync(RT_FULL, (t >> 3) & 1u, 1);
         if (lane == 0) left = (x0 > 0 && __ldg(row + x0 - 1) > thr) ? 1u : 0u;
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(128) bitmap_runs_kernel(const DetPostPage* __r
     }
     const unsigned anyw = __ballot_sync(RT_FULL, any != 0);
     if (lane == 0) tileflags[tile] = anyw ? 1 : 0;
-    if (__any_sync(RT_FULL, nf != nf) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
+    if (__any_sync(RT_FULL, nf_bad(nf)) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
 }
 
 // neighbourhood bits of a 4-pixel group for rows y (c) and y-1 (u): bit k = pixel x-1+k, k = 0..5
@@ -1029,7 +1037,7 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
     unsigned char* bm = bitmap + pg.px_base;
     const float* __restrict__ prob = pg.prob;
     RunRec* prun = runs + (size_t)page * 3 * RUN_CAP;
-    float nf = 0.0f;   // v * 0 accumulates to NaN iff some loaded probability is NaN / +-Inf (see PageCounters::nonfinite)
+    float nf = 0.0f;   // running NaN-propagating max of |v| over the loaded probabilities (see nf_max3 / PageCounters::nonfinite)
 
     // raw (float4, left-edge scalar) of one row; the threshold / shuffles are applied when the row is consumed, so the
     // loads of row y+1 are in flight while row y is processed
@@ -1045,7 +1053,6 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
             if (x + 2 < W) r.v.z = __ldg(row + x + 2);
             if (x + 3 < W) r.v.w = __ldg(row + x + 3);
         }
-        nf = __fmaf_rn(r.v.x, 0.0f, nf); nf = __fmaf_rn(r.v.y, 0.0f, nf); nf = __fmaf_rn(r.v.z, 0.0f, nf); nf = __fmaf_rn(r.v.w, 0.0f, nf);
         if (lane == 0 && x0 > 0) r.l = __ldg(row + x0 - 1);
         return r;
     };
@@ -1067,6 +1074,7 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
     for (int y = y0; y < y1; ++y) {
         const Raw rawc = nxt;
         nxt = fetch(y + 1);
+        nf = nf_max3(nf_max3(nf, rawc.v.x, rawc.v.y), rawc.v.z, rawc.v.w);   // lanes beyond the page hold zeros
         const unsigned cur = bits5(rawc, true);
         unsigned nib;
         if (dilate) {
@@ -1115,7 +1123,7 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
         for (int k = 0; k < cnt; ++k)
             if (base + k < RUN_CAP) prun[base + k] = RunRec{y * W + starts[k], ends[k]};
     }
-    if (__any_sync(RT_FULL, nf != nf) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
+    if (__any_sync(RT_FULL, nf_bad(nf)) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
 }
 
 // A'' (default): the same stage with one warp per 256-px strip and the row held as EIGHT warp-uniform 32-bit words —
@@ -1125,7 +1133,7 @@ __global__ void __launch_bounds__(128) bitmap_runs2_kernel(const DetPostPage* __
 // instructions per 128-px row and is issue-bound at 73 % issue utilisation; this form needs about half per pixel).
 // Runs are buffered per warp in shared memory and appended to the page's run table with ONE atomic per tile.
 #define BR3_BUF 96
-template <bool ALIGNED, int NW, int MINB>   // NW words of 32 pixels per strip row (4: 128-px strips on the tile grid of the pixel path, 8: 256-px strips)
+template <bool ALIGNED, int NW, int MINB, bool PROBE = true>   // NW words of 32 pixels per strip row (4: 128-px strips on the tile grid of the pixel path, 8: 256-px strips)
 __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPage* __restrict__ pages, const int* __restrict__ tile_prefix,
                                                             int n_pages, int total_tiles, float thr, int dilate,
                                                             unsigned char* __restrict__ bitmap, RunRec* __restrict__ runs,
@@ -1160,26 +1168,21 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
     };
     const int nv = W - x0;                  // pixels of the strip inside the page (only the last strip of a row is partial)
     const bool partial = nv < SW;
-    float nf = 0.0f;   // v * 0 accumulates to NaN iff some loaded probability is NaN / +-Inf (see PageCounters::nonfinite)
+    float nf = 0.0f;   // running NaN-propagating max of |v| over the loaded probabilities (see nf_max3 / PageCounters::nonfinite)
     struct Raw { float v[NW]; float l; };
     auto fetch = [&](int y) -> Raw {
         Raw r;
 #pragma unroll
-        for (int j = 0; j < NW; ++j) r.v[j] = -CUDART_INF_F;   // outside the page: below every threshold
-        r.l = -CUDART_INF_F;
+        for (int j = 0; j < NW; ++j) r.v[j] = -3.0e38f;   // outside the page: below every threshold (finite: the non-finite probe sees these too)
+        r.l = -3.0e38f;
         if (y < 0 || y >= y1) return r;
         const float* row = prob + (size_t)y * W + x0 + lane;
         if (!partial) {   // full strip (all but the last of a page row): unpredicated loads
 #pragma unroll
             for (int j = 0; j < NW; ++j) r.v[j] = __ldg(row + 32 * j);
-            // non-finite probe: a pairwise sum tree (NaN and +-Inf propagate; a finite overflow would only send the page down the exact
-            // — still correct — score path) and ONE fused multiply by zero per row, off the load -> ballot chain
-            float t0 = __fadd_rn(r.v[0], r.v[1 % NW]), t1 = __fadd_rn(r.v[2 % NW], r.v[3 % NW]);
-            if (NW == 8) { t0 = __fadd_rn(t0, __fadd_rn(r.v[4 % NW], r.v[5 % NW])); t1 = __fadd_rn(t1, __fadd_rn(r.v[6 % NW], r.v[7 % NW])); }
-            nf = __fmaf_rn(__fadd_rn(t0, t1), 0.0f, nf);
         } else {
 #pragma unroll
-            for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) { r.v[j] = __ldg(row + 32 * j); nf = __fmaf_rn(r.v[j], 0.0f, nf); }
+            for (int j = 0; j < NW; ++j) if (32 * j + lane < nv) r.v[j] = __ldg(row + 32 * j);
         }
         if (lane == 0 && x0 > 0) r.l = __ldg(row - 1);
         return r;
@@ -1197,6 +1200,11 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
     for (int y = y0; y < y1; ++y) {
         const Raw rc = nxt;
         nxt = fetch(y + 1);
+        if (PROBE) {   // probe the row being CONSUMED (its loads have landed): probing inside fetch() made the warp wait for the loads it had
+                       // just issued and cost 0.09 ms per 256 pages (the next row's loads are meant to fly during this row's work)
+#pragma unroll
+            for (int j = 0; j < NW; j += 2) nf = nf_max3(nf, rc.v[j], rc.v[j + 1]);
+        }
         unsigned d[NW];
         {
             const unsigned curL = __ballot_sync(RT_FULL, rc.l > thr) & 1u;
@@ -1274,7 +1282,7 @@ __global__ void __launch_bounds__(128, MINB) bitmap_runs3_kernel(const DetPostPa
         }
     }
     if (nbuf) flush();
-    if (__any_sync(RT_FULL, nf != nf) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
+    if (__any_sync(RT_FULL, nf_bad(nf)) && lane == 0) atomicOr(&counters[page].nonfinite, 1);
 }
 
 // B': one block per page.  Shared memory: sorted runs (key, x1) | parent | per-row index.
@@ -1663,7 +1671,8 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
             RT_LAUNCH_BEGIN(ctx, "bitmap_runs3_kernel");
             if (nw == 8) {   // 62 registers, 8 blocks per SM; capping the registers for 10 / 12 blocks spills and is slower (0.59 / 0.92 ms)
                 const int tgrid = (R.total_tiles2 + 3) / 4;
-                if (R.a8) bitmap_runs3_kernel<true, 8, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
+                if (getenv("RETTO_B200_NO_NF_PROBE") && R.a8) bitmap_runs3_kernel<true, 8, 8, false><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));   // A/B only
+                else if (R.a8) bitmap_runs3_kernel<true, 8, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
                 else bitmap_runs3_kernel<false, 8, 8><<<tgrid, 128, 0, st>>>(BR3_ARGS(d_tile2_prefix, R.total_tiles2));
             } else {
                 const int tgrid = (total_tiles + 3) / 4;
@@ -2035,33 +2044,10 @@ extern "C" retto_b200_status retto_b200_det_post_fetch_trace(retto_b200_ctx* ctx
     for (int i = 0; i < n; ++i) {
         h_key[i] = t[i].key; h_status[i] = t[i].status; h_sside1[i] = t[i].sside1; h_score[i] = t[i].score;
         for (int k = 0; k < 8; ++k) h_rect1[8 * i + k] = t[i].rect1[k];
-        if (ctx->dbg_extra.size() < (size_t)(10 * n)) ctx->dbg_extra.resize(10 * n);
-        for (int k = 0; k < 8; ++k) ctx->dbg_extra[10 * i + k] = t[i].rect2[k];
-        ctx->dbg_extra[10 * i + 8] = t[i].n_off;
-        memcpy(&ctx->dbg_extra[10 * i + 9], &t[i].dist, 4);
     }
     return RETTO_B200_OK;
 }
 
-extern "C" const int32_t* retto_b200_debug_extra(retto_b200_ctx* ctx) { return ctx ? ctx->dbg_extra.data() : nullptr; }
-
-// debug tap: raw CompRec table of a page (8 ints per component)
-extern "C" retto_b200_status retto_b200_debug_comps(retto_b200_ctx* ctx, int32_t page, int32_t* out, int32_t max_n) {
-    RtDeviceGuard _dg(ctx);
-    if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size()) return RETTO_B200_ERR_INVALID_ARG;
-    const int n = std::min(ctx->dp_ncomp[page], max_n);
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_comps.as<CompRec>() + (size_t)page * ctx->cfg.max_components_per_page, sizeof(CompRec) * n,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    return RETTO_B200_OK;
-}
-extern "C" retto_b200_status retto_b200_debug_rowtab(retto_b200_ctx* ctx, int32_t page, int32_t* out, int32_t n_rows) {
-    RtDeviceGuard _dg(ctx);
-    if (!ctx || page < 0 || page >= (int)ctx->dp_pages.size()) return RETTO_B200_ERR_INVALID_ARG;
-    RT_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_rowtab.as<int2>() + (size_t)page * ROWCAP, sizeof(int2) * n_rows, cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    return RETTO_B200_OK;
-}
 
 // batched variant used by the session: per-box (inv_w, inv_h, ori_w, ori_h), one launch, one sync
 __global__ void scale_clip_multi_kernel(retto_b200_box* b, const double4* __restrict__ prm, int n) {

@@ -23,6 +23,23 @@ def test_library_exports_every_declared_symbol():
     assert L.retto_b200_abi_version() == 2
 
 
+def test_rust_sys_crate_covers_the_whole_header():
+    """rust/retto-b200-sys/src/lib.rs is generated from include/retto_b200.h (tools/gen_rust_sys.py): it is up to date, and every
+    function, struct and status code the header declares appears in it (the extern block is complete, not a sample)"""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py"), "--check"]).returncode == 0
+    rs = open(os.path.join(ROOT, "rust", "retto-b200-sys", "src", "lib.rs")).read()
+    hdr = open(os.path.join(ROOT, "include", "retto_b200.h")).read()
+    for sym in _lib.EXPORTS:
+        assert re.search(r"pub fn %s\(" % sym, rs), sym
+    for st in re.findall(r"\} (retto_b200_\w+);", hdr):
+        assert ("pub struct %s" % st) in rs or ("pub type %s" % st) in rs, st
+    for code in re.findall(r"(RETTO_B200_ERR_\w+) = \d+", hdr):
+        assert ("pub const %s:" % code) in rs, code
+    assert 'pub type retto_b200_forward_fn = Option<unsafe extern "C" fn(' in rs and "pub type retto_b200_stage_fn" in rs
+
+
 def test_config_defaults_match_reference():
     c = _lib.Config()
     _lib.lib().retto_b200_config_default(C.byref(c))
