@@ -106,7 +106,7 @@ def _make_one(args):
     return dict(rgb=rgb, prob=prob, files=files, hw=(h, w))
 
 
-def make_workload(workload, n_unique, size, seed0, kinds):
+def make_workload(workload, n_unique, size, seed0, kinds, ranks=1):
     import multiprocessing as mp
     specs = []
     if workload == "pages1280":
@@ -118,7 +118,7 @@ def make_workload(workload, n_unique, size, seed0, kinds):
             short = max(64, int(round(long_side * rng.uniform(0.5, 1.0))))
             h, w = (long_side, short) if rng.random() < 0.5 else (short, long_side)
             specs.append((seed0 + i, h, w, kinds))
-    procs = min(len(specs), os.cpu_count() or 1, 32)
+    procs = max(1, min(len(specs), (os.cpu_count() or 1) // max(1, ranks), 32))   # every rank of a torchrun launch renders its own pages
     if procs > 1:
         with mp.get_context("fork").Pool(procs) as pool:
             return pool.map(_make_one, specs)
@@ -452,7 +452,7 @@ def main():
             bus = None
         numa_cores = bind_host_to_gpu(local_rank, bus)
     # the workload is generated BEFORE the process group exists (fork pool) and identically on every rank
-    work = make_workload(args.workload, U, S, 500 if mixed else 4 + 1000 * rank, kinds)
+    work = make_workload(args.workload, U, S, 500 if mixed else 4 + 1000 * rank, kinds, ranks=world)
     cpu_arm = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_arm = CpuArm(work, "dri_mcu_row", dict_text, cores)   # forked NOW, before this process creates its CUDA context; idle until the end
