@@ -468,14 +468,25 @@ __device__ __forceinline__ unsigned ji_range_limit(int x) {   // range_limit[x &
 }
 // 256 threads = 32 blocks of 8x8; thread (g, t): row t of the coefficient load, column t of pass 1, row t of pass 2
 __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDev* __restrict__ files, const JpegTables* __restrict__ tables,
+                                                        const unsigned* __restrict__ grp_prefix, int n_files,
                                                         const short* __restrict__ coef, unsigned char* __restrict__ planes) {
-    // `files` / `tables` point at the first file of the unit
+    // `files` / `tables` point at the first file of the unit; the grid is flat over the files' groups of 32 blocks (grp_prefix), so a
+    // batch of mixed page sizes launches no idle thread blocks; one binary search per thread block
     __shared__ short s_coef[32][72];
     __shared__ int s_ws[32][72];
+    __shared__ int s_fi;
+    if (grp_prefix) {
+        if (threadIdx.x == 0) {
+            int lo = 0, hi = n_files;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (grp_prefix[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+            s_fi = lo;
+        }
+        __syncthreads();
+    }
     const int g = threadIdx.x >> 3, t = threadIdx.x & 7;
-    const int fi = blockIdx.y;                       // grid: (32-block groups of the largest file, files)
+    const int fi = grp_prefix ? s_fi : (int)blockIdx.y;               // uniform batches: grid (groups, files), no search
     const JpegDev& f = files[fi];
-    const unsigned lb = blockIdx.x * 32u + g;        // block index inside the file
+    const unsigned lb = (grp_prefix ? blockIdx.x - grp_prefix[fi] : blockIdx.x) * 32u + g;        // block index inside the file
     const bool live = lb < f.n_blocks;
     const unsigned B = f.block_base + lb;
     int ci = 0;
@@ -584,10 +595,24 @@ __device__ __forceinline__ void jc_chroma8(const unsigned char* __restrict__ pl,
     }
 }
 __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* __restrict__ files, const unsigned char* __restrict__ planes,
-                                                                uint8_t* const* __restrict__ outs) {
+                                                                uint8_t* const* __restrict__ outs, const unsigned* __restrict__ unit_prefix, int n_files) {
     __shared__ unsigned s_rgb[JC_THREADS * 6 + 1];
-    const JpegDev& f = files[blockIdx.z];
-    const int y = blockIdx.y, xb = blockIdx.x * (blockDim.x * JC_PX);
+    __shared__ int s_fi;
+    int fi, y, xb;
+    const int chunk_px = (int)blockDim.x * JC_PX;
+    if (unit_prefix) {   // mixed page sizes: flat grid over (file, row, chunk of blockDim.x * 8 pixels), one binary search per thread block
+        if (threadIdx.x == 0) {
+            int lo = 0, hi = n_files;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (unit_prefix[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+            s_fi = lo;
+        }
+        __syncthreads();
+        fi = s_fi;
+        const int xchunks = (files[fi].X + chunk_px - 1) / chunk_px;
+        const int u = (int)(blockIdx.x - unit_prefix[fi]);
+        y = u / xchunks; xb = (u - y * xchunks) * chunk_px;
+    } else { fi = blockIdx.z; y = blockIdx.y; xb = blockIdx.x * chunk_px; }   // uniform batch: grid (x chunks, rows, files)
+    const JpegDev& f = files[fi];
     if (y >= f.Y || xb >= f.X) return;
     const int x0 = xb + threadIdx.x * JC_PX;
     // the sample planes are padded to whole blocks (stride wb*8 >= X rounded up to 8), so a thread with x0 < X may read its 8 samples
@@ -618,7 +643,7 @@ __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* _
     __syncthreads();
     const int npx = min((int)blockDim.x * JC_PX, f.X - xb);
     const int nbytes = 3 * npx;
-    unsigned char* gp = outs[blockIdx.z] + ((size_t)y * f.X + xb) * 3;
+    unsigned char* gp = outs[fi] + ((size_t)y * f.X + xb) * 3;
     const int head = min((int)((4u - ((unsigned)(uintptr_t)gp & 3u)) & 3u), nbytes);
     const unsigned char* sb = reinterpret_cast<const unsigned char*>(s_rgb);
     if ((int)threadIdx.x < head) gp[threadIdx.x] = sb[threadIdx.x];
@@ -736,21 +761,47 @@ retto_b200_status rt_jpeg_pixels_enqueue(retto_b200_ctx* owner, retto_b200_ctx* 
     const retto_b200_ctx::JpegBatch& JB = owner->jpeg;
     if (n <= 0) return RETTO_B200_OK;
     if (first < 0 || first + n > JB.n) { lane->set_error("jpeg decode: unit outside the decoded batch"); return RETTO_B200_ERR_INVALID_ARG; }
-    int max_x = 1, max_y = 1;
-    unsigned max_file_blocks = 1;
-    for (int i = first; i < first + n; ++i) { max_x = std::max(max_x, JB.X[i]); max_y = std::max(max_y, JB.Y[i]); max_file_blocks = std::max(max_file_blocks, JB.n_blocks[i]); }
-    RT_TRY(rt_upload(lane, lane->d_jpeg_out, d_out, sizeof(uint8_t*) * (size_t)n));
+    // block width of the colour kernel: an exact fit when every page of the unit has the same width, 64 threads (512 px) otherwise
+    bool uniform = true;
+    for (int i = first + 1; i < first + n; ++i) uniform &= JB.X[i] == JB.X[first];
+    const int jc_threads = uniform ? std::min(JC_THREADS, ((JB.X[first] + JC_PX - 1) / JC_PX + 31) / 32 * 32) : 64;
+    // one upload: output pointers, then the two flat-grid prefix tables
+    const size_t o_bytes = (sizeof(uint8_t*) * (size_t)n + 15) & ~size_t(15), p_bytes = (sizeof(unsigned) * ((size_t)n + 1) + 15) & ~size_t(15);
+    int slot = -1;
+    void* sp = nullptr;
+    RT_TRY(rt_stage_begin(lane, o_bytes + 2 * p_bytes, &slot, &sp));
+    memcpy(sp, d_out, sizeof(uint8_t*) * (size_t)n);
+    unsigned* h_ip = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(sp) + o_bytes);
+    unsigned* h_cp = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(sp) + o_bytes + p_bytes);
+    unsigned long long ig = 0, cu = 0;
+    for (int k = 0; k < n; ++k) {
+        const int i = first + k;
+        h_ip[k] = (unsigned)ig; h_cp[k] = (unsigned)cu;
+        ig += (JB.n_blocks[i] + 31) / 32;
+        cu += (unsigned long long)JB.Y[i] * ((JB.X[i] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX));
+    }
+    h_ip[n] = (unsigned)ig; h_cp[n] = (unsigned)cu;
+    if (ig > 0x7fffffffULL || cu > 0x7fffffffULL) { lane->stage_slots[slot].busy = false; lane->set_error("jpeg decode: unit too large"); return RETTO_B200_ERR_CAPACITY; }
+    RT_TRY(rt_stage_commit(lane, lane->d_jpeg_out, slot, o_bytes + 2 * p_bytes));
+    const char* op = lane->d_jpeg_out.as<char>();
+    uint8_t* const* d_outs = reinterpret_cast<uint8_t* const*>(op);
+    const unsigned* d_ip = reinterpret_cast<const unsigned*>(op + o_bytes);
+    const unsigned* d_cp = reinterpret_cast<const unsigned*>(op + o_bytes + p_bytes);
     const char* dp = owner->d_jpeg_desc.as<char>();
     const JpegDev* d_files = reinterpret_cast<const JpegDev*>(dp) + first;
     const JpegTables* d_tab = reinterpret_cast<const JpegTables*>(dp + JB.head_bytes) + first;
     cudaStream_t st = lane->stream;
+    bool same_blocks = true;
+    for (int i = first + 1; i < first + n; ++i) same_blocks &= JB.n_blocks[i] == JB.n_blocks[first] && JB.Y[i] == JB.Y[first];
     RT_LAUNCH_BEGIN(lane, "jpeg_idct_kernel");
-    jpeg_idct_kernel<<<dim3((max_file_blocks + 31) / 32, (unsigned)n), 256, 0, st>>>(d_files, d_tab, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
+    if (uniform && same_blocks) jpeg_idct_kernel<<<dim3((JB.n_blocks[first] + 31) / 32, (unsigned)n), 256, 0, st>>>(d_files, d_tab, nullptr, n, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
+    else jpeg_idct_kernel<<<(unsigned)ig, 256, 0, st>>>(d_files, d_tab, d_ip, n, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
     RT_LAUNCH_CHECK(lane);
-    const int jc_threads = std::min(JC_THREADS, ((max_x + JC_PX - 1) / JC_PX + 31) / 32 * 32);
     RT_LAUNCH_BEGIN(lane, "jpeg_color_kernel");
-    jpeg_color_kernel<<<dim3((unsigned)((max_x + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)max_y, (unsigned)n), jc_threads, 0, st>>>(
-        d_files, owner->d_jpeg_planes.as<unsigned char>(), lane->d_jpeg_out.as<uint8_t*>());
+    if (uniform && same_blocks)
+        jpeg_color_kernel<<<dim3((unsigned)((JB.X[first] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)JB.Y[first], (unsigned)n), jc_threads, 0, st>>>(
+            d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, nullptr, n);
+    else jpeg_color_kernel<<<(unsigned)cu, jc_threads, 0, st>>>(d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, d_cp, n);
     RT_LAUNCH_CHECK(lane);
     return RETTO_B200_OK;
 }
