@@ -232,7 +232,7 @@ struct retto_b200_ctx {
     // crops
     struct CropHost { int w, h, rot, status; unsigned long long offset; };   // host view of the current crop set
     std::vector<CropHost> crops;
-    DevBuf d_crop_descs, d_crop_pix, d_crop_flip, d_crop_pages;
+    DevBuf d_crop_descs, d_crop_pix, d_crop_flip, d_crop_pages, d_crop_any;
     int crop_dev_cap = 0;                 // device-built descriptor table (crop.cu): capacities at enqueue time, 0 = not enqueued
     size_t crop_dev_cap_bytes = 0, crop_dev_desc_bytes = 0;
     bool crop_dev_check = false;          // rt_crop_finish compares the device's crop sizes with the host's

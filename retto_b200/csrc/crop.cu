@@ -29,7 +29,7 @@ static __device__ bool solve8(double A[8][9]) {
     return true;
 }
 
-__global__ void crop_setup_kernel(CropDev* __restrict__ crops, int n, const int* __restrict__ n_dev) {
+__global__ void crop_setup_kernel(CropDev* __restrict__ crops, int n, const int* __restrict__ n_dev, int* __restrict__ any_indirect) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev) n = min(n, *n_dev);   // device-built table: n is the capacity, *n_dev the count (0 on overflow)
     if (i >= n) return;
@@ -100,6 +100,7 @@ __global__ void crop_setup_kernel(CropDev* __restrict__ crops, int n, const int*
         }
     }
     crops[i].direct = direct; crops[i].tx = itx; crops[i].ty = ity; crops[i].pad = 0;
+    if (!direct && any_indirect) *any_indirect = 1;   // some crop needs crop_rows_kernel even in the session's lazy mode
 }
 
 __device__ __forceinline__ unsigned char clamp_u8_trunc(float x) { return x < 255.0f ? (x > 0.0f ? (unsigned char)x : 0) : 255; }
@@ -156,15 +157,22 @@ __device__ __forceinline__ void crop_pixel(const CropDev& c, int x, int y, unsig
 struct CropTotals { int n, rows, overflow, pad; unsigned long long bytes; };   // written by crop_scan_kernel
 template <bool VEC>
 __global__ void __launch_bounds__(256) crop_rows_kernel(const CropDev* __restrict__ crops, const int* __restrict__ row_prefix, int n_crops,
-                                                         int total_rows, unsigned char* __restrict__ pix, const CropTotals* __restrict__ totals, int lazy) {
+                                                         int total_rows, unsigned char* __restrict__ pix, const CropTotals* __restrict__ totals, int lazy,
+                                                         const int* __restrict__ any_indirect) {
+    if (lazy && any_indirect && *any_indirect == 0) return;   // every crop of the batch is read from its page by the batch build: nothing to materialise
     if (totals) {   // device-built descriptor table: the sizes come from the device, the grid from the host's row hint
         if (totals->overflow) return;
         n_crops = totals->n; total_rows = totals->rows;
     }
     const int lane = threadIdx.x & 31;
     const int ru = blockIdx.x * 8 + (threadIdx.x >> 5);
+    // the eight rows of a block mostly belong to one crop: one binary search per block (13 dependent loads), then a short walk
+    __shared__ int s_k0;
+    if (threadIdx.x == 0) s_k0 = rt_find_segment(row_prefix, n_crops, min(blockIdx.x * 8, max(total_rows - 1, 0)));
+    __syncthreads();
     if (ru >= total_rows) return;
-    const int k = rt_find_segment(row_prefix, n_crops, ru);
+    int k = s_k0;
+    while (k + 1 < n_crops && row_prefix[k + 1] <= ru) ++k;
     const CropDev& c = crops[k];
     if (c.status != RETTO_B200_OK) return;
     if (lazy && c.direct) return;   // session path: the batch build reads the page itself (rec_batch.cu bb_px<true>); retto_b200_crop_fetch materialises on demand
@@ -396,12 +404,14 @@ static retto_b200_status crop_launch_impl(retto_b200_ctx* ctx, int n, retto_b200
     CropDev* d_crops = ctx->d_crop_descs.as<CropDev>();
     const int* d_prefix = reinterpret_cast<const int*>(ctx->d_crop_descs.as<char>() + desc_bytes);
     RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
-    crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n, nullptr);
+    RT_CUDA_OK(ctx, ctx->d_crop_any.ensure(16, st));
+    RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_crop_any.p, 0, 4, st));
+    crop_setup_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_crops, n, nullptr, ctx->d_crop_any.as<int>());
     RT_LAUNCH_CHECK(ctx);
     if (rows > 0) {
         RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
-        if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr, ctx->crops_lazy ? 1 : 0);
-        else crop_rows_kernel<false><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr, ctx->crops_lazy ? 1 : 0);
+        if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr, ctx->crops_lazy ? 1 : 0, ctx->d_crop_any.as<int>());
+        else crop_rows_kernel<false><<<(rows + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, n, rows, ctx->d_crop_pix.as<unsigned char>(), nullptr, ctx->crops_lazy ? 1 : 0, ctx->d_crop_any.as<int>());
         RT_LAUNCH_CHECK(ctx);
     }
     ctx->crop_launch.d_prefix = d_prefix; ctx->crop_launch.n = n; ctx->crop_launch.rows = rows; ctx->crop_launch.d_totals = nullptr;
@@ -478,7 +488,9 @@ retto_b200_status rt_crop_enqueue_device(retto_b200_ctx* ctx, const retto_b200_b
     crop_scan_kernel<<<1, 1024, 0, st>>>(d_box_off, n_pages, d_crops, d_prefix, cap_crops, (unsigned long long)ctx->d_crop_pix.cap, d_tot, max_boxes);
     RT_LAUNCH_CHECK(ctx);
     RT_LAUNCH_BEGIN(ctx, "crop_setup_kernel");
-    crop_setup_kernel<<<(cap_crops + 63) / 64, 64, 0, st>>>(d_crops, cap_crops, &d_tot->n);
+    RT_CUDA_OK(ctx, ctx->d_crop_any.ensure(16, st));
+    RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_crop_any.p, 0, 4, st));
+    crop_setup_kernel<<<(cap_crops + 63) / 64, 64, 0, st>>>(d_crops, cap_crops, &d_tot->n, ctx->d_crop_any.as<int>());
     RT_LAUNCH_CHECK(ctx);
     // one warp per row like the host-sized launch, the grid sized from the largest batch seen so far (+25 %); a batch with more
     // rows than that falls back to the host-built table (a persistent grid-stride variant was measured 0.03-0.05 ms slower:
@@ -486,8 +498,8 @@ retto_b200_status rt_crop_enqueue_device(retto_b200_ctx* ctx, const retto_b200_b
     const int row_hint = std::max(ctx->crop_rows_seen_max + ctx->crop_rows_seen_max / 4, 8192);
     ctx->crop_dev_row_cap = (row_hint + 7) / 8 * 8;
     RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
-    if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot, ctx->crops_lazy ? 1 : 0);
-    else crop_rows_kernel<false><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot, ctx->crops_lazy ? 1 : 0);
+    if (!getenv("RETTO_B200_CROP_SCALAR")) crop_rows_kernel<true><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot, ctx->crops_lazy ? 1 : 0, ctx->d_crop_any.as<int>());
+    else crop_rows_kernel<false><<<(row_hint + 7) / 8, 256, 0, st>>>(d_crops, d_prefix, 0, 0, ctx->d_crop_pix.as<unsigned char>(), d_tot, ctx->crops_lazy ? 1 : 0, ctx->d_crop_any.as<int>());
     RT_LAUNCH_CHECK(ctx);
     ctx->crop_launch.d_prefix = d_prefix; ctx->crop_launch.n = 0; ctx->crop_launch.rows = ctx->crop_dev_row_cap; ctx->crop_launch.d_totals = d_tot;
     ctx->crop_dev_cap = cap_crops;
@@ -561,7 +573,7 @@ extern "C" retto_b200_status retto_b200_crop_fetch(retto_b200_ctx* ctx, int32_t 
         const retto_b200_ctx::CropLaunch& cl = ctx->crop_launch;
         RT_LAUNCH_BEGIN(ctx, "crop_rows_kernel");
         crop_rows_kernel<true><<<(std::max(cl.rows, 1) + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_crop_descs.as<CropDev>(), cl.d_prefix, cl.n, cl.rows, ctx->d_crop_pix.as<unsigned char>(),
-                                                                                      reinterpret_cast<const CropTotals*>(cl.d_totals), 0);
+                                                                                      reinterpret_cast<const CropTotals*>(cl.d_totals), 0, nullptr);
         RT_LAUNCH_CHECK(ctx);
         ctx->crops_lazy = false;
     }

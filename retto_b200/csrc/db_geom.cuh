@@ -84,6 +84,15 @@ static __device__ void warp_min_area_rect(const int2* hull, int n, double q[8]) 
     double b_s = 0, b_c = 1, b_minx = 0, b_maxx = 0, b_miny = 0, b_maxy = 0;
     for (int e = lane; e < n - 1; e += 32) {
         const int2 a = hull[e], b = hull[e + 1];
+        // an earlier edge with the same vector has the same angle, hence the same rectangle and area — and the earlier edge wins
+        // the "first strictly smallest" rule anyway: skip the double-double trig (the hull of a rasterised slanted side repeats a
+        // handful of step vectors many times)
+        {
+            const int dxi = b.x - a.x, dyi = b.y - a.y;
+            bool dup = false;
+            for (int k = 0; k < e && !dup; ++k) dup = (hull[k + 1].x - hull[k].x == dxi) && (hull[k + 1].y - hull[k].y == dyi);
+            if (dup) continue;
+        }
         const double ex = (double)b.x - (double)a.x, ey = (double)b.y - (double)a.y;
         const double ang = fabs(fmod(__dadd_rn(rtm::rt_atan2(ey, ex), PI), PI / 2.0));
         double s, c;
@@ -482,6 +491,116 @@ static __device__ int clipper_offset_round(const int qx[4], const int qy[4], dou
     }
 #undef RT_PUSH
     return m;
+}
+
+// The same offset computed by the whole warp: every lane evaluates the shared prologue (orientation, step count, the one
+// sincos / acos — SIMT executes the big double-double routines once for the warp), then lane j < len produces the points of corner j
+// (its arc is a serial rotation recurrence) at the position an exclusive prefix over the corners' point counts gives it.  Same
+// operations in the same order per corner as clipper_offset_round, so the points are bit-identical; all lanes return the count.
+__device__ __forceinline__ double sel4d(const double v[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
+__device__ __forceinline__ long long sel4l(const long long v[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
+static __device__ int warp_clipper_offset_round(const int qx[4], const int qy[4], double delta, double arc_tol, int2* out, int max_out) {
+    const int lane = threadIdx.x & 31;
+    long long X[4], Y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { X[i] = qx[(i + 1) & 3]; Y[i] = qy[(i + 1) & 3]; }  // geo-clipper: ring minus its first point
+    int highI = 3;
+    while (highI > 0 && X[0] == X[highI] && Y[0] == Y[highI]) --highI;
+    long long cx[4], cy[4];
+    int len = 0;
+    cx[0] = X[0]; cy[0] = Y[0]; cx[1] = cx[2] = cx[3] = 0; cy[1] = cy[2] = cy[3] = 0;
+    len = 1;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i <= highI) {
+            const long long px = len == 1 ? cx[0] : (len == 2 ? cx[1] : cx[2]), py = len == 1 ? cy[0] : (len == 2 ? cy[1] : cy[2]);
+            if (px != X[i] || py != Y[i]) {
+                if (len == 1) { cx[1] = X[i]; cy[1] = Y[i]; } else if (len == 2) { cx[2] = X[i]; cy[2] = Y[i]; } else { cx[3] = X[i]; cy[3] = Y[i]; }
+                ++len;
+            }
+        }
+    if (len < 3) return 0;
+    double a = 0;
+    for (int i = 0, j = len - 1; i < len; ++i) {
+        a = __dadd_rn(a, __dmul_rn(__dadd_rn((double)sel4l(cx, j), (double)sel4l(cx, i)), __dsub_rn((double)sel4l(cy, j), (double)sel4l(cy, i))));
+        j = i;
+    }
+    const double area = __dmul_rn(-a, 0.5);
+    if (!(area >= 0)) {   // reverse the first `len` entries
+        if (len == 3) { long long t = cx[0]; cx[0] = cx[2]; cx[2] = t; t = cy[0]; cy[0] = cy[2]; cy[2] = t; }
+        else { long long t = cx[0]; cx[0] = cx[3]; cx[3] = t; t = cy[0]; cy[0] = cy[3]; cy[3] = t; t = cx[1]; cx[1] = cx[2]; cx[2] = t; t = cy[1]; cy[1] = cy[2]; cy[2] = t; }
+    }
+    if (fabs(delta) < 1.0e-20) {
+        if (lane < len) out[lane] = make_int2((int)sel4l(cx, lane), (int)sel4l(cy, lane));
+        return len;
+    }
+    const double pi = 3.141592653589793238;
+    const double two_pi = __dmul_rn(pi, 2.0);
+    double yv;
+    if (arc_tol <= 0.0) yv = 0.25;
+    else if (arc_tol > __dmul_rn(fabs(delta), 0.25)) yv = __dmul_rn(fabs(delta), 0.25);
+    else yv = arc_tol;
+    double steps = __ddiv_rn(pi, rtm::rt_acos(__dsub_rn(1.0, __ddiv_rn(yv, fabs(delta)))));
+    if (steps > __dmul_rn(fabs(delta), pi)) steps = __dmul_rn(fabs(delta), pi);
+    double m_sin, m_cos;
+    rtm::rt_sincos(__ddiv_rn(two_pi, steps), &m_sin, &m_cos);
+    const double steps_per_rad = __ddiv_rn(steps, two_pi);
+    if (delta < 0.0) m_sin = -m_sin;
+    // lane j: its corner (j) and the previous one (k); unit normals of the edges leaving them
+    const int j = lane < len ? lane : 0, k = (j + len - 1) % len;
+    auto normal = [&](int e, double& nxe, double& nye) {
+        const int e2 = (e + 1) % len;
+        double Dx = (double)(sel4l(cx, e2) - sel4l(cx, e)), dy = (double)(sel4l(cy, e2) - sel4l(cy, e));
+        if (Dx == 0 && dy == 0) { nxe = 0; nye = 0; return; }
+        const double f = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(Dx, Dx), __dmul_rn(dy, dy))));
+        Dx = __dmul_rn(Dx, f); dy = __dmul_rn(dy, f);
+        nxe = dy; nye = -Dx;
+    };
+    double nxj, nyj, nxk, nyk;
+    normal(j, nxj, nyj);
+    normal(k, nxk, nyk);
+    const double pxj = (double)sel4l(cx, j), pyj = (double)sel4l(cy, j);
+    double sinA = __dsub_rn(__dmul_rn(nxk, nyj), __dmul_rn(nxj, nyk));
+    int mode = 2;   // 0: one point, 1: concave patch (3 points), 2: round join
+    if (fabs(__dmul_rn(sinA, delta)) < 1.0) {
+        const double cosA = __dadd_rn(__dmul_rn(nxk, nxj), __dmul_rn(nyj, nyk));
+        if (cosA > 0) mode = 0;
+    } else if (sinA > 1.0) sinA = 1.0;
+    else if (sinA < -1.0) sinA = -1.0;
+    if (mode == 2 && __dmul_rn(sinA, delta) < 0) mode = 1;
+    int nsteps = 0;
+    if (mode == 2) {
+        const double ang = rtm::rt_atan2(sinA, __dadd_rn(__dmul_rn(nxk, nxj), __dmul_rn(nyk, nyj)));
+        const long long ns = clipper_round(__dmul_rn(steps_per_rad, fabs(ang)));
+        nsteps = ns < 1 ? 1 : (ns > 100000 ? 100000 : (int)ns);
+    }
+    int cnt = lane < len ? (mode == 0 ? 1 : (mode == 1 ? 3 : nsteps + 1)) : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 4; d <<= 1) { const int v = __shfl_up_sync(RT_FULL, incl, d); if (lane >= d) incl += v; }
+    const int total = __shfl_sync(RT_FULL, incl, 3);
+    if (total > max_out) return -1;
+    int m = incl - cnt;
+    if (lane < len) {
+#define RT_PUT(xx, yy) out[m++] = make_int2((int)clipper_round(xx), (int)clipper_round(yy))
+        if (mode == 0) RT_PUT(__dadd_rn(pxj, __dmul_rn(nxk, delta)), __dadd_rn(pyj, __dmul_rn(nyk, delta)));
+        else if (mode == 1) {
+            RT_PUT(__dadd_rn(pxj, __dmul_rn(nxk, delta)), __dadd_rn(pyj, __dmul_rn(nyk, delta)));
+            out[m++] = make_int2((int)sel4l(cx, j), (int)sel4l(cy, j));
+            RT_PUT(__dadd_rn(pxj, __dmul_rn(nxj, delta)), __dadd_rn(pyj, __dmul_rn(nyj, delta)));
+        } else {
+            double Xv = nxk, Yv = nyk;
+            for (int i = 0; i < nsteps; ++i) {
+                RT_PUT(__dadd_rn(pxj, __dmul_rn(Xv, delta)), __dadd_rn(pyj, __dmul_rn(Yv, delta)));
+                const double X2 = Xv;
+                Xv = __dsub_rn(__dmul_rn(Xv, m_cos), __dmul_rn(m_sin, Yv));
+                Yv = __dadd_rn(__dmul_rn(X2, m_sin), __dmul_rn(Yv, m_cos));
+            }
+            RT_PUT(__dadd_rn(pxj, __dmul_rn(nxj, delta)), __dadd_rn(pyj, __dmul_rn(nyj, delta)));
+        }
+#undef RT_PUT
+    }
+    return total;
 }
 
 // points.rs:179-194

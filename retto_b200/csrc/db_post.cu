@@ -24,6 +24,7 @@
 #define TILE_H 16
 #define ROWCAP 131072        // row-table entries per page
 #define MAX_OFFSET_PTS 256   // points of one unclipped polygon
+#define P0_ROWS 192          // rows of a component whose first hull / rect is computed out of shared memory
 
 #define RUN_CAP 6144                       // runs per page held in shared memory by ccl_runs_kernel (88 KB: two blocks per SM)
 struct RunRec { int key; int x1; };        // key = y * W + x0 (raster index of the first pixel), x1 = last pixel
@@ -520,14 +521,28 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
 
     if (PHASE == 0) {
         __shared__ int s_n0[4];
+        __shared__ int2 s_rows[4][P0_ROWS];        // the component's row extremes, staged by the whole warp (coalesced)
+        __shared__ int2 s_h0[4][2 * P0_ROWS];      // hull stack of the serial monotone chains + input of the calipers
         const CompRec cr = comps[(size_t)page * max_comps + id];
         const int ymin = cr.ymin;
         const int R = cr.ymax - ymin + 1;
         const int2* rt = rowtab + (size_t)page * ROWCAP + cr.row_off;
         int2* hull = hullbuf + ((size_t)page * ROWCAP + cr.row_off) * 2;
-        // hull of the component == hull of its border
+        // hull of the component == hull of its border.  The two monotone chains are serial (lane 0) and pop / push a stack at every
+        // row: with the rows and the stack in global memory every step was a dependent global access (0.55 ms on config 2's rotated
+        // rectangles); components of up to P0_ROWS rows now run entirely out of shared memory, taller ones keep the global path.
+        const bool in_smem = R <= P0_ROWS;
+        if (in_smem) {
+            for (int i = lane; i < R; i += 32) s_rows[wib][i] = rt[i];
+            __syncwarp();
+            hull = s_h0[wib];
+        }
         if (lane == 0) {
-            s_n0[wib] = hull_from_rows(R, [&](int i, int& y, int& a, int& b) { const int2 v = rt[i]; y = ymin + i; a = v.x; b = v.y; }, hull);
+            if (in_smem) {
+                const int2* sr = s_rows[wib];
+                s_n0[wib] = hull_from_rows(R, [&](int i, int& y, int& a, int& b) { const int2 v = sr[i]; y = ymin + i; a = v.x; b = v.y; }, hull);
+            } else
+                s_n0[wib] = hull_from_rows(R, [&](int i, int& y, int& a, int& b) { const int2 v = rt[i]; y = ymin + i; a = v.x; b = v.y; }, hull);
         }
         __syncwarp();
         const int nh = s_n0[wib];
@@ -585,32 +600,45 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
 #pragma unroll
         for (int i = 0; i < 4; ++i) { qx[i] = out->rect1[2 * i]; qy[i] = out->rect1[2 * i + 1]; }
         __syncwarp();
-        if (lane == 0) {
+        {
+            // unclip by the whole warp: the Clipper offset with one corner per lane, a rank sort of the offset points by (y, x), then
+            // lane 0 compresses the sorted points to per-row extremes and runs the two monotone chains (was: everything on lane 0)
             const float dist = unclip_distance(qx, qy, gp.unclip_ratio);
-            out->dist = dist;
-            int m = clipper_offset_round(qx, qy, (double)dist, 0.5, s_pts[wib], MAX_OFFSET_PTS);
+            if (lane == 0) out->dist = dist;
+            int2* p = s_pts[wib];
+            int m = warp_clipper_offset_round(qx, qy, (double)dist, 0.5, p, MAX_OFFSET_PTS);
+            __syncwarp();
             if (m > 0) {
-                // rows of the offset polygon: sort by (y, x), group by y
-                int2* p = s_pts[wib];
-                for (int i = 1; i < m; ++i) {
+                int2* sorted = s_hull[wib];   // scratch: sorted copy, then copied back
+                for (int i = lane; i < m; i += 32) {
                     const int2 v = p[i];
-                    int j = i;
-                    while (j > 0 && (p[j - 1].y > v.y || (p[j - 1].y == v.y && p[j - 1].x > v.x))) { p[j] = p[j - 1]; --j; }
-                    p[j] = v;
+                    int rank = 0;
+                    for (int j = 0; j < m; ++j) {
+                        const int2 u = p[j];
+                        rank += (u.y < v.y || (u.y == v.y && (u.x < v.x || (u.x == v.x && j < i)))) ? 1 : 0;
+                    }
+                    sorted[rank] = v;
                 }
-                // compress to rows in place: (y, xmin, xmax) stored as pairs in s_hull's upper half
-                int2* rows_y = s_hull[wib] + MAX_OFFSET_PTS;            // .x = y, .y unused
-                int2* rows_x = s_hull[wib] + MAX_OFFSET_PTS + MAX_OFFSET_PTS / 2;  // .x = xmin, .y = xmax
-                int nr = 0;
-                for (int i = 0; i < m;) {
-                    int j = i;
-                    while (j + 1 < m && p[j + 1].y == p[i].y) ++j;
-                    if (nr < MAX_OFFSET_PTS / 2) { rows_y[nr] = make_int2(p[i].y, 0); rows_x[nr] = make_int2(p[i].x, p[j].x); ++nr; }
-                    i = j + 1;
-                }
-                m = hull_from_rows(nr, [&](int i, int& y, int& a, int& b) { y = rows_y[i].x; a = rows_x[i].x; b = rows_x[i].y; }, s_hull[wib]);
+                __syncwarp();
+                for (int i = lane; i < m; i += 32) p[i] = sorted[i];
+                __syncwarp();
             }
-            s_n[wib] = m;
+            if (lane == 0) {
+                if (m > 0) {
+                    // compress to rows in place: (y, xmin, xmax) stored as pairs in s_hull's upper half
+                    int2* rows_y = s_hull[wib] + MAX_OFFSET_PTS;            // .x = y, .y unused
+                    int2* rows_x = s_hull[wib] + MAX_OFFSET_PTS + MAX_OFFSET_PTS / 2;  // .x = xmin, .y = xmax
+                    int nr = 0;
+                    for (int i = 0; i < m;) {
+                        int j = i;
+                        while (j + 1 < m && p[j + 1].y == p[i].y) ++j;
+                        if (nr < MAX_OFFSET_PTS / 2) { rows_y[nr] = make_int2(p[i].y, 0); rows_x[nr] = make_int2(p[i].x, p[j].x); ++nr; }
+                        i = j + 1;
+                    }
+                    m = hull_from_rows(nr, [&](int i, int& y, int& a, int& b) { y = rows_y[i].x; a = rows_x[i].x; b = rows_x[i].y; }, s_hull[wib]);
+                }
+                s_n[wib] = m;
+            }
         }
         __syncwarp();
         const int nh = s_n[wib];

@@ -68,7 +68,7 @@ struct RowS { int o0, o1; float fv, omv; };
 
 // k23 = 0x4B000000 held in a register (opaque to the optimiser) so that the PRMT selector can be the immediate
 __device__ __forceinline__ float u8f(unsigned word, unsigned k23, unsigned sel) {   // exact float of byte `sel & 3` of word
-    return __fsub_rn(__uint_as_float(__byte_perm(word, k23, sel)), 8388608.0f);
+    return __fsub_rn(__uint_as_float(__byte_perm(word, k23, sel)), 8388608.0f);   // (I2F on a byte costs SHF + LOP + I2FP here)
 }
 __device__ __forceinline__ float u32f(unsigned v) {                   // exact float of v < 2^23
     return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
@@ -483,6 +483,9 @@ retto_b200_status rt_build_batches_prepare(retto_b200_ctx* ctx, int32_t kind, co
         n_chunks[k] += (size_t)(l.img_w + BB_COLS - 1) / BB_COLS;
     }
     const size_t total_chunks = n_chunks[0] + n_chunks[1] + n_chunks[2] + n_chunks[3] + n_chunks[4] + n_chunks[5];
+    if (getenv("RETTO_B200_BB_STATS"))
+        fprintf(stderr, "[build_batches kind %d] lines %d chunks FF %zu BB %zu BF %zu GEN %zu BB2 %zu BF4 %zu\n", kind, n_lines, n_chunks[BB_FF], n_chunks[BB_BB],
+                n_chunks[BB_BF], n_chunks[BB_GEN], n_chunks[BB_BB2], n_chunks[BB_BF4]);
     const size_t lb = (sizeof(LineDev) * n_lines + 15) & ~size_t(15);
     std::vector<char>& blob = ctx->bb_blob;
     blob.resize(lb + sizeof(ChunkDev) * total_chunks);
