@@ -105,6 +105,25 @@ class Context:
     def sync(self):
         self._check(self._L.retto_b200_sync(self._h))
 
+    def _ordered(self):
+        """Stream ordering for calls that read / write torch tensors: the context enqueues on its OWN non-blocking stream, torch
+        allocates and fills tensors on its current stream.  Entering makes the context's stream wait for everything queued on
+        torch's current stream (the inputs are ready when our kernels run); leaving makes torch's current stream wait for the
+        context's (the outputs are ready for whatever torch does next) — no host synchronisation either way."""
+        import contextlib
+        import torch
+
+        @contextlib.contextmanager
+        def cm():
+            with torch.cuda.device(self.device_id):
+                cur, mine = torch.cuda.current_stream(), self.torch_stream()
+                mine.wait_stream(cur)
+                try:
+                    yield
+                finally:
+                    cur.wait_stream(mine)
+        return cm()
+
     def set_pipeline(self, lanes: int = 0, unit_pages: int = 0):
         """run_pages pipeline: lanes 1 or 2 (0 = default 1), pages per unit (0 = default)"""
         self._check(self._L.retto_b200_set_pipeline(self._h, int(lanes), int(unit_pages)))
@@ -148,9 +167,9 @@ class Context:
             else:
                 outs.append(None)
                 ptrs[i] = None
-        torch.cuda.synchronize()
         status = (C.c_int32 * max(n, 1))()
-        self._L.retto_b200_decode_images(self._h, enc, n, ptrs, status)
+        with self._ordered():
+            self._L.retto_b200_decode_images(self._h, enc, n, ptrs, status)
         return outs, [int(status[i]) for i in range(n)]
 
     # ---- resizes ------------------------------------------------------------------------------
@@ -163,7 +182,8 @@ class Context:
             o = torch.empty((oh, ow, 3), dtype=torch.uint8, device=s.device)
             outs.append(o)
             descs[i] = ResizeDesc(s.data_ptr(), s.shape[0], s.shape[1], o.data_ptr(), oh, ow)
-        self._check(self._L.retto_b200_thumbnail(self._h, descs, len(srcs)))
+        with self._ordered():
+            self._check(self._L.retto_b200_thumbnail(self._h, descs, len(srcs)))
         return outs
 
     # ---- det preprocess -----------------------------------------------------------------------
@@ -177,7 +197,8 @@ class Context:
             o = torch.empty((1, 3, oh, ow), dtype=torch.float32, device=p.device)
             outs.append(o)
             descs[i] = DetPreDesc(p.data_ptr(), p.shape[0], p.shape[1], o.data_ptr(), oh, ow)
-        self._check(self._L.retto_b200_det_preprocess(self._h, descs, len(pages)))
+        with self._ordered():
+            self._check(self._L.retto_b200_det_preprocess(self._h, descs, len(pages)))
         return outs
 
     # ---- det postprocess ----------------------------------------------------------------------
@@ -193,8 +214,9 @@ class Context:
         status = np.zeros(max(n, 1), np.int32)
         offs = np.zeros(n + 1, np.int32)
         boxes = (Box * cap)()
-        st = self._L.retto_b200_det_postprocess(self._h, descs, n, status.ctypes.data_as(C.POINTER(C.c_int32)),
-                                                offs.ctypes.data_as(C.POINTER(C.c_int32)), boxes, cap)
+        with self._ordered():
+            st = self._L.retto_b200_det_postprocess(self._h, descs, n, status.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    offs.ctypes.data_as(C.POINTER(C.c_int32)), boxes, cap)
         self._check(st)
         tot = int(offs[n])
         arr = np.frombuffer(boxes, dtype=np.float32, count=tot * 9).reshape(tot, 9) if tot else np.zeros((0, 9), np.float32)
@@ -244,7 +266,8 @@ class Context:
             jobs[i].page_h, jobs[i].page_w = p.shape[0], p.shape[1]
             jobs[i].box.xy[:] = [float(v) for v in np.asarray(boxes[i]).reshape(8)]
         infos = (CropInfo * max(n, 1))()
-        self._check(self._L.retto_b200_crop_boxes(self._h, jobs, n, infos))
+        with self._ordered():
+            self._check(self._L.retto_b200_crop_boxes(self._h, jobs, n, infos))
         return [infos[i] for i in range(n)]
 
     def crop_fetch(self, i: int, info: CropInfo) -> np.ndarray:
@@ -269,14 +292,16 @@ class Context:
         n = len(lines)
         arr = (LineJob * max(n, 1))(*lines)
         base = C.c_void_p()
-        self._check(self._L.retto_b200_build_batches(self._h, kind, arr, n, total_floats, C.byref(base)))
+        with self._ordered():
+            self._check(self._L.retto_b200_build_batches(self._h, kind, arr, n, total_floats, C.byref(base)))
         return int(base.value or 0)
 
     def cls_postprocess(self, logits, crop_index: Sequence[int]):
         n = len(crop_index)
         idx = (C.c_int32 * max(n, 1))(*crop_index)
         res = (ClsResult * max(n, 1))()
-        self._check(self._L.retto_b200_cls_postprocess(self._h, logits.data_ptr(), n, idx, res))
+        with self._ordered():
+            self._check(self._L.retto_b200_cls_postprocess(self._h, logits.data_ptr(), n, idx, res))
         return [(res[i].label, res[i].score) for i in range(n)]
 
     # ---- CTC ------------------------------------------------------------------------------------
@@ -307,11 +332,12 @@ class Context:
         scores = np.zeros(max(total, 1), np.float32)
         tokens = np.zeros((max(total, 1), max_t), np.int32) if want_tokens else None
         counts = np.zeros(max(total, 1), np.int32) if want_tokens else None
-        st = self._L.retto_b200_ctc_decode(
-            self._h, descs, nd, Cc, offs.ctypes.data_as(C.POINTER(C.c_uint32)), C.cast(text, C.c_void_p), cap,
-            scores.ctypes.data_as(C.POINTER(C.c_float)),
-            tokens.ctypes.data_as(C.POINTER(C.c_int32)) if want_tokens else None,
-            counts.ctypes.data_as(C.POINTER(C.c_int32)) if want_tokens else None, max_t)
+        with self._ordered():
+            st = self._L.retto_b200_ctc_decode(
+                self._h, descs, nd, Cc, offs.ctypes.data_as(C.POINTER(C.c_uint32)), C.cast(text, C.c_void_p), cap,
+                scores.ctypes.data_as(C.POINTER(C.c_float)),
+                tokens.ctypes.data_as(C.POINTER(C.c_int32)) if want_tokens else None,
+                counts.ctypes.data_as(C.POINTER(C.c_int32)) if want_tokens else None, max_t)
         self._check(st)
         raw = text.raw
         texts = [raw[offs[i]:offs[i + 1]].decode("utf-8") for i in range(total)]
@@ -326,5 +352,6 @@ class Context:
         descs = (LogitsDesc * 1)(LogitsDesc(logits.data_ptr(), n, T))
         idx = torch.empty((n, T), dtype=torch.int32, device=logits.device)
         prob = torch.empty((n, T), dtype=torch.float32, device=logits.device)
-        self._check(self._L.retto_b200_ctc_argmax(self._h, descs, 1, Cc, idx.data_ptr(), prob.data_ptr()))
+        with self._ordered():
+            self._check(self._L.retto_b200_ctc_argmax(self._h, descs, 1, Cc, idx.data_ptr(), prob.data_ptr()))
         return idx, prob

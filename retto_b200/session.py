@@ -267,7 +267,12 @@ class RettoSession:
         res = Results()
         self._keep = {}
         self._err = None
-        st = self.ctx._L.retto_b200_run_pages(self.ctx.handle, pages, n, self._cb, None, C.byref(res))
+        if on_device:
+            # device pages were produced on torch's current stream; the context works on its own (see Context._ordered)
+            with self.ctx._ordered():
+                st = self.ctx._L.retto_b200_run_pages(self.ctx.handle, pages, n, self._cb, None, C.byref(res))
+        else:
+            st = self.ctx._L.retto_b200_run_pages(self.ctx.handle, pages, n, self._cb, None, C.byref(res))
         if self._err is not None:
             raise self._err
         if st not in (_lib.OK, _lib.ERR_DEGENERATE_QUAD, _lib.ERR_CAPACITY) or (st != _lib.OK and res.n_pages == 0):

@@ -136,6 +136,19 @@ def test_cli_surface(tmp_path):
         (tmp_path / n).write_bytes(b"x")
     assert [os.path.relpath(f, tmp_path) for f in cli.find_files(str(tmp_path))] == ["a.png", "b.png", "sub/c.png"]
     assert cli.find_files(str(tmp_path / "a.png")) == [str(tmp_path / "a.png")]
+    # the log lines use the reference's Debug shapes: custom PointBox impl (points.rs:70-82), OrderedFloat coordinates, f32 `{:?}`
+    # digits, str escape_debug
+    from retto_b200.session import ClsPostProcessLabel, DetProcessorInnerResult, RecProcessorSingleResult, RettoWorkerResult
+    import numpy as np
+    r = RettoWorkerResult([DetProcessorInnerResult(np.array([[1, 2], [30, 2], [30, 9], [1, 9]], np.float32), 0.8235294)],
+                          [ClsPostProcessLabel(180, 0.95)], [RecProcessorSingleResult('a"b\\c\n中', float("nan"))])
+    d, c, t = cli.fmt_debug(r)
+    assert d == ("Det result: DetProcessorResult([DetProcessorInnerResult { boxes: PointBox { tl: Point { x: OrderedFloat(1.0), y: OrderedFloat(2.0) }, "
+                 "tr: Point { x: OrderedFloat(30.0), y: OrderedFloat(2.0) }, br: Point { x: OrderedFloat(30.0), y: OrderedFloat(9.0) }, "
+                 "bl: Point { x: OrderedFloat(1.0), y: OrderedFloat(9.0) } }, score: 0.8235294 }])")
+    assert c == "Cls result: ClsProcessorResult([ClsProcessorSingleResult { label: ClsPostProcessLabel { label: 180, score: 0.95 } }])"
+    assert t == 'Rec result: RecProcessorResult([RecProcessorSingleResult { text: "a\\"b\\\\c\\n中", score: NaN }])'
+    assert cli._f32(1e-7) == "1e-7" and cli._f32(100000.0) == "100000.0"
 
 
 def test_bench_reference_arm_contract():

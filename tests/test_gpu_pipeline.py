@@ -426,3 +426,61 @@ def test_cli_entry_point(ctx, synth_dict, tmp_path, capsys):
         want = sess.run(im).to_json()
         assert len(want["det_result"]) > 0
         assert json.dumps(want, sort_keys=True) == json.dumps({k: j[k] for k in ("det_result", "cls_result", "rec_result")}, sort_keys=True)
+
+
+def test_cli_jpeg_files_and_debug_shapes(ctx, synth_dict, tmp_path, capsys):
+    """JPEG files reach the device as file bytes (decoded by csrc/jpeg_decode.cu), PNG files are decoded on the host: both give
+    the results of a session run on the libjpeg-turbo / Pillow pixels; the log lines have the reference's Debug shapes
+    (PointBox {tl, tr, br, bl}, OrderedFloat(..), points.rs:70-82); `--worker standin` runs torch networks through the seam"""
+    import json
+    from PIL import Image
+    from retto_b200 import cli
+    imgs = _small_pages(4, 31)
+    (tmp_path / "imgs").mkdir()
+    for k, im in enumerate(imgs):
+        if k % 2 == 0:
+            Image.fromarray(im).save(tmp_path / "imgs" / f"p{k}.jpg", quality=92, restart_marker_rows=1)
+        else:
+            Image.fromarray(im).save(tmp_path / "imgs" / f"p{k}.png")
+    (tmp_path / "keys.txt").write_text(synth_dict, encoding="utf-8")
+    rc = cli.main(["-i", str(tmp_path / "imgs"), "--device", "b200", "--rec-keys-path", str(tmp_path / "keys.txt"),
+                   "--worker", "tools.demo_worker:make_worker", "--json"])
+    cap = capsys.readouterr()
+    assert rc == 0 and "2 JPEG files decoded on the device, 2 files decoded on the host" in cap.err
+    out = cap.out.splitlines()
+    det = [l for l in out if l.startswith("Det result: ")]
+    assert len(det) == 4 and "PointBox { tl: Point { x: OrderedFloat(" in det[0] and "inner" not in det[0]
+    js = {os.path.basename(j["file"]): j for j in (json.loads(l) for l in out if l.startswith("{"))}
+    sess = _session(ctx, StatelessWorker(), synth_dict)
+    for k in range(4):
+        name = f"p{k}.jpg" if k % 2 == 0 else f"p{k}.png"
+        px = np.asarray(Image.open(tmp_path / "imgs" / name).convert("RGB"))
+        want = sess.run(px).to_json()
+        assert len(want["det_result"]) > 0
+        assert json.dumps(want, sort_keys=True) == json.dumps({q: js[name][q] for q in ("det_result", "cls_result", "rec_result")}, sort_keys=True)
+    rc = cli.main(["-i", str(tmp_path / "imgs" / "p0.jpg"), "--device", "b200", "--rec-keys-path", str(tmp_path / "keys.txt"), "--worker", "standin"])
+    assert rc == 0 and "Successfully processed 1 images" in capsys.readouterr().out
+
+
+def test_stage_api_orders_with_torch_current_stream(ctx):
+    """The stage wrappers read tensors produced on torch's current stream and hand back tensors torch consumes next, while the
+    context enqueues on its own non-blocking stream: no host synchronisation is needed either side (Context._ordered).  The
+    producer here is kept busy by a long matmul chain first, so an unordered call would read the page before it is written."""
+    import torch
+    from oracle import oracle as O
+    rng = np.random.default_rng(77)
+    page = rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    ref = O.det_preprocess(page, 0, 736)
+    pinned = torch.from_numpy(page).pin_memory()
+    a = torch.randn(4096, 4096, device="cuda")
+    side = torch.cuda.Stream()
+    for s in (torch.cuda.current_stream(), side):
+        with torch.cuda.stream(s):
+            g = torch.zeros((720, 1280, 3), dtype=torch.uint8, device="cuda")
+            b = a
+            for _ in range(12):
+                b = (b @ a) * 1e-3                     # ~ms of queued work ahead of the page upload
+            g.copy_(pinned, non_blocking=True)
+            out = ctx.det_preprocess([g])[0]
+            got = (out + b[0, 0] * 0).cpu().numpy()    # consumed by torch on the same stream, no sync in between
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
