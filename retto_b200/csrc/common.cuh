@@ -219,6 +219,7 @@ struct retto_b200_ctx {
     std::vector<int> dp_holes;   // per page: #hole borders of the last det_postprocess (components - Euler number)
     DevBuf d_dp_pages, d_dp_counters, d_bitmap, d_labels, d_tileflags, d_roots, d_comps, d_cid_at, d_rowtab, d_cand, d_boxes_out, d_holes, d_hole_pages, d_key_at;
     DevBuf d_order;          // per page: permutation of the valid box candidates (page_sort_kernel -> pack_boxes_kernel)
+    DevBuf d_biglist;        // det postprocess: [count, pad, (page, id) x SCORE_BIG_CAP] — boxes box_score_kernel scores first
     DevBuf d_runs;           // run-table CCL: per page RUN_CAP raw records + RUN_CAP sorted records (key, x1|flags) + RUN_CAP labels
     bool ccl_runs_attr_set = false;   // cudaFuncSetAttribute(ccl_runs_kernel, max dynamic shared memory) done on this context's device
     bool dp_run_path = false;   // the last det_postprocess used the run-table CCL (labels are materialised lazily from the runs)

@@ -239,7 +239,7 @@ static __device__ void polygon_row_cover(const int px[4], const int py[4], int b
             cover_add(rc, x0 + klo, x0 + khi, bw);
         }
     }
-    // sort by a, merge overlaps (adjacent intervals may stay separate: order is what matters)
+    // sort by a, merge overlapping and touching intervals (the pixels and their order are what matters)
     for (int i = 1; i < rc.n; ++i) {
         const int va = rc.a[i], vb = rc.b[i];
         int j = i;
@@ -248,7 +248,7 @@ static __device__ void polygon_row_cover(const int px[4], const int py[4], int b
     }
     int m = 0;
     for (int i = 0; i < rc.n; ++i) {
-        if (m > 0 && rc.a[i] <= rc.b[m - 1]) { if (rc.b[i] > rc.b[m - 1]) rc.b[m - 1] = rc.b[i]; }
+        if (m > 0 && rc.a[i] <= rc.b[m - 1] + 1) { if (rc.b[i] > rc.b[m - 1]) rc.b[m - 1] = rc.b[i]; }
         else { rc.a[m] = rc.a[i]; rc.b[m] = rc.b[i]; ++m; }
     }
     rc.n = m;
@@ -286,8 +286,16 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
             rc.n = 0;
             if (y_base + lane < bh) polygon_row_cover(px, py, bw, bh, y_base + lane, rc);
             cov_n[lane] = rc.n;
+            const float* prow = pred + (size_t)(y_base + lane + y_min) * w + x_min;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { if (k < rc.n) { cov_ab[lane * 16 + k] = rc.a[k]; cov_ab[lane * 16 + 8 + k] = rc.b[k]; } }
+            for (int k = 0; k < 8; ++k) {
+                if (k < rc.n) {
+                    cov_ab[lane * 16 + k] = rc.a[k]; cov_ab[lane * 16 + 8 + k] = rc.b[k];
+                    // the first load of every segment is exposed (its chain cannot start before it lands): pull the rows of this
+                    // 32-row group into L2 now, one request per 128-byte line
+                    for (int x = rc.a[k]; x <= rc.b[k]; x += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + x));
+                }
+            }
         }
         __syncwarp();
         const int nrows = min(32, bh - y_base);
@@ -320,7 +328,16 @@ static __device__ bool warp_box_score(const float* __restrict__ pred, int h, int
                             acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
                         }
                     } else {
-                        for (int k = 0; k < n; ++k) acc = __fadd_rn(acc, sbuf[k]);
+                        // the slots past the segment's end hold +0.0 (the predicated loads above), and acc + (+0.0) == acc bit for
+                        // bit (acc is never -0.0: it starts at +0.0 and x + (-x) rounds to +0.0) — whole groups of 16, no scalar tail
+                        const int groups = (n + 15) >> 4;
+                        for (int gq = 0; gq < groups; ++gq) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float4 t = sb4[4 * gq + k];
+                                acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
+                            }
+                        }
                     }
                     __syncwarp();
 #pragma unroll

@@ -50,6 +50,7 @@ struct BoxCand {
     int n_off;      // hull size of the unclipped polygon
     int st0;        // status after the first rect (immutable once PHASE 0 has run)
     int st2, err2;  // PHASE 3 (unclip running beside the score kernel): its status / page error, merged by geom_merge_kernel
+    int big;        // PHASE 0: score list the box went to (0 huge, 1 big, 2 small)
 };
 
 __device__ __forceinline__ int find_root(const int* __restrict__ L, int a) {
@@ -502,12 +503,15 @@ struct GeomParams {
 //            unclip of a box does not need its score, only the decision).  It writes st2 / err2 instead of status /
 //            valid / the page status; geom_merge_kernel applies them to the boxes whose score passed.
 #define ST_NEED_SCORE 7
+#define SCORE_HUGE_AREA 49152    // bounding-box pixels above which a box is scored ahead of the others (one warp per box)
+#define SCORE_BIG_AREA 16384     // ... above which a box comes before the small ones
+#define SCORE_HUGE_BLOCKS 74     // leading blocks of box_score_wpb_kernel that work through the huge list
 #define ST_NEED_UNCLIP 8
 template <int PHASE>
-__global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(const DetPostPage* __restrict__ pages,
+__global__ void __launch_bounds__(128, PHASE == 1 ? 10 : 4) box_geometry_kernel(const DetPostPage* __restrict__ pages,
                                                             int n_pages, PageCounters* __restrict__ counters, const CompRec* __restrict__ comps,
                                                             const int2* __restrict__ rowtab, int2* __restrict__ hullbuf, BoxCand* __restrict__ cand,
-                                                            int max_comps, GeomParams gp, const int* __restrict__ hole_pages) {
+                                                            int max_comps, GeomParams gp, const int* __restrict__ hole_pages, int* __restrict__ biglist = nullptr, int list_cap = 0) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // hole_pages == nullptr: ids [0, n_roots) of every page (outer borders); else ids [n_roots, n_roots + n_holes)
     // of the listed pages (hole borders)
@@ -557,6 +561,19 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
             if (cr.key == 0x7fffffff) st = 6;                          // every run spans the full width: never discovered
             else if (sside < (float)gp.min_mini_box_size) st = 1;
             out->status = st; out->st0 = st; out->st2 = -2; out->err2 = 0;
+            int big = 0;
+            if (biglist && st == ST_NEED_SCORE) {
+                // class by bounding-box area
+                int xa = (int)q[0], xb = xa, ya = (int)q[1], yb = ya;
+#pragma unroll
+                for (int i = 1; i < 4; ++i) { xa = min(xa, (int)q[2 * i]); xb = max(xb, (int)q[2 * i]); ya = min(ya, (int)q[2 * i + 1]); yb = max(yb, (int)q[2 * i + 1]); }
+                xa = min(max(xa, 0), pg.w - 1); xb = min(max(xb, 0), pg.w - 1); ya = min(max(ya, 0), pg.h - 1); yb = min(max(yb, 0), pg.h - 1);
+                const long long area = (long long)(xb - xa + 1) * (long long)(yb - ya + 1);
+                big = area > SCORE_HUGE_AREA ? 0 : area > SCORE_BIG_AREA ? 1 : 2;
+                const int slot = atomicAdd(&biglist[big], 1);
+                if (slot < list_cap) reinterpret_cast<int2*>(biglist + 4)[(size_t)big * list_cap + slot] = make_int2(page, id);
+            }
+            out->big = big;
         }
         return;
     }
@@ -674,6 +691,44 @@ __global__ void __launch_bounds__(128, PHASE == 1 ? 12 : 4) box_geometry_kernel(
                 else out->st2 = 0;
             }
         }
+    }
+}
+
+// box_score_fast for the outer-border boxes of a batch (PHASE 1 of box_geometry_kernel, re-cut): one warp per box
+// (warp_box_score), but in an order that suits the add chains instead of component order.  PHASE 0 sorts the boxes that need a
+// score into three lists by bounding-box area (huge / big / small); the first SCORE_HUGE_BLOCKS blocks work through the huge
+// list — block order is dispatch order, so the longest chains of the batch (they ARE the kernel's duration when they start late)
+// start first — and the other blocks take the big list, then the small one, grid-stride (the counts live on the device).
+// Measured and dropped this round (all bit-exact, `profiles/r02_score_variants.md`): eight boxes per warp with the pieces staged
+// through shared memory (half the instructions, but 16 warps per SM and a serial piece generator: no faster), one box per lane
+// (a tenth of the instructions, but every 8-pixel step waits for an L2 round trip: 3x slower).
+__device__ __forceinline__ const int2* score_list(const int* lists, int cap, int which) { return reinterpret_cast<const int2*>(lists + 4) + (size_t)which * cap; }
+
+__global__ void __launch_bounds__(128, 10) box_score_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
+                                                            BoxCand* __restrict__ cand, int max_comps, GeomParams gp,
+                                                            const int* __restrict__ lists, int cap) {
+    __shared__ __align__(16) float s_buf[4][128];
+    __shared__ int s_cov[4][32 * 17];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const bool huge = blockIdx.x < SCORE_HUGE_BLOCKS;
+    const int n_huge = min(lists[0], cap), n_big = min(lists[1], cap), n_small = min(lists[2], cap);
+    const int cnt = huge ? n_huge : n_big + n_small;
+    const int first = (huge ? blockIdx.x : blockIdx.x - SCORE_HUGE_BLOCKS) * 4 + wib;
+    const int stride = (huge ? SCORE_HUGE_BLOCKS : (int)gridDim.x - SCORE_HUGE_BLOCKS) * 4;
+    for (int i = first; i < cnt; i += stride) {
+        const int2 e = huge ? score_list(lists, cap, 0)[i] : i < n_big ? score_list(lists, cap, 1)[i] : score_list(lists, cap, 2)[i - n_big];
+        const DetPostPage pg = pages[e.x];
+        BoxCand* out = cand + (size_t)e.x * max_comps + e.y;
+        int qx[4], qy[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { qx[k] = out->rect1[2 * k]; qy[k] = out->rect1[2 * k + 1]; }
+        float score;
+        const bool ok = warp_box_score(pg.prob, pg.h, pg.w, qx, qy, &score, s_buf[wib], s_cov[wib]);
+        if (lane == 0) {
+            if (!ok) { atomicMax(&counters[e.x].status, RETTO_B200_ERR_DEGENERATE_QUAD); out->status = -1; }
+            else { out->score = score; out->status = (score < gp.box_thresh) ? 2 : ST_NEED_UNCLIP; }
+        }
+        __syncwarp();
     }
 }
 
@@ -1762,14 +1817,33 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
     if (max_n > 0) {
         GeomParams gp{ctx->cfg.det_box_thresh, ctx->cfg.det_unclip_ratio, ctx->cfg.det_min_mini_box_size};
         dim3 grid((max_n + 3) / 4, n);
+        // score lists: every component can need a score, so their capacity is the batch's component count
+        long long n_comp_total = 0;
+        for (int i = 0; i < n; ++i) n_comp_total += std::min(h_cnt0[i].n_roots, max_comps);
+        const int list_cap = (int)std::min<long long>(n_comp_total, 0x3fffffff);
+        RT_CUDA_OK(ctx, ctx->d_biglist.ensure(sizeof(int) * (4 + 6 * (size_t)list_cap), st));
+        int* d_lists = ctx->d_biglist.as<int>();
+        RT_CUDA_OK(ctx, cudaMemsetAsync(d_lists, 0, 16, st));
         RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<0:rect1>");
-        box_geometry_kernel<0><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+        box_geometry_kernel<0><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr, d_lists, list_cap);
         RT_LAUNCH_CHECK(ctx);
+        // score: one warp per box, the huge boxes first (RETTO_B200_SCORE_WPB=1: component order, the previous kernel — A/B)
+        static const bool score_wpb = getenv("RETTO_B200_SCORE_WPB") != nullptr;
+        auto launch_score = [&]() -> retto_b200_status {
+            if (score_wpb) {
+                RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
+                box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
+                RT_LAUNCH_CHECK(ctx);
+                return RETTO_B200_OK;
+            }
+            RT_LAUNCH_BEGIN(ctx, "box_score_kernel");
+            box_score_kernel<<<SCORE_HUGE_BLOCKS + std::min((list_cap + 3) / 4, 148 * 10 * 2), 128, 0, st>>>(d_pages, d_cnt, d_cand, max_comps, gp, d_lists, list_cap);
+            RT_LAUNCH_CHECK(ctx);
+            return RETTO_B200_OK;
+        };
         const bool concurrent = getenv("RETTO_B200_GEOM_CONCURRENT") != nullptr;   // opt-in: no gain on 256 text pages (4.89 vs 4.90 ms), -5 % on config 2 (40 k boxes)
         if (!concurrent) {
-            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
-            box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
-            RT_LAUNCH_CHECK(ctx);
+            RT_TRY(launch_score());
             if (any_nonfinite) {
                 RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<4:score,nonfinite>");
                 box_geometry_kernel<4><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
@@ -1787,9 +1861,7 @@ retto_b200_status rt_det_post_mid(retto_b200_ctx* ctx) {
             }
             RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork, st));
             RT_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-            RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<1:score>");
-            box_geometry_kernel<1><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
-            RT_LAUNCH_CHECK(ctx);
+            RT_TRY(launch_score());
             if (any_nonfinite) {
                 RT_LAUNCH_BEGIN(ctx, "box_geometry_kernel<4:score,nonfinite>");
                 box_geometry_kernel<4><<<grid, 128, 0, st>>>(d_pages, n, d_cnt, d_comps, d_rowtab, d_hull, d_cand, max_comps, gp, nullptr);
