@@ -707,7 +707,7 @@ def main():
                 "ms_per_launch": top_k["ms_per_launch"], "share_of_step": top_k["ms_per_step"] / (ms_serial / K),
                 "timed_in": "a repeat of the value pass with per-kernel CUDA events enabled (summary.serial_pass)",
                 "frac_of_nominal_8TBs": (top_k["gbs"] / 8000.0) if top_k.get("gbs") else None}
-    db_names = ["zero_counters", "bitmap_runs", "ccl_runs", "ccl_merge", "ccl_flatten", "comp_sort", "run_end", "row_alloc", "box_geometry", "geom_merge", "page_sort", "pack_"]
+    db_names = ["zero_counters", "bitmap_runs", "ccl_runs", "ccl_merge", "ccl_flatten", "comp_sort", "run_end", "row_alloc", "box_geometry", "box_score", "geom_merge", "page_sort", "pack_"]
     db_ms = sum(v["ms_per_step"] for k, v in path_kernels.items() if any(k.startswith(n) for n in db_names))
     cb_ms = sum(v["ms_per_step"] for k, v in path_kernels.items() if k.startswith("crop_") or k.startswith("build_batches"))
     cb_bytes = 6.0 * crop_px + 2 * 3.0 * crop_px + 4.0 * (info["cls_floats"] + info["rec_floats"])

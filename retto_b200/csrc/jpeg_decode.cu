@@ -267,16 +267,29 @@ struct HuffDev {               // shared memory, one per distinct table of the f
     int valoff[17];            // valptr - mincode
     unsigned char vals[256];
 };
-#define JH_THREADS 128
+#define JH_THREADS 128          // dense layout: every lane decodes
+#define JH_T_THREADS 512        // tiered layout: 16 warps per block
+#define JH_T_SOLO 8             // ... the first 8 decode ONE restart interval each (lane 0; nested loops)
+#define JH_T_IPB 112            // ... intervals per block: 8 x 1 lane, 4 x 4 lanes, 2 x 12 lanes, 2 x 32 lanes
+#define JH_IPB_MAX 128
+// Tiered layout, rank r (0 = longest interval of the block) of thread (warp w, lane l), -1 = idle lane.  The kernel lasts as long as
+// its longest interval's chain, and a warp runs the union of its lanes' paths for as long as its slowest lane: the longest intervals
+// get a warp to themselves (no divergence, shortest iteration), the shortest — blank rows of a page: DC + EOB per block — fill whole warps.
+__device__ __forceinline__ int jh_tier_rank(int w, int l) {
+    if (w < JH_T_SOLO) return l == 0 ? w : -1;
+    if (w < 12) return l < 4 ? 8 + (w - 8) * 4 + l : -1;
+    if (w < 14) return l < 12 ? 24 + (w - 12) * 12 + l : -1;
+    return 48 + (w - 14) * 32 + l;
+}
 __device__ __forceinline__ int jh_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
 __device__ __forceinline__ unsigned jh_has_ff(unsigned w) { return __vcmpeq4(w, 0xFFFFFFFFu); }
 
 // Bit reader over the CLEAN stream (K-J1): w0:w1 = the next 64 bits (big-endian words), o = bits of w0 already consumed;
 // the 32-bit window at the read position is one funnel shift; `nxt` is the raw word after w1, loaded one refill ahead.
-__global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file,
+__global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file,
                                                               const int* __restrict__ block_first, const JpegTables* __restrict__ tables,
                                                               const unsigned* __restrict__ seg, const unsigned char* __restrict__ clean,
-                                                              const unsigned* __restrict__ clean_len, short* __restrict__ coef) {
+                                                              const unsigned* __restrict__ clean_len, short* __restrict__ coef, int tiered) {
     extern __shared__ __align__(16) unsigned char jh_smem[];
     HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);   // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
     __shared__ unsigned char s_zz[64];
@@ -306,9 +319,9 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
             }
             H.maxcode[0] = -1; H.valoff[0] = 0; H.nsub = 0;
         }
-        for (int i = threadIdx.x; i < 256; i += JH_THREADS) H.vals[i] = raw.vals[i];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) H.vals[i] = raw.vals[i];
         __syncthreads();
-        for (int i = threadIdx.x; i < (1 << JH_LUT_BITS); i += JH_THREADS) {
+        for (int i = threadIdx.x; i < (1 << JH_LUT_BITS); i += blockDim.x) {
             unsigned e = 0;
             for (int l = 1; l <= JH_LUT_BITS; ++l) {
                 const int code = i >> (JH_LUT_BITS - l);
@@ -345,10 +358,32 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
         }
     }
     __syncthreads();
-    const int j = block_first[blockIdx.x] + threadIdx.x;   // restart interval of this thread
-    if (j >= f.n_seg) return;
-    const unsigned char* base = clean + f.clean_off;             // 16-byte aligned
+    // The block's restart intervals, longest first (their lengths in the clean stream are the work: ncu showed the kernel at 0.14 IPC,
+    // one warp per scheduler, 100 instructions per symbol iteration — the union of 32 lanes' paths — and as long as the longest
+    // interval of the batch, 4.4x the mean on text pages).  Lanes of a warp then hold intervals of similar length, and in the tiered
+    // layout the longest ones decode alone in their warp.
+    __shared__ unsigned s_len[JH_IPB_MAX];
+    __shared__ unsigned char s_order[JH_IPB_MAX];
     const unsigned clen = clean_len[fi];
+    const int j0 = block_first[blockIdx.x];
+    const int cnt = min(tiered ? JH_T_IPB : JH_THREADS, f.n_seg - j0);
+    if ((int)threadIdx.x < cnt) {
+        const int jj = j0 + threadIdx.x;
+        const unsigned a0 = min(seg[f.seg_base + jj], clen), a1 = jj + 1 < f.n_seg ? min(seg[f.seg_base + jj + 1], clen) : clen;
+        s_len[threadIdx.x] = a1 > a0 ? a1 - a0 : 0u;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+        const unsigned me = s_len[threadIdx.x];
+        int rank = 0;
+        for (int u = 0; u < cnt; ++u) { const unsigned o = s_len[u]; rank += (o > me || (o == me && u < (int)threadIdx.x)) ? 1 : 0; }
+        s_order[rank] = (unsigned char)threadIdx.x;
+    }
+    __syncthreads();
+    const int rk = tiered ? jh_tier_rank(threadIdx.x >> 5, threadIdx.x & 31) : (int)threadIdx.x;
+    if (rk < 0 || rk >= cnt) return;
+    const int j = j0 + s_order[rk];   // restart interval of this thread
+    const unsigned char* base = clean + f.clean_off;             // 16-byte aligned
     const unsigned start = min(seg[f.seg_base + j], clen);
     const unsigned* wp = reinterpret_cast<const unsigned*>(base + (start & ~3u));
     unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
@@ -376,6 +411,77 @@ __global__ void __launch_bounds__(JH_THREADS) jpeg_huff_kernel(const JpegDev* __
     int b = 0, k = 0, ci = 0;
     short* blk = coef + ((size_t)cbase0 + (size_t)(my * v0) * cwb0 + mx * h0) * 64;
     const HuffDev* tab = tdc0;
+    if (tiered && (threadIdx.x >> 5) < JH_T_SOLO) {
+        // A warp with ONE decoding lane (the longest intervals of the block): nothing to keep in step with, so the decoder is
+        // written as libjpeg's nested loops — MCU, block, one DC symbol, the AC symbols — instead of the flat one-symbol-per-iteration
+        // loop below, whose block / table switches and three-way symbol branch sit inside every iteration.
+        // (Measured and dropped: all 32 lanes of such a warp decoding the 32 possible next bit offsets, the chain of real symbol
+        // starts walked with one shuffle per symbol — bit-exact, but 640 cycles per symbol against 310 here: rounds end at every
+        // block boundary (the next code is a DC code of another table), text pages average a handful of symbols per block, and the
+        // per-round set-up is serial code at 0.2 IPC.)
+        auto symbol = [&](const HuffDev* t, bool is_dc, int& r, int& sz, int& v) {
+            const unsigned win = __funnelshift_l(w1, w0, o);
+            unsigned e = t->lut[win >> (32 - JH_LUT_BITS)];
+            if ((e & 31u) == 0) {
+                const unsigned slot = e >> 16;
+                if (slot < JH_SUB_SLOTS) e = t->sub[slot * 64 + ((win >> 16) & 63u)];
+                else {
+                    const unsigned top = win >> 16;
+                    unsigned sym = 0, l = 16;
+#pragma unroll 1
+                    for (int q = JH_LUT_BITS + 1; q <= 16; ++q) {
+                        const int code = (int)(top >> (16 - q));
+                        if (code <= t->maxcode[q]) { sym = t->vals[(t->valoff[q] + code) & 255]; l = q; break; }
+                    }
+                    e = is_dc ? (l | ((sym & 15u) << 9)) : (l | ((sym >> 4) << 5) | ((sym & 15u) << 9));
+                }
+            }
+            unsigned L = e & 31u;
+            r = (int)((e >> 5) & 15u); sz = (int)((e >> 9) & 15u);
+            v = (int)e >> 16;
+            if (!(e & (1u << 13)) && sz) {
+                v = jh_extend((int)((win << L) >> (32 - sz)), sz);
+                L += (unsigned)sz;
+            }
+            o += L;
+            if (o >= 32u) {
+                o -= 32u;
+                w0 = w1;
+                w1 = __byte_perm(nxt, 0, 0x0123);
+                nxt = __ldg(wp);
+                ++wp;
+            }
+        };
+        for (; m < m1; ++m) {
+            for (int bb = 0; bb < nb; ++bb) {
+                const int cc = max(0, bb - nb0 + 1);
+                const int bi = cc == 0 ? bb : 0;
+                const int dy = h0 == 2 ? (bi >> 1) : bi, dx = h0 == 2 ? (bi & 1) : 0;
+                const int hh = cc == 0 ? h0 : 1, vv = cc == 0 ? v0 : 1;
+                const unsigned cb_ = cc == 0 ? cbase0 : (cc == 1 ? cbase1 : cbase2);
+                const int wb_ = cc == 0 ? cwb0 : (cc == 1 ? cwb1 : cwb2);
+                short* bp = coef + ((size_t)cb_ + (size_t)(my * vv + dy) * wb_ + (mx * hh + dx)) * 64;
+                const HuffDev* tdc = cc == 0 ? tdc0 : (cc == 1 ? tdc1 : tdc2);
+                const HuffDev* tac = cc == 0 ? tac0 : (cc == 1 ? tac1 : tac2);
+                int r, sz, v;
+                symbol(tdc, true, r, sz, v);
+                int pv;
+                if (cc == 0) { pred0 += v; pv = pred0; } else if (cc == 1) { pred1 += v; pv = pred1; } else { pred2 += v; pv = pred2; }
+                if (pv) bp[0] = (short)pv;
+                int kk = 1;
+                while (kk < 64) {
+                    symbol(tac, false, r, sz, v);
+                    if (sz) {
+                        kk += r;
+                        if (kk < 64) bp[s_zz[kk]] = (short)v;
+                        ++kk;
+                    } else kk = r == 15 ? kk + 16 : 64;
+                }
+            }
+            if (++mx == f.mcux) { mx = 0; ++my; }
+        }
+        return;
+    }
     while (m < m1) {
         const unsigned win = __funnelshift_l(w1, w0, o);          // the 32 bits at the read position
         unsigned e = tab->lut[win >> (32 - JH_LUT_BITS)];
@@ -671,7 +777,14 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     const size_t desc_bytes = (sizeof(JpegDev) * (size_t)n + 15) & ~size_t(15);
     long long total_seg = 0;
     size_t n_tblocks = 0;
-    for (int i = 0; i < n; ++i) { total_seg += infos[i].n_seg; n_tblocks += ((size_t)infos[i].n_seg + JH_THREADS - 1) / JH_THREADS; }
+    for (int i = 0; i < n; ++i) total_seg += infos[i].n_seg;
+    // jpeg_huff_kernel layout: tiered (16 warps share 112 intervals, the 8 longest alone in their warp) while every block of the batch
+    // is resident at once (4 blocks of 512 threads per SM); dense (128 intervals per 128 threads) for batches with more intervals
+    // than that — short restart intervals, where throughput, not the longest chain, is the bound.  RETTO_B200_JPEG_DENSE=1: A/B.
+    static const bool force_dense = getenv("RETTO_B200_JPEG_DENSE") != nullptr;
+    const bool tiered = !force_dense && total_seg <= 148LL * 4 * JH_T_IPB;
+    const int jh_ipb = tiered ? JH_T_IPB : JH_THREADS;   // restart intervals per block
+    for (int i = 0; i < n; ++i) n_tblocks += ((size_t)infos[i].n_seg + jh_ipb - 1) / jh_ipb;
     if (total_seg > 0x3fffffffLL) { ctx->set_error("jpeg decode: too many restart intervals"); return RETTO_B200_ERR_CAPACITY; }
     const size_t tb_bytes = (sizeof(int) * 2 * n_tblocks + 15) & ~size_t(15);
     const size_t head_bytes = desc_bytes + tb_bytes;
@@ -711,7 +824,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         if (blocks > 0x7fffffffULL) { ctx->set_error("jpeg decode: batch too large (coefficient blocks)"); return RETTO_B200_ERR_CAPACITY; }
         D.n_blocks = (unsigned)blocks - D.block_base;
         JB.X[i] = J.X; JB.Y[i] = J.Y; JB.n_blocks[i] = D.n_blocks;
-        for (int j0 = 0; j0 < J.n_seg; j0 += JH_THREADS) { h_tb_file[tb] = i; h_tb_first[tb] = j0; ++tb; }
+        for (int j0 = 0; j0 < J.n_seg; j0 += jh_ipb) { h_tb_file[tb] = i; h_tb_first[tb] = j0; ++tb; }
         seg_base += J.n_seg;
         for (int k = 0; k < 4; ++k) {
             memcpy(h_tab[i].qt[k], J.qt[k], sizeof(J.qt[k]));
@@ -748,8 +861,8 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         RT_CUDA_OK(ctx, cudaFuncSetAttribute(jpeg_huff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(HuffDev) * 6)));
         ctx->jpeg_huff_attr_set = true;
     }
-    jpeg_huff_kernel<<<(unsigned)n_tblocks, JH_THREADS, sizeof(HuffDev) * 6, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len,
-                                                                 ctx->d_jpeg_coef.as<short>());
+    jpeg_huff_kernel<<<(unsigned)n_tblocks, tiered ? JH_T_THREADS : JH_THREADS, sizeof(HuffDev) * 6, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg,
+                                                                 ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len, ctx->d_jpeg_coef.as<short>(), tiered ? 1 : 0);
     RT_LAUNCH_CHECK(ctx);
     ctx->timer_stream = nullptr;
     return RETTO_B200_OK;
