@@ -266,6 +266,7 @@ struct retto_b200_ctx {
         size_t desc_bytes = 0, head_bytes = 0;
         std::vector<int> X, Y;
         std::vector<unsigned> n_blocks;
+        std::vector<unsigned char> is420;   // 3 components, 2x2 luma : 1x1 chroma (the colour kernel has a specialisation for it)
         HostBuf h_desc;
     } jpeg;
     bool jpeg_huff_attr_set = false;             // dynamic shared memory opt-in of jpeg_huff_kernel done on this context's device

@@ -597,13 +597,24 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDev* __restric
     const unsigned B = f.block_base + lb;
     int ci = 0;
     unsigned local = 0;
+    bool ac = false;       // this thread's coefficient row holds something besides the block's DC term
+    int dc = 0;
     if (live) {
         while (ci + 1 < f.nc && B >= f.c[ci + 1].coef_base) ++ci;
         local = B - f.c[ci].coef_base;
-        *reinterpret_cast<uint4*>(&s_coef[g][t * 8]) = __ldg(reinterpret_cast<const uint4*>(coef + (size_t)B * 64 + t * 8));
+        const uint4 cv = __ldg(reinterpret_cast<const uint4*>(coef + (size_t)B * 64 + t * 8));
+        *reinterpret_cast<uint4*>(&s_coef[g][t * 8]) = cv;
+        ac = ((t == 0 ? (cv.x & 0xffff0000u) : cv.x) | cv.y | cv.z | cv.w) != 0u;
+        dc = (int)(short)(cv.x & 0xffffu);
     }
+    // DC-only blocks (the blank background of a page: most blocks of a text page): both passes collapse to one value — exactly what
+    // jidctint.c's zero-AC shortcuts compute, and what the full passes below would (DESCALE(dc << 13, 11) == dc << 2 without a rounding
+    // carry) — so the eight threads of such a block skip the passes and the shared-memory transposes
+    const unsigned grp = (__ballot_sync(0xffffffffu, ac) >> (threadIdx.x & 24)) & 0xffu;
+    const bool full = live && grp != 0u;
+    dc = __shfl_sync(0xffffffffu, dc, threadIdx.x & 24);
     __syncwarp();
-    if (live) {
+    if (full) {
         const unsigned short* q = tables[fi].qt[f.c[ci].tq];
         int in[8], o[8];
 #pragma unroll
@@ -615,12 +626,19 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDev* __restric
     __syncwarp();
     if (live) {
         const JpegComp& c = f.c[ci];
-        int in[8], o[8];
+        unsigned lo4, hi4;
+        if (full) {
+            int in[8], o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) in[k] = s_ws[g][t * 8 + k];
-        ji_idct_1d(in, o, JI_CONST_BITS + JI_PASS1_BITS + 3);
-        const unsigned lo4 = ji_range_limit(o[0]) | (ji_range_limit(o[1]) << 8) | (ji_range_limit(o[2]) << 16) | (ji_range_limit(o[3]) << 24);
-        const unsigned hi4 = ji_range_limit(o[4]) | (ji_range_limit(o[5]) << 8) | (ji_range_limit(o[6]) << 16) | (ji_range_limit(o[7]) << 24);
+            for (int k = 0; k < 8; ++k) in[k] = s_ws[g][t * 8 + k];
+            ji_idct_1d(in, o, JI_CONST_BITS + JI_PASS1_BITS + 3);
+            lo4 = ji_range_limit(o[0]) | (ji_range_limit(o[1]) << 8) | (ji_range_limit(o[2]) << 16) | (ji_range_limit(o[3]) << 24);
+            hi4 = ji_range_limit(o[4]) | (ji_range_limit(o[5]) << 8) | (ji_range_limit(o[6]) << 16) | (ji_range_limit(o[7]) << 24);
+        } else {
+            const int w0 = (dc * (int)__ldg(tables[fi].qt[c.tq])) << JI_PASS1_BITS;                        // pass 1, column 0, every row
+            const unsigned px = ji_range_limit(ji_descale(w0 << JI_CONST_BITS, JI_CONST_BITS + JI_PASS1_BITS + 3));   // pass 2, every column
+            lo4 = hi4 = px * 0x01010101u;
+        }
         const unsigned by = local / (unsigned)c.wb, bx = local - by * (unsigned)c.wb;
         unsigned char* dst = planes + c.plane_off + ((size_t)by * 8 + t) * ((size_t)c.wb * 8) + (size_t)bx * 8;
         *reinterpret_cast<uint2*>(dst) = make_uint2(lo4, hi4);
@@ -700,6 +718,8 @@ __device__ __forceinline__ void jc_chroma8(const unsigned char* __restrict__ pl,
         out[2 * k + 1] = (c[1 + k] * 3 + next + 7) >> 4;
     }
 }
+// FIXED = 1: every file of the launch is 3-component 4:2:0 (the sampling factors fold into the code; checked by the host), 0: per file
+template <int FIXED>
 __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* __restrict__ files, const unsigned char* __restrict__ planes,
                                                                 uint8_t* const* __restrict__ outs, const unsigned* __restrict__ unit_prefix, int n_files) {
     __shared__ unsigned s_rgb[JC_THREADS * 6 + 1];
@@ -725,11 +745,11 @@ __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* _
     if (x0 < f.X) {
         const uint2 yv = __ldg(reinterpret_cast<const uint2*>(planes + f.c[0].plane_off + (size_t)y * ((size_t)f.c[0].wb * 8) + x0));
         unsigned char o[24];
-        if (f.nc == 1) {
+        if (!FIXED && f.nc == 1) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const unsigned v = ((k < 4 ? yv.x : yv.y) >> (8 * (k & 3))) & 0xFFu; o[3 * k] = o[3 * k + 1] = o[3 * k + 2] = (unsigned char)v; }
         } else {
-            const int hs = f.max_h / f.c[1].h, vs = f.max_v / f.c[1].v;
+            const int hs = FIXED ? 2 : f.max_h / f.c[1].h, vs = FIXED ? 2 : f.max_v / f.c[1].v;
             int cb[8], cr[8];
             jc_chroma8(planes + f.c[1].plane_off, f.c[1].wb * 8, f.c[1].ds_w, f.c[1].ds_h, hs, vs, x0, y, cb);
             jc_chroma8(planes + f.c[2].plane_off, f.c[2].wb * 8, f.c[2].ds_w, f.c[2].ds_h, hs, vs, x0, y, cr);
@@ -762,6 +782,97 @@ __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* _
     }
     const int tail0 = head + 4 * nw;
     if ((int)threadIdx.x < nbytes - tail0) gp[tail0 + threadIdx.x] = sb[tail0 + threadIdx.x];
+}
+
+// K-J4 for 3-component 4:2:0 files of one size (the common case: every page of a scanner / camera batch): one thread = 8 pixels of
+// TWO output rows.  Rows 2r+1 and 2r+2 use the same two chroma rows (r and r+1: 3a + b for the upper of the two, a + 3b for the lower), so
+// the chroma words are loaded and unpacked once for 16 pixels; everything is the same arithmetic as jc_chroma8 + the generic kernel
+// (jdsample.c h2v2_fancy_upsample, jdcolor.c), written for one sampling so the compiler sees constants (ncu: the generic kernel issues
+// 83 instructions per pixel at 77 % issue utilisation — it is instruction-bound, not memory-bound).
+// grid (x chunks, Y / 2 + 1 row pairs, files); row pair p = output rows 2p - 1 and 2p.  The host picks it only for chroma planes wider
+// than two samples (jdsample.c falls back to replication below that; the generic kernel has that branch).
+__global__ void __launch_bounds__(JC_THREADS) jpeg_color420_kernel(const JpegDev* __restrict__ files, const unsigned char* __restrict__ planes,
+                                                                   uint8_t* const* __restrict__ outs) {
+    __shared__ unsigned s_rgb[2][JC_THREADS * 6 + 1];
+    const JpegDev& f = files[blockIdx.z];
+    const int X = f.X, Y = f.Y;
+    const int p = blockIdx.y, ya = 2 * p - 1, yb = 2 * p;
+    const int xb = blockIdx.x * (int)blockDim.x * JC_PX;
+    if (xb >= X || ya >= Y) return;
+    const int x0 = xb + threadIdx.x * JC_PX;
+    const bool has_a = ya >= 0, has_b = yb < Y;
+    if (x0 < X) {
+        const int cw = f.c[1].ds_w, ch = f.c[1].ds_h, cstride = f.c[1].wb * 8;
+        const int rA = min(max(p - 1, 0), ch - 1), rB = min(p, ch - 1);
+        const int i0 = x0 >> 1, il = max(i0 - 1, 0), ir = min(i0 + 4, cw - 1);
+        int sa[2][6], sb[2][6];   // [plane][column i0-1 .. i0+4]: 3a + b (row ya) and a + 3b (row yb)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            const unsigned char* base = planes + f.c[1 + pl].plane_off;
+            const unsigned char* a = base + (size_t)rA * cstride;
+            const unsigned char* b = base + (size_t)rB * cstride;
+            const unsigned wa = __ldg(reinterpret_cast<const unsigned*>(a + i0)), wb = __ldg(reinterpret_cast<const unsigned*>(b + i0));
+            int ca[6], cb[6];
+            ca[0] = __ldg(a + il); ca[5] = __ldg(a + ir); cb[0] = __ldg(b + il); cb[5] = __ldg(b + ir);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { ca[1 + k] = (int)__byte_perm(wa, 0, 0x4440 + k); cb[1 + k] = (int)__byte_perm(wb, 0, 0x4440 + k); }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { sa[pl][k] = ca[k] * 3 + cb[k]; sb[pl][k] = cb[k] * 3 + ca[k]; }
+        }
+        const size_t ystride = (size_t)f.c[0].wb * 8;
+        const unsigned char* yp = planes + f.c[0].plane_off + x0;
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            if (row == 0 ? !has_a : !has_b) continue;
+            const uint2 yv = __ldg(reinterpret_cast<const uint2*>(yp + (size_t)(row == 0 ? ya : yb) * ystride));
+            unsigned char o[24];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                int uv[2][2];
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                    const int* s6 = row == 0 ? sa[pl] : sb[pl];
+                    const int c = s6[1 + k];
+                    const int prev = i == 0 ? c : s6[k], next = i >= cw - 1 ? c : s6[2 + k];
+                    uv[pl][0] = ((c * 3 + prev + 8) >> 4) - 128;
+                    uv[pl][1] = ((c * 3 + next + 7) >> 4) - 128;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int kk = 2 * k + h;
+                    const int yy = (int)__byte_perm(kk < 4 ? yv.x : yv.y, 0, 0x4440 + (kk & 3));
+                    const int u = uv[0][h], v = uv[1][h];
+                    const int r = yy + ((91881 * v + 32768) >> 16);
+                    const int g = yy + ((-22554 * u + 32768 - 46802 * v) >> 16);
+                    const int bl = yy + ((116130 * u + 32768) >> 16);
+                    o[3 * kk] = (unsigned char)min(max(r, 0), 255); o[3 * kk + 1] = (unsigned char)min(max(g, 0), 255); o[3 * kk + 2] = (unsigned char)min(max(bl, 0), 255);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s_rgb[row][threadIdx.x * 6 + k] = o[4 * k] | (o[4 * k + 1] << 8) | (o[4 * k + 2] << 16) | ((unsigned)o[4 * k + 3] << 24);
+        }
+    }
+    __syncthreads();
+    const int npx = min((int)blockDim.x * JC_PX, X - xb);
+    const int nbytes = 3 * npx;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+        if (row == 0 ? !has_a : !has_b) continue;
+        unsigned char* gp = outs[blockIdx.z] + ((size_t)(row == 0 ? ya : yb) * X + xb) * 3;
+        const int head = min((int)((4u - ((unsigned)(uintptr_t)gp & 3u)) & 3u), nbytes);
+        const unsigned char* sbp = reinterpret_cast<const unsigned char*>(s_rgb[row]);
+        if ((int)threadIdx.x < head) gp[threadIdx.x] = sbp[threadIdx.x];
+        const int nw = (nbytes - head) >> 2;
+        unsigned* gw = reinterpret_cast<unsigned*>(gp + head);
+        const unsigned sh = 8u * (unsigned)(head & 3);
+        for (int wi = threadIdx.x; wi < nw; wi += blockDim.x) {
+            const int so = (head + 4 * wi) >> 2;
+            gw[wi] = __funnelshift_r(s_rgb[row][so], s_rgb[row][so + 1], sh);
+        }
+        const int tail0 = head + 4 * nw;
+        if ((int)threadIdx.x < nbytes - tail0) gp[tail0 + threadIdx.x] = sbp[tail0 + threadIdx.x];
+    }
 }
 
 // ---- host: two phases ---------------------------------------------------------------------------------------------------------------
@@ -799,7 +910,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     unsigned long long blocks = 0, plane_bytes = 0, clean_bytes = 0;
     int seg_base = 0;
     size_t tb = 0;
-    JB.X.resize(n); JB.Y.resize(n); JB.n_blocks.resize(n);
+    JB.X.resize(n); JB.Y.resize(n); JB.n_blocks.resize(n); JB.is420.resize(n);
     for (int i = 0; i < n; ++i) {
         const JpegInfo& J = infos[i];
         JpegDev& D = hd[i];
@@ -824,6 +935,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         if (blocks > 0x7fffffffULL) { ctx->set_error("jpeg decode: batch too large (coefficient blocks)"); return RETTO_B200_ERR_CAPACITY; }
         D.n_blocks = (unsigned)blocks - D.block_base;
         JB.X[i] = J.X; JB.Y[i] = J.Y; JB.n_blocks[i] = D.n_blocks;
+        JB.is420[i] = (J.nc == 3 && J.h[0] == 2 && J.v[0] == 2 && J.h[1] == 1 && J.v[1] == 1 && J.h[2] == 1 && J.v[2] == 1) ? 1 : 0;
         for (int j0 = 0; j0 < J.n_seg; j0 += jh_ipb) { h_tb_file[tb] = i; h_tb_first[tb] = j0; ++tb; }
         seg_base += J.n_seg;
         for (int k = 0; k < 4; ++k) {
@@ -910,11 +1022,20 @@ retto_b200_status rt_jpeg_pixels_enqueue(retto_b200_ctx* owner, retto_b200_ctx* 
     if (uniform && same_blocks) jpeg_idct_kernel<<<dim3((JB.n_blocks[first] + 31) / 32, (unsigned)n), 256, 0, st>>>(d_files, d_tab, nullptr, n, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
     else jpeg_idct_kernel<<<(unsigned)ig, 256, 0, st>>>(d_files, d_tab, d_ip, n, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
     RT_LAUNCH_CHECK(lane);
+    bool all420 = true;
+    for (int i = first; i < first + n; ++i) all420 &= JB.is420[i] != 0;
     RT_LAUNCH_BEGIN(lane, "jpeg_color_kernel");
-    if (uniform && same_blocks)
-        jpeg_color_kernel<<<dim3((unsigned)((JB.X[first] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)JB.Y[first], (unsigned)n), jc_threads, 0, st>>>(
+    static const bool no_c420 = getenv("RETTO_B200_JPEG_NO_C420") != nullptr;   // A/B: the one-row kernel with the sampling folded in
+    if (uniform && same_blocks && all420 && JB.X[first] > 4 && !no_c420)
+        jpeg_color420_kernel<<<dim3((unsigned)((JB.X[first] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)(JB.Y[first] / 2 + 1), (unsigned)n), jc_threads, 0, st>>>(
+            d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs);
+    else if (uniform && same_blocks && all420)
+        jpeg_color_kernel<1><<<dim3((unsigned)((JB.X[first] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)JB.Y[first], (unsigned)n), jc_threads, 0, st>>>(
             d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, nullptr, n);
-    else jpeg_color_kernel<<<(unsigned)cu, jc_threads, 0, st>>>(d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, d_cp, n);
+    else if (uniform && same_blocks)
+        jpeg_color_kernel<0><<<dim3((unsigned)((JB.X[first] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)JB.Y[first], (unsigned)n), jc_threads, 0, st>>>(
+            d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, nullptr, n);
+    else jpeg_color_kernel<0><<<(unsigned)cu, jc_threads, 0, st>>>(d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, d_cp, n);
     RT_LAUNCH_CHECK(lane);
     return RETTO_B200_OK;
 }
