@@ -267,8 +267,10 @@ struct retto_b200_ctx {
         std::vector<int> X, Y;
         std::vector<unsigned> n_blocks;
         std::vector<unsigned char> is420;   // 3 components, 2x2 luma : 1x1 chroma (the colour kernel has a specialisation for it)
-        HostBuf h_desc;
+        HostBuf h_desc, h_sub;
     } jpeg;
+    DevBuf d_jpeg_sub;                           // K-J2s: slot tables, parse states, MCU-start bitmaps of the sub-sequence decode
+    bool jpeg_sub_attr_set = false;
     bool jpeg_huff_attr_set = false;             // dynamic shared memory opt-in of jpeg_huff_kernel done on this context's device
     int* jpeg_status_dev = nullptr;              // per-file device status of the last decode (inside d_jpeg_seg)
     HostBuf h_jpeg_status;

@@ -14,9 +14,13 @@
 //                              byte-aligned) — a 64-bit window of two big-endian words read with one funnel shift per symbol,
 //                              words loaded one refill ahead; 10-bit Huffman look-up tables in shared memory whose entries carry
 //                              the EXTENDed value when code + magnitude bits fit; non-zero coefficients are scattered into a
-//                              pre-zeroed int16 coefficient plane (a file without DRI is one interval = one thread)
-//   K-J3  jpeg_idct_kernel   : 8 threads per 8x8 block: dequantise + libjpeg's jidctint "islow" integer IDCT (columns, then rows)
-//   K-J4  jpeg_color_kernel  : libjpeg's fancy (triangle) chroma up-sampling h2v1 / h2v2 / h1v2 + YCbCr->RGB fixed point -> HWC u8
+//                              pre-zeroed int16 coefficient plane (a file without DRI is one interval = one thread).  Per block the
+//                              intervals are sorted by length and spread in tiers: the longest decode alone in their warp (nested
+//                              loops), the shortest fill whole warps (see jh_tier_rank)
+//   K-J3  jpeg_idct_kernel   : 8 threads per 8x8 block: dequantise + libjpeg's jidctint "islow" integer IDCT (columns, then rows);
+//                              DC-only blocks skip both passes
+//   K-J4  jpeg_color_kernel  : libjpeg's fancy (triangle) chroma up-sampling h2v1 / h2v2 / h1v2 + YCbCr->RGB fixed point -> HWC u8;
+//         jpeg_color420_kernel: the same for batches of 4:2:0 files of one size, two output rows per thread
 // Pixel policy: bit-exact with libjpeg-turbo's default decode (what Pillow / OpenCV produce); the oracle for this row is
 // oracle/jpeg_oracle.cpp, itself pinned against both libraries (tests/test_cpu_jpeg.py).  The reference's own decoder (zune-jpeg via
 // `image 0.25.6`) is an un-vendored dependency; JPEG decoders agree to +-1 LSB, not bit for bit — stated in DESIGN.md.
@@ -284,19 +288,9 @@ __device__ __forceinline__ int jh_tier_rank(int w, int l) {
 __device__ __forceinline__ int jh_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
 __device__ __forceinline__ unsigned jh_has_ff(unsigned w) { return __vcmpeq4(w, 0xFFFFFFFFu); }
 
-// Bit reader over the CLEAN stream (K-J1): w0:w1 = the next 64 bits (big-endian words), o = bits of w0 already consumed;
-// the 32-bit window at the read position is one funnel shift; `nxt` is the raw word after w1, loaded one refill ahead.
-__global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file,
-                                                              const int* __restrict__ block_first, const JpegTables* __restrict__ tables,
-                                                              const unsigned* __restrict__ seg, const unsigned char* __restrict__ clean,
-                                                              const unsigned* __restrict__ clean_len, short* __restrict__ coef, int tiered) {
-    extern __shared__ __align__(16) unsigned char jh_smem[];
-    HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);   // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
-    __shared__ unsigned char s_zz[64];
-    __shared__ int s_slot[6];
-    const int fi = block_file[blockIdx.x];
-    const JpegDev& f = files[fi];
-    const JpegTables& T = tables[fi];
+// Shared-memory decode tables of one file (canonical codes, jdhuff.c jpeg_make_d_derived_tbl): s_tab[2 * ci] = DC table of component
+// ci, [2 * ci + 1] = its AC table (s_slot maps tables shared by several components onto one copy).  Whole block; ends with a barrier.
+__device__ __forceinline__ void jh_build_tables(const JpegDev& f, const JpegTables& T, HuffDev* s_tab, unsigned char* s_zz, int* s_slot) {
     if (threadIdx.x < 64) s_zz[threadIdx.x] = D_ZIGZAG[threadIdx.x];
     // distinct tables -> shared memory (canonical codes, jdhuff.c jpeg_make_d_derived_tbl)
     for (int t = 0; t < 2 * f.nc; ++t) {
@@ -358,6 +352,22 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
         }
     }
     __syncthreads();
+}
+
+// Bit reader over the CLEAN stream (K-J1): w0:w1 = the next 64 bits (big-endian words), o = bits of w0 already consumed;
+// the 32-bit window at the read position is one funnel shift; `nxt` is the raw word after w1, loaded one refill ahead.
+__global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file,
+                                                              const int* __restrict__ block_first, const JpegTables* __restrict__ tables,
+                                                              const unsigned* __restrict__ seg, const unsigned char* __restrict__ clean,
+                                                              const unsigned* __restrict__ clean_len, short* __restrict__ coef, int tiered) {
+    extern __shared__ __align__(16) unsigned char jh_smem[];
+    HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);   // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
+    __shared__ unsigned char s_zz[64];
+    __shared__ int s_slot[6];
+    const int fi = block_file[blockIdx.x];
+    const JpegDev& f = files[fi];
+    const JpegTables& T = tables[fi];
+    jh_build_tables(f, T, s_tab, s_zz, s_slot);
     // The block's restart intervals, longest first (their lengths in the clean stream are the work: ncu showed the kernel at 0.14 IPC,
     // one warp per scheduler, 100 instructions per symbol iteration — the union of 32 lanes' paths — and as long as the longest
     // interval of the batch, 4.4x the mean on text pages).  Lanes of a warp then hold intervals of similar length, and in the tiered
@@ -539,6 +549,367 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
             blk = coef + ((size_t)cb_ + (size_t)(my * vv + dy) * wb_ + (mx * hh + dx)) * 64;
             tab = ci == 0 ? tdc0 : (ci == 1 ? tdc1 : tdc2);
         }
+    }
+}
+
+// ---- K-J2s: Huffman decode of SUB-SEQUENCES of a restart interval (self-synchronising parse) ------------------------------------
+// A restart interval is one serial chain, and a GPU thread walks it at ~310 cycles per symbol: a file without restart markers is ONE
+// chain (42 ms for a 1280x1280 page), and with one interval per MCU row the longest row of a text page is the kernel's duration.
+// Huffman streams re-synchronise: a decoder started at an arbitrary bit, in an arbitrary state, soon falls in step with the true
+// parse (Klein & Wiseman; Weissenberger & Schmidt, "Massively parallel Huffman decoding on GPUs", for JPEG: the state also holds
+// the position inside the MCU).  So every interval longer than JS_SUB_BYTES is cut into sub-sequences of JS_SUB_BYTES, one THREAD each:
+//   jpeg_sub_kernel    slot table: sub-sequence k of interval j of file f (the counts are only known on the device, after K-J1)
+//   jpeg_sync_kernel<1> every slot parses its own region from its first bit AS IF an MCU started there (lengths only: no values, no
+//                      stores) and records, in a bitmap over its region, the bit positions at which ITS parse starts an MCU, plus a
+//                      running count per bitmap word
+//   jpeg_sync_kernel<2> every slot keeps parsing into the following regions until it stands at an MCU start that the slot owning that
+//                      region ALSO recorded: from that bit on the two parses are identical.  Slot 0's parse is the true one from
+//                      its first bit, so by induction the chain of matches gives every slot a true start
+//   jpeg_resolve_kernel one thread per interval walks that chain: true start bit and MCU index of every slot (a slot whose region the
+//                      true parse crossed without a common MCU start gets no MCUs; an interval whose chain breaks is decoded by its
+//                      first slot alone, from bit 0 — correct, just serial)
+//   jpeg_huff_sub_kernel the real decode (values, coefficient stores) of every slot's MCU range, DC predictors starting at 0
+//   jpeg_dcfix_kernel  adds to the DC terms of a slot's blocks the predictors carried in from the slots before it
+#define JS_SUB_BYTES 1024
+#define JS_SUB_BITS (JS_SUB_BYTES * 8)
+#define JS_WORDS (JS_SUB_BITS / 32)
+#define JS_MAX_OVERLAP 3        // regions a parse may cross while looking for a common MCU start before the interval falls back
+struct JsSlot { int j, k, nsub, pad; };                 // interval (index inside the file), sub-sequence, sub-sequences of the interval
+struct JsState { unsigned p; int b, kk, marked; };      // after pass 1: bit position (relative to the interval), block in MCU, zig-zag index, MCU starts recorded
+struct JsSync { int t; unsigned X; int C, pad; };       // written by slot s: first later slot t of the interval it met (-1: none, -2: gave up), at bit X; C = MCU starts of s's parse before X
+struct JsStart { unsigned bit; int mcu, n_mcu, pad; };  // true start of a slot: bit (relative to the interval), first MCU (relative to the interval), MCUs to decode
+
+__global__ void __launch_bounds__(256) jpeg_sub_kernel(const JpegDev* __restrict__ files, const unsigned* __restrict__ seg, const unsigned* __restrict__ clean_len,
+                                                       const int* __restrict__ sub_base, int* __restrict__ isub, JsSlot* __restrict__ slots) {
+    const int fi = blockIdx.x;
+    const JpegDev& f = files[fi];
+    const unsigned clen = clean_len[fi];
+    const int first = sub_base[fi], cap = sub_base[fi + 1] - first;
+    __shared__ int s_scan[256];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < f.n_seg; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        int ns = 0;
+        if (j < f.n_seg) {
+            const unsigned a0 = min(seg[f.seg_base + j], clen), a1 = j + 1 < f.n_seg ? min(seg[f.seg_base + j + 1], clen) : clen;
+            const unsigned len = a1 > a0 ? a1 - a0 : 0u;
+            ns = max(1, (int)((len + JS_SUB_BYTES - 1) / JS_SUB_BYTES));
+        }
+        s_scan[threadIdx.x] = ns;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            const int v = (int)threadIdx.x >= d ? s_scan[threadIdx.x - d] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const int at = s_run + s_scan[threadIdx.x] - ns;
+        if (j < f.n_seg) {
+            isub[f.seg_base + j] = first + at;
+            for (int k = 0; k < ns; ++k) if (at + k < cap) slots[first + at + k] = JsSlot{j, k, ns, 0};
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_run += s_scan[255];
+        __syncthreads();
+    }
+    for (int i = s_run + threadIdx.x; i < cap; i += 256) slots[first + i] = JsSlot{-1, 0, 0, 0};
+}
+
+// One symbol of the parse: total length in bits (code + magnitude), run, size.  t = the table the state selects.
+__device__ __forceinline__ void js_symbol(const HuffDev* t, bool is_dc, unsigned win, unsigned& L, int& r, int& sz) {
+    unsigned e = t->lut[win >> (32 - JH_LUT_BITS)];
+    if ((e & 31u) == 0) {
+        const unsigned slot = e >> 16;
+        if (slot < JH_SUB_SLOTS) e = t->sub[slot * 64 + ((win >> 16) & 63u)];
+        else {
+            const unsigned top = win >> 16;
+            unsigned sym = 0, l = 16;
+#pragma unroll 1
+            for (int q = JH_LUT_BITS + 1; q <= 16; ++q) {
+                const int code = (int)(top >> (16 - q));
+                if (code <= t->maxcode[q]) { sym = t->vals[(t->valoff[q] + code) & 255]; l = q; break; }
+            }
+            e = is_dc ? (l | ((sym & 15u) << 9)) : (l | ((sym >> 4) << 5) | ((sym & 15u) << 9));
+        }
+    }
+    r = (int)((e >> 5) & 15u); sz = (int)((e >> 9) & 15u);
+    L = (e & 31u) + ((e & (1u << 13)) ? 0u : (unsigned)sz);
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file, const int* __restrict__ block_first,
+                                                        const JpegTables* __restrict__ tables, const unsigned* __restrict__ seg,
+                                                        const unsigned char* __restrict__ clean, const unsigned* __restrict__ clean_len,
+                                                        const JsSlot* __restrict__ slots, unsigned* __restrict__ bitmaps, unsigned short* __restrict__ counts,
+                                                        JsState* __restrict__ states, JsSync* __restrict__ syncs) {
+    extern __shared__ __align__(16) unsigned char jh_smem[];
+    HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);
+    __shared__ unsigned char s_zz[64];
+    __shared__ int s_slot[6];
+    const int fi = block_file[blockIdx.x];
+    const JpegDev& f = files[fi];
+    jh_build_tables(f, tables[fi], s_tab, s_zz, s_slot);
+    const int slot = block_first[blockIdx.x] + threadIdx.x;
+    if (slot >= block_first[blockIdx.x + 1]) return;   // block_first holds one more entry: the end of the last block's file
+    const JsSlot sl = slots[slot];
+    if (sl.j < 0 || sl.nsub <= 1) return;               // single-slot intervals need no parse
+    if (PHASE == 2 && sl.k == sl.nsub - 1) { syncs[slot] = JsSync{-1, 0u, 0, 0}; return; }
+    const unsigned clen = clean_len[fi];
+    const unsigned a0 = min(seg[f.seg_base + sl.j], clen), a1 = sl.j + 1 < f.n_seg ? min(seg[f.seg_base + sl.j + 1], clen) : clen;
+    const unsigned len_bits = 8u * (a1 > a0 ? a1 - a0 : 0u);
+    const unsigned r0 = (unsigned)sl.k * JS_SUB_BITS, r1 = min(r0 + JS_SUB_BITS, len_bits);
+    const int nb0 = f.c[0].h * f.c[0].v, nb = f.nc == 1 ? 1 : nb0 + 2;
+    const int c1 = f.nc > 1 ? 1 : 0, c2 = f.nc > 2 ? 2 : 0;
+    const HuffDev* tdc0 = &s_tab[s_slot[0]];
+    const HuffDev* tac0 = &s_tab[s_slot[1]];
+    const HuffDev* tdc1 = &s_tab[s_slot[2 * c1]];
+    const HuffDev* tac1 = &s_tab[s_slot[2 * c1 + 1]];
+    const HuffDev* tdc2 = &s_tab[s_slot[2 * c2]];
+    const HuffDev* tac2 = &s_tab[s_slot[2 * c2 + 1]];
+    unsigned p;
+    int b, kk;
+    if (PHASE == 1) { p = r0; b = 0; kk = 0; }
+    else { const JsState st = states[slot]; p = st.p; b = st.b; kk = st.kk; }
+    // bit reader at absolute bit 8 * a0 + p of the file's clean stream (16-byte aligned base)
+    const unsigned char* base = clean + f.clean_off;
+    const unsigned long long abit = 8ull * a0 + p;
+    const unsigned* wp = reinterpret_cast<const unsigned*>(base) + (abit >> 5);
+    unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
+    unsigned nxt = __ldg(wp + 2);
+    wp += 3;
+    unsigned o = (unsigned)(abit & 31ull);
+    // PHASE 1: bitmap of this slot's MCU starts + running count per word
+    unsigned* bm = bitmaps + (size_t)slot * JS_WORDS;
+    unsigned short* cnt = counts + (size_t)slot * JS_WORDS;
+    int cw = 0, run = 0;
+    unsigned cur = 0;
+    int extra = 0;                       // PHASE 2: MCU starts of this parse at or after r1 that were not common
+    int found_t = -1;
+    unsigned found_x = 0;
+    bool gave_up = false;
+    for (;;) {
+        if (b == 0 && kk == 0) {         // an MCU starts at p
+            if (PHASE == 1) {
+                if (p >= r1) break;
+                const int d = (int)(p - r0), wd = d >> 5;
+                while (cw < wd) { bm[cw] = cur; cnt[cw] = (unsigned short)run; run += __popc(cur); cur = 0; ++cw; }
+                cur |= 1u << (d & 31);
+            } else if (p >= r1) {
+                if (p >= len_bits) break;                                   // the interval ends: this parse runs to its end
+                const int t = (int)(p / JS_SUB_BITS);                     // the region p lies in
+                if (t - sl.k > JS_MAX_OVERLAP) { gave_up = true; break; }
+                const int d = (int)(p - (unsigned)t * JS_SUB_BITS);
+                if ((bitmaps[(size_t)(slot + (t - sl.k)) * JS_WORDS + (d >> 5)] >> (d & 31)) & 1u) { found_t = t; found_x = p; break; }
+                ++extra;
+            }
+        } else if (PHASE == 1 && p >= r1) break;   // mid-MCU at the end of the region: pass 2 continues from this state
+        if (p >= len_bits) break;                  // out of data
+        const unsigned win = __funnelshift_l(w1, w0, o);
+        const int ci = max(0, b - nb0 + 1);
+        const HuffDev* t = kk == 0 ? (ci == 0 ? tdc0 : (ci == 1 ? tdc1 : tdc2)) : (ci == 0 ? tac0 : (ci == 1 ? tac1 : tac2));
+        unsigned L;
+        int r, sz;
+        js_symbol(t, kk == 0, win, L, r, sz);
+        p += L;
+        o += L;
+        if (o >= 32u) {
+            o -= 32u;
+            w0 = w1;
+            w1 = __byte_perm(nxt, 0, 0x0123);
+            nxt = __ldg(wp);
+            ++wp;
+        }
+        if (kk == 0) kk = 1;
+        else if (sz) kk += r + 1;
+        else kk = r == 15 ? kk + 16 : 64;
+        if (kk >= 64) { kk = 0; if (++b == nb) b = 0; }
+    }
+    if (PHASE == 1) {
+        while (cw < JS_WORDS) { bm[cw] = cur; cnt[cw] = (unsigned short)run; run += __popc(cur); cur = 0; ++cw; }
+        states[slot] = JsState{p, b, kk, run};
+    } else {
+        syncs[slot] = JsSync{gave_up ? -2 : found_t, found_x, states[slot].marked + extra, 0};
+    }
+}
+
+// One thread per restart interval with more than one slot: the chain of common MCU starts -> true start of every slot.
+__global__ void jpeg_resolve_kernel(const JpegDev* __restrict__ files, const int* __restrict__ seg_file, int total_seg, const int* __restrict__ isub,
+                                    const JsSlot* __restrict__ slots, const unsigned* __restrict__ bitmaps, const unsigned short* __restrict__ counts,
+                                    const JsSync* __restrict__ syncs, JsStart* __restrict__ starts) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;   // global interval index
+    if (g >= total_seg) return;
+    const JpegDev& f = files[seg_file[g]];
+    const int j = g - f.seg_base;
+    const int first = isub[g];
+    const int nsub = slots[first].nsub;
+    const long long n_mcu_file = (long long)f.mcux * f.mcuy;
+    const long long m0 = f.ri > 0 ? (long long)j * f.ri : 0;
+    const int total = (int)max(0ll, min(f.ri > 0 ? (long long)f.ri : n_mcu_file, n_mcu_file - m0));   // MCUs of this interval
+    if (nsub <= 1) { starts[first] = JsStart{0u, 0, total, 0}; return; }
+    for (int s = 0; s < nsub; ++s) starts[first + s] = JsStart{0u, 0, 0, 0};
+    int s = 0, m = 0;
+    unsigned X = 0;
+    bool ok = true;
+    while (true) {
+        const JsSync sy = syncs[first + s];
+        if (sy.t == -2) { ok = false; break; }
+        if (sy.t < 0) { starts[first + s] = JsStart{X, m, max(total - m, 0), 0}; break; }
+        const int d = (int)(X - (unsigned)s * JS_SUB_BITS);                  // X lies in slot s's own region (it was found in its bitmap)
+        const int before = (int)counts[(size_t)(first + s) * JS_WORDS + (d >> 5)] + __popc(bitmaps[(size_t)(first + s) * JS_WORDS + (d >> 5)] & ((1u << (d & 31)) - 1u));
+        const int n = sy.C - before;
+        if (n < 0 || m + n > total || sy.t <= s || sy.t >= nsub) { ok = false; break; }
+        starts[first + s] = JsStart{X, m, n, 0};
+        m += n; s = sy.t; X = sy.X;
+    }
+    if (!ok) {   // the chain broke (or the data is damaged): the first slot decodes the whole interval
+        for (int u = 1; u < nsub; ++u) starts[first + u] = JsStart{0u, 0, 0, 0};
+        starts[first] = JsStart{0u, 0, total, 0};
+    }
+}
+
+// The real decode of one slot's MCU range (the flat symbol loop of jpeg_huff_kernel), DC predictors starting at 0; the predictors
+// at the end of the range go to preds[slot] for jpeg_dcfix_kernel.
+__global__ void __launch_bounds__(128) jpeg_huff_sub_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file, const int* __restrict__ block_first,
+                                                            const JpegTables* __restrict__ tables, const unsigned* __restrict__ seg,
+                                                            const unsigned char* __restrict__ clean, const unsigned* __restrict__ clean_len,
+                                                            const JsSlot* __restrict__ slots, const JsStart* __restrict__ starts, int4* __restrict__ preds,
+                                                            short* __restrict__ coef) {
+    extern __shared__ __align__(16) unsigned char jh_smem[];
+    HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);
+    __shared__ unsigned char s_zz[64];
+    __shared__ int s_slot[6];
+    const int fi = block_file[blockIdx.x];
+    const JpegDev& f = files[fi];
+    jh_build_tables(f, tables[fi], s_tab, s_zz, s_slot);
+    const int slot = block_first[blockIdx.x] + threadIdx.x;
+    if (slot >= block_first[blockIdx.x + 1]) return;
+    const JsSlot sl = slots[slot];
+    if (sl.j < 0) return;
+    const JsStart st = starts[slot];
+    if (st.n_mcu <= 0) { preds[slot] = make_int4(0, 0, 0, 0); return; }
+    const unsigned clen = clean_len[fi];
+    const unsigned a0 = min(seg[f.seg_base + sl.j], clen);
+    const unsigned char* base = clean + f.clean_off;
+    const unsigned long long abit = 8ull * a0 + st.bit;
+    const unsigned* wp = reinterpret_cast<const unsigned*>(base) + (abit >> 5);
+    unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
+    unsigned nxt = __ldg(wp + 2);
+    wp += 3;
+    unsigned o = (unsigned)(abit & 31ull);
+    long long m = (f.ri > 0 ? (long long)sl.j * f.ri : 0) + st.mcu;
+    const long long m1 = m + st.n_mcu;
+    int my = (int)(m / f.mcux), mx = (int)(m - (long long)my * f.mcux);
+    const int nb0 = f.c[0].h * f.c[0].v, nb = f.nc == 1 ? 1 : nb0 + 2;
+    const int h0 = f.c[0].h, v0 = f.c[0].v;
+    const int c1 = f.nc > 1 ? 1 : 0, c2 = f.nc > 2 ? 2 : 0;
+    const HuffDev* tdc0 = &s_tab[s_slot[0]];
+    const HuffDev* tac0 = &s_tab[s_slot[1]];
+    const HuffDev* tdc1 = &s_tab[s_slot[2 * c1]];
+    const HuffDev* tac1 = &s_tab[s_slot[2 * c1 + 1]];
+    const HuffDev* tdc2 = &s_tab[s_slot[2 * c2]];
+    const HuffDev* tac2 = &s_tab[s_slot[2 * c2 + 1]];
+    const unsigned cbase0 = f.c[0].coef_base, cbase1 = f.c[c1].coef_base, cbase2 = f.c[c2].coef_base;
+    const int cwb0 = f.c[0].wb, cwb1 = f.c[c1].wb, cwb2 = f.c[c2].wb;
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    int b = 0, k = 0, ci = 0;
+    short* blk = coef + ((size_t)cbase0 + (size_t)(my * v0) * cwb0 + mx * h0) * 64;
+    const HuffDev* tab = tdc0;
+    while (m < m1) {
+        const unsigned win = __funnelshift_l(w1, w0, o);
+        unsigned e = tab->lut[win >> (32 - JH_LUT_BITS)];
+        if ((e & 31u) == 0) {
+            const unsigned slot2 = e >> 16;
+            if (slot2 < JH_SUB_SLOTS) e = tab->sub[slot2 * 64 + ((win >> 16) & 63u)];
+            else {
+                const unsigned top = win >> 16;
+                unsigned sym = 0, l = 16;
+#pragma unroll 1
+                for (int q = JH_LUT_BITS + 1; q <= 16; ++q) {
+                    const int code = (int)(top >> (16 - q));
+                    if (code <= tab->maxcode[q]) { sym = tab->vals[(tab->valoff[q] + code) & 255]; l = q; break; }
+                }
+                e = k == 0 ? (l | ((sym & 15u) << 9)) : (l | ((sym >> 4) << 5) | ((sym & 15u) << 9));
+            }
+        }
+        unsigned L = e & 31u;
+        const int r = (int)((e >> 5) & 15u), sz = (int)((e >> 9) & 15u);
+        int v = (int)e >> 16;
+        if (!(e & (1u << 13)) && sz) {
+            v = jh_extend((int)((win << L) >> (32 - sz)), sz);
+            L += (unsigned)sz;
+        }
+        o += L;
+        if (o >= 32u) {
+            o -= 32u;
+            w0 = w1;
+            w1 = __byte_perm(nxt, 0, 0x0123);
+            nxt = __ldg(wp);
+            ++wp;
+        }
+        if (k == 0) {
+            int pv;
+            if (ci == 0) { pred0 += v; pv = pred0; } else if (ci == 1) { pred1 += v; pv = pred1; } else { pred2 += v; pv = pred2; }
+            if (pv) blk[0] = (short)pv;
+            k = 1;
+            tab = ci == 0 ? tac0 : (ci == 1 ? tac1 : tac2);
+        } else if (sz) {
+            k += r;
+            if (k < 64) blk[s_zz[k]] = (short)v;
+            ++k;
+        } else {
+            k = r == 15 ? k + 16 : 64;
+        }
+        if (k >= 64) {
+            k = 0;
+            if (++b == nb) { b = 0; ++m; if (++mx == f.mcux) { mx = 0; ++my; } }
+            ci = max(0, b - nb0 + 1);
+            const int bi = ci == 0 ? b : 0;
+            const int dy = h0 == 2 ? (bi >> 1) : bi, dx = h0 == 2 ? (bi & 1) : 0;
+            const int hh = ci == 0 ? h0 : 1, vv = ci == 0 ? v0 : 1;
+            const unsigned cb_ = ci == 0 ? cbase0 : (ci == 1 ? cbase1 : cbase2);
+            const int wb_ = ci == 0 ? cwb0 : (ci == 1 ? cwb1 : cwb2);
+            blk = coef + ((size_t)cb_ + (size_t)(my * vv + dy) * wb_ + (mx * hh + dx)) * 64;
+            tab = ci == 0 ? tdc0 : (ci == 1 ? tdc1 : tdc2);
+        }
+    }
+    preds[slot] = make_int4(pred0, pred1, pred2, 0);
+}
+
+// DC terms are coded as differences: a slot that did not start its interval decoded its DC terms from predictors 0, so the
+// predictors at the end of all earlier slots of the interval are added to the DC term of every block of its MCU range.
+__global__ void __launch_bounds__(128) jpeg_dcfix_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file, const int* __restrict__ block_first,
+                                                         const JsSlot* __restrict__ slots, const JsStart* __restrict__ starts, const int4* __restrict__ preds,
+                                                         short* __restrict__ coef) {
+    const int fi = block_file[blockIdx.x];
+    const JpegDev& f = files[fi];
+    const int slot = block_first[blockIdx.x] + threadIdx.x;
+    if (slot >= block_first[blockIdx.x + 1]) return;
+    const JsSlot sl = slots[slot];
+    if (sl.j < 0 || sl.k == 0) return;
+    const JsStart st = starts[slot];
+    if (st.n_mcu <= 0) return;
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int u = 1; u <= sl.k; ++u) { const int4 q = preds[slot - u]; c0 += q.x; c1 += q.y; c2 += q.z; }
+    if ((c0 | c1 | c2) == 0) return;
+    const int nb0 = f.c[0].h * f.c[0].v, h0 = f.c[0].h, v0 = f.c[0].v;
+    long long m = (f.ri > 0 ? (long long)sl.j * f.ri : 0) + st.mcu;
+    const long long m1 = m + st.n_mcu;
+    int my = (int)(m / f.mcux), mx = (int)(m - (long long)my * f.mcux);
+    for (; m < m1; ++m) {
+        if (c0) {
+            for (int bi = 0; bi < nb0; ++bi) {
+                const int dy = h0 == 2 ? (bi >> 1) : bi, dx = h0 == 2 ? (bi & 1) : 0;
+                short* bp = coef + ((size_t)f.c[0].coef_base + (size_t)(my * v0 + dy) * f.c[0].wb + (mx * h0 + dx)) * 64;
+                bp[0] = (short)(bp[0] + c0);
+            }
+        }
+        if (f.nc > 1) {
+            if (c1) { short* bp = coef + ((size_t)f.c[1].coef_base + (size_t)my * f.c[1].wb + mx) * 64; bp[0] = (short)(bp[0] + c1); }
+            if (c2) { short* bp = coef + ((size_t)f.c[2].coef_base + (size_t)my * f.c[2].wb + mx) * 64; bp[0] = (short)(bp[0] + c2); }
+        }
+        if (++mx == f.mcux) { mx = 0; ++my; }
     }
 }
 
@@ -967,6 +1338,95 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     RT_LAUNCH_BEGIN(ctx, "jpeg_scan_kernel");
     jpeg_scan_kernel<<<n, 256, 0, st>>>(d_files, d_seg, d_status, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len);
     RT_LAUNCH_CHECK(ctx);
+    // Long restart intervals (one per MCU row, or a file without restart markers = ONE interval): cut into sub-sequences and decoded
+    // through the self-synchronising parse (K-J2s); short intervals (a few MCUs each) are already parallel enough for K-J2.
+    static const bool no_sub = getenv("RETTO_B200_JPEG_NOSUB") != nullptr;   // A/B
+    unsigned long long total_ecs = 0;
+    for (int i = 0; i < n; ++i) total_ecs += infos[i].ecs_len;
+    const bool use_sub = !no_sub && total_seg > 0 && total_ecs / (unsigned long long)total_seg > JS_SUB_BYTES / 2;
+    if (use_sub) {
+        // host tables: slot ranges per file (upper bounds: the interval lengths are only known on the device), file of every interval,
+        // thread blocks of 128 slots of one file
+        std::vector<int> sub_base(n + 1, 0);
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long cap = infos[i].ecs_len / JS_SUB_BYTES + (unsigned long long)infos[i].n_seg + 1;
+            if ((unsigned long long)sub_base[i] + cap > 0x3fffffffULL) { ctx->set_error("jpeg decode: batch too large (sub-sequences)"); return RETTO_B200_ERR_CAPACITY; }
+            sub_base[i + 1] = sub_base[i] + (int)cap;
+        }
+        const size_t S = (size_t)sub_base[n];
+        size_t nsb = 0;
+        for (int i = 0; i < n; ++i) nsb += ((size_t)(sub_base[i + 1] - sub_base[i]) + 127) / 128;
+        const size_t tab_ints = (size_t)(n + 1) + (size_t)total_seg + nsb + (nsb + 1);
+        const size_t tab_b = (tab_ints * 4 + 15) & ~size_t(15);
+        RT_CUDA_OK(ctx, JB.h_sub.ensure(tab_b));
+        int* ht = JB.h_sub.as<int>();
+        int* h_sub_base = ht;
+        int* h_seg_file = h_sub_base + (n + 1);
+        int* h_sb_file = h_seg_file + total_seg;
+        int* h_sb_first = h_sb_file + nsb;
+        memcpy(h_sub_base, sub_base.data(), sizeof(int) * (size_t)(n + 1));
+        {
+            size_t g = 0, bq = 0;
+            for (int i = 0; i < n; ++i) {
+                for (int j = 0; j < infos[i].n_seg; ++j) h_seg_file[g++] = i;
+                for (int s0 = sub_base[i]; s0 < sub_base[i + 1]; s0 += 128) { h_sb_file[bq] = i; h_sb_first[bq] = s0; ++bq; }
+            }
+            h_sb_first[nsb] = (int)S;
+        }
+        const size_t off_isub = tab_b;
+        const size_t off_slots = (off_isub + (size_t)total_seg * 4 + 15) & ~size_t(15);
+        const size_t off_states = off_slots + S * 16, off_syncs = off_states + S * 16, off_starts = off_syncs + S * 16, off_preds = off_starts + S * 16;
+        const size_t off_counts = off_preds + S * 16, off_bitmaps = off_counts + S * JS_WORDS * 2;
+        RT_CUDA_OK(ctx, ctx->d_jpeg_sub.ensure(off_bitmaps + S * JS_WORDS * 4, ctx->stream));
+        char* db = ctx->d_jpeg_sub.as<char>();
+        RT_CUDA_OK(ctx, cudaMemcpyAsync(db, ht, tab_b, cudaMemcpyHostToDevice, st));
+        const int* d_sub_base = reinterpret_cast<const int*>(db);
+        const int* d_seg_file = d_sub_base + (n + 1);
+        const int* d_sb_file = d_seg_file + total_seg;
+        const int* d_sb_first = d_sb_file + nsb;
+        int* d_isub = reinterpret_cast<int*>(db + off_isub);
+        JsSlot* d_slots = reinterpret_cast<JsSlot*>(db + off_slots);
+        JsState* d_states = reinterpret_cast<JsState*>(db + off_states);
+        JsSync* d_syncs = reinterpret_cast<JsSync*>(db + off_syncs);
+        JsStart* d_starts = reinterpret_cast<JsStart*>(db + off_starts);
+        int4* d_preds = reinterpret_cast<int4*>(db + off_preds);
+        unsigned short* d_counts = reinterpret_cast<unsigned short*>(db + off_counts);
+        unsigned* d_bitmaps = reinterpret_cast<unsigned*>(db + off_bitmaps);
+        const int smem = (int)(sizeof(HuffDev) * 6);
+        if (!ctx->jpeg_sub_attr_set) {
+            RT_CUDA_OK(ctx, cudaFuncSetAttribute(jpeg_sync_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            RT_CUDA_OK(ctx, cudaFuncSetAttribute(jpeg_sync_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            RT_CUDA_OK(ctx, cudaFuncSetAttribute(jpeg_huff_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ctx->jpeg_sub_attr_set = true;
+        }
+        const unsigned char* d_clean = ctx->d_jpeg_clean.as<unsigned char>();
+        ctx->timer_stream = st;
+        RT_LAUNCH_BEGIN(ctx, "jpeg_sub_kernel");
+        jpeg_sub_kernel<<<n, 256, 0, st>>>(d_files, d_seg, d_clean_len, d_sub_base, d_isub, d_slots);
+        RT_LAUNCH_CHECK(ctx);
+        ctx->timer_stream = st;
+        RT_LAUNCH_BEGIN(ctx, "jpeg_sync_kernel<1>");
+        jpeg_sync_kernel<1><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs);
+        RT_LAUNCH_CHECK(ctx);
+        ctx->timer_stream = st;
+        RT_LAUNCH_BEGIN(ctx, "jpeg_sync_kernel<2>");
+        jpeg_sync_kernel<2><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs);
+        RT_LAUNCH_CHECK(ctx);
+        ctx->timer_stream = st;
+        RT_LAUNCH_BEGIN(ctx, "jpeg_resolve_kernel");
+        jpeg_resolve_kernel<<<(unsigned)((total_seg + 127) / 128), 128, 0, st>>>(d_files, d_seg_file, (int)total_seg, d_isub, d_slots, d_bitmaps, d_counts, d_syncs, d_starts);
+        RT_LAUNCH_CHECK(ctx);
+        ctx->timer_stream = st;
+        RT_LAUNCH_BEGIN(ctx, "jpeg_huff_sub_kernel");
+        jpeg_huff_sub_kernel<<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_starts, d_preds, ctx->d_jpeg_coef.as<short>());
+        RT_LAUNCH_CHECK(ctx);
+        ctx->timer_stream = st;
+        RT_LAUNCH_BEGIN(ctx, "jpeg_dcfix_kernel");
+        jpeg_dcfix_kernel<<<(unsigned)nsb, 128, 0, st>>>(d_files, d_sb_file, d_sb_first, d_slots, d_starts, d_preds, ctx->d_jpeg_coef.as<short>());
+        RT_LAUNCH_CHECK(ctx);
+        ctx->timer_stream = nullptr;
+        return RETTO_B200_OK;
+    }
     ctx->timer_stream = st;
     RT_LAUNCH_BEGIN(ctx, "jpeg_huff_kernel");
     if (!ctx->jpeg_huff_attr_set) {

@@ -1,0 +1,115 @@
+"""DESIGN.md = docs_src/DESIGN.md.in with the @@...@@ blocks filled from the committed evidence under profiles/ (r02_*):
+   python tools/fill_design.py            (run after the evidence files changed)"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = lambda n: os.path.join(ROOT, "profiles", n)
+
+
+def load(n):
+    with open(P(n)) as f:
+        lines = [l for l in f.read().splitlines() if l.strip().startswith("{")]
+    return [json.loads(l) for l in lines]
+
+
+b = load("r02_bench_final.json")[-1]
+cfg = load("r02_side_configs_2_3.json")
+mixed = load("r02_bench_mixed_n1.json")[-1] if os.path.exists(P("r02_bench_mixed_n1.json")) else None
+ref = load("r02_bench_reference.json")[-1]
+K = b["kernels"]
+S = b["summary"]
+peak = b["roofline"]["peak"]
+notes = {
+    "ctc_argmax": ("4·rows·C (26.5 KB/row)", "HBM; warp per row, 4×LDG.128 in flight per lane, head/tail peel for 4-B-aligned rows"),
+    "det_pre_identity": ("3·H·W + 12·H'·W' = 24.6 MB/page", "HBM; 16 px/thread, smem LUT, smem-staged fully coalesced plane stores"),
+    "build_batches": ("Σ (3·w·h + 12·48·img_w)", "latency: first use of the prefetched source words; 41–45 % occupancy at 64 registers; direct lines read the page"),
+    "bitmap_runs3": ("5·H·W (4 read + 1 bitmap) = 8.2 MB/page", "issue (≈ 80 %): strip row = 8 ballot words, funnel-shift dilation / run detection on warp-uniform registers, FMNMX3.NAN probe"),
+    "box_score": ("4·Σ polygon px (not in the 5·H·W unit)", "dependency chains: the reference's sequential f32 fold; 1 warp instruction per pixel + LDS.128 per 4; floor 0.155–0.165 ms"),
+    "crop_rows": ("Σ 6·w·h of the NON-direct crops", "bicubic / border crops only (6 % of the crops of a text page); the direct ones are never written"),
+    "box_geometry_kernel<2": ("—", "serial f64 (Clipper offset, one corner per lane; double-double trig), 96 registers"),
+    "box_geometry_kernel<0": ("—", "hull (serial monotone chains in shared memory) + calipers (f64, one edge per lane)"),
+    "ccl_runs": ("run table only (≈ 10³ runs/page)", "shared-memory union-find; barrier-bound"),
+    "jpeg_huff": ("entropy bytes (0.18 MB/page)", "serial chain per restart interval: 310 cycles per symbol for a lone lane; tiered by interval length"),
+    "jpeg_idct": ("2 B coefficient + 1 B sample per sample", "issue-bound (80 %); DC-only blocks short-cut"),
+    "jpeg_color": ("1.5 B samples + 3 B RGB per pixel", "issue-bound; 4:2:0: two rows per thread"),
+    "jpeg_scan": ("2 × entropy bytes", "ordered block-wide compaction, one block per file"),
+}
+rows = []
+for name, v in sorted(K.items(), key=lambda kv: -kv[1]["ms_per_step"]):
+    if v["ms_per_step"] < 0.02:
+        continue
+    note = next((n for k, n in notes.items() if name.startswith(k)), ("—", ""))
+    gbs = v.get("gbs")
+    tr = v.get("traffic_bytes_per_step") or v.get("traffic")
+    rows.append("| `%s` | %s | %.3f | %s | %s |" % (name, note[0], v["ms_per_step"], ("%.0f (%.2f)" % (gbs, gbs / peak)) if gbs else "—", note[1]))
+rest = sum(v["ms_per_step"] for v in K.values() if v["ms_per_step"] < 0.02)
+table = "| Kernel | Algorithmic bytes / unit | ms / 256 pages | GB/s (frac of measured peak) | Bound / note |\n|---|---|---|---|---|\n" + "\n".join(rows) + \
+        "\n| rest (kernels below 0.02 ms: sort / pack / scan / setup / `cls_post` / `zero`) | — | %.3f | — | launch-latency sized |" % rest
+
+
+def unit(u):
+    return "%.3f ms → %.0f GB/s, **%.2f** of the measured peak" % (u["ms_per_step"], u["gbs"], u["frac_of_hbm_peak"])
+
+
+db5, db9, cb = S["db_postprocess_unit_moved_bytes"], S["db_postprocess_unit_survey_bytes"], S["crop_batch_unit"]
+dec = S.get("decode_unit", {})
+c2 = cfg[0]
+e2e = b["e2e"]
+var = b.get("e2e_variants", {})
+wf = b.get("with_forward") or {}
+cpu = b.get("cpu_baseline") or {}
+bench_txt = (
+    "Round-2 numbers (1×B200, `profiles/r02_bench_final.json`, default flags = 20 timed steps):\n"
+    "* `value` **%.1f k pages/s** (%.2f ms per 256 pages; round 1: 52.5 k).\n"
+    "* `e2e` **%.1f k pages/s** (%.2f ms per step; %d MB of files up, %.1f MB of results down per step; round 1, from raw RGB: 10.2 k). Variants: %s.\n"
+    "* `with_forward`: %s.\n"
+    "* CPU oracle (`cpu_baseline`, `kind: \"port\"`, JPEG decode included): %.0f pages/s on %d host processes; `--impl reference`: %.0f pages/s (`profiles/r02_bench_reference.json`).\n"
+    "* Side benchmarks (`profiles/r02_side_configs_2_3.json`): configs[1] DB postprocess only, 1024 maps 960² (%d boxes): **%.2f ms** through the C ABI = %.0f k maps/s "
+    "(%.2f of peak on 5·H·W, %.2f on SURVEY's 9·H·W; %.2f ms through the Python wrapper; kernels: %s); configs[2] CTC only, 16 384 lines: `ctc_argmax_kernel` %.2f ms = %.2f TB/s.\n"
+    % (b["value"] / 1e3, b["ms_per_step"], e2e["value"] / 1e3, e2e["ms_per_step"], round(e2e["h2d_bytes_per_step"] / 1e6), e2e["d2h_bytes_per_step"] / 1e6,
+       ", ".join("%s %.1f k" % (k, v["value"] / 1e3) for k, v in var.items()) if isinstance(var, dict) else "—",
+       ("%.0f pages/s, the stand-in forwards are %.0f %% of the step, %d tensors checked zero-copy" % (wf.get("value", 0), 100 * wf.get("forward_share_of_step", 0), wf.get("tensors_checked_zero_copy", 0))) if wf else "—",
+       cpu.get("value", 0), cpu.get("cores", 0), ref["value"],
+       c2.get("boxes", 0), c2["ms"], c2["maps_per_s"] / 1e3, c2["frac_of_hbm_peak_5HW"], c2["frac_of_hbm_peak_9HW"], c2["ms_through_python_wrapper"],
+       ", ".join("%s %.2f" % (k.replace("_kernel", "").replace("box_geometry", "geom"), v) for k, v in sorted(c2["kernels_ms"].items(), key=lambda kv: -kv[1])[:6]),
+       cfg[1]["kernels_ms"]["ctc_argmax_kernel<WARPS>"], cfg[1]["algorithmic_bytes"] / cfg[1]["kernels_ms"]["ctc_argmax_kernel<WARPS>"] / 1e9))
+if mixed:
+    bench_txt += "* `bench.py --workload mixed` on one GPU (2048 mixed-size pages per step, 64 unique, `profiles/r02_bench_mixed_n1.json`): value %.1f k pages/s, e2e %.1f k pages/s.\n" % (mixed["value"] / 1e3, mixed["e2e"]["value"] / 1e3)
+scal = []
+for n in (2, 4, 8):
+    fn = "r02_bench_n%d.json" % n
+    if os.path.exists(P(fn)):
+        d = load(fn)[-1]
+        raw = (d.get("e2e_variants") or {}).get("raw_rgb", {}).get("value")
+        scal.append("| %d | %.1f k | %.1f k | %s |" % (n, d["value"] / 1e3, d["e2e"]["value"] / 1e3, ("%.1f k" % (raw / 1e3)) if raw else "—"))
+h2d = []
+for n in (2, 4, 8):
+    fn = "r02_h2d_ceiling_n%d.json" % n
+    if os.path.exists(P(fn)):
+        d = load(fn)[-1]
+        h2d.append("N = %d: %.0f GB/s" % (n, d["h2d"]["page_sized_copies"]["aggregate_gbs"]))
+scaling = ("Measured on one 8×B200 box, max over ranks (`profiles/r02_bench_n{2,4,8}.json`, taken BEFORE the last Huffman / IDCT / colour / score changes — "
+           "N = 1 was 52.8 k value / 19.4 k e2e on that tree):\n\n| N | value pages/s | e2e (JPEG) pages/s | e2e from raw RGB |\n|---|---|---|---|\n" + "\n".join(scal) +
+           "\n\nDevice-resident: 7.7× at N = 8. **e2e from JPEG files: 7.7× at N = 8** (round 1, from raw RGB: 3.5×) — with 0.18 MB per page on the wire the host's "
+           "H2D bandwidth is no longer the limit. From raw RGB the path still tracks the bare H2D ceiling of the box (" + "; ".join(h2d) +
+           " aggregate, `tools/measure_h2d.py`, `profiles/r02_h2d_ceiling_n*.json`: e.g. 38.3 k pages/s of 4.9-MB pages at N = 8 against 35.2 k measured). "
+           "The box is a single-NUMA VM (`profiles/r02_topo_8gpu_box.txt`).")
+out = open(os.path.join(ROOT, "docs_src", "DESIGN.md.in")).read()
+rep = {
+    "@@KERNEL_TABLE@@": table,
+    "@@DB_UNIT@@": "on the 5·H·W bytes the path moves: " + unit(db5) + " (on SURVEY's 9·H·W, which counts a label plane the run-table CCL never writes: %.2f)" % db9["frac_of_hbm_peak"],
+    "@@CB_UNIT@@": unit(cb),
+    "@@DEC_UNIT@@": "%.2f ms per 256 pages (round-2 start: 6.1 ms)" % dec.get("ms_per_step", 0),
+    "@@CFG2_MS@@": "%.2f" % c2["ms"],
+    "@@E2E@@": "%.1f k" % (e2e["value"] / 1e3),
+    "@@BENCH_NUMBERS@@": bench_txt,
+    "@@SCALING@@": scaling,
+    "@@DB_FRAC@@": "%.2f" % db5["frac_of_hbm_peak"],
+    "@@DB_REST@@": "%.2f" % (db5["ms_per_step"] - next(v["ms_per_step"] for k, v in K.items() if k.startswith("bitmap_runs3"))),
+    "@@CB_FRAC@@": "%.2f" % cb["frac_of_hbm_peak"],
+    "@@SCALE_E2E@@": "7.7× at N = 8 from JPEG files (0.97 per GPU)",
+}
+for k, v in rep.items():
+    out = out.replace(k, v)
+assert "@@" not in out, [l for l in out.splitlines() if "@@" in l]
+open(os.path.join(ROOT, "DESIGN.md"), "w").write("<!-- generated by tools/fill_design.py from docs_src/DESIGN.md.in + profiles/r02_*.json -->\n" + out)
+print("DESIGN.md written")

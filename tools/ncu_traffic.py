@@ -37,6 +37,9 @@ for r in rows[2:]:
         "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "inst_executed": val(r, "smsp__inst_executed.sum"),
     }
+import os
 commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+if not commit and os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".commit_id")):   # the GPU box has no .git
+    commit = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".commit_id")).read().strip()
 json.dump({"source": note, "commit": commit, "kernels": kernels}, open(out, "w"), indent=1)
 print(out, len(kernels), "kernels")
