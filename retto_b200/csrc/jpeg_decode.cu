@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
 #define JS_SUB_BYTES 1024
 #define JS_SUB_BITS (JS_SUB_BYTES * 8)
 #define JS_WORDS (JS_SUB_BITS / 32)
-#define JS_MAX_OVERLAP 3        // regions a parse may cross while looking for a common MCU start before the interval falls back
+#define JS_MAX_OVERLAP 4096     // regions a parse may cross while looking for a common MCU start before the interval falls back to one serial chain
 struct JsSlot { int j, k, nsub, pad; };                 // interval (index inside the file), sub-sequence, sub-sequences of the interval
 struct JsState { unsigned p; int b, kk, marked; };      // after pass 1: bit position (relative to the interval), block in MCU, zig-zag index, MCU starts recorded
 struct JsSync { int t; unsigned X; int C, pad; };       // written by slot s: first later slot t of the interval it met (-1: none, -2: gave up), at bit X; C = MCU starts of s's parse before X
@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(256) jpeg_sub_kernel(const JpegDev* __restrict
     const JpegDev& f = files[fi];
     const unsigned clen = clean_len[fi];
     const int first = sub_base[fi], cap = sub_base[fi + 1] - first;
+    if (cap == 0) return;   // a file K-J2 decodes
     __shared__ int s_scan[256];
     __shared__ int s_run;
     if (threadIdx.x == 0) s_run = 0;
@@ -735,12 +736,15 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
 }
 
 // One thread per restart interval with more than one slot: the chain of common MCU starts -> true start of every slot.
-__global__ void jpeg_resolve_kernel(const JpegDev* __restrict__ files, const int* __restrict__ seg_file, int total_seg, const int* __restrict__ isub,
+__global__ void jpeg_resolve_kernel(const JpegDev* __restrict__ files, const int* __restrict__ seg_file, int total_seg, const int* __restrict__ sub_base,
+                                    const int* __restrict__ isub,
                                     const JsSlot* __restrict__ slots, const unsigned* __restrict__ bitmaps, const unsigned short* __restrict__ counts,
                                     const JsSync* __restrict__ syncs, JsStart* __restrict__ starts) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;   // global interval index
     if (g >= total_seg) return;
-    const JpegDev& f = files[seg_file[g]];
+    const int fi = seg_file[g];
+    if (sub_base[fi + 1] == sub_base[fi]) return;   // a file K-J2 decodes
+    const JpegDev& f = files[fi];
     const int j = g - f.seg_base;
     const int first = isub[g];
     const int nsub = slots[first].nsub;
@@ -879,13 +883,17 @@ __global__ void __launch_bounds__(128) jpeg_huff_sub_kernel(const JpegDev* __res
 
 // DC terms are coded as differences: a slot that did not start its interval decoded its DC terms from predictors 0, so the
 // predictors at the end of all earlier slots of the interval are added to the DC term of every block of its MCU range.
+#define JS_FIX_LANES 8   // threads that share the MCU range of one slot
 __global__ void __launch_bounds__(128) jpeg_dcfix_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file, const int* __restrict__ block_first,
                                                          const JsSlot* __restrict__ slots, const JsStart* __restrict__ starts, const int4* __restrict__ preds,
                                                          short* __restrict__ coef) {
-    const int fi = block_file[blockIdx.x];
+    // grid: JS_FIX_LANES blocks per block of 128 slots; thread t of block q works for slot (q % JS_FIX_LANES) * 16 + t / 8 of that group
+    const int sb = blockIdx.x / JS_FIX_LANES, part = blockIdx.x % JS_FIX_LANES;
+    const int fi = block_file[sb];
     const JpegDev& f = files[fi];
-    const int slot = block_first[blockIdx.x] + threadIdx.x;
-    if (slot >= block_first[blockIdx.x + 1]) return;
+    const int slot = block_first[sb] + part * (128 / JS_FIX_LANES) + (threadIdx.x / JS_FIX_LANES);
+    const int lane8 = threadIdx.x % JS_FIX_LANES;
+    if (slot >= block_first[sb + 1]) return;
     const JsSlot sl = slots[slot];
     if (sl.j < 0 || sl.k == 0) return;
     const JsStart st = starts[slot];
@@ -894,10 +902,9 @@ __global__ void __launch_bounds__(128) jpeg_dcfix_kernel(const JpegDev* __restri
     for (int u = 1; u <= sl.k; ++u) { const int4 q = preds[slot - u]; c0 += q.x; c1 += q.y; c2 += q.z; }
     if ((c0 | c1 | c2) == 0) return;
     const int nb0 = f.c[0].h * f.c[0].v, h0 = f.c[0].h, v0 = f.c[0].v;
-    long long m = (f.ri > 0 ? (long long)sl.j * f.ri : 0) + st.mcu;
-    const long long m1 = m + st.n_mcu;
-    int my = (int)(m / f.mcux), mx = (int)(m - (long long)my * f.mcux);
-    for (; m < m1; ++m) {
+    const long long mb = (f.ri > 0 ? (long long)sl.j * f.ri : 0) + st.mcu;
+    for (long long m = mb + lane8; m < mb + st.n_mcu; m += JS_FIX_LANES) {
+        const int my = (int)(m / f.mcux), mx = (int)(m - (long long)my * f.mcux);
         if (c0) {
             for (int bi = 0; bi < nb0; ++bi) {
                 const int dy = h0 == 2 ? (bi >> 1) : bi, dx = h0 == 2 ? (bi & 1) : 0;
@@ -909,7 +916,6 @@ __global__ void __launch_bounds__(128) jpeg_dcfix_kernel(const JpegDev* __restri
             if (c1) { short* bp = coef + ((size_t)f.c[1].coef_base + (size_t)my * f.c[1].wb + mx) * 64; bp[0] = (short)(bp[0] + c1); }
             if (c2) { short* bp = coef + ((size_t)f.c[2].coef_base + (size_t)my * f.c[2].wb + mx) * 64; bp[0] = (short)(bp[0] + c2); }
         }
-        if (++mx == f.mcux) { mx = 0; ++my; }
     }
 }
 
@@ -1259,15 +1265,28 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     const size_t desc_bytes = (sizeof(JpegDev) * (size_t)n + 15) & ~size_t(15);
     long long total_seg = 0;
     size_t n_tblocks = 0;
-    for (int i = 0; i < n; ++i) total_seg += infos[i].n_seg;
+    // Per file: long restart intervals (above all a file without restart markers = ONE interval) are cut into sub-sequences and decoded
+    // through the self-synchronising parse (K-J2s); files with shorter intervals are parallel enough for K-J2.
+    // Measured (256 pages 1280x1280, q90, 4:2:0): no restart markers: K-J2 42.6 ms -> K-J2s 8.0 ms (parse 1.2 + look-ahead 2.0 + decode 2.7 +
+    // DC fix-up); one interval per MCU row (2.2 KB on average): tiered K-J2 2.84 ms, K-J2s 3.65 ms.
+    static const bool no_sub = getenv("RETTO_B200_JPEG_NOSUB") != nullptr;       // A/B: never
+    static const bool force_sub = getenv("RETTO_B200_JPEG_SUB") != nullptr;      // A/B / tests: every file
+    std::vector<unsigned char> file_sub(n, 0);
+    long long total_seg_all = 0;
+    int n_sub_files = 0;
+    for (int i = 0; i < n; ++i) {
+        total_seg_all += infos[i].n_seg;
+        file_sub[i] = !no_sub && infos[i].n_seg > 0 && (force_sub || infos[i].ecs_len / (unsigned long long)infos[i].n_seg > 8 * JS_SUB_BYTES);
+        if (file_sub[i]) ++n_sub_files; else total_seg += infos[i].n_seg;
+    }
     // jpeg_huff_kernel layout: tiered (16 warps share 112 intervals, the 8 longest alone in their warp) while every block of the batch
     // is resident at once (4 blocks of 512 threads per SM); dense (128 intervals per 128 threads) for batches with more intervals
     // than that — short restart intervals, where throughput, not the longest chain, is the bound.  RETTO_B200_JPEG_DENSE=1: A/B.
     static const bool force_dense = getenv("RETTO_B200_JPEG_DENSE") != nullptr;
     const bool tiered = !force_dense && total_seg <= 148LL * 4 * JH_T_IPB;
     const int jh_ipb = tiered ? JH_T_IPB : JH_THREADS;   // restart intervals per block
-    for (int i = 0; i < n; ++i) n_tblocks += ((size_t)infos[i].n_seg + jh_ipb - 1) / jh_ipb;
-    if (total_seg > 0x3fffffffLL) { ctx->set_error("jpeg decode: too many restart intervals"); return RETTO_B200_ERR_CAPACITY; }
+    for (int i = 0; i < n; ++i) if (!file_sub[i]) n_tblocks += ((size_t)infos[i].n_seg + jh_ipb - 1) / jh_ipb;
+    if (total_seg_all > 0x3fffffffLL) { ctx->set_error("jpeg decode: too many restart intervals"); return RETTO_B200_ERR_CAPACITY; }
     const size_t tb_bytes = (sizeof(int) * 2 * n_tblocks + 15) & ~size_t(15);
     const size_t head_bytes = desc_bytes + tb_bytes;
     const size_t tab_bytes = sizeof(JpegTables) * (size_t)n;
@@ -1307,7 +1326,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         D.n_blocks = (unsigned)blocks - D.block_base;
         JB.X[i] = J.X; JB.Y[i] = J.Y; JB.n_blocks[i] = D.n_blocks;
         JB.is420[i] = (J.nc == 3 && J.h[0] == 2 && J.v[0] == 2 && J.h[1] == 1 && J.v[1] == 1 && J.h[2] == 1 && J.v[2] == 1) ? 1 : 0;
-        for (int j0 = 0; j0 < J.n_seg; j0 += jh_ipb) { h_tb_file[tb] = i; h_tb_first[tb] = j0; ++tb; }
+        if (!file_sub[i]) for (int j0 = 0; j0 < J.n_seg; j0 += jh_ipb) { h_tb_file[tb] = i; h_tb_first[tb] = j0; ++tb; }
         seg_base += J.n_seg;
         for (int k = 0; k < 4; ++k) {
             memcpy(h_tab[i].qt[k], J.qt[k], sizeof(J.qt[k]));
@@ -1338,18 +1357,14 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     RT_LAUNCH_BEGIN(ctx, "jpeg_scan_kernel");
     jpeg_scan_kernel<<<n, 256, 0, st>>>(d_files, d_seg, d_status, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len);
     RT_LAUNCH_CHECK(ctx);
-    // Long restart intervals (one per MCU row, or a file without restart markers = ONE interval): cut into sub-sequences and decoded
-    // through the self-synchronising parse (K-J2s); short intervals (a few MCUs each) are already parallel enough for K-J2.
-    static const bool no_sub = getenv("RETTO_B200_JPEG_NOSUB") != nullptr;   // A/B
-    unsigned long long total_ecs = 0;
-    for (int i = 0; i < n; ++i) total_ecs += infos[i].ecs_len;
-    const bool use_sub = !no_sub && total_seg > 0 && total_ecs / (unsigned long long)total_seg > JS_SUB_BYTES / 2;
+    const bool use_sub = n_sub_files > 0;
+    total_seg = total_seg_all;
     if (use_sub) {
         // host tables: slot ranges per file (upper bounds: the interval lengths are only known on the device), file of every interval,
         // thread blocks of 128 slots of one file
         std::vector<int> sub_base(n + 1, 0);
         for (int i = 0; i < n; ++i) {
-            const unsigned long long cap = infos[i].ecs_len / JS_SUB_BYTES + (unsigned long long)infos[i].n_seg + 1;
+            const unsigned long long cap = file_sub[i] ? infos[i].ecs_len / JS_SUB_BYTES + (unsigned long long)infos[i].n_seg + 1 : 0ull;
             if ((unsigned long long)sub_base[i] + cap > 0x3fffffffULL) { ctx->set_error("jpeg decode: batch too large (sub-sequences)"); return RETTO_B200_ERR_CAPACITY; }
             sub_base[i + 1] = sub_base[i] + (int)cap;
         }
@@ -1414,7 +1429,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_resolve_kernel");
-        jpeg_resolve_kernel<<<(unsigned)((total_seg + 127) / 128), 128, 0, st>>>(d_files, d_seg_file, (int)total_seg, d_isub, d_slots, d_bitmaps, d_counts, d_syncs, d_starts);
+        jpeg_resolve_kernel<<<(unsigned)((total_seg + 127) / 128), 128, 0, st>>>(d_files, d_seg_file, (int)total_seg, d_sub_base, d_isub, d_slots, d_bitmaps, d_counts, d_syncs, d_starts);
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_huff_sub_kernel");
@@ -1422,11 +1437,10 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_dcfix_kernel");
-        jpeg_dcfix_kernel<<<(unsigned)nsb, 128, 0, st>>>(d_files, d_sb_file, d_sb_first, d_slots, d_starts, d_preds, ctx->d_jpeg_coef.as<short>());
+        jpeg_dcfix_kernel<<<(unsigned)nsb * JS_FIX_LANES, 128, 0, st>>>(d_files, d_sb_file, d_sb_first, d_slots, d_starts, d_preds, ctx->d_jpeg_coef.as<short>());
         RT_LAUNCH_CHECK(ctx);
-        ctx->timer_stream = nullptr;
-        return RETTO_B200_OK;
     }
+    if (n_tblocks == 0) { ctx->timer_stream = nullptr; return RETTO_B200_OK; }
     ctx->timer_stream = st;
     RT_LAUNCH_BEGIN(ctx, "jpeg_huff_kernel");
     if (!ctx->jpeg_huff_attr_set) {

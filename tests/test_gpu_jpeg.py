@@ -217,3 +217,50 @@ def test_contexts_on_two_devices_from_one_thread(synth_dict):
         c0.close()
         c1.close()
         torch.cuda.set_device(0)
+
+
+_ENTROPY_PATHS_SCRIPT = r'''
+import io, sys
+import numpy as np
+sys.path.insert(0, ".")
+import cv2
+from PIL import Image, ImageFile
+ImageFile.MAXBLOCK = 1 << 24          # optimised tables on noise images need a larger encoder buffer
+from retto_b200.api import Context
+from tools.synth import gen_page
+def enc(a, **kw):
+    b = io.BytesIO(); Image.fromarray(a).save(b, "JPEG", **kw); return b.getvalue()
+rng = np.random.default_rng(3)
+blank = np.full((640, 800, 3), 255, np.uint8); blank[300:340, 100:700] = 0          # long runs of DC-only MCUs around one bar
+imgs = [gen_page(8, 1280, 1280)[0], gen_page(9, 700, 2000, n_lines=(3, 6))[0], blank,
+        cv2.GaussianBlur(rng.integers(0, 256, (512, 768, 3), dtype=np.uint8), (0, 0), 2), rng.integers(0, 256, (300, 200, 3), dtype=np.uint8),
+        rng.integers(0, 256, (16, 16, 3), dtype=np.uint8)]
+files = []
+for img in imgs:
+    for sub in (0, 1, 2):
+        for kw in (dict(), dict(optimize=True), dict(restart_marker_rows=1), dict(restart_marker_rows=7), dict(restart_marker_blocks=5)):
+            files.append(enc(img, quality=88, subsampling=sub, **kw))
+files.append(enc(np.asarray(Image.fromarray(imgs[0]).convert("L")), quality=92))
+ctx = Context(0)
+outs, status = ctx.decode_images(files)
+assert all(s == 0 for s in status), status
+for k, (f, t) in enumerate(zip(files, outs)):
+    ref = np.asarray(Image.open(io.BytesIO(f)).convert("RGB"))
+    assert np.array_equal(t.cpu().numpy(), ref), k
+print("OK", len(files))
+'''
+
+
+@pytest.mark.parametrize("env", [{"RETTO_B200_JPEG_SUB": "1"}, {"RETTO_B200_JPEG_NOSUB": "1"}, {"RETTO_B200_JPEG_NOSUB": "1", "RETTO_B200_JPEG_DENSE": "1"}, {}],
+                         ids=["sub-sequences everywhere", "intervals only (tiered)", "intervals only (dense)", "default: per file"])
+def test_entropy_paths_agree_with_libjpeg(env):
+    """the three Huffman layouts — K-J2 tiered / dense (one thread per restart interval) and K-J2s (self-synchronising sub-sequences of
+    long intervals) — are chosen per file from its mean interval length; the switches are read once per process, so each forced
+    configuration decodes the same 91 files (with / without restart markers, three samplings, optimised tables, blank stretches,
+    2000-px-wide rows, greyscale) in its own interpreter and compares with Pillow"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", _ENTROPY_PATHS_SCRIPT], cwd=root, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK 91" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
