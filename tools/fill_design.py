@@ -101,6 +101,7 @@ rep = {
     "@@DEC_UNIT@@": "%.2f ms per 256 pages (round-2 start: 6.1 ms)" % dec.get("ms_per_step", 0),
     "@@CFG2_MS@@": "%.2f" % c2["ms"],
     "@@E2E@@": "%.1f k" % (e2e["value"] / 1e3),
+    "@@NORST@@": "%.1f k" % (var["jpeg_no_restart"]["value"] / 1e3),
     "@@BENCH_NUMBERS@@": bench_txt,
     "@@SCALING@@": scaling,
     "@@DB_FRAC@@": "%.2f" % db5["frac_of_hbm_peak"],
