@@ -369,7 +369,11 @@ def algorithmic_bytes(name, info):
     if name.startswith("ctc_argmax"):
         return 4.0 * info["rec_rows"] * C_CLASSES
     if name.startswith("det_pre_identity"):
-        return 15.0 * HW                      # 3 B in + 12 B out per pixel
+        return 15.0 * info.get("ident_px", HW)   # 3 B in + 12 B out per pixel of the pages whose det size equals their own
+    if name.startswith("det_pre_resize"):
+        return 3.0 * info.get("resize_src_px", 0) + 12.0 * info.get("resize_dst_px", 0) or None   # resized-page read + det tensor written
+    if name.startswith("thumbnail"):
+        return 3.0 * info.get("thumb_src_px", 0) + 3.0 * info.get("thumb_dst_px", 0) or None      # resize_both: page read + resized page written
     if name.startswith("bitmap_runs2") or name.startswith("bitmap_runs3"):
         return 5.0 * HW                       # prob read 4 + bitmap write 1 (run-table CCL: the label plane is not materialised)
     if name.startswith("bitmap_runs"):
@@ -663,6 +667,20 @@ def main():
     st = stats_acc / K
     info = {"pages": NP, "det_px": st[2], "crop_px": st[3], "cls_floats": st[4], "rec_floats": st[5], "rec_rows": st[6],
             "jpeg_px": float(sum(h * w for h, w in hw))}
+    # per-class pixel counts of the resize kernels (from the same host-side plans the library uses)
+    from retto_b200.api import resize_both_plan, resize_either_plan
+    acc = {"ident_px": 0, "resize_src_px": 0, "resize_dst_px": 0, "thumb_src_px": 0, "thumb_dst_px": 0}
+    for h, w in hw:
+        h2, w2 = h, w
+        for (hh, ww) in resize_both_plan(h, w):
+            acc["thumb_src_px"] += h2 * w2; acc["thumb_dst_px"] += hh * ww
+            h2, w2 = hh, ww
+        dh, dw = resize_either_plan(h2, w2)
+        if (dh, dw) == (h2, w2):
+            acc["ident_px"] += dh * dw
+        else:
+            acc["resize_src_px"] += h2 * w2; acc["resize_dst_px"] += dh * dw
+    info.update({k: float(v) for k, v in acc.items()})
     crop_px = info["crop_px"]
     kernels = {}
 

@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
 #define JS_SUB_BYTES 1024
 #define JS_SUB_BITS (JS_SUB_BYTES * 8)
 #define JS_WORDS (JS_SUB_BITS / 32)
+#define JS_MIN_MEAN_INTERVAL 4096   // a file goes through K-J2s when its mean restart interval is longer than this many bytes
 #define JS_MAX_OVERLAP 4096     // regions a parse may cross while looking for a common MCU start before the interval falls back to one serial chain
 struct JsSlot { int j, k, nsub, pad; };                 // interval (index inside the file), sub-sequence, sub-sequences of the interval
 struct JsState { unsigned p; int b, kk, marked; };      // after pass 1: bit position (relative to the interval), block in MCU, zig-zag index, MCU starts recorded
@@ -1169,12 +1170,26 @@ __global__ void __launch_bounds__(JC_THREADS) jpeg_color_kernel(const JpegDev* _
 // grid (x chunks, Y / 2 + 1 row pairs, files); row pair p = output rows 2p - 1 and 2p.  The host picks it only for chroma planes wider
 // than two samples (jdsample.c falls back to replication below that; the generic kernel has that branch).
 __global__ void __launch_bounds__(JC_THREADS) jpeg_color420_kernel(const JpegDev* __restrict__ files, const unsigned char* __restrict__ planes,
-                                                                   uint8_t* const* __restrict__ outs) {
+                                                                   uint8_t* const* __restrict__ outs, const unsigned* __restrict__ unit_prefix, int n_files) {
     __shared__ unsigned s_rgb[2][JC_THREADS * 6 + 1];
-    const JpegDev& f = files[blockIdx.z];
+    __shared__ int s_fi;
+    int fi, p, xb;
+    const int chunk_px = (int)blockDim.x * JC_PX;
+    if (unit_prefix) {   // pages of different sizes: flat grid over (file, row pair, chunk), one binary search per thread block
+        if (threadIdx.x == 0) {
+            int lo = 0, hi = n_files;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (unit_prefix[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+            s_fi = lo;
+        }
+        __syncthreads();
+        fi = s_fi;
+        const int xchunks = (files[fi].X + chunk_px - 1) / chunk_px;
+        const int u = (int)(blockIdx.x - unit_prefix[fi]);
+        p = u / xchunks; xb = (u - p * xchunks) * chunk_px;
+    } else { fi = blockIdx.z; p = blockIdx.y; xb = blockIdx.x * chunk_px; }
+    const JpegDev& f = files[fi];
     const int X = f.X, Y = f.Y;
-    const int p = blockIdx.y, ya = 2 * p - 1, yb = 2 * p;
-    const int xb = blockIdx.x * (int)blockDim.x * JC_PX;
+    const int ya = 2 * p - 1, yb = 2 * p;
     if (xb >= X || ya >= Y) return;
     const int x0 = xb + threadIdx.x * JC_PX;
     const bool has_a = ya >= 0, has_b = yb < Y;
@@ -1236,7 +1251,7 @@ __global__ void __launch_bounds__(JC_THREADS) jpeg_color420_kernel(const JpegDev
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
         if (row == 0 ? !has_a : !has_b) continue;
-        unsigned char* gp = outs[blockIdx.z] + ((size_t)(row == 0 ? ya : yb) * X + xb) * 3;
+        unsigned char* gp = outs[fi] + ((size_t)(row == 0 ? ya : yb) * X + xb) * 3;
         const int head = min((int)((4u - ((unsigned)(uintptr_t)gp & 3u)) & 3u), nbytes);
         const unsigned char* sbp = reinterpret_cast<const unsigned char*>(s_rgb[row]);
         if ((int)threadIdx.x < head) gp[threadIdx.x] = sbp[threadIdx.x];
@@ -1276,7 +1291,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     int n_sub_files = 0;
     for (int i = 0; i < n; ++i) {
         total_seg_all += infos[i].n_seg;
-        file_sub[i] = !no_sub && infos[i].n_seg > 0 && (force_sub || infos[i].ecs_len / (unsigned long long)infos[i].n_seg > 8 * JS_SUB_BYTES);
+        file_sub[i] = !no_sub && infos[i].n_seg > 0 && (force_sub || infos[i].ecs_len / (unsigned long long)infos[i].n_seg > JS_MIN_MEAN_INTERVAL);
         if (file_sub[i]) ++n_sub_files; else total_seg += infos[i].n_seg;
     }
     // jpeg_huff_kernel layout: tiered (16 warps share 112 intervals, the 8 longest alone in their warp) while every block of the batch
@@ -1472,12 +1487,16 @@ retto_b200_status rt_jpeg_pixels_enqueue(retto_b200_ctx* owner, retto_b200_ctx* 
     memcpy(sp, d_out, sizeof(uint8_t*) * (size_t)n);
     unsigned* h_ip = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(sp) + o_bytes);
     unsigned* h_cp = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(sp) + o_bytes + p_bytes);
+    bool all420 = true, wide420 = true;   // 4:2:0 throughout / chroma planes wider than two samples (jpeg_color420_kernel's domain)
+    for (int i = first; i < first + n; ++i) { all420 &= JB.is420[i] != 0; wide420 &= JB.X[i] > 4; }
+    static const bool no_c420 = getenv("RETTO_B200_JPEG_NO_C420") != nullptr;   // A/B: the one-row kernels
+    const bool c420 = all420 && wide420 && !no_c420;
     unsigned long long ig = 0, cu = 0;
     for (int k = 0; k < n; ++k) {
         const int i = first + k;
         h_ip[k] = (unsigned)ig; h_cp[k] = (unsigned)cu;
         ig += (JB.n_blocks[i] + 31) / 32;
-        cu += (unsigned long long)JB.Y[i] * ((JB.X[i] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX));
+        cu += (unsigned long long)(c420 ? JB.Y[i] / 2 + 1 : JB.Y[i]) * ((JB.X[i] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX));   // flat-grid units: row pairs / rows
     }
     h_ip[n] = (unsigned)ig; h_cp[n] = (unsigned)cu;
     if (ig > 0x7fffffffULL || cu > 0x7fffffffULL) { lane->stage_slots[slot].busy = false; lane->set_error("jpeg decode: unit too large"); return RETTO_B200_ERR_CAPACITY; }
@@ -1496,13 +1515,12 @@ retto_b200_status rt_jpeg_pixels_enqueue(retto_b200_ctx* owner, retto_b200_ctx* 
     if (uniform && same_blocks) jpeg_idct_kernel<<<dim3((JB.n_blocks[first] + 31) / 32, (unsigned)n), 256, 0, st>>>(d_files, d_tab, nullptr, n, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
     else jpeg_idct_kernel<<<(unsigned)ig, 256, 0, st>>>(d_files, d_tab, d_ip, n, owner->d_jpeg_coef.as<short>(), owner->d_jpeg_planes.as<unsigned char>());
     RT_LAUNCH_CHECK(lane);
-    bool all420 = true;
-    for (int i = first; i < first + n; ++i) all420 &= JB.is420[i] != 0;
     RT_LAUNCH_BEGIN(lane, "jpeg_color_kernel");
-    static const bool no_c420 = getenv("RETTO_B200_JPEG_NO_C420") != nullptr;   // A/B: the one-row kernel with the sampling folded in
-    if (uniform && same_blocks && all420 && JB.X[first] > 4 && !no_c420)
+    if (uniform && same_blocks && c420)
         jpeg_color420_kernel<<<dim3((unsigned)((JB.X[first] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)(JB.Y[first] / 2 + 1), (unsigned)n), jc_threads, 0, st>>>(
-            d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs);
+            d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, nullptr, n);
+    else if (c420)
+        jpeg_color420_kernel<<<(unsigned)cu, jc_threads, 0, st>>>(d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, d_cp, n);
     else if (uniform && same_blocks && all420)
         jpeg_color_kernel<1><<<dim3((unsigned)((JB.X[first] + jc_threads * JC_PX - 1) / (jc_threads * JC_PX)), (unsigned)JB.Y[first], (unsigned)n), jc_threads, 0, st>>>(
             d_files, owner->d_jpeg_planes.as<unsigned char>(), d_outs, nullptr, n);

@@ -235,18 +235,21 @@ blank = np.full((640, 800, 3), 255, np.uint8); blank[300:340, 100:700] = 0      
 imgs = [gen_page(8, 1280, 1280)[0], gen_page(9, 700, 2000, n_lines=(3, 6))[0], blank,
         cv2.GaussianBlur(rng.integers(0, 256, (512, 768, 3), dtype=np.uint8), (0, 0), 2), rng.integers(0, 256, (300, 200, 3), dtype=np.uint8),
         rng.integers(0, 256, (16, 16, 3), dtype=np.uint8)]
-files = []
+files, f420 = [], []
 for img in imgs:
     for sub in (0, 1, 2):
         for kw in (dict(), dict(optimize=True), dict(restart_marker_rows=1), dict(restart_marker_rows=7), dict(restart_marker_blocks=5)):
             files.append(enc(img, quality=88, subsampling=sub, **kw))
+            if sub == 2:
+                f420.append(files[-1])
 files.append(enc(np.asarray(Image.fromarray(imgs[0]).convert("L")), quality=92))
 ctx = Context(0)
-outs, status = ctx.decode_images(files)
-assert all(s == 0 for s in status), status
-for k, (f, t) in enumerate(zip(files, outs)):
-    ref = np.asarray(Image.open(io.BytesIO(f)).convert("RGB"))
-    assert np.array_equal(t.cpu().numpy(), ref), k
+for batch in (files, f420):      # mixed samplings (generic colour kernel) / 4:2:0 pages of different sizes (flat-grid two-row kernel)
+    outs, status = ctx.decode_images(batch)
+    assert all(s == 0 for s in status), status
+    for k, (f, t) in enumerate(zip(batch, outs)):
+        ref = np.asarray(Image.open(io.BytesIO(f)).convert("RGB"))
+        assert np.array_equal(t.cpu().numpy(), ref), k
 print("OK", len(files))
 '''
 
