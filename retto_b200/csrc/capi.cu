@@ -67,6 +67,7 @@ extern "C" void retto_b200_destroy(retto_b200_ctx* c) {
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_jpeg_zero) cudaEventDestroy(c->ev_jpeg_zero);
     for (auto& sl : c->stage_slots) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     delete c;  // DevBuf / HostBuf members free their memory
     cudaStreamDestroy(s);

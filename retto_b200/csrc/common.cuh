@@ -271,6 +271,7 @@ struct retto_b200_ctx {
     } jpeg;
     DevBuf d_jpeg_sub;                           // K-J2s: slot tables, parse states, MCU-start bitmaps of the sub-sequence decode
     bool jpeg_sub_attr_set = false;
+    cudaEvent_t ev_jpeg_zero = nullptr;          // behind the zero-fill of the coefficient planes (issued on `stream` while the copy stream uploads)
     bool jpeg_huff_attr_set = false;             // dynamic shared memory opt-in of jpeg_huff_kernel done on this context's device
     int* jpeg_status_dev = nullptr;              // per-file device status of the last decode (inside d_jpeg_seg)
     HostBuf h_jpeg_status;

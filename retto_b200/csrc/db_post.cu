@@ -1409,18 +1409,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_scan, int* total) {
     __syncthreads();
     return incl - v;
 }
-// TIER 0: the only launch (1024 threads, RUN_CAP runs, RUN_MAX_H rows: 90 KB of shared memory, two blocks per SM).
-// Batches of more pages than fit one wave of those blocks (config 2: 1024 maps = 3.5 waves) launch TIER 1 first — 256 threads,
-// RUN_CAP_S runs, RUN_MAX_H_S rows: 30 KB, seven blocks per SM, the whole batch resident at once — and then TIER 2 = TIER 0 for the
-// pages TIER 1 passed on (fallback == 2: more runs or rows than it holds); every other block of TIER 2 exits at once.
-#define RUN_CAP_S 2048
-#define RUN_MAX_H_S 1280
-template <int TIER>
-__global__ void __launch_bounds__(TIER == 1 ? 256 : 1024, TIER == 1 ? 7 : 2) ccl_runs_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
+// (Measured and dropped in round 2: a first tier of 256-thread / 30-KB blocks so that a 1024-page batch is resident at once instead
+// of in 3.5 waves of these blocks — 0.54 ms against 0.41 ms on config 2: the kernel is bound by the work per page, not by the waves.)
+__global__ void __launch_bounds__(1024, 2) ccl_runs_kernel(const DetPostPage* __restrict__ pages, PageCounters* __restrict__ counters,
                                                             RunRec* __restrict__ runs, CompRec* __restrict__ comps, int2* __restrict__ rowtab,
                                                             int max_comps) {
-    constexpr int CAP = TIER == 1 ? RUN_CAP_S : RUN_CAP;
-    constexpr int MAXH = TIER == 1 ? RUN_MAX_H_S : RUN_MAX_H;
+    constexpr int CAP = RUN_CAP;
+    constexpr int MAXH = RUN_MAX_H;
     extern __shared__ int s_mem[];
     __shared__ int s_scan[32];
     __shared__ int s_flag;
@@ -1428,14 +1423,8 @@ __global__ void __launch_bounds__(TIER == 1 ? 256 : 1024, TIER == 1 ? 7 : 2) ccl
     const DetPostPage pg = pages[page];
     const int W = pg.w, H = pg.h;
     const int n = counters[page].n_runs;
-    if (TIER == 2) {
-        const int fb = counters[page].fallback;
-        __syncthreads();
-        if (fb != 2) return;
-        if (threadIdx.x == 0) counters[page].fallback = 0;
-    }
     if (n > CAP || H > MAXH) {
-        if (threadIdx.x == 0) counters[page].fallback = TIER == 1 ? 2 : 1;
+        if (threadIdx.x == 0) counters[page].fallback = 1;
         return;
     }
     int2* srt = reinterpret_cast<int2*>(s_mem);          // CAP x (key, x1), raster order
@@ -1521,7 +1510,17 @@ __global__ void __launch_bounds__(TIER == 1 ? 256 : 1024, TIER == 1 ? 7 : 2) ccl
     int tot_pairs, tot_heads;
     block_excl_scan(pairs, s_scan, &tot_pairs);
     block_excl_scan(heads, s_scan, &tot_heads);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) par[i] = sm_find(par, i);   // concurrent reads only ever move towards the root
+    {   // flatten: every run points at its root.  Roots are collected first and written after a barrier, so no plain store races with
+        // another thread's find (compute-sanitizer racecheck is clean; a concurrent store would be benign — every value on the way
+        // leads to the same root — but it is cheaper to keep the tool quiet than to explain 712 hazards)
+        constexpr int PER = RUN_CAP / 1024;
+        int roots[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { const int i = (int)threadIdx.x + q * (int)blockDim.x; roots[q] = i < n ? sm_find(par, i) : 0; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { const int i = (int)threadIdx.x + q * (int)blockDim.x; if (i < n) par[i] = roots[q]; }
+    }
     __syncthreads();
     // dense component ids in raster order of the root run
     const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -1746,13 +1745,7 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
     if (ctx->dp_run_path) {
         bool& attr_set = ctx->ccl_runs_attr_set;   // per context = per device: a process may drive several GPUs (retto_b200/cli.py --gpus N)
         const int smem = RUN_CAP * 12 + (RUN_MAX_H + 1) * 4;   // sorted runs (8 B) + parent per run, per-row index
-        const int smem_s = RUN_CAP_S * 12 + (RUN_MAX_H_S + 1) * 4;
-        if (!attr_set) {
-            RT_CUDA_OK(ctx, cudaFuncSetAttribute(ccl_runs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            RT_CUDA_OK(ctx, cudaFuncSetAttribute(ccl_runs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            RT_CUDA_OK(ctx, cudaFuncSetAttribute(ccl_runs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
-            attr_set = true;
-        }
+        if (!attr_set) { RT_CUDA_OK(ctx, cudaFuncSetAttribute(ccl_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
         RT_CUDA_OK(ctx, ctx->d_runs.ensure(sizeof(RunRec) * 3 * RUN_CAP * (size_t)n, st));
         RT_LAUNCH_BEGIN(ctx, "zero_counters_kernel");
         zero_counters_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, n);
@@ -1786,19 +1779,9 @@ retto_b200_status rt_det_post_begin(retto_b200_ctx* ctx, const retto_b200_det_po
 #undef BR3_ARGS
             RT_LAUNCH_CHECK(ctx);
         }
-        static const bool no_tiers = getenv("RETTO_B200_CCL_ONE_TIER") != nullptr;   // A/B
-        if (n > 148 * 2 && !no_tiers) {   // more pages than one wave of the big blocks
-            RT_LAUNCH_BEGIN(ctx, "ccl_runs_kernel");
-            ccl_runs_kernel<1><<<n, 256, smem_s, st>>>(d_pages, d_cnt, ctx->d_runs.as<RunRec>(), d_comps, d_rowtab, max_comps);
-            RT_LAUNCH_CHECK(ctx);
-            RT_LAUNCH_BEGIN(ctx, "ccl_runs_kernel");
-            ccl_runs_kernel<2><<<n, 1024, smem, st>>>(d_pages, d_cnt, ctx->d_runs.as<RunRec>(), d_comps, d_rowtab, max_comps);
-            RT_LAUNCH_CHECK(ctx);
-        } else {
-            RT_LAUNCH_BEGIN(ctx, "ccl_runs_kernel");
-            ccl_runs_kernel<0><<<n, 1024, smem, st>>>(d_pages, d_cnt, ctx->d_runs.as<RunRec>(), d_comps, d_rowtab, max_comps);
-            RT_LAUNCH_CHECK(ctx);
-        }
+        RT_LAUNCH_BEGIN(ctx, "ccl_runs_kernel");
+        ccl_runs_kernel<<<n, 1024, smem, st>>>(d_pages, d_cnt, ctx->d_runs.as<RunRec>(), d_comps, d_rowtab, max_comps);
+        RT_LAUNCH_CHECK(ctx);
         RT_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_dp.as<PageCounters>(), d_cnt, sizeof(PageCounters) * n, cudaMemcpyDeviceToHost, st));
         RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_dp, st));
         return RETTO_B200_OK;

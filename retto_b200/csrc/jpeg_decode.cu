@@ -1367,7 +1367,14 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     ctx->jpeg_status_dev = d_status;
     JB.n = n; JB.desc_bytes = desc_bytes; JB.head_bytes = head_bytes;
     RT_CUDA_OK(ctx, cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)n, st));
-    RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_jpeg_coef.p, 0, (size_t)blocks * 128, st));
+    // the coefficient planes are zeroed (the Huffman kernels store non-zero terms only) on the context's own stream when `st` is another
+    // one — run_pages: the copy stream, still busy with the files' uploads — so 1.3 GB of writes overlap the PCIe copies
+    if (st != ctx->stream) {
+        if (!ctx->ev_jpeg_zero) RT_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_jpeg_zero, cudaEventDisableTiming));
+        RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_jpeg_coef.p, 0, (size_t)blocks * 128, ctx->stream));
+        RT_CUDA_OK(ctx, cudaEventRecord(ctx->ev_jpeg_zero, ctx->stream));
+        RT_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_jpeg_zero, 0));
+    } else RT_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_jpeg_coef.p, 0, (size_t)blocks * 128, st));
     ctx->timer_stream = st;
     RT_LAUNCH_BEGIN(ctx, "jpeg_scan_kernel");
     jpeg_scan_kernel<<<n, 256, 0, st>>>(d_files, d_seg, d_status, ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len);

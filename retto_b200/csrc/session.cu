@@ -638,14 +638,7 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
             std::vector<JpegInfo>& infos = ctx->jpeg_infos;
             infos.resize(n_pages);
             size_t blob = 0;
-            for (int i = 0; i < n_pages; ++i) {
-                const retto_b200_status s = h_pages[i].rgb ? rt_jpeg_parse(h_pages[i].rgb, (size_t)h_pages[i].n_bytes, &infos[i]) : RETTO_B200_ERR_INVALID_ARG;
-                if (s != RETTO_B200_OK) {
-                    ctx->set_error("run_pages: page " + std::to_string(i) + (s == RETTO_B200_ERR_UNSUPPORTED ? ": not a baseline JPEG this decoder covers (decode it on the host and pass RGB)" : ": damaged or unknown image file"));
-                    return s;
-                }
-                blob += ((size_t)h_pages[i].n_bytes + 31) & ~size_t(15);
-            }
+            for (int i = 0; i < n_pages; ++i) blob += ((size_t)h_pages[i].n_bytes + 31) & ~size_t(15);
             const int unit = ctx->pipe_unit_pages > 0 ? ctx->pipe_unit_pages : env_int("RETTO_B200_ENC_UNIT_PAGES", 1 << 20, 1, 1 << 20);   // default: one unit
             if (!ctx->copy_stream) {
                 int lo = 0, hi = 0;
@@ -663,7 +656,14 @@ extern "C" retto_b200_status retto_b200_run_pages(retto_b200_ctx* ctx, const ret
             std::vector<const uint8_t*> d_files(n_pages);
             size_t off = 0;
             uint64_t enc_bytes = 0;
+            // header parse (host, ~1 us per file) and upload of file i in one loop: the copy engine works while the next headers are read
             for (int i = 0; i < n_pages; ++i) {
+                const retto_b200_status s = h_pages[i].rgb ? rt_jpeg_parse(h_pages[i].rgb, (size_t)h_pages[i].n_bytes, &infos[i]) : RETTO_B200_ERR_INVALID_ARG;
+                if (s != RETTO_B200_OK) {
+                    cudaStreamSynchronize(ctx->copy_stream);
+                    ctx->set_error("run_pages: page " + std::to_string(i) + (s == RETTO_B200_ERR_UNSUPPORTED ? ": not a baseline JPEG this decoder covers (decode it on the host and pass RGB)" : ": damaged or unknown image file"));
+                    return s;
+                }
                 uint8_t* d = ctx->d_jpeg_blob.as<uint8_t>() + off;
                 off += ((size_t)h_pages[i].n_bytes + 31) & ~size_t(15);
                 enc_bytes += h_pages[i].n_bytes;
