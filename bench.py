@@ -379,7 +379,7 @@ def algorithmic_bytes(name, info):
     if name.startswith("bitmap_runs"):
         return 9.0 * HW                       # prob read 4 + bitmap write 1 + label write 4
     if name.startswith("crop_rows"):
-        return 6.0 * info["crop_px"]          # 3 B read + 3 B written per crop pixel
+        return None                           # only the non-direct crops are written (the others are read by build_batches from the page): counted in crop_batch_unit
     if name.startswith("build_batches"):      # two launches per unit (cls + rec): both together
         return 2 * 3.0 * info["crop_px"] + 4.0 * (info["cls_floats"] + info["rec_floats"])
     if name.startswith("jpeg_idct"):

@@ -33,6 +33,22 @@ notes = {
     "jpeg_color": ("1.5 B samples + 3 B RGB per pixel", "issue-bound; 4:2:0: two rows per thread"),
     "jpeg_scan": ("2 × entropy bytes", "ordered block-wide compaction, one block per file"),
 }
+traffic = json.load(open(P("r02_traffic.json")))["kernels"] if os.path.exists(P("r02_traffic.json")) else {}
+
+
+def ncu_traffic(name, v):
+    """DRAM bytes per STEP from the committed ncu capture (per launch x launches per step) next to the algorithmic bytes"""
+    key = name.split("<")[0]
+    hit = next((t for k, t in traffic.items() if k.split("<")[0] == key or (key == "jpeg_color_kernel" and k.startswith("jpeg_color420"))), None)
+    if not hit:
+        return "—"
+    n = v.get("launches_per_step") or 1
+    per_step = hit["dram_bytes_per_launch"] * n
+    ab = v.get("algorithmic_bytes")          # per launch (mean over the step's launches)
+    pre = "≈ " if n > 1 else ""              # the capture holds ONE launch of the kernel; a step's launches differ in size
+    return ("%s%.2f / %.2f GB" % (pre, per_step / 1e9, ab * n / 1e9)) if ab else ("%s%.2f GB" % (pre, per_step / 1e9))
+
+
 rows = []
 for name, v in sorted(K.items(), key=lambda kv: -kv[1]["ms_per_step"]):
     if v["ms_per_step"] < 0.02:
@@ -40,10 +56,10 @@ for name, v in sorted(K.items(), key=lambda kv: -kv[1]["ms_per_step"]):
     note = next((n for k, n in notes.items() if name.startswith(k)), ("—", ""))
     gbs = v.get("gbs")
     tr = v.get("traffic_bytes_per_step") or v.get("traffic")
-    rows.append("| `%s` | %s | %.3f | %s | %s |" % (name, note[0], v["ms_per_step"], ("%.0f (%.2f)" % (gbs, gbs / peak)) if gbs else "—", note[1]))
+    rows.append("| `%s` | %s | %.3f | %s | %s | %s |" % (name, note[0], v["ms_per_step"], ("%.0f (%.2f)" % (gbs, gbs / peak)) if gbs else "—", ncu_traffic(name, v), note[1]))
 rest = sum(v["ms_per_step"] for v in K.values() if v["ms_per_step"] < 0.02)
-table = "| Kernel | Algorithmic bytes / unit | ms / 256 pages | GB/s (frac of measured peak) | Bound / note |\n|---|---|---|---|---|\n" + "\n".join(rows) + \
-        "\n| rest (kernels below 0.02 ms: sort / pack / scan / setup / `cls_post` / `zero`) | — | %.3f | — | launch-latency sized |" % rest
+table = "| Kernel | Algorithmic bytes / unit | ms / 256 pages | GB/s (frac of measured peak) | ncu DRAM traffic / algorithmic, per step | Bound / note |\n|---|---|---|---|---|---|\n" + "\n".join(rows) + \
+        "\n| rest (kernels below 0.02 ms: sort / pack / scan / setup / `cls_post` / `zero`) | — | %.3f | — | — | launch-latency sized |" % rest
 
 
 def unit(u):
