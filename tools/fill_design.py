@@ -103,12 +103,20 @@ for n in (2, 4, 8):
     if os.path.exists(P(fn)):
         d = load(fn)[-1]
         h2d.append("N = %d: %.0f GB/s" % (n, d["h2d"]["page_sized_copies"]["aggregate_gbs"]))
-scaling = ("Measured on one 8×B200 box, max over ranks (`profiles/r02_bench_n{2,4,8}.json`, taken BEFORE the last Huffman / IDCT / colour / score changes — "
-           "N = 1 was 52.8 k value / 19.4 k e2e on that tree):\n\n| N | value pages/s | e2e (JPEG) pages/s | e2e from raw RGB |\n|---|---|---|---|\n" + "\n".join(scal) +
-           "\n\nDevice-resident: 7.7× at N = 8. **e2e from JPEG files: 7.7× at N = 8** (round 1, from raw RGB: 3.5×) — with 0.18 MB per page on the wire the host's "
-           "H2D bandwidth is no longer the limit. From raw RGB the path still tracks the bare H2D ceiling of the box (" + "; ".join(h2d) +
-           " aggregate, `tools/measure_h2d.py`, `profiles/r02_h2d_ceiling_n*.json`: e.g. 38.3 k pages/s of 4.9-MB pages at N = 8 against 35.2 k measured). "
+n1 = b
+d8 = load("r02_bench_n8.json")[-1]
+mixed8 = load("r02_bench_mixed_n8.json")[-1] if os.path.exists(P("r02_bench_mixed_n8.json")) else None
+scaling = ("Measured on one 8×B200 box, max over ranks (`profiles/r02_bench_n8.json`: final tree; `r02_bench_n2.json` / `n4` were taken earlier in the round, "
+           "before the last Huffman / IDCT / colour / score changes, when N = 1 gave 52.8 k value / 19.4 k e2e):\n\n| N | value pages/s | e2e (JPEG) pages/s | e2e from raw RGB |\n|---|---|---|---|\n" +
+           "| 1 | %.1f k | %.1f k | %.1f k |\n" % (n1["value"] / 1e3, n1["e2e"]["value"] / 1e3, n1["e2e_variants"]["raw_rgb"]["value"] / 1e3) + "\n".join(scal) +
+           "\n\nDevice-resident: %.2f× at N = 8. **e2e from JPEG files: %.2f× at N = 8 (%.2f per GPU)** (round 1, from raw RGB: 3.5×) — with 0.18 MB per page on the wire the host's "
+           "H2D bandwidth is no longer the limit. From raw RGB the path still tracks the bare H2D ceiling of the box (" % (d8["value"] / n1["value"], d8["e2e"]["value"] / n1["e2e"]["value"], d8["e2e"]["value"] / n1["e2e"]["value"] / 8) + "; ".join(h2d) +
+           " aggregate, `tools/measure_h2d.py`, `profiles/r02_h2d_ceiling_n*.json`: the ceiling at N = 8 is 38 k pages/s of 4.9-MB pages). "
            "The box is a single-NUMA VM (`profiles/r02_topo_8gpu_box.txt`).")
+if mixed8 and mixed:
+    scaling += ("\nBASELINE.json configs[4] (`bench.py --workload mixed`, 2048 mixed-size pages per GPU per step, LPT-sharded per image): **%.1f k pages/s on 8 GPUs** against %.1f k on one (%.2f×); "
+                "end to end from JPEG files %.1f k against %.1f k (%.2f×) (`profiles/r02_bench_mixed_n8.json`, `…_n1.json`)." %
+                (mixed8["value"] / 1e3, mixed["value"] / 1e3, mixed8["value"] / mixed["value"], mixed8["e2e"]["value"] / 1e3, mixed["e2e"]["value"] / 1e3, mixed8["e2e"]["value"] / mixed["e2e"]["value"]))
 out = open(os.path.join(ROOT, "docs_src", "DESIGN.md.in")).read()
 rep = {
     "@@KERNEL_TABLE@@": table,
@@ -123,7 +131,7 @@ rep = {
     "@@DB_FRAC@@": "%.2f" % db5["frac_of_hbm_peak"],
     "@@DB_REST@@": "%.2f" % (db5["ms_per_step"] - next(v["ms_per_step"] for k, v in K.items() if k.startswith("bitmap_runs3"))),
     "@@CB_FRAC@@": "%.2f" % cb["frac_of_hbm_peak"],
-    "@@SCALE_E2E@@": "7.7× at N = 8 from JPEG files (0.97 per GPU)",
+    "@@SCALE_E2E@@": "%.2f× at N = 8 from JPEG files (%.2f per GPU)" % (d8["e2e"]["value"] / n1["e2e"]["value"], d8["e2e"]["value"] / n1["e2e"]["value"] / 8),
 }
 for k, v in rep.items():
     out = out.replace(k, v)
