@@ -106,13 +106,12 @@ for n in (2, 4, 8):
 n1 = b
 d8 = load("r02_bench_n8.json")[-1]
 mixed8 = load("r02_bench_mixed_n8.json")[-1] if os.path.exists(P("r02_bench_mixed_n8.json")) else None
-scaling = ("Measured on one 8×B200 box, max over ranks (`profiles/r02_bench_n8.json`: final tree; `r02_bench_n2.json` / `n4` were taken earlier in the round, "
-           "before the last Huffman / IDCT / colour / score changes, when N = 1 gave 52.8 k value / 19.4 k e2e):\n\n| N | value pages/s | e2e (JPEG) pages/s | e2e from raw RGB |\n|---|---|---|---|\n" +
+scaling = ("Measured on the final tree, max over ranks (`profiles/r02_bench_n{2,4,8}.json`; N = 8 on an 8-GPU box, N = 4 and 2 on a 4-GPU box, N = 1 on a 1-GPU box):\n\n| N | value pages/s | e2e (JPEG) pages/s | e2e from raw RGB |\n|---|---|---|---|\n" +
            "| 1 | %.1f k | %.1f k | %.1f k |\n" % (n1["value"] / 1e3, n1["e2e"]["value"] / 1e3, n1["e2e_variants"]["raw_rgb"]["value"] / 1e3) + "\n".join(scal) +
            "\n\nDevice-resident: %.2f× at N = 8. **e2e from JPEG files: %.2f× at N = 8 (%.2f per GPU)** (round 1, from raw RGB: 3.5×) — with 0.18 MB per page on the wire the host's "
            "H2D bandwidth is no longer the limit. From raw RGB the path still tracks the bare H2D ceiling of the box (" % (d8["value"] / n1["value"], d8["e2e"]["value"] / n1["e2e"]["value"], d8["e2e"]["value"] / n1["e2e"]["value"] / 8) + "; ".join(h2d) +
-           " aggregate, `tools/measure_h2d.py`, `profiles/r02_h2d_ceiling_n*.json`: the ceiling at N = 8 is 38 k pages/s of 4.9-MB pages). "
-           "The box is a single-NUMA VM (`profiles/r02_topo_8gpu_box.txt`).")
+           " aggregate, `tools/measure_h2d.py`, `profiles/r02_h2d_ceiling_n*.json`: the ceiling at N = 8 is 38 k pages/s of 4.9-MB pages; the 4-GPU box gives "
+           "every rank its full 54 GB/s, the 8-GPU box 23–36 GB/s per rank). The boxes are single-NUMA VMs (`profiles/r02_topo_8gpu_box.txt`).")
 if mixed8 and mixed:
     scaling += ("\nBASELINE.json configs[4] (`bench.py --workload mixed`, 2048 mixed-size pages per GPU per step, LPT-sharded per image): **%.1f k pages/s on 8 GPUs** against %.1f k on one (%.2f×); "
                 "end to end from JPEG files %.1f k against %.1f k (%.2f×) (`profiles/r02_bench_mixed_n8.json`, `…_n1.json`)." %
