@@ -359,7 +359,7 @@ __device__ __forceinline__ void jh_build_tables(const JpegDev& f, const JpegTabl
 __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* __restrict__ files, const int* __restrict__ block_file,
                                                               const int* __restrict__ block_first, const JpegTables* __restrict__ tables,
                                                               const unsigned* __restrict__ seg, const unsigned char* __restrict__ clean,
-                                                              const unsigned* __restrict__ clean_len, short* __restrict__ coef, int tiered) {
+                                                              const unsigned* __restrict__ clean_len, short* __restrict__ coef, int tiered, const unsigned* __restrict__ wend) {
     extern __shared__ __align__(16) unsigned char jh_smem[];
     HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);   // [2 * ci] = DC table of component ci, [2 * ci + 1] = its AC table (aliased when shared)
     __shared__ unsigned char s_zz[64];
@@ -395,10 +395,15 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
     const int j = j0 + s_order[rk];   // restart interval of this thread
     const unsigned char* base = clean + f.clean_off;             // 16-byte aligned
     const unsigned start = min(seg[f.seg_base + j], clen);
-    const unsigned* wp = reinterpret_cast<const unsigned*>(base + (start & ~3u));
-    unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
-    unsigned nxt = __ldg(wp + 2);
-    wp += 3;
+    // word index into the file's clean stream; wmax = the last readable word of the arena: the look-ahead index is clamped to it, so a
+    // truncated / damaged stream that runs on into whatever follows never reads past the allocation (32-bit min: a clamp of the
+    // 64-bit pointer cost the parse kernels a factor of two)
+    const unsigned* wb = reinterpret_cast<const unsigned*>(base);
+    const unsigned wmax = (unsigned)(wend - wb);
+    unsigned wi = start >> 2;
+    unsigned w0 = __byte_perm(__ldg(wb + wi), 0, 0x0123), w1 = __byte_perm(__ldg(wb + wi + 1), 0, 0x0123);
+    unsigned nxt = __ldg(wb + wi + 2);
+    wi += 3;
     unsigned o = 8u * (start & 3u);
     const long long n_mcu = (long long)f.mcux * f.mcuy;
     long long m = f.ri > 0 ? (long long)j * f.ri : 0;
@@ -458,8 +463,8 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
                 o -= 32u;
                 w0 = w1;
                 w1 = __byte_perm(nxt, 0, 0x0123);
-                nxt = __ldg(wp);
-                ++wp;
+                nxt = __ldg(wb + wi);
+                wi = min(wi + 1u, wmax);
             }
         };
         for (; m < m1; ++m) {
@@ -521,8 +526,8 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
             o -= 32u;
             w0 = w1;
             w1 = __byte_perm(nxt, 0, 0x0123);
-            nxt = __ldg(wp);     // unconditional (the clean arena is padded): a select here made the compiler consume the load at once
-            ++wp;
+            nxt = __ldg(wb + wi);     // unconditional: a select on the VALUE made the compiler consume the load at once; the INDEX is clamped instead
+            wi = min(wi + 1u, wmax);
         }
         if (k == 0) {
             int pv;
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
                                                         const JpegTables* __restrict__ tables, const unsigned* __restrict__ seg,
                                                         const unsigned char* __restrict__ clean, const unsigned* __restrict__ clean_len,
                                                         const JsSlot* __restrict__ slots, unsigned* __restrict__ bitmaps, unsigned short* __restrict__ counts,
-                                                        JsState* __restrict__ states, JsSync* __restrict__ syncs) {
+                                                        JsState* __restrict__ states, JsSync* __restrict__ syncs, const unsigned* __restrict__ wend) {
     extern __shared__ __align__(16) unsigned char jh_smem[];
     HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);
     __shared__ unsigned char s_zz[64];
@@ -677,10 +682,12 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
     // bit reader at absolute bit 8 * a0 + p of the file's clean stream (16-byte aligned base)
     const unsigned char* base = clean + f.clean_off;
     const unsigned long long abit = 8ull * a0 + p;
-    const unsigned* wp = reinterpret_cast<const unsigned*>(base) + (abit >> 5);
-    unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
-    unsigned nxt = __ldg(wp + 2);
-    wp += 3;
+    const unsigned* wb = reinterpret_cast<const unsigned*>(base);
+    const unsigned wmax = (unsigned)(wend - wb);
+    unsigned wi = (unsigned)(abit >> 5);
+    unsigned w0 = __byte_perm(__ldg(wb + wi), 0, 0x0123), w1 = __byte_perm(__ldg(wb + wi + 1), 0, 0x0123);
+    unsigned nxt = __ldg(wb + wi + 2);
+    wi += 3;
     unsigned o = (unsigned)(abit & 31ull);
     // PHASE 1: bitmap of this slot's MCU starts + running count per word
     unsigned* bm = bitmaps + (size_t)slot * JS_WORDS;
@@ -720,8 +727,8 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
             o -= 32u;
             w0 = w1;
             w1 = __byte_perm(nxt, 0, 0x0123);
-            nxt = __ldg(wp);
-            ++wp;
+            nxt = __ldg(wb + wi);
+            wi = min(wi + 1u, wmax);
         }
         if (kk == 0) kk = 1;
         else if (sz) kk += r + 1;
@@ -780,7 +787,7 @@ __global__ void __launch_bounds__(128) jpeg_huff_sub_kernel(const JpegDev* __res
                                                             const JpegTables* __restrict__ tables, const unsigned* __restrict__ seg,
                                                             const unsigned char* __restrict__ clean, const unsigned* __restrict__ clean_len,
                                                             const JsSlot* __restrict__ slots, const JsStart* __restrict__ starts, int4* __restrict__ preds,
-                                                            short* __restrict__ coef) {
+                                                            short* __restrict__ coef, const unsigned* __restrict__ wend) {
     extern __shared__ __align__(16) unsigned char jh_smem[];
     HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);
     __shared__ unsigned char s_zz[64];
@@ -798,10 +805,12 @@ __global__ void __launch_bounds__(128) jpeg_huff_sub_kernel(const JpegDev* __res
     const unsigned a0 = min(seg[f.seg_base + sl.j], clen);
     const unsigned char* base = clean + f.clean_off;
     const unsigned long long abit = 8ull * a0 + st.bit;
-    const unsigned* wp = reinterpret_cast<const unsigned*>(base) + (abit >> 5);
-    unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123), w1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
-    unsigned nxt = __ldg(wp + 2);
-    wp += 3;
+    const unsigned* wb = reinterpret_cast<const unsigned*>(base);
+    const unsigned wmax = (unsigned)(wend - wb);
+    unsigned wi = (unsigned)(abit >> 5);
+    unsigned w0 = __byte_perm(__ldg(wb + wi), 0, 0x0123), w1 = __byte_perm(__ldg(wb + wi + 1), 0, 0x0123);
+    unsigned nxt = __ldg(wb + wi + 2);
+    wi += 3;
     unsigned o = (unsigned)(abit & 31ull);
     long long m = (f.ri > 0 ? (long long)sl.j * f.ri : 0) + st.mcu;
     const long long m1 = m + st.n_mcu;
@@ -850,8 +859,8 @@ __global__ void __launch_bounds__(128) jpeg_huff_sub_kernel(const JpegDev* __res
             o -= 32u;
             w0 = w1;
             w1 = __byte_perm(nxt, 0, 0x0123);
-            nxt = __ldg(wp);
-            ++wp;
+            nxt = __ldg(wb + wi);
+            wi = min(wi + 1u, wmax);
         }
         if (k == 0) {
             int pv;
@@ -1366,6 +1375,8 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     int* d_status = reinterpret_cast<int*>(d_clean_len + n);
     ctx->jpeg_status_dev = d_status;
     JB.n = n; JB.desc_bytes = desc_bytes; JB.head_bytes = head_bytes;
+    // last readable word of the clean arena (clean_bytes + 64 bytes were ensured): the bit readers clamp their look-ahead pointer to it
+    const unsigned* d_wend = reinterpret_cast<const unsigned*>(ctx->d_jpeg_clean.as<unsigned char>()) + ((size_t)clean_bytes + 60) / 4;
     RT_CUDA_OK(ctx, cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)n, st));
     // the coefficient planes are zeroed (the Huffman kernels store non-zero terms only) on the context's own stream when `st` is another
     // one — run_pages: the copy stream, still busy with the files' uploads — so 1.3 GB of writes overlap the PCIe copies
@@ -1443,11 +1454,11 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_sync_kernel<1>");
-        jpeg_sync_kernel<1><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs);
+        jpeg_sync_kernel<1><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs, d_wend);
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_sync_kernel<2>");
-        jpeg_sync_kernel<2><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs);
+        jpeg_sync_kernel<2><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs, d_wend);
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_resolve_kernel");
@@ -1455,7 +1466,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_huff_sub_kernel");
-        jpeg_huff_sub_kernel<<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_starts, d_preds, ctx->d_jpeg_coef.as<short>());
+        jpeg_huff_sub_kernel<<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_starts, d_preds, ctx->d_jpeg_coef.as<short>(), d_wend);
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_dcfix_kernel");
@@ -1470,7 +1481,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         ctx->jpeg_huff_attr_set = true;
     }
     jpeg_huff_kernel<<<(unsigned)n_tblocks, tiered ? JH_T_THREADS : JH_THREADS, sizeof(HuffDev) * 6, st>>>(d_files, d_tb_file, d_tb_first, d_tab, d_seg,
-                                                                 ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len, ctx->d_jpeg_coef.as<short>(), tiered ? 1 : 0);
+                                                                 ctx->d_jpeg_clean.as<unsigned char>(), d_clean_len, ctx->d_jpeg_coef.as<short>(), tiered ? 1 : 0, d_wend);
     RT_LAUNCH_CHECK(ctx);
     ctx->timer_stream = nullptr;
     return RETTO_B200_OK;

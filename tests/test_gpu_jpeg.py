@@ -66,6 +66,37 @@ def test_decode_statuses(ctx):
     assert status[3] == _lib.ERR_DECODE and status[4] == _lib.ERR_DECODE
 
 
+def test_damaged_streams_terminate_and_do_not_hurt_their_neighbours(ctx):
+    """bytes flipped inside the entropy-coded data, files cut short (also as the LAST file of the batch: its bit readers run off the
+    end of the data) — with and without restart markers, i.e. through K-J2 and through the self-synchronising K-J2s: every decode
+    returns (status 0 or ERR_DECODE, never a hang or a fault), and the intact files of the same batch still decode bit-exactly"""
+    import torch
+    from retto_b200 import _lib
+    from tools.synth import gen_page
+    rng = np.random.default_rng(11)
+    img = gen_page(12, 480, 640, n_lines=(5, 9))[0]
+    goods = [_enc(img, quality=85), _enc(img, quality=85, restart_marker_rows=1), _enc(img, quality=85, subsampling=0, restart_marker_blocks=4)]
+    files = []
+    for g in goods:
+        sos = g.index(b"\xff\xda")
+        for k in range(6):
+            b = bytearray(g)
+            for p in rng.integers(sos + 20, len(b) - 2, size=int(rng.integers(1, 24))):
+                b[p] = int(rng.integers(0, 256))
+            files.append(bytes(b))
+        files.append(g[:sos + 14 + (len(g) - sos) // 3] + b"\xff\xd9")     # cut after a third of the scan, EOI appended
+        files.append(g[:len(g) * 2 // 3])                                       # cut without EOI
+    batch = [goods[0]] + files + [goods[1], goods[2][:len(goods[2]) // 2]]      # the last file of the batch is a truncated one
+    outs, status = ctx.decode_images(batch)
+    torch.cuda.synchronize()
+    assert all(s in (0, _lib.ERR_DECODE) for s in status), status
+    assert status[0] == 0 and np.array_equal(outs[0].cpu().numpy(), _pil(goods[0]))
+    assert status[-2] == 0 and np.array_equal(outs[-2].cpu().numpy(), _pil(goods[1]))
+    # the context is still healthy
+    outs2, status2 = ctx.decode_images(goods)
+    assert status2 == [0, 0, 0] and all(np.array_equal(o.cpu().numpy(), _pil(g)) for o, g in zip(outs2, goods))
+
+
 def _worker():
     from retto_b200.session import CallableWorker
     from tools.demo_worker import StatelessWorker
