@@ -85,3 +85,54 @@ def test_image_info_header_parse():
     assert image_info(b"garbage that is no image at all").status == _lib.ERR_DECODE
     data = _enc(img, quality=85)
     assert image_info(data[:200]).status == _lib.ERR_DECODE      # truncated inside the tables
+
+
+def test_image_info_survives_mutated_headers():
+    """the marker parser reads attacker-controlled lengths: 3000 mutations of valid files (flipped bytes / cut / grown inside the
+    header region, segment lengths forged) must each give a status — never a crash, never a read past the buffer (the buffers sit at
+    the END of an mmap'd page run followed by a PROT_NONE guard page, so an over-read segfaults the test process)"""
+    import ctypes as C
+    import mmap
+    from retto_b200 import _lib
+    img = _images()["page"]
+    seeds = [_enc(img, quality=85), _enc(img, quality=60, subsampling=0, restart_marker_blocks=3, optimize=True),
+             _enc(np.asarray(__import__("PIL.Image", fromlist=["Image"]).fromarray(img).convert("L")), quality=80)]
+    L = _lib.lib()
+    libc = C.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    PAGE = mmap.PAGESIZE
+    span = 64 * PAGE
+    mm = mmap.mmap(-1, span + PAGE)
+    base = C.addressof(C.c_char.from_buffer(mm))
+    assert libc.mprotect(base + span, PAGE, 0) == 0            # guard page behind the buffer
+    rng = np.random.default_rng(5)
+    seen = set()
+    info = _lib.ImageInfo()
+    for it in range(3000):
+        src = bytearray(seeds[it % len(seeds)])
+        hdr = src.index(b"\xff\xda") + 14
+        kind = it % 5
+        if kind == 0:
+            for p in rng.integers(2, hdr, size=int(rng.integers(1, 6))):
+                src[p] = int(rng.integers(0, 256))
+        elif kind == 1:
+            src = src[:int(rng.integers(1, hdr + 40))]
+        elif kind == 2:                                       # forge a segment length
+            pos = [i for i in range(2, hdr - 3) if src[i] == 0xFF and src[i + 1] in (0xDB, 0xC4, 0xC0, 0xDD, 0xDA, 0xE0)]
+            p = pos[int(rng.integers(0, len(pos)))]
+            src[p + 2], src[p + 3] = int(rng.integers(0, 256)), int(rng.integers(0, 256))
+        elif kind == 3:
+            p = int(rng.integers(2, hdr))
+            src[p:p] = bytes(rng.integers(0, 256, size=int(rng.integers(1, 9)), dtype=np.uint8))
+        else:
+            p = int(rng.integers(2, hdr))
+            del src[p:p + int(rng.integers(1, 9))]
+        n = min(len(src), span)
+        C.memmove(base + span - n, bytes(src[:n]), n)          # the file ends exactly at the guard page
+        st = L.retto_b200_image_info(C.c_void_p(base + span - n), n, C.byref(info))
+        assert st in (_lib.OK, _lib.ERR_DECODE, _lib.ERR_UNSUPPORTED), st
+        seen.add(st)
+        if st == _lib.OK:
+            assert 0 < info.h <= 65535 and 0 < info.w <= 65535 and info.components in (1, 3)
+    assert seen == {_lib.OK, _lib.ERR_DECODE, _lib.ERR_UNSUPPORTED}
+    libc.mprotect(base + span, PAGE, 3)
