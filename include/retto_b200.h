@@ -111,7 +111,9 @@ retto_b200_status retto_b200_d2h(retto_b200_ctx* ctx, void* h_dst, const void* d
 /* ImageHelper::new_from_raw_img_flow (image_helper.rs:34-44: image::load_from_memory(bytes).to_rgb8()) on the device, for the file
  * kind that matters at scale: baseline JPEG (Huffman, 8 bit, YCbCr 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 or grayscale, interleaved scan).
  * Pixels are bit-exact with libjpeg-turbo's default decode (integer "islow" IDCT, fancy up-sampling — what Pillow / OpenCV give).
- * Restart intervals (DRI) are decoded in parallel, one GPU thread each; a file without DRI is one interval.
+ * Restart intervals (DRI) are decoded in parallel, one GPU thread each; files with long intervals — above all files without DRI, which
+ * are ONE interval — are cut into 1-KB sub-sequences that are parsed self-synchronisingly, so they decode in
+ * parallel too.
  * Anything else (progressive / arithmetic / 12-bit JPEG, CMYK, PNG, ...) reports RETTO_B200_ERR_UNSUPPORTED — the caller decodes
  * those on the host and passes RGB; a damaged file reports RETTO_B200_ERR_DECODE.  There is no silent CPU fallback. */
 typedef struct retto_b200_encoded {

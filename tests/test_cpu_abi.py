@@ -178,3 +178,28 @@ def test_bind_host_to_gpu_is_harmless_without_nvml():
     assert isinstance(n, int) and n >= 0
     if n == 0:
         assert os.sched_getaffinity(0) == before
+
+
+def _build_c_demo(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_api_demo")
+    lib_dir = os.path.join(ROOT, "retto_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_api_demo.c"),
+           "-L" + lib_dir, "-lretto_b200", "-L/usr/local/cuda/lib64", "-Wl,-rpath-link,/usr/local/cuda/lib64", "-Wl,-rpath," + lib_dir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_c99_and_the_c_demo_links(tmp_path):
+    """the boundary is a C ABI: the header must compile as plain C99 (pedantic, warnings as errors), and a C program that uses nothing
+    but the header and the .so (examples/c_api_demo.c: no CUDA headers, no torch) must link; without a CUDA device it fails loudly"""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "retto_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = _build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode in (0, 2), (r.returncode, r.stdout, r.stderr)         # 2 = retto_b200_create found no CUDA device
+    if r.returncode == 2:
+        assert "retto_b200_create" in r.stderr

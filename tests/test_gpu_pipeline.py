@@ -484,3 +484,16 @@ def test_stage_api_orders_with_torch_current_stream(ctx):
             out = ctx.det_preprocess([g])[0]
             got = (out + b[0, 0] * 0).cpu().numpy()    # consumed by torch on the same stream, no sync in between
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_c_api_demo_runs(tmp_path):
+    """examples/c_api_demo.c — plain C99 over include/retto_b200.h + libretto_b200.so only — runs one page through
+    retto_b200_run_pages with a stand-in forward callback and finds its three lines"""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_cpu_abi import _build_c_demo
+    exe = _build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "c_api_demo ok" in r.stdout, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
+    assert "lines 3" in r.stdout and 'text "abcdef"' in r.stdout
