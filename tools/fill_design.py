@@ -117,7 +117,10 @@ if mixed8 and mixed:
                 "end to end from JPEG files %.1f k against %.1f k (%.2f×) (`profiles/r02_bench_mixed_n8.json`, `…_n1.json`)." %
                 (mixed8["value"] / 1e3, mixed["value"] / 1e3, mixed8["value"] / mixed["value"], mixed8["e2e"]["value"] / 1e3, mixed["e2e"]["value"] / 1e3, mixed8["e2e"]["value"] / mixed["e2e"]["value"]))
 out = open(os.path.join(ROOT, "docs_src", "DESIGN.md.in")).read()
+import re
+gt = re.findall(r"(\d+ passed(?:, \d+ skipped)?)", open(P("r02_gputests.log")).read())
 rep = {
+    "@@GPUTESTS@@": gt[-1] if gt else "see profiles/r02_gputests.log",
     "@@KERNEL_TABLE@@": table,
     "@@DB_UNIT@@": "on the 5·H·W bytes the path moves: " + unit(db5) + " (on SURVEY's 9·H·W, which counts a label plane the run-table CCL never writes: %.2f)" % db9["frac_of_hbm_peak"],
     "@@CB_UNIT@@": unit(cb),
