@@ -116,10 +116,35 @@ if mixed8 and mixed:
     scaling += ("\nBASELINE.json configs[4] (`bench.py --workload mixed`, 2048 mixed-size pages per GPU per step, LPT-sharded per image): **%.1f k pages/s on 8 GPUs** against %.1f k on one (%.2f×); "
                 "end to end from JPEG files %.1f k against %.1f k (%.2f×) (`profiles/r02_bench_mixed_n8.json`, `…_n1.json`)." %
                 (mixed8["value"] / 1e3, mixed["value"] / 1e3, mixed8["value"] / mixed["value"], mixed8["e2e"]["value"] / 1e3, mixed["e2e"]["value"] / 1e3, mixed8["e2e"]["value"] / mixed["e2e"]["value"]))
+def launch_list_check():
+    """per-launch durations of the committed ncu launch list next to the CUDA-event timings of the bench"""
+    import collections, csv
+    rows = list(csv.reader(open(P("r02_launches_bench.csv"))))
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    h = rows[hi]
+    kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+    tot, cnt = collections.Counter(), collections.Counter()
+    for r in rows[hi + 1:]:
+        if len(r) <= mv:
+            continue
+        name = r[kn].split("(")[0].replace("void ", "").split("<")[0]
+        tot[name] += float(r[mv].replace(",", "")) * {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0}.get(r[mu], 1e-6)
+        cnt[name] += 1
+    parts = []
+    for name, v in sorted(K.items(), key=lambda kv: -kv[1]["ms_per_step"])[:9]:
+        key = name.split("<")[0]
+        key = "jpeg_color420_kernel" if key == "jpeg_color_kernel" and "jpeg_color420_kernel" in tot else key
+        if cnt.get(key):
+            parts.append("`%s` %.3f / %.3f" % (name.split("<")[0], tot[key] / cnt[key], v["ms_per_launch"]))
+    return ("ncu launch list of `bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-variants --no-forward` (`profiles/r02_launches_bench.csv`; cold-cache, serialised): "
+            "ms per launch under ncu / by CUDA events in the bench — " + ", ".join(parts) + " — the two agree to a few per cent kernel by kernel, so the shares of the step do too.")
+
+
 out = open(os.path.join(ROOT, "docs_src", "DESIGN.md.in")).read()
 import re
 gt = re.findall(r"(\d+ passed(?:, \d+ skipped)?)", open(P("r02_gputests.log")).read())
 rep = {
+    "@@LAUNCHLIST@@": launch_list_check(),
     "@@GPUTESTS@@": gt[-1] if gt else "see profiles/r02_gputests.log",
     "@@KERNEL_TABLE@@": table,
     "@@DB_UNIT@@": "on the 5·H·W bytes the path moves: " + unit(db5) + " (on SURVEY's 9·H·W, which counts a label plane the run-table CCL never writes: %.2f)" % db9["frac_of_hbm_peak"],
