@@ -21,7 +21,7 @@ peak = b["roofline"]["peak"]
 notes = {
     "ctc_argmax": ("4·rows·C (26.5 KB/row)", "HBM; warp per row, 4×LDG.128 in flight per lane, head/tail peel for 4-B-aligned rows"),
     "det_pre_identity": ("3·H·W + 12·H'·W' = 24.6 MB/page", "HBM; 16 px/thread, smem LUT, smem-staged fully coalesced plane stores"),
-    "build_batches": ("Σ (3·w·h + 12·48·img_w)", "latency: first use of the prefetched source words; 41–45 % occupancy at 64 registers; direct lines read the page"),
+    "build_batches": ("Σ (3·w·h + 12·48·img_w)", "memory latency + issue: ncu (final tree) rec launch 0.58 ms = 3.65 TB/s of DRAM traffic, cls launch 0.36 ms = 3.0 TB/s; long-scoreboard stalls 5.5 per issue, 41 % of the stall samples on the first use of the three source words of a pixel pair, 65 % issue utilisation, 44 % of the warps resident at 63 registers; direct lines read the page"),
     "bitmap_runs3": ("5·H·W (4 read + 1 bitmap) = 8.2 MB/page", "issue (≈ 80 %): strip row = 8 ballot words, funnel-shift dilation / run detection on warp-uniform registers, FMNMX3.NAN probe"),
     "box_score": ("4·Σ polygon px (not in the 5·H·W unit)", "dependency chains: the reference's sequential f32 fold; 1 warp instruction per pixel + LDS.128 per 4; floor 0.155–0.165 ms"),
     "crop_rows": ("Σ 6·w·h of the NON-direct crops", "bicubic / border crops only (6 % of the crops of a text page); the direct ones are never written"),
