@@ -571,18 +571,21 @@ __global__ void __launch_bounds__(JH_T_THREADS) jpeg_huff_kernel(const JpegDev* 
 //                      region ALSO recorded: from that bit on the two parses are identical.  Slot 0's parse is the true one from
 //                      its first bit, so by induction the chain of matches gives every slot a true start
 //   jpeg_resolve_kernel one thread per interval walks that chain: true start bit and MCU index of every slot (a slot whose region the
-//                      true parse crossed without a common MCU start gets no MCUs; an interval whose chain breaks is decoded by its
-//                      first slot alone, from bit 0 — correct, just serial)
+//                      true parse crossed without a common MCU start takes over at the first MCU start the true parse made inside
+//                      its region — the look-ahead's check points; an interval whose chain breaks is decoded by its first slot
+//                      alone, from bit 0 — correct, just serial)
 //   jpeg_huff_sub_kernel the real decode (values, coefficient stores) of every slot's MCU range, DC predictors starting at 0
 //   jpeg_dcfix_kernel  adds to the DC terms of a slot's blocks the predictors carried in from the slots before it
 #define JS_SUB_BYTES 1024
 #define JS_SUB_BITS (JS_SUB_BYTES * 8)
 #define JS_WORDS (JS_SUB_BITS / 32)
 #define JS_MIN_MEAN_INTERVAL 4096   // a file goes through K-J2s when its mean restart interval is longer than this many bytes
+#define JS_CK 8                    // check points a slot keeps (one per region its look-ahead crosses without meeting that region's parse)
 #define JS_MAX_OVERLAP 4096     // regions a parse may cross while looking for a common MCU start before the interval falls back to one serial chain
 struct JsSlot { int j, k, nsub, pad; };                 // interval (index inside the file), sub-sequence, sub-sequences of the interval
 struct JsState { unsigned p; int b, kk, marked; };      // after pass 1: bit position (relative to the interval), block in MCU, zig-zag index, MCU starts recorded
 struct JsSync { int t; unsigned X; int C, pad; };       // written by slot s: first later slot t of the interval it met (-1: none, -2: gave up), at bit X; C = MCU starts of s's parse before X
+struct JsCk { unsigned bit; int count; };                // where a slot's look-ahead parse first starts an MCU inside a later region, and its MCU-start count before that bit
 struct JsStart { unsigned bit; int mcu, n_mcu, pad; };  // true start of a slot: bit (relative to the interval), first MCU (relative to the interval), MCUs to decode
 
 __global__ void __launch_bounds__(256) jpeg_sub_kernel(const JpegDev* __restrict__ files, const unsigned* __restrict__ seg, const unsigned* __restrict__ clean_len,
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
                                                         const JpegTables* __restrict__ tables, const unsigned* __restrict__ seg,
                                                         const unsigned char* __restrict__ clean, const unsigned* __restrict__ clean_len,
                                                         const JsSlot* __restrict__ slots, unsigned* __restrict__ bitmaps, unsigned short* __restrict__ counts,
-                                                        JsState* __restrict__ states, JsSync* __restrict__ syncs, const unsigned* __restrict__ wend) {
+                                                        JsState* __restrict__ states, JsSync* __restrict__ syncs, JsCk* __restrict__ cks, const unsigned* __restrict__ wend) {
     extern __shared__ __align__(16) unsigned char jh_smem[];
     HuffDev* s_tab = reinterpret_cast<HuffDev*>(jh_smem);
     __shared__ unsigned char s_zz[64];
@@ -695,6 +698,12 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
     int cw = 0, run = 0;
     unsigned cur = 0;
     int extra = 0;                       // PHASE 2: MCU starts of this parse at or after r1 that were not common
+    int last_ck_t = sl.k;                // PHASE 2: last region a check point was stored for
+    const int marked0 = PHASE == 2 ? states[slot].marked : 0;
+    if (PHASE == 2) {
+#pragma unroll
+        for (int i = 0; i < JS_CK; ++i) cks[(size_t)slot * JS_CK + i] = JsCk{0xFFFFFFFFu, 0};
+    }
     int found_t = -1;
     unsigned found_x = 0;
     bool gave_up = false;
@@ -711,6 +720,12 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
                 if (t - sl.k > JS_MAX_OVERLAP) { gave_up = true; break; }
                 const int d = (int)(p - (unsigned)t * JS_SUB_BITS);
                 if ((bitmaps[(size_t)(slot + (t - sl.k)) * JS_WORDS + (d >> 5)] >> (d & 31)) & 1u) { found_t = t; found_x = p; break; }
+                // region t's own parse is not in step here.  If THIS parse turns out to be the true one (jpeg_resolve_kernel), slot t can
+                // still take over at the first MCU start inside its region: remember that bit and the MCU count before it
+                if (t > last_ck_t) {
+                    if (t - sl.k - 1 < JS_CK) cks[(size_t)slot * JS_CK + (t - sl.k - 1)] = JsCk{p, marked0 + extra};
+                    last_ck_t = t;
+                }
                 ++extra;
             }
         } else if (PHASE == 1 && p >= r1) break;   // mid-MCU at the end of the region: pass 2 continues from this state
@@ -739,7 +754,7 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
         while (cw < JS_WORDS) { bm[cw] = cur; cnt[cw] = (unsigned short)run; run += __popc(cur); cur = 0; ++cw; }
         states[slot] = JsState{p, b, kk, run};
     } else {
-        syncs[slot] = JsSync{gave_up ? -2 : found_t, found_x, states[slot].marked + extra, 0};
+        syncs[slot] = JsSync{gave_up ? -2 : found_t, found_x, marked0 + extra, 0};
     }
 }
 
@@ -747,7 +762,7 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(const JpegDev* __restric
 __global__ void jpeg_resolve_kernel(const JpegDev* __restrict__ files, const int* __restrict__ seg_file, int total_seg, const int* __restrict__ sub_base,
                                     const int* __restrict__ isub,
                                     const JsSlot* __restrict__ slots, const unsigned* __restrict__ bitmaps, const unsigned short* __restrict__ counts,
-                                    const JsSync* __restrict__ syncs, JsStart* __restrict__ starts) {
+                                    const JsSync* __restrict__ syncs, const JsCk* __restrict__ cks, JsStart* __restrict__ starts) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;   // global interval index
     if (g >= total_seg) return;
     const int fi = seg_file[g];
@@ -767,13 +782,28 @@ __global__ void jpeg_resolve_kernel(const JpegDev* __restrict__ files, const int
     while (true) {
         const JsSync sy = syncs[first + s];
         if (sy.t == -2) { ok = false; break; }
-        if (sy.t < 0) { starts[first + s] = JsStart{X, m, max(total - m, 0), 0}; break; }
         const int d = (int)(X - (unsigned)s * JS_SUB_BITS);                  // X lies in slot s's own region (it was found in its bitmap)
         const int before = (int)counts[(size_t)(first + s) * JS_WORDS + (d >> 5)] + __popc(bitmaps[(size_t)(first + s) * JS_WORDS + (d >> 5)] & ((1u << (d & 31)) - 1u));
-        const int n = sy.C - before;
-        if (n < 0 || m + n > total || sy.t <= s || sy.t >= nsub) { ok = false; break; }
-        starts[first + s] = JsStart{X, m, n, 0};
-        m += n; s = sy.t; X = sy.X;
+        const bool last = sy.t < 0;
+        const int n_link = last ? max(total - m, 0) : sy.C - before;        // MCUs between X_s and the next common start (or the interval's end)
+        if (n_link < 0 || m + n_link > total || (!last && (sy.t <= s || sy.t >= nsub))) { ok = false; break; }
+        // slot s's parse is the true one from X_s on.  The slots whose regions it crossed without a common start take over at the first
+        // MCU start inside their region (the check points of slot s), so no slot decodes much more than one region
+        int owner = s, prev_cnt = before;
+        unsigned prev_bit = X;
+        const int u_end = last ? nsub : sy.t;
+        for (int u = s + 1; u < u_end && u - s - 1 < JS_CK; ++u) {
+            const JsCk ck = cks[(size_t)(first + s) * JS_CK + (u - s - 1)];
+            if (ck.bit == 0xFFFFFFFFu) continue;                           // no MCU start of the true parse inside region u: it stays with the owner
+            const int at = ck.count - before;                               // MCUs of this link before the check point
+            if (at < prev_cnt - before || at > n_link) { ok = false; break; }
+            starts[first + owner] = JsStart{prev_bit, m + (prev_cnt - before), ck.count - prev_cnt, 0};
+            owner = u; prev_bit = ck.bit; prev_cnt = ck.count;
+        }
+        if (!ok) break;
+        starts[first + owner] = JsStart{prev_bit, m + (prev_cnt - before), n_link - (prev_cnt - before), 0};
+        if (last) break;
+        m += n_link; s = sy.t; X = sy.X;
     }
     if (!ok) {   // the chain broke (or the data is damaged): the first slot decodes the whole interval
         for (int u = 1; u < nsub; ++u) starts[first + u] = JsStart{0u, 0, 0, 0};
@@ -1291,8 +1321,8 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
     size_t n_tblocks = 0;
     // Per file: long restart intervals (above all a file without restart markers = ONE interval) are cut into sub-sequences and decoded
     // through the self-synchronising parse (K-J2s); files with shorter intervals are parallel enough for K-J2.
-    // Measured (256 pages 1280x1280, q90, 4:2:0): no restart markers: K-J2 42.6 ms -> K-J2s 8.0 ms (parse 1.2 + look-ahead 2.0 + decode 2.7 +
-    // DC fix-up); one interval per MCU row (2.2 KB on average): tiered K-J2 2.84 ms, K-J2s 3.65 ms.
+    // Measured (256 pages 1280x1280, q90, 4:2:0): no restart markers: K-J2 42.6 ms -> K-J2s 6.0 ms (parse 1.4 + look-ahead 2.2 + resolve 0.3 +
+    // decode 1.7 + DC fix-up 0.3); one interval per MCU row (2.2 KB on average): tiered K-J2 2.84 ms, K-J2s 3.65 ms.
     static const bool no_sub = getenv("RETTO_B200_JPEG_NOSUB") != nullptr;       // A/B: never
     static const bool force_sub = getenv("RETTO_B200_JPEG_SUB") != nullptr;      // A/B / tests: every file
     std::vector<unsigned char> file_sub(n, 0);
@@ -1424,7 +1454,8 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         const size_t off_isub = tab_b;
         const size_t off_slots = (off_isub + (size_t)total_seg * 4 + 15) & ~size_t(15);
         const size_t off_states = off_slots + S * 16, off_syncs = off_states + S * 16, off_starts = off_syncs + S * 16, off_preds = off_starts + S * 16;
-        const size_t off_counts = off_preds + S * 16, off_bitmaps = off_counts + S * JS_WORDS * 2;
+        const size_t off_cks = off_preds + S * 16;
+        const size_t off_counts = off_cks + S * JS_CK * sizeof(JsCk), off_bitmaps = off_counts + S * JS_WORDS * 2;
         RT_CUDA_OK(ctx, ctx->d_jpeg_sub.ensure(off_bitmaps + S * JS_WORDS * 4, ctx->stream));
         char* db = ctx->d_jpeg_sub.as<char>();
         RT_CUDA_OK(ctx, cudaMemcpyAsync(db, ht, tab_b, cudaMemcpyHostToDevice, st));
@@ -1438,6 +1469,7 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         JsSync* d_syncs = reinterpret_cast<JsSync*>(db + off_syncs);
         JsStart* d_starts = reinterpret_cast<JsStart*>(db + off_starts);
         int4* d_preds = reinterpret_cast<int4*>(db + off_preds);
+        JsCk* d_cks = reinterpret_cast<JsCk*>(db + off_cks);
         unsigned short* d_counts = reinterpret_cast<unsigned short*>(db + off_counts);
         unsigned* d_bitmaps = reinterpret_cast<unsigned*>(db + off_bitmaps);
         const int smem = (int)(sizeof(HuffDev) * 6);
@@ -1454,15 +1486,15 @@ retto_b200_status rt_jpeg_entropy_enqueue(retto_b200_ctx* ctx, cudaStream_t st, 
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_sync_kernel<1>");
-        jpeg_sync_kernel<1><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs, d_wend);
+        jpeg_sync_kernel<1><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs, d_cks, d_wend);
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_sync_kernel<2>");
-        jpeg_sync_kernel<2><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs, d_wend);
+        jpeg_sync_kernel<2><<<(unsigned)nsb, 128, smem, st>>>(d_files, d_sb_file, d_sb_first, d_tab, d_seg, d_clean, d_clean_len, d_slots, d_bitmaps, d_counts, d_states, d_syncs, d_cks, d_wend);
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_resolve_kernel");
-        jpeg_resolve_kernel<<<(unsigned)((total_seg + 127) / 128), 128, 0, st>>>(d_files, d_seg_file, (int)total_seg, d_sub_base, d_isub, d_slots, d_bitmaps, d_counts, d_syncs, d_starts);
+        jpeg_resolve_kernel<<<(unsigned)((total_seg + 127) / 128), 128, 0, st>>>(d_files, d_seg_file, (int)total_seg, d_sub_base, d_isub, d_slots, d_bitmaps, d_counts, d_syncs, d_cks, d_starts);
         RT_LAUNCH_CHECK(ctx);
         ctx->timer_stream = st;
         RT_LAUNCH_BEGIN(ctx, "jpeg_huff_sub_kernel");
