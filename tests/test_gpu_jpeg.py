@@ -129,6 +129,31 @@ def test_session_on_file_bytes_equals_session_on_pixels(ctx, synth_dict):
             assert np.array_equal(x.det_result[i].boxes, ref["boxes"][i]) and x.rec_result[i].text == ref["rec"][i][0]
 
 
+def test_encoded_pages_on_two_lanes_equal_one_unit(ctx, synth_dict):
+    """file bytes in, units of 4 pages software-pipelined on two lanes (entropy phase once per call on the copy stream, pixel phase
+    per unit on the lane's stream) == the same call as one unit; files with and without restart markers in one batch"""
+    from retto_b200.session import RettoSession
+    from tools.synth import gen_page
+    ctx.dict_load(synth_dict)
+    pages = [gen_page(60 + i, 480 + 32 * (i % 3), 640 + 48 * (i % 4), n_lines=(4, 8))[0] for i in range(14)]
+    files = [_enc(p, quality=88, subsampling=2, **(dict(restart_marker_rows=1) if i % 2 else dict())) for i, p in enumerate(pages)]
+    w, cw = _worker()
+    sess = RettoSession(worker=cw, ctx=ctx)
+    try:
+        ctx.set_pipeline(1, 1 << 20)
+        one = sess.run_pages(files)
+        ctx.set_pipeline(2, 4)
+        piped = sess.run_pages(files)
+    finally:
+        ctx.set_pipeline(0, 0)
+    assert len(one) == len(piped) == 14 and sum(len(r.det_result) for r in one) > 14
+    for x, y in zip(one, piped):
+        assert x.status == y.status == 0 and len(x.det_result) == len(y.det_result)
+        for i in range(len(x.det_result)):
+            assert np.array_equal(x.det_result[i].boxes, y.det_result[i].boxes) and x.det_result[i].score == y.det_result[i].score
+            assert x.cls_result[i].label == y.cls_result[i].label and x.rec_result[i].text == y.rec_result[i].text
+
+
 def test_unsupported_file_fails_loudly(ctx, synth_dict):
     from retto_b200 import _lib
     from retto_b200._lib import RettoB200Error
