@@ -145,6 +145,7 @@ import re
 gt = re.findall(r"(\d+ passed(?:, \d+ skipped)?)", open(P("r02_gputests.log")).read())
 rep = {
     "@@LAUNCHLIST@@": launch_list_check(),
+    "@@RESIZE_FRAC@@": ", ".join("`%s` %.2f" % (k, v["frac_of_hbm_peak"]) for k, v in (mixed or {}).get("kernels", {}).items() if k.startswith(("det_pre_resize", "thumbnail")) and v.get("frac_of_hbm_peak")) or "n/a",
     "@@GPUTESTS@@": gt[-1] if gt else "see profiles/r02_gputests.log",
     "@@KERNEL_TABLE@@": table,
     "@@DB_UNIT@@": "on the 5·H·W bytes the path moves: " + unit(db5) + " (on SURVEY's 9·H·W, which counts a label plane the run-table CCL never writes: %.2f)" % db9["frac_of_hbm_peak"],
