@@ -203,3 +203,20 @@ def test_header_is_c99_and_the_c_demo_links(tmp_path):
     assert r.returncode in (0, 2), (r.returncode, r.stdout, r.stderr)         # 2 = retto_b200_create found no CUDA device
     if r.returncode == 2:
         assert "retto_b200_create" in r.stderr
+
+
+def test_design_md_is_the_generators_output(tmp_path):
+    """DESIGN.md is generated (tools/fill_design.py: docs_src/DESIGN.md.in + the evidence under profiles/): the committed file must be what
+    the generator writes from the committed evidence, so the numbers in the document cannot drift from the JSON they cite"""
+    import shutil
+    import subprocess
+    import sys
+    committed = open(os.path.join(ROOT, "DESIGN.md")).read()
+    backup = tmp_path / "DESIGN.md"
+    shutil.copy(os.path.join(ROOT, "DESIGN.md"), backup)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fill_design.py")], capture_output=True, text=True, cwd=ROOT)
+        assert r.returncode == 0, r.stderr
+        assert open(os.path.join(ROOT, "DESIGN.md")).read() == committed
+    finally:
+        shutil.copy(backup, os.path.join(ROOT, "DESIGN.md"))
